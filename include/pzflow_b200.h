@@ -1,0 +1,196 @@
+/*
+ * pzflow_b200 -- C-ABI of the B200-native evaluator for pzflow's
+ * neural-spline-flow hot path (Flow.log_prob / Flow.sample / Flow.posterior).
+ *
+ * pzflow itself has no FFI: its extension seam is the Bijector protocol
+ * (pzflow/bijectors.py:16-118) -- InitFunction(rng, input_dim) ->
+ * (params, ForwardFunction, InverseFunction), with
+ * Forward/InverseFunction(params, inputs[N,D], conditions=[N,C]) ->
+ * (outputs[N,D], log_det[N]) -- which Flow binds as _forward/_inverse
+ * (pzflow/flow.py:285-288, 185-188) and funnels through
+ * Flow._log_prob(params, inputs, conditions) (pzflow/flow.py:397-407).
+ * The entry points below are what a ctypes / XLA-FFI binding for that seam
+ * would bind; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer to C-contiguous row-major float32
+ *    (rows = samples, exactly the reference's [N, D] layout) unless the
+ *    parameter is documented as host memory;
+ *  - the caller owns every buffer; a plan owns only its packed weight copy;
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - every function returns 0 on success and a negative pzb_status otherwise,
+ *    nothing throws across the ABI; pzb_last_error() describes the last
+ *    failure on the calling thread;
+ *  - a plan is immutable after creation and may be launched concurrently from
+ *    several host threads / streams; one plan per device.
+ */
+#ifndef PZFLOW_B200_H
+#define PZFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PZB_ABI_VERSION 1
+
+typedef enum {
+  PZB_OK = 0,
+  PZB_ERR_INVALID = -1,      /* bad argument (maps to ValueError in the Python mirror)  */
+  PZB_ERR_UNSUPPORTED = -2,  /* stage / shape outside the hot path                       */
+  PZB_ERR_CUDA = -3,         /* CUDA runtime error, see pzb_last_error()                 */
+  PZB_ERR_NO_DEVICE = -4     /* no CUDA device: there is no CPU fallback                 */
+} pzb_status;
+
+/* Bijector stages of the hot path (a flattened Bijector_Info, nested Chains
+ * inlined: pzflow/bijectors.py:12-13, pzflow/utils.py:11-19). */
+typedef enum {
+  PZB_STAGE_SHIFT_BOUNDS = 1,     /* pzflow/bijectors.py:717-777 */
+  PZB_STAGE_STANDARD_SCALER = 2,  /* pzflow/bijectors.py:817-861 */
+  PZB_STAGE_ROLL = 3,             /* pzflow/bijectors.py:559-598 */
+  PZB_STAGE_NSC = 4,              /* pzflow/bijectors.py:375-522 (NeuralSplineCoupling) */
+  /* Chain nesting markers (pzflow/bijectors.py:155-160): every Chain sums its
+   * stages' log-determinants from zeros before its parent adds the total, so
+   * the flattening keeps the brackets to reproduce the fp32 summation order. */
+  PZB_STAGE_CHAIN_BEGIN = 5,
+  PZB_STAGE_CHAIN_END = 6
+} pzb_stage_kind;
+
+/* Latent distributions of the hot path. */
+typedef enum {
+  PZB_LATENT_UNIFORM = 1,    /* pzflow/distributions.py:395-470 */
+  PZB_LATENT_CENTBETA13 = 2  /* pzflow/distributions.py:137-229 */
+} pzb_latent_kind;
+
+/* Conditioner evaluation engines. */
+typedef enum {
+  PZB_ENGINE_AUTO = 0,  /* tensor-core engine when the plan's shapes allow it, else SIMT */
+  PZB_ENGINE_SIMT = 1,  /* fp32 FFMA conditioner (any shape)                              */
+  PZB_ENGINE_TC = 2     /* tcgen05 conditioner, fp16x2 split-accumulate in fp32 TMEM      */
+} pzb_engine;
+
+typedef struct {
+  int32_t kind; /* pzb_stage_kind */
+
+  /* ROLL: jnp.roll(x, shift, axis=-1). */
+  int32_t shift;
+
+  /* SHIFT_BOUNDS: vec_a = min, vec_b = max, n_vec = 1 or D, B = output half-range.
+   * STANDARD_SCALER: vec_a = means, vec_b = stds, n_vec = D.  HOST pointers. */
+  const float *vec_a;
+  const float *vec_b;
+  int32_t n_vec;
+
+  /* NSC: the Bijector_Info argument tuple
+   * (K, B, hidden_layers, hidden_dim, transformed_dim, n_conditions, periodic);
+   * transformed_dim < 0 means "None" (lower = D - D/2). B is shared with SHIFT_BOUNDS. */
+  float B;
+  int32_t K;
+  int32_t hidden_layers;
+  int32_t hidden_dim;
+  int32_t transformed_dim;
+  int32_t n_conditions;
+  int32_t periodic;
+  /* NSC parameters in stax order: 2*(hidden_layers+1) HOST pointers
+   * W0, b0, W1, b1, ... with W[in, out] row-major float32
+   * (pzflow/utils.py:45-48; stax Dense = x @ W + b). */
+  const float *const *weights;
+} pzb_stage_desc;
+
+typedef struct pzb_plan pzb_plan;
+
+/* ABI version of the loaded library (== PZB_ABI_VERSION). */
+int pzb_abi_version(void);
+
+/* Last error message of the calling thread (never NULL). */
+const char *pzb_last_error(void);
+
+/* Number of visible CUDA devices (0 when there is none; never an error). */
+int pzb_device_count(void);
+
+/* Compile a flattened bijector chain + latent into a device plan.
+ * Replaces: Flow.set_bijector / the load path's build_bijector_from_info +
+ * init_fun (pzflow/flow.py:183-189, 285-294) as the owner of the evaluation
+ * functions.  Weights are copied and packed once; rebuild the plan when
+ * flow._params changes identity.  `device` is the CUDA ordinal. */
+int pzb_plan_create(const pzb_stage_desc *stages, int32_t n_stages, int32_t input_dim,
+                    int32_t latent_kind, float latent_B, int32_t device, pzb_plan **out);
+
+void pzb_plan_destroy(pzb_plan *plan);
+
+/* Introspection used by the host mirror, the tests and bench.py. */
+int pzb_plan_input_dim(const pzb_plan *plan);
+int pzb_plan_n_conditions(const pzb_plan *plan);
+/* total number of spline-transformed columns over all NSC stages
+ * (the row width of the optional `bins` debug output). */
+int pzb_plan_n_spline_dims(const pzb_plan *plan);
+/* conditioner MLP FLOPs per row (SURVEY.md §8d formula), for rooflines. */
+double pzb_plan_flops_per_row(const pzb_plan *plan);
+/* 1 if the tensor-core engine supports this plan's shapes. */
+int pzb_plan_tc_supported(const pzb_plan *plan);
+/* select the conditioner engine for subsequent launches (default AUTO). */
+int pzb_plan_set_engine(pzb_plan *plan, int32_t engine);
+/* engine a launch of this plan uses right now (PZB_ENGINE_SIMT or _TC). */
+int pzb_plan_engine(const pzb_plan *plan);
+/* how many kernels of this library were launched by this process so far. */
+int64_t pzb_launch_count(void);
+
+/* Flow._log_prob (pzflow/flow.py:397-407): u, ld = forward(x, cond);
+ * out = latent.log_prob(u) + ld; NaN -> zero probability.
+ * X [N, D]; cond [N, C] already standard-scaled (pzflow/flow.py:334-336) or
+ * NULL when C == 0; out [N].  bins (optional, may be NULL) receives the
+ * spline bin index of every transformed column, int32 [N, n_spline_dims],
+ * NSC stages in chain order. */
+int pzb_log_prob(const pzb_plan *plan, const float *X, const float *cond, int64_t N,
+                 float *out, int32_t *bins, void *stream);
+
+/* Bijector ForwardFunction of the whole chain (pzflow/bijectors.py:162-164):
+ * U [N, D], log_det [N]. */
+int pzb_forward(const pzb_plan *plan, const float *X, const float *cond, int64_t N,
+                float *U, float *log_det, int32_t *bins, void *stream);
+
+/* Bijector InverseFunction of the whole chain (pzflow/bijectors.py:166-170),
+ * the map Flow.sample applies to latent draws (pzflow/flow.py:795):
+ * X [N, D], log_det [N] (may be NULL: Flow.sample discards it). */
+int pzb_inverse(const pzb_plan *plan, const float *U, const float *cond, int64_t N,
+                float *X, float *log_det, int32_t *bins, void *stream);
+
+/* Flow.posterior main loop (pzflow/flow.py:666-738, err_samples=None,
+ * marg_rules=None): rest [Ng, D-1] = data columns with `col_idx` removed,
+ * cond [Ng, C] or NULL, grid [G]; pdfs [Ng, G] = exp(log_prob) on the
+ * galaxy-major / grid-minor expansion, never materialised; then, per galaxy,
+ * pdfs /= trapezoid(pdfs, grid) if normalize, NaN -> 0 if nan_to_zero. */
+int pzb_posterior(const pzb_plan *plan, const float *rest, const float *cond, int64_t Ng,
+                  int32_t col_idx, const float *grid, int32_t G, int32_t normalize,
+                  int32_t nan_to_zero, float *pdfs, void *stream);
+
+/* FlowEnsemble.log_prob reduction (pzflow/flowEnsemble.py:236-243):
+ * lp [n_flows, N] (one pzb_log_prob result per row) -> out [N] =
+ * log(mean_f(exp(lp[f, i]))), the naive form the reference uses. */
+int pzb_ensemble_logmeanexp(const float *lp, int32_t n_flows, int64_t N, float *out,
+                            void *stream);
+
+/* FlowEnsemble.posterior reduction (pzflow/flowEnsemble.py:346-351):
+ * pdfs [n_flows, Ng, G] un-normalised -> out [Ng, G] = mean over flows, then
+ * trapezoid-normalised per galaxy if normalize.  (NaNs were already zeroed
+ * per flow, as in the reference.) */
+int pzb_ensemble_posterior_mean(const float *pdfs, int32_t n_flows, int64_t Ng, int32_t G,
+                                const float *grid, int32_t normalize, float *out,
+                                void *stream);
+
+/* Per-galaxy trapezoid normalisation + NaN->0 of pdfs [Ng, G] in place
+ * (pzflow/flow.py:732-737); also used for returnEnsemble=True
+ * (pzflow/flowEnsemble.py:335-344). */
+int pzb_normalize_pdfs(float *pdfs, int64_t Ng, int32_t G, const float *grid,
+                       int32_t normalize, int32_t nan_to_zero, void *stream);
+
+/* Latent draws for Flow.sample speed runs (pzflow/distributions.py:443-470):
+ * U [N, D] ~ Uniform(-B, B) from a counter-based Philox stream.  This is NOT
+ * jax.random's threefry stream; sample parity is defined on the map u -> x. */
+int pzb_sample_uniform(float *U, int64_t N, int32_t D, float B, uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PZFLOW_B200_H */

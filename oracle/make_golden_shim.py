@@ -1,0 +1,196 @@
+"""Golden vectors from the reference's own code over oracle/jax_shim (build container only).
+
+Each tests/golden/ref_shim_*.npz holds inputs, the Bijector_Info / params the
+reference built, and what the reference's functions returned.  The oracle and
+the CUDA path are then checked against these files (tests/test_oracle.py,
+tests/test_gpu_parity.py).  See oracle/jax_shim/__init__.py for what this pins.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import pandas as pd
+
+from . import fixtures as F
+from . import jax_shim
+
+GOLDEN = F.GOLDEN
+
+
+def _save(name, store):
+    path = os.path.join(GOLDEN, f"ref_shim_{name}.npz")
+    np.savez_compressed(path, **store)
+    print("wrote", os.path.basename(path), f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def _np(x):
+    return np.asarray(x)
+
+
+def case_example_flow(pzflow):
+    """Shipped 7-D flow through Flow.log_prob / _forward / _inverse / posterior (tests/test_examples.py:31-40)."""
+    from pzflow import examples
+    import jax.numpy as jnp
+    flow = examples.get_example_flow()
+    X = F.galaxy_rows(384, seed=7)
+    # edge rows: far out of bounds, exactly on the ShiftBounds box, NaN
+    mins, maxs = _np(flow._bijector_info[1][0][1][0]), _np(flow._bijector_info[1][0][1][1])
+    X[0] = maxs
+    X[1] = mins
+    X[2] = maxs + 3 * (maxs - mins)
+    X[3, 4] = np.nan
+    X[4] = 0.5 * (mins + maxs)
+    df = pd.DataFrame(X, columns=flow.data_columns)
+    store = dict(X=X)
+    store["log_prob"] = _np(flow.log_prob(df))
+    cond = jnp.zeros((X.shape[0], 1))
+    u, ld = flow._forward(flow._params[1], jnp.array(X), conditions=cond)
+    store["forward_u"], store["forward_ld"] = _np(u), _np(ld)
+    U = np.random.default_rng(11).uniform(-5, 5, size=(384, 7)).astype(np.float32)
+    U[0] = 5.0
+    U[1] = -5.0
+    U[2] = 7.5
+    x, ldi = flow._inverse(flow._params[1], jnp.array(U), conditions=cond)
+    store["U"], store["inverse_x"], store["inverse_ld"] = U, _np(x), _np(ldi)
+    grid = np.linspace(0.0, 2.3, 60).astype(np.float32)
+    store["grid"] = grid
+    store["posterior"] = _np(flow.posterior(df.iloc[:24], column="redshift", grid=jnp.array(grid)))
+    store["posterior_batched"] = _np(flow.posterior(df.iloc[:24], column="redshift", grid=jnp.array(grid), batch_size=7))
+    store["posterior_unnorm"] = _np(flow.posterior(df.iloc[:24], column="redshift", grid=jnp.array(grid),
+                                                   normalize=False, nan_to_zero=False))
+    grid_r = np.linspace(14.0, 30.0, 33).astype(np.float32)
+    store["grid_r"] = grid_r
+    store["posterior_r"] = _np(flow.posterior(df.iloc[:24], column="r", grid=jnp.array(grid_r)))
+    # the two samples printed at docs/tutorials/marginalization.ipynb:133-135 (real-JAX outputs)
+    Xs = np.array([[0.386102, 28.406404, 27.508736, 26.419685, 26.196583, 25.901255, 25.889046],
+                   [2.118688, 28.220659, 27.798203, 27.371502, 27.211376, 26.869678, 26.502558]], np.float32)
+    store["nb_X"] = Xs
+    store["nb_log_prob"] = _np(flow.log_prob(pd.DataFrame(Xs, columns=flow.data_columns)))
+    _save("example_flow", store)
+
+
+def case_bijectors(pzflow):
+    """The hot-path rows of tests/test_bijectors.py:16-51 on its fixed 3x7 input."""
+    from pzflow import bijectors as B
+    import jax.numpy as jnp
+    from jax import random
+    x = np.array([[0.2, 0.1, -0.3, 0.5, 0.1, -0.4, -0.3],
+                  [0.6, 0.5, 0.2, 0.2, -0.4, -0.1, 0.7],
+                  [0.9, 0.2, -0.3, 0.3, 0.4, -0.4, -0.1]], np.float32)
+    cases = [
+        ("standard_scaler", B.StandardScaler, (jnp.linspace(-1, 1, 7), jnp.linspace(1, 8, 7)), np.zeros((3, 1))),
+        ("nsc_default", B.NeuralSplineCoupling, (), np.zeros((3, 1))),
+        ("nsc_cond", B.NeuralSplineCoupling, (16, 3, 2, 128, 3), np.arange(9).reshape(3, 3)),
+        ("rsc2", B.RollingSplineCoupling, (2,), np.zeros((3, 1))),
+        ("rsc_periodic", B.RollingSplineCoupling, (2, 1, 16, 3, 2, 128, None, 0, True), np.zeros((3, 1))),
+        ("shift_scalar", B.ShiftBounds, (-0.5, 0.9, 5), np.zeros((3, 1))),
+        ("shift_vector", B.ShiftBounds, (-1 * jnp.ones(7), 1.1 * jnp.ones(7), 3), np.zeros((3, 1))),
+        ("roll2", B.Roll, (2,), np.zeros((3, 1))),
+        ("chain_mixed", B.Chain, (B.ShiftBounds(-1 * jnp.ones(7), 1.1 * jnp.ones(7), 3), B.Roll(-1),
+                                  B.RollingSplineCoupling(3, 2, 8, 3, 1, 32), B.StandardScaler(jnp.linspace(-1, 1, 7), jnp.linspace(1, 8, 7))),
+         np.zeros((3, 1))),
+    ]
+    store = dict(x=x, names=np.array([c[0] for c in cases]))
+    for name, bij, args, cond in cases:
+        if name == "nsc_cond":
+            # conditional test row uses n_conditions = 3 (tests/test_bijectors.py:33-37 passes it as 6th arg
+            # implicitly 0 -> conditions ignored); exercise the real conditional path here
+            args = (16, 3, 2, 128, 3, 3)
+        init_fun, info = bij(*args)
+        params, fwd, inv = init_fun(random.PRNGKey(0), 7)
+        # widen the conditioner outputs so the splines are far from identity
+        cond = np.asarray(cond, dtype=np.float32)
+        y, ld = fwd(params, jnp.array(x), conditions=jnp.array(cond))
+        xi, ldi = inv(params, y, conditions=jnp.array(cond))
+        xi2, ldi2 = inv(params, jnp.array(x), conditions=jnp.array(cond))
+        F.pack_tree(f"{name}_info", info, store)
+        F.pack_tree(f"{name}_params", params, store)
+        store[f"{name}_cond"] = cond
+        store[f"{name}_fwd"], store[f"{name}_fwd_ld"] = _np(y), _np(ld)
+        store[f"{name}_inv_of_fwd"], store[f"{name}_inv_of_fwd_ld"] = _np(xi), _np(ldi)
+        store[f"{name}_inv"], store[f"{name}_inv_ld"] = _np(xi2), _np(ldi2)
+    _save("bijectors", store)
+
+
+def _boost(params, rng, scale=3.0):
+    """Scale the last Dense layer of every conditioner so splines are strongly non-identity."""
+    if isinstance(params, list) and len(params) and isinstance(params[0], tuple) and len(params[0]) == 2 \
+            and getattr(params[0][0], "ndim", 0) == 2:
+        W, b = params[-1]
+        params[-1] = (np.asarray(W) * np.float32(scale), rng.normal(0, 0.5, size=np.asarray(b).shape).astype(np.float32))
+        return params
+    if isinstance(params, (list, tuple)):
+        out = [_boost(p, rng, scale) for p in params]
+        return out if isinstance(params, list) else tuple(out)
+    return params
+
+
+def case_default_flows(pzflow):
+    """Default bijector (flow.py:296-322): 2-D two-moons / CentBeta13 and a conditional 3-D + 2 flow, plus an ensemble."""
+    from pzflow import Flow, FlowEnsemble
+    from pzflow.examples import get_twomoons_data
+    import jax.numpy as jnp
+    rng = np.random.default_rng(5)
+    store = {}
+    # ---- C1: two moons ----
+    data = get_twomoons_data().iloc[:512].reset_index(drop=True)
+    flow = Flow(data_columns=("x", "y"))
+    flow._set_default_bijector(get_twomoons_data(), seed=0)
+    flow._params = (flow._params[0], _boost(flow._params[1], rng))
+    X = data[["x", "y"]].to_numpy().astype(np.float32)
+    store["c1_X"] = X
+    F.pack_tree("c1_info", flow._bijector_info, store)
+    F.pack_tree("c1_params", flow._params[1], store)
+    store["c1_log_prob"] = _np(flow.log_prob(data))
+    grid = np.linspace(-1.5, 2.5, 41).astype(np.float32)
+    store["c1_grid"] = grid
+    store["c1_posterior_x"] = _np(flow.posterior(data.iloc[:32], column="x", grid=jnp.array(grid)))
+    store["c1_posterior_y"] = _np(flow.posterior(data.iloc[:32], column="y", grid=jnp.array(grid), normalize=False))
+    u = flow.latent.sample(flow._params[0], 256, 3)
+    xs = flow._inverse(flow._params[1], u, conditions=jnp.zeros((256, 1)))[0]
+    store["c1_sample_u"], store["c1_sample_x"] = _np(u), _np(xs)
+
+    # ---- conditional flow + ensemble ----
+    n = 200
+    df = pd.DataFrame({"a": rng.normal(0, 1, n), "b": rng.uniform(-2, 3, n), "c": rng.normal(1, 2, n),
+                       "p": rng.normal(5, 2, n), "q": rng.uniform(0, 1, n)})
+    ens = FlowEnsemble(data_columns=("a", "b", "c"), conditional_columns=("p", "q"), N=3)
+    for i, fl in enumerate(ens._ensemble.values()):
+        fl._set_default_bijector(df, seed=i)
+        fl._params = (fl._params[0], _boost(fl._params[1], rng, 2.0))
+        fl._condition_means = jnp.array(df[["p", "q"]].to_numpy().mean(axis=0))
+        fl._condition_stds = jnp.array(df[["p", "q"]].to_numpy().std(axis=0))
+    store["ens_df"] = df.to_numpy().astype(np.float64)
+    store["ens_columns"] = np.array(list(df.columns))
+    f0 = ens._ensemble["Flow 0"]
+    store["ens_cond_means"], store["ens_cond_stds"] = _np(f0._condition_means), _np(f0._condition_stds)
+    for i, fl in enumerate(ens._ensemble.values()):
+        F.pack_tree(f"ens{i}_info", fl._bijector_info, store)
+        F.pack_tree(f"ens{i}_params", fl._params[1], store)
+    store["ens_flow0_log_prob"] = _np(f0.log_prob(df))
+    store["ens_log_prob"] = _np(ens.log_prob(df))
+    store["ens_log_prob_all"] = _np(ens.log_prob(df, returnEnsemble=True))
+    g = np.linspace(-3, 3, 25).astype(np.float32)
+    store["ens_grid"] = g
+    store["ens_posterior"] = _np(ens.posterior(df.iloc[:20], column="a", grid=jnp.array(g)))
+    store["ens_posterior_all"] = _np(ens.posterior(df.iloc[:20], column="a", grid=jnp.array(g), returnEnsemble=True))
+    store["ens_flow0_posterior_b"] = _np(f0.posterior(df.iloc[:20], column="b", grid=jnp.array(g)))
+    # conditional sampling map: u -> x with 2 copies of each condition row (flow.py:787-795)
+    cdf = df.iloc[:10]
+    conds = jnp.repeat(f0._get_conditions(cdf), 2, axis=0)
+    u = f0.latent.sample(f0._params[0], 20, 1)
+    store["ens_sample_u"], store["ens_sample_cond"] = _np(u), _np(conds)
+    store["ens_sample_x"] = _np(f0._inverse(f0._params[1], u, conditions=conds)[0])
+    _save("default_flows", store)
+
+
+def main():
+    pzflow = jax_shim.install()
+    case_example_flow(pzflow)
+    case_bijectors(pzflow)
+    case_default_flows(pzflow)
+
+
+if __name__ == "__main__":
+    main()

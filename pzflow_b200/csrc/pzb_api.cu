@@ -1,0 +1,672 @@
+// C-ABI of libpzflow_b200.so (see include/pzflow_b200.h): plan compilation
+// (Bijector_Info flattening -> packed device plan) and the launch entry points.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pzflow_b200.h"
+#include "pzb_common.cuh"
+
+namespace pzb {
+cudaError_t launch_simt(const PlanDev* d_plan, const LaunchArgs& args, int D, int C, int Lmax,
+                        int act_rows, bool pingpong, int num_sms, cudaStream_t stream);
+bool tc_plan_supported(const PlanDev& hp);
+size_t tc_pack_bytes(const NscDev& st);
+void tc_pack_stage(const NscDev& st, const float* const* weights, void* dst);
+cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms,
+                      void* workspace, cudaStream_t stream);
+}  // namespace pzb
+
+using namespace pzb;
+
+static thread_local std::string g_err = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(PZB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+struct pzb_plan {
+  int device = 0;
+  int num_sms = 0;
+  PlanDev host;  // host copy (device pointers inside)
+  PlanDev* d_plan = nullptr;
+  void* d_weights = nullptr;
+  size_t weight_bytes = 0;
+  int Lmax = 1, act_rows = 1;
+  bool pingpong = false;
+  double flops_per_row = 0.0;
+  bool tc_ok = false;
+  int engine = PZB_ENGINE_AUTO;
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+extern "C" {
+
+int pzb_abi_version(void) { return PZB_ABI_VERSION; }
+const char* pzb_last_error(void) { return g_err.c_str(); }
+long long pzb_launch_count_ll(void) { return g_launches.load(); }
+int64_t pzb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int pzb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t input_dim,
+                    int32_t latent_kind, float latent_B, int32_t device, pzb_plan** out) {
+  if (out == nullptr) return fail(PZB_ERR_INVALID, "plan_create: out is NULL");
+  *out = nullptr;
+  if (n_stages < 0 || (n_stages > 0 && stages == nullptr))
+    return fail(PZB_ERR_INVALID, "plan_create: bad stage list");
+  const int D = input_dim;
+  if (D < 1 || D > MAX_D)
+    return fail(PZB_ERR_UNSUPPORTED, "plan_create: input_dim %d outside [1, %d]", D, MAX_D);
+  if (latent_kind != PZB_LATENT_UNIFORM && latent_kind != PZB_LATENT_CENTBETA13)
+    return fail(PZB_ERR_UNSUPPORTED, "plan_create: latent kind %d is outside the hot path", latent_kind);
+  if (pzb_device_count() <= 0)
+    return fail(PZB_ERR_NO_DEVICE, "plan_create: no CUDA device (this library has no CPU fallback)");
+
+  pzb_plan* plan = new (std::nothrow) pzb_plan();
+  if (!plan) return fail(PZB_ERR_INVALID, "plan_create: out of host memory");
+  PlanDev& hp = plan->host;
+  memset(&hp, 0, sizeof(hp));
+  hp.D = D;
+  hp.C = 0;
+  hp.latent_kind = latent_kind;
+  hp.latent_B = latent_B;
+  if (latent_kind == PZB_LATENT_UNIFORM) {
+    hp.latent_const = (float)(-D) * logf(2.0f * latent_B);  // -input_dim * log(2B)
+  } else {
+    const float g13 = (float)lgamma(13.0), g26 = (float)lgamma(26.0);
+    hp.latent_const = (g13 + g13) - g26;
+  }
+
+  // ---- pass 1: flatten, fold Roll into permutations, size the weight blob ----
+  int cur[MAX_D];
+  for (int j = 0; j < D; ++j) cur[j] = j;
+  int depth = 0;
+  size_t blob = 0;
+  struct Pending {
+    int nsc_idx;
+    const float* const* weights;
+  };
+  std::vector<Pending> pend;
+  int rc = PZB_OK;
+  for (int si = 0; si < n_stages && rc == PZB_OK; ++si) {
+    const pzb_stage_desc& sd = stages[si];
+    if (hp.n_steps >= MAX_STEPS) {
+      rc = fail(PZB_ERR_UNSUPPORTED, "plan_create: more than %d steps", MAX_STEPS);
+      break;
+    }
+    switch (sd.kind) {
+      case 5: {  // chain begin
+        if (++depth >= MAX_CHAIN_DEPTH) {
+          rc = fail(PZB_ERR_UNSUPPORTED, "plan_create: Chain nesting deeper than %d", MAX_CHAIN_DEPTH - 1);
+          break;
+        }
+        hp.steps[hp.n_steps++] = {STEP_CHAIN_BEGIN, 0};
+        break;
+      }
+      case 6: {  // chain end
+        if (--depth < 0) {
+          rc = fail(PZB_ERR_INVALID, "plan_create: unbalanced chain markers");
+          break;
+        }
+        hp.steps[hp.n_steps++] = {STEP_CHAIN_END, 0};
+        break;
+      }
+      case PZB_STAGE_ROLL: {
+        // out[:, j] = in[:, (j - shift) mod D]  (jnp.roll, pzflow/bijectors.py:586)
+        int nxt[MAX_D];
+        for (int j = 0; j < D; ++j) {
+          int src = ((j - sd.shift) % D + D) % D;
+          nxt[j] = cur[src];
+        }
+        memcpy(cur, nxt, sizeof(int) * D);
+        break;
+      }
+      case PZB_STAGE_SHIFT_BOUNDS:
+      case PZB_STAGE_STANDARD_SCALER: {
+        if (hp.n_affine >= MAX_AFFINE) {
+          rc = fail(PZB_ERR_UNSUPPORTED, "plan_create: more than %d affine stages", MAX_AFFINE);
+          break;
+        }
+        if (sd.vec_a == nullptr || sd.vec_b == nullptr || (sd.n_vec != 1 && sd.n_vec != D)) {
+          rc = fail(PZB_ERR_INVALID, "plan_create: affine stage %d needs 1 or %d values", si, D);
+          break;
+        }
+        AffineDev& af = hp.affine[hp.n_affine];
+        af.B = sd.B;
+        if (sd.kind == PZB_STAGE_SHIFT_BOUNDS) {
+          af.kind = AFF_SHIFT_BOUNDS;
+          float pf = 1.0f, pi = 1.0f;
+          for (int v = 0; v < sd.n_vec; ++v) {
+            if (sd.vec_a[v] > sd.vec_b[v]) {
+              rc = fail(PZB_ERR_INVALID, "All mins must be less than maxes.");
+              break;
+            }
+            const float hr = (sd.vec_b[v] - sd.vec_a[v]) / 2.0f;
+            pf = pf * (sd.B / hr);  // jnp.prod(B / half_range), over the n_vec entries
+            pi = pi * (hr / sd.B);
+          }
+          if (rc != PZB_OK) break;
+          af.logdet_fwd = logf(pf);
+          af.logdet_inv = logf(pi);
+          for (int j = 0; j < D; ++j) {
+            const int v = sd.n_vec == 1 ? 0 : j;
+            af.a[cur[j]] = (sd.vec_b[v] + sd.vec_a[v]) / 2.0f;
+            af.b[cur[j]] = (sd.vec_b[v] - sd.vec_a[v]) / 2.0f;
+          }
+        } else {
+          af.kind = AFF_STANDARD_SCALER;
+          if (sd.n_vec != D) {
+            rc = fail(PZB_ERR_INVALID, "plan_create: StandardScaler needs %d means/stds", D);
+            break;
+          }
+          float p = 1.0f;
+          for (int j = 0; j < D; ++j) {
+            p = p * sd.vec_b[j];
+            af.a[cur[j]] = sd.vec_a[j];
+            af.b[cur[j]] = sd.vec_b[j];
+          }
+          af.logdet_fwd = logf(1.0f / p);
+          af.logdet_inv = logf(p);
+        }
+        hp.steps[hp.n_steps++] = {STEP_AFFINE, hp.n_affine++};
+        break;
+      }
+      case PZB_STAGE_NSC: {
+        if (hp.n_nsc >= MAX_NSC) {
+          rc = fail(PZB_ERR_UNSUPPORTED, "plan_create: more than %d coupling stages", MAX_NSC);
+          break;
+        }
+        NscDev& st = hp.nsc[hp.n_nsc];
+        const int L = sd.transformed_dim < 0 ? D - D / 2 : sd.transformed_dim;
+        const int U = D - L;
+        if (L < 1 || U < 0) {
+          rc = fail(PZB_ERR_INVALID, "plan_create: transformed_dim %d invalid for input_dim %d", L, D);
+          break;
+        }
+        if (sd.K < 1 || sd.hidden_layers < 0 || sd.hidden_layers + 1 > MAX_DENSE ||
+            sd.hidden_dim < 1 || sd.n_conditions < 0 || sd.weights == nullptr) {
+          rc = fail(PZB_ERR_INVALID, "plan_create: bad NeuralSplineCoupling arguments at stage %d", si);
+          break;
+        }
+        if (U + sd.n_conditions > MAX_KEY) {
+          rc = fail(PZB_ERR_UNSUPPORTED, "plan_create: conditioner input wider than %d", MAX_KEY);
+          break;
+        }
+        const int cpd = 3 * sd.K - 1 + (sd.periodic ? 1 : 0);
+        if (cpd > MAX_NC) {
+          rc = fail(PZB_ERR_UNSUPPORTED, "plan_create: K = %d needs more than %d logits per dim", sd.K, MAX_NC);
+          break;
+        }
+        // every stage keys on hstack(upper, conditions)[:, :U + n_conditions] (bijectors.py:481-483):
+        // stages may use different prefixes of the same conditions array.
+        if (sd.n_conditions > hp.C) hp.C = sd.n_conditions;
+        st.U = U;
+        st.L = L;
+        st.C = sd.n_conditions;
+        st.K = sd.K;
+        st.cpd = cpd;
+        st.dpc = MAX_NC / cpd < L ? MAX_NC / cpd : L;
+        st.periodic = sd.periodic ? 1 : 0;
+        st.n_dense = sd.hidden_layers + 1;
+        st.H = sd.hidden_dim;
+        st.Hpad = (int)align_up(sd.hidden_dim, 128);
+        st.B = sd.B;
+        st.bins_off = hp.n_spline_dims;
+        hp.n_spline_dims += L;
+        for (int j = 0; j < D; ++j) st.perm[j] = (int16_t)cur[j];
+        int in_dim = U + sd.n_conditions;
+        for (int li = 0; li < st.n_dense; ++li) {
+          DenseDev& dl = st.dense[li];
+          const bool last = (li == st.n_dense - 1);
+          dl.in_dim = in_dim;
+          dl.out_dim = last ? cpd * L : sd.hidden_dim;
+          if (last) {
+            dl.n_chunks = (L + st.dpc - 1) / st.dpc;
+            dl.NC = (int)align_up((size_t)st.dpc * cpd, 64);
+          } else {
+            dl.n_chunks = st.Hpad / 128;
+            dl.NC = 128;
+          }
+          blob += align_up((size_t)dl.n_chunks * dl.in_dim * dl.NC * sizeof(float), 256);
+          blob += align_up((size_t)dl.n_chunks * dl.NC * sizeof(float), 256);
+          in_dim = sd.hidden_dim;
+          if (!last && dl.n_chunks > 1) plan->pingpong = true;
+          if (sd.weights[2 * li] == nullptr || sd.weights[2 * li + 1] == nullptr) {
+            rc = fail(PZB_ERR_INVALID, "plan_create: NULL weight pointer at stage %d layer %d", si, li);
+            break;
+          }
+        }
+        if (rc != PZB_OK) break;
+        if (L > plan->Lmax) plan->Lmax = L;
+        int ar = U + sd.n_conditions;
+        if (st.n_dense > 1 && st.Hpad > ar) ar = st.Hpad;
+        if (ar > plan->act_rows) plan->act_rows = ar;
+        plan->flops_per_row += 2.0 * ((double)(U + sd.n_conditions) * (st.n_dense > 1 ? sd.hidden_dim : cpd * L) +
+                                      (st.n_dense > 1 ? (double)(sd.hidden_layers - 1) * sd.hidden_dim * sd.hidden_dim +
+                                                            (double)sd.hidden_dim * cpd * L
+                                                      : 0.0));
+        pend.push_back({hp.n_nsc, sd.weights});
+        hp.steps[hp.n_steps++] = {STEP_NSC, hp.n_nsc++};
+        break;
+      }
+      default:
+        rc = fail(PZB_ERR_UNSUPPORTED, "plan_create: stage kind %d is outside the hot path", sd.kind);
+    }
+  }
+  if (rc == PZB_OK && depth != 0) rc = fail(PZB_ERR_INVALID, "plan_create: unbalanced chain markers");
+  if (rc != PZB_OK) {
+    delete plan;
+    return rc;
+  }
+  for (int j = 0; j < D; ++j) hp.perm_final[j] = (int16_t)cur[j];
+
+  // tensor-core packing is appended to the same blob
+  plan->tc_ok = tc_plan_supported(hp);
+  size_t tc_off = align_up(blob, 1024);
+  size_t tc_total = 0;
+  if (plan->tc_ok) {
+    for (int s = 0; s < hp.n_nsc; ++s) tc_total += align_up(tc_pack_bytes(hp.nsc[s]), 1024);
+  }
+  const size_t total = tc_off + tc_total;
+
+  // ---- pass 2: pack on the host, upload once ----
+  plan->device = device;
+  DeviceGuard guard(device);
+  if (!guard.ok) {
+    delete plan;
+    return fail(PZB_ERR_CUDA, "plan_create: cannot select device %d", device);
+  }
+  cudaDeviceProp prop;
+  cudaError_t ce = cudaGetDeviceProperties(&prop, device);
+  if (ce != cudaSuccess) {
+    delete plan;
+    return cuda_fail(ce, "cudaGetDeviceProperties");
+  }
+  plan->num_sms = prop.multiProcessorCount;
+
+  std::vector<unsigned char> hblob(total > 0 ? total : 256, 0);
+  if (total > 0 || true) {
+    ce = cudaMalloc(&plan->d_weights, hblob.size());
+    if (ce != cudaSuccess) {
+      delete plan;
+      return cuda_fail(ce, "cudaMalloc(weights)");
+    }
+  }
+  plan->weight_bytes = hblob.size();
+  size_t off = 0;
+  unsigned char* dbase = static_cast<unsigned char*>(plan->d_weights);
+  for (const Pending& pe : pend) {
+    NscDev& st = hp.nsc[pe.nsc_idx];
+    for (int li = 0; li < st.n_dense; ++li) {
+      DenseDev& dl = st.dense[li];
+      const bool last = (li == st.n_dense - 1);
+      const float* W = pe.weights[2 * li];
+      const float* b = pe.weights[2 * li + 1];
+      float* Wp = reinterpret_cast<float*>(hblob.data() + off);
+      dl.W = reinterpret_cast<const float*>(dbase + off);
+      off += align_up((size_t)dl.n_chunks * dl.in_dim * dl.NC * sizeof(float), 256);
+      float* bp = reinterpret_cast<float*>(hblob.data() + off);
+      dl.b = reinterpret_cast<const float*>(dbase + off);
+      off += align_up((size_t)dl.n_chunks * dl.NC * sizeof(float), 256);
+      const int cols_per_chunk = last ? st.dpc * st.cpd : 128;
+      for (int c = 0; c < dl.n_chunks; ++c) {
+        for (int n = 0; n < dl.NC; ++n) {
+          const int col = c * cols_per_chunk + n;
+          const bool valid = (n < cols_per_chunk) && (col < dl.out_dim);
+          bp[c * dl.NC + n] = valid ? b[col] : 0.0f;
+          for (int k = 0; k < dl.in_dim; ++k)
+            Wp[((size_t)c * dl.in_dim + k) * dl.NC + n] = valid ? W[(size_t)k * dl.out_dim + col] : 0.0f;
+        }
+      }
+    }
+  }
+  if (plan->tc_ok) {
+    size_t o = tc_off;
+    for (const Pending& pe : pend) {
+      NscDev& st = hp.nsc[pe.nsc_idx];
+      const size_t nb = tc_pack_bytes(st);
+      tc_pack_stage(st, pe.weights, hblob.data() + o);
+      st.tc.blob = dbase + o;
+      st.tc.blob_bytes = (int)nb;
+      o += align_up(nb, 1024);
+    }
+  }
+  ce = cudaMemcpy(plan->d_weights, hblob.data(), hblob.size(), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMalloc(&plan->d_plan, sizeof(PlanDev));
+  if (ce == cudaSuccess) ce = cudaMemcpy(plan->d_plan, &hp, sizeof(PlanDev), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    int r = cuda_fail(ce, "plan upload");
+    pzb_plan_destroy(plan);
+    return r;
+  }
+  *out = plan;
+  return PZB_OK;
+}
+
+void pzb_plan_destroy(pzb_plan* plan) {
+  if (!plan) return;
+  DeviceGuard guard(plan->device);
+  if (plan->d_plan) cudaFree(plan->d_plan);
+  if (plan->d_weights) cudaFree(plan->d_weights);
+  delete plan;
+}
+
+int pzb_plan_input_dim(const pzb_plan* plan) { return plan ? plan->host.D : -1; }
+int pzb_plan_n_conditions(const pzb_plan* plan) { return plan ? plan->host.C : -1; }
+int pzb_plan_n_spline_dims(const pzb_plan* plan) { return plan ? plan->host.n_spline_dims : -1; }
+double pzb_plan_flops_per_row(const pzb_plan* plan) { return plan ? plan->flops_per_row : 0.0; }
+int pzb_plan_tc_supported(const pzb_plan* plan) { return plan && plan->tc_ok ? 1 : 0; }
+
+int pzb_plan_set_engine(pzb_plan* plan, int32_t engine) {
+  if (!plan) return fail(PZB_ERR_INVALID, "set_engine: plan is NULL");
+  if (engine != PZB_ENGINE_AUTO && engine != PZB_ENGINE_SIMT && engine != PZB_ENGINE_TC)
+    return fail(PZB_ERR_INVALID, "set_engine: unknown engine %d", engine);
+  if (engine == PZB_ENGINE_TC && !plan->tc_ok)
+    return fail(PZB_ERR_UNSUPPORTED, "set_engine: the tensor-core engine does not support this plan's shapes");
+  plan->engine = engine;
+  return PZB_OK;
+}
+
+int pzb_plan_engine(const pzb_plan* plan) {
+  if (!plan) return -1;
+  if (plan->engine == PZB_ENGINE_AUTO) return plan->tc_ok ? PZB_ENGINE_TC : PZB_ENGINE_SIMT;
+  return plan->engine;
+}
+
+static int launch_chain(const pzb_plan* plan, const LaunchArgs& args, void* stream) {
+  if (args.N == 0) return PZB_OK;
+  DeviceGuard guard(plan->device);
+  if (!guard.ok) return fail(PZB_ERR_CUDA, "cannot select device %d", plan->device);
+  cudaError_t ce;
+  if (pzb_plan_engine(plan) == PZB_ENGINE_TC) {
+    ce = launch_tc(plan->d_plan, plan->host, args, plan->num_sms, nullptr, (cudaStream_t)stream);
+  } else {
+    ce = launch_simt(plan->d_plan, args, plan->host.D, plan->host.C, plan->Lmax, plan->act_rows,
+                     plan->pingpong, plan->num_sms, (cudaStream_t)stream);
+  }
+  if (ce != cudaSuccess) return cuda_fail(ce, "chain kernel launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+static int check_common(const pzb_plan* plan, const void* in, const float* cond, int64_t N,
+                        const void* outp, const char* who) {
+  if (!plan) return fail(PZB_ERR_INVALID, "%s: plan is NULL", who);
+  if (N < 0) return fail(PZB_ERR_INVALID, "%s: negative row count", who);
+  if (N > 0 && (in == nullptr || outp == nullptr)) return fail(PZB_ERR_INVALID, "%s: NULL buffer", who);
+  if (N > 0 && plan->host.C > 0 && cond == nullptr)
+    return fail(PZB_ERR_INVALID, "%s: this plan is conditional (C = %d) but conditions are NULL", who, plan->host.C);
+  return PZB_OK;
+}
+
+int pzb_log_prob(const pzb_plan* plan, const float* X, const float* cond, int64_t N, float* out,
+                 int32_t* bins, void* stream) {
+  int rc = check_common(plan, X, cond, N, out, "log_prob");
+  if (rc) return rc;
+  LaunchArgs a{};
+  a.mode = MODE_LOGPROB;
+  a.X = X;
+  a.cond = cond;
+  a.N = N;
+  a.out0 = out;
+  a.bins = bins;
+  return launch_chain(plan, a, stream);
+}
+
+int pzb_forward(const pzb_plan* plan, const float* X, const float* cond, int64_t N, float* U,
+                float* log_det, int32_t* bins, void* stream) {
+  int rc = check_common(plan, X, cond, N, U, "forward");
+  if (rc) return rc;
+  LaunchArgs a{};
+  a.mode = MODE_FORWARD;
+  a.X = X;
+  a.cond = cond;
+  a.N = N;
+  a.out0 = U;
+  a.out1 = log_det;
+  a.bins = bins;
+  return launch_chain(plan, a, stream);
+}
+
+int pzb_inverse(const pzb_plan* plan, const float* U, const float* cond, int64_t N, float* X,
+                float* log_det, int32_t* bins, void* stream) {
+  int rc = check_common(plan, U, cond, N, X, "inverse");
+  if (rc) return rc;
+  LaunchArgs a{};
+  a.mode = MODE_INVERSE;
+  a.X = U;
+  a.cond = cond;
+  a.N = N;
+  a.out0 = X;
+  a.out1 = log_det;
+  a.bins = bins;
+  return launch_chain(plan, a, stream);
+}
+
+// ---- small memory-bound helper kernels ----
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.0f;
+  const int nw = (blockDim.x + 31) >> 5;
+  for (int w = 0; w < nw; ++w) t += red[w];
+  return t;
+}
+
+__device__ __forceinline__ float nan_to_num0(float v) {
+  if (isnan(v)) return 0.0f;
+  if (v == INFINITY) return 3.4028234663852886e38f;
+  if (v == -INFINITY) return -3.4028234663852886e38f;
+  return v;
+}
+
+// pdfs / trapezoid(pdfs, grid) per row, then nan_to_num(nan=0)  (pzflow/flow.py:732-737).
+// Optionally averages n_flows stacked inputs first (pzflow/flowEnsemble.py:346-351).
+__global__ void __launch_bounds__(256)
+normalize_pdfs_kernel(const float* __restrict__ in, int n_flows, long long Ng, int G,
+                      const float* __restrict__ grid, int normalize, int nan_to_zero,
+                      float* __restrict__ out) {
+  __shared__ float red[8];
+  for (long long g = blockIdx.x; g < Ng; g += gridDim.x) {
+    float part = 0.0f;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+      float y;
+      if (n_flows > 1) {
+        float s = 0.0f;
+        for (int f = 0; f < n_flows; ++f) s += in[((size_t)f * Ng + g) * G + i];
+        y = s / (float)n_flows;
+        out[(size_t)g * G + i] = y;
+      } else {
+        y = in[(size_t)g * G + i];
+      }
+      if (normalize && i + 1 < G) {
+        float y1;
+        if (n_flows > 1) {
+          float s = 0.0f;
+          for (int f = 0; f < n_flows; ++f) s += in[((size_t)f * Ng + g) * G + i + 1];
+          y1 = s / (float)n_flows;
+        } else {
+          y1 = in[(size_t)g * G + i + 1];
+        }
+        part += (grid[i + 1] - grid[i]) * (y1 + y);
+      }
+    }
+    float integral = 1.0f;
+    if (normalize) integral = 0.5f * block_sum(part, red);
+    __syncthreads();
+    if (normalize || nan_to_zero || n_flows == 1) {
+      for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        float y = (n_flows > 1) ? out[(size_t)g * G + i] : in[(size_t)g * G + i];
+        if (normalize) y = y / integral;
+        if (nan_to_zero) y = nan_to_num0(y);
+        out[(size_t)g * G + i] = y;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+logmeanexp_kernel(const float* __restrict__ lp, int n_flows, long long N, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int f = 0; f < n_flows; ++f) s += expf(lp[(size_t)f * N + i]);
+    out[i] = logf(s / (float)n_flows);  // naive log(mean(exp)), pzflow/flowEnsemble.py:243
+  }
+}
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0;
+  c[1] = lo1;
+  c[2] = n2;
+  c[3] = lo0;
+}
+
+__global__ void __launch_bounds__(256)
+sample_uniform_kernel(float* __restrict__ U, long long n, float B, uint64_t seed) {
+  const long long nq = (n + 3) / 4;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq;
+       q += (long long)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)((unsigned long long)q >> 32), 0u, 0u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const long long i = q * 4 + t;
+      if (i >= n) break;
+      // 23 random mantissa bits -> [1, 2) - 1 -> [0, 1); scale to [-B, B) like jax.random.uniform
+      const float u01 = __uint_as_float((c[t] >> 9) | 0x3f800000u) - 1.0f;
+      U[i] = fmaxf(-B, u01 * (2.0f * B) + (-B));
+    }
+  }
+}
+
+int pzb_normalize_pdfs(float* pdfs, int64_t Ng, int32_t G, const float* grid, int32_t normalize,
+                       int32_t nan_to_zero, void* stream) {
+  if (Ng < 0 || G < 1) return fail(PZB_ERR_INVALID, "normalize_pdfs: bad shape");
+  if (Ng == 0) return PZB_OK;
+  if (!pdfs || !grid) return fail(PZB_ERR_INVALID, "normalize_pdfs: NULL buffer");
+  if (!normalize && !nan_to_zero) return PZB_OK;
+  const unsigned blocks = (unsigned)(Ng < 148 * 64 ? Ng : 148 * 64);
+  normalize_pdfs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pdfs, 1, Ng, G, grid, normalize,
+                                                                  nan_to_zero, pdfs);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "normalize_pdfs launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+int pzb_posterior(const pzb_plan* plan, const float* rest, const float* cond, int64_t Ng,
+                  int32_t col_idx, const float* grid, int32_t G, int32_t normalize,
+                  int32_t nan_to_zero, float* pdfs, void* stream) {
+  int rc = check_common(plan, plan && plan->host.D > 1 ? (const void*)rest : (const void*)grid, cond, Ng, pdfs, "posterior");
+  if (rc) return rc;
+  if (G < 1 || grid == nullptr) return fail(PZB_ERR_INVALID, "posterior: empty grid");
+  if (col_idx < 0 || col_idx >= plan->host.D) return fail(PZB_ERR_INVALID, "posterior: column index %d out of range", col_idx);
+  LaunchArgs a{};
+  a.mode = MODE_POSTERIOR;
+  a.X = rest;
+  a.cond = cond;
+  a.grid = grid;
+  a.G = G;
+  a.col_idx = col_idx;
+  a.N = Ng * (int64_t)G;
+  a.out0 = pdfs;
+  rc = launch_chain(plan, a, stream);
+  if (rc) return rc;
+  DeviceGuard guard(plan->device);
+  return pzb_normalize_pdfs(pdfs, Ng, G, grid, normalize, nan_to_zero, stream);
+}
+
+int pzb_ensemble_logmeanexp(const float* lp, int32_t n_flows, int64_t N, float* out, void* stream) {
+  if (n_flows < 1 || N < 0) return fail(PZB_ERR_INVALID, "ensemble_logmeanexp: bad shape");
+  if (N == 0) return PZB_OK;
+  if (!lp || !out) return fail(PZB_ERR_INVALID, "ensemble_logmeanexp: NULL buffer");
+  long long blocks = (N + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  logmeanexp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(lp, n_flows, N, out);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "logmeanexp launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+int pzb_ensemble_posterior_mean(const float* pdfs, int32_t n_flows, int64_t Ng, int32_t G,
+                                const float* grid, int32_t normalize, float* out, void* stream) {
+  if (n_flows < 1 || Ng < 0 || G < 1) return fail(PZB_ERR_INVALID, "ensemble_posterior_mean: bad shape");
+  if (Ng == 0) return PZB_OK;
+  if (!pdfs || !out || !grid) return fail(PZB_ERR_INVALID, "ensemble_posterior_mean: NULL buffer");
+  const unsigned blocks = (unsigned)(Ng < 148 * 64 ? Ng : 148 * 64);
+  // n_flows == 1 degenerates to a copy (+ normalisation)
+  normalize_pdfs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pdfs, n_flows, Ng, G, grid, normalize, 0, out);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "ensemble_posterior_mean launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+int pzb_sample_uniform(float* U, int64_t N, int32_t D, float B, uint64_t seed, void* stream) {
+  if (N < 0 || D < 1) return fail(PZB_ERR_INVALID, "sample_uniform: bad shape");
+  if (N == 0) return PZB_OK;
+  if (!U) return fail(PZB_ERR_INVALID, "sample_uniform: NULL buffer");
+  const long long n = N * (long long)D;
+  long long blocks = ((n + 3) / 4 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  sample_uniform_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(U, n, B, seed);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "sample_uniform launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,347 @@
+"""``Flow``: host-side mirror of pzflow/flow.py for the inference hot path.
+
+Same constructor, attributes, ``_params`` pytree ``(latent_params,
+bijector_params)``, ``_bijector_info``, save-dict keys and error behaviour as
+the reference (pzflow/flow.py:49-251, 819-866); ``log_prob`` (409-464),
+``posterior`` (466-738) and ``sample`` (740-817) evaluate through one fused CUDA
+kernel per call via the C-ABI (``pzflow_b200.plan.Plan``).  There is no CPU
+path: without a CUDA device every evaluation raises.
+
+Out of scope here: ``train`` and Gaussian error convolution
+(``err_samples``) raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import sys
+import types
+from typing import Any, Callable, Sequence, Tuple
+
+import dill as pickle
+import numpy as np
+import pandas as pd
+import torch
+
+from . import distributions
+from .bijectors import Bijector_Info, Chain, InitFunction, Pytree, RollingSplineCoupling, ShiftBounds
+from .plan import Plan, params_fingerprint
+from .utils import build_bijector_from_info, gaussian_error_model
+
+
+def _load_pickle(file: str) -> dict:
+    """dill-load a reference ``.pzflow.pkl`` without jax: the only by-reference global
+    in the save dict is pzflow.utils.gaussian_error_model (pzflow/flow.py:238)."""
+    injected = []
+    if "pzflow" not in sys.modules:
+        pkg = types.ModuleType("pzflow")
+        sub = types.ModuleType("pzflow.utils")
+        sub.gaussian_error_model = gaussian_error_model
+        pkg.utils = sub
+        sys.modules["pzflow"], sys.modules["pzflow.utils"] = pkg, sub
+        injected = ["pzflow", "pzflow.utils"]
+    try:
+        with open(file, "rb") as handle:
+            return pickle.load(handle)
+    finally:
+        for k in injected:
+            sys.modules.pop(k, None)
+
+
+def _to_numpy_tree(p):
+    if isinstance(p, (list, tuple)):
+        return type(p)(_to_numpy_tree(q) for q in p)
+    if isinstance(p, (int, float)):
+        return p
+    return np.asarray(p)
+
+
+class Flow:
+    """A normalizing flow that models tabular data (inference on B200)."""
+
+    def __init__(
+        self,
+        data_columns: Sequence[str] = None,
+        bijector: Tuple[InitFunction, Bijector_Info] = None,
+        latent: distributions.LatentDist = None,
+        conditional_columns: Sequence[str] = None,
+        data_error_model: Callable = None,
+        condition_error_model: Callable = None,
+        autoscale_conditions: bool = True,
+        seed: int = 0,
+        info: Any = None,
+        file: str = None,
+        _dictionary: dict = None,
+    ) -> None:
+        # validate parameters (pzflow/flow.py:126-149)
+        if data_columns is None and file is None and _dictionary is None:
+            raise ValueError("You must provide data_columns OR file.")
+        if any((data_columns is not None, bijector is not None, conditional_columns is not None,
+                latent is not None, data_error_model is not None, condition_error_model is not None,
+                info is not None)):
+            if file is not None:
+                raise ValueError("If providing a file, please do not provide any other parameters.")
+            if _dictionary is not None:
+                raise ValueError("If providing a dictionary, please do not provide any other parameters.")
+        if file is not None and _dictionary is not None:
+            raise ValueError("Only provide file or _dictionary, not both.")
+
+        self._plan_cache = {}
+        if file is not None or _dictionary is not None:
+            save_dict = self._save_dict()
+            save_dict.update(_load_pickle(file) if file is not None else _dictionary)
+            if save_dict["class"] != self.__class__.__name__:
+                raise TypeError(f"This save file isn't a {self.__class__.__name__}. "
+                                f"It is a {save_dict['class']}")
+            self.data_columns = save_dict["data_columns"]
+            self.conditional_columns = save_dict["conditional_columns"]
+            self._input_dim = len(self.data_columns)
+            self.info = save_dict["info"]
+            self._latent_info = save_dict["latent_info"]
+            self.latent = getattr(distributions, self._latent_info[0])(*self._latent_info[1])
+            self.data_error_model = save_dict["data_error_model"]
+            self.condition_error_model = save_dict["condition_error_model"]
+            self._bijector_info = save_dict["bijector_info"]
+            if self._bijector_info is not None:
+                init_fun, _ = build_bijector_from_info(self._bijector_info)
+                _, self._forward, self._inverse = init_fun(0, self._input_dim)
+            self._params = _to_numpy_tree(save_dict["params"])
+            self._condition_means = save_dict["condition_means"]
+            self._condition_stds = save_dict["condition_stds"]
+            self._autoscale_conditions = save_dict["autoscale_conditions"]
+        else:
+            self.data_columns = tuple(data_columns)
+            self._input_dim = len(self.data_columns)
+            self.info = info
+            if conditional_columns is None:
+                self.conditional_columns = None
+                self._condition_means = None
+                self._condition_stds = None
+            else:
+                self.conditional_columns = tuple(conditional_columns)
+                self._condition_means = np.zeros(len(self.conditional_columns), dtype=np.float32)
+                self._condition_stds = np.ones(len(self.conditional_columns), dtype=np.float32)
+            self._autoscale_conditions = autoscale_conditions
+            if latent is None:
+                self.latent = distributions.CentBeta13(self._input_dim, 5)
+            else:
+                self.latent = latent
+            self._latent_info = self.latent.info
+            if self.latent.input_dim != len(data_columns):
+                raise ValueError(f"The latent distribution has {self.latent.input_dim} "
+                                 f"dimensions, but data_columns has {len(data_columns)} "
+                                 "dimensions. They must match!")
+            self.data_error_model = gaussian_error_model if data_error_model is None else data_error_model
+            self.condition_error_model = (gaussian_error_model if condition_error_model is None
+                                          else condition_error_model)
+            if bijector is not None:
+                self.set_bijector(bijector, seed=seed)
+            else:
+                self._bijector_info = None
+
+    # ------------------------------------------------------------------ #
+    def _check_bijector(self) -> None:
+        if self._bijector_info is None:
+            raise ValueError("The bijector has not been set up yet! "
+                             "You can do this by calling "
+                             "flow.set_bijector(bijector, params), "
+                             "or by calling train, in which case the default "
+                             "bijector will be used.")
+
+    def set_bijector(self, bijector: Tuple[InitFunction, Bijector_Info], params: Pytree = None,
+                     seed: int = 0) -> None:
+        """Set the bijector (pzflow/flow.py:263-294)."""
+        init_fun, self._bijector_info = bijector
+        bijector_params, self._forward, self._inverse = init_fun(seed, self._input_dim)
+        bijector_params = params if params is not None else bijector_params
+        self._params = (self.latent._params, bijector_params)
+        self._plan_cache = {}
+
+    def _set_default_bijector(self, inputs: pd.DataFrame, seed: int = 0) -> None:
+        """ShiftBounds -> RollingSplineCoupling (pzflow/flow.py:296-322)."""
+        data = inputs[list(self.data_columns)].to_numpy()
+        mins = data.min(axis=0)
+        maxs = data.max(axis=0)
+        n_conditions = 0 if self.conditional_columns is None else len(self.conditional_columns)
+        self.set_bijector(Chain(ShiftBounds(mins, maxs, 4.0),
+                                RollingSplineCoupling(len(self.data_columns), n_conditions=n_conditions)),
+                          seed=seed)
+
+    # ------------------------------------------------------------------ #
+    def _plan(self, params: Pytree = None) -> Plan:
+        """The fused device plan of (bijector, latent) for ``params`` on the current device."""
+        params = self._params if params is None else params
+        key = (params_fingerprint(params[1]), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        plan = self._plan_cache.get(key)
+        if plan is None:
+            self._plan_cache.clear()
+            plan = Plan(self._bijector_info, params[1], self._input_dim, self._latent_info)
+            self._plan_cache[key] = plan
+        return plan
+
+    def _get_conditions(self, inputs: pd.DataFrame):
+        """Standard-scaled conditions, or None for an unconditional flow -- the reference's
+        zeros[N, 1] dummy is sliced away inside the bijector (pzflow/flow.py:324-337)."""
+        if self.conditional_columns is None:
+            return None
+        columns = list(self.conditional_columns)
+        conditions = inputs[columns].to_numpy().astype(np.float32)
+        means = np.asarray(self._condition_means, dtype=np.float32)
+        stds = np.asarray(self._condition_stds, dtype=np.float32)
+        return (conditions - means) / stds
+
+    def _log_prob(self, params: Pytree, inputs, conditions=None):
+        """Log prob for arrays (pzflow/flow.py:397-407): forward, latent log-density +
+        log_det, NaN -> zero probability -- one fused kernel.  Returns a device tensor."""
+        return self._plan(params).log_prob(inputs, conditions)
+
+    def log_prob(self, inputs: pd.DataFrame, err_samples: int = None, seed: int = None) -> np.ndarray:
+        """Calculates log probability density of inputs (pzflow/flow.py:409-464)."""
+        self._check_bijector()
+        if err_samples is None:
+            columns = list(self.data_columns)
+            X = inputs[columns].to_numpy().astype(np.float32, copy=False)
+            conditions = self._get_conditions(inputs)
+            return self._log_prob(self._params, X, conditions).cpu().numpy()
+        assert isinstance(err_samples, int), "err_samples must be a positive integer."
+        assert err_samples > 0, "err_samples must be a positive integer."
+        raise NotImplementedError("err_samples (Gaussian error convolution) is a next-round row "
+                                  "of the B200 hot path (SURVEY.md §8f-1)")
+
+    def posterior(self, inputs: pd.DataFrame, column: str, grid, marg_rules: dict = None,
+                  normalize: bool = True, err_samples: int = None, seed: int = None,
+                  batch_size: int = None, nan_to_zero: bool = True) -> np.ndarray:
+        """Calculates posterior distributions for the provided column
+        (pzflow/flow.py:466-738).  The [rows x grid] expansion is generated inside the
+        kernel; ``batch_size`` only bounds the size of one launch."""
+        self._check_bijector()
+        columns = list(self.data_columns)
+        idx = columns.index(column)
+        columns.remove(column)
+        nrows = inputs.shape[0]
+        batch_size = nrows if batch_size is None else batch_size
+        inputs = inputs.reset_index(drop=True)
+        if err_samples is not None:
+            assert isinstance(err_samples, int), "err_samples must be a positive integer."
+            assert err_samples > 0, "err_samples must be a positive integer."
+            raise NotImplementedError("err_samples (Gaussian error convolution) is a next-round row "
+                                      "of the B200 hot path (SURVEY.md §8f-1)")
+        grid = np.asarray(grid, dtype=np.float32).reshape(-1)
+
+        if marg_rules is not None:
+            return self._posterior_marginalized(inputs, column, columns, grid, marg_rules, normalize,
+                                                batch_size, nan_to_zero)
+
+        plan = self._plan()
+        grid_t = torch.from_numpy(grid).to(plan.device)
+        pdfs = torch.empty((nrows, grid.size), dtype=torch.float32, device=plan.device)
+        for b0 in range(0, nrows, max(1, batch_size)):
+            batch = inputs.iloc[b0:b0 + batch_size]
+            conditions = self._get_conditions(batch)
+            rest = batch[columns].to_numpy().astype(np.float32, copy=False).reshape(len(batch), -1)
+            # un-normalised exp(log_prob); normalisation happens once over all rows below,
+            # exactly like pzflow/flow.py:732-737
+            plan.posterior(rest, idx, grid_t, conditions, normalize=False, nan_to_zero=False,
+                           out=pdfs[b0:b0 + batch_size])
+        if normalize or nan_to_zero:
+            from .plan import normalize_pdfs_
+            normalize_pdfs_(pdfs, grid_t, normalize, nan_to_zero)
+        return pdfs.cpu().numpy()
+
+    def _posterior_marginalized(self, inputs, column, columns, grid, marg_rules, normalize, batch_size,
+                                nan_to_zero):
+        """Host orchestration of pzflow/flow.py:560-664 over the fused posterior."""
+        nrows = inputs.shape[0]
+        pdfs = np.zeros((nrows, len(grid)), dtype=np.float32)
+        if np.isnan(marg_rules["flag"]):
+            def check_flags(data):
+                return np.isnan(data)
+        else:
+            def check_flags(data):
+                return np.isclose(data, marg_rules["flag"])
+        unflagged_idx = inputs[~check_flags(inputs[columns]).any(axis=1)].index.tolist()
+        if len(unflagged_idx):
+            pdfs[unflagged_idx, :] = self.posterior(inputs=inputs.iloc[unflagged_idx], column=column, grid=grid,
+                                                    batch_size=batch_size, normalize=False,
+                                                    nan_to_zero=nan_to_zero)
+        already_done = list(unflagged_idx)
+        for name, rule in marg_rules.items():
+            if name == "flag":
+                continue
+            flagged_idx = inputs[check_flags(inputs[name])].index.tolist()
+            flagged_idx = list(set(flagged_idx).difference(already_done))
+            if len(flagged_idx) == 0:
+                continue
+            marg_grids = inputs.iloc[flagged_idx].apply(rule, axis=1, result_type="expand").to_numpy()
+            marg_inputs = pd.DataFrame(np.repeat(inputs.iloc[flagged_idx].to_numpy(), marg_grids.shape[1], axis=0),
+                                       columns=inputs.columns)
+            marg_inputs[name] = marg_grids.reshape(marg_inputs.shape[0], 1)
+            marg_inputs.drop(f"{name}_err", axis=1, inplace=True, errors="ignore")
+            marg_pdfs = self.posterior(inputs=marg_inputs, column=column, grid=grid, marg_rules=marg_rules,
+                                       batch_size=batch_size, normalize=False, nan_to_zero=nan_to_zero)
+            marg_pdfs = marg_pdfs.reshape(len(flagged_idx), marg_grids.shape[1], grid.size).sum(axis=1)
+            pdfs[flagged_idx, :] = marg_pdfs
+            already_done += flagged_idx
+        if normalize or nan_to_zero:
+            from .plan import normalize_pdfs_
+            dev = self._plan().device
+            t = normalize_pdfs_(torch.from_numpy(pdfs).to(dev), torch.from_numpy(grid).to(dev), normalize,
+                                nan_to_zero)
+            pdfs = t.cpu().numpy()
+        return pdfs
+
+    def sample(self, nsamples: int = 1, conditions: pd.DataFrame = None, save_conditions: bool = True,
+               seed: int = None) -> pd.DataFrame:
+        """Returns samples from the normalizing flow (pzflow/flow.py:740-817)."""
+        self._check_bijector()
+        assert isinstance(nsamples, int), "nsamples must be a positive integer."
+        assert nsamples > 0, "nsamples must be a positive integer."
+        if self.conditional_columns is not None and conditions is None:
+            raise ValueError(f"Must provide the following conditions\n{self.conditional_columns}")
+
+        if self.conditional_columns is None:
+            cond = None
+            n = nsamples
+        else:
+            conditions_idx = list(conditions.index)
+            cond = self._get_conditions(conditions)
+            conditions_idx = np.repeat(conditions_idx, nsamples)
+            cond = np.repeat(cond, nsamples, axis=0)
+            n = cond.shape[0]
+
+        plan = self._plan()
+        u = self.latent.sample_device(n, seed)  # draws stay on the device
+        x = plan.inverse(u, cond, want_log_det=False)[0].cpu().numpy()
+        if self.conditional_columns is None:
+            return pd.DataFrame(x, columns=self.data_columns)
+        if save_conditions:
+            cond = cond * np.asarray(self._condition_stds, np.float32) + np.asarray(self._condition_means, np.float32)
+            return pd.DataFrame(np.hstack((x, cond)),
+                                columns=self.data_columns + self.conditional_columns).set_index(conditions_idx)
+        return pd.DataFrame(x, columns=self.data_columns).set_index(conditions_idx)
+
+    # ------------------------------------------------------------------ #
+    def _save_dict(self) -> dict:
+        """Dictionary of everything ``save`` writes (pzflow/flow.py:819-845)."""
+        save_dict = {"class": self.__class__.__name__}
+        keys = ["data_columns", "conditional_columns", "condition_means", "condition_stds",
+                "data_error_model", "condition_error_model", "autoscale_conditions", "info",
+                "latent_info", "bijector_info", "params"]
+        for key in keys:
+            try:
+                save_dict[key] = getattr(self, key)
+            except AttributeError:
+                try:
+                    save_dict[key] = getattr(self, "_" + key)
+                except AttributeError:
+                    save_dict[key] = None
+        return save_dict
+
+    def save(self, file: str) -> None:
+        """Saves the flow to a file (pzflow/flow.py:847-866)."""
+        save_dict = self._save_dict()
+        with open(file, "wb") as handle:
+            pickle.dump(save_dict, handle, recurse=True)
+
+    def train(self, *args, **kwargs):
+        """Training (pzflow/flow.py:868-1159) is outside the B200 hot path."""
+        raise NotImplementedError("Flow.train is outside the B200 inference hot path; "
+                                  "train with pzflow and load the saved flow here")

@@ -1,0 +1,168 @@
+"""``FlowEnsemble``: host-side mirror of pzflow/flowEnsemble.py for the hot path.
+
+``log_prob`` (189-243), ``posterior`` (245-351) and ``sample`` (353-471) keep the
+reference's signatures and reduction rules -- naive ``log(mean(exp(lp)))`` and
+"average the un-normalised pdfs, then normalise" -- with every flow evaluated by
+its fused kernel and the reductions done on the device.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Sequence, Tuple
+
+import dill as pickle
+import numpy as np
+import pandas as pd
+import torch
+
+from . import distributions
+from .bijectors import Bijector_Info, InitFunction
+from .flow import Flow, _load_pickle
+from .plan import ensemble_logmeanexp, ensemble_posterior_mean, normalize_pdfs_
+
+
+class FlowEnsemble:
+    """An ensemble of normalizing flows (inference on B200)."""
+
+    def __init__(
+        self,
+        data_columns: Sequence[str] = None,
+        bijector: Tuple[InitFunction, Bijector_Info] = None,
+        latent: distributions.LatentDist = None,
+        conditional_columns: Sequence[str] = None,
+        data_error_model: Callable = None,
+        condition_error_model: Callable = None,
+        autoscale_conditions: bool = True,
+        N: int = 1,
+        info: Any = None,
+        file: str = None,
+    ) -> None:
+        # validate parameters (pzflow/flowEnsemble.py:108-133)
+        if data_columns is None and bijector is None and file is None:
+            raise ValueError("You must provide data_columns and bijector OR file.")
+        if file is not None and any((data_columns is not None, bijector is not None,
+                                     conditional_columns is not None, latent is not None,
+                                     data_error_model is not None, condition_error_model is not None,
+                                     info is not None)):
+            raise ValueError("If providing a file, please do not provide any other parameters.")
+
+        if file is not None:
+            save_dict = _load_pickle(file)
+            c = save_dict.pop("class")
+            if c != self.__class__.__name__:
+                raise TypeError(f"This save file isn't a {self.__class__.__name__}. It is a {c}.")
+            self._ensemble = {name: Flow(_dictionary=flow_dict)
+                              for name, flow_dict in save_dict["ensemble"].items()}
+            self.data_columns = save_dict["data_columns"]
+            self.conditional_columns = save_dict["conditional_columns"]
+            self.data_error_model = save_dict["data_error_model"]
+            self.condition_error_model = save_dict["condition_error_model"]
+            self.info = save_dict["info"]
+            self._latent_info = save_dict["latent_info"]
+            self.latent = getattr(distributions, self._latent_info[0])(*self._latent_info[1])
+        else:
+            self._ensemble = {
+                f"Flow {i}": Flow(data_columns=data_columns, bijector=bijector,
+                                  conditional_columns=conditional_columns, latent=latent,
+                                  data_error_model=data_error_model,
+                                  condition_error_model=condition_error_model,
+                                  autoscale_conditions=autoscale_conditions, seed=i, info=f"Flow {i}")
+                for i in range(N)
+            }
+            self.data_columns = data_columns
+            self.conditional_columns = conditional_columns
+            self.latent = self._ensemble["Flow 0"].latent
+            self.data_error_model = data_error_model
+            self.condition_error_model = condition_error_model
+            self.info = info
+
+    # ------------------------------------------------------------------ #
+    def log_prob(self, inputs: pd.DataFrame, err_samples: int = None, seed: int = None,
+                 returnEnsemble: bool = False) -> np.ndarray:
+        """log probability density, [N] or [N, n_flows] (pzflow/flowEnsemble.py:189-243)."""
+        if err_samples is not None:
+            raise NotImplementedError("err_samples is a next-round row of the B200 hot path (SURVEY.md §8f-1)")
+        flows = list(self._ensemble.values())
+        columns = list(flows[0].data_columns)
+        X = None
+        lps = []
+        for flow in flows:
+            flow._check_bijector()
+            plan = flow._plan()
+            if X is None:  # one host->device copy of the rows, shared by every flow
+                X = torch.from_numpy(inputs[columns].to_numpy().astype(np.float32, copy=False)).to(plan.device)
+            lps.append(flow._log_prob(flow._params, X, flow._get_conditions(inputs)))
+        ensemble = torch.stack(lps, dim=0)  # [n_flows, N]
+        if returnEnsemble:
+            return ensemble.t().contiguous().cpu().numpy()
+        return ensemble_logmeanexp(ensemble).cpu().numpy()
+
+    def posterior(self, inputs: pd.DataFrame, column: str, grid, marg_rules: dict = None,
+                  normalize: bool = True, err_samples: int = None, seed: int = None,
+                  batch_size: int = None, returnEnsemble: bool = False,
+                  nan_to_zero: bool = True) -> np.ndarray:
+        """posterior pdfs, [N, G] or [N, n_flows, G] (pzflow/flowEnsemble.py:245-351)."""
+        grid = np.asarray(grid, dtype=np.float32).reshape(-1)
+        per_flow = [flow.posterior(inputs=inputs, column=column, grid=grid, marg_rules=marg_rules,
+                                   err_samples=err_samples, seed=seed, batch_size=batch_size,
+                                   normalize=False, nan_to_zero=nan_to_zero)
+                    for flow in self._ensemble.values()]
+        dev = next(iter(self._ensemble.values()))._plan().device
+        ensemble = torch.from_numpy(np.stack(per_flow, axis=0)).to(dev)  # [n_flows, N, G]
+        grid_t = torch.from_numpy(grid).to(dev)
+        if returnEnsemble:
+            nf, n, g = ensemble.shape
+            if normalize:
+                flat = ensemble.reshape(nf * n, g).contiguous()
+                normalize_pdfs_(flat, grid_t, True, False)
+                ensemble = flat.reshape(nf, n, g)
+            return ensemble.permute(1, 0, 2).contiguous().cpu().numpy()
+        return ensemble_posterior_mean(ensemble, grid_t, normalize).cpu().numpy()
+
+    def sample(self, nsamples: int = 1, conditions: pd.DataFrame = None, save_conditions: bool = True,
+               seed: int = None, returnEnsemble: bool = False) -> pd.DataFrame:
+        """samples from the ensemble (pzflow/flowEnsemble.py:353-471)."""
+        if returnEnsemble:
+            return pd.concat([flow.sample(nsamples, conditions, save_conditions, seed)
+                              for flow in self._ensemble.values()], keys=self._ensemble.keys())
+        if conditions is None:
+            N = int(np.ceil(nsamples / len(self._ensemble)))
+            samples = pd.concat([flow.sample(N, conditions, save_conditions, seed)
+                                 for flow in self._ensemble.values()])
+            return samples.sample(nsamples, random_state=seed).reset_index(drop=True)
+        if nsamples > 1:
+            conditions = pd.concat([conditions] * nsamples)
+        seed = np.random.randint(1e18) if seed is None else seed
+        if conditions.shape[0] > len(self._ensemble):
+            conditions_shuffled = conditions.sample(frac=1.0, random_state=int(seed / 1e9))
+            n = len(self._ensemble)
+            chunks = [conditions_shuffled.iloc[idx] for idx in
+                      np.array_split(np.arange(conditions_shuffled.shape[0]), n)]
+            order = np.random.default_rng(seed).permutation(len(chunks))
+            chunks = [chunks[i] for i in order]
+            return pd.concat([flow.sample(1, chunk, save_conditions, seed).set_index(chunk.index)
+                              for flow, chunk in zip(self._ensemble.values(), chunks)]).sort_index()
+        rng = np.random.default_rng(seed)
+        flows = rng.choice(list(self._ensemble.values()), size=conditions.shape[0], replace=True)
+        seeds = rng.integers(1e18, size=conditions.shape[0])
+        return pd.concat([flow.sample(1, conditions[i:i + 1], save_conditions, int(new_seed))
+                          for i, (flow, new_seed) in enumerate(zip(flows, seeds))]).set_index(conditions.index)
+
+    # ------------------------------------------------------------------ #
+    def save(self, file: str) -> None:
+        """Saves the ensemble to a file (pzflow/flowEnsemble.py:473-505)."""
+        save_dict = {
+            "data_columns": self.data_columns,
+            "conditional_columns": self.conditional_columns,
+            "latent_info": self.latent.info,
+            "data_error_model": self.data_error_model,
+            "condition_error_model": self.condition_error_model,
+            "info": self.info,
+            "class": self.__class__.__name__,
+            "ensemble": {name: flow._save_dict() for name, flow in self._ensemble.items()},
+        }
+        with open(file, "wb") as handle:
+            pickle.dump(save_dict, handle, recurse=True)
+
+    def train(self, *args, **kwargs):
+        """Training (pzflow/flowEnsemble.py:507-609) is outside the B200 hot path."""
+        raise NotImplementedError("FlowEnsemble.train is outside the B200 inference hot path")

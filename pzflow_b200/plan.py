@@ -1,0 +1,281 @@
+"""Plan compiler: Bijector_Info + params pytree -> device plan (pzb_plan).
+
+Walks the nested ``("Name", (args...))`` tuples the reference stores in
+``Flow._bijector_info`` (pzflow/bijectors.py:12-13, rebuilt by
+pzflow/utils.py:11-19) in lock-step with the params pytree
+(``[stage_params, ...]`` per Chain, stax ``[(W, b), (), ...]`` per
+NeuralSplineCoupling; pzflow/bijectors.py:146-153, pzflow/utils.py:45-48) and
+flattens them into the ``pzb_stage_desc`` list ``pzb_plan_create`` takes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+HOT_PATH_BIJECTORS = ("Chain", "NeuralSplineCoupling", "Roll", "ShiftBounds", "StandardScaler")
+LATENTS = {"Uniform": N.LATENT_UNIFORM, "CentBeta13": N.LATENT_CENTBETA13}
+
+
+def _f32(a) -> np.ndarray:
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def flatten(info: Tuple[str, tuple], params: Any, input_dim: int) -> List[dict]:
+    """Flatten (Bijector_Info, params) into stage dictionaries, Chains bracketed."""
+    name, args = info
+    if name == "Chain":
+        if len(params) != len(args):
+            raise ValueError("Chain params do not match its Bijector_Info")
+        out = [dict(kind=N.STAGE_CHAIN_BEGIN)]
+        for sub, p in zip(args, params):
+            out += flatten(sub, p, input_dim)
+        out.append(dict(kind=N.STAGE_CHAIN_END))
+        return out
+    if name == "Roll":
+        (shift,) = args
+        return [dict(kind=N.STAGE_ROLL, shift=int(shift))]
+    if name == "ShiftBounds":
+        mn, mx = np.atleast_1d(_f32(args[0])), np.atleast_1d(_f32(args[1]))
+        B = float(args[2]) if len(args) > 2 else 5.0
+        if len(mn) != len(mx):
+            raise ValueError("Lengths of min and max do not match. Please provide either a single "
+                             "min and max, or a min and max for each dimension.")
+        return [dict(kind=N.STAGE_SHIFT_BOUNDS, vec_a=mn, vec_b=mx, B=B)]
+    if name == "StandardScaler":
+        return [dict(kind=N.STAGE_STANDARD_SCALER, vec_a=np.atleast_1d(_f32(args[0])),
+                     vec_b=np.atleast_1d(_f32(args[1])), B=0.0)]
+    if name == "NeuralSplineCoupling":
+        full = tuple(args) + (16, 5, 2, 128, None, 0, False)[len(args):]
+        K, B, hidden_layers, hidden_dim, transformed_dim, n_conditions, periodic = full
+        weights = []
+        for layer in params:
+            if len(layer) == 0:
+                continue
+            W, b = layer
+            weights += [_f32(W), _f32(b)]
+        if len(weights) != 2 * (hidden_layers + 1):
+            raise ValueError("NeuralSplineCoupling params do not match hidden_layers")
+        lower = input_dim - input_dim // 2 if transformed_dim is None else int(transformed_dim)
+        upper = input_dim - lower
+        dims = [upper + n_conditions] + [hidden_dim] * hidden_layers + \
+               [(3 * K - 1 + int(bool(periodic))) * lower]
+        for i in range(hidden_layers + 1):
+            if weights[2 * i].shape != (dims[i], dims[i + 1]) or weights[2 * i + 1].shape != (dims[i + 1],):
+                raise ValueError(
+                    f"NeuralSplineCoupling layer {i}: expected W{(dims[i], dims[i + 1])}, "
+                    f"got W{weights[2 * i].shape}, b{weights[2 * i + 1].shape}")
+        return [dict(kind=N.STAGE_NSC, K=int(K), B=float(B), hidden_layers=int(hidden_layers),
+                     hidden_dim=int(hidden_dim),
+                     transformed_dim=-1 if transformed_dim is None else int(transformed_dim),
+                     n_conditions=int(n_conditions), periodic=int(bool(periodic)), weights=weights)]
+    raise NotImplementedError(
+        f"bijector {name!r} is outside the B200 hot path (supported: {', '.join(HOT_PATH_BIJECTORS)})")
+
+
+def params_fingerprint(params: Any) -> tuple:
+    """Identity of every leaf array: the plan is rebuilt when Flow._params changes."""
+    if isinstance(params, (list, tuple)):
+        return tuple(params_fingerprint(p) for p in params)
+    return (id(params),)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Plan:
+    """One compiled chain + latent on one CUDA device."""
+
+    def __init__(self, bijector_info, bijector_params, input_dim: int,
+                 latent_info=("Uniform", (None, 5)), device: Optional[int] = None):
+        lib = N.lib()
+        if lib.pzb_device_count() <= 0 or not torch.cuda.is_available():
+            raise N.NativeError("pzflow_b200 needs a CUDA device: there is no CPU fallback")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        latent_name, latent_args = latent_info
+        if latent_name not in LATENTS:
+            raise NotImplementedError(
+                f"latent {latent_name!r} is outside the B200 hot path (supported: {', '.join(LATENTS)})")
+        latent_B = float(latent_args[1]) if len(latent_args) > 1 else 5.0
+        stages = flatten(bijector_info, bijector_params, input_dim)
+        self._keep = []  # host arrays the descriptors point into (until plan_create returns)
+        descs = (N.StageDesc * max(1, len(stages)))()
+        for d, st in zip(descs, stages):
+            d.kind = st["kind"]
+            d.shift = st.get("shift", 0)
+            d.B = st.get("B", 0.0)
+            for f in ("K", "hidden_layers", "hidden_dim", "transformed_dim", "n_conditions", "periodic"):
+                setattr(d, f, st.get(f, 0))
+            if "vec_a" in st:
+                a, b = st["vec_a"], st["vec_b"]
+                self._keep += [a, b]
+                d.vec_a = a.ctypes.data_as(N.c_float_p)
+                d.vec_b = b.ctypes.data_as(N.c_float_p)
+                d.n_vec = len(a)
+            if "weights" in st:
+                arr = (N.c_float_p * len(st["weights"]))()
+                for i, w in enumerate(st["weights"]):
+                    arr[i] = w.ctypes.data_as(N.c_float_p)
+                self._keep += st["weights"] + [arr]
+                d.weights = C.cast(arr, C.POINTER(N.c_float_p))
+        handle = C.c_void_p()
+        N.check(lib.pzb_plan_create(descs, len(stages), int(input_dim), LATENTS[latent_name],
+                                    latent_B, self.device_index, C.byref(handle)))
+        self._keep = []
+        self._h = handle
+        self.input_dim = int(input_dim)
+        self.n_conditions = lib.pzb_plan_n_conditions(handle)
+        self.n_spline_dims = lib.pzb_plan_n_spline_dims(handle)
+        self.flops_per_row = lib.pzb_plan_flops_per_row(handle)
+        self.tc_supported = bool(lib.pzb_plan_tc_supported(handle))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                N.lib().pzb_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- engine selection -------------------------------------------------
+    def set_engine(self, engine: str) -> None:
+        code = {"auto": N.ENGINE_AUTO, "simt": N.ENGINE_SIMT, "tc": N.ENGINE_TC}[engine]
+        N.check(N.lib().pzb_plan_set_engine(self._h, code))
+
+    @property
+    def engine(self) -> str:
+        return {N.ENGINE_SIMT: "simt", N.ENGINE_TC: "tc"}[N.lib().pzb_plan_engine(self._h)]
+
+    # ---- tensor plumbing --------------------------------------------------
+    def _rows(self, X, width: int, what: str) -> torch.Tensor:
+        t = torch.as_tensor(X) if not isinstance(X, torch.Tensor) else X
+        if t.dim() != 2 or t.shape[1] != width:
+            raise ValueError(f"{what} must have shape [N, {width}], got {tuple(t.shape)}")
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _cond(self, cond, n_rows: int) -> Optional[torch.Tensor]:
+        if self.n_conditions == 0:
+            return None  # the reference's zeros[N, 1] dummy is sliced away (bijectors.py:481-483)
+        if cond is None:
+            raise ValueError(f"this bijector is conditional: conditions [N, {self.n_conditions}] are required")
+        t = torch.as_tensor(cond) if not isinstance(cond, torch.Tensor) else cond
+        if t.dim() != 2 or t.shape[0] != n_rows or t.shape[1] < self.n_conditions:
+            raise ValueError(f"conditions must have shape [{n_rows}, {self.n_conditions}], got {tuple(t.shape)}")
+        t = t[:, : self.n_conditions]
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    # ---- entry points (all asynchronous on torch's current stream) -------
+    def log_prob(self, X, cond=None, return_bins: bool = False):
+        """Flow._log_prob (pzflow/flow.py:397-407) on device tensors."""
+        X = self._rows(X, self.input_dim, "inputs")
+        cond = self._cond(cond, X.shape[0])
+        out = torch.empty(X.shape[0], dtype=torch.float32, device=self.device)
+        bins = (torch.empty((X.shape[0], self.n_spline_dims), dtype=torch.int32, device=self.device)
+                if return_bins else None)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().pzb_log_prob(self._h, _ptr(X), _ptr(cond), X.shape[0], _ptr(out), _ptr(bins),
+                                         _stream(self.device)))
+        return (out, bins) if return_bins else out
+
+    def forward(self, X, cond=None, return_bins: bool = False):
+        """Chain ForwardFunction (pzflow/bijectors.py:162-164): (u, log_det)."""
+        X = self._rows(X, self.input_dim, "inputs")
+        cond = self._cond(cond, X.shape[0])
+        U = torch.empty_like(X)
+        ld = torch.empty(X.shape[0], dtype=torch.float32, device=self.device)
+        bins = (torch.empty((X.shape[0], self.n_spline_dims), dtype=torch.int32, device=self.device)
+                if return_bins else None)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().pzb_forward(self._h, _ptr(X), _ptr(cond), X.shape[0], _ptr(U), _ptr(ld),
+                                        _ptr(bins), _stream(self.device)))
+        return (U, ld, bins) if return_bins else (U, ld)
+
+    def inverse(self, U, cond=None, return_bins: bool = False, want_log_det: bool = True):
+        """Chain InverseFunction (pzflow/bijectors.py:166-170): (x, log_det)."""
+        U = self._rows(U, self.input_dim, "inputs")
+        cond = self._cond(cond, U.shape[0])
+        X = torch.empty_like(U)
+        ld = torch.empty(U.shape[0], dtype=torch.float32, device=self.device) if want_log_det else None
+        bins = (torch.empty((U.shape[0], self.n_spline_dims), dtype=torch.int32, device=self.device)
+                if return_bins else None)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().pzb_inverse(self._h, _ptr(U), _ptr(cond), U.shape[0], _ptr(X), _ptr(ld),
+                                        _ptr(bins), _stream(self.device)))
+        return (X, ld, bins) if return_bins else (X, ld)
+
+    def posterior(self, rest, col_idx: int, grid, cond=None, normalize: bool = True,
+                  nan_to_zero: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Flow.posterior main loop (pzflow/flow.py:666-738) without materialising the
+        [Ng*G, D] expansion: rest [Ng, D-1], grid [G] -> pdfs [Ng, G]."""
+        rest = self._rows(rest, self.input_dim - 1, "inputs")
+        cond = self._cond(cond, rest.shape[0])
+        grid = torch.as_tensor(grid).to(device=self.device, dtype=torch.float32).contiguous().reshape(-1)
+        Ng, G = rest.shape[0], grid.numel()
+        if out is None:
+            out = torch.empty((Ng, G), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().pzb_posterior(self._h, _ptr(rest), _ptr(cond), Ng, int(col_idx), _ptr(grid), G,
+                                          int(bool(normalize)), int(bool(nan_to_zero)), _ptr(out),
+                                          _stream(self.device)))
+        return out
+
+
+# ---- reductions that are not tied to one plan ---------------------------------
+def ensemble_logmeanexp(lp: torch.Tensor) -> torch.Tensor:
+    """log(mean(exp(lp), axis=flows)) for lp [n_flows, N] (pzflow/flowEnsemble.py:243)."""
+    lp = lp.contiguous()
+    out = torch.empty(lp.shape[1], dtype=torch.float32, device=lp.device)
+    with torch.cuda.device(lp.device):
+        N.check(N.lib().pzb_ensemble_logmeanexp(_ptr(lp), lp.shape[0], lp.shape[1], _ptr(out),
+                                                _stream(lp.device)))
+    return out
+
+
+def ensemble_posterior_mean(pdfs: torch.Tensor, grid: torch.Tensor, normalize: bool) -> torch.Tensor:
+    """mean over flows of pdfs [n_flows, Ng, G], then trapezoid-normalise
+    (pzflow/flowEnsemble.py:346-351)."""
+    pdfs = pdfs.contiguous()
+    grid = grid.to(device=pdfs.device, dtype=torch.float32).contiguous()
+    out = torch.empty(pdfs.shape[1:], dtype=torch.float32, device=pdfs.device)
+    with torch.cuda.device(pdfs.device):
+        N.check(N.lib().pzb_ensemble_posterior_mean(_ptr(pdfs), pdfs.shape[0], pdfs.shape[1], pdfs.shape[2],
+                                                    _ptr(grid), int(bool(normalize)), _ptr(out),
+                                                    _stream(pdfs.device)))
+    return out
+
+
+def normalize_pdfs_(pdfs: torch.Tensor, grid: torch.Tensor, normalize: bool, nan_to_zero: bool) -> torch.Tensor:
+    """In-place per-row trapezoid normalisation + NaN->0 of pdfs [Ng, G] (pzflow/flow.py:732-737)."""
+    assert pdfs.is_contiguous()
+    grid = grid.to(device=pdfs.device, dtype=torch.float32).contiguous()
+    with torch.cuda.device(pdfs.device):
+        N.check(N.lib().pzb_normalize_pdfs(_ptr(pdfs), pdfs.shape[0], pdfs.shape[1], _ptr(grid),
+                                           int(bool(normalize)), int(bool(nan_to_zero)), _stream(pdfs.device)))
+    return pdfs
+
+
+def sample_uniform(n: int, dim: int, B: float, seed: int, device=None) -> torch.Tensor:
+    """U(-B, B)^dim latent draws from the library's Philox stream (not jax's threefry)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((n, dim), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        N.check(N.lib().pzb_sample_uniform(_ptr(out), n, dim, float(B), int(seed) & (2 ** 64 - 1),
+                                           _stream(device)))
+    return out
+
+
+def launch_count() -> int:
+    return int(N.lib().pzb_launch_count())

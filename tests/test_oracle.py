@@ -1,0 +1,213 @@
+"""The oracle against (1) the reference's own code run over oracle/jax_shim (committed golden
+vectors), (2) the reference test-suite's properties, (3) the JAX-produced anchor in the docs."""
+import numpy as np
+import pytest
+
+from conftest import golden, zero_class
+from oracle import fixtures as F
+from oracle import nsf_oracle as O
+
+TIGHT = dict(rtol=2e-6, atol=2e-6)  # same primitives, same order: only ulp-level slack
+
+
+def _close(a, b, **kw):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    za, zb = zero_class(a), zero_class(b)
+    assert (za == zb).all()
+    np.testing.assert_allclose(a[~za], b[~zb], **(kw or TIGHT))
+
+
+# --------------------------------------------------------------------------- #
+# (1) golden vectors produced by the reference's code                          #
+# --------------------------------------------------------------------------- #
+def test_example_flow_golden():
+    z = golden("ref_shim_example_flow.npz")
+    ex = F.example_flow()
+    bi, li, p = ex["bijector_info"], ex["latent_info"], ex["params"]
+    X, U = z["X"], z["U"]
+    _close(O.flow_log_prob(bi, li, p, X), z["log_prob"])
+    u, ld = O.apply_bijector(bi, p[1], X, np.zeros((len(X), 1), np.float32))
+    _close(u, z["forward_u"])
+    _close(ld, z["forward_ld"])
+    x, ldi = O.flow_inverse(bi, p, U)
+    _close(x, z["inverse_x"])
+    _close(ldi, z["inverse_ld"])
+    rest = np.ascontiguousarray(X[:24, 1:])
+    _close(O.flow_posterior(bi, li, p, rest, 0, z["grid"]), z["posterior"])
+    _close(O.flow_posterior(bi, li, p, rest, 0, z["grid"], batch_size=7), z["posterior_batched"])
+    _close(O.flow_posterior(bi, li, p, rest, 0, z["grid"], normalize=False, nan_to_zero=False),
+           z["posterior_unnorm"])
+    rest_r = np.ascontiguousarray(np.delete(X[:24], 3, axis=1))
+    _close(O.flow_posterior(bi, li, p, rest_r, 3, z["grid_r"]), z["posterior_r"])
+    # edge rows really exercise the edge paths
+    assert zero_class(z["log_prob"])[[2, 3]].all()  # far out of bounds / NaN input -> zero probability
+    assert not zero_class(z["log_prob"])[4]
+
+
+def test_bijector_battery_golden():
+    """Hot-path rows of the reference's tests/test_bijectors.py:16-51 on its fixed 3x7 input."""
+    z = golden("ref_shim_bijectors.npz")
+    x = z["x"]
+    for name in z["names"]:
+        name = str(name)
+        info = F.unpack_tree(f"{name}_info", z)
+        params = F.unpack_tree(f"{name}_params", z)
+        cond = z[f"{name}_cond"]
+        y, ld = O.apply_bijector(info, params, x, cond)
+        _close(y, z[f"{name}_fwd"])
+        _close(ld, z[f"{name}_fwd_ld"])
+        xi, ldi = O.apply_bijector(info, params, y, cond, inverse=True)
+        _close(xi, z[f"{name}_inv_of_fwd"])
+        _close(ldi, z[f"{name}_inv_of_fwd_ld"])
+        xi2, ldi2 = O.apply_bijector(info, params, x, cond, inverse=True)
+        _close(xi2, z[f"{name}_inv"])
+        _close(ldi2, z[f"{name}_inv_ld"])
+        # the reference's own assertions (tests/test_bijectors.py:71-86); its atol of 1e-6 is a few
+        # float32 ulps of these log-dets (|ld| up to ~5), so NumPy-vs-XLA primitive noise gets 4 ulps
+        assert y.shape == x.shape and ld.shape == x.shape[:1]
+        np.testing.assert_allclose(xi, x, atol=2e-6, err_msg=name)
+        np.testing.assert_allclose(ld, -ldi, atol=4e-6, err_msg=name)
+
+
+def test_default_flow_and_ensemble_golden():
+    z = golden("ref_shim_default_flows.npz")
+    # C1: default 2-D flow, CentBeta13(2, 5)
+    info, bp = F.unpack_tree("c1_info", z), F.unpack_tree("c1_params", z)
+    li, p = ("CentBeta13", (2, 5)), ((), bp)
+    X = z["c1_X"]
+    _close(O.flow_log_prob(info, li, p, X), z["c1_log_prob"])
+    # pdf = exp(lp): an ulp of lp (|lp| ~ 5) is a few 1e-6 relative on the pdf
+    _close(O.flow_posterior(info, li, p, X[:32, 1:], 0, z["c1_grid"]), z["c1_posterior_x"], rtol=1e-5, atol=1e-7)
+    _close(O.flow_posterior(info, li, p, X[:32, :1], 1, z["c1_grid"], normalize=False), z["c1_posterior_y"],
+           rtol=1e-5, atol=1e-7)
+    _close(O.flow_inverse(info, p, z["c1_sample_u"])[0], z["c1_sample_x"])
+    # conditional ensemble (flowEnsemble.py:227-243, 317-351; flow.py:324-337)
+    cols = [str(c) for c in z["ens_columns"]]
+    df = z["ens_df"]
+    Xd = df[:, :3].astype(np.float32)
+    cond = ((df[:, 3:].astype(np.float32) - z["ens_cond_means"]) / z["ens_cond_stds"]).astype(np.float32)
+    assert cols == ["a", "b", "c", "p", "q"]
+    flows = [(F.unpack_tree(f"ens{i}_info", z), ("CentBeta13", (3, 5)), ((), F.unpack_tree(f"ens{i}_params", z)))
+             for i in range(3)]
+    _close(O.flow_log_prob(*flows[0], Xd, cond), z["ens_flow0_log_prob"])
+    _close(O.ensemble_log_prob(flows, Xd, cond), z["ens_log_prob"])
+    _close(O.ensemble_log_prob(flows, Xd, cond, return_ensemble=True), z["ens_log_prob_all"])
+    g = z["ens_grid"]
+    _close(O.ensemble_posterior(flows, Xd[:20, 1:], 0, g, cond[:20]), z["ens_posterior"], rtol=1e-5, atol=1e-6)
+    _close(O.ensemble_posterior(flows, Xd[:20, 1:], 0, g, cond[:20], return_ensemble=True),
+           z["ens_posterior_all"], rtol=1e-5, atol=1e-6)
+    _close(O.flow_posterior(*flows[0], np.delete(Xd[:20], 1, axis=1), 1, g, cond[:20]),
+           z["ens_flow0_posterior_b"], rtol=1e-5, atol=1e-6)
+    _close(O.flow_inverse(flows[0][0], flows[0][2], z["ens_sample_u"], z["ens_sample_cond"])[0],
+           z["ens_sample_x"])
+
+
+# --------------------------------------------------------------------------- #
+# (2) properties the reference's tests assert                                  #
+# --------------------------------------------------------------------------- #
+X37 = np.array([[0.2, 0.1, -0.3, 0.5, 0.1, -0.4, -0.3],
+                [0.6, 0.5, 0.2, 0.2, -0.4, -0.1, 0.7],
+                [0.9, 0.2, -0.3, 0.3, 0.4, -0.4, -0.1]], np.float32)
+
+
+@pytest.mark.parametrize("info,cond", [
+    (("NeuralSplineCoupling", (16, 5, 2, 128, None, 0, False)), np.zeros((3, 1), np.float32)),
+    (("NeuralSplineCoupling", (16, 3, 2, 128, 3, 3, False)), np.arange(9, dtype=np.float32).reshape(3, 3)),
+    (F.rolling_info(2), np.zeros((3, 1), np.float32)),
+    (F.rolling_info(2, 1, 16, 3, 2, 128, None, 0, True), np.zeros((3, 1), np.float32)),
+    (("ShiftBounds", (-0.5, 0.9, 5)), np.zeros((3, 1), np.float32)),
+    (("ShiftBounds", (-np.ones(7, np.float32), 1.1 * np.ones(7, np.float32), 3)), np.zeros((3, 1), np.float32)),
+    (("StandardScaler", (np.linspace(-1, 1, 7), np.linspace(1, 8, 7))), np.zeros((3, 1), np.float32)),
+    (("Roll", (2,)), np.zeros((3, 1), np.float32)),
+])
+def test_bijective_and_logdet_antisymmetric(info, cond):
+    """tests/test_bijectors.py:53-86: shapes, inverse(forward(x)) == x and fwd_ld == -inv_ld at atol 1e-6."""
+    params = O.synth_bijector_params(info, 7, np.random.default_rng(0))
+    y, ld = O.apply_bijector(info, params, X37, cond)
+    assert y.shape == X37.shape and ld.shape == (3,)
+    xi, ldi = O.apply_bijector(info, params, y, cond, inverse=True)
+    # the reference asserts atol 1e-6 under XLA; NumPy primitives get 4 float32 ulps of |ld| ~ 2
+    np.testing.assert_allclose(xi, X37, atol=2e-6)
+    np.testing.assert_allclose(ld, -ldi, atol=4e-6)
+
+
+def test_batched_posterior_equals_unbatched():
+    """tests/test_flow.py:275-287."""
+    ex = F.example_flow()
+    X = F.galaxy_rows(12, seed=3, oob_frac=0)
+    grid = np.linspace(0, 2.3, 30).astype(np.float32)
+    a = O.flow_posterior(ex["bijector_info"], ex["latent_info"], ex["params"], X[:, 1:], 0, grid)
+    b = O.flow_posterior(ex["bijector_info"], ex["latent_info"], ex["params"], X[:, 1:], 0, grid, batch_size=5)
+    np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-5)  # different GEMM shapes -> fp32 noise floor
+    np.testing.assert_allclose(O.trapezoid(a, grid), 1.0, rtol=1e-5)
+
+
+def test_ensemble_rules():
+    """tests/test_ensemble.py:20-56: column i == flow i; log(mean(exp)); mean then normalise."""
+    flows = [(c["bijector_info"], c["latent_info"], c["params"]) for c in F.config_c4(3)]
+    rng = np.random.default_rng(0)
+    ex = F.example_flow()
+    mins, maxs = ex["bijector_info"][1][0][1][0], ex["bijector_info"][1][0][1][1]
+    X = rng.uniform(mins, maxs, size=(40, 7)).astype(np.float32)
+    cond = rng.normal(size=(40, 2)).astype(np.float32)
+    ens = O.ensemble_log_prob(flows, X, cond, return_ensemble=True)
+    assert ens.shape == (40, 3)
+    for i, fl in enumerate(flows):
+        np.testing.assert_array_equal(ens[:, i], O.flow_log_prob(*fl, X, cond))
+    np.testing.assert_allclose(O.ensemble_log_prob(flows, X, cond), np.log(np.exp(ens).mean(axis=1)), rtol=1e-6)
+    grid = np.linspace(0, 2.3, 20).astype(np.float32)
+    per = np.stack([O.flow_posterior(*fl, X[:8, 1:], 0, grid, cond[:8], normalize=False) for fl in flows], 1)
+    mean = per.mean(axis=1)
+    np.testing.assert_allclose(O.ensemble_posterior(flows, X[:8, 1:], 0, grid, cond[:8]),
+                               mean / O.trapezoid(mean, grid)[:, None], rtol=1e-5)
+
+
+# --------------------------------------------------------------------------- #
+# (3) the JAX-produced anchor + edge semantics                                 #
+# --------------------------------------------------------------------------- #
+def test_notebook_samples_anchor():
+    """docs/tutorials/marginalization.ipynb:133-135 prints two samples drawn by the real JAX
+    reference from the shipped flow: they must map into the Uniform(7,5) support, have finite
+    log_prob, and round-trip."""
+    ex = F.example_flow()
+    X = golden("ref_shim_example_flow.npz")["nb_X"]
+    u, _ = O.apply_bijector(ex["bijector_info"], ex["params"][1], X, np.zeros((2, 1), np.float32))
+    assert (np.abs(u) <= 5).all()
+    lp = O.flow_log_prob(ex["bijector_info"], ex["latent_info"], ex["params"], X)
+    np.testing.assert_allclose(lp, [5.4340, 6.7095], atol=2e-3)  # regression seed
+    xr, _ = O.flow_inverse(ex["bijector_info"], ex["params"], u)
+    np.testing.assert_allclose(xr, X, atol=2e-5)
+
+
+def test_spline_edge_semantics():
+    """utils.py:145-152, 177-178, 191-193: out-of-bounds identity per element with zero log-det
+    contribution; left-closed bins; NaN in -> zero probability (flow.py:406)."""
+    rng = np.random.default_rng(1)
+    K, B = 16, 5.0
+    W = O._softmax(rng.normal(size=(4, 3, K)).astype(np.float32)) * np.float32(2 * B)
+    H = O._softmax(rng.normal(size=(4, 3, K)).astype(np.float32)) * np.float32(2 * B)
+    D = O._softplus(rng.normal(size=(4, 3, K - 1)).astype(np.float32))
+    x = np.array([[-5.0, 0.3, 5.0], [7.0, -9.5, 4.999], [0.0, -4.999, 20.0], [1.0, 2.0, 3.0]], np.float32)
+    y, ld, idx = O.rational_quadratic_spline(x, W, H, D, B, return_idx=True)
+    oob = (x <= -B) | (x >= B)
+    np.testing.assert_array_equal(y[oob], x[oob])
+    assert np.isfinite(y).all() and np.isfinite(ld).all()
+    # x exactly on an interior knot goes to the bin on its right
+    xk = np.concatenate([np.full((4, 3, 1), -B, np.float32), -np.float32(B) + np.cumsum(W, -1, dtype=np.float32)], -1)
+    xon = xk[:, :, 5].copy()
+    _, _, idx_on = O.rational_quadratic_spline(xon, W, H, D, B, return_idx=True)
+    assert (idx_on == 5).all()
+    # rows that are entirely out of bounds have exactly zero log-det
+    y2, ld2 = O.rational_quadratic_spline(np.full((4, 3), 6.0, np.float32), W, H, D, B)
+    assert (ld2 == 0).all() and (y2 == 6.0).all()
+
+
+def test_nan_and_support_go_to_zero_probability():
+    ex = F.example_flow()
+    X = F.galaxy_rows(8, seed=2, oob_frac=0)
+    X[1, 2] = np.nan
+    X[2] = 1e3
+    lp = O.flow_log_prob(ex["bijector_info"], ex["latent_info"], ex["params"], X)
+    assert zero_class(lp)[[1, 2]].all() and np.isfinite(lp[[0, 3, 4]]).all()
+    assert lp[1] == np.finfo(np.float32).min  # jnp.nan_to_num(nan=-inf) then -inf -> finfo.min
