@@ -1,0 +1,53 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/*.h declares;
+the product path refuses to run without CUDA (no fallback, no oracle behind it)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pzflow_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pzb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from pzflow_b200 import _native
+    lib = _native.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/pzflow_b200.h but not exported"
+    assert sorted(_native.SIGNATURES) == declared, "ctypes SIGNATURES out of sync with the header"
+    assert lib.pzb_abi_version() == 1
+    assert isinstance(_native.last_error(), str)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pzflow_b200 import _native
+    from pzflow_b200.plan import Plan
+    lib = _native.lib()
+    assert lib.pzb_device_count() == 0
+    handle = ctypes.c_void_p()
+    desc = (_native.StageDesc * 1)()
+    rc = lib.pzb_plan_create(desc, 0, 2, _native.LATENT_UNIFORM, 5.0, 0, ctypes.byref(handle))
+    assert rc == _native.PZB_ERR_NO_DEVICE and "no CPU fallback" in _native.last_error()
+    with pytest.raises(_native.NativeError):
+        Plan(("Roll", (1,)), (), 3)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pzflow_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "nsf_oracle" not in src, f

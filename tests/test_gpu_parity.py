@@ -1,0 +1,428 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle and the committed golden
+vectors produced by the reference's own code.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from conftest import golden
+from oracle import fixtures as F
+from oracle import nsf_oracle as O
+from parity import (LP_UNDERFLOW, assert_noise_floor, assert_tolerance, count_bin_flips, summarize,
+                    within_tol, zero_class)
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["simt", "tc"]
+
+
+def _plan(cfg, engine):
+    from pzflow_b200.plan import Plan
+    plan = Plan(cfg["bijector_info"], cfg["params"][1], cfg["input_dim"], cfg["latent_info"])
+    if engine == "tc" and not plan.tc_supported:
+        pytest.skip("tensor-core engine does not support this shape")
+    plan.set_engine(engine)
+    assert plan.engine == engine
+    return plan
+
+
+def _o64(cfg):
+    return cfg["bijector_info"], cfg["latent_info"], O.cast_params(cfg["params"], np.float64)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# --------------------------------------------------------------------------- #
+# the shipped 7-D galaxy flow (configs 2/3): noise-floor gate + golden vectors  #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("engine", ENGINES)
+def test_example_flow_log_prob_noise_floor(engine):
+    ex = F.example_flow()
+    plan = _plan(ex, engine)
+    X = F.galaxy_rows(20000, seed=0)
+    ob = []
+    o32 = O.flow_log_prob(ex["bijector_info"], ex["latent_info"], ex["params"], X, bins=ob)
+    bi, li, p64 = _o64(ex)
+    o64 = O.flow_log_prob(bi, li, p64, X.astype(np.float64))
+    lp, bins = plan.log_prob(torch.from_numpy(X), return_bins=True)
+    s = assert_noise_floor(f"C2 log_prob [{engine}]", _np(lp), o32, o64, below=LP_UNDERFLOW)
+    assert s["frac_within_tol"] > 0.4  # reported, not the gate: see tests/parity.py
+    # bin indices: bit-exact except knot ties, which are counted
+    flips, rows, total = count_bin_flips(_np(bins), np.concatenate(ob, axis=1))
+    print(f"BINS [{engine}] flipped {flips} of {total} ({rows} rows)")
+    assert flips <= max(3, int(2e-4 * total))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_example_flow_against_reference_golden(engine):
+    """Golden vectors = the reference's own pzflow code (oracle/make_golden_shim.py)."""
+    z = golden("ref_shim_example_flow.npz")
+    ex = F.example_flow()
+    plan = _plan(ex, engine)
+    bi, li, p64 = _o64(ex)
+    X, U = z["X"], z["U"]
+    lp = _np(plan.log_prob(torch.from_numpy(X)))
+    assert_noise_floor(f"golden log_prob [{engine}]", lp, z["log_prob"],
+                       O.flow_log_prob(bi, li, p64, X.astype(np.float64)), ratio=2.0, max_class_mismatch=1,
+                       below=LP_UNDERFLOW)
+    assert zero_class(lp)[[2, 3]].all() and not zero_class(lp)[4]  # far out of bounds, NaN input
+    u, ld = plan.forward(torch.from_numpy(X))
+    u64, ld64 = O.apply_bijector(bi, p64[1], X.astype(np.float64), np.zeros((len(X), 1)))
+    ok = ~np.isnan(X).any(axis=1)
+    assert_noise_floor(f"golden forward u [{engine}]", _np(u)[ok], z["forward_u"][ok], u64[ok], ratio=2.0)
+    assert_noise_floor(f"golden forward ld [{engine}]", _np(ld)[ok], z["forward_ld"][ok], ld64[ok], ratio=2.0)
+    assert np.isnan(_np(u)[3]).any() and np.isnan(_np(ld)[3])
+    x, ldi = plan.inverse(torch.from_numpy(U))
+    x64, ldi64 = O.flow_inverse(bi, p64, U.astype(np.float64))
+    assert_noise_floor(f"golden inverse x [{engine}]", _np(x), z["inverse_x"], x64, ratio=2.0, slack=2e-5)
+    assert_noise_floor(f"golden inverse ld [{engine}]", _np(ldi), z["inverse_ld"], ldi64, ratio=2.0, slack=2e-5)
+    # out-of-bounds latent rows pass through the splines untouched: only ShiftBounds^-1 acts
+    mins, maxs = ex["bijector_info"][1][0][1][0], ex["bijector_info"][1][0][1][1]
+    np.testing.assert_allclose(_np(x)[2], 7.5 * (maxs - mins) / 2 / 4 + (maxs + mins) / 2, rtol=1e-6)
+    # posterior (normalised, batched == unbatched, un-normalised, another column)
+    rest = np.ascontiguousarray(X[:24, 1:])
+    grid = z["grid"]
+    pdf = _np(plan.posterior(torch.from_numpy(rest), 0, torch.from_numpy(grid)))
+    p64v = O.flow_posterior(bi, li, p64, rest.astype(np.float64), 0, grid.astype(np.float64))
+    assert_noise_floor(f"golden posterior [{engine}]", pdf, z["posterior"], p64v, ratio=2.0, slack=1e-5,
+                       max_class_mismatch=0)
+    np.testing.assert_allclose(O.trapezoid(pdf[pdf.sum(1) > 0], grid), 1.0, rtol=2e-6)
+    assert (pdf[3] == 0).all() and (z["posterior"][3] == 0).all()  # NaN input row -> all-zero pdf
+    un = _np(plan.posterior(torch.from_numpy(rest), 0, torch.from_numpy(grid), normalize=False, nan_to_zero=False))
+    un64 = O.flow_posterior(bi, li, p64, rest.astype(np.float64), 0, grid.astype(np.float64), normalize=False,
+                            nan_to_zero=False)
+    assert_noise_floor(f"golden posterior unnorm [{engine}]", un, z["posterior_unnorm"], un64, ratio=2.0,
+                       slack=1e-3, max_class_mismatch=0)
+    rest_r = np.ascontiguousarray(np.delete(X[:24], 3, axis=1))
+    pdf_r = _np(plan.posterior(torch.from_numpy(rest_r), 3, torch.from_numpy(z["grid_r"])))
+    p64r = O.flow_posterior(bi, li, p64, rest_r.astype(np.float64), 3, z["grid_r"].astype(np.float64))
+    assert_noise_floor(f"golden posterior col r [{engine}]", pdf_r, z["posterior_r"], p64r, ratio=2.0, slack=1e-5,
+                       max_class_mismatch=0)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_notebook_samples_anchor(engine):
+    """docs/tutorials/marginalization.ipynb:133-135 (real-JAX samples of the shipped flow)."""
+    ex = F.example_flow()
+    plan = _plan(ex, engine)
+    X = golden("ref_shim_example_flow.npz")["nb_X"]
+    u, _ = plan.forward(torch.from_numpy(X))
+    assert (_np(u).__abs__() <= 5).all()
+    np.testing.assert_allclose(_np(plan.log_prob(torch.from_numpy(X))), [5.4340, 6.7095], atol=2e-3)
+    np.testing.assert_allclose(_np(plan.inverse(u)[0]), X, atol=2e-5)
+
+
+# --------------------------------------------------------------------------- #
+# the reference's bijector battery (tests/test_bijectors.py) through the mirror #
+# --------------------------------------------------------------------------- #
+def test_bijector_battery_golden_through_protocol():
+    from pzflow_b200.utils import build_bijector_from_info
+    z = golden("ref_shim_bijectors.npz")
+    x = z["x"]
+    for name in z["names"]:
+        name = str(name)
+        info = F.unpack_tree(f"{name}_info", z)
+        params = F.unpack_tree(f"{name}_params", z)
+        cond = z[f"{name}_cond"]
+        init_fun, info2 = build_bijector_from_info(info)
+        _, fwd, inv = init_fun(0, 7)
+        y, ld = fwd(params, x, conditions=cond)
+        assert y.shape == x.shape and ld.shape == (3,)
+        assert_tolerance(f"battery {name} fwd", y, z[f"{name}_fwd"])
+        assert_tolerance(f"battery {name} fwd ld", ld, z[f"{name}_fwd_ld"])
+        xi, ldi = inv(params, y, conditions=cond)
+        # the reference's own property (tests/test_bijectors.py:71-86), in float32 ulps of the values
+        np.testing.assert_allclose(xi, x, atol=4e-6, err_msg=name)
+        np.testing.assert_allclose(ld, -ldi, atol=8e-6, err_msg=name)
+        xi2, ldi2 = inv(params, x, conditions=cond)
+        assert_tolerance(f"battery {name} inv", xi2, z[f"{name}_inv"])
+        assert_tolerance(f"battery {name} inv ld", ldi2, z[f"{name}_inv_ld"])
+
+
+# --------------------------------------------------------------------------- #
+# default 2-D flow (config 1) and the conditional ensemble (config 4) goldens   #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("engine", ENGINES)
+def test_two_moons_default_flow_golden(engine):
+    z = golden("ref_shim_default_flows.npz")
+    cfg = dict(bijector_info=F.unpack_tree("c1_info", z), latent_info=("CentBeta13", (2, 5)),
+               params=((), F.unpack_tree("c1_params", z)), input_dim=2)
+    plan = _plan(cfg, engine)
+    X = z["c1_X"]
+    bi, li, p64 = _o64(cfg)
+    lp = _np(plan.log_prob(torch.from_numpy(X)))
+    assert_noise_floor(f"C1 log_prob [{engine}]", lp, z["c1_log_prob"],
+                       O.flow_log_prob(bi, li, p64, X.astype(np.float64)), ratio=2.0, slack=5e-6,
+                       max_class_mismatch=0)
+    assert within_tol(lp, z["c1_log_prob"]).mean() > 0.98
+    g = z["c1_grid"]
+    px = _np(plan.posterior(torch.from_numpy(np.ascontiguousarray(X[:32, 1:])), 0, torch.from_numpy(g)))
+    assert_tolerance(f"C1 posterior x [{engine}]", px, z["c1_posterior_x"], min_frac=0.99)
+    py = _np(plan.posterior(torch.from_numpy(np.ascontiguousarray(X[:32, :1])), 1, torch.from_numpy(g),
+                            normalize=False))
+    assert_tolerance(f"C1 posterior y [{engine}]", py, z["c1_posterior_y"], min_frac=0.99)
+    xs = _np(plan.inverse(torch.from_numpy(z["c1_sample_u"]))[0])
+    assert_tolerance(f"C1 sample map [{engine}]", xs, z["c1_sample_x"], min_frac=0.995)
+
+
+def test_flow_and_ensemble_api_against_golden():
+    """Flow / FlowEnsemble mirrors called the way a pzflow user calls them (DataFrames in)."""
+    from pzflow_b200 import Flow, FlowEnsemble
+    from pzflow_b200 import bijectors as B
+    from pzflow_b200.utils import build_bijector_from_info
+    z = golden("ref_shim_default_flows.npz")
+    cols = [str(c) for c in z["ens_columns"]]
+    df = pd.DataFrame(z["ens_df"], columns=cols)
+    ens = FlowEnsemble(data_columns=("a", "b", "c"), conditional_columns=("p", "q"),
+                       bijector=B.RollingSplineCoupling(3, n_conditions=2), N=3)
+    for i, fl in enumerate(ens._ensemble.values()):
+        fl.set_bijector(build_bijector_from_info(F.unpack_tree(f"ens{i}_info", z)),
+                        params=F.unpack_tree(f"ens{i}_params", z))
+        fl._condition_means, fl._condition_stds = z["ens_cond_means"], z["ens_cond_stds"]
+    f0 = ens._ensemble["Flow 0"]
+    lp0 = f0.log_prob(df)
+    assert lp0.shape == (200,)
+    assert_tolerance("API flow0 log_prob", lp0, z["ens_flow0_log_prob"], min_frac=0.97)
+    allp = ens.log_prob(df, returnEnsemble=True)
+    assert allp.shape == (200, 3)
+    np.testing.assert_array_equal(allp[:, 0], lp0)  # tests/test_ensemble.py:20-27
+    assert_tolerance("API ensemble log_prob all", allp, z["ens_log_prob_all"], min_frac=0.97)
+    mean = ens.log_prob(df)
+    np.testing.assert_allclose(mean, np.log(np.exp(allp).mean(axis=1)), rtol=2e-6, atol=2e-6)  # test_ensemble.py:29-35
+    assert_tolerance("API ensemble log_prob", mean, z["ens_log_prob"], min_frac=0.97)
+    g = z["ens_grid"]
+    post = ens.posterior(df.iloc[:20], column="a", grid=g)
+    assert post.shape == (20, 25)
+    assert_tolerance("API ensemble posterior", post, z["ens_posterior"], min_frac=0.98)
+    post_all = ens.posterior(df.iloc[:20], column="a", grid=g, returnEnsemble=True)
+    assert post_all.shape == (20, 3, 25)
+    assert_tolerance("API ensemble posterior all", post_all, z["ens_posterior_all"], min_frac=0.98)
+    pb = f0.posterior(df.iloc[:20], column="b", grid=g)
+    assert_tolerance("API flow0 posterior b", pb, z["ens_flow0_posterior_b"], min_frac=0.98)
+    pb_batched = f0.posterior(df.iloc[:20], column="b", grid=g, batch_size=7)  # tests/test_flow.py:275-287
+    np.testing.assert_array_equal(pb, pb_batched)
+    # conditional sampling: the map u -> x (flow.py:787-795)
+    xs = f0._inverse(f0._params[1], z["ens_sample_u"], conditions=z["ens_sample_cond"])[0]
+    assert_tolerance("API conditional sample map", xs, z["ens_sample_x"], min_frac=0.99)
+    s = f0.sample(2, conditions=df.iloc[:10], seed=0)
+    assert s.shape == (20, 5) and list(s.columns) == cols
+    np.testing.assert_allclose(s[["p", "q"]].to_numpy(), np.repeat(df.iloc[:10][["p", "q"]].to_numpy(), 2, 0),
+                               rtol=1e-5)
+    s2 = f0.sample(2, conditions=df.iloc[:10], seed=0)
+    pd.testing.assert_frame_equal(s, s2)  # seed control, tests/test_flow.py:337-342
+    assert ens.sample(10, conditions=df.iloc[:4], seed=0).shape == (40, 5)
+    assert ens.sample(3, conditions=df.iloc[:2], seed=0, returnEnsemble=True).shape == (18, 5)
+
+
+def test_example_flow_through_flow_api(tmp_path):
+    """tests/test_examples.py:31-40 on the mirror: load, sample, log_prob, posterior."""
+    from pzflow_b200 import Flow
+    ex = F.example_flow()
+    d = {"class": "Flow", "data_columns": F.GALAXY_COLUMNS, "conditional_columns": None,
+         "condition_means": None, "condition_stds": None, "data_error_model": None,
+         "condition_error_model": None, "autoscale_conditions": True, "info": "example",
+         "latent_info": ex["latent_info"], "bijector_info": ex["bijector_info"], "params": ex["params"]}
+    flow = Flow(_dictionary=d)
+    samples = flow.sample(200, seed=0)
+    assert samples.shape == (200, 7) and list(samples.columns) == list(F.GALAXY_COLUMNS)
+    pd.testing.assert_frame_equal(samples, flow.sample(200, seed=0))
+    assert not samples.equals(flow.sample(200, seed=1))
+    lp = flow.log_prob(samples)
+    assert lp.shape == (200,) and np.isfinite(lp).all() and (lp > -50).all()
+    grid = np.arange(0, 2.5, 0.5)
+    pdfs = flow.posterior(samples, column="redshift", grid=grid)
+    assert pdfs.shape == (200, 5)
+    X = samples.to_numpy().astype(np.float32)
+    o32 = O.flow_log_prob(ex["bijector_info"], ex["latent_info"], ex["params"], X)
+    o64 = O.flow_log_prob(ex["bijector_info"], ex["latent_info"], O.cast_params(ex["params"], np.float64),
+                          X.astype(np.float64))
+    assert_noise_floor("API example log_prob", lp, o32, o64, ratio=2.5, max_class_mismatch=0, below=LP_UNDERFLOW)
+    # marginalisation rules run through the same fused posterior (flow.py:560-664)
+    flagged = samples.iloc[:6].copy()
+    flagged.iloc[1, 1] = 99.0
+    flagged.iloc[4, 1] = 99.0
+    rules = {"flag": 99, "u": lambda row: np.linspace(26, 31, 9)}
+    pm = flow.posterior(flagged, column="redshift", grid=grid, marg_rules=rules)
+    assert pm.shape == (6, 5) and np.isfinite(pm).all()
+    np.testing.assert_allclose(pm[[0, 2, 3, 5]], pdfs[[0, 2, 3, 5]], rtol=1e-5, atol=1e-7)
+
+
+# --------------------------------------------------------------------------- #
+# synthetic-parameter configs: conditional (4), 32-D (5), periodic / odd shapes #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("engine", ENGINES)
+def test_conditional_flow_c4(engine):
+    cfg = F.config_c4(1)[0]
+    plan = _plan(cfg, engine)
+    rng = np.random.default_rng(0)
+    ex = F.example_flow()
+    mins, maxs = ex["bijector_info"][1][0][1][0], ex["bijector_info"][1][0][1][1]
+    X = rng.uniform(mins - 0.05, maxs + 0.05, size=(8192, 7)).astype(np.float32)
+    cond = rng.normal(size=(8192, 2)).astype(np.float32)
+    bi, li, p64 = _o64(cfg)
+    ob = []
+    o32 = O.flow_log_prob(cfg["bijector_info"], cfg["latent_info"], cfg["params"], X, cond, bins=ob)
+    o64 = O.flow_log_prob(bi, li, p64, X.astype(np.float64), cond.astype(np.float64))
+    lp, bins = plan.log_prob(torch.from_numpy(X), torch.from_numpy(cond), return_bins=True)
+    assert_noise_floor(f"C4 log_prob [{engine}]", _np(lp), o32, o64, ratio=2.0, slack=5e-6, below=LP_UNDERFLOW)
+    assert within_tol(_np(lp), o32)[~zero_class(o32)].mean() > 0.99
+    flips, rows, total = count_bin_flips(_np(bins), np.concatenate(ob, axis=1))
+    print(f"BINS C4 [{engine}] flipped {flips} of {total}")
+    assert flips <= max(3, int(2e-4 * total))
+    with pytest.raises(ValueError):
+        plan.log_prob(torch.from_numpy(X))  # conditions are required (flow.py:777-780 analogue)
+
+
+def test_high_dim_c5_simt():
+    cfg = F.config_c5()
+    plan = _plan(cfg, "simt")
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, size=(1536, 32)).astype(np.float32)
+    X[:8] *= 1.3  # a few rows outside the ShiftBounds box -> out-of-bounds identity paths
+    bi, li, p64 = _o64(cfg)
+    o32 = O.flow_log_prob(cfg["bijector_info"], cfg["latent_info"], cfg["params"], X)
+    o64 = O.flow_log_prob(bi, li, p64, X.astype(np.float64))
+    lp = _np(plan.log_prob(torch.from_numpy(X)))
+    assert_noise_floor("C5 log_prob", lp, o32, o64, ratio=2.0, slack=1e-5, below=-1e4)
+    u32, ld32 = O.apply_bijector(cfg["bijector_info"], cfg["params"][1], X, np.zeros((len(X), 1), np.float32))
+    u64, _ = O.apply_bijector(bi, p64[1], X.astype(np.float64), np.zeros((len(X), 1)))
+    u, ld = plan.forward(torch.from_numpy(X))
+    assert_noise_floor("C5 forward u", _np(u), u32, u64, ratio=2.0, slack=2e-6)
+    x32, _ = O.flow_inverse(cfg["bijector_info"], cfg["params"], u32)
+    x64, _ = O.flow_inverse(bi, p64, u32.astype(np.float64))
+    xi = _np(plan.inverse(torch.from_numpy(u32))[0])
+    assert_noise_floor("C5 inverse x", xi, x32, x64, ratio=2.0, slack=2e-6)
+
+
+@pytest.mark.parametrize("info,D,C", [
+    (("Chain", (("StandardScaler", (np.linspace(-1, 1, 7).astype(np.float32), np.linspace(1, 8, 7).astype(np.float32))),
+                F.rolling_info(2, 1, 16, 3, 2, 128, None, 0, True),
+                ("NeuralSplineCoupling", (16, 3, 2, 128, 3, 3, False)))), 7, 3),   # periodic + transformed_dim + conditions
+    (("Chain", (("ShiftBounds", (-2.0, 2.0, 3.0)), F.rolling_info(3, 2, 5, 4, 1, 40))), 5, 0),  # odd K, 1 hidden layer, H=40
+    (F.rolling_info(2, 1, 8, 5, 3, 200, 1, 2), 4, 2),   # 3 hidden layers, H=200 (2 column chunks), L=1
+    (("NeuralSplineCoupling", (4, 5, 0, 16, None, 0, False)), 3, 0),  # no hidden layer at all
+    (("Chain", (F.rolling_info(1, 1, 16, 5, 2, 128, None, 3), )), 1, 3),  # D=1: U=0, key = conditions only
+])
+def test_odd_shapes_simt(info, D, C):
+    rng = np.random.default_rng(2)
+    params = O.synth_bijector_params(info, D, rng, out_scale=3.0)
+    p64 = O.cast_params(params, np.float64)
+    li = ("CentBeta13", (D, 5))
+    cfg = dict(bijector_info=info, latent_info=li, params=((), params), input_dim=D)
+    plan = _plan(cfg, "simt")
+    n = 777
+    X = rng.uniform(-6, 6, size=(n, D)).astype(np.float32)
+    cond = rng.normal(size=(n, max(C, 1))).astype(np.float32) if C else np.zeros((n, 1), np.float32)
+    ct = torch.from_numpy(cond) if C else None
+    kw = dict(ratio=2.0, slack=1e-5, max_class_mismatch=2)
+    o32 = O.flow_log_prob(info, li, ((), params), X, cond)
+    o64 = O.flow_log_prob(info, li, ((), p64), X.astype(np.float64), cond.astype(np.float64))
+    lp = _np(plan.log_prob(torch.from_numpy(X), ct))
+    assert_noise_floor(f"odd {info[0]} D={D} log_prob", lp, o32, o64, below=LP_UNDERFLOW, **kw)
+    assert within_tol(lp, o32)[~zero_class(o32, LP_UNDERFLOW) & ~zero_class(lp, LP_UNDERFLOW)].mean() > 0.97
+    u32, ld32 = O.apply_bijector(info, params, X, cond)
+    u64, ld64 = O.apply_bijector(info, p64, X.astype(np.float64), cond.astype(np.float64))
+    u, ld = plan.forward(torch.from_numpy(X), ct)
+    assert_noise_floor("odd forward u", _np(u), u32, u64, **kw)
+    assert_noise_floor("odd forward ld", _np(ld), ld32, ld64, **kw)
+    x32, ldi32 = O.apply_bijector(info, params, u32, cond, inverse=True)
+    x64, ldi64 = O.apply_bijector(info, p64, u32.astype(np.float64), cond.astype(np.float64), inverse=True)
+    xi, ldi = plan.inverse(torch.from_numpy(u32), ct)
+    assert_noise_floor("odd inverse x", _np(xi), x32, x64, **kw)
+    assert_noise_floor("odd inverse ld", _np(ldi), ldi32, ldi64, **kw)
+
+
+def test_empty_and_ragged_inputs():
+    ex = F.example_flow()
+    plan = _plan(ex, "simt")
+    assert plan.log_prob(torch.empty((0, 7))).shape == (0,)
+    assert plan.posterior(torch.empty((0, 6)), 0, torch.linspace(0, 2, 5)).shape == (0, 5)
+    X = F.galaxy_rows(130, seed=4, oob_frac=0)
+    full = _np(plan.log_prob(torch.from_numpy(X)))
+    for n in (1, 63, 64, 65, 129):  # row counts around the 64-row tile
+        np.testing.assert_array_equal(_np(plan.log_prob(torch.from_numpy(X[:n]))), full[:n])
+    with pytest.raises(ValueError):
+        plan.log_prob(torch.zeros((4, 6)))
+
+
+# --------------------------------------------------------------------------- #
+# BASELINE.json sizes: size-independent properties                             #
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("engine", ENGINES)
+def test_full_size_properties_c2(engine):
+    """10 M rows (config 2): determinism, shard independence (the multi-GPU partition computes
+    exactly what one GPU computes), round trip and log-det antisymmetry."""
+    from pzflow_b200.sharding import shard_rows
+    ex = F.example_flow()
+    plan = _plan(ex, engine)
+    base = torch.from_numpy(F.galaxy_rows(40000, seed=9))
+    n = 10_000_000
+    X = base.cuda().repeat(n // base.shape[0], 1).contiguous()
+    X += torch.linspace(0, 1e-3, X.shape[0], device="cuda")[:, None]  # make rows distinct
+    lp1 = plan.log_prob(X)
+    lp2 = plan.log_prob(X)
+    assert torch.equal(lp1, lp2)
+    for r in range(8):
+        a, b = shard_rows(n, r, 8)
+        assert torch.equal(plan.log_prob(X[a:b]), lp1[a:b])
+    u, ld = plan.forward(X[:2_000_000])
+    xr, ldi = plan.inverse(u)
+    inside = (u.abs() < 4.9).all(dim=1) & torch.isfinite(lp1[:2_000_000]) & (lp1[:2_000_000] > -30)
+    err = (xr - X[:2_000_000]).abs()[inside]
+    assert inside.float().mean() > 0.5
+    assert err.median() < 1e-5 and torch.quantile(err.flatten()[:4_000_000], 0.99) < 2e-3
+    asym = (ld + ldi).abs()[inside]
+    assert asym.median() < 1e-4
+    # the latent of the shipped flow is uniform: finite log_prob == log_det + const
+    fin = lp1[:2_000_000] > -1e30
+    assert torch.allclose(lp1[:2_000_000][fin], ld[fin] + (-7 * np.log(np.float32(10.0))), atol=1e-5)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_posterior_properties_c3_slice(engine):
+    """Config 3 geometry (G = 1000) on a slice of galaxies: every pdf integrates to one, equals
+    exp(log_prob) of the expanded rows, and is independent of how galaxies are batched."""
+    ex = F.example_flow()
+    plan = _plan(ex, engine)
+    X = F.galaxy_rows(2048, seed=5, oob_frac=0)
+    rest = torch.from_numpy(np.ascontiguousarray(X[:, 1:])).cuda()
+    grid = torch.linspace(0.0, 2.3, 1000)
+    pdf = plan.posterior(rest, 0, grid)
+    assert pdf.shape == (2048, 1000)
+    integ = 0.5 * ((grid[1:] - grid[:-1]).cuda() * (pdf[:, 1:] + pdf[:, :-1])).sum(1)
+    assert torch.allclose(integ, torch.ones_like(integ), rtol=3e-6)
+    assert torch.equal(pdf[100:900], plan.posterior(rest[100:900], 0, grid))
+    un = plan.posterior(rest[:64], 0, grid, normalize=False)
+    rows = torch.cat([grid.cuda().repeat(64)[:, None], rest[:64].repeat_interleave(1000, 0)], dim=1)
+    assert torch.equal(un.flatten(), torch.exp(plan.log_prob(rows)))
+
+
+def test_ensemble_reductions_match_oracle():
+    from pzflow_b200.plan import ensemble_logmeanexp, ensemble_posterior_mean
+    rng = np.random.default_rng(0)
+    lp = rng.normal(0, 30, size=(4, 5000)).astype(np.float32)
+    lp[:, :10] = -200.0  # all flows underflow -> -inf, the naive form (flowEnsemble.py:243)
+    lp[1, 20] = np.finfo(np.float32).min
+    with np.errstate(all="ignore"):
+        ref = np.log(np.exp(lp).mean(axis=0, dtype=np.float32))
+    out = _np(ensemble_logmeanexp(torch.from_numpy(lp).cuda()))
+    assert (np.isneginf(out) == np.isneginf(ref)).all() and np.isneginf(out[:10]).all()
+    fin = np.isfinite(ref)
+    np.testing.assert_allclose(out[fin], ref[fin], rtol=2e-6, atol=2e-6)
+    pd_ = rng.uniform(0, 3, size=(3, 40, 33)).astype(np.float32)
+    grid = np.sort(rng.uniform(0, 2, 33)).astype(np.float32)
+    mean = pd_.mean(axis=0)
+    want = mean / O.trapezoid(mean, grid)[:, None]
+    got = _np(ensemble_posterior_mean(torch.from_numpy(pd_).cuda(), torch.from_numpy(grid), True))
+    np.testing.assert_allclose(got, want, rtol=5e-6)
+
+
+def test_uniform_sampler():
+    from pzflow_b200.plan import sample_uniform
+    u = sample_uniform(200_000, 7, 5.0, seed=3)
+    assert u.shape == (200_000, 7) and float(u.min()) >= -5.0 and float(u.max()) < 5.0
+    assert abs(float(u.mean())) < 0.02 and abs(float(u.std()) - 10 / np.sqrt(12)) < 0.02
+    assert torch.equal(u, sample_uniform(200_000, 7, 5.0, seed=3))
+    assert not torch.equal(u, sample_uniform(200_000, 7, 5.0, seed=4))

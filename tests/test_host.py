@@ -1,0 +1,196 @@
+"""Host logic that needs no GPU: Bijector_Info flattening, the API mirror's error behaviour,
+save/load, row sharding and the 2-rank (gloo) gather."""
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import fixtures as F
+from oracle import nsf_oracle as O
+from pzflow_b200 import Flow, FlowEnsemble, _native as N
+from pzflow_b200 import bijectors as B
+from pzflow_b200 import distributions as Dz
+from pzflow_b200 import plan as P
+from pzflow_b200 import sharding
+from pzflow_b200.utils import build_bijector_from_info
+
+
+def test_bijector_info_matches_reference_layout():
+    """RollingSplineCoupling == Chain(*(NSC, Roll) * nlayers) (bijectors.py:651-665)."""
+    _, info = B.RollingSplineCoupling(3, n_conditions=2)
+    assert info == F.rolling_info(3, n_conditions=2)
+    _, info = B.Chain(B.ShiftBounds(0.0, 1.0, 4.0), B.RollingSplineCoupling(2))
+    assert info[0] == "Chain" and info[1][0][0] == "ShiftBounds" and info[1][1][0] == "Chain"
+    rebuilt = build_bijector_from_info(info)[1]
+    assert rebuilt[1][1] == info[1][1]
+
+
+def test_init_params_have_the_stax_layout():
+    init_fun, info = B.Chain(B.ShiftBounds(np.zeros(7), np.ones(7), 4.0), B.RollingSplineCoupling(7, n_conditions=2))
+    params, fwd, inv = init_fun(0, 7)
+    assert isinstance(params, list) and params[0] == () and len(params[1]) == 14
+    nsc = params[1][0]
+    assert [len(p) for p in nsc] == [2, 0, 2, 0, 2]
+    assert nsc[0][0].shape == (5, 128) and nsc[2][0].shape == (128, 128) and nsc[4][0].shape == (128, 188)
+    assert nsc[4][1].shape == (188,) and nsc[0][0].dtype == np.float32
+    assert isinstance(fwd, B.ForwardFunction) and isinstance(inv, B.InverseFunction)
+
+
+def test_flatten_brackets_and_stage_order():
+    ex = F.example_flow()
+    stages = P.flatten(ex["bijector_info"], ex["params"][1], 7)
+    kinds = [s["kind"] for s in stages]
+    assert kinds[:3] == [N.STAGE_CHAIN_BEGIN, N.STAGE_SHIFT_BOUNDS, N.STAGE_CHAIN_BEGIN]
+    assert kinds[3:-2] == [N.STAGE_NSC, N.STAGE_ROLL] * 7
+    assert kinds[-2:] == [N.STAGE_CHAIN_END, N.STAGE_CHAIN_END]
+    nsc = stages[3]
+    assert (nsc["K"], nsc["hidden_layers"], nsc["hidden_dim"], nsc["transformed_dim"]) == (16, 2, 128, -1)
+    assert [w.shape for w in nsc["weights"]] == [(3, 128), (128,), (128, 128), (128,), (128, 188), (188,)]
+
+
+def test_flatten_rejects_bad_shapes_and_foreign_bijectors():
+    info = ("NeuralSplineCoupling", (16, 5, 2, 128, None, 0, False))
+    params = O.synth_bijector_params(info, 7, np.random.default_rng(0))
+    with pytest.raises(ValueError):
+        P.flatten(info, params, 9)  # weights were built for input_dim 7
+    with pytest.raises(NotImplementedError):
+        P.flatten(("Reverse", ()), (), 7)
+    with pytest.raises(NotImplementedError):
+        build_bijector_from_info(("InvSoftplus", (0,)))
+
+
+def test_constructor_validation_matches_reference():
+    """pzflow/flow.py:127-149, 225-231; bijectors.py:446-447, 577-578, 744-751."""
+    with pytest.raises(ValueError):
+        Flow()
+    with pytest.raises(ValueError):
+        Flow(data_columns=("x", "y"), file="nope.pkl")
+    with pytest.raises(ValueError):
+        Flow(data_columns=("x", "y"), latent=Dz.Uniform(3, 5))
+    with pytest.raises(ValueError):
+        B.NeuralSplineCoupling(periodic="yes")
+    with pytest.raises(ValueError):
+        B.Roll(1.5)
+    with pytest.raises(ValueError):
+        B.ShiftBounds(np.zeros(3), np.ones(2))
+    with pytest.raises(ValueError):
+        B.ShiftBounds(1.0, 0.0)
+    flow = Flow(data_columns=("x", "y"))
+    with pytest.raises(ValueError):
+        flow.log_prob(pd.DataFrame({"x": [0.0], "y": [0.0]}))  # bijector not set up
+    with pytest.raises(ValueError):
+        flow.sample(1)
+    with pytest.raises(ValueError):
+        FlowEnsemble()
+    assert flow.latent.info == ("CentBeta13", (2, 5))  # default latent, flow.py:221-222
+    with pytest.raises(NotImplementedError):
+        flow.train(pd.DataFrame({"x": [0.0], "y": [0.0]}))
+
+
+def test_sample_argument_validation():
+    flow = Flow(("x", "y"), B.RollingSplineCoupling(2))
+    with pytest.raises(AssertionError):
+        flow.sample(0)
+    with pytest.raises(AssertionError):
+        flow.sample(1.5)
+    cflow = Flow(("x", "y"), B.RollingSplineCoupling(2, n_conditions=1), conditional_columns=("c",))
+    with pytest.raises(ValueError):
+        cflow.sample(2)
+
+
+def test_save_load_roundtrip(tmp_path):
+    """pzflow/flow.py:819-866, 152-197; flowEnsemble.py:490-505, 135-162."""
+    flow = Flow(("x", "y"), B.Chain(B.ShiftBounds(np.zeros(2), np.ones(2), 4.0), B.RollingSplineCoupling(2)),
+                info=["anything"])
+    path = str(tmp_path / "flow.pzflow.pkl")
+    flow.save(path)
+    back = Flow(file=path)
+    assert back.data_columns == flow.data_columns and back.info == ["anything"]
+    assert back._latent_info == flow._latent_info
+    assert back._bijector_info[1][1] == flow._bijector_info[1][1]
+    np.testing.assert_array_equal(back._params[1][1][0][4][0], flow._params[1][1][0][4][0])
+    with pytest.raises(TypeError):
+        FlowEnsemble(file=path)
+    ens = FlowEnsemble(("x", "y"), B.RollingSplineCoupling(2), N=2)
+    epath = str(tmp_path / "ens.pkl")
+    ens.save(epath)
+    eback = FlowEnsemble(file=epath)
+    assert list(eback._ensemble) == ["Flow 0", "Flow 1"]
+    with pytest.raises(TypeError):
+        Flow(file=epath)
+
+
+def test_loads_reference_style_pickle(tmp_path):
+    """A save dict with the reference's by-reference global pzflow.utils.gaussian_error_model."""
+    import dill
+    import types
+    ex = F.example_flow()
+    pkg, sub = types.ModuleType("pzflow"), types.ModuleType("pzflow.utils")
+
+    def gaussian_error_model(key, X, Xerr, nsamples):
+        return None
+    gaussian_error_model.__module__ = "pzflow.utils"
+    gaussian_error_model.__qualname__ = "gaussian_error_model"  # pickled by reference, like flow.py:238
+    sub.gaussian_error_model = gaussian_error_model
+    pkg.utils = sub
+    sys.modules["pzflow"], sys.modules["pzflow.utils"] = pkg, sub
+    try:
+        d = {"class": "Flow", "data_columns": F.GALAXY_COLUMNS, "conditional_columns": None,
+             "condition_means": None, "condition_stds": None, "data_error_model": gaussian_error_model,
+             "condition_error_model": gaussian_error_model, "autoscale_conditions": True, "info": "x",
+             "latent_info": ex["latent_info"], "bijector_info": ex["bijector_info"], "params": ex["params"]}
+        path = str(tmp_path / "ref.pkl")
+        with open(path, "wb") as fh:
+            dill.dump(d, fh)
+    finally:
+        sys.modules.pop("pzflow"), sys.modules.pop("pzflow.utils")
+    flow = Flow(file=path)
+    assert flow._input_dim == 7 and flow.latent.info == ("Uniform", (7, 5))
+    assert len(flow._params[1][1]) == 14
+
+
+def test_shard_rows_partition():
+    for n in (0, 1, 7, 1000, 10_000_019):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_rows(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 1003
+    full = torch.arange(n, dtype=torch.float32)
+
+    def fake_eval(rows):  # stands in for the per-rank kernel launch
+        return rows * 2.0 + 1.0
+    out = sharding.sharded_eval(fake_eval, full, gather=True)
+    ok = torch.equal(out, full * 2.0 + 1.0)
+    a, b = sharding.shard_rows(n, rank, world)
+    local = sharding.sharded_eval(fake_eval, full, gather=False)
+    ok = ok and torch.equal(local, full[a:b] * 2.0 + 1.0)
+    t = sharding.max_over_ranks(float(rank + 1))
+    ok = ok and t == float(world)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_eval_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
