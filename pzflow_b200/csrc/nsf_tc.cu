@@ -157,8 +157,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);  // leave the issue slots to the other tile's warps
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -242,7 +242,9 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_tmem, uin
 }
 
 // softmax knots, bin search, RQS and log-det of one (row, dim) with the 48 logits in registers
-// (pzflow/bijectors.py:488-491 + pzflow/utils.py:113-227; K = 16).
+// (pzflow/bijectors.py:488-491 + pzflow/utils.py:113-227; K = 16).  The bin search runs on the
+// un-normalised cumulative sums (knot_j <= x  <=>  cumsum(e)_j <= (x + B) * sum(e) / 2B), so only
+// the selected bin's knots and sizes are ever scaled.
 template <bool INV>
 __device__ __forceinline__ void spline_regs(const float (&lg)[48], float x, float B, bool periodic, float& out,
                                             float& ld, int& idx_out) {
@@ -264,45 +266,44 @@ __device__ __forceinline__ void spline_regs(const float (&lg)[48], float x, floa
     sw += W[j];
     sh += H[j];
   }
-  const float rw = __fdividef(twoB, sw), rh = __fdividef(twoB, sh);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    W[j] *= rw;
-    H[j] *= rh;
-  }
+  const float rw = __fdividef(twoB, sw), rh = __fdividef(twoB, sh);  // 2B / sum(e)
   const bool oob = (x <= -B) || (x >= B);
   const float mx = oob ? fabsf(x) - B : x;
+  // searched axis S (widths forward, heights inverse), other axis O
+  const float rs = INV ? rh : rw, ro = INV ? rw : rh;
+  const float target = __fdividef(mx + B, rs);  // (x + B) * sum(e_S) / 2B
   int cnt = (-B <= mx) ? 1 : 0;
-  float cum = 0.0f, ksel = -B;
+  float cs = 0.0f, co = 0.0f;
+  float cs_sel = 0.0f, co_sel = 0.0f;           // cumulative sums at the selected bin's left knot
+  float s_sel = INV ? H[0] : W[0], o_sel = INV ? W[0] : H[0];
+  float r0 = 0.0f, r1 = lg[32];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    cum += INV ? H[j] : W[j];
-    const float knot = -B + cum;
-    const bool p = knot <= mx;
+    cs += INV ? H[j] : W[j];
+    co += INV ? W[j] : H[j];
+    const bool p = cs <= target;  // knot j+1 <= x: a prefix of trues (cumsum of positives is monotone)
     cnt += p ? 1 : 0;
-    ksel = p ? knot : ksel;
+    cs_sel = p ? cs : cs_sel;
+    co_sel = p ? co : co_sel;
+    if (j < 15) {
+      s_sel = p ? (INV ? H[j + 1] : W[j + 1]) : s_sel;
+      o_sel = p ? (INV ? W[j + 1] : H[j + 1]) : o_sel;
+      r1 = p ? lg[32 + j + 1] : r1;  // lg[47] is the zero pad unless periodic
+    }
+    r0 = p ? lg[32 + j] : r0;
   }
   const int idx = cnt - 1;
   idx_out = idx;
   const float qnan = __int_as_float(0x7fc00000);
-  float ssel = qnan, osel = qnan, oknot = -B, cum2 = 0.0f, r0 = 0.0f, r1 = 0.0f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const bool e = (j == idx);
-    ssel = e ? (INV ? H[j] : W[j]) : ssel;
-    osel = e ? (INV ? W[j] : H[j]) : osel;
-    cum2 += INV ? W[j] : H[j];
-    oknot = (j + 1 == idx) ? (-B + cum2) : oknot;
-    r1 = e ? lg[32 + j] : r1;
-    r0 = (j + 1 == idx) ? lg[32 + j] : r0;
-  }
+  const bool bad = (idx < 0) || (idx >= 16);  // take_along_axis "fill" -> NaN (pzflow/utils.py:155-161)
   SplineKnotSel s;
   s.idx = idx;
-  s.wk = INV ? osel : ssel;
-  s.hk = INV ? ssel : osel;
+  const float ksel = fmaf(cs_sel, rs, -B), oknot = fmaf(co_sel, ro, -B);
+  const float ssz = bad ? qnan : s_sel * rs, osz = bad ? qnan : o_sel * ro;
+  s.wk = INV ? osz : ssz;
+  s.hk = INV ? ssz : osz;
   s.xk = INV ? oknot : ksel;
   s.yk = INV ? ksel : oknot;
-  const bool bad = (idx < 0) || (idx >= 16);
   if (periodic) {
     if (idx == 0) r0 = lg[32 + 15];  // dk = pad(D, (1, 0), "wrap")
     s.dk = pz_softplus(r0);
@@ -311,11 +312,7 @@ __device__ __forceinline__ void spline_regs(const float (&lg)[48], float x, floa
     s.dk = (idx == 0) ? 1.0f : pz_softplus(r0);
     s.dkp1 = (idx == 15) ? 1.0f : pz_softplus(r1);
   }
-  if (bad) {
-    s.dk = qnan;
-    s.dkp1 = qnan;
-  }
-  pz_rqs_eval(s, x, mx, oob, INV, periodic, out, ld);
+  pz_rqs_eval<true>(s, x, mx, oob, INV, periodic, out, ld);
 }
 
 struct TcShared {
@@ -366,7 +363,8 @@ template <bool INV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, float* __restrict__ wsp, int smem_blob_bytes) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* blob = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for SWIZZLE_128B, derived by pointer arithmetic so loads stay LDS (not generic LD)
+  uint8_t* blob = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   TcShared* sh = reinterpret_cast<TcShared*>(blob + smem_blob_bytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = plan->D, C = plan->C, ns = plan->n_steps;

@@ -94,8 +94,8 @@ __device__ __forceinline__ float pz_softplus(float x) {
 }
 
 __device__ __forceinline__ float pz_leaky(float x) {
-  // stax.LeakyRelu: where(x >= 0, x, 0.01 * x)
-  return x >= 0.0f ? x : 0.01f * x;
+  // stax.LeakyRelu: where(x >= 0, x, 0.01 * x) == max(x, 0.01 * x), bit for bit (FMUL + FMNMX)
+  return fmaxf(x, 0.01f * x);
 }
 
 __device__ __forceinline__ float pz_nan_to_num_lp(float lp) {
@@ -110,7 +110,16 @@ struct SplineKnotSel {
   int idx;
 };
 
-// pzflow/utils.py:163-227 once the bin's seven values are known.
+__device__ __forceinline__ float pz_lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// pzflow/utils.py:163-227 once the bin's seven values are known.  FASTLOG evaluates the three
+// logarithms of the log-determinant with lg2.approx (absolute error ~2e-7 each, far below the
+// float32 noise floor of the path); the SIMT engine keeps logf.
+template <bool FASTLOG = false>
 __device__ __forceinline__ void pz_rqs_eval(const SplineKnotSel& s, float x, float mx, bool oob,
                                             bool inverse, bool periodic, float& out, float& ld) {
   const float sk = s.hk / s.wk;
@@ -132,7 +141,10 @@ __device__ __forceinline__ void pz_rqs_eval(const SplineKnotSel& s, float x, flo
   const float omr = 1.0f - relx;
   const float dnum = (s.dkp1 * (relx * relx) + ((2.0f * sk) * relx) * omr) + s.dk * (omr * omr);
   const float dden = sk + (dsum * relx) * omr;
-  ld = (2.0f * logf(sk) + logf(dnum)) - 2.0f * logf(dden);
+  if (FASTLOG)
+    ld = 0.6931471805599453f * ((2.0f * pz_lg2_approx(sk) + pz_lg2_approx(dnum)) - 2.0f * pz_lg2_approx(dden));
+  else
+    ld = (2.0f * logf(sk) + logf(dnum)) - 2.0f * logf(dden);
   if (!periodic && oob) {
     out = x;
     ld = 0.0f;

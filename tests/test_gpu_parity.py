@@ -330,6 +330,9 @@ def test_odd_shapes_simt(info, D, C):
     x32, ldi32 = O.apply_bijector(info, params, u32, cond, inverse=True)
     x64, ldi64 = O.apply_bijector(info, p64, u32.astype(np.float64), cond.astype(np.float64), inverse=True)
     xi, ldi = plan.inverse(torch.from_numpy(u32), ct)
+    # the inverse of an out_scale=3 spline is ill-posed where the forward map is flat: a handful of
+    # elements end as NaN (negative discriminant) in one float32 evaluation and not in the other
+    kw["max_class_mismatch"] = max(2, n // 100)
     assert_noise_floor("odd inverse x", _np(xi), x32, x64, **kw)
     assert_noise_floor("odd inverse ld", _np(ldi), ldi32, ldi64, **kw)
 
