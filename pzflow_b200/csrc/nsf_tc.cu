@@ -7,19 +7,24 @@
 // in fp32 in TMEM.  Weights are pre-scaled by a power of two so their lo parts stay normal.
 // Measured against the float64 twin this is indistinguishable from an fp32 GEMM.
 //
-// Data flow per CTA (1 per SM, persistent, 288 threads):
-//   * warps 0-3 / 4-7: two epilogue groups, each owns one 128-row tile at a time (thread = row,
-//     TMEM lane = row).  They ping-pong so the tensor pipe works on one tile while CUDA cores
-//     run the other tile's epilogue.
-//   * warp 8 (one elected lane): TMA bulk loads of the layer's packed weights into shared
-//     memory, and every tcgen05.mma / tcgen05.commit.
-//   * A operands (the activations) never touch shared memory: epilogue threads write the
-//     fp16 hi/lo pairs straight into TMEM (tcgen05.st) and the MMA reads A from TMEM (.ts form);
+// Structure (one persistent CTA per SM, 544 threads):
+//   * 16 epilogue warps in two groups of 8.  A group owns one 128-row tile at a time; TMEM lane =
+//     row, and TWO threads share a row (warp w and w+4 of the group address the same TMEM lane
+//     quarter): each does half of the hidden columns in E1/E2 and one of the two spline
+//     dimensions of an output-layer pass in E3.  The groups ping-pong so the tensor pipe works on
+//     one tile while CUDA cores run the other tile's epilogue.
+//   * warp 16, one elected lane: an event loop that issues every tcgen05.mma / tcgen05.commit
+//     (whichever group is ready first is served first) and streams the weights of the NEXT
+//     coupling stage with TMA bulk copies as soon as the tensor pipe has released a buffer:
+//     W2 (64 KB) after the stage's last hidden GEMM, W3 (48/96 KB) after its last output pass,
+//     the small fp32 parameter block (W1, biases) double buffered.
+//   * A operands (the activations) never touch shared memory: epilogue threads write the fp16
+//     hi/lo pairs straight into TMEM (tcgen05.st) and the MMA reads A from TMEM (.ts form);
 //     B (weights) comes from shared memory, K-major SWIZZLE_128B.
-//   * TMEM (512 columns): tile X: A[0,128) D[128,256); tile Y: A[256,384) D[384,512).
-//   * layer-outer order: a CTA takes a chunk of 2048 rows, keeps the layer's weights resident
-//     (~166 KB) and walks the chunk's 16 tiles; the per-row state (x[D], log-det stack,
-//     conditions) lives in an L2-resident workspace between layers.
+//   * TMEM (512 columns): group 0: A[0,128) D[128,256); group 1: A[256,384) D[384,512).
+//   * stage-outer order: a CTA takes a chunk of up to 1024 rows whose state (x[D], log-det
+//     levels, conditions) lives in shared memory as [column][row] for the whole chain, and walks
+//     the chunk's tiles once per coupling stage.  HBM sees the input rows and the result only.
 //
 // Follows the same reference lines as nsf_simt.cu.
 #include <cuda_fp16.h>
@@ -32,28 +37,30 @@
 namespace pzb {
 
 constexpr int TC_TILE = 128;
-constexpr int TC_CHUNK_TILES = 16;
-constexpr int TC_CHUNK = TC_TILE * TC_CHUNK_TILES;
-constexpr int TC_THREADS = 288;
+constexpr int TC_GROUP_THREADS = 256;
+constexpr int TC_EPI_THREADS = 512;
+constexpr int TC_THREADS = 544;
 constexpr int TC_IN_MAX = 8;
 constexpr int TC_L_MAX = 4;
 constexpr int TC_D_MAX = 8;
-constexpr int TC_PASS_N = 96;          // two spline dims x 48 logit columns per output-layer pass
-constexpr int TC_W2_BYTES = 128 * 128 * 2;          // one fp16 [128 x 128] tile
-constexpr int TC_W3_BYTES = TC_PASS_N * 128 * 2;    // one fp16 [96 x 128] tile
+constexpr int TC_MAX_CHUNK_TILES = 16;
+constexpr int TC_PASS_N = 96;                     // two spline dims x 48 logit columns per output-layer pass
+constexpr int TC_W2_BYTES = 2 * 128 * 128 * 2;    // fp16 hi + lo [128 x 128] tiles
+constexpr int TC_W3_PASS_BYTES = 2 * TC_PASS_N * 128 * 2;  // fp16 hi + lo [96 x 128] tiles of one pass
+// fp32 parameter block: W1[TC_IN_MAX][128], b1[128], b2[128], b3[2 * 96], scal[4]
+constexpr int TC_PAR_FLOATS = TC_IN_MAX * 128 + 128 + 128 + 2 * TC_PASS_N + 4;
+constexpr int TC_PAR_BYTES = TC_PAR_FLOATS * 4;   // 5904, a multiple of 16
+constexpr int TC_SMEM_MAX = 232448;               // 227 KB opt-in limit per CTA
 
+// global blob of one coupling stage: [W2 hi | W2 lo | pass0 hi | pass0 lo | pass1 hi | pass1 lo | par]
 struct TcLayout {
-  int w2hi, w2lo, w3, par, total, n_pass;
-  // par (floats): W1[TC_IN_MAX][128], b1[128], b2[128], b3[n_pass*96], scal[4]
+  int w3, par, total, n_pass;
   __host__ __device__ static TcLayout make(int L) {
     TcLayout t;
     t.n_pass = (L + 1) / 2;
-    t.w2hi = 0;
-    t.w2lo = TC_W2_BYTES;
-    t.w3 = 2 * TC_W2_BYTES;
-    t.par = t.w3 + t.n_pass * 2 * TC_W3_BYTES;
-    t.total = t.par + (TC_IN_MAX * 128 + 128 + 128 + t.n_pass * TC_PASS_N + 4) * 4;
-    t.total = (t.total + 15) / 16 * 16;
+    t.w3 = TC_W2_BYTES;
+    t.par = t.w3 + t.n_pass * TC_W3_PASS_BYTES;
+    t.total = t.par + TC_PAR_BYTES;
     return t;
   }
 };
@@ -104,13 +111,13 @@ void tc_pack_stage(const NscDev& st, const float* const* weights, void* dst) {
   const int in_dim = st.U + st.C, out_dim = st.cpd * st.L;
   const int e2 = pow2_scale_exp(W2, 128 * 128), e3 = pow2_scale_exp(W3, (size_t)128 * out_dim);
   const float s2 = ldexpf(1.0f, e2), s3 = ldexpf(1.0f, e3);
-  __half* w2hi = reinterpret_cast<__half*>(base + lay.w2hi);
-  __half* w2lo = reinterpret_cast<__half*>(base + lay.w2lo);
+  __half* w2hi = reinterpret_cast<__half*>(base);
+  __half* w2lo = reinterpret_cast<__half*>(base + TC_W2_BYTES / 2);
   for (int n = 0; n < 128; ++n)
     for (int k = 0; k < 128; ++k) split_store(w2hi, w2lo, sw128_index(128, n, k), W2[k * 128 + n] * s2);
   for (int p = 0; p < lay.n_pass; ++p) {
-    __half* hi = reinterpret_cast<__half*>(base + lay.w3 + p * 2 * TC_W3_BYTES);
-    __half* lo = reinterpret_cast<__half*>(base + lay.w3 + p * 2 * TC_W3_BYTES + TC_W3_BYTES);
+    __half* hi = reinterpret_cast<__half*>(base + lay.w3 + p * TC_W3_PASS_BYTES);
+    __half* lo = reinterpret_cast<__half*>(base + lay.w3 + p * TC_W3_PASS_BYTES + TC_W3_PASS_BYTES / 2);
     for (int j = 0; j < 2; ++j) {
       const int d = 2 * p + j;
       if (d >= st.L) continue;
@@ -132,7 +139,7 @@ void tc_pack_stage(const NscDev& st, const float* const* weights, void* dst) {
   }
   for (int d = 0; d < st.L; ++d)
     for (int q = 0; q < st.cpd; ++q) pb3[(d / 2) * TC_PASS_N + 48 * (d % 2) + q] = b3[d * st.cpd + q];
-  float* scal = pb3 + lay.n_pass * TC_PASS_N;
+  float* scal = pb3 + 2 * TC_PASS_N;
   scal[0] = ldexpf(1.0f, -e2);
   scal[1] = ldexpf(1.0f, -e3);
 }
@@ -156,9 +163,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {  // never suspends the thread
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(32);  // leave the issue slots to the other tile's warps
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);  // leave the issue slots to the other group's warps
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -170,6 +188,9 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -241,59 +262,94 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_tmem, uin
   }
 }
 
-// softmax knots, bin search, RQS and log-det of one (row, dim) with the 48 logits in registers
+// softmax knots, bin search, RQS and log-det of one (row, dim) from its 48 raw accumulator values
 // (pzflow/bijectors.py:488-491 + pzflow/utils.py:113-227; K = 16).  The bin search runs on the
 // un-normalised cumulative sums (knot_j <= x  <=>  cumsum(e)_j <= (x + B) * sum(e) / 2B), so only
-// the selected bin's knots and sizes are ever scaled.
+// the selected bin's knots and sizes are ever scaled.  The searched axis (widths forward, heights
+// inverse) is processed first, then the other axis and the two derivatives the bin needs.
 template <bool INV>
-__device__ __forceinline__ void spline_regs(const float (&lg)[48], float x, float B, bool periodic, float& out,
-                                            float& ld, int& idx_out) {
+__device__ __forceinline__ void spline_regs(const float (&raw)[48], const float* __restrict__ bias, float sinv, float x,
+                                            float B, bool periodic, float& out, float& ld, int& idx_out) {
   constexpr float L2E = 1.4426950408889634f;
+  constexpr int SO = INV ? 16 : 0, OO = INV ? 0 : 16;
   const float twoB = 2.0f * B;
-  float mw = lg[0], mh = lg[16];
-#pragma unroll
-  for (int j = 1; j < 16; ++j) {
-    mw = fmaxf(mw, lg[j]);
-    mh = fmaxf(mh, lg[16 + j]);
-  }
-  const float nmw = -(mw * L2E), nmh = -(mh * L2E);
-  float W[16], H[16];
-  float sw = 0.0f, sh = 0.0f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    W[j] = ex2_approx(fmaf(lg[j], L2E, nmw));
-    H[j] = ex2_approx(fmaf(lg[16 + j], L2E, nmh));
-    sw += W[j];
-    sh += H[j];
-  }
-  const float rw = __fdividef(twoB, sw), rh = __fdividef(twoB, sh);  // 2B / sum(e)
   const bool oob = (x <= -B) || (x >= B);
   const float mx = oob ? fabsf(x) - B : x;
-  // searched axis S (widths forward, heights inverse), other axis O
-  const float rs = INV ? rh : rw, ro = INV ? rw : rh;
-  const float target = __fdividef(mx + B, rs);  // (x + B) * sum(e_S) / 2B
-  int cnt = (-B <= mx) ? 1 : 0;
-  float cs = 0.0f, co = 0.0f;
-  float cs_sel = 0.0f, co_sel = 0.0f;           // cumulative sums at the selected bin's left knot
-  float s_sel = INV ? H[0] : W[0], o_sel = INV ? W[0] : H[0];
-  float r0 = 0.0f, r1 = lg[32];
+
+  // ---- searched axis ----
+  float e[16];
+#pragma unroll
+  for (int q = 0; q < 16; q += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias + SO + q);
+    e[q + 0] = fmaf(raw[SO + q + 0], sinv, b4.x);
+    e[q + 1] = fmaf(raw[SO + q + 1], sinv, b4.y);
+    e[q + 2] = fmaf(raw[SO + q + 2], sinv, b4.z);
+    e[q + 3] = fmaf(raw[SO + q + 3], sinv, b4.w);
+  }
+  float m = e[0];
+#pragma unroll
+  for (int j = 1; j < 16; ++j) m = fmaxf(m, e[j]);
+  float nm = -(m * L2E);
+  float run = 0.0f;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    cs += INV ? H[j] : W[j];
-    co += INV ? W[j] : H[j];
-    const bool p = cs <= target;  // knot j+1 <= x: a prefix of trues (cumsum of positives is monotone)
+    e[j] = ex2_approx(fmaf(e[j], L2E, nm));
+    run += e[j];
+  }
+  const float rs = __fdividef(twoB, run);              // 2B / sum(e)
+  const float target = __fdividef(mx + B, rs);         // (x + B) * sum(e) / 2B
+  int cnt = (-B <= mx) ? 1 : 0;
+  float cs_sel = 0.0f, s_sel = e[0];
+  run = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    run += e[j];
+    const bool p = run <= target;  // knot j+1 <= x: a prefix of trues (cumsum of positives is monotone)
     cnt += p ? 1 : 0;
-    cs_sel = p ? cs : cs_sel;
-    co_sel = p ? co : co_sel;
-    if (j < 15) {
-      s_sel = p ? (INV ? H[j + 1] : W[j + 1]) : s_sel;
-      o_sel = p ? (INV ? W[j + 1] : H[j + 1]) : o_sel;
-      r1 = p ? lg[32 + j + 1] : r1;  // lg[47] is the zero pad unless periodic
-    }
-    r0 = p ? lg[32 + j] : r0;
+    cs_sel = p ? run : cs_sel;
+    if (j < 15) s_sel = p ? e[j + 1] : s_sel;
   }
   const int idx = cnt - 1;
   idx_out = idx;
+  // prefix count over the 16 interior/right knots; the other-axis selections replay it as (j < np)
+  const int np = cnt - ((-B <= mx) ? 1 : 0);
+
+  // ---- other axis ----
+#pragma unroll
+  for (int q = 0; q < 16; q += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias + OO + q);
+    e[q + 0] = fmaf(raw[OO + q + 0], sinv, b4.x);
+    e[q + 1] = fmaf(raw[OO + q + 1], sinv, b4.y);
+    e[q + 2] = fmaf(raw[OO + q + 2], sinv, b4.z);
+    e[q + 3] = fmaf(raw[OO + q + 3], sinv, b4.w);
+  }
+  m = e[0];
+#pragma unroll
+  for (int j = 1; j < 16; ++j) m = fmaxf(m, e[j]);
+  nm = -(m * L2E);
+  run = 0.0f;
+  float co_sel = 0.0f, o_sel = 0.0f;
+  float r0 = 0.0f, r1 = fmaf(raw[32], sinv, bias[32]);
+  bool pprev = true;  // (j - 1 < np)
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float ej = ex2_approx(fmaf(e[j], L2E, nm));
+    run += ej;
+    o_sel = pprev ? ej : o_sel;  // ends as e[min(np, 15)]
+    const bool p = j < np;
+    co_sel = p ? run : co_sel;
+    if (j < 15) r1 = p ? raw[32 + j + 1] : r1;  // raw[47] is the zero pad unless periodic
+    r0 = p ? raw[32 + j] : r0;
+    pprev = p;
+  }
+  const float ro = __fdividef(twoB, run);
+  // the two derivative logits: bias applied after the selection (bias index = selected index)
+  {
+    const int i0 = min(max(np - 1, 0), 15), i1 = min(np, 15);
+    if (np > 0) r0 = fmaf(r0, sinv, bias[32 + i0]);
+    if (np > 0) r1 = fmaf(r1, sinv, bias[32 + i1]);
+  }
+
   const float qnan = __int_as_float(0x7fc00000);
   const bool bad = (idx < 0) || (idx >= 16);  // take_along_axis "fill" -> NaN (pzflow/utils.py:155-161)
   SplineKnotSel s;
@@ -305,7 +361,7 @@ __device__ __forceinline__ void spline_regs(const float (&lg)[48], float x, floa
   s.xk = INV ? oknot : ksel;
   s.yk = INV ? ksel : oknot;
   if (periodic) {
-    if (idx == 0) r0 = lg[32 + 15];  // dk = pad(D, (1, 0), "wrap")
+    if (idx == 0) r0 = fmaf(raw[32 + 15], sinv, bias[32 + 15]);  // dk = pad(D, (1, 0), "wrap")
     s.dk = pz_softplus(r0);
     s.dkp1 = pz_softplus(r1);
   } else {
@@ -316,30 +372,53 @@ __device__ __forceinline__ void spline_regs(const float (&lg)[48], float x, floa
 }
 
 struct TcShared {
-  uint64_t go[2];    // epilogue group -> MMA thread (128 arrivals): operands ready / accumulator drained
-  uint64_t done[2];  // MMA thread -> epilogue group (tcgen05.commit)
-  uint64_t wbar;     // weight blob landed (TMA complete_tx)
+  uint64_t go[2];        // epilogue group -> MMA thread (256 arrivals): operands ready / accumulator drained
+  uint64_t done[2];      // MMA thread -> epilogue group (tcgen05.commit)
+  uint64_t lay_done[2];  // epilogue group finished a coupling stage (256 arrivals): its parameter block is free
+  uint64_t w2full, w3full, parfull[2];  // TMA complete_tx
+  uint64_t w2free, w3free;              // tcgen05.commit after the stage's last hidden GEMM / output pass
   uint32_t tmem_base;
-  int16_t perm[MAX_D];
+  uint8_t order[MAX_NSC];  // coupling stages in walk order (index into PlanDev::nsc)
 };
 
-// One row's light steps between NSC stages, on the workspace row in global/L2 memory.
-__device__ __forceinline__ void apply_affine_row(const AffineDev& af, bool inverse, int D, float* row) {
+struct TcSmem {  // byte offsets from the 1024-aligned base
+  int w2, w3, par, state, shared, total;
+};
+
+__host__ __device__ inline TcSmem tc_smem_layout(int max_pass, int chunk_tiles, int state_cols) {
+  TcSmem s;
+  s.w2 = 0;
+  s.w3 = TC_W2_BYTES;
+  s.par = s.w3 + max_pass * TC_W3_PASS_BYTES;
+  s.state = s.par + 2 * TC_PAR_BYTES;
+  s.shared = s.state + chunk_tiles * TC_TILE * state_cols * 4;
+  s.shared = (s.shared + 15) / 16 * 16;
+  s.total = s.shared + (int)sizeof(TcShared);
+  return s;
+}
+
+struct TcLaunch {
+  int chunk_tiles, max_pass, state_cols, n_lev;
+};
+
+// state column indices: x[0, D), log-det levels [D, D + n_lev), pending log-det halves (2), conditions (C)
+__device__ __forceinline__ void apply_affine_cols(const AffineDev& af, bool inverse, int D, float* st, int CR) {
   for (int j = 0; j < D; ++j) {
-    const float x = row[j];
+    const float x = st[j * CR];
     float y;
     if (af.kind == AFF_SHIFT_BOUNDS)
       y = inverse ? (x * af.b[j]) / af.B + af.a[j] : (af.B * (x - af.a[j])) / af.b[j];
     else
       y = inverse ? x * af.b[j] + af.a[j] : (x - af.a[j]) / af.b[j];
-    row[j] = y;
+    st[j * CR] = y;
   }
 }
 
-// Applies the non-NSC steps in [s0, s1) (already mapped to walk order) to one workspace row.
-__device__ __forceinline__ void light_steps_row(const PlanDev* plan, bool inverse, int s0, int s1, int& level, float* row) {
+// Applies the non-NSC steps in [s0, s1) (already mapped to walk order) to one state row.
+__device__ __forceinline__ void light_steps_cols(const PlanDev* plan, bool inverse, int s0, int s1, int& level, float* st,
+                                                 int CR) {
   const int D = plan->D, ns = plan->n_steps;
-  float* ldl = row + D;
+  float* ldl = st + D * CR;
   for (int si = s0; si < s1; ++si) {
     const StepDev step = plan->steps[inverse ? ns - 1 - si : si];
     int kind = step.kind;
@@ -347,42 +426,93 @@ __device__ __forceinline__ void light_steps_row(const PlanDev* plan, bool invers
     else if (inverse && kind == STEP_CHAIN_END) kind = STEP_CHAIN_BEGIN;
     if (kind == STEP_CHAIN_BEGIN) {
       ++level;
-      ldl[level] = 0.0f;
+      ldl[level * CR] = 0.0f;
     } else if (kind == STEP_CHAIN_END) {
-      ldl[level - 1] += ldl[level];
+      ldl[(level - 1) * CR] += ldl[level * CR];
       --level;
     } else if (kind == STEP_AFFINE) {
       const AffineDev& af = plan->affine[step.idx];
-      apply_affine_row(af, inverse, D, row);
-      ldl[level] += inverse ? af.logdet_inv : af.logdet_fwd;
+      apply_affine_cols(af, inverse, D, st, CR);
+      ldl[level * CR] += inverse ? af.logdet_inv : af.logdet_fwd;
     }
+  }
+}
+
+__device__ __forceinline__ int level_after(const PlanDev* plan, bool inverse, int s0, int s1, int level) {
+  const int ns = plan->n_steps;
+  for (int si = s0; si < s1; ++si) {
+    int kind = plan->steps[inverse ? ns - 1 - si : si].kind;
+    if (inverse && kind == STEP_CHAIN_BEGIN) kind = STEP_CHAIN_END;
+    else if (inverse && kind == STEP_CHAIN_END) kind = STEP_CHAIN_BEGIN;
+    level += (kind == STEP_CHAIN_BEGIN) - (kind == STEP_CHAIN_END);
+  }
+  return level;
+}
+
+// E1 for one half row: 64 hidden columns of LeakyReLU(key @ W1 + b1) -> fp16 hi/lo in TMEM
+template <int IN>
+__device__ __forceinline__ void e1_half(const float (&key)[TC_IN_MAX], const float* __restrict__ sW1,
+                                        const float* __restrict__ sb1, int half, uint32_t t_a) {
+#pragma unroll
+  for (int bt = 0; bt < 2; ++bt) {
+    uint32_t rh[16], rl[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int k0 = half * 64 + bt * 32 + q * 4;
+      float4 acc = *reinterpret_cast<const float4*>(sb1 + k0);
+#pragma unroll
+      for (int i = 0; i < IN; ++i) {
+        const float4 w = *reinterpret_cast<const float4*>(sW1 + i * 128 + k0);
+        acc.x = fmaf(key[i], w.x, acc.x);
+        acc.y = fmaf(key[i], w.y, acc.y);
+        acc.z = fmaf(key[i], w.z, acc.z);
+        acc.w = fmaf(key[i], w.w, acc.w);
+      }
+      split2(pz_leaky(acc.x), pz_leaky(acc.y), rh[2 * q], rl[2 * q]);
+      split2(pz_leaky(acc.z), pz_leaky(acc.w), rh[2 * q + 1], rl[2 * q + 1]);
+    }
+    tmem_st16(t_a + half * 32 + bt * 16, rh);
+    tmem_st16(t_a + 64 + half * 32 + bt * 16, rl);
   }
 }
 
 template <bool INV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, float* __restrict__ wsp, int smem_blob_bytes) {
+nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch lp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B, derived by pointer arithmetic so loads stay LDS (not generic LD)
-  uint8_t* blob = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  TcShared* sh = reinterpret_cast<TcShared*>(blob + smem_blob_bytes);
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols);
+  TcShared* sh = reinterpret_cast<TcShared*>(base + sl.shared);
+  float* state = reinterpret_cast<float*>(base + sl.state);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int D = plan->D, C = plan->C, ns = plan->n_steps;
-  const int RS = D + MAX_CHAIN_DEPTH + C;  // workspace row: x[D], ld[4], cond[C]
-  float* ws = wsp + (size_t)blockIdx.x * TC_CHUNK * RS;
-  const bool is_epi = warp < 8;
-  const int grp = warp >> 2;                       // epilogue group (tile X / Y)
-  const int lrow = ((warp & 3) << 5) + lane;       // row within the tile == TMEM lane
+  const int D = plan->D, C = plan->C, ns = plan->n_steps, n_nsc = plan->n_nsc, n_lev = lp.n_lev;
+  const int CR = lp.chunk_tiles * TC_TILE;           // rows of state per column
+  const int COL_PEND = D + n_lev, COL_COND = D + n_lev + 2;
+  const bool is_epi = warp < 16;
+  const int grp = (warp >> 3) & 1;                   // epilogue group
+  const int half = (warp >> 2) & 1;                  // which half of the row's work
+  const int lrow = ((warp & 3) << 5) + lane;         // row within the tile == TMEM lane
 
   if (tid == 0) {
-    mbar_init(smem_u32(&sh->go[0]), 128);
-    mbar_init(smem_u32(&sh->go[1]), 128);
-    mbar_init(smem_u32(&sh->done[0]), 1);
-    mbar_init(smem_u32(&sh->done[1]), 1);
-    mbar_init(smem_u32(&sh->wbar), 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(smem_u32(&sh->go[g]), TC_GROUP_THREADS);
+      mbar_init(smem_u32(&sh->done[g]), 1);
+      mbar_init(smem_u32(&sh->lay_done[g]), TC_GROUP_THREADS);
+      mbar_init(smem_u32(&sh->parfull[g]), 1);
+    }
+    mbar_init(smem_u32(&sh->w2full), 1);
+    mbar_init(smem_u32(&sh->w3full), 1);
+    mbar_init(smem_u32(&sh->w2free), 1);
+    mbar_init(smem_u32(&sh->w3free), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int seen = 0;
+    for (int si = 0; si < plan->n_steps; ++si) {
+      const StepDev step = plan->steps[INV ? plan->n_steps - 1 - si : si];
+      if (step.kind == STEP_NSC) sh->order[seen++] = (uint8_t)step.idx;
+    }
   }
-  if (warp == 8) {
+  if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -391,29 +521,37 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, float* __
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = sh->tmem_base;
-  const uint32_t t_lane = tbase + ((uint32_t)((warp & 3) << 5) << 16);
-  const uint32_t a_col = (uint32_t)grp * 256u, d_col = (uint32_t)grp * 256u + 128u;
-  uint32_t ph_go[2] = {0u, 0u}, ph_done = 0u, ph_w = 0u;
 
-  const long long n_chunks = (args.N + TC_CHUNK - 1) / TC_CHUNK;
-  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const long long row0 = chunk * TC_CHUNK;
-    const int nrows = (int)min((long long)TC_CHUNK, args.N - row0);
-    const int npairs = ((nrows + TC_TILE - 1) / TC_TILE + 1) / 2;
+  const long long chunk_rows = (long long)CR;
+  const long long n_chunks = (args.N + chunk_rows - 1) / chunk_rows;
+  const int my_chunks = (int)((n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x);  // blockIdx.x < n_chunks
 
-    // first / last NSC step in walk order
-    int first_nsc = ns, last_nsc = -1;
-    for (int si = 0; si < ns; ++si)
-      if (plan->steps[INV ? ns - 1 - si : si].kind == STEP_NSC) {
-        if (first_nsc == ns) first_nsc = si;
-        last_nsc = si;
-      }
+  // NSC steps in walk order
+  int first_nsc = ns, last_nsc = -1;
+  for (int si = 0; si < ns; ++si)
+    if (plan->steps[INV ? ns - 1 - si : si].kind == STEP_NSC) {
+      if (first_nsc == ns) first_nsc = si;
+      last_nsc = si;
+    }
 
-    // ---- pass A: load rows into the workspace, run the steps in front of the first NSC ----
-    if (is_epi) {
-      for (int r = tid; r < nrows; r += 256) {
+  if (is_epi) {
+    // ======================================= epilogue warps =======================================
+    const uint32_t t_lane = tbase + ((uint32_t)((warp & 3) << 5) << 16);
+    const uint32_t t_a = t_lane + (uint32_t)grp * 256u, t_d = t_lane + (uint32_t)grp * 256u + 128u;
+    const uint32_t bar_go = smem_u32(&sh->go[grp]), bar_done = smem_u32(&sh->done[grp]);
+    uint32_t ph_done = 0u;
+    int seq = 0;  // coupling stages processed so far by this CTA (over all its chunks)
+
+    for (int ci = 0; ci < my_chunks; ++ci) {
+      const long long row0 = ((long long)blockIdx.x + (long long)ci * gridDim.x) * chunk_rows;
+      const int nrows = (int)min(chunk_rows, args.N - row0);
+      const int ntiles = max(2, (nrows + TC_TILE - 1) / TC_TILE);
+      const int my_tiles = (ntiles - grp + 1) / 2;
+
+      // ---- pass A: rows -> state, steps in front of the first coupling stage ----
+      for (int r = tid; r < nrows; r += TC_EPI_THREADS) {
         const long long row = row0 + r;
-        float* wr = ws + (size_t)r * RS;
+        float* st = state + r;
         for (int j = 0; j < D; ++j) {
           float v;
           if (args.mode == MODE_POSTERIOR) {
@@ -423,125 +561,94 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, float* __
           } else {
             v = args.X[row * D + j];
           }
-          wr[INV ? plan->perm_final[j] : j] = v;
+          st[(INV ? plan->perm_final[j] : j) * CR] = v;
         }
-        for (int l = 0; l < MAX_CHAIN_DEPTH; ++l) wr[D + l] = 0.0f;
+        for (int l = 0; l < n_lev; ++l) st[(D + l) * CR] = 0.0f;
         const long long crow = (args.mode == MODE_POSTERIOR) ? row / args.G : row;
-        for (int j = 0; j < C; ++j) wr[D + MAX_CHAIN_DEPTH + j] = args.cond ? args.cond[crow * C + j] : 0.0f;
+        for (int j = 0; j < C; ++j) st[(COL_COND + j) * CR] = args.cond ? args.cond[crow * C + j] : 0.0f;
         int level = 0;
-        light_steps_row(plan, INV, 0, first_nsc, level, wr);
+        light_steps_cols(plan, INV, 0, first_nsc, level, st, CR);
       }
-    }
-    int level = 0;  // chain depth after the steps walked so far (row independent)
-    for (int si = 0; si < first_nsc; ++si) {
-      int kind = plan->steps[INV ? ns - 1 - si : si].kind;
-      if (INV && kind == STEP_CHAIN_BEGIN) kind = STEP_CHAIN_END;
-      else if (INV && kind == STEP_CHAIN_END) kind = STEP_CHAIN_BEGIN;
-      level += (kind == STEP_CHAIN_BEGIN) - (kind == STEP_CHAIN_END);
-    }
-    __syncthreads();
+      int level = level_after(plan, INV, 0, first_nsc, 0);  // chain depth (row independent)
+      named_bar_sync(1, TC_EPI_THREADS);
 
-    // ---- the coupling stages ----
-    int prev_end = first_nsc;
-    for (int si = first_nsc; si <= last_nsc; ++si) {
-      const StepDev step = plan->steps[INV ? ns - 1 - si : si];
-      if (step.kind != STEP_NSC) continue;
-      if (si > prev_end) {  // light steps between two coupling stages
-        if (is_epi)
-          for (int r = tid; r < nrows; r += 256) {
-            int lv = level;
-            light_steps_row(plan, INV, prev_end, si, lv, ws + (size_t)r * RS);
-          }
-        for (int sj = prev_end; sj < si; ++sj) {
-          int kind = plan->steps[INV ? ns - 1 - sj : sj].kind;
-          if (INV && kind == STEP_CHAIN_BEGIN) kind = STEP_CHAIN_END;
-          else if (INV && kind == STEP_CHAIN_END) kind = STEP_CHAIN_BEGIN;
-          level += (kind == STEP_CHAIN_BEGIN) - (kind == STEP_CHAIN_END);
-        }
-        __syncthreads();
-      }
-      prev_end = si + 1;
-      const NscDev& st = plan->nsc[step.idx];
-      const TcLayout lay = TcLayout::make(st.L);
-      const int U = st.U, L = st.L, in_dim = st.U + st.C;
+      // ---- the coupling stages ----
+      int prev_end = first_nsc;
+      bool pending = false;  // the previous stage's two log-det halves still sit in the pending columns
+      int pend_level = 0;
+      for (int si = first_nsc; si <= last_nsc; ++si) {
+        const StepDev step = plan->steps[INV ? ns - 1 - si : si];
+        if (step.kind != STEP_NSC) continue;
+        const bool has_light = si > prev_end;
+        const int light0 = prev_end;
+        const int level_in = level;
+        level = level_after(plan, INV, prev_end, si, level);
+        prev_end = si + 1;
+        const NscDev& st = plan->nsc[step.idx];
+        const int U = st.U, L = st.L, in_dim = st.U + st.C, n_pass = (L + 1) / 2;
+        const float B = st.B;
+        const bool periodic = st.periodic != 0;
 
-      if (tid < D) sh->perm[tid] = st.perm[tid];
-      if (warp == 8 && lane == 0) {
-        // weights of this stage: global (L2) -> shared memory, one TMA bulk copy per 16 KB
-        const uint32_t bar = smem_u32(&sh->wbar);
-        mbar_expect_tx(bar, (uint32_t)lay.total);
-        const uint8_t* src = static_cast<const uint8_t*>(st.tc.blob);
-        for (int off = 0; off < lay.total; off += 16384) {
-          const int nb = min(16384, lay.total - off);
-          tma_bulk_g2s(smem_u32(blob + off), src + off, (uint32_t)nb, bar);
-        }
-      }
-      __syncthreads();
-      mbar_wait(smem_u32(&sh->wbar), ph_w);
-      ph_w ^= 1u;
+        // parameter block of this stage (double buffered); previous-stage state writes of the row's other half
+        mbar_wait(smem_u32(&sh->parfull[seq & 1]), (uint32_t)((seq >> 1) & 1));
+        named_bar_sync(2 + grp, TC_GROUP_THREADS);
+        const float* par = reinterpret_cast<const float*>(base + sl.par + (seq & 1) * TC_PAR_BYTES);
+        const float* sW1 = par;
+        const float* sb1 = par + TC_IN_MAX * 128;
+        const float* sb2 = sb1 + 128;
+        const float* sb3 = sb2 + 128;
+        const float s2inv = sb3[2 * TC_PASS_N], s3inv = sb3[2 * TC_PASS_N + 1];
 
-      const float* par = reinterpret_cast<const float*>(blob + lay.par);
-      const float* sW1 = par;
-      const float* sb1 = par + TC_IN_MAX * 128;
-      const float* sb2 = sb1 + 128;
-      const float* sb3 = sb2 + 128;
-      const float s2inv = sb3[lay.n_pass * TC_PASS_N], s3inv = sb3[lay.n_pass * TC_PASS_N + 1];
-
-      if (is_epi) {
-        // =============================== epilogue groups ===============================
-        for (int pair = 0; pair < npairs; ++pair) {
-          const int r = (2 * pair + grp) * TC_TILE + lrow;
+        for (int k = 0; k < my_tiles; ++k) {
+          const int r = (2 * k + grp) * TC_TILE + lrow;  // row within the chunk (state is allocated for every tile)
           const bool valid = r < nrows;
-          float* wr = ws + (size_t)(valid ? r : 0) * RS;
-          float key[TC_IN_MAX], low[TC_L_MAX];
+          float* srow = state + r;
+
+          if (pending || has_light) {
+            if (half == 0) {
+              if (pending) srow[(D + pend_level) * CR] += srow[COL_PEND * CR] + srow[(COL_PEND + 1) * CR];
+              if (has_light) {
+                int lv = level_in;
+                light_steps_cols(plan, INV, light0, si, lv, srow, CR);
+              }
+            }
+            if (has_light) named_bar_sync(2 + grp, TC_GROUP_THREADS);
+          }
+
+          float key[TC_IN_MAX];
 #pragma unroll
-          for (int k = 0; k < TC_IN_MAX; ++k)
-            key[k] = (valid && k < in_dim) ? (k < U ? wr[sh->perm[k]] : wr[D + MAX_CHAIN_DEPTH + (k - U)]) : 0.0f;
-#pragma unroll
-          for (int d = 0; d < TC_L_MAX; ++d) low[d] = (valid && d < L) ? wr[sh->perm[U + d]] : 0.0f;
+          for (int i = 0; i < TC_IN_MAX; ++i)
+            key[i] = (i < in_dim) ? (i < U ? srow[st.perm[i] * CR] : srow[(COL_COND + (i - U)) * CR]) : 0.0f;
 
           // ---- E1: h1 = LeakyReLU(key @ W1 + b1) -> A (fp16 hi/lo) in TMEM ----
-#pragma unroll
-          for (int bt = 0; bt < 4; ++bt) {
-            uint32_t rh[16], rl[16];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int k0 = bt * 32 + q * 4;
-              float4 acc = *reinterpret_cast<const float4*>(sb1 + k0);
-#pragma unroll
-              for (int i = 0; i < TC_IN_MAX; ++i) {
-                if (i < in_dim) {
-                  const float4 w = *reinterpret_cast<const float4*>(sW1 + i * 128 + k0);
-                  acc.x = fmaf(key[i], w.x, acc.x);
-                  acc.y = fmaf(key[i], w.y, acc.y);
-                  acc.z = fmaf(key[i], w.z, acc.z);
-                  acc.w = fmaf(key[i], w.w, acc.w);
-                }
-              }
-              split2(pz_leaky(acc.x), pz_leaky(acc.y), rh[2 * q], rl[2 * q]);
-              split2(pz_leaky(acc.z), pz_leaky(acc.w), rh[2 * q + 1], rl[2 * q + 1]);
-            }
-            tmem_st16(t_lane + a_col + bt * 16, rh);
-            tmem_st16(t_lane + a_col + 64 + bt * 16, rl);
+          switch (in_dim) {
+            case 1: e1_half<1>(key, sW1, sb1, half, t_a); break;
+            case 2: e1_half<2>(key, sW1, sb1, half, t_a); break;
+            case 3: e1_half<3>(key, sW1, sb1, half, t_a); break;
+            case 4: e1_half<4>(key, sW1, sb1, half, t_a); break;
+            case 5: e1_half<5>(key, sW1, sb1, half, t_a); break;
+            case 6: e1_half<6>(key, sW1, sb1, half, t_a); break;
+            case 7: e1_half<7>(key, sW1, sb1, half, t_a); break;
+            default: e1_half<8>(key, sW1, sb1, half, t_a); break;
           }
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(smem_u32(&sh->go[grp]));
+          mbar_arrive(bar_go);
 
           // ---- E2: h2 = LeakyReLU(D * 2^-e2 + b2) -> A ----
-          mbar_wait(smem_u32(&sh->done[grp]), ph_done);
+          mbar_wait(bar_done, ph_done);
           ph_done ^= 1u;
           tc_fence_after();
 #pragma unroll
-          for (int bt = 0; bt < 4; ++bt) {
+          for (int bt = 0; bt < 2; ++bt) {
             float dv[32];
-            tmem_ld16(t_lane + d_col + bt * 32, dv);
-            tmem_ld16(t_lane + d_col + bt * 32 + 16, dv + 16);
+            tmem_ld16(t_d + half * 64 + bt * 32, dv);
+            tmem_ld16(t_d + half * 64 + bt * 32 + 16, dv + 16);
             tc_wait_ld();
             uint32_t rh[16], rl[16];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 bb = *reinterpret_cast<const float4*>(sb2 + bt * 32 + q * 4);
+              const float4 bb = *reinterpret_cast<const float4*>(sb2 + half * 64 + bt * 32 + q * 4);
               const float h0 = pz_leaky(fmaf(dv[4 * q + 0], s2inv, bb.x));
               const float h1 = pz_leaky(fmaf(dv[4 * q + 1], s2inv, bb.y));
               const float h2 = pz_leaky(fmaf(dv[4 * q + 2], s2inv, bb.z));
@@ -549,111 +656,204 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, float* __
               split2(h0, h1, rh[2 * q], rl[2 * q]);
               split2(h2, h3, rh[2 * q + 1], rl[2 * q + 1]);
             }
-            tmem_st16(t_lane + a_col + bt * 16, rh);
-            tmem_st16(t_lane + a_col + 64 + bt * 16, rl);
+            tmem_st16(t_a + half * 32 + bt * 16, rh);
+            tmem_st16(t_a + 64 + half * 32 + bt * 16, rl);
           }
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(smem_u32(&sh->go[grp]));
+          mbar_arrive(bar_go);
 
-          // ---- E3: logits -> knots -> spline, two dims per output-layer pass ----
+          // ---- E3: logits -> knots -> spline; this thread takes dim 2p + half of pass p ----
           float ldsum = 0.0f;
-          for (int p = 0; p < lay.n_pass; ++p) {
-            mbar_wait(smem_u32(&sh->done[grp]), ph_done);
+          for (int p = 0; p < n_pass; ++p) {
+            mbar_wait(bar_done, ph_done);
             ph_done ^= 1u;
             tc_fence_after();
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int d = 2 * p + j;
-              if (d < L) {  // warp-uniform
-                float lg[48];
-                tmem_ld16(t_lane + d_col + 48 * j, lg);
-                tmem_ld16(t_lane + d_col + 48 * j + 16, lg + 16);
-                tmem_ld16(t_lane + d_col + 48 * j + 32, lg + 32);
-                tc_wait_ld();
-                const float* bb = sb3 + p * TC_PASS_N + 48 * j;
-#pragma unroll
-                for (int q = 0; q < 48; q += 4) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(bb + q);
-                  lg[q + 0] = fmaf(lg[q + 0], s3inv, b4.x);
-                  lg[q + 1] = fmaf(lg[q + 1], s3inv, b4.y);
-                  lg[q + 2] = fmaf(lg[q + 2], s3inv, b4.z);
-                  lg[q + 3] = fmaf(lg[q + 3], s3inv, b4.w);
-                }
-                float xin = 0.0f;
-#pragma unroll
-                for (int dd = 0; dd < TC_L_MAX; ++dd) xin = (dd == d) ? low[dd] : xin;
-                float y, ldd;
-                int idx;
-                spline_regs<INV>(lg, xin, st.B, st.periodic != 0, y, ldd, idx);
-                ldsum += ldd;  // log_det.sum(axis=1), dims in order
-                if (valid) {
-                  wr[sh->perm[U + d]] = y;
-                  if (args.bins != nullptr) args.bins[(row0 + r) * plan->n_spline_dims + st.bins_off + d] = idx;
-                }
-              }
+            const int d = 2 * p + half;
+            const bool mine = d < L;  // warp-uniform
+            float raw[48];
+            if (mine) {
+              tmem_ld16(t_d + 48 * half, raw);
+              tmem_ld16(t_d + 48 * half + 16, raw + 16);
+              tmem_ld16(t_d + 48 * half + 32, raw + 32);
+              tc_wait_ld();
             }
-            if (p + 1 < lay.n_pass) {  // accumulator drained: the next pass may overwrite it
+            if (p + 1 < n_pass) {  // accumulator drained: the next pass may overwrite it
               tc_fence_before();
-              mbar_arrive(smem_u32(&sh->go[grp]));
+              mbar_arrive(bar_go);
+            }
+            if (mine) {
+              const int col = st.perm[U + d];
+              const float xin = srow[col * CR];
+              float y, ldd;
+              int idx;
+              spline_regs<INV>(raw, sb3 + p * TC_PASS_N + 48 * half, s3inv, xin, B, periodic, y, ldd, idx);
+              ldsum += ldd;
+              srow[col * CR] = y;
+              if (valid && args.bins != nullptr)
+                args.bins[(row0 + r) * plan->n_spline_dims + st.bins_off + d] = idx;
             }
           }
-          if (valid) wr[D + level] += INV ? -ldsum : ldsum;
+          srow[(COL_PEND + half) * CR] = INV ? -ldsum : ldsum;
         }
-      } else if (lane == 0) {
-        // =============================== MMA issuer ===============================
-        const uint32_t sb = smem_u32(blob);
-        const uint32_t idesc2 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc3 = (1u << 4) | ((uint32_t)(TC_PASS_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        for (int pair = 0; pair < npairs; ++pair) {
-          for (int g = 0; g < 2; ++g) {
-            mbar_wait(smem_u32(&sh->go[g]), ph_go[g]);
-            ph_go[g] ^= 1u;
-            tc_fence_after();
-            issue_gemm(tbase + g * 256 + 128, tbase + g * 256, sb + lay.w2hi, sb + lay.w2lo, 128, idesc2);
-            umma_commit(smem_u32(&sh->done[g]));
-          }
-          for (int p = 0; p < lay.n_pass; ++p) {
-            for (int g = 0; g < 2; ++g) {
-              mbar_wait(smem_u32(&sh->go[g]), ph_go[g]);
-              ph_go[g] ^= 1u;
-              tc_fence_after();
-              const uint32_t w3 = sb + lay.w3 + p * 2 * TC_W3_BYTES;
-              issue_gemm(tbase + g * 256 + 128, tbase + g * 256, w3, w3 + TC_W3_BYTES, TC_PASS_N, idesc3);
-              umma_commit(smem_u32(&sh->done[g]));
-            }
-          }
-        }
+        mbar_arrive(smem_u32(&sh->lay_done[grp]));
+        pending = true;
+        pend_level = level;
+        ++seq;
       }
-      tc_fence_before();
-      __syncthreads();  // weights, TMEM and the workspace rows are settled before the next stage
-      tc_fence_after();
-    }
+      named_bar_sync(1, TC_EPI_THREADS);
 
-    // ---- pass Z: trailing steps, latent log-density, outputs ----
-    if (is_epi) {
-      for (int r = tid; r < nrows; r += 256) {
+      // ---- pass Z: trailing steps, latent log-density, outputs ----
+      for (int r = tid; r < nrows; r += TC_EPI_THREADS) {
         const long long row = row0 + r;
-        float* wr = ws + (size_t)r * RS;
+        float* st = state + r;
+        if (pending) st[(D + pend_level) * CR] += st[COL_PEND * CR] + st[(COL_PEND + 1) * CR];
         int lv = level;
-        light_steps_row(plan, INV, prev_end, ns, lv, wr);
+        light_steps_cols(plan, INV, prev_end, ns, lv, st, CR);
         if (args.mode == MODE_LOGPROB || args.mode == MODE_POSTERIOR) {
           const float lat = pz_latent_logprob(plan->latent_kind, D, plan->latent_B, plan->latent_const,
-                                              [&](int j) { return wr[plan->perm_final[j]]; });
-          const float lp = pz_nan_to_num_lp(lat + wr[D]);
-          args.out0[row] = (args.mode == MODE_POSTERIOR) ? expf(lp) : lp;
+                                              [&](int j) { return st[plan->perm_final[j] * CR]; });
+          const float lpv = pz_nan_to_num_lp(lat + st[D * CR]);
+          args.out0[row] = (args.mode == MODE_POSTERIOR) ? expf(lpv) : lpv;
         } else {
-          for (int j = 0; j < D; ++j) args.out0[row * D + j] = wr[INV ? j : plan->perm_final[j]];
-          if (args.out1 != nullptr) args.out1[row] = wr[D];
+          for (int j = 0; j < D; ++j) args.out0[row * D + j] = st[(INV ? j : plan->perm_final[j]) * CR];
+          if (args.out1 != nullptr) args.out1[row] = st[D * CR];
         }
       }
+      // (pass A of the next chunk touches a row from the same thread as pass Z did: no barrier needed)
     }
-    __syncthreads();
+  } else if (lane == 0) {
+    // =============================== MMA issuer + weight streamer ===============================
+    const uint32_t sb = smem_u32(base);
+    const uint32_t idesc2 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc3 = (1u << 4) | ((uint32_t)(TC_PASS_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int total_seq = my_chunks * n_nsc;
+
+    // coupling stage (walk order) of sequence number s, and the tile count of its chunk
+    auto stage_of = [&](int s) -> const NscDev& { return plan->nsc[sh->order[s % n_nsc]]; };
+    auto tiles_of = [&](int s) -> int {
+      const long long row0 = ((long long)blockIdx.x + (long long)(s / n_nsc) * gridDim.x) * chunk_rows;
+      const int nrows = (int)min(chunk_rows, args.N - row0);
+      return max(2, (nrows + TC_TILE - 1) / TC_TILE);
+    };
+
+    // per group: sequence number, tile, phase (0 = hidden GEMM, p + 1 = output pass p) and the cached
+    // shape of its current stage
+    int gs[2] = {0, 0}, gk[2] = {0, 0}, gp[2] = {0, 0}, gnp[2], gnt[2];
+    uint32_t gpar[2] = {0u, 0u};
+    bool gready[2] = {false, false};
+    gnp[0] = gnp[1] = total_seq > 0 ? (stage_of(0).L + 1) / 2 : 1;
+    gnt[0] = gnt[1] = total_seq > 0 ? tiles_of(0) : 2;
+    int w2_next = 0, w3_next = 0, par_next = 0;      // next sequence number to load
+    int w2_ready = 0, w3_ready = 0;                  // loads observed complete
+    int w2_freed = 0, w3_freed = 0;                  // buffer releases observed
+    int lay_seen[2] = {0, 0};                        // stages each group has finished
+    int c2_cnt = 0, c3_cnt = 0;                      // GEMMs issued in the stage currently holding W2 / W3
+
+    while (gs[0] < total_seq || gs[1] < total_seq) {
+      bool progress = false;
+      // ---- weight streaming ----
+      if (w2_next < total_seq) {
+        if (w2_next > w2_freed && mbar_test_wait(smem_u32(&sh->w2free), (uint32_t)(w2_freed & 1))) ++w2_freed;
+        if (w2_next <= w2_freed) {
+          const NscDev& st = stage_of(w2_next);
+          const uint32_t bar = smem_u32(&sh->w2full);
+          mbar_expect_tx(bar, TC_W2_BYTES);
+          const uint8_t* src = static_cast<const uint8_t*>(st.tc.blob);
+          for (int off = 0; off < TC_W2_BYTES; off += 16384) tma_bulk_g2s(sb + sl.w2 + off, src + off, 16384u, bar);
+          ++w2_next;
+          progress = true;
+        }
+      }
+      if (w3_next < total_seq) {
+        if (w3_next > w3_freed && mbar_test_wait(smem_u32(&sh->w3free), (uint32_t)(w3_freed & 1))) ++w3_freed;
+        if (w3_next <= w3_freed) {
+          const NscDev& st = stage_of(w3_next);
+          const TcLayout lay = TcLayout::make(st.L);
+          const uint32_t bar = smem_u32(&sh->w3full);
+          const int nb = lay.n_pass * TC_W3_PASS_BYTES;
+          mbar_expect_tx(bar, (uint32_t)nb);
+          const uint8_t* src = static_cast<const uint8_t*>(st.tc.blob) + lay.w3;
+          for (int off = 0; off < nb; off += 16384) tma_bulk_g2s(sb + sl.w3 + off, src + off, 16384u, bar);
+          ++w3_next;
+          progress = true;
+        }
+      }
+      if (par_next < total_seq) {
+        // block par_next reuses the buffer of stage par_next - 2: both groups must have finished it
+        for (int g = 0; g < 2; ++g)
+          if (lay_seen[g] < par_next - 1 && mbar_test_wait(smem_u32(&sh->lay_done[g]), (uint32_t)(lay_seen[g] & 1)))
+            ++lay_seen[g];
+        if (par_next < 2 || (lay_seen[0] >= par_next - 1 && lay_seen[1] >= par_next - 1)) {
+          const NscDev& st = stage_of(par_next);
+          const TcLayout lay = TcLayout::make(st.L);
+          const uint32_t bar = smem_u32(&sh->parfull[par_next & 1]);
+          mbar_expect_tx(bar, TC_PAR_BYTES);
+          tma_bulk_g2s(sb + sl.par + (par_next & 1) * TC_PAR_BYTES, static_cast<const uint8_t*>(st.tc.blob) + lay.par,
+                       TC_PAR_BYTES, bar);
+          ++par_next;
+          progress = true;
+        }
+      }
+      // ---- GEMMs: serve whichever group is ready ----
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (gs[g] >= total_seq) continue;
+        if (!gready[g]) {
+          if (!mbar_test_wait(smem_u32(&sh->go[g]), gpar[g])) continue;
+          gpar[g] ^= 1u;
+          gready[g] = true;
+        }
+        const int s = gs[g];
+        if (gp[g] == 0) {
+          if (w2_ready <= s) {
+            if (w2_next > s && mbar_test_wait(smem_u32(&sh->w2full), (uint32_t)(s & 1))) w2_ready = s + 1;
+            else continue;
+          }
+        } else {
+          if (w3_ready <= s) {
+            if (w3_next > s && mbar_test_wait(smem_u32(&sh->w3full), (uint32_t)(s & 1))) w3_ready = s + 1;
+            else continue;
+          }
+        }
+        tc_fence_after();
+        const uint32_t a_t = tbase + g * 256, d_t = tbase + g * 256 + 128;
+        if (gp[g] == 0) {
+          issue_gemm(d_t, a_t, sb + sl.w2, sb + sl.w2 + TC_W2_BYTES / 2, 128, idesc2);
+          umma_commit(smem_u32(&sh->done[g]));
+          if (++c2_cnt == gnt[g]) {  // every hidden GEMM of the stage is issued: release W2 when they complete
+            umma_commit(smem_u32(&sh->w2free));
+            c2_cnt = 0;
+          }
+        } else {
+          const uint32_t w3 = sb + sl.w3 + (gp[g] - 1) * TC_W3_PASS_BYTES;
+          issue_gemm(d_t, a_t, w3, w3 + TC_W3_PASS_BYTES / 2, TC_PASS_N, idesc3);
+          umma_commit(smem_u32(&sh->done[g]));
+          if (++c3_cnt == gnt[g] * gnp[g]) {
+            umma_commit(smem_u32(&sh->w3free));
+            c3_cnt = 0;
+          }
+        }
+        gready[g] = false;
+        progress = true;
+        if (++gp[g] > gnp[g]) {
+          gp[g] = 0;
+          if (++gk[g] == (gnt[g] - g + 1) / 2) {
+            gk[g] = 0;
+            if (++gs[g] < total_seq) {
+              gnp[g] = (stage_of(gs[g]).L + 1) / 2;
+              gnt[g] = tiles_of(gs[g]);
+            }
+          }
+        }
+      }
+      if (!progress) __nanosleep(20);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "n"(512) : "memory");
   }
 }
@@ -661,28 +861,46 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, float* __
 cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms, void* workspace,
                       cudaStream_t stream) {
   (void)workspace;
-  int blob = 0;
-  for (int s = 0; s < hp.n_nsc; ++s) blob = max(blob, TcLayout::make(hp.nsc[s].L).total);
-  const size_t smem = (size_t)blob + sizeof(TcShared) + 1024 + 64;
+  TcLaunch lp;
+  lp.max_pass = 1;
+  for (int s = 0; s < hp.n_nsc; ++s) lp.max_pass = max(lp.max_pass, (hp.nsc[s].L + 1) / 2);
+  // chain nesting depth actually used (log-det levels)
+  int depth = 0, level = 0;
+  for (int i = 0; i < hp.n_steps; ++i) {
+    if (hp.steps[i].kind == STEP_CHAIN_BEGIN) depth = max(depth, ++level);
+    else if (hp.steps[i].kind == STEP_CHAIN_END) --level;
+  }
+  lp.n_lev = depth + 1;
+  lp.state_cols = hp.D + lp.n_lev + 2 + hp.C;
+  // rows per chunk: as many 128-row tiles as shared memory holds, fewer when that leaves SMs idle
+  int fit = TC_MAX_CHUNK_TILES;
+  while (fit > 2 && tc_smem_layout(lp.max_pass, fit, lp.state_cols).total + 1024 > TC_SMEM_MAX) --fit;
+  const long long tiles_total = (args.N + TC_TILE - 1) / TC_TILE;
+  long long want = (tiles_total + num_sms - 1) / num_sms;
+  if (want < 2) want = 2;
+  lp.chunk_tiles = (int)(want < fit ? want : fit);
+  if (lp.chunk_tiles > 8 && want > fit) {
+    // balance: the largest chunk size <= fit that leaves the last wave as full as possible is not worth
+    // a search here; 8 tiles keep the per-stage weight reload below 2 % of the stage's math
+    lp.chunk_tiles = fit;
+  }
+  const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols);
+  const size_t smem = (size_t)sl.total + 1024;
+  if (smem > (size_t)TC_SMEM_MAX) return cudaErrorInvalidConfiguration;
   const bool inv = (args.mode == MODE_INVERSE);
   cudaError_t e = inv ? cudaFuncSetAttribute(nsf_chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                       : cudaFuncSetAttribute(nsf_chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const long long n_chunks = (args.N + TC_CHUNK - 1) / TC_CHUNK;
+  const long long chunk_rows = (long long)lp.chunk_tiles * TC_TILE;
+  const long long n_chunks = (args.N + chunk_rows - 1) / chunk_rows;
   long long grid = num_sms;
   if (grid > n_chunks) grid = n_chunks;
   if (grid < 1) grid = 1;
-  const int RS = hp.D + MAX_CHAIN_DEPTH + hp.C;
-  float* ws = nullptr;
-  e = cudaMallocAsync(&ws, (size_t)grid * TC_CHUNK * RS * sizeof(float), stream);
-  if (e != cudaSuccess) return e;
   if (inv)
-    nsf_chain_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, ws, blob);
+    nsf_chain_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, lp);
   else
-    nsf_chain_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, ws, blob);
-  e = cudaGetLastError();
-  cudaError_t e2 = cudaFreeAsync(ws, stream);
-  return e != cudaSuccess ? e : e2;
+    nsf_chain_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, lp);
+  return cudaGetLastError();
 }
 
 }  // namespace pzb
