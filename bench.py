@@ -227,8 +227,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the Flow-facing API with pinned host buffers ----
     def e2e_step():
-        lp = flow._log_prob(flow._params, X_host)  # H2D copy of the step's rows, then the kernel
-        return lp.cpu()                            # D2H read of the result
+        # pinned HOST rows in, HOST result out, through the host-buffer C-ABI call
+        # (pzb_log_prob_host): chunked H2D | kernel | D2H pipeline, blocking
+        return flow._log_prob(flow._params, X_host)
     for _ in range(2):
         e2e_step()
     barrier()

@@ -190,6 +190,27 @@ int pzb_normalize_pdfs(float *pdfs, int64_t Ng, int32_t G, const float *grid,
  * jax.random's threefry stream; sample parity is defined on the map u -> x. */
 int pzb_sample_uniform(float *U, int64_t N, int32_t D, float B, uint64_t seed, void *stream);
 
+/* ---- host-buffer forms --------------------------------------------------
+ * The same evaluations for callers whose arrays live in HOST memory, which is
+ * where the reference's callers hold them (NumPy arrays cut from a DataFrame,
+ * pzflow/flow.py:440-446, 697-737, 783-795).  All data pointers below are
+ * HOST pointers.  Rows are cut into chunks that move through a three-deep ring
+ * of device staging buffers on plan-owned streams, so H2D copy, chain kernel
+ * and D2H copy of consecutive chunks overlap and HBM holds three chunks at
+ * most (the 4 GB posterior of config 3 never sits on the device as a whole).
+ * Blocking: the results are in the output arrays on return.  Page-locked host
+ * arrays move at PCIe speed; pageable arrays work but do not overlap.  Calls on
+ * one plan serialise. */
+int pzb_log_prob_host(const pzb_plan *plan, const float *X, const float *cond, int64_t N,
+                      float *out);
+int pzb_forward_host(const pzb_plan *plan, const float *X, const float *cond, int64_t N,
+                     float *U, float *log_det);
+int pzb_inverse_host(const pzb_plan *plan, const float *U, const float *cond, int64_t N,
+                     float *X, float *log_det);
+int pzb_posterior_host(const pzb_plan *plan, const float *rest, const float *cond, int64_t Ng,
+                       int32_t col_idx, const float *grid, int32_t G, int32_t normalize,
+                       int32_t nan_to_zero, float *pdfs);
+
 #ifdef __cplusplus
 }
 #endif

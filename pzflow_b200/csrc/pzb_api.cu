@@ -4,7 +4,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -40,6 +42,22 @@ static int cuda_fail(cudaError_t e, const char* what) {
   return fail(PZB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
+// Streams, events and device staging buffers of the host-buffer entry points (pzb_*_host): a
+// three-deep ring so chunk i's H2D copy, chunk i-1's kernel and chunk i-2's D2H copy overlap.
+struct HostPipe {
+  static constexpr int NBUF = 3;
+  std::mutex mu;
+  bool ready = false;
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[NBUF] = {}, ev_k[NBUF] = {}, ev_out[NBUF] = {};
+  void* d_in[NBUF] = {};
+  void* d_cond[NBUF] = {};
+  void* d_out0[NBUF] = {};
+  void* d_out1[NBUF] = {};
+  void* d_grid = nullptr;
+  size_t cap_in = 0, cap_cond = 0, cap_out0 = 0, cap_out1 = 0, cap_grid = 0;
+};
+
 struct pzb_plan {
   int device = 0;
   int num_sms = 0;
@@ -52,6 +70,7 @@ struct pzb_plan {
   double flops_per_row = 0.0;
   bool tc_ok = false;
   int engine = PZB_ENGINE_AUTO;
+  mutable HostPipe pipe;
 };
 
 struct DeviceGuard {
@@ -385,6 +404,25 @@ void pzb_plan_destroy(pzb_plan* plan) {
   DeviceGuard guard(plan->device);
   if (plan->d_plan) cudaFree(plan->d_plan);
   if (plan->d_weights) cudaFree(plan->d_weights);
+  HostPipe& hp = plan->pipe;
+  if (hp.ready) {
+    cudaStreamSynchronize(hp.s_in);
+    cudaStreamSynchronize(hp.s_k);
+    cudaStreamSynchronize(hp.s_out);
+    for (int b = 0; b < HostPipe::NBUF; ++b) {
+      cudaFree(hp.d_in[b]);
+      cudaFree(hp.d_cond[b]);
+      cudaFree(hp.d_out0[b]);
+      cudaFree(hp.d_out1[b]);
+      cudaEventDestroy(hp.ev_in[b]);
+      cudaEventDestroy(hp.ev_k[b]);
+      cudaEventDestroy(hp.ev_out[b]);
+    }
+    cudaFree(hp.d_grid);
+    cudaStreamDestroy(hp.s_in);
+    cudaStreamDestroy(hp.s_k);
+    cudaStreamDestroy(hp.s_out);
+  }
   delete plan;
 }
 
@@ -667,6 +705,201 @@ int pzb_sample_uniform(float* U, int64_t N, int32_t D, float B, uint64_t seed, v
   if (ce != cudaSuccess) return cuda_fail(ce, "sample_uniform launch");
   g_launches.fetch_add(1);
   return PZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer entry points: the same evaluations for callers whose arrays live in HOST memory
+// (the reference's NumPy / DataFrame world, pzflow/flow.py:440-446).  Rows are cut into chunks
+// that flow through a three-deep ring of device staging buffers on three streams, so the H2D
+// copy of chunk i, the chain kernel of chunk i-1 and the D2H copy of chunk i-2 overlap; HBM
+// never holds more than three chunks.  Blocking: results are in the host buffers on return.
+// Pinned (page-locked) host arrays copy at PCIe speed; pageable ones still work (the driver
+// stages them) but do not overlap.
+// ---------------------------------------------------------------------------------------------
+struct HostJob {
+  int mode = MODE_LOGPROB;
+  const float* in = nullptr;   // [units, in_w]
+  int in_w = 0;
+  const float* cond = nullptr; // [units, C] or NULL
+  float* out0 = nullptr;       // [units, out0_w]
+  int out0_w = 1;
+  float* out1 = nullptr;       // [units] or NULL
+  const float* grid = nullptr; // posterior: host [G]
+  int G = 1, col_idx = 0, normalize = 0, nan_to_zero = 0;
+  int64_t units = 0;           // rows, or galaxies for the posterior
+};
+
+static cudaError_t pipe_reserve(void** p, size_t* cap, size_t want, int n) {
+  if (want <= *cap) return cudaSuccess;
+  for (int b = 0; b < n; ++b) {
+    if (p[b]) cudaFree(p[b]);
+    p[b] = nullptr;
+  }
+  *cap = 0;
+  for (int b = 0; b < n; ++b) {
+    cudaError_t e = cudaMalloc(&p[b], want);
+    if (e != cudaSuccess) return e;
+  }
+  *cap = want;
+  return cudaSuccess;
+}
+
+static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
+  if (job.units == 0) return PZB_OK;
+  HostPipe& hp = plan->pipe;
+  std::lock_guard<std::mutex> lock(hp.mu);
+  DeviceGuard guard(plan->device);
+  if (!guard.ok) return fail(PZB_ERR_CUDA, "%s: cannot select device %d", who, plan->device);
+  cudaError_t ce = cudaSuccess;
+  if (!hp.ready) {
+    ce = cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&hp.s_k, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking);
+    for (int b = 0; b < HostPipe::NBUF && ce == cudaSuccess; ++b) {
+      ce = cudaEventCreateWithFlags(&hp.ev_in[b], cudaEventDisableTiming);
+      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&hp.ev_k[b], cudaEventDisableTiming);
+      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&hp.ev_out[b], cudaEventDisableTiming);
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "host pipeline setup");
+    hp.ready = true;
+  }
+  const int C = plan->host.C;
+  const int rows_per_unit = (job.mode == MODE_POSTERIOR) ? job.G : 1;
+  // chunk: ~1.2 M chain rows (8 waves of 148 CTAs x 1024 rows), staging buffers <= 64 MB each
+  int64_t chunk = (int64_t)plan->num_sms * 1024 * 8 / rows_per_unit;
+  const int64_t widest = (int64_t)sizeof(float) * std::max<int64_t>(std::max(job.in_w, C), job.out0_w);
+  if (widest > 0 && chunk * widest > (64ll << 20)) chunk = (64ll << 20) / widest;
+  if (chunk < 1) chunk = 1;
+  if (chunk > job.units) chunk = job.units;
+  // every ring buffer may still be in flight from this call only (the previous call drained)
+  ce = pipe_reserve(hp.d_in, &hp.cap_in, (size_t)chunk * std::max(job.in_w, 1) * sizeof(float), HostPipe::NBUF);
+  if (ce == cudaSuccess && C > 0)
+    ce = pipe_reserve(hp.d_cond, &hp.cap_cond, (size_t)chunk * C * sizeof(float), HostPipe::NBUF);
+  if (ce == cudaSuccess)
+    ce = pipe_reserve(hp.d_out0, &hp.cap_out0, (size_t)chunk * job.out0_w * sizeof(float), HostPipe::NBUF);
+  if (ce == cudaSuccess && job.out1)
+    ce = pipe_reserve(hp.d_out1, &hp.cap_out1, (size_t)chunk * sizeof(float), HostPipe::NBUF);
+  if (ce == cudaSuccess && job.grid) {
+    ce = pipe_reserve(&hp.d_grid, &hp.cap_grid, (size_t)job.G * sizeof(float), 1);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(hp.d_grid, job.grid, (size_t)job.G * sizeof(float), cudaMemcpyHostToDevice, hp.s_k);
+  }
+  if (ce != cudaSuccess) return cuda_fail(ce, "host pipeline staging buffers");
+
+  int rc = PZB_OK;
+  int64_t i = 0;
+  for (int64_t u0 = 0; u0 < job.units && rc == PZB_OK; u0 += chunk, ++i) {
+    const int b = (int)(i % HostPipe::NBUF);
+    const int64_t nu = std::min(chunk, job.units - u0);
+    if (i >= HostPipe::NBUF) cudaStreamWaitEvent(hp.s_in, hp.ev_k[b], 0);  // kernel i-NBUF has read d_in[b]
+    if (job.in_w > 0)
+      ce = cudaMemcpyAsync(hp.d_in[b], job.in + u0 * job.in_w, (size_t)nu * job.in_w * sizeof(float),
+                           cudaMemcpyHostToDevice, hp.s_in);
+    if (ce == cudaSuccess && C > 0)
+      ce = cudaMemcpyAsync(hp.d_cond[b], job.cond + u0 * C, (size_t)nu * C * sizeof(float), cudaMemcpyHostToDevice,
+                           hp.s_in);
+    if (ce == cudaSuccess) ce = cudaEventRecord(hp.ev_in[b], hp.s_in);
+    if (ce != cudaSuccess) { rc = cuda_fail(ce, "host pipeline H2D"); break; }
+    cudaStreamWaitEvent(hp.s_k, hp.ev_in[b], 0);
+    if (i >= HostPipe::NBUF) cudaStreamWaitEvent(hp.s_k, hp.ev_out[b], 0);  // D2H i-NBUF has read d_out[b]
+    LaunchArgs a{};
+    a.mode = job.mode;
+    a.X = static_cast<const float*>(hp.d_in[b]);
+    a.cond = C > 0 ? static_cast<const float*>(hp.d_cond[b]) : nullptr;
+    a.grid = static_cast<const float*>(hp.d_grid);
+    a.G = job.G;
+    a.col_idx = job.col_idx;
+    a.N = nu * rows_per_unit;
+    a.out0 = static_cast<float*>(hp.d_out0[b]);
+    a.out1 = job.out1 ? static_cast<float*>(hp.d_out1[b]) : nullptr;
+    rc = launch_chain(plan, a, hp.s_k);
+    if (rc == PZB_OK && job.mode == MODE_POSTERIOR && (job.normalize || job.nan_to_zero))
+      rc = pzb_normalize_pdfs(a.out0, nu, job.G, a.grid, job.normalize, job.nan_to_zero, hp.s_k);
+    if (rc != PZB_OK) break;
+    cudaEventRecord(hp.ev_k[b], hp.s_k);
+    cudaStreamWaitEvent(hp.s_out, hp.ev_k[b], 0);
+    ce = cudaMemcpyAsync(job.out0 + u0 * job.out0_w, hp.d_out0[b], (size_t)nu * job.out0_w * sizeof(float),
+                         cudaMemcpyDeviceToHost, hp.s_out);
+    if (ce == cudaSuccess && job.out1)
+      ce = cudaMemcpyAsync(job.out1 + u0, hp.d_out1[b], (size_t)nu * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out);
+    if (ce == cudaSuccess) ce = cudaEventRecord(hp.ev_out[b], hp.s_out);
+    if (ce != cudaSuccess) { rc = cuda_fail(ce, "host pipeline D2H"); break; }
+  }
+  // drain everything, also on the error path: the ring must be idle when the next call starts
+  cudaError_t e1 = cudaStreamSynchronize(hp.s_in), e2 = cudaStreamSynchronize(hp.s_k),
+              e3 = cudaStreamSynchronize(hp.s_out);
+  if (rc != PZB_OK) return rc;
+  ce = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+  if (ce != cudaSuccess) return cuda_fail(ce, who);
+  return PZB_OK;
+}
+
+int pzb_log_prob_host(const pzb_plan* plan, const float* X, const float* cond, int64_t N, float* out) {
+  int rc = check_common(plan, X, cond, N, out, "log_prob_host");
+  if (rc) return rc;
+  HostJob j;
+  j.mode = MODE_LOGPROB;
+  j.in = X;
+  j.in_w = plan->host.D;
+  j.cond = cond;
+  j.out0 = out;
+  j.out0_w = 1;
+  j.units = N;
+  return run_host(plan, j, "log_prob_host");
+}
+
+int pzb_forward_host(const pzb_plan* plan, const float* X, const float* cond, int64_t N, float* U, float* log_det) {
+  int rc = check_common(plan, X, cond, N, U, "forward_host");
+  if (rc) return rc;
+  HostJob j;
+  j.mode = MODE_FORWARD;
+  j.in = X;
+  j.in_w = plan->host.D;
+  j.cond = cond;
+  j.out0 = U;
+  j.out0_w = plan->host.D;
+  j.out1 = log_det;
+  j.units = N;
+  return run_host(plan, j, "forward_host");
+}
+
+int pzb_inverse_host(const pzb_plan* plan, const float* U, const float* cond, int64_t N, float* X, float* log_det) {
+  int rc = check_common(plan, U, cond, N, X, "inverse_host");
+  if (rc) return rc;
+  HostJob j;
+  j.mode = MODE_INVERSE;
+  j.in = U;
+  j.in_w = plan->host.D;
+  j.cond = cond;
+  j.out0 = X;
+  j.out0_w = plan->host.D;
+  j.out1 = log_det;
+  j.units = N;
+  return run_host(plan, j, "inverse_host");
+}
+
+int pzb_posterior_host(const pzb_plan* plan, const float* rest, const float* cond, int64_t Ng, int32_t col_idx,
+                       const float* grid, int32_t G, int32_t normalize, int32_t nan_to_zero, float* pdfs) {
+  int rc = check_common(plan, plan && plan->host.D > 1 ? (const void*)rest : (const void*)grid, cond, Ng, pdfs,
+                        "posterior_host");
+  if (rc) return rc;
+  if (G < 1 || grid == nullptr) return fail(PZB_ERR_INVALID, "posterior_host: empty grid");
+  if (col_idx < 0 || col_idx >= plan->host.D)
+    return fail(PZB_ERR_INVALID, "posterior_host: column index %d out of range", col_idx);
+  HostJob j;
+  j.mode = MODE_POSTERIOR;
+  j.in = rest;
+  j.in_w = plan->host.D - 1;
+  j.cond = cond;
+  j.out0 = pdfs;
+  j.out0_w = G;
+  j.grid = grid;
+  j.G = G;
+  j.col_idx = col_idx;
+  j.normalize = normalize;
+  j.nan_to_zero = nan_to_zero;
+  j.units = Ng;
+  return run_host(plan, j, "posterior_host");
 }
 
 }  // extern "C"

@@ -46,6 +46,15 @@ def _load_pickle(file: str) -> dict:
             sys.modules.pop(k, None)
 
 
+def _pinned_f32(a: np.ndarray) -> torch.Tensor:
+    """Cast/copy a host array into a page-locked float32 tensor in one pass, so the H2D copies of
+    the host-buffer entry points run at PCIe speed and overlap with the kernel."""
+    a = np.asarray(a)
+    t = torch.empty(a.shape, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+    np.copyto(t.numpy(), a, casting="unsafe")
+    return t
+
+
 def _to_numpy_tree(p):
     if isinstance(p, (list, tuple)):
         return type(p)(_to_numpy_tree(q) for q in p)
@@ -198,7 +207,7 @@ class Flow:
         self._check_bijector()
         if err_samples is None:
             columns = list(self.data_columns)
-            X = inputs[columns].to_numpy().astype(np.float32, copy=False)
+            X = _pinned_f32(inputs[columns].to_numpy())  # the float64 -> float32 down-cast (flow.py:442)
             conditions = self._get_conditions(inputs)
             return self._log_prob(self._params, X, conditions).cpu().numpy()
         assert isinstance(err_samples, int), "err_samples must be a positive integer."
@@ -230,21 +239,16 @@ class Flow:
             return self._posterior_marginalized(inputs, column, columns, grid, marg_rules, normalize,
                                                 batch_size, nan_to_zero)
 
+        # The reference loops over batch_size rows because it materialises [batch * G, D]
+        # (pzflow/flow.py:697-730) and normalises once at the end (732-737).  Here the expansion is
+        # generated inside the kernel and the host-buffer entry point cuts the galaxies into chunks
+        # itself (normalisation is per galaxy, so chunking cannot change it): batch_size is accepted
+        # for signature compatibility and has no effect on the result.
         plan = self._plan()
-        grid_t = torch.from_numpy(grid).to(plan.device)
-        pdfs = torch.empty((nrows, grid.size), dtype=torch.float32, device=plan.device)
-        for b0 in range(0, nrows, max(1, batch_size)):
-            batch = inputs.iloc[b0:b0 + batch_size]
-            conditions = self._get_conditions(batch)
-            rest = batch[columns].to_numpy().astype(np.float32, copy=False).reshape(len(batch), -1)
-            # un-normalised exp(log_prob); normalisation happens once over all rows below,
-            # exactly like pzflow/flow.py:732-737
-            plan.posterior(rest, idx, grid_t, conditions, normalize=False, nan_to_zero=False,
-                           out=pdfs[b0:b0 + batch_size])
-        if normalize or nan_to_zero:
-            from .plan import normalize_pdfs_
-            normalize_pdfs_(pdfs, grid_t, normalize, nan_to_zero)
-        return pdfs.cpu().numpy()
+        conditions = self._get_conditions(inputs)
+        rest = _pinned_f32(inputs[columns].to_numpy().reshape(nrows, -1))
+        pdfs = plan.posterior_host(rest, idx, grid, conditions, normalize=normalize, nan_to_zero=nan_to_zero)
+        return pdfs.numpy()
 
     def _posterior_marginalized(self, inputs, column, columns, grid, marg_rules, normalize, batch_size,
                                 nan_to_zero):

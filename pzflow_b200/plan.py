@@ -177,9 +177,73 @@ class Plan:
         t = t[:, : self.n_conditions]
         return t.to(device=self.device, dtype=torch.float32).contiguous()
 
+    # ---- host-buffer entry points (blocking; chunks pipelined H2D | kernel | D2H) -------
+    def _host_rows(self, X, width: int, what: str) -> torch.Tensor:
+        """A C-contiguous float32 CPU tensor view of X (no copy when X already is one)."""
+        t = torch.as_tensor(X) if not isinstance(X, torch.Tensor) else X
+        if t.dim() != 2 or t.shape[1] != width:
+            raise ValueError(f"{what} must have shape [N, {width}], got {tuple(t.shape)}")
+        return t.to(dtype=torch.float32).contiguous()
+
+    def _host_cond(self, cond, n_rows: int) -> Optional[torch.Tensor]:
+        if self.n_conditions == 0:
+            return None
+        if cond is None:
+            raise ValueError(f"this bijector is conditional: conditions [N, {self.n_conditions}] are required")
+        t = torch.as_tensor(cond) if not isinstance(cond, torch.Tensor) else cond
+        if t.dim() != 2 or t.shape[0] != n_rows or t.shape[1] < self.n_conditions:
+            raise ValueError(f"conditions must have shape [{n_rows}, {self.n_conditions}], got {tuple(t.shape)}")
+        return t[:, : self.n_conditions].to(dtype=torch.float32).contiguous()
+
+    def log_prob_host(self, X, cond=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Flow._log_prob on HOST arrays -> pinned CPU tensor [N] (pzb_log_prob_host)."""
+        X = self._host_rows(X, self.input_dim, "inputs")
+        cond = self._host_cond(cond, X.shape[0])
+        if out is None:
+            out = pinned_empty((X.shape[0],))
+        N.check(N.lib().pzb_log_prob_host(self._h, _ptr(X), _ptr(cond), X.shape[0], _ptr(out)))
+        return out
+
+    def inverse_host(self, U, cond=None, want_log_det: bool = False):
+        """Chain InverseFunction on HOST arrays -> (x [N, D], log_det [N] or None), pinned CPU tensors."""
+        U = self._host_rows(U, self.input_dim, "inputs")
+        cond = self._host_cond(cond, U.shape[0])
+        X = pinned_empty(tuple(U.shape))
+        ld = pinned_empty((U.shape[0],)) if want_log_det else None
+        N.check(N.lib().pzb_inverse_host(self._h, _ptr(U), _ptr(cond), U.shape[0], _ptr(X), _ptr(ld)))
+        return X, ld
+
+    def forward_host(self, X, cond=None):
+        """Chain ForwardFunction on HOST arrays -> (u [N, D], log_det [N]), pinned CPU tensors."""
+        X = self._host_rows(X, self.input_dim, "inputs")
+        cond = self._host_cond(cond, X.shape[0])
+        U = pinned_empty(tuple(X.shape))
+        ld = pinned_empty((X.shape[0],))
+        N.check(N.lib().pzb_forward_host(self._h, _ptr(X), _ptr(cond), X.shape[0], _ptr(U), _ptr(ld)))
+        return U, ld
+
+    def posterior_host(self, rest, col_idx: int, grid, cond=None, normalize: bool = True,
+                       nan_to_zero: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Flow.posterior main loop on HOST arrays: rest [Ng, D-1], grid [G] -> pinned pdfs [Ng, G];
+        neither the [Ng*G, D] expansion nor the whole pdfs array ever sits in HBM."""
+        rest = self._host_rows(rest, self.input_dim - 1, "inputs")
+        cond = self._host_cond(cond, rest.shape[0])
+        grid = torch.as_tensor(grid).to(dtype=torch.float32).contiguous().reshape(-1).cpu()
+        Ng, G = rest.shape[0], grid.numel()
+        if out is None:
+            out = pinned_empty((Ng, G))
+        N.check(N.lib().pzb_posterior_host(self._h, _ptr(rest) if rest.numel() else None, _ptr(cond), Ng,
+                                           int(col_idx), _ptr(grid), G, int(bool(normalize)),
+                                           int(bool(nan_to_zero)), _ptr(out)))
+        return out
+
     # ---- entry points (all asynchronous on torch's current stream) -------
     def log_prob(self, X, cond=None, return_bins: bool = False):
-        """Flow._log_prob (pzflow/flow.py:397-407) on device tensors."""
+        """Flow._log_prob (pzflow/flow.py:397-407).  Device tensors are evaluated in place on torch's
+        current stream; HOST arrays (NumPy / CPU tensors) take the pipelined host-buffer path and
+        come back as a CPU tensor."""
+        if not return_bins and not (isinstance(X, torch.Tensor) and X.is_cuda):
+            return self.log_prob_host(X, cond)
         X = self._rows(X, self.input_dim, "inputs")
         cond = self._cond(cond, X.shape[0])
         out = torch.empty(X.shape[0], dtype=torch.float32, device=self.device)
@@ -275,6 +339,11 @@ def sample_uniform(n: int, dim: int, B: float, seed: int, device=None) -> torch.
         N.check(N.lib().pzb_sample_uniform(_ptr(out), n, dim, float(B), int(seed) & (2 ** 64 - 1),
                                            _stream(device)))
     return out
+
+
+def pinned_empty(shape, dtype=torch.float32) -> torch.Tensor:
+    """Page-locked CPU tensor (torch's caching host allocator): D2H/H2D copies at PCIe speed."""
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
 
 
 def launch_count() -> int:

@@ -429,3 +429,89 @@ def test_uniform_sampler():
     assert abs(float(u.mean())) < 0.02 and abs(float(u.std()) - 10 / np.sqrt(12)) < 0.02
     assert torch.equal(u, sample_uniform(200_000, 7, 5.0, seed=3))
     assert not torch.equal(u, sample_uniform(200_000, 7, 5.0, seed=4))
+
+
+# --------------------------------------------------------------------------- #
+# host-buffer entry points (pzb_*_host): chunked H2D | kernel | D2H pipeline    #
+# --------------------------------------------------------------------------- #
+def _same_bits(a, b):
+    """Bit-for-bit equality (NaN == NaN: idx = K rows carry NaN through forward / inverse)."""
+    return torch.equal(a.cpu().contiguous().view(torch.int32), b.cpu().contiguous().view(torch.int32))
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_pipeline_equals_device_path(pinned):
+    """Several pipeline chunks (3.7 M rows > 3 x 1.2 M), ragged tail, pinned and pageable host
+    arrays: the host-buffer call returns exactly what the device-pointer call computes."""
+    ex = F.example_flow()
+    plan = _plan(ex, "tc")
+    n = 3_700_017
+    base = torch.from_numpy(F.galaxy_rows(50_000, seed=11))
+    X = base.repeat(n // base.shape[0] + 1, 1)[:n].contiguous()
+    X += torch.linspace(0, 1e-3, n)[:, None]
+    if pinned:
+        X = X.pin_memory()
+    want = plan.log_prob(X.cuda())
+    got = plan.log_prob_host(X)
+    assert got.device.type == "cpu" and got.shape == (n,)
+    assert torch.equal(got, want.cpu())
+    assert torch.equal(plan.log_prob(X), got)  # Plan.log_prob routes host arrays to the host path
+    assert torch.equal(plan.log_prob_host(X.numpy()), got)
+    # forward / inverse round trip through the host forms
+    m = 1_300_000
+    u_d, ld_d = plan.forward(X[:m].cuda())
+    u_h, ld_h = plan.forward_host(X[:m])
+    assert _same_bits(u_h, u_d) and _same_bits(ld_h, ld_d)
+    x_d, ldi_d = plan.inverse(u_d)
+    x_h, ldi_h = plan.inverse_host(u_h, want_log_det=True)
+    assert _same_bits(x_h, x_d) and _same_bits(ldi_h, ldi_d)
+    assert plan.inverse_host(u_h[:1000])[1] is None
+    assert plan.log_prob_host(X[:0]).shape == (0,)
+
+
+def test_host_pipeline_posterior_and_conditions():
+    ex = F.example_flow()
+    plan = _plan(ex, "tc")
+    X = F.galaxy_rows(3000, seed=6, oob_frac=0)  # 3000 galaxies x 1000 grid points: 3 chunks
+    rest = torch.from_numpy(np.ascontiguousarray(X[:, 1:]))
+    grid = torch.linspace(0.0, 2.3, 1000)
+    want = plan.posterior(rest.cuda(), 0, grid)
+    got = plan.posterior_host(rest, 0, grid)
+    assert torch.equal(got, want.cpu())
+    un = plan.posterior_host(rest[:70], 0, grid, normalize=False, nan_to_zero=False)
+    assert torch.equal(un, plan.posterior(rest[:70].cuda(), 0, grid, normalize=False, nan_to_zero=False).cpu())
+    # conditional plan: conditions ride the same ring
+    cfg = F.config_c4(1)[0]
+    cplan = _plan(cfg, "tc")
+    rng = np.random.default_rng(2)
+    mins, maxs = ex["bijector_info"][1][0][1][0], ex["bijector_info"][1][0][1][1]
+    n = 2_500_003
+    Xc = torch.from_numpy(rng.uniform(mins, maxs, size=(n, 7)).astype(np.float32))
+    cond = torch.from_numpy(rng.normal(size=(n, 2)).astype(np.float32))
+    assert torch.equal(cplan.log_prob_host(Xc, cond), cplan.log_prob(Xc.cuda(), cond.cuda()).cpu())
+    with pytest.raises(ValueError):
+        cplan.log_prob_host(Xc)
+
+
+def test_flow_api_host_arrays_take_the_pipeline():
+    """Flow.log_prob / Flow.posterior on DataFrames (the reference's call) end in the host-buffer
+    entry points and agree with the device path."""
+    from pzflow_b200 import Flow
+    ex = F.example_flow()
+    flow = Flow(_dictionary={"class": "Flow", "data_columns": F.GALAXY_COLUMNS, "conditional_columns": None,
+                             "condition_means": None, "condition_stds": None, "data_error_model": None,
+                             "condition_error_model": None, "autoscale_conditions": True, "info": None,
+                             "latent_info": ex["latent_info"], "bijector_info": ex["bijector_info"],
+                             "params": ex["params"]})
+    X = F.galaxy_rows(5000, seed=8)
+    df = pd.DataFrame(X.astype(np.float64), columns=F.GALAXY_COLUMNS)
+    lp = flow.log_prob(df)
+    assert isinstance(lp, np.ndarray) and lp.dtype == np.float32
+    np.testing.assert_array_equal(lp, _np(flow._plan().log_prob(torch.from_numpy(X).cuda())))
+    grid = np.linspace(0, 2.3, 200)
+    pdfs = flow.posterior(df[:300], column="redshift", grid=grid)
+    pb = flow.posterior(df[:300], column="redshift", grid=grid, batch_size=64)
+    np.testing.assert_array_equal(pdfs, pb)  # tests/test_flow.py:275-287 of the reference
+    want = flow._plan().posterior(torch.from_numpy(np.ascontiguousarray(X[:300, 1:])).cuda(), 0,
+                                  torch.from_numpy(grid.astype(np.float32)))
+    np.testing.assert_array_equal(pdfs, _np(want))
