@@ -7,21 +7,28 @@
 // in fp32 in TMEM.  Weights are pre-scaled by a power of two so their lo parts stay normal.
 // Measured against the float64 twin this is indistinguishable from an fp32 GEMM.
 //
-// Structure (one persistent CTA per SM, 544 threads):
+// Structure (one persistent CTA per SM, 608 threads):
 //   * 16 epilogue warps in two groups of 8.  A group owns one 128-row tile at a time; TMEM lane =
 //     row, and TWO threads share a row (warp w and w+4 of the group address the same TMEM lane
-//     quarter): each does half of the hidden columns in E1/E2 and one of the two spline
-//     dimensions of an output-layer pass in E3.  The groups ping-pong so the tensor pipe works on
-//     one tile while CUDA cores run the other tile's epilogue.
-//   * warp 16, one elected lane: an event loop that issues every tcgen05.mma / tcgen05.commit
-//     (whichever group is ready first is served first) and streams the weights of the NEXT
-//     coupling stage with TMA bulk copies as soon as the tensor pipe has released a buffer:
-//     W2 (64 KB) after the stage's last hidden GEMM, W3 (48/96 KB) after its last output pass,
-//     the small fp32 parameter block (W1, biases) double buffered.
-//   * A operands (the activations) never touch shared memory: epilogue threads write the fp16
-//     hi/lo pairs straight into TMEM (tcgen05.st) and the MMA reads A from TMEM (.ts form);
-//     B (weights) comes from shared memory, K-major SWIZZLE_128B.
-//   * TMEM (512 columns): group 0: A[0,128) D[128,256); group 1: A[256,384) D[384,512).
+//     quarter): "half" h does hidden columns [64h, 64h+64) in E1/E2 and the spline dimensions
+//     h, h+2 in E3.  The two groups ping-pong, and inside a tile the tensor pipe and the CUDA
+//     cores overlap as well:
+//       - the hidden GEMM is issued as two N = 64 halves with a commit each, so half 0 starts its
+//         E2 while the tensor pipe still computes half 1;
+//       - the output layer is one N = 48 pass per spline dimension into two 48-column
+//         accumulator buffers, so pass p+1 runs while pass p's spline is evaluated.
+//   * warps 16/17, one elected lane each: MMA issuer of group 0/1 (blocking mbarrier waits, every
+//     tcgen05.mma / tcgen05.commit of its group).
+//   * warp 18, one lane: streams the weights of the NEXT coupling stage with TMA bulk copies as
+//     soon as the tensor pipe has released a buffer (W2 64 KB, W3 48/96 KB, the fp32 parameter
+//     block with W1, biases, scales and the stage's column map, double buffered).
+//   * A operands (activations) never touch shared memory: epilogue threads write fp16 hi/lo pairs
+//     straight into TMEM (tcgen05.st) and the MMA reads A from TMEM (.ts form); B (weights) sits in
+//     shared memory, K-major SWIZZLE_128B.
+//   * TMEM (512 columns), per group g two 128-column regions X = 256g, Y = 256g + 128:
+//       E1 writes h1 into X; hidden GEMM X -> Y (fp32 accumulators); E2 rewrites Y IN PLACE with
+//       h2 (32 accumulator columns become 16 hi + 16 lo columns); output passes Y -> X[0,48) /
+//       X[64,112); E3 drains them.  A thread only ever overwrites TMEM columns it alone has read.
 //   * stage-outer order: a CTA takes a chunk of up to 1024 rows whose state (x[D], log-det
 //     levels, conditions) lives in shared memory as [column][row] for the whole chain, and walks
 //     the chunk's tiles once per coupling stage.  HBM sees the input rows and the result only.
@@ -30,6 +37,7 @@
 #include <cuda_fp16.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 
 #include "pzb_common.cuh"
@@ -39,18 +47,28 @@ namespace pzb {
 constexpr int TC_TILE = 128;
 constexpr int TC_GROUP_THREADS = 256;
 constexpr int TC_EPI_THREADS = 512;
-constexpr int TC_THREADS = 544;
+constexpr int TC_THREADS = 608;                   // 16 epilogue warps + 2 MMA issuers + 1 loader
 constexpr int TC_IN_MAX = 8;
 constexpr int TC_L_MAX = 4;
 constexpr int TC_D_MAX = 8;
 constexpr int TC_MAX_CHUNK_TILES = 16;
-constexpr int TC_PASS_N = 96;                     // two spline dims x 48 logit columns per output-layer pass
+constexpr int TC_DIM_N = 48;                      // logit columns of one spline dimension (47 or 48 used)
+constexpr int TC_PASS_N = 96;                     // rows of one packed W3 tile: two spline dimensions
 constexpr int TC_W2_BYTES = 2 * 128 * 128 * 2;    // fp16 hi + lo [128 x 128] tiles
-constexpr int TC_W3_PASS_BYTES = 2 * TC_PASS_N * 128 * 2;  // fp16 hi + lo [96 x 128] tiles of one pass
-// fp32 parameter block: W1[TC_IN_MAX][128], b1[128], b2[128], b3[2 * 96], scal[4]
-constexpr int TC_PAR_FLOATS = TC_IN_MAX * 128 + 128 + 128 + 2 * TC_PASS_N + 4;
-constexpr int TC_PAR_BYTES = TC_PAR_FLOATS * 4;   // 5904, a multiple of 16
+constexpr int TC_W3_PASS_BYTES = 2 * TC_PASS_N * 128 * 2;  // fp16 hi + lo [96 x 128] tiles
+// fp32 parameter block of a stage: W1[TC_IN_MAX][128], b1[128], b2[128], b3[2 * 96], scal[4], then 24 ints
+constexpr int TC_PF_W1 = 0;
+constexpr int TC_PF_B1 = TC_IN_MAX * 128;
+constexpr int TC_PF_B2 = TC_PF_B1 + 128;
+constexpr int TC_PF_B3 = TC_PF_B2 + 128;
+constexpr int TC_PF_SCAL = TC_PF_B3 + 2 * TC_PASS_N;  // s2inv, s3inv, B, 1/(2B)
+constexpr int TC_PI = TC_PF_SCAL + 4;                 // ints: key_col[8], low_col[4], U, L, in_dim, periodic, bins_off
+constexpr int TC_PI_KEY = 0, TC_PI_LOW = 8, TC_PI_U = 12, TC_PI_L = 13, TC_PI_IN = 14, TC_PI_PERIODIC = 15,
+              TC_PI_BINS = 16;
+constexpr int TC_PAR_FLOATS = TC_PI + 24;
+constexpr int TC_PAR_BYTES = TC_PAR_FLOATS * 4;   // 6000, a multiple of 16
 constexpr int TC_SMEM_MAX = 232448;               // 227 KB opt-in limit per CTA
+static_assert(TC_PAR_BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 
 // global blob of one coupling stage: [W2 hi | W2 lo | pass0 hi | pass0 lo | pass1 hi | pass1 lo | par]
 struct TcLayout {
@@ -64,6 +82,16 @@ struct TcLayout {
     return t;
   }
 };
+
+// chain nesting depth actually used (number of log-det levels kept per row)
+static int tc_log_det_levels(const PlanDev& hp) {
+  int depth = 0, level = 0;
+  for (int i = 0; i < hp.n_steps; ++i) {
+    if (hp.steps[i].kind == STEP_CHAIN_BEGIN) depth = max(depth, ++level);
+    else if (hp.steps[i].kind == STEP_CHAIN_END) --level;
+  }
+  return depth + 1;
+}
 
 // ------------------------------------------------------------------------------------------
 // host side: shape check + packing
@@ -102,7 +130,9 @@ static inline void split_store(__half* hi, __half* lo, size_t idx, float v) {
   lo[idx] = __float2half_rn(v - __half2float(h));
 }
 
-void tc_pack_stage(const NscDev& st, const float* const* weights, void* dst) {
+// state columns of a chunk row: x[0, D), log-det levels [D, D + n_lev), pending log-det halves (2),
+// conditions (C)
+void tc_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weights, void* dst) {
   const TcLayout lay = TcLayout::make(st.L);
   unsigned char* base = static_cast<unsigned char*>(dst);
   memset(base, 0, lay.total);
@@ -122,26 +152,34 @@ void tc_pack_stage(const NscDev& st, const float* const* weights, void* dst) {
       const int d = 2 * p + j;
       if (d >= st.L) continue;
       for (int q = 0; q < st.cpd; ++q) {
-        const int col = d * st.cpd + q, n = 48 * j + q;
+        const int col = d * st.cpd + q, n = TC_DIM_N * j + q;
         for (int k = 0; k < 128; ++k) split_store(hi, lo, sw128_index(TC_PASS_N, n, k), W3[(size_t)k * out_dim + col] * s3);
       }
     }
   }
   float* par = reinterpret_cast<float*>(base + lay.par);
   for (int i = 0; i < in_dim; ++i)
-    for (int k = 0; k < 128; ++k) par[i * 128 + k] = W1[i * 128 + k];
-  float* pb1 = par + TC_IN_MAX * 128;
-  float* pb2 = pb1 + 128;
-  float* pb3 = pb2 + 128;
+    for (int k = 0; k < 128; ++k) par[TC_PF_W1 + i * 128 + k] = W1[i * 128 + k];
   for (int k = 0; k < 128; ++k) {
-    pb1[k] = b1[k];
-    pb2[k] = b2[k];
+    par[TC_PF_B1 + k] = b1[k];
+    par[TC_PF_B2 + k] = b2[k];
   }
   for (int d = 0; d < st.L; ++d)
-    for (int q = 0; q < st.cpd; ++q) pb3[(d / 2) * TC_PASS_N + 48 * (d % 2) + q] = b3[d * st.cpd + q];
-  float* scal = pb3 + 2 * TC_PASS_N;
-  scal[0] = ldexpf(1.0f, -e2);
-  scal[1] = ldexpf(1.0f, -e3);
+    for (int q = 0; q < st.cpd; ++q) par[TC_PF_B3 + d * TC_DIM_N + q] = b3[d * st.cpd + q];
+  par[TC_PF_SCAL + 0] = ldexpf(1.0f, -e2);
+  par[TC_PF_SCAL + 1] = ldexpf(1.0f, -e3);
+  par[TC_PF_SCAL + 2] = st.B;
+  par[TC_PF_SCAL + 3] = 1.0f / (2.0f * st.B);
+  int32_t* pi = reinterpret_cast<int32_t*>(par + TC_PI);
+  const int cond_col0 = hp.D + tc_log_det_levels(hp) + 2;
+  for (int i = 0; i < TC_IN_MAX; ++i)
+    pi[TC_PI_KEY + i] = i < st.U ? (int)st.perm[i] : (i < in_dim ? cond_col0 + (i - st.U) : 0);
+  for (int d = 0; d < TC_L_MAX; ++d) pi[TC_PI_LOW + d] = d < st.L ? (int)st.perm[st.U + d] : 0;
+  pi[TC_PI_U] = st.U;
+  pi[TC_PI_L] = st.L;
+  pi[TC_PI_IN] = in_dim;
+  pi[TC_PI_PERIODIC] = st.periodic;
+  pi[TC_PI_BINS] = st.bins_off;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -152,31 +190,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {  // never suspends the thread
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
+// Blocks until the phase with the given parity has completed.  try_wait suspends the thread in hardware
+// (up to the time hint) instead of polling, so waiting warps leave the issue slots to working ones.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(32);  // leave the issue slots to the other group's warps
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "PZB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra PZB_DONE;\n\t"
+      "bra PZB_WAIT;\n\t"
+      "PZB_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -215,17 +242,40 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+  uint32_t u[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+      "[%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
+}
 
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
   // K-major SWIZZLE_128B operand: start address, SBO = 1024 B (8 rows x 128 B), version 1 (sm100)
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  if (ACC)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc)
+        : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -245,110 +295,175 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// D[128 x N] = A(hi,lo)[128 x 128] * B(hi,lo)[N x 128]^T as lo*hi + hi*lo + hi*hi (24 MMAs)
-__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_tmem, uint32_t sb_hi, uint32_t sb_lo, int n_rows,
+// A operand layout in a 128-column TMEM region (K = 128 fp16 hi/lo): the 32 elements [32b, 32b+32)
+// occupy columns [32b, 32b+32): 16 hi columns then 16 lo columns (two elements per 32-bit column), so an
+// epilogue thread can rewrite 32 fp32 accumulator columns in place.  K-step k16 (16 elements):
+__device__ __forceinline__ constexpr uint32_t a_col_of(int k16) { return (uint32_t)((k16 >> 1) * 32 + (k16 & 1) * 8); }
+
+// D[128 x N] = A(hi,lo)[128 x 128] * B(hi,lo)[N x 128]^T as lo*hi + hi*lo + hi*hi (24 MMAs).
+// sb_hi / sb_lo: shared addresses of the first B row of the (sub-)tile; kblk: bytes between its two K blocks.
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_tmem, uint32_t sb_hi, uint32_t sb_lo, uint32_t kblk,
                                            uint32_t idesc) {
-  uint32_t acc = 0;
+  const uint64_t dh = make_b_desc(sb_hi), dl = make_b_desc(sb_lo);
+  const uint32_t kb16 = kblk >> 4;
 #pragma unroll
   for (int prod = 0; prod < 3; ++prod) {
-    const uint32_t a_col = a_tmem + (prod == 0 ? 64 : 0);
-    const uint32_t sb = (prod == 1) ? sb_lo : sb_hi;
+    const uint32_t a_off = (prod == 0) ? 16u : 0u;  // lo * hi first
+    const uint64_t db = (prod == 1) ? dl : dh;
 #pragma unroll
     for (int k16 = 0; k16 < 8; ++k16) {
-      const uint64_t bdesc = make_b_desc(sb + (k16 >> 2) * (n_rows * 128) + (k16 & 3) * 32);
-      umma_f16_ts(d_tmem, a_col + k16 * 8, bdesc, idesc, acc);
-      acc = 1;
+      const uint64_t bdesc = db + (uint64_t)((k16 >> 2) * kb16 + (k16 & 3) * 2);
+      if (prod == 0 && k16 == 0)
+        umma_f16_ts<false>(d_tmem, a_tmem + a_off + a_col_of(k16), bdesc, idesc);
+      else
+        umma_f16_ts<true>(d_tmem, a_tmem + a_off + a_col_of(k16), bdesc, idesc);
     }
   }
 }
 
+// jax.nn.softplus = logaddexp(x, 0) = max(x, 0) + log1p(exp(-|x|)), with log1p(t) = 2 atanh(t / (2 + t)):
+// t in (0, 1] keeps s = t / (2 + t) <= 1/3, where the odd series through s^13 is exact to 1.4e-8 relative.
+__device__ __forceinline__ float tc_softplus(float x) {
+  const float t = ex2_approx(fabsf(x) * -1.4426950408889634f);
+  const float s = __fdividef(t, 2.0f + t);
+  const float z = s * s;
+  float p = fmaf(z, 0.07692307692307693f, 0.09090909090909091f);
+  p = fmaf(z, p, 0.1111111111111111f);
+  p = fmaf(z, p, 0.14285714285714285f);
+  p = fmaf(z, p, 0.2f);
+  p = fmaf(z, p, 0.3333333333333333f);
+  p = fmaf(z, p, 1.0f);
+  return fmaf(s + s, p, fmaxf(x, 0.0f));
+}
+
+// pzflow/utils.py:163-227 once the bin's seven values are known (same op order as pz_rqs_eval), with the
+// three quotients as MUFU.RCP * x (2 ulp) and the logarithms as lg2.approx.
+__device__ __forceinline__ void tc_rqs_eval(const SplineKnotSel& s, float x, float mx, bool oob, bool inverse,
+                                            bool periodic, float& out, float& ld) {
+  const float sk = __fdividef(s.hk, s.wk);
+  const float dsum = (s.dkp1 + s.dk) - 2.0f * sk;
+  float relx;
+  if (inverse) {
+    const float t = mx - s.yk;
+    const float a = s.hk * (sk - s.dk) + t * dsum;
+    const float b = s.hk * s.dk - t * dsum;
+    const float c = (-sk) * t;
+    relx = __fdividef(2.0f * c, (-b) - sqrtf(b * b - (4.0f * a) * c));
+    out = relx * s.wk + s.xk;
+  } else {
+    relx = __fdividef(mx - s.xk, s.wk);
+    const float num = s.hk * (sk * (relx * relx) + (s.dk * relx) * (1.0f - relx));
+    const float den = sk + (dsum * relx) * (1.0f - relx);
+    out = s.yk + __fdividef(num, den);
+  }
+  const float omr = 1.0f - relx;
+  const float dnum = (s.dkp1 * (relx * relx) + ((2.0f * sk) * relx) * omr) + s.dk * (omr * omr);
+  const float dden = sk + (dsum * relx) * omr;
+  ld = 0.6931471805599453f * ((2.0f * pz_lg2_approx(sk) + pz_lg2_approx(dnum)) - 2.0f * pz_lg2_approx(dden));
+  if (!periodic && oob) {
+    out = x;
+    ld = 0.0f;
+  }
+}
+
+// 16 un-normalised softmax terms of one axis: e_j = 2^((l_j - max l) * log2 e), l = raw * sinv + bias
+__device__ __forceinline__ void softmax_terms(const float* __restrict__ raw, const float* __restrict__ bias, float sinv,
+                                              float (&e)[16]) {
+  constexpr float L2E = 1.4426950408889634f;
+#pragma unroll
+  for (int q = 0; q < 16; q += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias + q);
+    e[q + 0] = fmaf(raw[q + 0], sinv, b4.x);
+    e[q + 1] = fmaf(raw[q + 1], sinv, b4.y);
+    e[q + 2] = fmaf(raw[q + 2], sinv, b4.z);
+    e[q + 3] = fmaf(raw[q + 3], sinv, b4.w);
+  }
+  float m = fmaxf(e[0], e[1]);
+#pragma unroll
+  for (int j = 2; j < 16; j += 2) m = fmaxf(m, fmaxf(e[j], e[j + 1]));
+  const float nm = -(m * L2E);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) e[j] = ex2_approx(fmaf(e[j], L2E, nm));
+}
+
+// One bin of a 16-term cumulative sum, found in two levels of four: sums of the four groups, then the
+// prefix inside the selected group.  Returns the prefix at the bin's left edge and the bin's own term.
+struct BinPick {
+  bool p1, p2, p3, q1, q2, q3;  // group / in-group "right edge <= target" flags (each a prefix of trues)
+};
+__device__ __forceinline__ void group_sums(const float (&e)[16], float& G1, float& G2, float& G3, float& tot) {
+  const float g0 = (e[0] + e[1]) + (e[2] + e[3]), g1 = (e[4] + e[5]) + (e[6] + e[7]);
+  const float g2 = (e[8] + e[9]) + (e[10] + e[11]), g3 = (e[12] + e[13]) + (e[14] + e[15]);
+  G1 = g0;
+  G2 = G1 + g1;
+  G3 = G2 + g2;
+  tot = G3 + g3;
+}
+template <bool SEARCH>
+__device__ __forceinline__ void pick_bin(const float (&e)[16], float G1, float G2, float G3, float target, BinPick& k,
+                                         float& left, float& term) {
+  if (SEARCH) {
+    k.p1 = G1 <= target;
+    k.p2 = G2 <= target;
+    k.p3 = G3 <= target;
+  }
+  const float base = k.p3 ? G3 : (k.p2 ? G2 : (k.p1 ? G1 : 0.0f));
+  float a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = k.p3 ? e[12 + i] : (k.p2 ? e[8 + i] : (k.p1 ? e[4 + i] : e[i]));
+  const float c1 = base + a[0], c2 = c1 + a[1], c3 = c2 + a[2];
+  if (SEARCH) {
+    k.q1 = c1 <= target;
+    k.q2 = c2 <= target;
+    k.q3 = c3 <= target;
+  }
+  left = k.q3 ? c3 : (k.q2 ? c2 : (k.q1 ? c1 : base));
+  term = k.q3 ? a[3] : (k.q2 ? a[2] : (k.q1 ? a[1] : a[0]));
+}
+
 // softmax knots, bin search, RQS and log-det of one (row, dim) from its 48 raw accumulator values
 // (pzflow/bijectors.py:488-491 + pzflow/utils.py:113-227; K = 16).  The bin search runs on the
-// un-normalised cumulative sums (knot_j <= x  <=>  cumsum(e)_j <= (x + B) * sum(e) / 2B), so only
-// the selected bin's knots and sizes are ever scaled.  The searched axis (widths forward, heights
-// inverse) is processed first, then the other axis and the two derivatives the bin needs.
+// un-normalised cumulative sums (knot_j <= x  <=>  cumsum(e)_j <= (x + B) * sum(e) / 2B), so only the
+// selected bin's knots and sizes are ever scaled.  The searched axis (widths forward, heights inverse)
+// is processed first, then the other axis and the two derivatives the bin needs.
 template <bool INV>
-__device__ __forceinline__ void spline_regs(const float (&raw)[48], const float* __restrict__ bias, float sinv, float x,
-                                            float B, bool periodic, float& out, float& ld, int& idx_out) {
-  constexpr float L2E = 1.4426950408889634f;
+__device__ __forceinline__ void spline_dim(const float (&raw)[48], const float* __restrict__ bias, float sinv, float x,
+                                           float B, float inv2B, bool periodic, float& out, float& ld, int& idx_out) {
   constexpr int SO = INV ? 16 : 0, OO = INV ? 0 : 16;
   const float twoB = 2.0f * B;
   const bool oob = (x <= -B) || (x >= B);
   const float mx = oob ? fabsf(x) - B : x;
+  BinPick k;
+  float e[16], G1, G2, G3, tot;
 
-  // ---- searched axis ----
-  float e[16];
-#pragma unroll
-  for (int q = 0; q < 16; q += 4) {
-    const float4 b4 = *reinterpret_cast<const float4*>(bias + SO + q);
-    e[q + 0] = fmaf(raw[SO + q + 0], sinv, b4.x);
-    e[q + 1] = fmaf(raw[SO + q + 1], sinv, b4.y);
-    e[q + 2] = fmaf(raw[SO + q + 2], sinv, b4.z);
-    e[q + 3] = fmaf(raw[SO + q + 3], sinv, b4.w);
-  }
-  float m = e[0];
-#pragma unroll
-  for (int j = 1; j < 16; ++j) m = fmaxf(m, e[j]);
-  float nm = -(m * L2E);
-  float run = 0.0f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    e[j] = ex2_approx(fmaf(e[j], L2E, nm));
-    run += e[j];
-  }
-  const float rs = __fdividef(twoB, run);              // 2B / sum(e)
-  const float target = __fdividef(mx + B, rs);         // (x + B) * sum(e) / 2B
-  int cnt = (-B <= mx) ? 1 : 0;
-  float cs_sel = 0.0f, s_sel = e[0];
-  run = 0.0f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    run += e[j];
-    const bool p = run <= target;  // knot j+1 <= x: a prefix of trues (cumsum of positives is monotone)
-    cnt += p ? 1 : 0;
-    cs_sel = p ? run : cs_sel;
-    if (j < 15) s_sel = p ? e[j + 1] : s_sel;
-  }
-  const int idx = cnt - 1;
+  softmax_terms(raw + SO, bias + SO, sinv, e);
+  group_sums(e, G1, G2, G3, tot);
+  const float target = (mx + B) * (tot * inv2B);  // (x + B) * sum(e) / 2B
+  float cs_sel, s_sel;
+  pick_bin<true>(e, G1, G2, G3, target, k, cs_sel, s_sel);
+  const float rs = __fdividef(twoB, tot);
+  // knots <= x: the left edge -B, then a prefix of the 16 cumulative sums (pzflow/utils.py:150-152)
+  const int gi = k.p3 ? 3 : (k.p2 ? 2 : (k.p1 ? 1 : 0)), wi = k.q3 ? 3 : (k.q2 ? 2 : (k.q1 ? 1 : 0));
+  int idx = 4 * gi + wi;
+  if (tot <= target) idx = 16;
+  if (!(-B <= mx)) idx = -1;
   idx_out = idx;
-  // prefix count over the 16 interior/right knots; the other-axis selections replay it as (j < np)
-  const int np = cnt - ((-B <= mx) ? 1 : 0);
 
-  // ---- other axis ----
+  softmax_terms(raw + OO, bias + OO, sinv, e);
+  group_sums(e, G1, G2, G3, tot);
+  float co_sel, o_sel;
+  pick_bin<false>(e, G1, G2, G3, 0.0f, k, co_sel, o_sel);
+  const float ro = __fdividef(twoB, tot);
+
+  // derivative logits D[idx - 1], D[idx] (raw[32 + j]; raw[47] is the zero pad unless periodic)
+  float v[5];
 #pragma unroll
-  for (int q = 0; q < 16; q += 4) {
-    const float4 b4 = *reinterpret_cast<const float4*>(bias + OO + q);
-    e[q + 0] = fmaf(raw[OO + q + 0], sinv, b4.x);
-    e[q + 1] = fmaf(raw[OO + q + 1], sinv, b4.y);
-    e[q + 2] = fmaf(raw[OO + q + 2], sinv, b4.z);
-    e[q + 3] = fmaf(raw[OO + q + 3], sinv, b4.w);
-  }
-  m = e[0];
-#pragma unroll
-  for (int j = 1; j < 16; ++j) m = fmaxf(m, e[j]);
-  nm = -(m * L2E);
-  run = 0.0f;
-  float co_sel = 0.0f, o_sel = 0.0f;
-  float r0 = 0.0f, r1 = fmaf(raw[32], sinv, bias[32]);
-  bool pprev = true;  // (j - 1 < np)
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float ej = ex2_approx(fmaf(e[j], L2E, nm));
-    run += ej;
-    o_sel = pprev ? ej : o_sel;  // ends as e[min(np, 15)]
-    const bool p = j < np;
-    co_sel = p ? run : co_sel;
-    if (j < 15) r1 = p ? raw[32 + j + 1] : r1;  // raw[47] is the zero pad unless periodic
-    r0 = p ? raw[32 + j] : r0;
-    pprev = p;
-  }
-  const float ro = __fdividef(twoB, run);
-  // the two derivative logits: bias applied after the selection (bias index = selected index)
-  {
-    const int i0 = min(max(np - 1, 0), 15), i1 = min(np, 15);
-    if (np > 0) r0 = fmaf(r0, sinv, bias[32 + i0]);
-    if (np > 0) r1 = fmaf(r1, sinv, bias[32 + i1]);
-  }
+  for (int i = 0; i < 5; ++i) v[i] = k.p3 ? raw[43 + i] : (k.p2 ? raw[39 + i] : (k.p1 ? raw[35 + i] : raw[31 + i]));
+  float r0 = k.q3 ? v[3] : (k.q2 ? v[2] : (k.q1 ? v[1] : v[0]));
+  float r1 = k.q3 ? v[4] : (k.q2 ? v[3] : (k.q1 ? v[2] : v[1]));
+  const int ic = min(max(idx, 0), 15);
+  r0 = fmaf(r0, sinv, bias[32 + max(ic - 1, 0)]);
+  r1 = fmaf(r1, sinv, bias[32 + ic]);
 
   const float qnan = __int_as_float(0x7fc00000);
   const bool bad = (idx < 0) || (idx >= 16);  // take_along_axis "fill" -> NaN (pzflow/utils.py:155-161)
@@ -362,21 +477,23 @@ __device__ __forceinline__ void spline_regs(const float (&raw)[48], const float*
   s.yk = INV ? ksel : oknot;
   if (periodic) {
     if (idx == 0) r0 = fmaf(raw[32 + 15], sinv, bias[32 + 15]);  // dk = pad(D, (1, 0), "wrap")
-    s.dk = pz_softplus(r0);
-    s.dkp1 = pz_softplus(r1);
+    s.dk = tc_softplus(r0);
+    s.dkp1 = tc_softplus(r1);
   } else {
-    s.dk = (idx == 0) ? 1.0f : pz_softplus(r0);
-    s.dkp1 = (idx == 15) ? 1.0f : pz_softplus(r1);
+    s.dk = (idx == 0) ? 1.0f : tc_softplus(r0);
+    s.dkp1 = (idx == 15) ? 1.0f : tc_softplus(r1);
   }
-  pz_rqs_eval<true>(s, x, mx, oob, INV, periodic, out, ld);
+  tc_rqs_eval(s, x, mx, oob, INV, periodic, out, ld);
 }
 
 struct TcShared {
-  uint64_t go[2];        // epilogue group -> MMA thread (256 arrivals): operands ready / accumulator drained
-  uint64_t done[2];      // MMA thread -> epilogue group (tcgen05.commit)
-  uint64_t lay_done[2];  // epilogue group finished a coupling stage (256 arrivals): its parameter block is free
-  uint64_t w2full, w3full, parfull[2];  // TMA complete_tx
-  uint64_t w2free, w3free;              // tcgen05.commit after the stage's last hidden GEMM / output pass
+  uint64_t e_ready[2];     // epilogue group -> its MMA issuer (256 arrivals): A operand written (after E1 and after E2)
+  uint64_t d2_full[2][2];  // [group][half]: that N = 64 half of the hidden GEMM has completed (tcgen05.commit)
+  uint64_t d3_full[2][2];  // [group][buffer]: an output pass has landed in that accumulator buffer
+  uint64_t d3_free[2][2];  // [group][buffer]: the half's 128 threads have drained the buffer
+  uint64_t w2_full, w3_full, par_full[2];  // TMA complete_tx
+  uint64_t w2_free, w3_free;               // both issuers' tcgen05.commit after the stage's last hidden GEMM / pass
+  uint64_t par_free[2];                    // 512 arrivals: every epilogue thread is done with that parameter buffer
   uint32_t tmem_base;
   uint8_t order[MAX_NSC];  // coupling stages in walk order (index into PlanDev::nsc)
 };
@@ -415,8 +532,8 @@ __device__ __forceinline__ void apply_affine_cols(const AffineDev& af, bool inve
 }
 
 // Applies the non-NSC steps in [s0, s1) (already mapped to walk order) to one state row.
-__device__ __forceinline__ void light_steps_cols(const PlanDev* plan, bool inverse, int s0, int s1, int& level, float* st,
-                                                 int CR) {
+__device__ __noinline__ void light_steps_cols(const PlanDev* plan, bool inverse, int s0, int s1, int& level, float* st,
+                                              int CR) {
   const int D = plan->D, ns = plan->n_steps;
   float* ldl = st + D * CR;
   for (int si = s0; si < s1; ++si) {
@@ -438,7 +555,7 @@ __device__ __forceinline__ void light_steps_cols(const PlanDev* plan, bool inver
   }
 }
 
-__device__ __forceinline__ int level_after(const PlanDev* plan, bool inverse, int s0, int s1, int level) {
+__device__ __noinline__ int level_after(const PlanDev* plan, bool inverse, int s0, int s1, int level) {
   const int ns = plan->n_steps;
   for (int si = s0; si < s1; ++si) {
     int kind = plan->steps[inverse ? ns - 1 - si : si].kind;
@@ -449,32 +566,7 @@ __device__ __forceinline__ int level_after(const PlanDev* plan, bool inverse, in
   return level;
 }
 
-// E1 for one half row: 64 hidden columns of LeakyReLU(key @ W1 + b1) -> fp16 hi/lo in TMEM
-template <int IN>
-__device__ __forceinline__ void e1_half(const float (&key)[TC_IN_MAX], const float* __restrict__ sW1,
-                                        const float* __restrict__ sb1, int half, uint32_t t_a) {
-#pragma unroll
-  for (int bt = 0; bt < 2; ++bt) {
-    uint32_t rh[16], rl[16];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int k0 = half * 64 + bt * 32 + q * 4;
-      float4 acc = *reinterpret_cast<const float4*>(sb1 + k0);
-#pragma unroll
-      for (int i = 0; i < IN; ++i) {
-        const float4 w = *reinterpret_cast<const float4*>(sW1 + i * 128 + k0);
-        acc.x = fmaf(key[i], w.x, acc.x);
-        acc.y = fmaf(key[i], w.y, acc.y);
-        acc.z = fmaf(key[i], w.z, acc.z);
-        acc.w = fmaf(key[i], w.w, acc.w);
-      }
-      split2(pz_leaky(acc.x), pz_leaky(acc.y), rh[2 * q], rl[2 * q]);
-      split2(pz_leaky(acc.z), pz_leaky(acc.w), rh[2 * q + 1], rl[2 * q + 1]);
-    }
-    tmem_st16(t_a + half * 32 + bt * 16, rh);
-    tmem_st16(t_a + 64 + half * 32 + bt * 16, rl);
-  }
-}
+#define TC_BAR(field) (sh_addr + (uint32_t)offsetof(TcShared, field))
 
 template <bool INV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -484,36 +576,39 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols);
   TcShared* sh = reinterpret_cast<TcShared*>(base + sl.shared);
+  const uint32_t sh_addr = smem_u32(sh);
   float* state = reinterpret_cast<float*>(base + sl.state);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t tid;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));  // volatile: read once, never rematerialised as S2R
+  const int warp = (int)(tid >> 5), lane = (int)(tid & 31);
   const int D = plan->D, C = plan->C, ns = plan->n_steps, n_nsc = plan->n_nsc, n_lev = lp.n_lev;
   const int CR = lp.chunk_tiles * TC_TILE;           // rows of state per column
   const int COL_PEND = D + n_lev, COL_COND = D + n_lev + 2;
-  const bool is_epi = warp < 16;
-  const int grp = (warp >> 3) & 1;                   // epilogue group
-  const int half = (warp >> 2) & 1;                  // which half of the row's work
-  const int lrow = ((warp & 3) << 5) + lane;         // row within the tile == TMEM lane
 
   if (tid == 0) {
     for (int g = 0; g < 2; ++g) {
-      mbar_init(smem_u32(&sh->go[g]), TC_GROUP_THREADS);
-      mbar_init(smem_u32(&sh->done[g]), 1);
-      mbar_init(smem_u32(&sh->lay_done[g]), TC_GROUP_THREADS);
-      mbar_init(smem_u32(&sh->parfull[g]), 1);
+      mbar_init(TC_BAR(e_ready[g]), TC_GROUP_THREADS);
+      for (int h = 0; h < 2; ++h) {
+        mbar_init(TC_BAR(d2_full[g][h]), 1);
+        mbar_init(TC_BAR(d3_full[g][h]), 1);
+        mbar_init(TC_BAR(d3_free[g][h]), TC_TILE);
+      }
+      mbar_init(TC_BAR(par_full[g]), 1);
+      mbar_init(TC_BAR(par_free[g]), TC_EPI_THREADS);
     }
-    mbar_init(smem_u32(&sh->w2full), 1);
-    mbar_init(smem_u32(&sh->w3full), 1);
-    mbar_init(smem_u32(&sh->w2free), 1);
-    mbar_init(smem_u32(&sh->w3free), 1);
+    mbar_init(TC_BAR(w2_full), 1);
+    mbar_init(TC_BAR(w3_full), 1);
+    mbar_init(TC_BAR(w2_free), 2);
+    mbar_init(TC_BAR(w3_free), 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int seen = 0;
-    for (int si = 0; si < plan->n_steps; ++si) {
-      const StepDev step = plan->steps[INV ? plan->n_steps - 1 - si : si];
+    for (int si = 0; si < ns; ++si) {
+      const StepDev step = plan->steps[INV ? ns - 1 - si : si];
       if (step.kind == STEP_NSC) sh->order[seen++] = (uint8_t)step.idx;
     }
   }
   if (warp == 16) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "n"(512)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(TC_BAR(tmem_base)), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -526,21 +621,27 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
   const long long n_chunks = (args.N + chunk_rows - 1) / chunk_rows;
   const int my_chunks = (int)((n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x);  // blockIdx.x < n_chunks
 
-  // NSC steps in walk order
-  int first_nsc = ns, last_nsc = -1;
-  for (int si = 0; si < ns; ++si)
-    if (plan->steps[INV ? ns - 1 - si : si].kind == STEP_NSC) {
-      if (first_nsc == ns) first_nsc = si;
-      last_nsc = si;
-    }
-
-  if (is_epi) {
+  if (warp < 16) {
     // ======================================= epilogue warps =======================================
-    const uint32_t t_lane = tbase + ((uint32_t)((warp & 3) << 5) << 16);
-    const uint32_t t_a = t_lane + (uint32_t)grp * 256u, t_d = t_lane + (uint32_t)grp * 256u + 128u;
-    const uint32_t bar_go = smem_u32(&sh->go[grp]), bar_done = smem_u32(&sh->done[grp]);
-    uint32_t ph_done = 0u;
+    const int grp = (warp >> 3) & 1;                   // epilogue group
+    const int half = (warp >> 2) & 1;                  // which half of the row's work
+    const int lrow = ((warp & 3) << 5) + lane;         // row within the tile == TMEM lane
+    const uint32_t t_x = tbase + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)grp * 256u + (uint32_t)half * 64u;
+    const uint32_t t_y = t_x + 128u;                   // this half's 64 columns of X / Y
+    const uint32_t bar_ready = TC_BAR(e_ready[0]) + 8u * grp;
+    const uint32_t bar_d2 = TC_BAR(d2_full[0][0]) + 16u * grp + 8u * half;
+    const uint32_t bar_d3 = TC_BAR(d3_full[0][0]) + 16u * grp + 8u * half;
+    const uint32_t bar_free = TC_BAR(d3_free[0][0]) + 16u * grp + 8u * half;
+    uint32_t ph_d2 = 0u, ph_d3 = 0u;
     int seq = 0;  // coupling stages processed so far by this CTA (over all its chunks)
+
+    // NSC steps in walk order
+    int first_nsc = ns, last_nsc = -1;
+    for (int si = 0; si < ns; ++si)
+      if (plan->steps[INV ? ns - 1 - si : si].kind == STEP_NSC) {
+        if (first_nsc == ns) first_nsc = si;
+        last_nsc = si;
+      }
 
     for (int ci = 0; ci < my_chunks; ++ci) {
       const long long row0 = ((long long)blockIdx.x + (long long)ci * gridDim.x) * chunk_rows;
@@ -549,7 +650,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       const int my_tiles = (ntiles - grp + 1) / 2;
 
       // ---- pass A: rows -> state, steps in front of the first coupling stage ----
-      for (int r = tid; r < nrows; r += TC_EPI_THREADS) {
+      for (int r = (int)tid; r < nrows; r += TC_EPI_THREADS) {
         const long long row = row0 + r;
         float* st = state + r;
         for (int j = 0; j < D; ++j) {
@@ -577,31 +678,22 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       bool pending = false;  // the previous stage's two log-det halves still sit in the pending columns
       int pend_level = 0;
       for (int si = first_nsc; si <= last_nsc; ++si) {
-        const StepDev step = plan->steps[INV ? ns - 1 - si : si];
-        if (step.kind != STEP_NSC) continue;
+        if (plan->steps[INV ? ns - 1 - si : si].kind != STEP_NSC) continue;
         const bool has_light = si > prev_end;
         const int light0 = prev_end;
         const int level_in = level;
-        level = level_after(plan, INV, prev_end, si, level);
+        if (has_light) level = level_after(plan, INV, prev_end, si, level);
         prev_end = si + 1;
-        const NscDev& st = plan->nsc[step.idx];
-        const int U = st.U, L = st.L, in_dim = st.U + st.C, n_pass = (L + 1) / 2;
-        const float B = st.B;
-        const bool periodic = st.periodic != 0;
 
         // parameter block of this stage (double buffered); previous-stage state writes of the row's other half
-        mbar_wait(smem_u32(&sh->parfull[seq & 1]), (uint32_t)((seq >> 1) & 1));
+        mbar_wait(TC_BAR(par_full[0]) + 8u * (seq & 1), (uint32_t)((seq >> 1) & 1));
         named_bar_sync(2 + grp, TC_GROUP_THREADS);
         const float* par = reinterpret_cast<const float*>(base + sl.par + (seq & 1) * TC_PAR_BYTES);
-        const float* sW1 = par;
-        const float* sb1 = par + TC_IN_MAX * 128;
-        const float* sb2 = sb1 + 128;
-        const float* sb3 = sb2 + 128;
-        const float s2inv = sb3[2 * TC_PASS_N], s3inv = sb3[2 * TC_PASS_N + 1];
+        const int* pint = reinterpret_cast<const int*>(par + TC_PI);
+        const int L = pint[TC_PI_L];
 
         for (int k = 0; k < my_tiles; ++k) {
           const int r = (2 * k + grp) * TC_TILE + lrow;  // row within the chunk (state is allocated for every tile)
-          const bool valid = r < nrows;
           float* srow = state + r;
 
           if (pending || has_light) {
@@ -615,88 +707,102 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             if (has_light) named_bar_sync(2 + grp, TC_GROUP_THREADS);
           }
 
-          float key[TC_IN_MAX];
+          // ---- E1: h1 = LeakyReLU(key @ W1 + b1), this half's 64 hidden columns -> fp16 hi/lo in X ----
+          {
+            const int in_dim = pint[TC_PI_IN];
+#pragma unroll 1
+            for (int bt = 0; bt < 2; ++bt) {
+              const float* w = par + TC_PF_W1 + half * 64 + bt * 32;
+              float acc[32];
 #pragma unroll
-          for (int i = 0; i < TC_IN_MAX; ++i)
-            key[i] = (i < in_dim) ? (i < U ? srow[st.perm[i] * CR] : srow[(COL_COND + (i - U)) * CR]) : 0.0f;
-
-          // ---- E1: h1 = LeakyReLU(key @ W1 + b1) -> A (fp16 hi/lo) in TMEM ----
-          switch (in_dim) {
-            case 1: e1_half<1>(key, sW1, sb1, half, t_a); break;
-            case 2: e1_half<2>(key, sW1, sb1, half, t_a); break;
-            case 3: e1_half<3>(key, sW1, sb1, half, t_a); break;
-            case 4: e1_half<4>(key, sW1, sb1, half, t_a); break;
-            case 5: e1_half<5>(key, sW1, sb1, half, t_a); break;
-            case 6: e1_half<6>(key, sW1, sb1, half, t_a); break;
-            case 7: e1_half<7>(key, sW1, sb1, half, t_a); break;
-            default: e1_half<8>(key, sW1, sb1, half, t_a); break;
+              for (int q = 0; q < 8; ++q) {
+                const float4 b4 = *reinterpret_cast<const float4*>(w + (TC_PF_B1 - TC_PF_W1) + q * 4);
+                acc[4 * q + 0] = b4.x;
+                acc[4 * q + 1] = b4.y;
+                acc[4 * q + 2] = b4.z;
+                acc[4 * q + 3] = b4.w;
+              }
+#pragma unroll 1
+              for (int i = 0; i < in_dim; ++i) {
+                const float kv = srow[pint[TC_PI_KEY + i] * CR];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(w + i * 128 + q * 4);
+                  acc[4 * q + 0] = fmaf(kv, w4.x, acc[4 * q + 0]);
+                  acc[4 * q + 1] = fmaf(kv, w4.y, acc[4 * q + 1]);
+                  acc[4 * q + 2] = fmaf(kv, w4.z, acc[4 * q + 2]);
+                  acc[4 * q + 3] = fmaf(kv, w4.w, acc[4 * q + 3]);
+                }
+              }
+              uint32_t rh[16], rl[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) split2(pz_leaky(acc[2 * j]), pz_leaky(acc[2 * j + 1]), rh[j], rl[j]);
+              tmem_st16(t_x + bt * 32, rh);
+              tmem_st16(t_x + bt * 32 + 16, rl);
+            }
           }
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(bar_go);
+          mbar_arrive(bar_ready);
 
-          // ---- E2: h2 = LeakyReLU(D * 2^-e2 + b2) -> A ----
-          mbar_wait(bar_done, ph_done);
-          ph_done ^= 1u;
+          // ---- E2: h2 = LeakyReLU(D * 2^-e2 + b2), rewritten in place over this half's accumulator columns ----
+          mbar_wait(bar_d2, ph_d2);
+          ph_d2 ^= 1u;
           tc_fence_after();
+          {
+            const float s2inv = par[TC_PF_SCAL];
+#pragma unroll 1
+            for (int bt = 0; bt < 2; ++bt) {
+              float dv[32];
+              tmem_ld32(t_y + bt * 32, dv);
+              tc_wait_ld();
+              const float* b2 = par + TC_PF_B2 + half * 64 + bt * 32;
+              uint32_t rh[16], rl[16];
 #pragma unroll
-          for (int bt = 0; bt < 2; ++bt) {
-            float dv[32];
-            tmem_ld16(t_d + half * 64 + bt * 32, dv);
-            tmem_ld16(t_d + half * 64 + bt * 32 + 16, dv + 16);
-            tc_wait_ld();
-            uint32_t rh[16], rl[16];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 bb = *reinterpret_cast<const float4*>(sb2 + half * 64 + bt * 32 + q * 4);
-              const float h0 = pz_leaky(fmaf(dv[4 * q + 0], s2inv, bb.x));
-              const float h1 = pz_leaky(fmaf(dv[4 * q + 1], s2inv, bb.y));
-              const float h2 = pz_leaky(fmaf(dv[4 * q + 2], s2inv, bb.z));
-              const float h3 = pz_leaky(fmaf(dv[4 * q + 3], s2inv, bb.w));
-              split2(h0, h1, rh[2 * q], rl[2 * q]);
-              split2(h2, h3, rh[2 * q + 1], rl[2 * q + 1]);
+              for (int q = 0; q < 8; ++q) {
+                const float4 bb = *reinterpret_cast<const float4*>(b2 + q * 4);
+                const float h0 = pz_leaky(fmaf(dv[4 * q + 0], s2inv, bb.x));
+                const float h1 = pz_leaky(fmaf(dv[4 * q + 1], s2inv, bb.y));
+                const float h2 = pz_leaky(fmaf(dv[4 * q + 2], s2inv, bb.z));
+                const float h3 = pz_leaky(fmaf(dv[4 * q + 3], s2inv, bb.w));
+                split2(h0, h1, rh[2 * q], rl[2 * q]);
+                split2(h2, h3, rh[2 * q + 1], rl[2 * q + 1]);
+              }
+              tmem_st16(t_y + bt * 32, rh);
+              tmem_st16(t_y + bt * 32 + 16, rl);
             }
-            tmem_st16(t_a + half * 32 + bt * 16, rh);
-            tmem_st16(t_a + 64 + half * 32 + bt * 16, rl);
           }
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(bar_go);
+          mbar_arrive(bar_ready);
 
-          // ---- E3: logits -> knots -> spline; this thread takes dim 2p + half of pass p ----
+          // ---- E3: logits -> knots -> spline; this thread takes the dimensions half, half + 2 ----
           float ldsum = 0.0f;
-          for (int p = 0; p < n_pass; ++p) {
-            mbar_wait(bar_done, ph_done);
-            ph_done ^= 1u;
+#pragma unroll 1
+          for (int d = half; d < L; d += 2) {
+            mbar_wait(bar_d3, ph_d3);
+            ph_d3 ^= 1u;
             tc_fence_after();
-            const int d = 2 * p + half;
-            const bool mine = d < L;  // warp-uniform
             float raw[48];
-            if (mine) {
-              tmem_ld16(t_d + 48 * half, raw);
-              tmem_ld16(t_d + 48 * half + 16, raw + 16);
-              tmem_ld16(t_d + 48 * half + 32, raw + 32);
-              tc_wait_ld();
-            }
-            if (p + 1 < n_pass) {  // accumulator drained: the next pass may overwrite it
-              tc_fence_before();
-              mbar_arrive(bar_go);
-            }
-            if (mine) {
-              const int col = st.perm[U + d];
-              const float xin = srow[col * CR];
-              float y, ldd;
-              int idx;
-              spline_regs<INV>(raw, sb3 + p * TC_PASS_N + 48 * half, s3inv, xin, B, periodic, y, ldd, idx);
-              ldsum += ldd;
-              srow[col * CR] = y;
-              if (valid && args.bins != nullptr)
-                args.bins[(row0 + r) * plan->n_spline_dims + st.bins_off + d] = idx;
-            }
+            tmem_ld32(t_x, raw);
+            tmem_ld16(t_x + 32, raw + 32);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar_free);  // accumulator buffer drained: the next pass may overwrite it
+            const int col = pint[TC_PI_LOW + d];
+            const float xin = srow[col * CR];
+            float y, ldd;
+            int idx;
+            spline_dim<INV>(raw, par + TC_PF_B3 + d * TC_DIM_N, par[TC_PF_SCAL + 1], xin, par[TC_PF_SCAL + 2],
+                            par[TC_PF_SCAL + 3], pint[TC_PI_PERIODIC] != 0, y, ldd, idx);
+            ldsum += ldd;
+            srow[col * CR] = y;
+            if (args.bins != nullptr && r < nrows)
+              args.bins[(row0 + r) * plan->n_spline_dims + pint[TC_PI_BINS] + d] = idx;
           }
           srow[(COL_PEND + half) * CR] = INV ? -ldsum : ldsum;
         }
-        mbar_arrive(smem_u32(&sh->lay_done[grp]));
+        mbar_arrive(TC_BAR(par_free[0]) + 8u * (seq & 1));
         pending = true;
         pend_level = level;
         ++seq;
@@ -704,7 +810,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       named_bar_sync(1, TC_EPI_THREADS);
 
       // ---- pass Z: trailing steps, latent log-density, outputs ----
-      for (int r = tid; r < nrows; r += TC_EPI_THREADS) {
+      for (int r = (int)tid; r < nrows; r += TC_EPI_THREADS) {
         const long long row = row0 + r;
         float* st = state + r;
         if (pending) st[(D + pend_level) * CR] += st[COL_PEND * CR] + st[(COL_PEND + 1) * CR];
@@ -723,12 +829,8 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       // (pass A of the next chunk touches a row from the same thread as pass Z did: no barrier needed)
     }
   } else if (lane == 0) {
-    // =============================== MMA issuer + weight streamer ===============================
     const uint32_t sb = smem_u32(base);
-    const uint32_t idesc2 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t idesc3 = (1u << 4) | ((uint32_t)(TC_PASS_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int total_seq = my_chunks * n_nsc;
-
     // coupling stage (walk order) of sequence number s, and the tile count of its chunk
     auto stage_of = [&](int s) -> const NscDev& { return plan->nsc[sh->order[s % n_nsc]]; };
     auto tiles_of = [&](int s) -> int {
@@ -736,118 +838,81 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       const int nrows = (int)min(chunk_rows, args.N - row0);
       return max(2, (nrows + TC_TILE - 1) / TC_TILE);
     };
-
-    // per group: sequence number, tile, phase (0 = hidden GEMM, p + 1 = output pass p) and the cached
-    // shape of its current stage
-    int gs[2] = {0, 0}, gk[2] = {0, 0}, gp[2] = {0, 0}, gnp[2], gnt[2];
-    uint32_t gpar[2] = {0u, 0u};
-    bool gready[2] = {false, false};
-    gnp[0] = gnp[1] = total_seq > 0 ? (stage_of(0).L + 1) / 2 : 1;
-    gnt[0] = gnt[1] = total_seq > 0 ? tiles_of(0) : 2;
-    int w2_next = 0, w3_next = 0, par_next = 0;      // next sequence number to load
-    int w2_ready = 0, w3_ready = 0;                  // loads observed complete
-    int w2_freed = 0, w3_freed = 0;                  // buffer releases observed
-    int lay_seen[2] = {0, 0};                        // stages each group has finished
-    int c2_cnt = 0, c3_cnt = 0;                      // GEMMs issued in the stage currently holding W2 / W3
-
-    while (gs[0] < total_seq || gs[1] < total_seq) {
-      bool progress = false;
-      // ---- weight streaming ----
-      if (w2_next < total_seq) {
-        if (w2_next > w2_freed && mbar_test_wait(smem_u32(&sh->w2free), (uint32_t)(w2_freed & 1))) ++w2_freed;
-        if (w2_next <= w2_freed) {
-          const NscDev& st = stage_of(w2_next);
-          const uint32_t bar = smem_u32(&sh->w2full);
-          mbar_expect_tx(bar, TC_W2_BYTES);
-          const uint8_t* src = static_cast<const uint8_t*>(st.tc.blob);
-          for (int off = 0; off < TC_W2_BYTES; off += 16384) tma_bulk_g2s(sb + sl.w2 + off, src + off, 16384u, bar);
-          ++w2_next;
-          progress = true;
+    if (warp < 18) {
+      // =============================== MMA issuer of group g ===============================
+      const int g = warp - 16;
+      const uint32_t t_x = tbase + (uint32_t)g * 256u, t_y = t_x + 128u;
+      const uint32_t idesc2 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc3 = (1u << 4) | ((uint32_t)(TC_DIM_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t bar_ready = TC_BAR(e_ready[0]) + 8u * g;
+      const uint32_t bar_d2 = TC_BAR(d2_full[0][0]) + 16u * g;
+      const uint32_t bar_d3 = TC_BAR(d3_full[0][0]) + 16u * g;
+      const uint32_t bar_free = TC_BAR(d3_free[0][0]) + 16u * g;
+      const uint32_t w2 = sb + sl.w2, w3 = sb + sl.w3;
+      uint32_t ph_ready = 0u;
+      uint32_t np0 = 0u, np1 = 0u;  // passes issued so far into each accumulator buffer
+      for (int s = 0; s < total_seq; ++s) {
+        const int L = stage_of(s).L;
+        const int my_tiles = (tiles_of(s) - g + 1) / 2;
+        for (int k = 0; k < my_tiles; ++k) {
+          // ---- hidden GEMM, two N = 64 halves: X (h1) x W2 -> Y ----
+          if (k == 0) mbar_wait(TC_BAR(w2_full), (uint32_t)(s & 1));
+          mbar_wait(bar_ready, ph_ready);
+          ph_ready ^= 1u;
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            issue_gemm(t_y + 64u * h, t_x, w2 + h * 64 * 128, w2 + TC_W2_BYTES / 2 + h * 64 * 128, 128 * 128, idesc2);
+            umma_commit(bar_d2 + 8u * h);
+          }
+          if (k == my_tiles - 1) umma_commit(TC_BAR(w2_free));  // W2 is free once this group's last hidden GEMM is done
+          // ---- output layer, one N = 48 pass per spline dimension: Y (h2) x W3 -> X[0,48) / X[64,112) ----
+          if (k == 0) mbar_wait(TC_BAR(w3_full), (uint32_t)(s & 1));
+          mbar_wait(bar_ready, ph_ready);
+          ph_ready ^= 1u;
+          tc_fence_after();
+          for (int d = 0; d < L; ++d) {
+            const int b = d & 1;
+            const uint32_t np = b ? np1 : np0;
+            if (np > 0u) {  // the buffer's previous pass must have been drained
+              mbar_wait(bar_free + 8u * b, (np - 1u) & 1u);
+              tc_fence_after();
+            }
+            const uint32_t tile = w3 + (uint32_t)(d >> 1) * TC_W3_PASS_BYTES + (uint32_t)b * (TC_DIM_N * 128);
+            issue_gemm(t_x + 64u * b, t_y, tile, tile + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idesc3);
+            umma_commit(bar_d3 + 8u * b);
+            np0 += b ? 0u : 1u;
+            np1 += b ? 1u : 0u;
+          }
+          if (k == my_tiles - 1) umma_commit(TC_BAR(w3_free));
         }
       }
-      if (w3_next < total_seq) {
-        if (w3_next > w3_freed && mbar_test_wait(smem_u32(&sh->w3free), (uint32_t)(w3_freed & 1))) ++w3_freed;
-        if (w3_next <= w3_freed) {
-          const NscDev& st = stage_of(w3_next);
-          const TcLayout lay = TcLayout::make(st.L);
-          const uint32_t bar = smem_u32(&sh->w3full);
+    } else {
+      // =============================== weight streamer ===============================
+      for (int s = 0; s < total_seq; ++s) {
+        const NscDev& st = stage_of(s);
+        const TcLayout lay = TcLayout::make(st.L);
+        const uint8_t* src = static_cast<const uint8_t*>(st.tc.blob);
+        {  // parameter block: buffer s & 1 was last used by stage s - 2
+          if (s >= 2) mbar_wait(TC_BAR(par_free[0]) + 8u * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
+          const uint32_t bar = TC_BAR(par_full[0]) + 8u * (s & 1);
+          mbar_expect_tx(bar, TC_PAR_BYTES);
+          tma_bulk_g2s(sb + sl.par + (s & 1) * TC_PAR_BYTES, src + lay.par, TC_PAR_BYTES, bar);
+        }
+        {
+          if (s >= 1) mbar_wait(TC_BAR(w2_free), (uint32_t)((s - 1) & 1));
+          const uint32_t bar = TC_BAR(w2_full);
+          mbar_expect_tx(bar, TC_W2_BYTES);
+          for (int off = 0; off < TC_W2_BYTES; off += 16384) tma_bulk_g2s(sb + sl.w2 + off, src + off, 16384u, bar);
+        }
+        {
+          if (s >= 1) mbar_wait(TC_BAR(w3_free), (uint32_t)((s - 1) & 1));
+          const uint32_t bar = TC_BAR(w3_full);
           const int nb = lay.n_pass * TC_W3_PASS_BYTES;
           mbar_expect_tx(bar, (uint32_t)nb);
-          const uint8_t* src = static_cast<const uint8_t*>(st.tc.blob) + lay.w3;
-          for (int off = 0; off < nb; off += 16384) tma_bulk_g2s(sb + sl.w3 + off, src + off, 16384u, bar);
-          ++w3_next;
-          progress = true;
+          for (int off = 0; off < nb; off += 16384) tma_bulk_g2s(sb + sl.w3 + off, src + lay.w3 + off, 16384u, bar);
         }
       }
-      if (par_next < total_seq) {
-        // block par_next reuses the buffer of stage par_next - 2: both groups must have finished it
-        for (int g = 0; g < 2; ++g)
-          if (lay_seen[g] < par_next - 1 && mbar_test_wait(smem_u32(&sh->lay_done[g]), (uint32_t)(lay_seen[g] & 1)))
-            ++lay_seen[g];
-        if (par_next < 2 || (lay_seen[0] >= par_next - 1 && lay_seen[1] >= par_next - 1)) {
-          const NscDev& st = stage_of(par_next);
-          const TcLayout lay = TcLayout::make(st.L);
-          const uint32_t bar = smem_u32(&sh->parfull[par_next & 1]);
-          mbar_expect_tx(bar, TC_PAR_BYTES);
-          tma_bulk_g2s(sb + sl.par + (par_next & 1) * TC_PAR_BYTES, static_cast<const uint8_t*>(st.tc.blob) + lay.par,
-                       TC_PAR_BYTES, bar);
-          ++par_next;
-          progress = true;
-        }
-      }
-      // ---- GEMMs: serve whichever group is ready ----
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (gs[g] >= total_seq) continue;
-        if (!gready[g]) {
-          if (!mbar_test_wait(smem_u32(&sh->go[g]), gpar[g])) continue;
-          gpar[g] ^= 1u;
-          gready[g] = true;
-        }
-        const int s = gs[g];
-        if (gp[g] == 0) {
-          if (w2_ready <= s) {
-            if (w2_next > s && mbar_test_wait(smem_u32(&sh->w2full), (uint32_t)(s & 1))) w2_ready = s + 1;
-            else continue;
-          }
-        } else {
-          if (w3_ready <= s) {
-            if (w3_next > s && mbar_test_wait(smem_u32(&sh->w3full), (uint32_t)(s & 1))) w3_ready = s + 1;
-            else continue;
-          }
-        }
-        tc_fence_after();
-        const uint32_t a_t = tbase + g * 256, d_t = tbase + g * 256 + 128;
-        if (gp[g] == 0) {
-          issue_gemm(d_t, a_t, sb + sl.w2, sb + sl.w2 + TC_W2_BYTES / 2, 128, idesc2);
-          umma_commit(smem_u32(&sh->done[g]));
-          if (++c2_cnt == gnt[g]) {  // every hidden GEMM of the stage is issued: release W2 when they complete
-            umma_commit(smem_u32(&sh->w2free));
-            c2_cnt = 0;
-          }
-        } else {
-          const uint32_t w3 = sb + sl.w3 + (gp[g] - 1) * TC_W3_PASS_BYTES;
-          issue_gemm(d_t, a_t, w3, w3 + TC_W3_PASS_BYTES / 2, TC_PASS_N, idesc3);
-          umma_commit(smem_u32(&sh->done[g]));
-          if (++c3_cnt == gnt[g] * gnp[g]) {
-            umma_commit(smem_u32(&sh->w3free));
-            c3_cnt = 0;
-          }
-        }
-        gready[g] = false;
-        progress = true;
-        if (++gp[g] > gnp[g]) {
-          gp[g] = 0;
-          if (++gk[g] == (gnt[g] - g + 1) / 2) {
-            gk[g] = 0;
-            if (++gs[g] < total_seq) {
-              gnp[g] = (stage_of(gs[g]).L + 1) / 2;
-              gnt[g] = tiles_of(gs[g]);
-            }
-          }
-        }
-      }
-      if (!progress) __nanosleep(20);
     }
   }
 
@@ -864,13 +929,7 @@ cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs
   TcLaunch lp;
   lp.max_pass = 1;
   for (int s = 0; s < hp.n_nsc; ++s) lp.max_pass = max(lp.max_pass, (hp.nsc[s].L + 1) / 2);
-  // chain nesting depth actually used (log-det levels)
-  int depth = 0, level = 0;
-  for (int i = 0; i < hp.n_steps; ++i) {
-    if (hp.steps[i].kind == STEP_CHAIN_BEGIN) depth = max(depth, ++level);
-    else if (hp.steps[i].kind == STEP_CHAIN_END) --level;
-  }
-  lp.n_lev = depth + 1;
+  lp.n_lev = tc_log_det_levels(hp);
   lp.state_cols = hp.D + lp.n_lev + 2 + hp.C;
   // rows per chunk: as many 128-row tiles as shared memory holds, fewer when that leaves SMs idle
   int fit = TC_MAX_CHUNK_TILES;
@@ -879,11 +938,6 @@ cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs
   long long want = (tiles_total + num_sms - 1) / num_sms;
   if (want < 2) want = 2;
   lp.chunk_tiles = (int)(want < fit ? want : fit);
-  if (lp.chunk_tiles > 8 && want > fit) {
-    // balance: the largest chunk size <= fit that leaves the last wave as full as possible is not worth
-    // a search here; 8 tiles keep the per-stage weight reload below 2 % of the stage's math
-    lp.chunk_tiles = fit;
-  }
   const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols);
   const size_t smem = (size_t)sl.total + 1024;
   if (smem > (size_t)TC_SMEM_MAX) return cudaErrorInvalidConfiguration;

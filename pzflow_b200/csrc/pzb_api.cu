@@ -19,7 +19,7 @@ cudaError_t launch_simt(const PlanDev* d_plan, const LaunchArgs& args, int D, in
                         int act_rows, bool pingpong, int num_sms, cudaStream_t stream);
 bool tc_plan_supported(const PlanDev& hp);
 size_t tc_pack_bytes(const NscDev& st);
-void tc_pack_stage(const NscDev& st, const float* const* weights, void* dst);
+void tc_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weights, void* dst);
 cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms,
                       void* workspace, cudaStream_t stream);
 }  // namespace pzb
@@ -381,7 +381,7 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
     for (const Pending& pe : pend) {
       NscDev& st = hp.nsc[pe.nsc_idx];
       const size_t nb = tc_pack_bytes(st);
-      tc_pack_stage(st, pe.weights, hblob.data() + o);
+      tc_pack_stage(hp, st, pe.weights, hblob.data() + o);
       st.tc.blob = dbase + o;
       st.tc.blob_bytes = (int)nb;
       o += align_up(nb, 1024);
