@@ -280,6 +280,14 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One lane of a converged warp.  The region it guards stays on the uniform datapath (operands of
+// tcgen05.mma / commit in uniform registers), unlike a `lane == 0` branch, which ptxas treats as divergent
+// and pays ~10 instructions per MMA for (R2UR of every operand + its own ELECT).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -568,6 +576,19 @@ __device__ __noinline__ int level_after(const PlanDev* plan, bool inverse, int s
 
 #define TC_BAR(field) (sh_addr + (uint32_t)offsetof(TcShared, field))
 
+#ifdef PZB_TC_TRACE
+// debug build only: SM-clock timestamps of the epilogue phases of CTA 0, second coupling stage of its first chunk
+__device__ unsigned int g_tc_trace[19 * 8 * 8];
+#define TC_TRACE(ev)                                                                         \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && lane == 0 && seq == 1 && k < 8) g_tc_trace[(warp * 8 + k) * 8 + (ev)] = (unsigned int)clock64(); \
+  } while (0)
+#else
+#define TC_TRACE(ev) \
+  do {               \
+  } while (0)
+#endif
+
 template <bool INV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch lp) {
@@ -626,6 +647,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
     const int grp = (warp >> 3) & 1;                   // epilogue group
     const int half = (warp >> 2) & 1;                  // which half of the row's work
     const int lrow = ((warp & 3) << 5) + lane;         // row within the tile == TMEM lane
+    const int gtid = (int)(tid & (TC_GROUP_THREADS - 1));  // thread index within the group
     const uint32_t t_x = tbase + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)grp * 256u + (uint32_t)half * 64u;
     const uint32_t t_y = t_x + 128u;                   // this half's 64 columns of X / Y
     const uint32_t bar_ready = TC_BAR(e_ready[0]) + 8u * grp;
@@ -649,8 +671,11 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       const int ntiles = max(2, (nrows + TC_TILE - 1) / TC_TILE);
       const int my_tiles = (ntiles - grp + 1) / 2;
 
-      // ---- pass A: rows -> state, steps in front of the first coupling stage ----
-      for (int r = (int)tid; r < nrows; r += TC_EPI_THREADS) {
+      // ---- pass A: rows of this group's tiles -> state, steps in front of the first coupling stage ----
+      // (the two groups never wait for each other: they only meet through the weight buffers)
+      for (int q = gtid; q < my_tiles * TC_TILE; q += TC_GROUP_THREADS) {
+        const int r = (2 * (q >> 7) + grp) * TC_TILE + (q & (TC_TILE - 1));
+        if (r >= nrows) continue;
         const long long row = row0 + r;
         float* st = state + r;
         for (int j = 0; j < D; ++j) {
@@ -671,7 +696,13 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         light_steps_cols(plan, INV, 0, first_nsc, level, st, CR);
       }
       int level = level_after(plan, INV, 0, first_nsc, 0);  // chain depth (row independent)
-      named_bar_sync(1, TC_EPI_THREADS);
+      named_bar_sync(2 + grp, TC_GROUP_THREADS);
+#ifdef PZB_TC_STAGGER
+      if (ci == 0 && grp == 1) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < PZB_TC_STAGGER) __nanosleep(200);
+      }
+#endif
 
       // ---- the coupling stages ----
       int prev_end = first_nsc;
@@ -708,6 +739,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           }
 
           // ---- E1: h1 = LeakyReLU(key @ W1 + b1), this half's 64 hidden columns -> fp16 hi/lo in X ----
+          TC_TRACE(0);
           {
             const int in_dim = pint[TC_PI_IN];
 #pragma unroll 1
@@ -744,11 +776,13 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_ready);
+          TC_TRACE(1);
 
           // ---- E2: h2 = LeakyReLU(D * 2^-e2 + b2), rewritten in place over this half's accumulator columns ----
           mbar_wait(bar_d2, ph_d2);
           ph_d2 ^= 1u;
           tc_fence_after();
+          TC_TRACE(2);
           {
             const float s2inv = par[TC_PF_SCAL];
 #pragma unroll 1
@@ -775,6 +809,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_ready);
+          TC_TRACE(3);
 
           // ---- E3: logits -> knots -> spline; this thread takes the dimensions half, half + 2 ----
           float ldsum = 0.0f;
@@ -783,6 +818,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             mbar_wait(bar_d3, ph_d3);
             ph_d3 ^= 1u;
             tc_fence_after();
+            TC_TRACE(d < 2 ? 4 : 6);
             float raw[48];
             tmem_ld32(t_x, raw);
             tmem_ld16(t_x + 32, raw + 32);
@@ -797,6 +833,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
                             par[TC_PF_SCAL + 3], pint[TC_PI_PERIODIC] != 0, y, ldd, idx);
             ldsum += ldd;
             srow[col * CR] = y;
+            TC_TRACE(d < 2 ? 5 : 7);
             if (args.bins != nullptr && r < nrows)
               args.bins[(row0 + r) * plan->n_spline_dims + pint[TC_PI_BINS] + d] = idx;
           }
@@ -807,10 +844,12 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         pend_level = level;
         ++seq;
       }
-      named_bar_sync(1, TC_EPI_THREADS);
+      named_bar_sync(2 + grp, TC_GROUP_THREADS);
 
-      // ---- pass Z: trailing steps, latent log-density, outputs ----
-      for (int r = (int)tid; r < nrows; r += TC_EPI_THREADS) {
+      // ---- pass Z: trailing steps, latent log-density, outputs of this group's tiles ----
+      for (int q = gtid; q < my_tiles * TC_TILE; q += TC_GROUP_THREADS) {
+        const int r = (2 * (q >> 7) + grp) * TC_TILE + (q & (TC_TILE - 1));
+        if (r >= nrows) continue;
         const long long row = row0 + r;
         float* st = state + r;
         if (pending) st[(D + pend_level) * CR] += st[COL_PEND * CR] + st[(COL_PEND + 1) * CR];
@@ -828,11 +867,14 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       }
       // (pass A of the next chunk touches a row from the same thread as pass Z did: no barrier needed)
     }
-  } else if (lane == 0) {
+  } else {
+    // control warps run converged (all 32 lanes wait on the mbarriers); one elected lane issues
     const uint32_t sb = smem_u32(base);
     const int total_seq = my_chunks * n_nsc;
     // coupling stage (walk order) of sequence number s, and the tile count of its chunk
-    auto stage_of = [&](int s) -> const NscDev& { return plan->nsc[sh->order[s % n_nsc]]; };
+    auto stage_of = [&](int s) -> const NscDev& {
+      return plan->nsc[__shfl_sync(0xffffffffu, (int)sh->order[s % n_nsc], 0)];
+    };
     auto tiles_of = [&](int s) -> int {
       const long long row0 = ((long long)blockIdx.x + (long long)(s / n_nsc) * gridDim.x) * chunk_rows;
       const int nrows = (int)min(chunk_rows, args.N - row0);
@@ -840,8 +882,8 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
     };
     if (warp < 18) {
       // =============================== MMA issuer of group g ===============================
-      const int g = warp - 16;
-      const uint32_t t_x = tbase + (uint32_t)g * 256u, t_y = t_x + 128u;
+      const int g = __shfl_sync(0xffffffffu, warp, 0) - 16;
+      const uint32_t t_x = __shfl_sync(0xffffffffu, tbase, 0) + (uint32_t)g * 256u, t_y = t_x + 128u;
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc3 = (1u << 4) | ((uint32_t)(TC_DIM_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t bar_ready = TC_BAR(e_ready[0]) + 8u * g;
@@ -852,7 +894,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       uint32_t ph_ready = 0u;
       uint32_t np0 = 0u, np1 = 0u;  // passes issued so far into each accumulator buffer
       for (int s = 0; s < total_seq; ++s) {
-        const int L = stage_of(s).L;
+        const int L = __shfl_sync(0xffffffffu, stage_of(s).L, 0);
         const int my_tiles = (tiles_of(s) - g + 1) / 2;
         for (int k = 0; k < my_tiles; ++k) {
           // ---- hidden GEMM, two N = 64 halves: X (h1) x W2 -> Y ----
@@ -860,12 +902,15 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           mbar_wait(bar_ready, ph_ready);
           ph_ready ^= 1u;
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            issue_gemm(t_y + 64u * h, t_x, w2 + h * 64 * 128, w2 + TC_W2_BYTES / 2 + h * 64 * 128, 128 * 128, idesc2);
-            umma_commit(bar_d2 + 8u * h);
+            for (int h = 0; h < 2; ++h) {
+              issue_gemm(t_y + 64u * h, t_x, w2 + h * 64 * 128, w2 + TC_W2_BYTES / 2 + h * 64 * 128, 128 * 128, idesc2);
+              umma_commit(bar_d2 + 8u * h);
+            }
+            if (k == my_tiles - 1) umma_commit(TC_BAR(w2_free));  // W2 is free once this group's last hidden GEMM is done
           }
-          if (k == my_tiles - 1) umma_commit(TC_BAR(w2_free));  // W2 is free once this group's last hidden GEMM is done
+          __syncwarp();
           // ---- output layer, one N = 48 pass per spline dimension: Y (h2) x W3 -> X[0,48) / X[64,112) ----
           if (k == 0) mbar_wait(TC_BAR(w3_full), (uint32_t)(s & 1));
           mbar_wait(bar_ready, ph_ready);
@@ -879,12 +924,15 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               tc_fence_after();
             }
             const uint32_t tile = w3 + (uint32_t)(d >> 1) * TC_W3_PASS_BYTES + (uint32_t)b * (TC_DIM_N * 128);
-            issue_gemm(t_x + 64u * b, t_y, tile, tile + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idesc3);
-            umma_commit(bar_d3 + 8u * b);
+            if (elect_one()) {
+              issue_gemm(t_x + 64u * b, t_y, tile, tile + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idesc3);
+              umma_commit(bar_d3 + 8u * b);
+              if (d == L - 1 && k == my_tiles - 1) umma_commit(TC_BAR(w3_free));
+            }
+            __syncwarp();
             np0 += b ? 0u : 1u;
             np1 += b ? 1u : 0u;
           }
-          if (k == my_tiles - 1) umma_commit(TC_BAR(w3_free));
         }
       }
     } else {
@@ -896,22 +944,29 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         {  // parameter block: buffer s & 1 was last used by stage s - 2
           if (s >= 2) mbar_wait(TC_BAR(par_free[0]) + 8u * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
           const uint32_t bar = TC_BAR(par_full[0]) + 8u * (s & 1);
-          mbar_expect_tx(bar, TC_PAR_BYTES);
-          tma_bulk_g2s(sb + sl.par + (s & 1) * TC_PAR_BYTES, src + lay.par, TC_PAR_BYTES, bar);
+          if (lane == 0) {
+            mbar_expect_tx(bar, TC_PAR_BYTES);
+            tma_bulk_g2s(sb + sl.par + (s & 1) * TC_PAR_BYTES, src + lay.par, TC_PAR_BYTES, bar);
+          }
         }
         {
           if (s >= 1) mbar_wait(TC_BAR(w2_free), (uint32_t)((s - 1) & 1));
           const uint32_t bar = TC_BAR(w2_full);
-          mbar_expect_tx(bar, TC_W2_BYTES);
-          for (int off = 0; off < TC_W2_BYTES; off += 16384) tma_bulk_g2s(sb + sl.w2 + off, src + off, 16384u, bar);
+          if (lane == 0) {
+            mbar_expect_tx(bar, TC_W2_BYTES);
+            for (int off = 0; off < TC_W2_BYTES; off += 16384) tma_bulk_g2s(sb + sl.w2 + off, src + off, 16384u, bar);
+          }
         }
         {
           if (s >= 1) mbar_wait(TC_BAR(w3_free), (uint32_t)((s - 1) & 1));
           const uint32_t bar = TC_BAR(w3_full);
           const int nb = lay.n_pass * TC_W3_PASS_BYTES;
-          mbar_expect_tx(bar, (uint32_t)nb);
-          for (int off = 0; off < nb; off += 16384) tma_bulk_g2s(sb + sl.w3 + off, src + lay.w3 + off, 16384u, bar);
+          if (lane == 0) {
+            mbar_expect_tx(bar, (uint32_t)nb);
+            for (int off = 0; off < nb; off += 16384) tma_bulk_g2s(sb + sl.w3 + off, src + lay.w3 + off, 16384u, bar);
+          }
         }
+        __syncwarp();
       }
     }
   }
@@ -958,3 +1013,9 @@ cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs
 }
 
 }  // namespace pzb
+
+#ifdef PZB_TC_TRACE
+extern "C" int pzb_debug_tc_trace(unsigned int* out) {
+  return (int)cudaMemcpyFromSymbol(out, pzb::g_tc_trace, sizeof(pzb::g_tc_trace));
+}
+#endif
