@@ -295,11 +295,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // fp32 pair -> fp16 hi pair + fp16 lo pair (k even in the low half of each 32-bit column)
+// The residual a - float(hi) is one mixed-precision FMA per element (fma.rn.f32.f16 -> FHFMA: hi * -1 + a,
+// exact), so a pair costs F2FP + 2 FHFMA + F2FP.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
+  const unsigned short h0 = (unsigned short)(hi & 0xffffu), h1 = (unsigned short)(hi >> 16), m1 = 0xBC00;  // -1.0
+  float r0, r1;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r0) : "h"(h0), "h"(m1), "f"(a));
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r1) : "h"(h1), "h"(m1), "f"(b));
+  const __half2 l = __floats2half2_rn(r0, r1);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
