@@ -313,8 +313,10 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 // epilogue thread can rewrite 32 fp32 accumulator columns in place.  K-step k16 (16 elements):
 __device__ __forceinline__ constexpr uint32_t a_col_of(int k16) { return (uint32_t)((k16 >> 1) * 32 + (k16 & 1) * 8); }
 
-// D[128 x N] = A(hi,lo)[128 x 128] * B(hi,lo)[N x 128]^T as lo*hi + hi*lo + hi*hi (24 MMAs).
+// D[128 x N] (+)= A(hi,lo)[128 x 16 K] * B(hi,lo)[N x 16 K]^T over the K-steps [K0, K1) of 16 elements, as
+// lo*hi + hi*lo + hi*hi (3 MMAs per K-step).  FRESH: the first MMA overwrites the accumulator.
 // sb_hi / sb_lo: shared addresses of the first B row of the (sub-)tile; kblk: bytes between its two K blocks.
+template <int K0, int K1, bool FRESH>
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_tmem, uint32_t sb_hi, uint32_t sb_lo, uint32_t kblk,
                                            uint32_t idesc) {
   const uint64_t dh = make_b_desc(sb_hi), dl = make_b_desc(sb_lo);
@@ -324,9 +326,9 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_tmem, uin
     const uint32_t a_off = (prod == 0) ? 16u : 0u;  // lo * hi first
     const uint64_t db = (prod == 1) ? dl : dh;
 #pragma unroll
-    for (int k16 = 0; k16 < 8; ++k16) {
+    for (int k16 = K0; k16 < K1; ++k16) {
       const uint64_t bdesc = db + (uint64_t)((k16 >> 2) * kb16 + (k16 & 3) * 2);
-      if (prod == 0 && k16 == 0)
+      if (FRESH && prod == 0 && k16 == K0)
         umma_f16_ts<false>(d_tmem, a_tmem + a_off + a_col_of(k16), bdesc, idesc);
       else
         umma_f16_ts<true>(d_tmem, a_tmem + a_off + a_col_of(k16), bdesc, idesc);
@@ -447,10 +449,12 @@ __device__ __forceinline__ void spline_dim(const float (&raw)[48], const float* 
   const bool oob = (x <= -B) || (x >= B);
   const float mx = oob ? fabsf(x) - B : x;
   BinPick k;
-  float e[16], G1, G2, G3, tot;
-
+  // both axes' softmax terms and group sums up front: two independent dependency chains for the scheduler
+  float e[16], f[16], G1, G2, G3, tot, H1, H2, H3, tot2;
   softmax_terms(raw + SO, bias + SO, sinv, e);
+  softmax_terms(raw + OO, bias + OO, sinv, f);
   group_sums(e, G1, G2, G3, tot);
+  group_sums(f, H1, H2, H3, tot2);
   const float target = (mx + B) * (tot * inv2B);  // (x + B) * sum(e) / 2B
   float cs_sel, s_sel;
   pick_bin<true>(e, G1, G2, G3, target, k, cs_sel, s_sel);
@@ -462,11 +466,9 @@ __device__ __forceinline__ void spline_dim(const float (&raw)[48], const float* 
   if (!(-B <= mx)) idx = -1;
   idx_out = idx;
 
-  softmax_terms(raw + OO, bias + OO, sinv, e);
-  group_sums(e, G1, G2, G3, tot);
   float co_sel, o_sel;
-  pick_bin<false>(e, G1, G2, G3, 0.0f, k, co_sel, o_sel);
-  const float ro = __fdividef(twoB, tot);
+  pick_bin<false>(f, H1, H2, H3, 0.0f, k, co_sel, o_sel);
+  const float ro = __fdividef(twoB, tot2);
 
   // derivative logits D[idx - 1], D[idx] (raw[32 + j]; raw[47] is the zero pad unless periodic)
   float v[5];
@@ -500,7 +502,8 @@ __device__ __forceinline__ void spline_dim(const float (&raw)[48], const float* 
 }
 
 struct TcShared {
-  uint64_t e_ready[2];     // epilogue group -> its MMA issuer (256 arrivals): A operand written (after E1 and after E2)
+  uint64_t e_ready[2][2];  // [group][half] -> the group's MMA issuer (128 arrivals): that half's 64 K-elements of the
+                           // A operand are written (after E1 and after E2)
   uint64_t d2_full[2][2];  // [group][half]: that N = 64 half of the hidden GEMM has completed (tcgen05.commit)
   uint64_t d3_full[2][2];  // [group][buffer]: an output pass has landed in that accumulator buffer
   uint64_t d3_free[2][2];  // [group][buffer]: the half's 128 threads have drained the buffer
@@ -588,7 +591,14 @@ __device__ unsigned int g_tc_trace[19 * 8 * 8];
   do {                                                                                       \
     if (blockIdx.x == 0 && lane == 0 && seq == 1 && k < 8) g_tc_trace[(warp * 8 + k) * 8 + (ev)] = (unsigned int)clock64(); \
   } while (0)
+#define TC_TRACE_I(ev)                                                                       \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && lane == 0 && s == 1 && k < 8) g_tc_trace[(warp * 8 + k) * 8 + (ev)] = (unsigned int)clock64(); \
+  } while (0)
 #else
+#define TC_TRACE_I(ev) \
+  do {                 \
+  } while (0)
 #define TC_TRACE(ev) \
   do {               \
   } while (0)
@@ -613,8 +623,8 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
 
   if (tid == 0) {
     for (int g = 0; g < 2; ++g) {
-      mbar_init(TC_BAR(e_ready[g]), TC_GROUP_THREADS);
       for (int h = 0; h < 2; ++h) {
+        mbar_init(TC_BAR(e_ready[g][h]), TC_TILE);
         mbar_init(TC_BAR(d2_full[g][h]), 1);
         mbar_init(TC_BAR(d3_full[g][h]), 1);
         mbar_init(TC_BAR(d3_free[g][h]), TC_TILE);
@@ -655,7 +665,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
     const int gtid = (int)(tid & (TC_GROUP_THREADS - 1));  // thread index within the group
     const uint32_t t_x = tbase + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)grp * 256u + (uint32_t)half * 64u;
     const uint32_t t_y = t_x + 128u;                   // this half's 64 columns of X / Y
-    const uint32_t bar_ready = TC_BAR(e_ready[0]) + 8u * grp;
+    const uint32_t bar_ready = TC_BAR(e_ready[0][0]) + 16u * grp + 8u * half;
     const uint32_t bar_d2 = TC_BAR(d2_full[0][0]) + 16u * grp + 8u * half;
     const uint32_t bar_d3 = TC_BAR(d3_full[0][0]) + 16u * grp + 8u * half;
     const uint32_t bar_free = TC_BAR(d3_free[0][0]) + 16u * grp + 8u * half;
@@ -891,7 +901,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       const uint32_t t_x = __shfl_sync(0xffffffffu, tbase, 0) + (uint32_t)g * 256u, t_y = t_x + 128u;
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc3 = (1u << 4) | ((uint32_t)(TC_DIM_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t bar_ready = TC_BAR(e_ready[0]) + 8u * g;
+      const uint32_t bar_ready = TC_BAR(e_ready[0][0]) + 16u * g;
       const uint32_t bar_d2 = TC_BAR(d2_full[0][0]) + 16u * g;
       const uint32_t bar_d3 = TC_BAR(d3_full[0][0]) + 16u * g;
       const uint32_t bar_free = TC_BAR(d3_free[0][0]) + 16u * g;
@@ -904,33 +914,67 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         for (int k = 0; k < my_tiles; ++k) {
           // ---- hidden GEMM, two N = 64 halves: X (h1) x W2 -> Y ----
           if (k == 0) mbar_wait(TC_BAR(w2_full), (uint32_t)(s & 1));
+          TC_TRACE_I(0);
           mbar_wait(bar_ready, ph_ready);
+          mbar_wait(bar_ready + 8u, ph_ready);
           ph_ready ^= 1u;
           tc_fence_after();
+          TC_TRACE_I(1);
           if (elect_one()) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              issue_gemm(t_y + 64u * h, t_x, w2 + h * 64 * 128, w2 + TC_W2_BYTES / 2 + h * 64 * 128, 128 * 128, idesc2);
+              issue_gemm<0, 8, true>(t_y + 64u * h, t_x, w2 + h * 64 * 128, w2 + TC_W2_BYTES / 2 + h * 64 * 128, 128 * 128,
+                                     idesc2);
               umma_commit(bar_d2 + 8u * h);
             }
             if (k == my_tiles - 1) umma_commit(TC_BAR(w2_free));  // W2 is free once this group's last hidden GEMM is done
           }
           __syncwarp();
-          // ---- output layer, one N = 48 pass per spline dimension: Y (h2) x W3 -> X[0,48) / X[64,112) ----
+          // ---- output layer, one N = 48 pass per spline dimension: Y (h2) x W3 -> X[0,48) / X[64,112).  Half 0
+          // finishes its E2 first (its GEMM half commits first): the first two passes start on its 64 K-elements
+          // and take the other 64 when half 1 arrives ----
+          TC_TRACE_I(2);
           if (k == 0) mbar_wait(TC_BAR(w3_full), (uint32_t)(s & 1));
           mbar_wait(bar_ready, ph_ready);
-          ph_ready ^= 1u;
           tc_fence_after();
-          for (int d = 0; d < L; ++d) {
-            const int b = d & 1;
-            const uint32_t np = b ? np1 : np0;
+          TC_TRACE_I(3);
+          const int n_early = L < 2 ? L : 2;
+          for (int d = 0; d < n_early; ++d) {
+            const uint32_t np = d ? np1 : np0;
             if (np > 0u) {  // the buffer's previous pass must have been drained
-              mbar_wait(bar_free + 8u * b, (np - 1u) & 1u);
+              mbar_wait(bar_free + 8u * d, (np - 1u) & 1u);
               tc_fence_after();
             }
+            const uint32_t tile = w3 + (uint32_t)d * (TC_DIM_N * 128);
+            if (elect_one()) issue_gemm<0, 4, true>(t_x + 64u * d, t_y, tile, tile + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idesc3);
+            __syncwarp();
+          }
+          TC_TRACE_I(4);
+          mbar_wait(bar_ready + 8u, ph_ready);
+          ph_ready ^= 1u;
+          tc_fence_after();
+          TC_TRACE_I(5);
+          for (int d = 0; d < n_early; ++d) {
+            const uint32_t tile = w3 + (uint32_t)d * (TC_DIM_N * 128);
+            if (elect_one()) {
+              issue_gemm<4, 8, false>(t_x + 64u * d, t_y, tile, tile + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idesc3);
+              umma_commit(bar_d3 + 8u * d);
+              if (d == L - 1 && k == my_tiles - 1) umma_commit(TC_BAR(w3_free));
+            }
+            __syncwarp();
+            np0 += d ? 0u : 1u;
+            np1 += d ? 1u : 0u;
+          }
+          TC_TRACE_I(6);
+          for (int d = 2; d < L; ++d) {
+            const int b = d & 1;
+            const uint32_t np = b ? np1 : np0;
+            mbar_wait(bar_free + 8u * b, (np - 1u) & 1u);  // the buffer's previous pass must have been drained
+            tc_fence_after();
+            if (d == L - 1) TC_TRACE_I(7);
             const uint32_t tile = w3 + (uint32_t)(d >> 1) * TC_W3_PASS_BYTES + (uint32_t)b * (TC_DIM_N * 128);
             if (elect_one()) {
-              issue_gemm(t_x + 64u * b, t_y, tile, tile + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idesc3);
+              issue_gemm<0, 8, true>(t_x + 64u * b, t_y, tile, tile + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idesc3);
               umma_commit(bar_d3 + 8u * b);
               if (d == L - 1 && k == my_tiles - 1) umma_commit(TC_BAR(w3_free));
             }
