@@ -56,28 +56,28 @@ constexpr int TC_DIM_N = 48;                      // logit columns of one spline
 constexpr int TC_PASS_N = 96;                     // rows of one packed W3 tile: two spline dimensions
 constexpr int TC_W2_BYTES = 2 * 128 * 128 * 2;    // fp16 hi + lo [128 x 128] tiles
 constexpr int TC_W3_PASS_BYTES = 2 * TC_PASS_N * 128 * 2;  // fp16 hi + lo [96 x 128] tiles
-// fp32 parameter block of a stage: W1[TC_IN_MAX][128], b1[128], b2[128], b3[2 * 96], scal[4], then 24 ints
-constexpr int TC_PF_W1 = 0;
-constexpr int TC_PF_B1 = TC_IN_MAX * 128;
-constexpr int TC_PF_B2 = TC_PF_B1 + 128;
+constexpr int TC_W1_BYTES = 2 * 128 * 16 * 2;     // fp16 hi + lo [128 x 16] tiles: K = key (<= 8), 1 (bias row), zero pad
+// fp32 parameter block of a stage: b2[128], b3[2 * 96], scal[4], then 24 ints
+constexpr int TC_PF_B2 = 0;
 constexpr int TC_PF_B3 = TC_PF_B2 + 128;
 constexpr int TC_PF_SCAL = TC_PF_B3 + 2 * TC_PASS_N;  // s2inv, s3inv, B, 1/(2B)
 constexpr int TC_PI = TC_PF_SCAL + 4;                 // ints: key_col[8], low_col[4], U, L, in_dim, periodic, bins_off
 constexpr int TC_PI_KEY = 0, TC_PI_LOW = 8, TC_PI_U = 12, TC_PI_L = 13, TC_PI_IN = 14, TC_PI_PERIODIC = 15,
               TC_PI_BINS = 16;
 constexpr int TC_PAR_FLOATS = TC_PI + 24;
-constexpr int TC_PAR_BYTES = TC_PAR_FLOATS * 4;   // 6000, a multiple of 16
+constexpr int TC_PAR_BYTES = TC_PAR_FLOATS * 4;   // 1392, a multiple of 16
 constexpr int TC_SMEM_MAX = 232448;               // 227 KB opt-in limit per CTA
 static_assert(TC_PAR_BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 
-// global blob of one coupling stage: [W2 hi | W2 lo | pass0 hi | pass0 lo | pass1 hi | pass1 lo | par]
+// global blob of one coupling stage: [W2 hi | W2 lo | pass0 hi | pass0 lo | pass1 hi | pass1 lo | W1 hi | W1 lo | par]
 struct TcLayout {
-  int w3, par, total, n_pass;
+  int w3, w1, par, total, n_pass;
   __host__ __device__ static TcLayout make(int L) {
     TcLayout t;
     t.n_pass = (L + 1) / 2;
     t.w3 = TC_W2_BYTES;
-    t.par = t.w3 + t.n_pass * TC_W3_PASS_BYTES;
+    t.w1 = t.w3 + t.n_pass * TC_W3_PASS_BYTES;
+    t.par = t.w1 + TC_W1_BYTES;
     t.total = t.par + TC_PAR_BYTES;
     return t;
   }
@@ -124,6 +124,10 @@ static inline size_t sw128_index(int rows, int n, int k) {
   return (size_t)kb * rows * 64 + (size_t)n * 64 + (size_t)((c ^ (n & 7)) * 8) + e;
 }
 
+// element (n, k) of the K-major SWIZZLE_NONE [128 x 16] tile: 8 x 8 core matrices of 128 contiguous bytes,
+// K-adjacent cores 128 B apart (LBO), 8-row groups 256 B apart (SBO)
+static inline size_t w1_index(int n, int k) { return (size_t)(n >> 3) * 128 + (size_t)(k >> 3) * 64 + (size_t)(n & 7) * 8 + (k & 7); }
+
 static inline void split_store(__half* hi, __half* lo, size_t idx, float v) {
   const __half h = __float2half_rn(v);
   hi[idx] = h;
@@ -157,13 +161,19 @@ void tc_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weig
       }
     }
   }
-  float* par = reinterpret_cast<float*>(base + lay.par);
-  for (int i = 0; i < in_dim; ++i)
-    for (int k = 0; k < 128; ++k) par[TC_PF_W1 + i * 128 + k] = W1[i * 128 + k];
-  for (int k = 0; k < 128; ++k) {
-    par[TC_PF_B1 + k] = b1[k];
-    par[TC_PF_B2 + k] = b2[k];
+  {  // first layer as a [128 x 16] B operand, K-major without swizzle: K = (key_0 .. key_{in-1}, 0.., 1 at k = 8)
+     // so the bias rides in the GEMM.  Unscaled: |W1| and b1 are O(1), and the lo parts of small weights are
+     // fp16 subnormals, which the tensor core takes at full precision of their 2^-24 grid.
+    __half* hi = reinterpret_cast<__half*>(base + lay.w1);
+    __half* lo = reinterpret_cast<__half*>(base + lay.w1 + TC_W1_BYTES / 2);
+    for (int n = 0; n < 128; ++n)
+      for (int k = 0; k < 16; ++k) {
+        const float v = k < in_dim ? W1[k * 128 + n] : (k == 8 ? b1[n] : 0.0f);
+        split_store(hi, lo, w1_index(n, k), v);
+      }
   }
+  float* par = reinterpret_cast<float*>(base + lay.par);
+  for (int k = 0; k < 128; ++k) par[TC_PF_B2 + k] = b2[k];
   for (int d = 0; d < st.L; ++d)
     for (int q = 0; q < st.cpd; ++q) par[TC_PF_B3 + d * TC_DIM_N + q] = b3[d * st.cpd + q];
   par[TC_PF_SCAL + 0] = ldexpf(1.0f, -e2);
@@ -231,6 +241,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
   uint32_t u[16];
   asm volatile(
@@ -261,6 +276,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
   // K-major SWIZZLE_128B operand: start address, SBO = 1024 B (8 rows x 128 B), version 1 (sm100)
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t make_b_desc_w1(uint32_t saddr) {
+  // K-major SWIZZLE_NONE operand: LBO = 128 B between K-adjacent core matrices, SBO = 256 B between 8-row groups
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
 }
 template <bool ACC>
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
@@ -507,22 +526,26 @@ struct TcShared {
   uint64_t d2_full[2][2];  // [group][half]: that N = 64 half of the hidden GEMM has completed (tcgen05.commit)
   uint64_t d3_full[2][2];  // [group][buffer]: an output pass has landed in that accumulator buffer
   uint64_t d3_free[2][2];  // [group][buffer]: the half's 128 threads have drained the buffer
-  uint64_t w2_full, w3_full, par_full[2];  // TMA complete_tx
-  uint64_t w2_free, w3_free;               // both issuers' tcgen05.commit after the stage's last hidden GEMM / pass
+  uint64_t k_ready[2];     // [group] (256 arrivals): the next tile's key operand is written and X is drained
+  uint64_t d1_full[2];     // [group]: the first-layer GEMM has landed in X
+  uint64_t g3_done[2];     // [group]: every output pass of the tile has completed (Y is free again)
+  uint64_t w1_full, w2_full, w3_full, par_full[2];  // TMA complete_tx
+  uint64_t w1_free, w2_free, w3_free;      // both issuers' tcgen05.commit after the stage's last GEMM on that buffer
   uint64_t par_free[2];                    // 512 arrivals: every epilogue thread is done with that parameter buffer
   uint32_t tmem_base;
   uint8_t order[MAX_NSC];  // coupling stages in walk order (index into PlanDev::nsc)
 };
 
 struct TcSmem {  // byte offsets from the 1024-aligned base
-  int w2, w3, par, state, shared, total;
+  int w2, w3, w1, par, state, shared, total;
 };
 
 __host__ __device__ inline TcSmem tc_smem_layout(int max_pass, int chunk_tiles, int state_cols) {
   TcSmem s;
   s.w2 = 0;
   s.w3 = TC_W2_BYTES;
-  s.par = s.w3 + max_pass * TC_W3_PASS_BYTES;
+  s.w1 = s.w3 + max_pass * TC_W3_PASS_BYTES;
+  s.par = s.w1 + TC_W1_BYTES;
   s.state = s.par + 2 * TC_PAR_BYTES;
   s.shared = s.state + chunk_tiles * TC_TILE * state_cols * 4;
   s.shared = (s.shared + 15) / 16 * 16;
@@ -631,9 +654,14 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       }
       mbar_init(TC_BAR(par_full[g]), 1);
       mbar_init(TC_BAR(par_free[g]), TC_EPI_THREADS);
+      mbar_init(TC_BAR(k_ready[g]), TC_GROUP_THREADS);
+      mbar_init(TC_BAR(d1_full[g]), 1);
+      mbar_init(TC_BAR(g3_done[g]), 1);
     }
+    mbar_init(TC_BAR(w1_full), 1);
     mbar_init(TC_BAR(w2_full), 1);
     mbar_init(TC_BAR(w3_full), 1);
+    mbar_init(TC_BAR(w1_free), 2);
     mbar_init(TC_BAR(w2_free), 2);
     mbar_init(TC_BAR(w3_free), 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -669,7 +697,10 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
     const uint32_t bar_d2 = TC_BAR(d2_full[0][0]) + 16u * grp + 8u * half;
     const uint32_t bar_d3 = TC_BAR(d3_full[0][0]) + 16u * grp + 8u * half;
     const uint32_t bar_free = TC_BAR(d3_free[0][0]) + 16u * grp + 8u * half;
-    uint32_t ph_d2 = 0u, ph_d3 = 0u;
+    const uint32_t t_key = tbase + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)grp * 256u + 128u;  // Y[0, 24)
+    const uint32_t bar_key = TC_BAR(k_ready[0]) + 8u * grp, bar_d1 = TC_BAR(d1_full[0]) + 8u * grp;
+    const uint32_t bar_g3 = TC_BAR(g3_done[0]) + 8u * grp;
+    uint32_t ph_d1 = 0u, ph_d2 = 0u, ph_d3 = 0u, ph_g3 = 0u;
     int seq = 0;  // coupling stages processed so far by this CTA (over all its chunks)
 
     // NSC steps in walk order
@@ -737,56 +768,67 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         const float* par = reinterpret_cast<const float*>(base + sl.par + (seq & 1) * TC_PAR_BYTES);
         const int* pint = reinterpret_cast<const int*>(par + TC_PI);
         const int L = pint[TC_PI_L];
+        // The half that evaluates the last spline dimension finishes a tile last; the OTHER half writes the next
+        // tile's key operand once it is through with its own dimensions.
+        const int kw = L & 1;
+
+        // Between two coupling stages: fold the previous stage's log-det halves into their chain level and apply the
+        // non-NSC steps (e.g. an affine inside the chain), for every tile of this group, before any key is read.
+        if (pending || has_light) {
+          for (int q = gtid; q < my_tiles * TC_TILE; q += TC_GROUP_THREADS) {
+            float* st = state + (2 * (q >> 7) + grp) * TC_TILE + (q & (TC_TILE - 1));
+            if (pending) st[(D + pend_level) * CR] += st[COL_PEND * CR] + st[(COL_PEND + 1) * CR];
+            if (has_light) {
+              int lv = level_in;
+              light_steps_cols(plan, INV, light0, si, lv, st, CR);
+            }
+          }
+          if (has_light) named_bar_sync(2 + grp, TC_GROUP_THREADS);
+        }
+
+        // E0: the <= 8 conditioner inputs of a row and a constant 1 (bias row) as a K = 16 fp16 hi/lo A operand in
+        // Y[0,8) / Y[16,24).  One thread per row (half kw) writes it; the tile's first-layer GEMM then runs on the
+        // tensor pipe.  For tile k + 1 this happens while tile k's last spline dimension is still being evaluated.
+        auto write_keys = [&](int kk) {
+          const float* krow = state + (2 * kk + grp) * TC_TILE + lrow;
+          const int in_dim = pint[TC_PI_IN];
+          float key[TC_IN_MAX];
+#pragma unroll
+          for (int i = 0; i < TC_IN_MAX; ++i) key[i] = (i < in_dim) ? krow[pint[TC_PI_KEY + i] * CR] : 0.0f;
+          uint32_t rh[8], rl[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split2(key[2 * j], key[2 * j + 1], rh[j], rl[j]);
+          rh[4] = 0x00003C00u;  // (1.0, 0): k = 8 multiplies the bias row of the W1 tile
+          rl[4] = 0u;
+#pragma unroll
+          for (int j = 5; j < 8; ++j) rh[j] = rl[j] = 0u;
+          tmem_st8(t_key, rh);
+          tmem_st8(t_key + 16u, rl);
+          tc_wait_st();
+        };
+        if (half == kw) write_keys(0);
+        tc_fence_before();
+        mbar_arrive(bar_key);
 
         for (int k = 0; k < my_tiles; ++k) {
           const int r = (2 * k + grp) * TC_TILE + lrow;  // row within the chunk (state is allocated for every tile)
           float* srow = state + r;
 
-          if (pending || has_light) {
-            if (half == 0) {
-              if (pending) srow[(D + pend_level) * CR] += srow[COL_PEND * CR] + srow[(COL_PEND + 1) * CR];
-              if (has_light) {
-                int lv = level_in;
-                light_steps_cols(plan, INV, light0, si, lv, srow, CR);
-              }
-            }
-            if (has_light) named_bar_sync(2 + grp, TC_GROUP_THREADS);
-          }
-
-          // ---- E1: h1 = LeakyReLU(key @ W1 + b1), this half's 64 hidden columns -> fp16 hi/lo in X ----
+          // ---- E1: h1 = LeakyReLU(D1) (bias already in the GEMM), rewritten in place over this half's 64 columns of X ----
           TC_TRACE(0);
-          {
-            const int in_dim = pint[TC_PI_IN];
+          mbar_wait(bar_d1, ph_d1);
+          ph_d1 ^= 1u;
+          tc_fence_after();
 #pragma unroll 1
-            for (int bt = 0; bt < 2; ++bt) {
-              const float* w = par + TC_PF_W1 + half * 64 + bt * 32;
-              float acc[32];
+          for (int bt = 0; bt < 2; ++bt) {
+            float dv[32];
+            tmem_ld32(t_x + bt * 32, dv);
+            tc_wait_ld();
+            uint32_t rh[16], rl[16];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 b4 = *reinterpret_cast<const float4*>(w + (TC_PF_B1 - TC_PF_W1) + q * 4);
-                acc[4 * q + 0] = b4.x;
-                acc[4 * q + 1] = b4.y;
-                acc[4 * q + 2] = b4.z;
-                acc[4 * q + 3] = b4.w;
-              }
-#pragma unroll 1
-              for (int i = 0; i < in_dim; ++i) {
-                const float kv = srow[pint[TC_PI_KEY + i] * CR];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const float4 w4 = *reinterpret_cast<const float4*>(w + i * 128 + q * 4);
-                  acc[4 * q + 0] = fmaf(kv, w4.x, acc[4 * q + 0]);
-                  acc[4 * q + 1] = fmaf(kv, w4.y, acc[4 * q + 1]);
-                  acc[4 * q + 2] = fmaf(kv, w4.z, acc[4 * q + 2]);
-                  acc[4 * q + 3] = fmaf(kv, w4.w, acc[4 * q + 3]);
-                }
-              }
-              uint32_t rh[16], rl[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) split2(pz_leaky(acc[2 * j]), pz_leaky(acc[2 * j + 1]), rh[j], rl[j]);
-              tmem_st16(t_x + bt * 32, rh);
-              tmem_st16(t_x + bt * 32 + 16, rl);
-            }
+            for (int j = 0; j < 16; ++j) split2(pz_leaky(dv[2 * j]), pz_leaky(dv[2 * j + 1]), rh[j], rl[j]);
+            tmem_st16(t_x + bt * 32, rh);
+            tmem_st16(t_x + bt * 32 + 16, rl);
           }
           tc_wait_st();
           tc_fence_before();
@@ -827,6 +869,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           TC_TRACE(3);
 
           // ---- E3: logits -> knots -> spline; this thread takes the dimensions half, half + 2 ----
+          const bool more = k + 1 < my_tiles;
           float ldsum = 0.0f;
 #pragma unroll 1
           for (int d = half; d < L; d += 2) {
@@ -840,6 +883,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             tc_wait_ld();
             tc_fence_before();
             mbar_arrive(bar_free);  // accumulator buffer drained: the next pass may overwrite it
+            if (d + 2 >= L && more && half != kw) mbar_arrive(bar_key);  // my last dimension: X is drained on my side
             const int col = pint[TC_PI_LOW + d];
             const float xin = srow[col * CR];
             float y, ldd;
@@ -853,6 +897,17 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               args.bins[(row0 + r) * plan->n_spline_dims + pint[TC_PI_BINS] + d] = idx;
           }
           srow[(COL_PEND + half) * CR] = INV ? -ldsum : ldsum;
+          if (half == kw) {
+            // every output pass of this tile has completed, so Y is free: write the next tile's key operand
+            mbar_wait(bar_g3, ph_g3);
+            ph_g3 ^= 1u;
+            if (more) {
+              tc_fence_after();
+              write_keys(k + 1);
+              tc_fence_before();
+              mbar_arrive(bar_key);
+            }
+          }
         }
         mbar_arrive(TC_BAR(par_free[0]) + 8u * (seq & 1));
         pending = true;
@@ -905,13 +960,29 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       const uint32_t bar_d2 = TC_BAR(d2_full[0][0]) + 16u * g;
       const uint32_t bar_d3 = TC_BAR(d3_full[0][0]) + 16u * g;
       const uint32_t bar_free = TC_BAR(d3_free[0][0]) + 16u * g;
-      const uint32_t w2 = sb + sl.w2, w3 = sb + sl.w3;
-      uint32_t ph_ready = 0u;
+      const uint32_t w1 = sb + sl.w1, w2 = sb + sl.w2, w3 = sb + sl.w3;
+      const uint32_t idesc1 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t bar_key = TC_BAR(k_ready[0]) + 8u * g, bar_d1 = TC_BAR(d1_full[0]) + 8u * g;
+      uint32_t ph_ready = 0u, ph_key = 0u;
       uint32_t np0 = 0u, np1 = 0u;  // passes issued so far into each accumulator buffer
       for (int s = 0; s < total_seq; ++s) {
         const int L = __shfl_sync(0xffffffffu, stage_of(s).L, 0);
         const int my_tiles = (tiles_of(s) - g + 1) / 2;
         for (int k = 0; k < my_tiles; ++k) {
+          // ---- first layer: keys (Y[0,24), K = 16) x W1 tile -> X, fp32, bias included ----
+          if (k == 0) mbar_wait(TC_BAR(w1_full), (uint32_t)(s & 1));
+          mbar_wait(bar_key, ph_key);
+          ph_key ^= 1u;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t dh = make_b_desc_w1(w1), dl = make_b_desc_w1(w1 + TC_W1_BYTES / 2);
+            umma_f16_ts<false>(t_x, t_y + 16u, dh, idesc1);  // lo * hi
+            umma_f16_ts<true>(t_x, t_y, dl, idesc1);         // hi * lo
+            umma_f16_ts<true>(t_x, t_y, dh, idesc1);         // hi * hi
+            umma_commit(bar_d1);
+            if (k == my_tiles - 1) umma_commit(TC_BAR(w1_free));
+          }
+          __syncwarp();
           // ---- hidden GEMM, two N = 64 halves: X (h1) x W2 -> Y ----
           if (k == 0) mbar_wait(TC_BAR(w2_full), (uint32_t)(s & 1));
           TC_TRACE_I(0);
@@ -959,6 +1030,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             if (elect_one()) {
               issue_gemm<4, 8, false>(t_x + 64u * d, t_y, tile, tile + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idesc3);
               umma_commit(bar_d3 + 8u * d);
+              if (d == L - 1) umma_commit(TC_BAR(g3_done[0]) + 8u * g);
               if (d == L - 1 && k == my_tiles - 1) umma_commit(TC_BAR(w3_free));
             }
             __syncwarp();
@@ -976,6 +1048,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             if (elect_one()) {
               issue_gemm<0, 8, true>(t_x + 64u * b, t_y, tile, tile + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idesc3);
               umma_commit(bar_d3 + 8u * b);
+              if (d == L - 1) umma_commit(TC_BAR(g3_done[0]) + 8u * g);
               if (d == L - 1 && k == my_tiles - 1) umma_commit(TC_BAR(w3_free));
             }
             __syncwarp();
@@ -996,6 +1069,14 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           if (lane == 0) {
             mbar_expect_tx(bar, TC_PAR_BYTES);
             tma_bulk_g2s(sb + sl.par + (s & 1) * TC_PAR_BYTES, src + lay.par, TC_PAR_BYTES, bar);
+          }
+        }
+        {
+          if (s >= 1) mbar_wait(TC_BAR(w1_free), (uint32_t)((s - 1) & 1));
+          const uint32_t bar = TC_BAR(w1_full);
+          if (lane == 0) {
+            mbar_expect_tx(bar, TC_W1_BYTES);
+            tma_bulk_g2s(sb + sl.w1, src + lay.w1, TC_W1_BYTES, bar);
           }
         }
         {
