@@ -285,6 +285,16 @@ def run_ours(args, rank, world, local_rank):
                 "traffic": None, "peak_source": "nominal 148 SM x 128 FFMA/clk x 2 x clocks.max.sm "
                                                 "(the FP32 pipe has no entry in MEASURED_PEAKS.json)"}
     roof["kernel"] = "nsf_chain_tc_kernel" if engine == "tc" else "nsf_chain_simt_kernel"
+    # DRAM traffic of one launch from the committed ncu --set full capture, scaled by rows (the kernel reads each
+    # input row and writes each result once, so traffic is linear in rows); algorithmic bytes: 4 * (D + 1) per row
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)[roof["kernel"]]
+        roof["traffic"] = (t["dram_bytes_read"] + t["dram_bytes_write"]) * n / t["rows_per_launch"]
+        roof["traffic_source"] = t["source"]
+    except (OSError, KeyError, ValueError):
+        roof["traffic"] = None
+    roof["algorithmic_bytes"] = 4.0 * (7 + 1) * n
     roof["flops_per_row"] = flops_row
     roof["kernel_ms"] = kernel_ms
 

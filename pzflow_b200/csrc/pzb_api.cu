@@ -788,9 +788,12 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
 
   int rc = PZB_OK;
   int64_t i = 0;
-  for (int64_t u0 = 0; u0 < job.units && rc == PZB_OK; u0 += chunk, ++i) {
+  // ramp: the first chunks are 1/8, 1/4, 1/2 of the steady-state chunk, so the first kernel starts after a short
+  // copy instead of a full-size one (the un-overlapped head of the pipeline)
+  int64_t cur = std::max<int64_t>(1, chunk / 8);
+  for (int64_t u0 = 0; u0 < job.units && rc == PZB_OK; ++i) {
     const int b = (int)(i % HostPipe::NBUF);
-    const int64_t nu = std::min(chunk, job.units - u0);
+    const int64_t nu = std::min(cur, job.units - u0);
     if (i >= HostPipe::NBUF) cudaStreamWaitEvent(hp.s_in, hp.ev_k[b], 0);  // kernel i-NBUF has read d_in[b]
     if (job.in_w > 0)
       ce = cudaMemcpyAsync(hp.d_in[b], job.in + u0 * job.in_w, (size_t)nu * job.in_w * sizeof(float),
@@ -824,6 +827,8 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
       ce = cudaMemcpyAsync(job.out1 + u0, hp.d_out1[b], (size_t)nu * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out);
     if (ce == cudaSuccess) ce = cudaEventRecord(hp.ev_out[b], hp.s_out);
     if (ce != cudaSuccess) { rc = cuda_fail(ce, "host pipeline D2H"); break; }
+    u0 += nu;
+    cur = std::min(chunk, cur * 2);
   }
   // drain everything, also on the error path: the ring must be idle when the next call starts
   cudaError_t e1 = cudaStreamSynchronize(hp.s_in), e2 = cudaStreamSynchronize(hp.s_k),
