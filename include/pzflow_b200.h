@@ -190,6 +190,41 @@ int pzb_normalize_pdfs(float *pdfs, int64_t Ng, int32_t G, const float *grid,
  * jax.random's threefry stream; sample parity is defined on the map u -> x. */
 int pzb_sample_uniform(float *U, int64_t N, int32_t D, float B, uint64_t seed, void *stream);
 
+/* ---- Gaussian error convolution (err_samples) ---------------------------
+ * Flow.log_prob(inputs, err_samples=S) (pzflow/flow.py:448-464) with the default
+ * gaussian_error_model (pzflow/utils.py:52-61): every row is expanded into S
+ * samples x + eps * x_err (and cond + eps' * cond_err), evaluated, and reduced as
+ * out[i] = log(mean_s exp(lp[i, s])).  The expansion is generated inside the
+ * chain kernel and never stored.  Xerr [N, D] / cond_err [N, C] are the stds
+ * (cond_err in standard-scaled units, i.e. divided by condition_stds); either
+ * may be NULL = zero error (the reference fills missing *_err columns with
+ * zeros, flow.py:366-369).  eps comes from a counter-based Philox stream keyed
+ * by `seed` (not jax.random.normal's threefry: parity is defined given eps, see
+ * pzb_error_eps).  scratch: caller-owned device buffer of N * S floats.
+ * row_offset: index of X's first row in the caller's whole array, so that a
+ * call cut into row chunks draws exactly the eps of one big call. */
+int pzb_log_prob_err(const pzb_plan *plan, const float *X, const float *Xerr, const float *cond,
+                     const float *cond_err, int64_t N, int32_t err_samples, uint64_t seed,
+                     int64_t row_offset, float *out, float *scratch, void *stream);
+
+/* Flow.posterior(..., err_samples=S) main loop (pzflow/flow.py:675-737): the S
+ * samples of every galaxy's other columns (and conditions) are each expanded
+ * over the grid, exp(log_prob) is averaged over the samples (flow.py:722-724),
+ * then normalised like pzb_posterior.  rest_err [Ng, D-1] may be NULL.
+ * scratch: caller-owned device buffer of Ng * S * G floats. */
+int pzb_posterior_err(const pzb_plan *plan, const float *rest, const float *rest_err,
+                      const float *cond, const float *cond_err, int64_t Ng, int32_t col_idx,
+                      const float *grid, int32_t G, int32_t err_samples, uint64_t seed,
+                      int64_t row_offset, int32_t normalize, int32_t nan_to_zero, float *pdfs,
+                      float *scratch, void *stream);
+
+/* The standard normals the two calls above use: eps [n, W] for sample index
+ * es in [0, n) (log_prob: es = row * S + s; posterior: es = galaxy * S + s) and
+ * column j in [0, W); stream_id 0 = data columns (posterior: the D-1 remaining
+ * columns in order), 1 = conditions.  Lets a caller (and the parity tests)
+ * reproduce the expansion exactly. */
+int pzb_error_eps(float *eps, int64_t n, int32_t W, int32_t stream_id, uint64_t seed, void *stream);
+
 /* ---- host-buffer forms --------------------------------------------------
  * The same evaluations for callers whose arrays live in HOST memory, which is
  * where the reference's callers hold them (NumPy arrays cut from a DataFrame,

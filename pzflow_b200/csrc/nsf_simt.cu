@@ -326,28 +326,14 @@ nsf_chain_simt_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, int Lma
     for (int e = tid; e < D * TM; e += NTHREADS) {
       const int r = e / D, j = e % D;
       const long long row = row0 + r;
-      float v = 0.0f;
-      if (row < args.N) {
-        if (args.mode == MODE_POSTERIOR) {
-          const long long g = row / args.G;
-          const int gi = (int)(row - g * args.G);
-          v = (j == args.col_idx) ? args.grid[gi]
-                                  : args.X[g * (D - 1) + (j < args.col_idx ? j : j - 1)];
-        } else {
-          v = args.X[row * D + j];
-        }
-      }
+      const float v = row < args.N ? pz_input_value(args, row, j, D) : 0.0f;
       const int phys = inverse ? plan->perm_final[j] : j;
       Xs[phys * TM + r] = v;
     }
     for (int e = tid; e < C * TM; e += NTHREADS) {
       const int r = e / C, j = e % C;
       const long long row = row0 + r;
-      float v = 0.0f;
-      if (row < args.N && args.cond != nullptr) {
-        const long long crow = (args.mode == MODE_POSTERIOR) ? row / args.G : row;
-        v = args.cond[crow * C + j];
-      }
+      const float v = row < args.N ? pz_cond_value(args, row, j, C) : 0.0f;
       Cs[j * TM + r] = v;
     }
     for (int e = tid; e < MAX_CHAIN_DEPTH * TM; e += NTHREADS) ldacc[e] = 0.0f;

@@ -730,20 +730,9 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         if (r >= nrows) continue;
         const long long row = row0 + r;
         float* st = state + r;
-        for (int j = 0; j < D; ++j) {
-          float v;
-          if (args.mode == MODE_POSTERIOR) {
-            const long long g = row / args.G;
-            const int gi = (int)(row - g * args.G);
-            v = (j == args.col_idx) ? args.grid[gi] : args.X[g * (D - 1) + (j < args.col_idx ? j : j - 1)];
-          } else {
-            v = args.X[row * D + j];
-          }
-          st[(INV ? plan->perm_final[j] : j) * CR] = v;
-        }
+        for (int j = 0; j < D; ++j) st[(INV ? plan->perm_final[j] : j) * CR] = pz_input_value(args, row, j, D);
         for (int l = 0; l < n_lev; ++l) st[(D + l) * CR] = 0.0f;
-        const long long crow = (args.mode == MODE_POSTERIOR) ? row / args.G : row;
-        for (int j = 0; j < C; ++j) st[(COL_COND + j) * CR] = args.cond ? args.cond[crow * C + j] : 0.0f;
+        for (int j = 0; j < C; ++j) st[(COL_COND + j) * CR] = pz_cond_value(args, row, j, C);
         int level = 0;
         light_steps_cols(plan, INV, 0, first_nsc, level, st, CR);
       }

@@ -595,16 +595,6 @@ logmeanexp_kernel(const float* __restrict__ lp, int n_flows, long long N, float*
   }
 }
 
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-  c[0] = n0;
-  c[1] = lo1;
-  c[2] = n2;
-  c[3] = lo0;
-}
-
 __global__ void __launch_bounds__(256)
 sample_uniform_kernel(float* __restrict__ U, long long n, float B, uint64_t seed) {
   const long long nq = (n + 3) / 4;
@@ -614,7 +604,7 @@ sample_uniform_kernel(float* __restrict__ U, long long n, float B, uint64_t seed
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-      philox_round(c, k0, k1);
+      pz_philox_round(c, k0, k1);
       k0 += 0x9E3779B9u;
       k1 += 0xBB67AE85u;
     }
@@ -705,6 +695,127 @@ int pzb_sample_uniform(float* U, int64_t N, int32_t D, float B, uint64_t seed, v
   if (ce != cudaSuccess) return cuda_fail(ce, "sample_uniform launch");
   g_launches.fetch_add(1);
   return PZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gaussian error convolution (pzflow/flow.py:339-395, 448-464, 675-724): err_samples draws per row,
+// generated inside the chain kernel from a counter-based stream, reduced by two small kernels.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+logmeanexp_samples_kernel(const float* __restrict__ lp, long long N, int S, float* __restrict__ out) {
+  // out[i] = log(mean_s exp(lp[i, s])), the naive form of pzflow/flow.py:463-464
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N;
+       i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int k = 0; k < S; ++k) s += expf(lp[(size_t)i * S + k]);
+    out[i] = logf(s / (float)S);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mean_samples_kernel(const float* __restrict__ p, long long Ng, int S, int G, float* __restrict__ out) {
+  // out[g, i] = mean_s p[g, s, i] (pzflow/flow.py:722-724)
+  const long long n = Ng * (long long)G;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long g = e / G;
+    const int i = (int)(e - g * G);
+    float s = 0.0f;
+    for (int k = 0; k < S; ++k) s += p[((size_t)g * S + k) * G + i];
+    out[e] = s / (float)S;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+error_eps_kernel(float* __restrict__ eps, long long n, int W, uint32_t stream_id, unsigned long long seed) {
+  const long long total = n * (long long)W;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long es = e / W;
+    eps[e] = pz_err_normal(seed, stream_id, (unsigned long long)es, (int)(e - es * W));
+  }
+}
+
+static unsigned grid_for(long long n) {
+  long long b = (n + 255) / 256;
+  if (b > 148 * 32) b = 148 * 32;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+int pzb_error_eps(float* eps, int64_t n, int32_t W, int32_t stream_id, uint64_t seed, void* stream) {
+  if (n < 0 || W < 1 || (stream_id != 0 && stream_id != 1)) return fail(PZB_ERR_INVALID, "error_eps: bad arguments");
+  if (n == 0) return PZB_OK;
+  if (!eps) return fail(PZB_ERR_INVALID, "error_eps: NULL buffer");
+  error_eps_kernel<<<grid_for(n * W), 256, 0, (cudaStream_t)stream>>>(eps, n, W, (uint32_t)stream_id, seed);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "error_eps launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+int pzb_log_prob_err(const pzb_plan* plan, const float* X, const float* Xerr, const float* cond,
+                     const float* cond_err, int64_t N, int32_t err_samples, uint64_t seed, int64_t row_offset,
+                     float* out, float* scratch, void* stream) {
+  int rc = check_common(plan, X, cond, N, out, "log_prob_err");
+  if (rc) return rc;
+  if (err_samples < 1) return fail(PZB_ERR_INVALID, "log_prob_err: err_samples must be positive");
+  if (N > 0 && scratch == nullptr) return fail(PZB_ERR_INVALID, "log_prob_err: scratch [N * err_samples] is NULL");
+  if (N == 0) return PZB_OK;
+  LaunchArgs a{};
+  a.mode = MODE_LOGPROB;
+  a.X = X;
+  a.Xerr = Xerr;
+  a.cond = cond;
+  a.cond_err = plan->host.C > 0 ? cond_err : nullptr;
+  a.S = err_samples;
+  a.seed = seed;
+  a.unit0 = row_offset;
+  a.N = N * (int64_t)err_samples;
+  a.out0 = scratch;
+  rc = launch_chain(plan, a, stream);
+  if (rc) return rc;
+  DeviceGuard guard(plan->device);
+  logmeanexp_samples_kernel<<<grid_for(N), 256, 0, (cudaStream_t)stream>>>(scratch, N, err_samples, out);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "logmeanexp_samples launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+int pzb_posterior_err(const pzb_plan* plan, const float* rest, const float* rest_err, const float* cond,
+                      const float* cond_err, int64_t Ng, int32_t col_idx, const float* grid, int32_t G,
+                      int32_t err_samples, uint64_t seed, int64_t row_offset, int32_t normalize, int32_t nan_to_zero,
+                      float* pdfs, float* scratch, void* stream) {
+  int rc = check_common(plan, plan && plan->host.D > 1 ? (const void*)rest : (const void*)grid, cond, Ng, pdfs,
+                        "posterior_err");
+  if (rc) return rc;
+  if (G < 1 || grid == nullptr) return fail(PZB_ERR_INVALID, "posterior_err: empty grid");
+  if (col_idx < 0 || col_idx >= plan->host.D)
+    return fail(PZB_ERR_INVALID, "posterior_err: column index %d out of range", col_idx);
+  if (err_samples < 1) return fail(PZB_ERR_INVALID, "posterior_err: err_samples must be positive");
+  if (Ng > 0 && scratch == nullptr) return fail(PZB_ERR_INVALID, "posterior_err: scratch [Ng * err_samples * G] is NULL");
+  if (Ng == 0) return PZB_OK;
+  LaunchArgs a{};
+  a.mode = MODE_POSTERIOR;
+  a.X = rest;
+  a.Xerr = plan->host.D > 1 ? rest_err : nullptr;
+  a.cond = cond;
+  a.cond_err = plan->host.C > 0 ? cond_err : nullptr;
+  a.grid = grid;
+  a.G = G;
+  a.col_idx = col_idx;
+  a.S = err_samples;
+  a.seed = seed;
+  a.unit0 = row_offset;
+  a.N = Ng * (int64_t)err_samples * (int64_t)G;
+  a.out0 = scratch;
+  rc = launch_chain(plan, a, stream);
+  if (rc) return rc;
+  DeviceGuard guard(plan->device);
+  mean_samples_kernel<<<grid_for(Ng * (long long)G), 256, 0, (cudaStream_t)stream>>>(scratch, Ng, err_samples, G, pdfs);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "mean_samples launch");
+  g_launches.fetch_add(1);
+  return pzb_normalize_pdfs(pdfs, Ng, G, grid, normalize, nan_to_zero, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

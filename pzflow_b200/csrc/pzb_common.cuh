@@ -39,7 +39,7 @@ struct DenseDev {
 // Extra packing for the tcgen05 engine (H = 128 conditioners): fp16 hi/lo
 // split weights in the UMMA canonical K-major SWIZZLE_128B layout.
 struct TcLayerDev {
-  const void* blob;   // [W2 hi | W2 lo | W3 hi | W3 lo | W1 | b1 | b2 | b3] for one NSC stage
+  const void* blob;   // [W2 hi | W2 lo | W3 hi | W3 lo | W1 hi | W1 lo | par] for one NSC stage (nsf_tc.cu)
   int blob_bytes;
 };
 
@@ -83,7 +83,83 @@ struct LaunchArgs {
   float* out0;        // lp[N] | U[N,D] | X[N,D] | pdfs[Ng*G]
   float* out1;        // log_det[N] (FORWARD/INVERSE, may be null)
   int32_t* bins;      // optional [N, n_spline_dims]
+  // Gaussian error convolution (pzflow/flow.py:339-395, pzflow/utils.py:52-61), S = err_samples > 0:
+  // every unit (row / galaxy) is expanded into S samples x + eps * x_err generated here, never stored.
+  // N then counts the EXPANDED rows: LOGPROB units*S (sample-minor), POSTERIOR units*S*G (grid-minor).
+  const float* Xerr;      // same shape as X (stds), or nullptr (no data errors)
+  const float* cond_err;  // [units, C] stds in standard-scaled condition units, or nullptr
+  int S;
+  unsigned long long seed;
+  long long unit0;        // index of X's first row in the caller's whole array: chunked calls draw the same eps
 };
+
+// ---- counter-based normals for the error samples: Philox-4x32-10 keyed by the seed, counter =
+// (sample index, 4-column block, stream: 0 data / 1 conditions), Box-Muller on the four words ----
+__device__ __forceinline__ void pz_philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0;
+  c[1] = lo1;
+  c[2] = n2;
+  c[3] = lo0;
+}
+
+__device__ __forceinline__ void pz_philox4(unsigned long long seed, unsigned long long ctr, uint32_t block,
+                                           uint32_t stream, uint32_t (&c)[4]) {
+  c[0] = (uint32_t)ctr;
+  c[1] = (uint32_t)(ctr >> 32);
+  c[2] = block;
+  c[3] = stream;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    pz_philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+// eps for (sample index es, column j) of a stream: standard normal, float32
+__device__ __forceinline__ float pz_err_normal(unsigned long long seed, uint32_t stream, unsigned long long es, int j) {
+  uint32_t c[4];
+  pz_philox4(seed, es, (uint32_t)(j >> 2), stream, c);
+  const int pair = (j >> 1) & 1;
+  // u1 in (0, 1], u2 in [0, 1): 24 random bits each
+  const float u1 = ((float)(c[2 * pair] >> 8) + 1.0f) * 5.9604644775390625e-8f;
+  const float u2 = (float)(c[2 * pair + 1] >> 8) * 5.9604644775390625e-8f;
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return (j & 1) ? r * sn : r * cs;
+}
+
+// Value of data column j (logical order) and of condition j for evaluation row `row`: the posterior's grid
+// expansion (pzflow/flow.py:697-714) and the Gaussian error samples are generated here.
+__device__ __forceinline__ float pz_input_value(const LaunchArgs& a, long long row, int j, int D) {
+  const long long es = (a.mode == MODE_POSTERIOR) ? row / a.G : row;  // sample index
+  const long long unit = a.S > 0 ? es / a.S : es;                       // row of X
+  int jj = j, W = D;
+  if (a.mode == MODE_POSTERIOR) {
+    if (j == a.col_idx) return a.grid[(int)(row - es * a.G)];
+    jj = j < a.col_idx ? j : j - 1;
+    W = D - 1;
+  }
+  float v = a.X[unit * W + jj];
+  if (a.S > 0 && a.Xerr != nullptr)
+    v = v + pz_err_normal(a.seed, 0u, (unsigned long long)(es + a.unit0 * a.S), jj) * a.Xerr[unit * W + jj];
+  return v;
+}
+
+__device__ __forceinline__ float pz_cond_value(const LaunchArgs& a, long long row, int j, int C) {
+  if (a.cond == nullptr) return 0.0f;
+  const long long es = (a.mode == MODE_POSTERIOR) ? row / a.G : row;
+  const long long unit = a.S > 0 ? es / a.S : es;
+  float v = a.cond[unit * C + j];
+  if (a.S > 0 && a.cond_err != nullptr)
+    v = v + pz_err_normal(a.seed, 1u, (unsigned long long)(es + a.unit0 * a.S), j) * a.cond_err[unit * C + j];
+  return v;
+}
 
 // ---- small numerics shared by both engines (reference op order, no FMA contraction:
 // the files are compiled with -fmad=false and GEMM loops call fmaf explicitly) ----

@@ -7,8 +7,9 @@ the reference (pzflow/flow.py:49-251, 819-866); ``log_prob`` (409-464),
 kernel per call via the C-ABI (``pzflow_b200.plan.Plan``).  There is no CPU
 path: without a CUDA device every evaluation raises.
 
-Out of scope here: ``train`` and Gaussian error convolution
-(``err_samples``) raise NotImplementedError.
+``err_samples`` (Gaussian error convolution, flow.py:339-395) is fused too: the samples are
+drawn inside the kernel from a counter-based stream.  Out of scope here:
+``train`` raises NotImplementedError.
 """
 from __future__ import annotations
 
@@ -212,8 +213,41 @@ class Flow:
             return self._log_prob(self._params, X, conditions).cpu().numpy()
         assert isinstance(err_samples, int), "err_samples must be a positive integer."
         assert err_samples > 0, "err_samples must be a positive integer."
-        raise NotImplementedError("err_samples (Gaussian error convolution) is a next-round row "
-                                  "of the B200 hot path (SURVEY.md §8f-1)")
+        # Gaussian samples (pzflow/flow.py:455-464): drawn inside the kernel, reduced as log(mean(exp))
+        seed = np.random.randint(1e18) if seed is None else seed
+        X, Xerr = self._get_err_arrays(inputs, "data")
+        C, Cerr = self._get_err_arrays(inputs, "conditions")
+        return self._plan().log_prob_err(X, Xerr, C, Cerr, err_samples, seed).cpu().numpy()
+
+    def _get_err_arrays(self, inputs: pd.DataFrame, type: str = "data", skip: str = None):
+        """Means and stds of the error samples for each row (pzflow/flow.py:339-395).  The reference draws
+        the samples here; the fused kernels draw them on the fly, so this returns (X, Xerr) float32 with
+        zeros for missing ``*_err`` columns (flow.py:366-369), the ``skip`` column removed (381-384) and
+        conditions standard-scaled (386-392: (c + eps*e - mean)/std == (c - mean)/std + eps * e/std)."""
+        if type == "data":
+            columns = [c for c in self.data_columns if c != skip]
+            model = self.data_error_model
+        elif type == "conditions":
+            if self.conditional_columns is None:
+                return None, None
+            columns = list(self.conditional_columns)
+            model = self.condition_error_model
+        else:
+            raise ValueError("type must be `data` or `conditions`.")
+        if model is not None and model is not gaussian_error_model:
+            raise NotImplementedError("only the default gaussian_error_model is fused into the B200 kernels; "
+                                      "custom error models need the reference's JAX path")
+        X = inputs[columns].to_numpy().astype(np.float32).reshape(len(inputs), len(columns))
+        Xerr = np.zeros_like(X)
+        for i, col in enumerate(columns):
+            if f"{col}_err" in inputs.columns:
+                Xerr[:, i] = inputs[f"{col}_err"].to_numpy().astype(np.float32)
+        if type == "conditions":
+            means = np.asarray(self._condition_means, dtype=np.float32)
+            stds = np.asarray(self._condition_stds, dtype=np.float32)
+            X = (X - means) / stds
+            Xerr = Xerr / stds
+        return X, Xerr
 
     def posterior(self, inputs: pd.DataFrame, column: str, grid, marg_rules: dict = None,
                   normalize: bool = True, err_samples: int = None, seed: int = None,
@@ -231,13 +265,26 @@ class Flow:
         if err_samples is not None:
             assert isinstance(err_samples, int), "err_samples must be a positive integer."
             assert err_samples > 0, "err_samples must be a positive integer."
-            raise NotImplementedError("err_samples (Gaussian error convolution) is a next-round row "
-                                      "of the B200 hot path (SURVEY.md §8f-1)")
+            seed = np.random.randint(1e18) if seed is None else seed
         grid = np.asarray(grid, dtype=np.float32).reshape(-1)
 
         if marg_rules is not None:
             return self._posterior_marginalized(inputs, column, columns, grid, marg_rules, normalize,
-                                                batch_size, nan_to_zero)
+                                                batch_size, nan_to_zero, err_samples, seed)
+
+        if err_samples is not None:
+            # flow.py:675-693, 722-724: samples of the other columns / conditions, each expanded over the grid,
+            # probabilities averaged over the samples -- all inside the kernel
+            plan = self._plan()
+            C, Cerr = self._get_err_arrays(inputs, "conditions")
+            if len(self.data_columns) == 1:
+                rest = np.zeros((nrows, 0), dtype=np.float32)
+                rest_err = None
+            else:
+                rest, rest_err = self._get_err_arrays(inputs, "data", skip=column)
+            pdfs = plan.posterior_err(rest, rest_err, idx, grid, C, Cerr, err_samples, seed,
+                                      normalize=normalize, nan_to_zero=nan_to_zero)
+            return pdfs.cpu().numpy()
 
         # The reference loops over batch_size rows because it materialises [batch * G, D]
         # (pzflow/flow.py:697-730) and normalises once at the end (732-737).  Here the expansion is
@@ -251,7 +298,7 @@ class Flow:
         return pdfs.numpy()
 
     def _posterior_marginalized(self, inputs, column, columns, grid, marg_rules, normalize, batch_size,
-                                nan_to_zero):
+                                nan_to_zero, err_samples=None, seed=None):
         """Host orchestration of pzflow/flow.py:560-664 over the fused posterior."""
         nrows = inputs.shape[0]
         pdfs = np.zeros((nrows, len(grid)), dtype=np.float32)
@@ -264,6 +311,7 @@ class Flow:
         unflagged_idx = inputs[~check_flags(inputs[columns]).any(axis=1)].index.tolist()
         if len(unflagged_idx):
             pdfs[unflagged_idx, :] = self.posterior(inputs=inputs.iloc[unflagged_idx], column=column, grid=grid,
+                                                    err_samples=err_samples, seed=seed,
                                                     batch_size=batch_size, normalize=False,
                                                     nan_to_zero=nan_to_zero)
         already_done = list(unflagged_idx)
@@ -280,6 +328,7 @@ class Flow:
             marg_inputs[name] = marg_grids.reshape(marg_inputs.shape[0], 1)
             marg_inputs.drop(f"{name}_err", axis=1, inplace=True, errors="ignore")
             marg_pdfs = self.posterior(inputs=marg_inputs, column=column, grid=grid, marg_rules=marg_rules,
+                                       err_samples=err_samples, seed=seed,
                                        batch_size=batch_size, normalize=False, nan_to_zero=nan_to_zero)
             marg_pdfs = marg_pdfs.reshape(len(flagged_idx), marg_grids.shape[1], grid.size).sum(axis=1)
             pdfs[flagged_idx, :] = marg_pdfs

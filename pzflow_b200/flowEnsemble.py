@@ -79,9 +79,14 @@ class FlowEnsemble:
     def log_prob(self, inputs: pd.DataFrame, err_samples: int = None, seed: int = None,
                  returnEnsemble: bool = False) -> np.ndarray:
         """log probability density, [N] or [N, n_flows] (pzflow/flowEnsemble.py:189-243)."""
-        if err_samples is not None:
-            raise NotImplementedError("err_samples is a next-round row of the B200 hot path (SURVEY.md §8f-1)")
         flows = list(self._ensemble.values())
+        if err_samples is not None:
+            # every flow averages over its own error samples, then the ensemble rule (flowEnsemble.py:227-243)
+            lps = np.stack([flow.log_prob(inputs, err_samples=err_samples, seed=seed) for flow in flows], axis=1)
+            if returnEnsemble:
+                return lps
+            with np.errstate(divide="ignore"):
+                return np.log(np.exp(lps).mean(axis=1, dtype=np.float32))
         columns = list(flows[0].data_columns)
         X = None
         lps = []

@@ -237,6 +237,64 @@ class Plan:
                                            int(bool(nan_to_zero)), _ptr(out)))
         return out
 
+    # ---- Gaussian error convolution (err_samples), device tensors -------
+    ERR_SCRATCH_FLOATS = 1 << 26  # expanded rows evaluated per launch (256 MB of scratch at most)
+
+    def _dev_opt(self, a, shape, what):
+        if a is None:
+            return None
+        t = torch.as_tensor(a) if not isinstance(a, torch.Tensor) else a
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{what} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def log_prob_err(self, X, Xerr, cond=None, cond_err=None, err_samples: int = 1, seed: int = 0) -> torch.Tensor:
+        """Flow.log_prob(err_samples=S) for arrays (pzflow/flow.py:448-464): log(mean_s exp(lp(x + eps x_err)))
+        with the Gaussian expansion generated inside the kernel.  cond / cond_err are standard-scaled."""
+        X = self._rows(X, self.input_dim, "inputs")
+        n = X.shape[0]
+        Xerr = self._dev_opt(Xerr, X.shape, "input errors")
+        cond = self._cond(cond, n)
+        cond_err = self._dev_opt(cond_err, (n, self.n_conditions), "condition errors") if cond is not None else None
+        S = int(err_samples)
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        step = max(1, self.ERR_SCRATCH_FLOATS // S)
+        scratch = torch.empty(min(n, step) * S, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            for r0 in range(0, n, step):
+                m = min(step, n - r0)
+                N.check(N.lib().pzb_log_prob_err(
+                    self._h, _ptr(X[r0:r0 + m]), _ptr(Xerr[r0:r0 + m]) if Xerr is not None else None,
+                    _ptr(cond[r0:r0 + m]) if cond is not None else None,
+                    _ptr(cond_err[r0:r0 + m]) if cond_err is not None else None, m, S,
+                    int(seed) & (2 ** 64 - 1), r0, _ptr(out[r0:r0 + m]), _ptr(scratch), _stream(self.device)))
+        return out
+
+    def posterior_err(self, rest, rest_err, col_idx: int, grid, cond=None, cond_err=None, err_samples: int = 1,
+                      seed: int = 0, normalize: bool = True, nan_to_zero: bool = True) -> torch.Tensor:
+        """Flow.posterior(err_samples=S) main loop (pzflow/flow.py:675-737) -> pdfs [Ng, G] on the device."""
+        rest = self._rows(rest, self.input_dim - 1, "inputs")
+        Ng = rest.shape[0]
+        rest_err = self._dev_opt(rest_err, rest.shape, "input errors")
+        cond = self._cond(cond, Ng)
+        cond_err = self._dev_opt(cond_err, (Ng, self.n_conditions), "condition errors") if cond is not None else None
+        grid = torch.as_tensor(grid).to(device=self.device, dtype=torch.float32).contiguous().reshape(-1)
+        G, S = grid.numel(), int(err_samples)
+        out = torch.empty((Ng, G), dtype=torch.float32, device=self.device)
+        step = max(1, self.ERR_SCRATCH_FLOATS // (S * G))
+        scratch = torch.empty(min(Ng, step) * S * G, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            for r0 in range(0, Ng, step):
+                m = min(step, Ng - r0)
+                N.check(N.lib().pzb_posterior_err(
+                    self._h, _ptr(rest[r0:r0 + m]) if rest.numel() else None,
+                    _ptr(rest_err[r0:r0 + m]) if rest_err is not None and rest_err.numel() else None,
+                    _ptr(cond[r0:r0 + m]) if cond is not None else None,
+                    _ptr(cond_err[r0:r0 + m]) if cond_err is not None else None, m, int(col_idx), _ptr(grid), G, S,
+                    int(seed) & (2 ** 64 - 1), r0, int(bool(normalize)), int(bool(nan_to_zero)),
+                    _ptr(out[r0:r0 + m]), _ptr(scratch), _stream(self.device)))
+        return out
+
     # ---- entry points (all asynchronous on torch's current stream) -------
     def log_prob(self, X, cond=None, return_bins: bool = False):
         """Flow._log_prob (pzflow/flow.py:397-407).  Device tensors are evaluated in place on torch's
@@ -344,6 +402,15 @@ def sample_uniform(n: int, dim: int, B: float, seed: int, device=None) -> torch.
 def pinned_empty(shape, dtype=torch.float32) -> torch.Tensor:
     """Page-locked CPU tensor (torch's caching host allocator): D2H/H2D copies at PCIe speed."""
     return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+def error_eps(n: int, width: int, stream_id: int, seed: int, device=None) -> torch.Tensor:
+    """The standard normals pzb_log_prob_err / pzb_posterior_err draw: eps [n, width] (stream 0 data, 1 conditions)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((n, width), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        N.check(N.lib().pzb_error_eps(_ptr(out), n, width, stream_id, int(seed) & (2 ** 64 - 1), _stream(device)))
+    return out
 
 
 def launch_count() -> int:

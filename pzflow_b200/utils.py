@@ -16,6 +16,17 @@ def build_bijector_from_info(info: tuple) -> tuple:
 
 
 def gaussian_error_model(key, X, Xerr, nsamples):
-    """Placeholder so pickles that reference pzflow.utils.gaussian_error_model load;
-    error convolution (pzflow/utils.py:52-61) is a "next" row."""
-    raise NotImplementedError("err_samples / Gaussian error convolution is not part of the B200 hot path yet")
+    """Default Gaussian error model (pzflow/utils.py:52-61): X[:, None, :] + eps * Xerr[:, None, :],
+    eps ~ N(0, 1) of shape [N, nsamples, D].  ``key`` is the integer seed here (the reference passes a
+    jax PRNGKey); the draws are the library's counter-based stream (pzflow_b200.plan.error_eps), the same
+    ones the fused kernels generate on the fly -- Flow.log_prob / posterior never call this function, they
+    only check that the flow's error model IS this one and let the kernel do the expansion."""
+    import numpy as np
+    import torch
+
+    from .plan import error_eps
+    X = np.asarray(X, dtype=np.float32)
+    Xerr = np.asarray(Xerr, dtype=np.float32)
+    eps = error_eps(X.shape[0] * int(nsamples), X.shape[1], 0, int(key)).cpu().numpy()
+    eps = eps.reshape(X.shape[0], int(nsamples), X.shape[1])
+    return X[:, None, :] + eps * Xerr[:, None, :]

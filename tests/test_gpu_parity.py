@@ -515,3 +515,117 @@ def test_flow_api_host_arrays_take_the_pipeline():
     want = flow._plan().posterior(torch.from_numpy(np.ascontiguousarray(X[:300, 1:])).cuda(), 0,
                                   torch.from_numpy(grid.astype(np.float32)))
     np.testing.assert_array_equal(pdfs, _np(want))
+
+
+# --------------------------------------------------------------------------- #
+# Gaussian error convolution (err_samples), SURVEY.md §8f-1                    #
+# --------------------------------------------------------------------------- #
+def _expand(X, Xerr, eps, S):
+    """gaussian_error_model (pzflow/utils.py:52-61) given eps [N*S, W] -> rows [N*S, W], float32."""
+    n, w = X.shape
+    return (X[:, None, :] + eps.reshape(n, S, w) * Xerr[:, None, :]).reshape(n * S, w).astype(np.float32)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_err_samples_log_prob_matches_oracle(engine):
+    from pzflow_b200.plan import error_eps
+    ex = F.example_flow()
+    plan = _plan(ex, engine)
+    rng = np.random.default_rng(3)
+    n, S, seed = 1500, 16, 12345
+    X = F.galaxy_rows(n, seed=21, oob_frac=0)
+    Xerr = (rng.uniform(0.0, 0.05, size=X.shape) * (rng.random(X.shape) > 0.3)).astype(np.float32)
+    eps = _np(error_eps(n * S, 7, 0, seed))
+    assert abs(eps.mean()) < 0.01 and abs(eps.std() - 1.0) < 0.01 and abs((eps ** 3).mean()) < 0.03
+    rows = _expand(X, Xerr, eps, S)
+    bi, li, p64 = _o64(ex)
+    with np.errstate(all="ignore"):
+        lp32 = O.flow_log_prob(ex["bijector_info"], ex["latent_info"], ex["params"], rows)
+        lp64 = O.flow_log_prob(bi, li, p64, rows.astype(np.float64))
+        o32 = np.log(np.exp(lp32.reshape(n, S)).mean(axis=1, dtype=np.float32))
+        o64 = np.log(np.exp(lp64.reshape(n, S)).mean(axis=1))
+    got = _np(plan.log_prob_err(X, Xerr, None, None, S, seed))
+    assert_noise_floor(f"C2 log_prob err_samples [{engine}]", got, o32, o64, ratio=2.0, slack=5e-6, below=LP_UNDERFLOW)
+    # the expansion is generated per expanded row: cutting the rows into launches cannot change it
+    plan.ERR_SCRATCH_FLOATS = 4096
+    try:
+        assert _same_bits(plan.log_prob_err(X, Xerr, None, None, S, seed), torch.from_numpy(got))
+    finally:
+        del plan.ERR_SCRATCH_FLOATS
+    # zero errors == plain log_prob (tests/test_flow.py:236-239 of the reference)
+    plain = _np(plan.log_prob(torch.from_numpy(X).cuda()))
+    zero = _np(plan.log_prob_err(X, None, None, None, 4, seed))
+    fin = plain > LP_UNDERFLOW
+    np.testing.assert_allclose(zero[fin], plain[fin], rtol=1e-5, atol=1e-5)
+    assert not np.array_equal(got, _np(plan.log_prob_err(X, Xerr, None, None, S, seed + 1)))
+
+
+def test_err_samples_posterior_and_conditions():
+    from pzflow_b200.plan import error_eps
+    ex = F.example_flow()
+    plan = _plan(ex, "tc")
+    rng = np.random.default_rng(4)
+    ng, S, G, seed = 40, 8, 50, 7
+    X = F.galaxy_rows(ng, seed=22, oob_frac=0)
+    rest = np.ascontiguousarray(X[:, 1:])
+    rest_err = rng.uniform(0.0, 0.05, size=rest.shape).astype(np.float32)
+    grid = np.linspace(0.0, 2.3, G).astype(np.float32)
+    eps = _np(error_eps(ng * S, 6, 0, seed))
+    samples = _expand(rest, rest_err, eps, S)                      # [ng*S, 6]
+    un = O.flow_posterior(ex["bijector_info"], ex["latent_info"], ex["params"], samples, 0, grid, normalize=False,
+                          nan_to_zero=False)                       # [ng*S, G]
+    want = un.reshape(ng, S, G).mean(axis=1)
+    want = want / O.trapezoid(want, grid)[:, None]
+    got = _np(plan.posterior_err(rest, rest_err, 0, grid, None, None, S, seed))
+    np.testing.assert_allclose(got, want, rtol=2e-3, atol=2e-4)
+    # zero errors == plain posterior (tests/test_flow.py:260-264: rtol 1e-4)
+    plain = _np(plan.posterior(torch.from_numpy(rest).cuda(), 0, torch.from_numpy(grid)))
+    zero = _np(plan.posterior_err(rest, None, 0, grid, None, None, 3, seed))
+    np.testing.assert_allclose(zero, plain, rtol=1e-4, atol=1e-6)
+    # conditional flow: condition errors ride stream 1
+    cfg = F.config_c4(1)[0]
+    cplan = _plan(cfg, "tc")
+    mins, maxs = ex["bijector_info"][1][0][1][0], ex["bijector_info"][1][0][1][1]
+    n, S2 = 600, 5
+    Xc = rng.uniform(mins, maxs, size=(n, 7)).astype(np.float32)
+    cond = rng.normal(size=(n, 2)).astype(np.float32)
+    cerr = rng.uniform(0, 0.1, size=(n, 2)).astype(np.float32)
+    xerr = rng.uniform(0, 0.02, size=(n, 7)).astype(np.float32)
+    rows = _expand(Xc, xerr, _np(error_eps(n * S2, 7, 0, seed)), S2)
+    crow = _expand(cond, cerr, _np(error_eps(n * S2, 2, 1, seed)), S2)
+    with np.errstate(all="ignore"):
+        lp = O.flow_log_prob(cfg["bijector_info"], cfg["latent_info"], cfg["params"], rows, crow)
+        want = np.log(np.exp(lp.reshape(n, S2)).mean(axis=1, dtype=np.float32))
+    got = _np(cplan.log_prob_err(Xc, xerr, cond, cerr, S2, seed))
+    ok = want > LP_UNDERFLOW
+    assert within_tol(got[ok], want[ok]).mean() > 0.98
+
+
+def test_err_samples_through_flow_api():
+    """DataFrame API: *_err columns, missing ones are zero (flow.py:366-369); ensemble rule on top."""
+    from pzflow_b200 import Flow, FlowEnsemble
+    ex = F.example_flow()
+    d = {"class": "Flow", "data_columns": F.GALAXY_COLUMNS, "conditional_columns": None,
+         "condition_means": None, "condition_stds": None, "data_error_model": None,
+         "condition_error_model": None, "autoscale_conditions": True, "info": None,
+         "latent_info": ex["latent_info"], "bijector_info": ex["bijector_info"], "params": ex["params"]}
+    flow = Flow(_dictionary=d)
+    X = F.galaxy_rows(300, seed=23, oob_frac=0)
+    df = pd.DataFrame(X.astype(np.float64), columns=F.GALAXY_COLUMNS)
+    df["u_err"] = 0.03
+    df["redshift_err"] = 0.01
+    lp = flow.log_prob(df, err_samples=10, seed=5)
+    assert lp.shape == (300,) and np.isfinite(lp).mean() > 0.9
+    np.testing.assert_array_equal(lp, flow.log_prob(df, err_samples=10, seed=5))   # seed reproducibility
+    Xerr = np.zeros_like(X)
+    Xerr[:, 0], Xerr[:, 1] = 0.01, 0.03
+    np.testing.assert_array_equal(lp, _np(flow._plan().log_prob_err(X, Xerr, None, None, 10, 5)))
+    grid = np.linspace(0, 2.3, 40)
+    pdfs = flow.posterior(df[:50], column="redshift", grid=grid, err_samples=6, seed=5)
+    assert pdfs.shape == (50, 40)
+    np.testing.assert_allclose(np.trapezoid(pdfs, grid, axis=1), 1.0, rtol=1e-4)
+    with pytest.raises(AssertionError):
+        flow.log_prob(df, err_samples=0)
+    flow2 = Flow(_dictionary=dict(d, data_error_model=lambda key, X, Xerr, n: None))
+    with pytest.raises(NotImplementedError):
+        flow2.log_prob(df, err_samples=2)

@@ -194,3 +194,37 @@ def test_two_rank_sharded_eval_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_err_sample_arrays_follow_the_reference_rules():
+    """Flow._get_err_arrays mirrors pzflow/flow.py:339-395: zeros for missing *_err columns, the
+    skipped column removed, conditions (and their errors) standard-scaled."""
+    import pandas as pd
+    from pzflow_b200 import Flow
+    from pzflow_b200.bijectors import Chain, RollingSplineCoupling, ShiftBounds
+    flow = Flow(data_columns=("x", "y", "z"), conditional_columns=("a", "b"),
+                bijector=Chain(ShiftBounds(np.zeros(3), np.ones(3), 4.0), RollingSplineCoupling(3, n_conditions=2)))
+    flow._condition_means = np.array([1.0, -2.0], dtype=np.float32)
+    flow._condition_stds = np.array([2.0, 0.5], dtype=np.float32)
+    rng = np.random.default_rng(0)
+    df = pd.DataFrame(rng.random((5, 5)), columns=["x", "y", "z", "a", "b"])
+    df["y_err"] = 0.1
+    df["b_err"] = 0.2
+    X, Xerr = flow._get_err_arrays(df, "data")
+    assert X.dtype == np.float32 and X.shape == (5, 3)
+    np.testing.assert_allclose(X, df[["x", "y", "z"]].to_numpy(), rtol=1e-6)
+    np.testing.assert_allclose(Xerr, np.array([[0.0, 0.1, 0.0]] * 5), rtol=1e-6)
+    Xs, Xserr = flow._get_err_arrays(df, "data", skip="y")
+    assert Xs.shape == (5, 2) and np.all(Xserr == 0.0)
+    np.testing.assert_allclose(Xs, df[["x", "z"]].to_numpy(), rtol=1e-6)
+    C, Cerr = flow._get_err_arrays(df, "conditions")
+    np.testing.assert_allclose(C, (df[["a", "b"]].to_numpy() - [1.0, -2.0]) / [2.0, 0.5], rtol=1e-5)
+    np.testing.assert_allclose(Cerr, np.array([[0.0, 0.4]] * 5), rtol=1e-6)
+    with pytest.raises(ValueError):
+        flow._get_err_arrays(df, "other")
+    uncond = Flow(data_columns=("x", "y"), bijector=Chain(ShiftBounds(np.zeros(2), np.ones(2), 4.0),
+                                                           RollingSplineCoupling(2)))
+    assert uncond._get_err_arrays(df, "conditions") == (None, None)
+    uncond.data_error_model = lambda key, X, Xerr, n: X
+    with pytest.raises(NotImplementedError):
+        uncond._get_err_arrays(df, "data")
