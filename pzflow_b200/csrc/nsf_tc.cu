@@ -529,7 +529,7 @@ __device__ __forceinline__ void spline_dim(const float (&raw)[48], const float* 
 struct TcShared {
   uint64_t e_ready[2][2];  // [group][half] -> the group's MMA issuer (4 warp arrivals): that half's 64 K-elements of the
                            // A operand are written (after E1 and after E2)
-  uint64_t d2_full[2][2];  // [group][half]: that N = 64 half of the hidden GEMM has completed (tcgen05.commit)
+  uint64_t d2_full[2][4];  // [group][2 * half + batch]: that N = 32 quarter of the hidden GEMM has completed (commit)
   uint64_t d3_full[2][2];  // [group][buffer]: an output pass has landed in that accumulator buffer
   uint64_t d3_free[2][2];  // [group][buffer]: the half's 4 warps have drained the buffer
   uint64_t k_ready[2];     // [group] (8 warp arrivals): the next tile's key operand is written and X is drained
@@ -652,9 +652,9 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
 
   if (tid == 0) {
     for (int g = 0; g < 2; ++g) {
+      for (int q = 0; q < 4; ++q) mbar_init(TC_BAR(d2_full[g][q]), 1);
       for (int h = 0; h < 2; ++h) {
         mbar_init(TC_BAR(e_ready[g][h]), TC_TILE / 32);
-        mbar_init(TC_BAR(d2_full[g][h]), 1);
         mbar_init(TC_BAR(d3_full[g][h]), 1);
         mbar_init(TC_BAR(d3_free[g][h]), TC_TILE / 32);
       }
@@ -700,7 +700,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
     const uint32_t t_x = tbase + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)grp * 256u + (uint32_t)half * 64u;
     const uint32_t t_y = t_x + 128u;                   // this half's 64 columns of X / Y
     const uint32_t bar_ready = TC_BAR(e_ready[0][0]) + 16u * grp + 8u * half;
-    const uint32_t bar_d2 = TC_BAR(d2_full[0][0]) + 16u * grp + 8u * half;
+    const uint32_t bar_d2 = TC_BAR(d2_full[0][0]) + 32u * grp + 16u * half;  // + 8 * batch
     const uint32_t bar_d3 = TC_BAR(d3_full[0][0]) + 16u * grp + 8u * half;
     const uint32_t bar_free = TC_BAR(d3_free[0][0]) + 16u * grp + 8u * half;
     const uint32_t t_key = tbase + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)grp * 256u + 128u;  // Y[0, 24)
@@ -831,14 +831,13 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           TC_TRACE(1);
 
           // ---- E2: h2 = LeakyReLU(D * 2^-e2 + b2), rewritten in place over this half's accumulator columns ----
-          mbar_wait(bar_d2, ph_d2);
-          ph_d2 ^= 1u;
-          tc_fence_after();
-          TC_TRACE(2);
           {
             const float s2inv = par[TC_PF_SCAL];
 #pragma unroll 1
             for (int bt = 0; bt < 2; ++bt) {
+              mbar_wait(bar_d2 + 8u * bt, ph_d2);  // this quarter of the hidden GEMM has landed
+              tc_fence_after();
+              if (bt == 0) TC_TRACE(2);
               float dv[32];
               tmem_ld32(t_y + bt * 32, dv);
               tc_wait_ld();
@@ -858,6 +857,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               tmem_st16(t_y + bt * 32 + 16, rl);
             }
           }
+          ph_d2 ^= 1u;
           tc_wait_st();
           tc_fence_before();
           warp_arrive(bar_ready, lane);
@@ -949,10 +949,10 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       // =============================== MMA issuer of group g ===============================
       const int g = __shfl_sync(0xffffffffu, warp, 0) - 16;
       const uint32_t t_x = __shfl_sync(0xffffffffu, tbase, 0) + (uint32_t)g * 256u, t_y = t_x + 128u;
-      const uint32_t idesc2 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc3 = (1u << 4) | ((uint32_t)(TC_DIM_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t bar_ready = TC_BAR(e_ready[0][0]) + 16u * g;
-      const uint32_t bar_d2 = TC_BAR(d2_full[0][0]) + 16u * g;
+      const uint32_t bar_d2 = TC_BAR(d2_full[0][0]) + 32u * g;
       const uint32_t bar_d3 = TC_BAR(d3_full[0][0]) + 16u * g;
       const uint32_t bar_free = TC_BAR(d3_free[0][0]) + 16u * g;
       const uint32_t w1 = sb + sl.w1, w2 = sb + sl.w2, w3 = sb + sl.w3;
@@ -987,11 +987,12 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           tc_fence_after();
           TC_TRACE_I(1);
           if (elect_one()) {
+            // four N = 32 quarters, alternating between the halves so both start their E2 early
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              issue_gemm<0, 8, true>(t_y + 64u * h, t_x, w2 + h * 64 * 128, w2 + TC_W2_BYTES / 2 + h * 64 * 128, 128 * 128,
-                                     idesc2);
-              umma_commit(bar_d2 + 8u * h);
+            for (int q = 0; q < 4; ++q) {
+              const int h = q & 1, bt = q >> 1, n0 = h * 64 + bt * 32;
+              issue_gemm<0, 8, true>(t_y + (uint32_t)n0, t_x, w2 + n0 * 128, w2 + TC_W2_BYTES / 2 + n0 * 128, 128 * 128, idesc2);
+              umma_commit(bar_d2 + 8u * (2 * h + bt));
             }
             if (k == my_tiles - 1) umma_commit(TC_BAR(w2_free));  // W2 is free once this group's last hidden GEMM is done
           }
