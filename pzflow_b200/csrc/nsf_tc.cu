@@ -388,7 +388,9 @@ __device__ __forceinline__ void tc_rqs_eval(const SplineKnotSel& s, float x, flo
     const float a = s.hk * (sk - s.dk) + t * dsum;
     const float b = s.hk * s.dk - t * dsum;
     const float c = (-sk) * t;
-    relx = __fdividef(2.0f * c, (-b) - sqrtf(b * b - (4.0f * a) * c));
+    float root;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(b * b - (4.0f * a) * c));
+    relx = __fdividef(2.0f * c, (-b) - root);
     out = relx * s.wk + s.xk;
   } else {
     relx = __fdividef(mx - s.xk, s.wk);
@@ -616,15 +618,25 @@ __device__ __noinline__ int level_after(const PlanDev* plan, bool inverse, int s
 #ifdef PZB_TC_TRACE
 // debug build only: SM-clock timestamps of the epilogue phases of CTA 0, second coupling stage of its first chunk
 __device__ unsigned int g_tc_trace[19 * 8 * 8];
+__device__ unsigned int g_tc_trace2[16 * 8];
+#define TC_TRACE_S(ev)                                                                       \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && lane == 0 && seq == 2) g_tc_trace2[warp * 8 + (ev)] = (unsigned int)clock64(); \
+  } while (0)
 #define TC_TRACE(ev)                                                                         \
   do {                                                                                       \
-    if (blockIdx.x == 0 && lane == 0 && seq == 1 && k < 8) g_tc_trace[(warp * 8 + k) * 8 + (ev)] = (unsigned int)clock64(); \
+    if (blockIdx.x == 0 && lane == 0 && (seq == 1 || seq == 2) && k < 4)                      \
+      g_tc_trace[(warp * 8 + k + 4 * (seq - 1)) * 8 + (ev)] = (unsigned int)clock64();        \
   } while (0)
 #define TC_TRACE_I(ev)                                                                       \
   do {                                                                                       \
-    if (blockIdx.x == 0 && lane == 0 && s == 1 && k < 8) g_tc_trace[(warp * 8 + k) * 8 + (ev)] = (unsigned int)clock64(); \
+    if (blockIdx.x == 0 && lane == 0 && (s == 1 || s == 2) && k < 4)                          \
+      g_tc_trace[(warp * 8 + k + 4 * (s - 1)) * 8 + (ev)] = (unsigned int)clock64();          \
   } while (0)
 #else
+#define TC_TRACE_S(ev) \
+  do {                 \
+  } while (0)
 #define TC_TRACE_I(ev) \
   do {                 \
   } while (0)
@@ -758,8 +770,11 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         prev_end = si + 1;
 
         // parameter block of this stage (double buffered); previous-stage state writes of the row's other half
+        TC_TRACE_S(0);
         mbar_wait(TC_BAR(par_full[0]) + 8u * (seq & 1), (uint32_t)((seq >> 1) & 1));
+        TC_TRACE_S(1);
         named_bar_sync(2 + grp, TC_GROUP_THREADS);
+        TC_TRACE_S(2);
         const float* par = reinterpret_cast<const float*>(base + sl.par + (seq & 1) * TC_PAR_BYTES);
         const int* pint = reinterpret_cast<const int*>(par + TC_PI);
         const int L = pint[TC_PI_L];
@@ -801,9 +816,11 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           tmem_st8(t_key + 16u, rl);
           tc_wait_st();
         };
+        TC_TRACE_S(3);
         if (half == kw) write_keys(0);
         tc_fence_before();
         warp_arrive(bar_key, lane);
+        TC_TRACE_S(4);
 
         for (int k = 0; k < my_tiles; ++k) {
           const int r = (2 * k + grp) * TC_TILE + lrow;  // row within the chunk (state is allocated for every tile)
@@ -1119,6 +1136,9 @@ cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs
   long long want = (tiles_total + num_sms - 1) / num_sms;
   if (want < 2) want = 2;
   lp.chunk_tiles = (int)(want < fit ? want : fit);
+  // the two epilogue groups take alternate tiles: an odd tile count leaves one group idle for a whole tile per stage
+  if (lp.chunk_tiles > 2 && (lp.chunk_tiles & 1)) lp.chunk_tiles -= (want > fit) ? 1 : -1;
+  if (lp.chunk_tiles > fit) lp.chunk_tiles = fit - (fit & 1);
   const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols);
   const size_t smem = (size_t)sl.total + 1024;
   if (smem > (size_t)TC_SMEM_MAX) return cudaErrorInvalidConfiguration;
@@ -1143,5 +1163,8 @@ cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs
 #ifdef PZB_TC_TRACE
 extern "C" int pzb_debug_tc_trace(unsigned int* out) {
   return (int)cudaMemcpyFromSymbol(out, pzb::g_tc_trace, sizeof(pzb::g_tc_trace));
+}
+extern "C" int pzb_debug_tc_trace2(unsigned int* out) {
+  return (int)cudaMemcpyFromSymbol(out, pzb::g_tc_trace2, sizeof(pzb::g_tc_trace2));
 }
 #endif
