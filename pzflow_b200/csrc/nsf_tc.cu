@@ -38,6 +38,7 @@
 
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 
 #include "pzb_common.cuh"
@@ -750,12 +751,6 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       }
       int level = level_after(plan, INV, 0, first_nsc, 0);  // chain depth (row independent)
       named_bar_sync(2 + grp, TC_GROUP_THREADS);
-#ifdef PZB_TC_STAGGER
-      if (ci == 0 && grp == 1) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < PZB_TC_STAGGER) __nanosleep(200);
-      }
-#endif
 
       // ---- the coupling stages ----
       int prev_end = first_nsc;
