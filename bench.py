@@ -70,7 +70,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu_index), "-lms", "100"], stdout=self.fh,
+                                          "-i", str(self.gpu_index), "-lms", "20"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -235,7 +235,6 @@ def run_ours(args, rank, world, local_rank):
         ev[i + 1].record()
     barrier()
     launches = launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = max_ranks(ev[0].elapsed_time(ev[-1]))
     kernel_ms = statistics.mean(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
     ms_per_step = total_ms / args.steps
@@ -255,6 +254,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_ms = max_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     e2e_value = n * world / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and e2e)
 
     # ---- secondary: posterior (config-3 geometry) and sample (inverse) ----
     ng = min(POSTERIOR_GALAXIES, n)
