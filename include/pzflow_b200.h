@@ -54,13 +54,20 @@ typedef enum {
    * stages' log-determinants from zeros before its parent adds the total, so
    * the flattening keeps the brackets to reproduce the fp32 summation order. */
   PZB_STAGE_CHAIN_BEGIN = 5,
-  PZB_STAGE_CHAIN_END = 6
+  PZB_STAGE_CHAIN_END = 6,
+  /* parameter-free bijectors, evaluated as steps of the same fused chain */
+  PZB_STAGE_REVERSE = 7,          /* pzflow/bijectors.py:525-556: columns reversed (folded like Roll)          */
+  PZB_STAGE_SCALE = 8,            /* pzflow/bijectors.py:668-714: B = scale                                     */
+  PZB_STAGE_INV_SOFTPLUS = 9,     /* pzflow/bijectors.py:314-372: vec_a = column indices, vec_b = sharpness(es) */
+  PZB_STAGE_COLOR_TRANSFORM = 10  /* pzflow/bijectors.py:177-311: shift = ref_idx, vec_a = mag_idx, n_vec       */
 } pzb_stage_kind;
 
 /* Latent distributions of the hot path. */
 typedef enum {
   PZB_LATENT_UNIFORM = 1,    /* pzflow/distributions.py:395-470 */
-  PZB_LATENT_CENTBETA13 = 2  /* pzflow/distributions.py:137-229 */
+  PZB_LATENT_CENTBETA13 = 2, /* pzflow/distributions.py:137-229 */
+  PZB_LATENT_NORMAL = 3,     /* pzflow/distributions.py:232-303 (B unused) */
+  PZB_LATENT_CENTBETA = 4    /* pzflow/distributions.py:45-135: per-dimension alpha, beta via pzb_plan_set_latent_params */
 } pzb_latent_kind;
 
 /* Conditioner evaluation engines. */
@@ -77,7 +84,9 @@ typedef struct {
   int32_t shift;
 
   /* SHIFT_BOUNDS: vec_a = min, vec_b = max, n_vec = 1 or D, B = output half-range.
-   * STANDARD_SCALER: vec_a = means, vec_b = stds, n_vec = D.  HOST pointers. */
+   * STANDARD_SCALER: vec_a = means, vec_b = stds, n_vec = D.  HOST pointers.
+   * INV_SOFTPLUS: vec_a = column indices (as floats), vec_b = sharpness per index (or one value), n_vec = #columns.
+   * COLOR_TRANSFORM: vec_a = mag_idx (as floats), n_vec = #magnitudes, shift = ref_idx. */
   const float *vec_a;
   const float *vec_b;
   int32_t n_vec;
@@ -116,6 +125,11 @@ int pzb_device_count(void);
  * flow._params changes identity.  `device` is the CUDA ordinal. */
 int pzb_plan_create(const pzb_stage_desc *stages, int32_t n_stages, int32_t input_dim,
                     int32_t latent_kind, float latent_B, int32_t device, pzb_plan **out);
+
+/* CentBeta only: the latent's parameter pytree ((log a_1, log b_1), ..., (log a_D, log b_D))
+ * (pzflow/distributions.py:70-99) flattened to 2 * D HOST floats.  Part of plan construction: call once,
+ * right after pzb_plan_create, before the first evaluation. */
+int pzb_plan_set_latent_params(pzb_plan *plan, const float *log_ab, int32_t n);
 
 void pzb_plan_destroy(pzb_plan *plan);
 

@@ -242,8 +242,13 @@ def _make_scipy():
 
     class _MVN:
         @staticmethod
-        def logpdf(*a, **k):
-            raise NotImplementedError("jax_shim: multivariate_normal is outside the hot path")
+        def logpdf(x, mean, cov):
+            # jax.scipy.stats.multivariate_normal.logpdf for cov = identity (the only use: distributions.py:271-275)
+            x, mean, cov = np.asarray(x, dtype=_F32), np.asarray(mean, dtype=_F32), np.asarray(cov, dtype=_F32)
+            assert np.array_equal(cov, np.eye(cov.shape[0], dtype=_F32)), "jax_shim: identity covariance only"
+            n = _F32(mean.shape[-1])
+            y = x - mean
+            return _out((_F32(-0.5) * (n * np.log(_F32(2 * np.pi)) + (y * y).sum(axis=-1, dtype=_F32))).astype(_F32))
 
     stats.beta, stats.multivariate_normal = _Beta, _MVN
 

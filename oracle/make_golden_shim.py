@@ -113,6 +113,56 @@ def case_bijectors(pzflow):
     _save("bijectors", store)
 
 
+def case_extra_bijectors(pzflow):
+    """the parameter-free rows of tests/test_bijectors.py:16-51 (ColorTransform, Reverse,
+    Scale, InvSoftplus, their Chain) plus a flow-shaped Chain, and the Normal / CentBeta latents."""
+    from pzflow import bijectors as B
+    from pzflow import distributions as Dn
+    import jax.numpy as jnp
+    from jax import random
+    x = np.array([[0.2, 0.1, -0.3, 0.5, 0.1, -0.4, -0.3],
+                  [0.6, 0.5, 0.2, 0.2, -0.4, -0.1, 0.7],
+                  [0.9, 0.2, -0.3, 0.3, 0.4, -0.4, -0.1]], np.float32)
+    rng = np.random.default_rng(5)
+    xr = np.vstack([x, rng.uniform(0.05, 1.5, size=(61, 7)).astype(np.float32)])
+    cases = [
+        ("color", B.ColorTransform, (3, [1, 3, 5])),
+        ("color_first", B.ColorTransform, (1, [1, 2, 4, 5, 6])),
+        ("reverse", B.Reverse, ()),
+        ("scale", B.Scale, (2.0,)),
+        ("invsoftplus0", B.InvSoftplus, (0,)),
+        ("invsoftplus2", B.InvSoftplus, ([1, 3], [2.0, 12.0])),
+        ("chain_free", B.Chain, (B.Reverse(), B.Scale(1 / 6), B.Roll(-1))),
+        ("chain_flow", B.Chain, (B.ColorTransform(3, [1, 2, 3, 4, 5, 6]), B.InvSoftplus(0, 4.0),
+                                 B.StandardScaler(jnp.linspace(-0.5, 0.5, 7), jnp.linspace(0.5, 2.0, 7)),
+                                 B.Reverse(), B.RollingSplineCoupling(3, 1, 8, 6, 1, 32), B.Scale(0.5))),
+    ]
+    store = dict(x=xr, names=np.array([c[0] for c in cases]))
+    cond = np.zeros((xr.shape[0], 1), np.float32)
+    for name, bij, args in cases:
+        init_fun, info = bij(*args)
+        params, fwd, inv = init_fun(random.PRNGKey(0), 7)
+        y, ld = fwd(params, jnp.array(xr), conditions=jnp.array(cond))
+        xi, ldi = inv(params, y, conditions=jnp.array(cond))
+        xi2, ldi2 = inv(params, jnp.array(xr), conditions=jnp.array(cond))
+        F.pack_tree(f"{name}_info", info, store)
+        F.pack_tree(f"{name}_params", params, store)
+        store[f"{name}_fwd"], store[f"{name}_fwd_ld"] = _np(y), _np(ld)
+        store[f"{name}_inv_of_fwd"], store[f"{name}_inv_of_fwd_ld"] = _np(xi), _np(ldi)
+        store[f"{name}_inv"], store[f"{name}_inv_ld"] = _np(xi2), _np(ldi2)
+    # latents (tests/test_distributions.py rows for Normal and CentBeta)
+    u = rng.uniform(-5.5, 5.5, size=(200, 3)).astype(np.float32)
+    store["latent_u"] = u
+    normal = Dn.Normal(3)
+    store["normal_lp"] = _np(normal.log_prob(normal._params, jnp.array(u)))
+    cb = Dn.CentBeta(3, 5)
+    cb_params = tuple((float(a), float(b)) for a, b in rng.normal(0.8, 0.6, size=(3, 2)))
+    store["centbeta_params"] = np.asarray(cb_params, np.float32)
+    store["centbeta_lp"] = _np(cb.log_prob(cb_params, jnp.array(u)))
+    store["centbeta_lp_default"] = _np(cb.log_prob(cb._params, jnp.array(u)))
+    _save("extra", store)
+
+
 def _boost(params, rng, scale=3.0):
     """Scale the last Dense layer of every conditioner so splines are strongly non-identity."""
     if isinstance(params, list) and len(params) and isinstance(params[0], tuple) and len(params[0]) == 2 \
@@ -189,6 +239,7 @@ def main():
     pzflow = jax_shim.install()
     case_example_flow(pzflow)
     case_bijectors(pzflow)
+    case_extra_bijectors(pzflow)
     case_default_flows(pzflow)
 
 

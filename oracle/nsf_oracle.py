@@ -252,6 +252,57 @@ def standard_scaler(inputs, means, stds, inverse):
     return out.astype(dt), ld.astype(dt)
 
 
+def reverse(inputs):
+    """bijectors.py:541-553 -- inputs[:, ::-1] both ways, log_det 0."""
+    return inputs[:, ::-1].copy(), np.zeros(inputs.shape[0], dtype=inputs.dtype)
+
+
+def scale_bijector(inputs, scale, inverse):
+    """bijectors.py:689-711 -- scale * x, log_det = log(scale ** D); inverse 1 / scale * x."""
+    dt = inputs.dtype.type
+    ld = np.log(dt(scale) ** dt(inputs.shape[-1])) * np.ones(inputs.shape[0], dtype=inputs.dtype)
+    if inverse:
+        return (dt(1) / dt(scale)) * inputs, -ld
+    return dt(scale) * inputs, ld
+
+
+def inv_softplus(inputs, column_idx, sharpness, inverse):
+    """bijectors.py:350-369."""
+    dt = inputs.dtype.type
+    idx = np.atleast_1d(column_idx)
+    k = np.atleast_1d(np.asarray(sharpness, dtype=inputs.dtype))
+    outputs = inputs.copy()
+    with np.errstate(all="ignore"):
+        if inverse:
+            outputs[:, idx] = np.log(dt(1) + np.exp(k * inputs[:, idx])) / k
+            log_det = -np.log(dt(1) + np.exp(-k * inputs[:, idx])).sum(axis=1, dtype=inputs.dtype)
+        else:
+            outputs[:, idx] = np.log(dt(-1) + np.exp(k * inputs[:, idx])) / k
+            log_det = np.log(dt(1) + np.exp(-k * outputs[:, idx])).sum(axis=1, dtype=inputs.dtype)
+    return outputs, log_det
+
+
+def color_transform(inputs, ref_idx, mag_idx, inverse):
+    """bijectors.py:236-308."""
+    input_dim = inputs.shape[1]
+    mag_idx = np.asarray(mag_idx)
+    front_idx = np.setdiff1d(np.arange(input_dim), mag_idx)
+    mag0_idx = len(front_idx)
+    new_idx = np.concatenate((front_idx, mag_idx))
+    new_ref = np.where(new_idx == ref_idx)[0][0]
+    zeros = np.zeros(inputs.shape[0], dtype=inputs.dtype)
+    if not inverse:
+        outputs = np.hstack((inputs[:, front_idx], inputs[:, ref_idx, None], -np.diff(inputs[:, mag_idx])))
+        return outputs.astype(inputs.dtype), zeros
+    outputs = np.hstack((inputs[:, 0:mag0_idx], inputs[:, mag0_idx, None],
+                         np.cumsum(inputs[:, mag0_idx + 1:], axis=-1, dtype=inputs.dtype)))
+    if ref_idx != mag_idx[0]:
+        outputs[:, mag0_idx] = outputs[:, mag0_idx] + outputs[:, new_ref]
+    outputs[:, mag0_idx + 1:] = outputs[:, mag0_idx, None] - outputs[:, mag0_idx + 1:]
+    outputs = outputs[:, np.argsort(new_idx)]
+    return outputs.astype(inputs.dtype), zeros
+
+
 def apply_bijector(info, params, inputs, conditions, inverse=False, bins=None):
     """Interpret a Bijector_Info tuple the way utils.py:11-19 rebuilds it and
     bijectors.py:155-170 (Chain) runs it.  Returns (outputs, log_det)."""
@@ -276,6 +327,14 @@ def apply_bijector(info, params, inputs, conditions, inverse=False, bins=None):
         return shift_bounds(inputs, args[0], args[1], args[2], inverse)
     if name == "StandardScaler":
         return standard_scaler(inputs, args[0], args[1], inverse)
+    if name == "Reverse":
+        return reverse(inputs)
+    if name == "Scale":
+        return scale_bijector(inputs, args[0], inverse)
+    if name == "InvSoftplus":
+        return inv_softplus(inputs, args[0], args[1] if len(args) > 1 else 1, inverse)
+    if name == "ColorTransform":
+        return color_transform(inputs, args[0], args[1], inverse)
     raise NotImplementedError(f"oracle: bijector {name!r} is outside the hot path (SURVEY.md §2)")
 
 
@@ -320,7 +379,31 @@ def latent_log_prob(latent_info, u):
                 lp = np.where((x > loc + scale) | (x < loc), dt(-np.inf), lp)
                 cols.append(lp.reshape(-1, 1))
             return np.hstack(cols).sum(axis=1, dtype=u.dtype)
+        if name == "Normal":
+            # distributions.py:255-275 -- multivariate_normal.logpdf(u, zeros, identity)
+            (input_dim,) = args
+            return (dt(-0.5) * (dt(input_dim) * np.log(dt(2 * np.pi)) + (u * u).sum(axis=1, dtype=u.dtype))).astype(u.dtype)
     raise NotImplementedError(f"oracle: latent {name!r} is outside the hot path")
+
+
+def centbeta_log_prob(latent_params, u, B):
+    """distributions.py:70-99 -- sum_i beta.logpdf(u_i; exp(p_i0), exp(p_i1), loc=-B, scale=2B), with
+    jax.scipy.stats.beta.logpdf = -betaln(a, b) + xlogy(a-1, y) + xlog1py(b-1, -y) - log(scale)."""
+    from scipy import special as sps
+    dt = u.dtype.type
+    loc, scale = dt(-B), dt(2 * B)
+    cols = []
+    with np.errstate(all="ignore"):
+        for i, (pa, pb) in enumerate(latent_params):
+            a, b = np.exp(dt(pa)), np.exp(dt(pb))
+            betaln = (dt(sps.gammaln(a)) + dt(sps.gammaln(b))) - dt(sps.gammaln(a + b))
+            x = u[:, i]
+            y = (x - loc) / scale
+            lin = sps.xlogy(a - dt(1), y).astype(u.dtype) + sps.xlog1py(b - dt(1), -y).astype(u.dtype)
+            lp = (-betaln + lin) - np.log(scale)
+            lp = np.where((x > loc + scale) | (x < loc), dt(-np.inf), lp)
+            cols.append(lp.reshape(-1, 1))
+    return np.hstack(cols).sum(axis=1, dtype=u.dtype)
 
 
 # --------------------------------------------------------------------------- #
@@ -334,7 +417,11 @@ def flow_log_prob(bijector_info, latent_info, params, X, conditions=None, bins=N
         conditions = np.zeros((X.shape[0], 1), dtype=X.dtype)  # flow.py:329
     with np.errstate(all="ignore"):
         u, log_det = apply_bijector(bijector_info, params[1], X, conditions, False, bins)
-        lp = latent_log_prob(latent_info, u) + log_det
+        if latent_info[0] == "CentBeta":
+            lat = centbeta_log_prob(params[0], u, latent_info[1][1])
+        else:
+            lat = latent_log_prob(latent_info, u)
+        lp = lat + log_det
     return _nan_to_num(lp.astype(X.dtype), nan=-np.inf)
 
 

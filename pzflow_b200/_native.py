@@ -23,9 +23,15 @@ STAGE_ROLL = 3
 STAGE_NSC = 4
 STAGE_CHAIN_BEGIN = 5
 STAGE_CHAIN_END = 6
+STAGE_REVERSE = 7
+STAGE_SCALE = 8
+STAGE_INV_SOFTPLUS = 9
+STAGE_COLOR_TRANSFORM = 10
 
 LATENT_UNIFORM = 1
 LATENT_CENTBETA13 = 2
+LATENT_NORMAL = 3
+LATENT_CENTBETA = 4
 
 ENGINE_AUTO = 0
 ENGINE_SIMT = 1
@@ -61,6 +67,7 @@ SIGNATURES = {
     "pzb_device_count": (C.c_int, []),
     "pzb_plan_create": (C.c_int, [C.POINTER(StageDesc), C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                   C.c_int32, C.POINTER(C.c_void_p)]),
+    "pzb_plan_set_latent_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "pzb_plan_destroy": (None, [C.c_void_p]),
     "pzb_plan_input_dim": (C.c_int, [C.c_void_p]),
     "pzb_plan_n_conditions": (C.c_int, [C.c_void_p]),

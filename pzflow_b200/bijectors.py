@@ -1,15 +1,17 @@
 """Host-side mirror of pzflow's Bijector protocol for the hot-path bijectors.
 
 Same names, arguments, ``Bijector_Info`` tuples, params pytrees and error
-behaviour as pzflow/bijectors.py (protocol 16-118, Chain 121-174,
-NeuralSplineCoupling 375-522, Roll 559-598, RollingSplineCoupling 601-665,
-ShiftBounds 717-777, StandardScaler 817-861) -- but the Forward/Inverse
+behaviour as pzflow/bijectors.py (protocol 16-118, Chain 121-174, ColorTransform 177-311,
+InvSoftplus 314-372, NeuralSplineCoupling 375-522, Reverse 525-556, Roll 559-598,
+RollingSplineCoupling 601-665, Scale 668-714, ShiftBounds 717-777,
+StandardScaler 817-861) -- but the Forward/Inverse
 functions an ``InitFunction`` returns do not run stage by stage: each one
 compiles the WHOLE bijector it belongs to (nested Chains included) into one
 device plan and evaluates it with one fused CUDA kernel through the C-ABI.
 
-Bijectors outside the hot path (ColorTransform, InvSoftplus, Reverse, Scale,
-Shuffle, UniformDequantizer) are not provided.
+Not provided: Shuffle (its permutation is drawn from the jax PRNG at init time and is
+not stored in the Bijector_Info or the params, so it cannot be reproduced without jax) and
+UniformDequantizer (training-time noise).
 """
 from __future__ import annotations
 
@@ -253,3 +255,57 @@ def StandardScaler(means, stds) -> Tuple[InitFunction, Bijector_Info]:
         return (), forward_fun, inverse_fun
 
     return init_fun, bijector_info
+
+
+def _parameter_free(bijector_info: Bijector_Info) -> InitFunction:
+    @InitFunction
+    def init_fun(rng, input_dim, **kwargs):
+        forward_fun, inverse_fun = _fused(bijector_info, input_dim)
+        return (), forward_fun, inverse_fun
+
+    return init_fun
+
+
+@Bijector
+def ColorTransform(ref_idx: int, mag_idx) -> Tuple[InitFunction, Bijector_Info]:
+    """Bijector that calculates photometric colors from magnitudes (pzflow/bijectors.py:177-311):
+    [.., mags ..] -> [other columns, reference magnitude, adjacent colors]."""
+    if ref_idx <= 0:
+        raise ValueError("ref_idx must be a positive integer.")
+    if not isinstance(ref_idx, int):
+        raise ValueError("ref_idx must be an integer.")
+    if ref_idx not in mag_idx:
+        raise ValueError("ref_idx must be in mag_idx.")
+    bijector_info = ("ColorTransform", (ref_idx, mag_idx))
+    return _parameter_free(bijector_info), bijector_info
+
+
+@Bijector
+def InvSoftplus(column_idx, sharpness=1) -> Tuple[InitFunction, Bijector_Info]:
+    """Bijector that applies inverse softplus to the specified column(s)
+    (pzflow/bijectors.py:314-372)."""
+    idx = np.atleast_1d(column_idx)
+    k = np.atleast_1d(sharpness)
+    if len(idx) != len(k) and len(k) != 1:
+        raise ValueError("Please provide either a single sharpness or one for each column index.")
+    bijector_info = ("InvSoftplus", (column_idx, sharpness))
+    return _parameter_free(bijector_info), bijector_info
+
+
+@Bijector
+def Reverse() -> Tuple[InitFunction, Bijector_Info]:
+    """Bijector that reverses the order of inputs (pzflow/bijectors.py:525-556)."""
+    bijector_info = ("Reverse", ())
+    return _parameter_free(bijector_info), bijector_info
+
+
+@Bijector
+def Scale(scale: float) -> Tuple[InitFunction, Bijector_Info]:
+    """Bijector that multiplies inputs by a scalar (pzflow/bijectors.py:668-714)."""
+    if isinstance(scale, np.ndarray):
+        if scale.dtype != np.float32:
+            raise ValueError("scale must be a float or array of floats.")
+    elif not isinstance(scale, float):
+        raise ValueError("scale must be a float or array of floats.")
+    bijector_info = ("Scale", (scale,))
+    return _parameter_free(bijector_info), bijector_info

@@ -357,21 +357,28 @@ nsf_chain_simt_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, int Lma
         __syncthreads();
       } else if (kind == STEP_AFFINE) {
         const AffineDev& af = plan->affine[step.idx];
-        for (int e = tid; e < D * TM; e += NTHREADS) {
-          const int j = e / TM;
-          const float x = Xs[e];
-          float y;
-          if (af.kind == AFF_SHIFT_BOUNDS) {
-            // fwd B*(x-mean)/half_range ; inv x*half_range/B + mean  (bijectors.py:760-773)
-            y = inverse ? (x * af.b[j]) / af.B + af.a[j] : (af.B * (x - af.a[j])) / af.b[j];
-          } else {
-            // fwd (x-means)/stds ; inv x*stds + means  (bijectors.py:848-857)
-            y = inverse ? x * af.b[j] + af.a[j] : (x - af.a[j]) / af.b[j];
+        if (af.kind == AFF_INV_SOFTPLUS) {
+          // data-dependent log-det: one thread walks a row's columns (sum in column order)
+          for (int r = tid; r < TM; r += NTHREADS) {
+            float lds = 0.0f;
+            for (int j = 0; j < D; ++j) {
+              float ld;
+              Xs[j * TM + r] = pz_affine_elem(af, inverse, j, Xs[j * TM + r], ld);
+              lds += ld;
+            }
+            ldacc[level * TM + r] += lds;
           }
-          Xs[e] = y;
+        } else {
+          for (int e = tid; e < D * TM; e += NTHREADS) {
+            float ld;
+            Xs[e] = pz_affine_elem(af, inverse, e / TM, Xs[e], ld);
+          }
+          const float ldc = inverse ? af.logdet_inv : af.logdet_fwd;
+          for (int r = tid; r < TM; r += NTHREADS) ldacc[level * TM + r] += ldc;
         }
-        const float ldc = inverse ? af.logdet_inv : af.logdet_fwd;
-        for (int r = tid; r < TM; r += NTHREADS) ldacc[level * TM + r] += ldc;
+        __syncthreads();
+      } else if (kind == STEP_COLOR) {
+        for (int r = tid; r < TM; r += NTHREADS) pz_color_row(plan->color[step.idx], inverse, Xs + r, TM);
         __syncthreads();
       } else {
         run_nsc(plan->nsc[step.idx], inverse, args, row0, Xs, Cs, ldacc + level * TM, ldp, act0,
@@ -384,8 +391,7 @@ nsf_chain_simt_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, int Lma
       for (int r = tid; r < TM; r += NTHREADS) {
         const long long row = row0 + r;
         if (row >= args.N) continue;
-        const float lat = pz_latent_logprob(plan->latent_kind, D, plan->latent_B, plan->latent_const,
-                                            [&](int j) { return Xs[plan->perm_final[j] * TM + r]; });
+        const float lat = pz_latent_logprob(plan, [&](int j) { return Xs[plan->perm_final[j] * TM + r]; });
         float lp = pz_nan_to_num_lp(lat + ldacc[r]);  // pzflow/flow.py:404-406
         args.out0[row] = (args.mode == MODE_POSTERIOR) ? expf(lp) : lp;  // flow.py:720
       }

@@ -567,16 +567,14 @@ struct TcLaunch {
 };
 
 // state column indices: x[0, D), log-det levels [D, D + n_lev), pending log-det halves (2), conditions (C)
-__device__ __forceinline__ void apply_affine_cols(const AffineDev& af, bool inverse, int D, float* st, int CR) {
+__device__ __forceinline__ float apply_affine_cols(const AffineDev& af, bool inverse, int D, float* st, int CR) {
+  float ldsum = 0.0f;
   for (int j = 0; j < D; ++j) {
-    const float x = st[j * CR];
-    float y;
-    if (af.kind == AFF_SHIFT_BOUNDS)
-      y = inverse ? (x * af.b[j]) / af.B + af.a[j] : (af.B * (x - af.a[j])) / af.b[j];
-    else
-      y = inverse ? x * af.b[j] + af.a[j] : (x - af.a[j]) / af.b[j];
-    st[j * CR] = y;
+    float ld;
+    st[j * CR] = pz_affine_elem(af, inverse, j, st[j * CR], ld);
+    ldsum += ld;
   }
+  return ldsum;
 }
 
 // Applies the non-NSC steps in [s0, s1) (already mapped to walk order) to one state row.
@@ -597,8 +595,10 @@ __device__ __noinline__ void light_steps_cols(const PlanDev* plan, bool inverse,
       --level;
     } else if (kind == STEP_AFFINE) {
       const AffineDev& af = plan->affine[step.idx];
-      apply_affine_cols(af, inverse, D, st, CR);
-      ldl[level * CR] += inverse ? af.logdet_inv : af.logdet_fwd;
+      const float ld = apply_affine_cols(af, inverse, D, st, CR);
+      ldl[level * CR] += (af.kind == AFF_INV_SOFTPLUS) ? ld : (inverse ? af.logdet_inv : af.logdet_fwd);
+    } else if (kind == STEP_COLOR) {
+      pz_color_row(plan->color[step.idx], inverse, st, CR);
     }
   }
 }
@@ -933,8 +933,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         int lv = level;
         light_steps_cols(plan, INV, prev_end, ns, lv, st, CR);
         if (args.mode == MODE_LOGPROB || args.mode == MODE_POSTERIOR) {
-          const float lat = pz_latent_logprob(plan->latent_kind, D, plan->latent_B, plan->latent_const,
-                                              [&](int j) { return st[plan->perm_final[j] * CR]; });
+          const float lat = pz_latent_logprob(plan, [&](int j) { return st[plan->perm_final[j] * CR]; });
           const float lpv = pz_nan_to_num_lp(lat + st[D * CR]);
           args.out0[row] = (args.mode == MODE_POSTERIOR) ? expf(lpv) : lpv;
         } else {

@@ -113,7 +113,7 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
   const int D = input_dim;
   if (D < 1 || D > MAX_D)
     return fail(PZB_ERR_UNSUPPORTED, "plan_create: input_dim %d outside [1, %d]", D, MAX_D);
-  if (latent_kind != PZB_LATENT_UNIFORM && latent_kind != PZB_LATENT_CENTBETA13)
+  if (latent_kind < PZB_LATENT_UNIFORM || latent_kind > PZB_LATENT_CENTBETA)
     return fail(PZB_ERR_UNSUPPORTED, "plan_create: latent kind %d is outside the hot path", latent_kind);
   if (pzb_device_count() <= 0)
     return fail(PZB_ERR_NO_DEVICE, "plan_create: no CUDA device (this library has no CPU fallback)");
@@ -175,6 +175,88 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
           nxt[j] = cur[src];
         }
         memcpy(cur, nxt, sizeof(int) * D);
+        break;
+      }
+      case PZB_STAGE_REVERSE: {
+        // out[:, j] = in[:, D - 1 - j]  (pzflow/bijectors.py:541-549)
+        int nxt[MAX_D];
+        for (int j = 0; j < D; ++j) nxt[j] = cur[D - 1 - j];
+        memcpy(cur, nxt, sizeof(int) * D);
+        break;
+      }
+      case PZB_STAGE_SCALE:
+      case PZB_STAGE_INV_SOFTPLUS: {
+        if (hp.n_affine >= MAX_AFFINE) {
+          rc = fail(PZB_ERR_UNSUPPORTED, "plan_create: more than %d elementwise stages", MAX_AFFINE);
+          break;
+        }
+        AffineDev& af = hp.affine[hp.n_affine];
+        memset(&af, 0, sizeof(af));
+        if (sd.kind == PZB_STAGE_SCALE) {
+          af.kind = AFF_SCALE;
+          af.B = sd.B;
+          // jnp.log(scale ** input_dim) (pzflow/bijectors.py:692-695)
+          af.logdet_fwd = logf(powf(sd.B, (float)D));
+          af.logdet_inv = -af.logdet_fwd;
+        } else {
+          af.kind = AFF_INV_SOFTPLUS;
+          if (sd.vec_a == nullptr || sd.vec_b == nullptr || sd.n_vec < 1) {
+            rc = fail(PZB_ERR_INVALID, "plan_create: InvSoftplus needs column indices and sharpness");
+            break;
+          }
+          for (int v = 0; v < sd.n_vec; ++v) {
+            int c = (int)sd.vec_a[v];
+            if (c < 0) c += D;  // numpy-style negative index
+            if (c < 0 || c >= D) {
+              rc = fail(PZB_ERR_INVALID, "plan_create: InvSoftplus column %d outside [0, %d)", (int)sd.vec_a[v], D);
+              break;
+            }
+            af.b[cur[c]] = sd.vec_b[v];
+          }
+          if (rc != PZB_OK) break;
+        }
+        hp.steps[hp.n_steps++] = {STEP_AFFINE, hp.n_affine++};
+        break;
+      }
+      case PZB_STAGE_COLOR_TRANSFORM: {
+        if (hp.n_color >= MAX_COLOR) {
+          rc = fail(PZB_ERR_UNSUPPORTED, "plan_create: more than %d ColorTransform stages", MAX_COLOR);
+          break;
+        }
+        const int n = sd.n_vec;
+        if (sd.vec_a == nullptr || n < 1 || n > D) {
+          rc = fail(PZB_ERR_INVALID, "plan_create: ColorTransform needs 1..%d magnitude indices", D);
+          break;
+        }
+        ColorDev& cd = hp.color[hp.n_color];
+        memset(&cd, 0, sizeof(cd));
+        cd.n_mag = n;
+        cd.ref = -1;
+        bool is_mag[MAX_D] = {false};
+        int mag[MAX_D];
+        for (int i = 0; i < n; ++i) {
+          mag[i] = (int)sd.vec_a[i];
+          if (mag[i] < 0 || mag[i] >= D || is_mag[mag[i]]) {
+            rc = fail(PZB_ERR_INVALID, "plan_create: bad ColorTransform magnitude index %d", mag[i]);
+            break;
+          }
+          is_mag[mag[i]] = true;
+          if (mag[i] == sd.shift) cd.ref = i;
+          cd.slot[i] = (int16_t)cur[mag[i]];
+        }
+        if (rc != PZB_OK) break;
+        if (cd.ref < 0) {
+          rc = fail(PZB_ERR_INVALID, "ref_idx must be in mag_idx.");
+          break;
+        }
+        // new logical order: [front columns (ascending), reference magnitude, colours]  (bijectors.py:236-262)
+        int nxt[MAX_D], k = 0;
+        for (int j = 0; j < D; ++j)
+          if (!is_mag[j]) nxt[k++] = cur[j];
+        nxt[k++] = cd.slot[n - 1];
+        for (int i = 0; i + 1 < n; ++i) nxt[k++] = cd.slot[i];
+        memcpy(cur, nxt, sizeof(int) * D);
+        hp.steps[hp.n_steps++] = {STEP_COLOR, hp.n_color++};
         break;
       }
       case PZB_STAGE_SHIFT_BOUNDS:
@@ -396,6 +478,24 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
     return r;
   }
   *out = plan;
+  return PZB_OK;
+}
+
+int pzb_plan_set_latent_params(pzb_plan* plan, const float* log_ab, int32_t n) {
+  if (!plan) return fail(PZB_ERR_INVALID, "set_latent_params: plan is NULL");
+  PlanDev& hp = plan->host;
+  if (hp.latent_kind != PZB_LATENT_CENTBETA)
+    return fail(PZB_ERR_INVALID, "set_latent_params: this plan's latent has no parameters");
+  if (log_ab == nullptr || n != 2 * hp.D) return fail(PZB_ERR_INVALID, "set_latent_params: expected %d values", 2 * hp.D);
+  for (int j = 0; j < hp.D; ++j) {
+    const float a = expf(log_ab[2 * j]), b = expf(log_ab[2 * j + 1]);  // jnp.exp(params[i][0/1])
+    hp.latent_a[j] = a;
+    hp.latent_b[j] = b;
+    hp.latent_betaln[j] = ((float)lgamma((double)a) + (float)lgamma((double)b)) - (float)lgamma((double)a + (double)b);
+  }
+  DeviceGuard guard(plan->device);
+  cudaError_t ce = cudaMemcpy(plan->d_plan, &hp, sizeof(PlanDev), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) return cuda_fail(ce, "set_latent_params upload");
   return PZB_OK;
 }
 

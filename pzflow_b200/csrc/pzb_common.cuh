@@ -23,8 +23,9 @@ constexpr int MAX_AFFINE = 16;
 constexpr int MAX_STEPS = 320;
 constexpr int MAX_CHAIN_DEPTH = 4;
 
-enum StepKind : int { STEP_AFFINE = 0, STEP_NSC = 1, STEP_CHAIN_BEGIN = 2, STEP_CHAIN_END = 3 };
-enum AffKind : int { AFF_SHIFT_BOUNDS = 1, AFF_STANDARD_SCALER = 2 };
+constexpr int MAX_COLOR = 8;
+enum StepKind : int { STEP_AFFINE = 0, STEP_NSC = 1, STEP_CHAIN_BEGIN = 2, STEP_CHAIN_END = 3, STEP_COLOR = 4 };
+enum AffKind : int { AFF_SHIFT_BOUNDS = 1, AFF_STANDARD_SCALER = 2, AFF_SCALE = 3, AFF_INV_SOFTPLUS = 4 };
 enum Mode : int { MODE_LOGPROB = 0, MODE_FORWARD = 1, MODE_INVERSE = 2, MODE_POSTERIOR = 3 };
 
 // One dense layer, packed chunk-major: W[n_chunks][in_dim][NC], b[n_chunks][NC]
@@ -59,6 +60,14 @@ struct AffineDev {
   float logdet_fwd, logdet_inv;
 };
 
+// ColorTransform (pzflow/bijectors.py:177-311): magnitudes -> (reference magnitude, adjacent colours).
+// slot[i] = physical column of magnitude i (mag_idx order) before the stage; after it slot[n_mag - 1] holds the
+// reference magnitude and slot[i], i < n_mag - 1, the colour mag[i] - mag[i + 1].
+struct ColorDev {
+  int n_mag, ref;  // ref: position of ref_idx inside mag_idx
+  int16_t slot[MAX_D];
+};
+
 struct StepDev {
   int kind, idx;
 };
@@ -68,6 +77,10 @@ struct PlanDev {
   float latent_B;
   float latent_const;  // Uniform: -D * log(2B); CentBeta13: betaln(13, 13) in f32 arithmetic
   int16_t perm_final[MAX_D];
+  // CentBeta (pzflow/distributions.py:45-135): per logical dimension alpha, beta and betaln(alpha, beta)
+  float latent_a[MAX_D], latent_b[MAX_D], latent_betaln[MAX_D];
+  int n_color;
+  ColorDev color[MAX_COLOR];
   StepDev steps[MAX_STEPS];
   AffineDev affine[MAX_AFFINE];
   NscDev nsc[MAX_NSC];
@@ -161,6 +174,69 @@ __device__ __forceinline__ float pz_cond_value(const LaunchArgs& a, long long ro
   return v;
 }
 
+// One element of an "affine" (elementwise) stage; returns the element's log-det contribution where the stage has
+// a data-dependent one (InvSoftplus), 0 otherwise (constant log-dets are added once per row by the caller).
+//   ShiftBounds   fwd B*(x-mean)/half_range ; inv x*half_range/B + mean          (bijectors.py:760-773)
+//   StandardScaler fwd (x-means)/stds ; inv x*stds + means                        (bijectors.py:848-857)
+//   Scale         fwd scale*x ; inv (1/scale)*x                                   (bijectors.py:689-711)
+//   InvSoftplus   fwd log(-1+exp(k x))/k, ld log(1+exp(-k y)) ; inv log(1+exp(k x))/k, ld -log(1+exp(-k x))
+//                 on the listed columns (k = b[j] != 0)                             (bijectors.py:350-369)
+__device__ __forceinline__ float pz_affine_elem(const AffineDev& af, bool inverse, int j, float x, float& ld) {
+  ld = 0.0f;
+  switch (af.kind) {
+    case AFF_SHIFT_BOUNDS:
+      return inverse ? (x * af.b[j]) / af.B + af.a[j] : (af.B * (x - af.a[j])) / af.b[j];
+    case AFF_STANDARD_SCALER:
+      return inverse ? x * af.b[j] + af.a[j] : (x - af.a[j]) / af.b[j];
+    case AFF_SCALE:
+      return inverse ? (1.0f / af.B) * x : af.B * x;
+    default: {
+      const float k = af.b[j];
+      if (k == 0.0f) return x;
+      if (inverse) {
+        ld = -logf(1.0f + expf((-k) * x));
+        return logf(1.0f + expf(k * x)) / k;
+      }
+      const float y = logf(-1.0f + expf(k * x)) / k;
+      ld = logf(1.0f + expf((-k) * y));
+      return y;
+    }
+  }
+}
+
+// ColorTransform on one row whose column c lives at st[c * stride] (log-det 0)
+__device__ __forceinline__ void pz_color_row(const ColorDev& cd, bool inverse, float* st, int stride) {
+  const int n = cd.n_mag;
+  if (!inverse) {
+    float prev = st[cd.slot[0] * stride];
+    const float refv = st[cd.slot[cd.ref] * stride];
+    for (int i = 0; i + 1 < n; ++i) {
+      const float nxt = st[cd.slot[i + 1] * stride];
+      st[cd.slot[i] * stride] = -(nxt - prev);  // -jnp.diff(mags)
+      prev = nxt;
+    }
+    st[cd.slot[n - 1] * stride] = refv;
+  } else {
+    const float refv = st[cd.slot[n - 1] * stride];
+    // cumsum of the colours: mag[0] - mag[i + 1]
+    float run = 0.0f, at_ref = 0.0f;
+    for (int i = 0; i + 1 < n; ++i) {
+      run = (i == 0) ? st[cd.slot[0] * stride] : run + st[cd.slot[i] * stride];
+      if (i + 1 == cd.ref) at_ref = run;
+    }
+    const float mag0 = cd.ref == 0 ? refv : refv + at_ref;
+    run = 0.0f;
+    float carry = mag0;  // value to store into slot[i]: mag[i]
+    for (int i = 0; i + 1 < n; ++i) {
+      const float c = st[cd.slot[i] * stride];
+      run = (i == 0) ? c : run + c;
+      st[cd.slot[i] * stride] = carry;
+      carry = mag0 - run;
+    }
+    st[cd.slot[n - 1] * stride] = carry;
+  }
+}
+
 // ---- small numerics shared by both engines (reference op order, no FMA contraction:
 // the files are compiled with -fmad=false and GEMM loops call fmaf explicitly) ----
 
@@ -229,26 +305,40 @@ __device__ __forceinline__ void pz_rqs_eval(const SplineKnotSel& s, float x, flo
 
 // Latent log-density of one row given u in LOGICAL column order through get(j).
 template <typename GetU>
-__device__ __forceinline__ float pz_latent_logprob(int latent_kind, int D, float B, float lconst,
-                                                   GetU get) {
+__device__ __forceinline__ float pz_latent_logprob(const PlanDev* plan, GetU get) {
+  const int latent_kind = plan->latent_kind, D = plan->D;
+  const float B = plan->latent_B;
   if (latent_kind == 1) {  // Uniform, pzflow/distributions.py:414-441
     bool inside = true;
     for (int j = 0; j < D; ++j) {
       const float u = get(j);
       inside = inside && (u >= -B) && (u <= B);
     }
-    return inside ? lconst : -INFINITY;
+    return inside ? plan->latent_const : -INFINITY;
   }
-  // CentBeta13, pzflow/distributions.py:165-194: sum_i beta.logpdf(u_i; 13, 13, -B, 2B)
-  const float betaln = lconst;  // gammaln(13) + gammaln(13) - gammaln(26), f32 arithmetic
+  if (latent_kind == 3) {  // Normal, pzflow/distributions.py:255-275: multivariate_normal.logpdf(u, 0, I)
+    float ss = 0.0f;
+    for (int j = 0; j < D; ++j) {
+      const float u = get(j);
+      ss += u * u;
+    }
+    return -0.5f * ((float)D * 1.8378770664093453f + ss);
+  }
+  // CentBeta13 (distributions.py:165-194) / CentBeta (45-99): sum_i beta.logpdf(u_i; a_i, b_i, loc=-B, scale=2B)
+  //   = -betaln(a, b) + xlogy(a - 1, y) + xlog1py(b - 1, -y) - log(scale),  y = (u + B) / 2B
+  const bool general = latent_kind == 4;
   const float loc = -B, scale = 2.0f * B;
   const float lscale = logf(scale);
   float acc = 0.0f;
   for (int j = 0; j < D; ++j) {
     const float u = get(j);
     const float y = (u - loc) / scale;
-    const float lin = 12.0f * logf(y) + 12.0f * log1pf(-y);
-    float lp = ((-betaln) + lin) - lscale;
+    const float am1 = general ? plan->latent_a[j] - 1.0f : 12.0f, bm1 = general ? plan->latent_b[j] - 1.0f : 12.0f;
+    const float betaln = general ? plan->latent_betaln[j] : plan->latent_const;
+    // xlogy(0, .) = 0 (scipy semantics), only reachable for the general form
+    const float t1 = (general && am1 == 0.0f) ? 0.0f : am1 * logf(y);
+    const float t2 = (general && bm1 == 0.0f) ? 0.0f : bm1 * log1pf(-y);
+    float lp = ((-betaln) + (t1 + t2)) - lscale;
     if (u > loc + scale || u < loc) lp = -INFINITY;
     acc += lp;
   }

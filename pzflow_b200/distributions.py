@@ -1,11 +1,11 @@
-"""Latent distributions of the hot path: Uniform and CentBeta13.
+"""Latent distributions of the hot path: Uniform, CentBeta13, and Normal and CentBeta.
 
-Mirrors pzflow/distributions.py (LatentDist 17-30, CentBeta13 137-229, Uniform
-395-470): same constructors, ``info`` tuples and ``_params``.  Inside
+Mirrors pzflow/distributions.py (LatentDist 17-30, CentBeta 45-135, CentBeta13 137-229, Normal
+232-303, Uniform 395-470): same constructors, ``info`` tuples and ``_params``.  Inside
 ``Flow._log_prob`` the latent log-density is the tail of the fused chain
 kernel; the stand-alone ``log_prob`` / ``sample`` below are the thin device
 versions of the reference methods (they are not on the hot path).
-CentBeta, Normal, Tdist and Joint are out of scope.
+Tdist and Joint are out of scope.
 """
 from __future__ import annotations
 
@@ -103,3 +103,68 @@ class Uniform(LatentDist):
     def sample(self, params: Pytree, nsamples: int, seed: int = None):
         """[nsamples, input_dim] draws from U(-B, B) (distributions.py:443-470)."""
         return self.sample_device(nsamples, seed).cpu().numpy()
+
+
+class Normal(LatentDist):
+    """A multivariate Gaussian distribution with mean zero and unit variance."""
+
+    def __init__(self, input_dim: int) -> None:
+        self.input_dim = input_dim
+        self._params = ()
+        self.info = ("Normal", (input_dim,))
+
+    def log_prob(self, params: Pytree, inputs):
+        """multivariate_normal.logpdf(inputs, 0, I) (distributions.py:255-275)."""
+        u = torch.as_tensor(inputs).to(_device(), torch.float32)
+        out = -0.5 * (self.input_dim * math.log(2.0 * math.pi) + (u * u).sum(dim=1))
+        return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
+
+    def sample_device(self, nsamples: int, seed: int = None) -> torch.Tensor:
+        gen = torch.Generator(device=_device())
+        gen.manual_seed(_seed(seed) % (2 ** 63))
+        return torch.randn((nsamples, self.input_dim), generator=gen, device=_device())
+
+    def sample(self, params: Pytree, nsamples: int, seed: int = None):
+        """[nsamples, input_dim] standard normal draws (distributions.py:277-303)."""
+        return self.sample_device(nsamples, seed).cpu().numpy()
+
+
+class CentBeta(LatentDist):
+    """A centered Beta distribution with learned alpha, beta per dimension (support [-B, B])."""
+
+    def __init__(self, input_dim: int, B: float = 5) -> None:
+        self.input_dim = input_dim
+        self.B = B
+        self._params = tuple([(0.0, 0.0) for i in range(input_dim)])
+        self.info = ("CentBeta", (input_dim, B))
+
+    @staticmethod
+    def _ab(params: Pytree, dev):
+        a = torch.tensor([math.exp(float(np.asarray(p[0]))) for p in params], dtype=torch.float32, device=dev)
+        b = torch.tensor([math.exp(float(np.asarray(p[1]))) for p in params], dtype=torch.float32, device=dev)
+        return a, b
+
+    def log_prob(self, params: Pytree, inputs):
+        """sum_i beta.logpdf(u_i; exp(p_i0), exp(p_i1), loc=-B, scale=2B) (distributions.py:70-99)."""
+        u = torch.as_tensor(inputs).to(_device(), torch.float32)
+        a, b = self._ab(params, u.device)
+        loc, scale = -float(self.B), 2.0 * float(self.B)
+        betaln = torch.lgamma(a) + torch.lgamma(b) - torch.lgamma(a + b)
+        y = (u - loc) / scale
+        lp = (-betaln + (torch.xlogy(a - 1, y) + torch.special.xlog1py(b - 1, -y))) - math.log(scale)
+        lp = torch.where((u > loc + scale) | (u < loc), torch.full_like(lp, -math.inf), lp)
+        out = lp.sum(dim=1)
+        return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
+
+    def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None) -> torch.Tensor:
+        gen = torch.Generator(device=_device())
+        gen.manual_seed(_seed(seed) % (2 ** 63))
+        a, b = self._ab(self._params if params is None else params, _device())
+        conc = torch.stack([a.expand(nsamples, -1), b.expand(nsamples, -1)], dim=-1).contiguous()
+        g = torch._standard_gamma(conc, generator=gen)
+        s = g[..., 0] / (g[..., 0] + g[..., 1])
+        return (2.0 * float(self.B) * (s - 0.5)).contiguous()
+
+    def sample(self, params: Pytree, nsamples: int, seed: int = None):
+        """[nsamples, input_dim] draws, 2B(Beta(a_i, b_i) - 0.5) (distributions.py:101-135)."""
+        return self.sample_device(nsamples, seed, params).cpu().numpy()

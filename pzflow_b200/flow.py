@@ -179,11 +179,13 @@ class Flow:
     def _plan(self, params: Pytree = None) -> Plan:
         """The fused device plan of (bijector, latent) for ``params`` on the current device."""
         params = self._params if params is None else params
-        key = (params_fingerprint(params[1]), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        key = (params_fingerprint(params[1]), params_fingerprint(params[0]),
+               torch.cuda.current_device() if torch.cuda.is_available() else -1)
         plan = self._plan_cache.get(key)
         if plan is None:
             self._plan_cache.clear()
-            plan = Plan(self._bijector_info, params[1], self._input_dim, self._latent_info)
+            plan = Plan(self._bijector_info, params[1], self._input_dim, self._latent_info,
+                        latent_params=params[0])
             self._plan_cache[key] = plan
         return plan
 
@@ -361,7 +363,10 @@ class Flow:
             n = cond.shape[0]
 
         plan = self._plan()
-        u = self.latent.sample_device(n, seed)  # draws stay on the device
+        if isinstance(self.latent, distributions.CentBeta):  # the only latent with parameters on this path
+            u = self.latent.sample_device(n, seed, self._params[0])
+        else:
+            u = self.latent.sample_device(n, seed)  # draws stay on the device
         x = plan.inverse(u, cond, want_log_det=False)[0].cpu().numpy()
         if self.conditional_columns is None:
             return pd.DataFrame(x, columns=self.data_columns)

@@ -17,8 +17,10 @@ import torch
 
 from . import _native as N
 
-HOT_PATH_BIJECTORS = ("Chain", "NeuralSplineCoupling", "Roll", "ShiftBounds", "StandardScaler")
-LATENTS = {"Uniform": N.LATENT_UNIFORM, "CentBeta13": N.LATENT_CENTBETA13}
+HOT_PATH_BIJECTORS = ("Chain", "ColorTransform", "InvSoftplus", "NeuralSplineCoupling", "Reverse", "Roll",
+                      "RollingSplineCoupling", "Scale", "ShiftBounds", "StandardScaler")
+LATENTS = {"Uniform": N.LATENT_UNIFORM, "CentBeta13": N.LATENT_CENTBETA13, "Normal": N.LATENT_NORMAL,
+           "CentBeta": N.LATENT_CENTBETA}
 
 
 def _f32(a) -> np.ndarray:
@@ -51,6 +53,30 @@ def flatten(info: Tuple[str, tuple], params: Any, input_dim: int) -> List[dict]:
     if name == "StandardScaler":
         return [dict(kind=N.STAGE_STANDARD_SCALER, vec_a=np.atleast_1d(_f32(args[0])),
                      vec_b=np.atleast_1d(_f32(args[1])), B=0.0)]
+    if name == "Reverse":
+        return [dict(kind=N.STAGE_REVERSE)]
+    if name == "Scale":
+        (scale,) = args
+        if np.ndim(scale) != 0:
+            raise NotImplementedError("Scale with an array of scales is outside the B200 hot path")
+        return [dict(kind=N.STAGE_SCALE, B=float(scale))]
+    if name == "InvSoftplus":
+        idx = np.atleast_1d(np.asarray(args[0])).astype(np.float32)
+        k = np.atleast_1d(np.asarray(args[1] if len(args) > 1 else 1, dtype=np.float32))
+        if len(k) == 1:
+            k = np.repeat(k, len(idx))
+        if len(k) != len(idx):
+            raise ValueError("Please provide either a single sharpness or one for each column index.")
+        return [dict(kind=N.STAGE_INV_SOFTPLUS, vec_a=np.ascontiguousarray(idx), vec_b=np.ascontiguousarray(k))]
+    if name == "ColorTransform":
+        ref_idx, mag_idx = args
+        mags = np.ascontiguousarray(np.asarray(mag_idx, dtype=np.float32).ravel())
+        return [dict(kind=N.STAGE_COLOR_TRANSFORM, shift=int(ref_idx), vec_a=mags, vec_b=mags)]
+    if name == "RollingSplineCoupling":
+        full = tuple(args) + (None, 1, 16, 5, 2, 128, None, 0, False)[len(args):]
+        nlayers, shift, K, B, hl, hd, td, nc, periodic = full
+        nsc = ("NeuralSplineCoupling", (K, B, hl, hd, td, nc, periodic))
+        return flatten(("Chain", (nsc, ("Roll", (shift,))) * nlayers), params, input_dim)
     if name == "NeuralSplineCoupling":
         full = tuple(args) + (16, 5, 2, 128, None, 0, False)[len(args):]
         K, B, hidden_layers, hidden_dim, transformed_dim, n_conditions, periodic = full
@@ -98,7 +124,7 @@ class Plan:
     """One compiled chain + latent on one CUDA device."""
 
     def __init__(self, bijector_info, bijector_params, input_dim: int,
-                 latent_info=("Uniform", (None, 5)), device: Optional[int] = None):
+                 latent_info=("Uniform", (None, 5)), device: Optional[int] = None, latent_params=None):
         lib = N.lib()
         if lib.pzb_device_count() <= 0 or not torch.cuda.is_available():
             raise N.NativeError("pzflow_b200 needs a CUDA device: there is no CPU fallback")
@@ -109,6 +135,7 @@ class Plan:
             raise NotImplementedError(
                 f"latent {latent_name!r} is outside the B200 hot path (supported: {', '.join(LATENTS)})")
         latent_B = float(latent_args[1]) if len(latent_args) > 1 else 5.0
+        self._latent_name = latent_name
         stages = flatten(bijector_info, bijector_params, input_dim)
         self._keep = []  # host arrays the descriptors point into (until plan_create returns)
         descs = (N.StageDesc * max(1, len(stages)))()
@@ -135,6 +162,12 @@ class Plan:
                                     latent_B, self.device_index, C.byref(handle)))
         self._keep = []
         self._h = handle
+        if latent_name == "CentBeta":
+            if latent_params is None:
+                latent_params = tuple((0.0, 0.0) for _ in range(int(input_dim)))
+            flat = np.ascontiguousarray(np.asarray([[float(np.asarray(a)), float(np.asarray(b))]
+                                                    for a, b in latent_params], dtype=np.float32).ravel())
+            N.check(lib.pzb_plan_set_latent_params(handle, flat.ctypes.data_as(C.c_void_p), flat.size))
         self.input_dim = int(input_dim)
         self.n_conditions = lib.pzb_plan_n_conditions(handle)
         self.n_spline_dims = lib.pzb_plan_n_spline_dims(handle)

@@ -629,3 +629,87 @@ def test_err_samples_through_flow_api():
     flow2 = Flow(_dictionary=dict(d, data_error_model=lambda key, X, Xerr, n: None))
     with pytest.raises(NotImplementedError):
         flow2.log_prob(df, err_samples=2)
+
+
+# --------------------------------------------------------------------------- #
+# parameter-free bijectors and the Normal / CentBeta latents   #
+# --------------------------------------------------------------------------- #
+def test_extra_bijectors_golden_through_protocol():
+    from pzflow_b200.utils import build_bijector_from_info
+    z = golden("ref_shim_extra.npz")
+    x = z["x"]
+    cond = np.zeros((x.shape[0], 1), np.float32)
+    for name in z["names"]:
+        name = str(name)
+        info = F.unpack_tree(f"{name}_info", z)
+        params = F.unpack_tree(f"{name}_params", z)
+        init_fun, _ = build_bijector_from_info(info)
+        _, fwd, inv = init_fun(0, 7)
+        y, ld = fwd(params, x, conditions=cond)
+        xi, ldi = inv(params, y, conditions=cond)
+        xi2, ldi2 = inv(params, x, conditions=cond)
+        for got, key in ((y, "fwd"), (ld, "fwd_ld"), (xi, "inv_of_fwd"), (ldi, "inv_of_fwd_ld"), (xi2, "inv"),
+                         (ldi2, "inv_ld")):
+            want = z[f"{name}_{key}"]
+            ok = np.isfinite(want)
+            assert (np.isfinite(got) == ok).mean() > 0.99, (name, key)
+            both = ok & np.isfinite(got)
+            assert within_tol(got[both], want[both]).mean() > 0.99, (name, key, np.abs(got - want)[both].max())
+
+
+def test_normal_and_centbeta_latents():
+    z = golden("ref_shim_extra.npz")
+    from pzflow_b200.plan import Plan
+    from pzflow_b200 import distributions as Dn
+    u = z["latent_u"]
+    ident = ("Chain", (("Roll", (0,)),))   # u = x: log_prob == latent log-density
+    plan = Plan(ident, [()], 3, ("Normal", (3,)))
+    np.testing.assert_allclose(_np(plan.log_prob(torch.from_numpy(u).cuda())), z["normal_lp"], rtol=3e-6, atol=3e-6)
+    np.testing.assert_allclose(Dn.Normal(3).log_prob((), u), z["normal_lp"], rtol=3e-6, atol=3e-6)
+    cbp = tuple((float(a), float(b)) for a, b in z["centbeta_params"])
+    for params, key in ((cbp, "centbeta_lp"), (None, "centbeta_lp_default")):
+        plan = Plan(ident, [()], 3, ("CentBeta", (3, 5)), latent_params=params)
+        got, want = _np(plan.log_prob(torch.from_numpy(u).cuda())), z[key]
+        zero = ~np.isfinite(want)
+        assert (zero_class(got) == zero).all()
+        np.testing.assert_allclose(got[~zero], want[~zero], rtol=1e-5, atol=1e-5)
+        lat = Dn.CentBeta(3, 5)
+        got2 = lat.log_prob(lat._params if params is None else params, u)
+        np.testing.assert_allclose(got2[~zero], want[~zero], rtol=1e-5, atol=1e-5)
+    s = Dn.CentBeta(3, 5).sample(cbp, 50_000, seed=1)
+    assert s.shape == (50_000, 3) and np.abs(s).max() <= 5.0
+    a, b = np.exp(z["centbeta_params"][:, 0]), np.exp(z["centbeta_params"][:, 1])
+    np.testing.assert_allclose(s.mean(axis=0), 10 * (a / (a + b) - 0.5), atol=0.05)
+    n = Dn.Normal(3).sample((), 50_000, seed=1)
+    assert abs(n.mean()) < 0.02 and abs(n.std() - 1) < 0.02
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_colour_flow_chain_both_engines(engine):
+    """A flow shaped like the reference's customizing tutorial: ColorTransform -> InvSoftplus -> StandardScaler
+    -> RollingSplineCoupling (default conditioners, so the tensor-core engine takes it) -> Scale, CentBeta latent."""
+    info = ("Chain", (("ColorTransform", (3, [1, 2, 3, 4, 5, 6])), ("InvSoftplus", (0, 4.0)),
+                      ("StandardScaler", (np.linspace(-0.5, 0.5, 7).astype(np.float32),
+                                          np.linspace(0.5, 2.0, 7).astype(np.float32))),
+                      ("Reverse", ()), ("RollingSplineCoupling", (3,)), ("Scale", (0.5,))))
+    rng = np.random.default_rng(9)
+    bparams = [(), (), (), (), O.synth_bijector_params(O.expand_rolling((3,)), 7, rng, out_scale=2.0), ()]
+    lat_params = tuple((float(a), float(b)) for a, b in rng.normal(1.0, 0.4, size=(7, 2)))
+    cfg = dict(bijector_info=info, params=(lat_params, bparams), input_dim=7, latent_info=("CentBeta", (7, 5)))
+    from pzflow_b200.plan import Plan
+    plan = Plan(info, bparams, 7, cfg["latent_info"], latent_params=lat_params)
+    if engine == "tc" and not plan.tc_supported:
+        pytest.skip("tensor-core engine does not support this shape")
+    plan.set_engine(engine)
+    X = rng.uniform(0.05, 1.5, size=(4096, 7)).astype(np.float32)
+    o32 = O.flow_log_prob(info, cfg["latent_info"], cfg["params"], X)
+    got = _np(plan.log_prob(torch.from_numpy(X).cuda()))
+    ok = ~zero_class(o32) & (o32 > LP_UNDERFLOW)
+    assert (zero_class(got) == zero_class(o32)).mean() > 0.995
+    assert within_tol(got[ok], o32[ok]).mean() > 0.97
+    u, ld = plan.forward(torch.from_numpy(X).cuda())
+    xr, ldi = plan.inverse(u)
+    inside = (u.abs() < 2.4).all(dim=1).cpu().numpy() & ok
+    assert inside.mean() > 0.3
+    np.testing.assert_allclose(_np(xr)[inside], X[inside], atol=2e-4)
+    np.testing.assert_allclose(_np(ld)[inside], -_np(ldi)[inside], atol=2e-4)

@@ -55,10 +55,26 @@ def test_flatten_rejects_bad_shapes_and_foreign_bijectors():
     params = O.synth_bijector_params(info, 7, np.random.default_rng(0))
     with pytest.raises(ValueError):
         P.flatten(info, params, 9)  # weights were built for input_dim 7
+    # Shuffle draws its permutation from the jax PRNG at init time: it cannot be rebuilt without jax
     with pytest.raises(NotImplementedError):
-        P.flatten(("Reverse", ()), (), 7)
+        P.flatten(("Shuffle", ()), (), 7)
     with pytest.raises(NotImplementedError):
-        build_bijector_from_info(("InvSoftplus", (0,)))
+        build_bijector_from_info(("UniformDequantizer", (0,)))
+    # the parameter-free bijectors flatten to their own stage kinds
+    kinds = [s["kind"] for s in P.flatten(("Chain", (("Reverse", ()), ("Scale", (0.5,)), ("InvSoftplus", ([1, 3], [2.0, 12.0])),
+                                                     ("ColorTransform", (3, [1, 3, 5])))), [(), (), (), ()], 7)]
+    assert kinds == [P.N.STAGE_CHAIN_BEGIN, P.N.STAGE_REVERSE, P.N.STAGE_SCALE, P.N.STAGE_INV_SOFTPLUS,
+                     P.N.STAGE_COLOR_TRANSFORM, P.N.STAGE_CHAIN_END]
+    from pzflow_b200 import bijectors as B
+    with pytest.raises(ValueError):
+        B.ColorTransform(0, [0, 1])          # ref_idx must be positive (bijectors.py:230-231)
+    with pytest.raises(ValueError):
+        B.ColorTransform(2, [1, 3])          # ref_idx must be in mag_idx
+    with pytest.raises(ValueError):
+        B.InvSoftplus([0, 1], [1.0, 2.0, 3.0])
+    with pytest.raises(ValueError):
+        B.Scale(2)                           # scale must be a float
+    assert B.Reverse()[1] == ("Reverse", ()) and B.Scale(2.0)[1] == ("Scale", (2.0,))
 
 
 def test_constructor_validation_matches_reference():

@@ -211,3 +211,33 @@ def test_nan_and_support_go_to_zero_probability():
     lp = O.flow_log_prob(ex["bijector_info"], ex["latent_info"], ex["params"], X)
     assert zero_class(lp)[[1, 2]].all() and np.isfinite(lp[[0, 3, 4]]).all()
     assert lp[1] == np.finfo(np.float32).min  # jnp.nan_to_num(nan=-inf) then -inf -> finfo.min
+
+
+def test_extra_bijectors_and_latents_golden():
+    """ColorTransform / Reverse / Scale / InvSoftplus (and Chains of them with the
+    coupling layers) and the Normal / CentBeta latents, against what the reference's own code returned
+    (oracle/make_golden_shim.py::case_extra_bijectors)."""
+    z = golden("ref_shim_extra.npz")
+    x = z["x"]
+    cond = np.zeros((x.shape[0], 1), np.float32)
+    for name in z["names"]:
+        name = str(name)
+        info = F.unpack_tree(f"{name}_info", z)
+        params = F.unpack_tree(f"{name}_params", z)
+        with np.errstate(all="ignore"):
+            y, ld = O.apply_bijector(info, params, x, cond)
+            xi, ldi = O.apply_bijector(info, params, y, cond, inverse=True)
+            xi2, ldi2 = O.apply_bijector(info, params, x, cond, inverse=True)
+        for got, key in ((y, "fwd"), (ld, "fwd_ld"), (xi, "inv_of_fwd"), (ldi, "inv_of_fwd_ld"), (xi2, "inv"),
+                         (ldi2, "inv_ld")):
+            want = z[f"{name}_{key}"]
+            assert np.array_equal(np.isnan(got), np.isnan(want)), (name, key)
+            np.testing.assert_allclose(got, want, rtol=3e-6, atol=3e-6, err_msg=f"{name} {key}")
+    u = z["latent_u"]
+    np.testing.assert_allclose(O.latent_log_prob(("Normal", (3,)), u), z["normal_lp"], rtol=2e-6)
+    cbp = tuple((float(a), float(b)) for a, b in z["centbeta_params"])
+    for params, key in ((cbp, "centbeta_lp"), (tuple((0.0, 0.0) for _ in range(3)), "centbeta_lp_default")):
+        got, want = O.centbeta_log_prob(params, u, 5), z[key]
+        assert np.array_equal(np.isneginf(got), np.isneginf(want))
+        fin = np.isfinite(want)
+        np.testing.assert_allclose(got[fin], want[fin], rtol=3e-6, atol=3e-6)
