@@ -34,6 +34,11 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
+def _same_bits(a, b):
+    """Bit-for-bit equality (NaN == NaN: idx = K rows carry NaN through forward / inverse)."""
+    return torch.equal(a.cpu().contiguous().view(torch.int32), b.cpu().contiguous().view(torch.int32))
+
+
 # --------------------------------------------------------------------------- #
 # the shipped 7-D galaxy flow (configs 2/3): noise-floor gate + golden vectors  #
 # --------------------------------------------------------------------------- #
@@ -350,6 +355,24 @@ def test_empty_and_ragged_inputs():
         plan.log_prob(torch.zeros((4, 6)))
 
 
+def test_ragged_inputs_tc_engine():
+    """Row counts around the tensor-core engine's tile (128), tile-pair (256) and chunk (1024 rows, 148 CTAs)
+    boundaries: every prefix of a batch evaluates to the prefix of the batch's result, both directions."""
+    ex = F.example_flow()
+    plan = _plan(ex, "tc")
+    n = 148 * 1024 + 300
+    X = torch.from_numpy(F.galaxy_rows(8192, seed=4, oob_frac=0)).cuda().repeat(n // 8192 + 1, 1)[:n].contiguous()
+    full = plan.log_prob(X)
+    u_full, ld_full = plan.forward(X)
+    for m in (1, 2, 127, 128, 129, 255, 256, 257, 1023, 1024, 1025, 148 * 1024 - 1, 148 * 1024 + 1):
+        assert _same_bits(plan.log_prob(X[:m]), full[:m]), m
+        u, ld = plan.forward(X[:m])
+        assert _same_bits(u, u_full[:m]) and _same_bits(ld, ld_full[:m]), m
+    xr, _ = plan.inverse(u_full[:1000])
+    assert _same_bits(plan.inverse(u_full[:300])[0], xr[:300])
+    assert plan.log_prob(X[:0]).shape == (0,)
+
+
 # --------------------------------------------------------------------------- #
 # BASELINE.json sizes: size-independent properties                             #
 # --------------------------------------------------------------------------- #
@@ -434,11 +457,6 @@ def test_uniform_sampler():
 # --------------------------------------------------------------------------- #
 # host-buffer entry points (pzb_*_host): chunked H2D | kernel | D2H pipeline    #
 # --------------------------------------------------------------------------- #
-def _same_bits(a, b):
-    """Bit-for-bit equality (NaN == NaN: idx = K rows carry NaN through forward / inverse)."""
-    return torch.equal(a.cpu().contiguous().view(torch.int32), b.cpu().contiguous().view(torch.int32))
-
-
 @pytest.mark.parametrize("pinned", [True, False])
 def test_host_pipeline_equals_device_path(pinned):
     """Several pipeline chunks (3.7 M rows > 3 x 1.2 M), ragged tail, pinned and pageable host
