@@ -8,8 +8,8 @@ kernel per call via the C-ABI (``pzflow_b200.plan.Plan``).  There is no CPU
 path: without a CUDA device every evaluation raises.
 
 ``err_samples`` (Gaussian error convolution, flow.py:339-395) is fused too: the samples are
-drawn inside the kernel from a counter-based stream.  Out of scope here:
-``train`` raises NotImplementedError.
+drawn inside the kernel from a counter-based stream.  ``train`` lives in
+``pzflow_b200/train.py``.
 """
 from __future__ import annotations
 
@@ -399,7 +399,18 @@ class Flow:
         with open(file, "wb") as handle:
             pickle.dump(save_dict, handle, recurse=True)
 
-    def train(self, *args, **kwargs):
-        """Training (pzflow/flow.py:868-1159) is outside the B200 hot path."""
-        raise NotImplementedError("Flow.train is outside the B200 inference hot path; "
-                                  "train with pzflow and load the saved flow here")
+    def train(self, inputs: pd.DataFrame, val_set: pd.DataFrame = None, train_weight: np.ndarray = None,
+              val_weight: np.ndarray = None, epochs: int = 100, batch_size: int = 1024, optimizer: Callable = None,
+              loss_fn: Callable = None, convolve_errs: bool = False, patience: int = None,
+              best_params: bool = True, seed: int = 0, verbose: bool = False, progress_bar: bool = False,
+              initial_loss: bool = True) -> list:
+        """Trains the normalizing flow on the provided inputs (pzflow/flow.py:868-1159).
+
+        The optional data-parallel training step of SURVEY.md §8f-4: gradients by torch autograd on the GPU
+        (a library-level baseline, see pzflow_b200/train.py), every reported loss by the fused CUDA kernels,
+        one all_reduce of the flat gradient per step when torch.distributed is initialised."""
+        from .train import train_flow
+        return train_flow(self, inputs, val_set=val_set, train_weight=train_weight, val_weight=val_weight,
+                          epochs=epochs, batch_size=batch_size, optimizer=optimizer, loss_fn=loss_fn,
+                          convolve_errs=convolve_errs, patience=patience, best_params=best_params, seed=seed,
+                          verbose=verbose, progress_bar=progress_bar, initial_loss=initial_loss)

@@ -168,6 +168,21 @@ class FlowEnsemble:
         with open(file, "wb") as handle:
             pickle.dump(save_dict, handle, recurse=True)
 
-    def train(self, *args, **kwargs):
-        """Training (pzflow/flowEnsemble.py:507-609) is outside the B200 hot path."""
-        raise NotImplementedError("FlowEnsemble.train is outside the B200 inference hot path")
+    def train(self, inputs: pd.DataFrame, val_set: pd.DataFrame = None, train_weight: np.ndarray = None,
+              val_weight: np.ndarray = None, epochs: int = 50, batch_size: int = 1024, optimizer=None, loss_fn=None,
+              convolve_errs: bool = False, patience: int = None, best_params: bool = True, seed: int = 0,
+              verbose: bool = False, progress_bar: bool = False, initial_loss: bool = True) -> dict:
+        """Trains the normalizing flows on the provided inputs (pzflow/flowEnsemble.py:507-609):
+        one seed per flow, dictionary of per-flow losses."""
+        rng = np.random.default_rng(seed)
+        seeds = rng.integers(1e9, size=len(self._ensemble))
+        loss_dict = dict()
+        for i, (name, flow) in enumerate(self._ensemble.items()):
+            if verbose:
+                print(name)
+            loss_dict[name] = flow.train(inputs=inputs, val_set=val_set, train_weight=train_weight,
+                                         val_weight=val_weight, epochs=epochs, batch_size=batch_size,
+                                         optimizer=optimizer, loss_fn=loss_fn, convolve_errs=convolve_errs,
+                                         patience=patience, best_params=best_params, seed=int(seeds[i]),
+                                         verbose=verbose, progress_bar=progress_bar, initial_loss=initial_loss)
+        return loss_dict

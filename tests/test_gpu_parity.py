@@ -731,3 +731,45 @@ def test_colour_flow_chain_both_engines(engine):
     assert inside.mean() > 0.3
     np.testing.assert_allclose(_np(xr)[inside], X[inside], atol=2e-4)
     np.testing.assert_allclose(_np(ld)[inside], -_np(ldi)[inside], atol=2e-4)
+
+
+# --------------------------------------------------------------------------- #
+# Flow.train (torch-autograd step, fused-kernel losses)         #
+# --------------------------------------------------------------------------- #
+def _two_moons(n, seed):
+    rng = np.random.default_rng(seed)
+    t = rng.uniform(0, np.pi, n)
+    up = rng.random(n) < 0.5
+    x = np.where(up, np.cos(t), 1 - np.cos(t)) + rng.normal(0, 0.06, n)
+    y = np.where(up, np.sin(t), 0.5 - np.sin(t)) + rng.normal(0, 0.06, n)
+    return pd.DataFrame({"x": x, "y": y})
+
+
+def test_flow_train_reduces_the_loss_and_feeds_the_fused_kernels():
+    from pzflow_b200 import Flow, FlowEnsemble
+    from pzflow_b200.train import TorchChain
+    data, val = _two_moons(6000, 0), _two_moons(1500, 1)
+    flow = Flow(data_columns=("x", "y"))
+    losses, val_losses = flow.train(data, val_set=val, epochs=6, seed=0)
+    assert len(losses) == 7 and len(val_losses) == 7 and all(np.isfinite(losses))
+    assert losses[-1] < losses[0] - 0.5 and val_losses[-1] < val_losses[0] - 0.5
+    assert flow._bijector_info[0] == "Chain" and flow._bijector_info[1][0][0] == "ShiftBounds"   # default bijector
+    # the parameters training left behind are what the fused kernels evaluate: same log_prob as the
+    # differentiable restatement, and a loss equal to the last reported one (best_params keeps the best epoch)
+    lp = flow.log_prob(data)
+    chain = TorchChain(flow._bijector_info, flow._params[1], flow._latent_info, flow._params[0], 2,
+                       torch.device("cuda"))
+    want = chain.log_prob(torch.from_numpy(data.to_numpy().astype(np.float32)).cuda()).detach().cpu().numpy()
+    fin = np.isfinite(want) & (want > LP_UNDERFLOW)
+    assert within_tol(lp[fin], want[fin]).mean() > 0.99
+    assert abs(-lp[fin].mean() - min(losses)) < 0.05
+    # samples of the trained flow land on the moons
+    s = flow.sample(4000, seed=3)
+    assert s.shape == (4000, 2) and abs(s["x"].mean() - data["x"].mean()) < 0.1
+    # early stopping and argument checks (flow.py:944-946, 1113-1134)
+    with pytest.raises(ValueError):
+        flow.train(data, epochs=0)
+    ens = FlowEnsemble(data_columns=("x", "y"), N=2)
+    out = ens.train(data[:2000], epochs=2, seed=1)
+    assert sorted(out) == ["Flow 0", "Flow 1"] and all(len(v) == 3 for v in out.values())
+    assert ens.log_prob(data[:100]).shape == (100,)
