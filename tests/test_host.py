@@ -101,8 +101,14 @@ def test_constructor_validation_matches_reference():
     with pytest.raises(ValueError):
         FlowEnsemble()
     assert flow.latent.info == ("CentBeta13", (2, 5))  # default latent, flow.py:221-222
-    with pytest.raises(NotImplementedError):
-        flow.train(pd.DataFrame({"x": [0.0], "y": [0.0]}))
+    # training needs the GPU like everything else: no CPU fallback (and no jax callables)
+    from pzflow_b200._native import NativeError
+    with pytest.raises((NativeError, NotImplementedError)):
+        flow.train(pd.DataFrame({"x": [0.0], "y": [0.0]}), loss_fn=lambda *a: 0.0)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(NativeError):
+            flow.train(pd.DataFrame({"x": [0.0], "y": [0.0]}))
 
 
 def test_sample_argument_validation():
