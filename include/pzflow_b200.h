@@ -67,8 +67,20 @@ typedef enum {
   PZB_LATENT_UNIFORM = 1,    /* pzflow/distributions.py:395-470 */
   PZB_LATENT_CENTBETA13 = 2, /* pzflow/distributions.py:137-229 */
   PZB_LATENT_NORMAL = 3,     /* pzflow/distributions.py:232-303 (B unused) */
-  PZB_LATENT_CENTBETA = 4    /* pzflow/distributions.py:45-135: per-dimension alpha, beta via pzb_plan_set_latent_params */
+  PZB_LATENT_CENTBETA = 4,   /* pzflow/distributions.py:45-135: alpha = beta = 1 until pzb_plan_set_latent     */
+  PZB_LATENT_TDIST = 5,      /* pzflow/distributions.py:306-392: nu = 30 until pzb_plan_set_latent (B unused)  */
+  PZB_LATENT_JOINT = 6       /* pzflow/distributions.py:473-562: segments via pzb_plan_set_latent (required)   */
 } pzb_latent_kind;
+
+/* One latent distribution over `dim` consecutive columns.  params: HOST floats in the reference's pytree order --
+ * CentBeta ((log a_1, log b_1), ...) flattened to 2 * dim values, Tdist log(nu) -- or NULL for the defaults. */
+typedef struct {
+  int32_t kind; /* pzb_latent_kind, not JOINT */
+  int32_t dim;
+  float B;
+  const float *params;
+  int32_t n_params;
+} pzb_latent_desc;
 
 /* Conditioner evaluation engines. */
 typedef enum {
@@ -126,10 +138,10 @@ int pzb_device_count(void);
 int pzb_plan_create(const pzb_stage_desc *stages, int32_t n_stages, int32_t input_dim,
                     int32_t latent_kind, float latent_B, int32_t device, pzb_plan **out);
 
-/* CentBeta only: the latent's parameter pytree ((log a_1, log b_1), ..., (log a_D, log b_D))
- * (pzflow/distributions.py:70-99) flattened to 2 * D HOST floats.  Part of plan construction: call once,
- * right after pzb_plan_create, before the first evaluation. */
-int pzb_plan_set_latent_params(pzb_plan *plan, const float *log_ab, int32_t n);
+/* Latent distributions with parameters, and Joint: the latent as a list of segments over consecutive columns
+ * (one segment for CentBeta / Tdist with learned parameters, several for Joint; the dims must add up to
+ * input_dim).  Part of plan construction: call right after pzb_plan_create, before the first evaluation. */
+int pzb_plan_set_latent(pzb_plan *plan, const pzb_latent_desc *segs, int32_t n_segs);
 
 void pzb_plan_destroy(pzb_plan *plan);
 

@@ -160,6 +160,14 @@ def case_extra_bijectors(pzflow):
     store["centbeta_params"] = np.asarray(cb_params, np.float32)
     store["centbeta_lp"] = _np(cb.log_prob(cb_params, jnp.array(u)))
     store["centbeta_lp_default"] = _np(cb.log_prob(cb._params, jnp.array(u)))
+    td = Dn.Tdist(3)
+    store["tdist_lp_default"] = _np(td.log_prob(td._params, jnp.array(u)))
+    store["tdist_lognu"] = np.float32(np.log(4.5))
+    store["tdist_lp"] = _np(td.log_prob(jnp.log(jnp.array(4.5)), jnp.array(u)))
+    joint = Dn.Joint(Dn.Uniform(1, 5), Dn.CentBeta(1, 5), Dn.Normal(1))
+    jp = [(), (cb_params[0],), ()]
+    store["joint_lp"] = _np(joint.log_prob(jp, jnp.array(u)))
+    F.pack_tree("joint_info", joint.info, store)
     _save("extra", store)
 
 

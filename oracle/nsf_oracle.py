@@ -386,6 +386,42 @@ def latent_log_prob(latent_info, u):
     raise NotImplementedError(f"oracle: latent {name!r} is outside the hot path")
 
 
+def tdist_log_prob(log_nu, u):
+    """distributions.py:330-358 with cov = identity: maha = sum(u^2), log_det = 0."""
+    from scipy import special as sps
+    dt = u.dtype.type
+    n = u.shape[1]
+    nu = np.exp(dt(log_nu))
+    maha = (u * u).sum(axis=1, dtype=u.dtype)
+    t = dt(0.5) * (nu + dt(n))
+    A = dt(sps.gammaln(t))
+    Bc = dt(sps.gammaln(dt(0.5) * nu))
+    Cc = dt(n / 2.0) * np.log(nu * dt(np.pi))
+    E = -t * np.log(dt(1) + (dt(1.0) / nu) * maha)
+    return ((A - Bc) - Cc - dt(0)) + E
+
+
+def joint_log_prob(latent_info, latent_params, u):
+    """distributions.py:528-541: split the columns, sum the sub-distributions' log-probs."""
+    infos = latent_info[1][1]
+    dims = [int(i[1][0]) for i in infos]
+    parts = np.split(u, np.cumsum(dims)[:-1], axis=1)
+    cols = [any_latent_log_prob(tuple(infos[i]), latent_params[i], parts[i]).reshape(-1, 1) for i in range(len(infos))]
+    return np.hstack(cols).sum(axis=1, dtype=u.dtype)
+
+
+def any_latent_log_prob(latent_info, latent_params, u):
+    name = latent_info[0]
+    with np.errstate(all="ignore"):
+        if name == "CentBeta":
+            return centbeta_log_prob(latent_params, u, latent_info[1][1])
+        if name == "Tdist":
+            return tdist_log_prob(latent_params, u)
+        if name == "Joint":
+            return joint_log_prob(latent_info, latent_params, u)
+        return latent_log_prob(latent_info, u)
+
+
 def centbeta_log_prob(latent_params, u, B):
     """distributions.py:70-99 -- sum_i beta.logpdf(u_i; exp(p_i0), exp(p_i1), loc=-B, scale=2B), with
     jax.scipy.stats.beta.logpdf = -betaln(a, b) + xlogy(a-1, y) + xlog1py(b-1, -y) - log(scale)."""
@@ -417,10 +453,7 @@ def flow_log_prob(bijector_info, latent_info, params, X, conditions=None, bins=N
         conditions = np.zeros((X.shape[0], 1), dtype=X.dtype)  # flow.py:329
     with np.errstate(all="ignore"):
         u, log_det = apply_bijector(bijector_info, params[1], X, conditions, False, bins)
-        if latent_info[0] == "CentBeta":
-            lat = centbeta_log_prob(params[0], u, latent_info[1][1])
-        else:
-            lat = latent_log_prob(latent_info, u)
+        lat = any_latent_log_prob(latent_info, params[0], u)
         lp = lat + log_det
     return _nan_to_num(lp.astype(X.dtype), nan=-np.inf)
 

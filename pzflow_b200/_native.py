@@ -32,6 +32,8 @@ LATENT_UNIFORM = 1
 LATENT_CENTBETA13 = 2
 LATENT_NORMAL = 3
 LATENT_CENTBETA = 4
+LATENT_TDIST = 5
+LATENT_JOINT = 6
 
 ENGINE_AUTO = 0
 ENGINE_SIMT = 1
@@ -60,6 +62,13 @@ class StageDesc(C.Structure):
     ]
 
 
+class LatentDesc(C.Structure):
+    """pzb_latent_desc."""
+
+    _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("B", C.c_float), ("params", c_float_p),
+                ("n_params", C.c_int32)]
+
+
 # every symbol include/pzflow_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "pzb_abi_version": (C.c_int, []),
@@ -67,7 +76,7 @@ SIGNATURES = {
     "pzb_device_count": (C.c_int, []),
     "pzb_plan_create": (C.c_int, [C.POINTER(StageDesc), C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                   C.c_int32, C.POINTER(C.c_void_p)]),
-    "pzb_plan_set_latent_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "pzb_plan_set_latent": (C.c_int, [C.c_void_p, C.POINTER(LatentDesc), C.c_int32]),
     "pzb_plan_destroy": (None, [C.c_void_p]),
     "pzb_plan_input_dim": (C.c_int, [C.c_void_p]),
     "pzb_plan_n_conditions": (C.c_int, [C.c_void_p]),

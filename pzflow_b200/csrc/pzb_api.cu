@@ -70,8 +70,66 @@ struct pzb_plan {
   double flops_per_row = 0.0;
   bool tc_ok = false;
   int engine = PZB_ENGINE_AUTO;
+  bool latent_ready = true;
   mutable HostPipe pipe;
 };
+
+// pzflow/distributions.py: every latent of the path as segments of the plan (host copy; caller uploads)
+static int fill_latent(PlanDev& hp, const pzb_latent_desc* segs, int n_segs) {
+  if (segs == nullptr || n_segs < 1 || n_segs > MAX_LAT)
+    return fail(PZB_ERR_UNSUPPORTED, "latent: between 1 and %d segments are supported", MAX_LAT);
+  int start = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    const pzb_latent_desc& d = segs[i];
+    LatentSeg& sg = hp.lat[i];
+    memset(&sg, 0, sizeof(sg));
+    sg.kind = d.kind;
+    sg.start = start;
+    sg.n = d.dim;
+    sg.B = d.B;
+    if (d.dim < 1 || start + d.dim > hp.D) return fail(PZB_ERR_INVALID, "latent: segment %d does not fit input_dim %d", i, hp.D);
+    switch (d.kind) {
+      case PZB_LATENT_UNIFORM:
+        sg.c0 = (float)(-d.dim) * logf(2.0f * d.B);  // -input_dim * log(2B)
+        break;
+      case PZB_LATENT_CENTBETA13: {
+        const float g13 = (float)lgamma(13.0), g26 = (float)lgamma(26.0);
+        sg.c0 = (g13 + g13) - g26;
+        break;
+      }
+      case PZB_LATENT_NORMAL:
+        break;
+      case PZB_LATENT_CENTBETA: {
+        if (d.params != nullptr && d.n_params != 2 * d.dim)
+          return fail(PZB_ERR_INVALID, "latent: CentBeta segment %d expects %d parameters", i, 2 * d.dim);
+        for (int j = 0; j < d.dim; ++j) {
+          // a = exp(params[i][0]), b = exp(params[i][1]); default (0, 0) (distributions.py:66, 84-85)
+          const float a = d.params ? expf(d.params[2 * j]) : 1.0f, b = d.params ? expf(d.params[2 * j + 1]) : 1.0f;
+          hp.latent_a[start + j] = a;
+          hp.latent_b[start + j] = b;
+          hp.latent_betaln[start + j] =
+              ((float)lgamma((double)a) + (float)lgamma((double)b)) - (float)lgamma((double)a + (double)b);
+        }
+        break;
+      }
+      case PZB_LATENT_TDIST: {
+        if (d.params != nullptr && d.n_params != 1) return fail(PZB_ERR_INVALID, "latent: Tdist expects one parameter (log nu)");
+        const float nu = d.params ? expf(d.params[0]) : 30.0f;  // default log(30) (distributions.py:326)
+        const float t = 0.5f * (nu + (float)d.dim);
+        sg.c0 = ((float)lgamma((double)t) - (float)lgamma(0.5 * (double)nu)) - ((float)d.dim / 2.0f) * logf(nu * 3.14159265358979323846f);
+        sg.c1 = t;
+        sg.c2 = 1.0f / nu;
+        break;
+      }
+      default:
+        return fail(PZB_ERR_UNSUPPORTED, "latent: kind %d cannot be a segment", d.kind);
+    }
+    start += d.dim;
+  }
+  if (start != hp.D) return fail(PZB_ERR_INVALID, "latent: segments cover %d of %d dimensions", start, hp.D);
+  hp.n_lat = n_segs;
+  return PZB_OK;
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -113,7 +171,7 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
   const int D = input_dim;
   if (D < 1 || D > MAX_D)
     return fail(PZB_ERR_UNSUPPORTED, "plan_create: input_dim %d outside [1, %d]", D, MAX_D);
-  if (latent_kind < PZB_LATENT_UNIFORM || latent_kind > PZB_LATENT_CENTBETA)
+  if (latent_kind < PZB_LATENT_UNIFORM || latent_kind > PZB_LATENT_JOINT)
     return fail(PZB_ERR_UNSUPPORTED, "plan_create: latent kind %d is outside the hot path", latent_kind);
   if (pzb_device_count() <= 0)
     return fail(PZB_ERR_NO_DEVICE, "plan_create: no CUDA device (this library has no CPU fallback)");
@@ -126,11 +184,20 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
   hp.C = 0;
   hp.latent_kind = latent_kind;
   hp.latent_B = latent_B;
-  if (latent_kind == PZB_LATENT_UNIFORM) {
-    hp.latent_const = (float)(-D) * logf(2.0f * latent_B);  // -input_dim * log(2B)
-  } else {
-    const float g13 = (float)lgamma(13.0), g26 = (float)lgamma(26.0);
-    hp.latent_const = (g13 + g13) - g26;
+  {
+    // one default segment over all D dimensions (a Joint latent gets its segments from pzb_plan_set_latent)
+    pzb_latent_desc one{};
+    one.kind = latent_kind == PZB_LATENT_JOINT ? PZB_LATENT_UNIFORM : latent_kind;
+    one.dim = D;
+    one.B = latent_B;
+    one.params = nullptr;
+    one.n_params = 0;
+    int lrc = fill_latent(hp, &one, 1);
+    if (lrc != PZB_OK) {
+      delete plan;
+      return lrc;
+    }
+    plan->latent_ready = latent_kind != PZB_LATENT_JOINT;
   }
 
   // ---- pass 1: flatten, fold Roll into permutations, size the weight blob ----
@@ -481,21 +548,15 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
   return PZB_OK;
 }
 
-int pzb_plan_set_latent_params(pzb_plan* plan, const float* log_ab, int32_t n) {
-  if (!plan) return fail(PZB_ERR_INVALID, "set_latent_params: plan is NULL");
+int pzb_plan_set_latent(pzb_plan* plan, const pzb_latent_desc* segs, int32_t n_segs) {
+  if (!plan) return fail(PZB_ERR_INVALID, "set_latent: plan is NULL");
   PlanDev& hp = plan->host;
-  if (hp.latent_kind != PZB_LATENT_CENTBETA)
-    return fail(PZB_ERR_INVALID, "set_latent_params: this plan's latent has no parameters");
-  if (log_ab == nullptr || n != 2 * hp.D) return fail(PZB_ERR_INVALID, "set_latent_params: expected %d values", 2 * hp.D);
-  for (int j = 0; j < hp.D; ++j) {
-    const float a = expf(log_ab[2 * j]), b = expf(log_ab[2 * j + 1]);  // jnp.exp(params[i][0/1])
-    hp.latent_a[j] = a;
-    hp.latent_b[j] = b;
-    hp.latent_betaln[j] = ((float)lgamma((double)a) + (float)lgamma((double)b)) - (float)lgamma((double)a + (double)b);
-  }
+  int rc = fill_latent(hp, segs, n_segs);
+  if (rc != PZB_OK) return rc;
   DeviceGuard guard(plan->device);
   cudaError_t ce = cudaMemcpy(plan->d_plan, &hp, sizeof(PlanDev), cudaMemcpyHostToDevice);
-  if (ce != cudaSuccess) return cuda_fail(ce, "set_latent_params upload");
+  if (ce != cudaSuccess) return cuda_fail(ce, "set_latent upload");
+  plan->latent_ready = true;
   return PZB_OK;
 }
 
@@ -550,6 +611,8 @@ int pzb_plan_engine(const pzb_plan* plan) {
 
 static int launch_chain(const pzb_plan* plan, const LaunchArgs& args, void* stream) {
   if (args.N == 0) return PZB_OK;
+  if (!plan->latent_ready && (args.mode == MODE_LOGPROB || args.mode == MODE_POSTERIOR))
+    return fail(PZB_ERR_INVALID, "this plan has a Joint latent: call pzb_plan_set_latent before evaluating densities");
   DeviceGuard guard(plan->device);
   if (!guard.ok) return fail(PZB_ERR_CUDA, "cannot select device %d", plan->device);
   cudaError_t ce;

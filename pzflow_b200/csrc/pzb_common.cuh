@@ -72,6 +72,15 @@ struct StepDev {
   int kind, idx;
 };
 
+constexpr int MAX_LAT = 8;
+// kind: 1 Uniform, 2 CentBeta13, 3 Normal, 4 CentBeta, 5 Tdist.  c0/c1/c2 are per-kind constants:
+//   Uniform: c0 = -n log(2B); CentBeta13: c0 = betaln(13, 13); Tdist: c0 = gammaln(t) - gammaln(nu/2) - n/2 log(nu pi),
+//   c1 = t = (nu + n)/2, c2 = 1/nu (pzflow/distributions.py:330-358 with cov = I).
+struct LatentSeg {
+  int kind, start, n;
+  float B, c0, c1, c2;
+};
+
 struct PlanDev {
   int D, C, n_steps, n_nsc, n_affine, latent_kind, n_spline_dims;
   float latent_B;
@@ -79,6 +88,10 @@ struct PlanDev {
   int16_t perm_final[MAX_D];
   // CentBeta (pzflow/distributions.py:45-135): per logical dimension alpha, beta and betaln(alpha, beta)
   float latent_a[MAX_D], latent_b[MAX_D], latent_betaln[MAX_D];
+  // The latent as a list of segments over consecutive logical dimensions: one segment for the plain latents,
+  // several for Joint (pzflow/distributions.py:473-562).
+  int n_lat;
+  LatentSeg lat[MAX_LAT];
   int n_color;
   ColorDev color[MAX_COLOR];
   StepDev steps[MAX_STEPS];
@@ -303,46 +316,59 @@ __device__ __forceinline__ void pz_rqs_eval(const SplineKnotSel& s, float x, flo
   }
 }
 
-// Latent log-density of one row given u in LOGICAL column order through get(j).
+// Latent log-density of one row given u in LOGICAL column order through get(j): the sum over the latent's
+// segments (Joint: pzflow/distributions.py:528-541; every other latent is a single segment).
 template <typename GetU>
 __device__ __forceinline__ float pz_latent_logprob(const PlanDev* plan, GetU get) {
-  const int latent_kind = plan->latent_kind, D = plan->D;
-  const float B = plan->latent_B;
-  if (latent_kind == 1) {  // Uniform, pzflow/distributions.py:414-441
-    bool inside = true;
-    for (int j = 0; j < D; ++j) {
-      const float u = get(j);
-      inside = inside && (u >= -B) && (u <= B);
+  float total = 0.0f;
+  for (int si = 0; si < plan->n_lat; ++si) {
+    const LatentSeg sg = plan->lat[si];
+    const float B = sg.B;
+    float lp;
+    if (sg.kind == 1) {  // Uniform, pzflow/distributions.py:414-441
+      bool inside = true;
+      for (int j = sg.start; j < sg.start + sg.n; ++j) {
+        const float u = get(j);
+        inside = inside && (u >= -B) && (u <= B);
+      }
+      lp = inside ? sg.c0 : -INFINITY;
+    } else if (sg.kind == 3) {  // Normal, pzflow/distributions.py:255-275: multivariate_normal.logpdf(u, 0, I)
+      float ss = 0.0f;
+      for (int j = sg.start; j < sg.start + sg.n; ++j) {
+        const float u = get(j);
+        ss += u * u;
+      }
+      lp = -0.5f * ((float)sg.n * 1.8378770664093453f + ss);
+    } else if (sg.kind == 5) {  // Tdist, pzflow/distributions.py:330-358 (cov = I: maha = |u|^2, log_det = 0)
+      float ss = 0.0f;
+      for (int j = sg.start; j < sg.start + sg.n; ++j) {
+        const float u = get(j);
+        ss += u * u;
+      }
+      lp = sg.c0 + (-sg.c1) * logf(1.0f + sg.c2 * ss);
+    } else {
+      // CentBeta13 (distributions.py:165-194) / CentBeta (45-99): sum_i beta.logpdf(u_i; a_i, b_i, loc=-B, scale=2B)
+      //   = -betaln(a, b) + xlogy(a - 1, y) + xlog1py(b - 1, -y) - log(scale),  y = (u + B) / 2B
+      const bool general = sg.kind == 4;
+      const float loc = -B, scale = 2.0f * B;
+      const float lscale = logf(scale);
+      lp = 0.0f;
+      for (int j = sg.start; j < sg.start + sg.n; ++j) {
+        const float u = get(j);
+        const float y = (u - loc) / scale;
+        const float am1 = general ? plan->latent_a[j] - 1.0f : 12.0f, bm1 = general ? plan->latent_b[j] - 1.0f : 12.0f;
+        const float betaln = general ? plan->latent_betaln[j] : sg.c0;
+        // xlogy(0, .) = 0 (scipy semantics), only reachable for the general form
+        const float t1 = (general && am1 == 0.0f) ? 0.0f : am1 * logf(y);
+        const float t2 = (general && bm1 == 0.0f) ? 0.0f : bm1 * log1pf(-y);
+        float l1 = ((-betaln) + (t1 + t2)) - lscale;
+        if (u > loc + scale || u < loc) l1 = -INFINITY;
+        lp += l1;
+      }
     }
-    return inside ? plan->latent_const : -INFINITY;
+    total = (si == 0) ? lp : total + lp;
   }
-  if (latent_kind == 3) {  // Normal, pzflow/distributions.py:255-275: multivariate_normal.logpdf(u, 0, I)
-    float ss = 0.0f;
-    for (int j = 0; j < D; ++j) {
-      const float u = get(j);
-      ss += u * u;
-    }
-    return -0.5f * ((float)D * 1.8378770664093453f + ss);
-  }
-  // CentBeta13 (distributions.py:165-194) / CentBeta (45-99): sum_i beta.logpdf(u_i; a_i, b_i, loc=-B, scale=2B)
-  //   = -betaln(a, b) + xlogy(a - 1, y) + xlog1py(b - 1, -y) - log(scale),  y = (u + B) / 2B
-  const bool general = latent_kind == 4;
-  const float loc = -B, scale = 2.0f * B;
-  const float lscale = logf(scale);
-  float acc = 0.0f;
-  for (int j = 0; j < D; ++j) {
-    const float u = get(j);
-    const float y = (u - loc) / scale;
-    const float am1 = general ? plan->latent_a[j] - 1.0f : 12.0f, bm1 = general ? plan->latent_b[j] - 1.0f : 12.0f;
-    const float betaln = general ? plan->latent_betaln[j] : plan->latent_const;
-    // xlogy(0, .) = 0 (scipy semantics), only reachable for the general form
-    const float t1 = (general && am1 == 0.0f) ? 0.0f : am1 * logf(y);
-    const float t2 = (general && bm1 == 0.0f) ? 0.0f : bm1 * log1pf(-y);
-    float lp = ((-betaln) + (t1 + t2)) - lscale;
-    if (u > loc + scale || u < loc) lp = -INFINITY;
-    acc += lp;
-  }
-  return acc;
+  return total;
 }
 
 }  // namespace pzb

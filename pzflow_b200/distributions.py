@@ -1,11 +1,11 @@
-"""Latent distributions of the hot path: Uniform, CentBeta13, and Normal and CentBeta.
+"""Latent distributions of the hot path: Uniform, CentBeta13, and Normal, CentBeta, Tdist, Joint.
 
 Mirrors pzflow/distributions.py (LatentDist 17-30, CentBeta 45-135, CentBeta13 137-229, Normal
 232-303, Uniform 395-470): same constructors, ``info`` tuples and ``_params``.  Inside
 ``Flow._log_prob`` the latent log-density is the tail of the fused chain
 kernel; the stand-alone ``log_prob`` / ``sample`` below are the thin device
 versions of the reference methods (they are not on the hot path).
-Tdist and Joint are out of scope.
+All of the reference's latents are covered (Tdist 306-392 and Joint 473-562 included).
 """
 from __future__ import annotations
 
@@ -167,4 +167,68 @@ class CentBeta(LatentDist):
 
     def sample(self, params: Pytree, nsamples: int, seed: int = None):
         """[nsamples, input_dim] draws, 2B(Beta(a_i, b_i) - 0.5) (distributions.py:101-135)."""
+        return self.sample_device(nsamples, seed, params).cpu().numpy()
+
+
+class Tdist(LatentDist):
+    """A multivariate T distribution with mean zero, unit scale matrix and learned degrees of freedom."""
+
+    def __init__(self, input_dim: int) -> None:
+        self.input_dim = input_dim
+        self._params = float(np.log(np.float32(30.0)))
+        self.info = ("Tdist", (input_dim,))
+
+    def log_prob(self, params: Pytree, inputs):
+        """distributions.py:330-358 with cov = I (maha = |u|^2, log_det = 0)."""
+        u = torch.as_tensor(inputs).to(_device(), torch.float32)
+        nu = math.exp(float(np.asarray(params)))
+        t = 0.5 * (nu + self.input_dim)
+        out = (math.lgamma(t) - math.lgamma(0.5 * nu) - self.input_dim / 2.0 * math.log(nu * math.pi)
+               - t * torch.log(1 + (1.0 / nu) * (u * u).sum(dim=1)))
+        return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
+
+    def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None) -> torch.Tensor:
+        """mean + z / sqrt(chi2(nu) / nu) (distributions.py:360-392)."""
+        nu = math.exp(float(np.asarray(self._params if params is None else params)))
+        gen = torch.Generator(device=_device())
+        gen.manual_seed(_seed(seed) % (2 ** 63))
+        z = torch.randn((nsamples, self.input_dim), generator=gen, device=_device())
+        chi2 = 2.0 * torch._standard_gamma(torch.full((nsamples,), nu / 2.0, device=_device()), generator=gen)
+        return z / torch.sqrt(chi2 / nu)[:, None]
+
+    def sample(self, params: Pytree, nsamples: int, seed: int = None):
+        return self.sample_device(nsamples, seed, params).cpu().numpy()
+
+
+class Joint(LatentDist):
+    """A joint distribution built from other distributions over consecutive columns (distributions.py:473-562)."""
+
+    def __init__(self, *inputs) -> None:
+        if inputs[0] == "Joint info":
+            self.dists = [globals()[dist[0]](*dist[1]) for dist in inputs[1]]
+        else:
+            self.dists = inputs
+        self._params = [dist._params for dist in self.dists]
+        self.input_dim = sum([dist.input_dim for dist in self.dists])
+        self.info = ("Joint", ("Joint info", [dist.info for dist in self.dists]))
+        self._splits = np.cumsum([dist.input_dim for dist in self.dists])[:-1]
+
+    def log_prob(self, params: Pytree, inputs):
+        u = torch.as_tensor(inputs).to(_device(), torch.float32)
+        parts = torch.tensor_split(u, [int(i) for i in self._splits], dim=1)
+        out = torch.stack([self.dists[i].log_prob(params[i], parts[i]) for i in range(len(self.dists))], dim=1).sum(dim=1)
+        return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
+
+    def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None) -> torch.Tensor:
+        params = self._params if params is None else params
+        seeds = np.random.default_rng(_seed(seed)).integers(0, int(1e9), size=len(self.dists))
+        cols = []
+        for dist, p, sd in zip(self.dists, params, seeds):
+            if isinstance(dist, (CentBeta, Tdist, Joint)):
+                cols.append(dist.sample_device(nsamples, int(sd), p).reshape(nsamples, -1))
+            else:
+                cols.append(dist.sample_device(nsamples, int(sd)).reshape(nsamples, -1))
+        return torch.cat(cols, dim=1).contiguous()
+
+    def sample(self, params: Pytree, nsamples: int, seed: int = None):
         return self.sample_device(nsamples, seed, params).cpu().numpy()

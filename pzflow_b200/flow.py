@@ -363,8 +363,8 @@ class Flow:
             n = cond.shape[0]
 
         plan = self._plan()
-        if isinstance(self.latent, distributions.CentBeta):  # the only latent with parameters on this path
-            u = self.latent.sample_device(n, seed, self._params[0])
+        if isinstance(self.latent, (distributions.CentBeta, distributions.Tdist, distributions.Joint)):
+            u = self.latent.sample_device(n, seed, self._params[0])  # latents with parameters
         else:
             u = self.latent.sample_device(n, seed)  # draws stay on the device
         x = plan.inverse(u, cond, want_log_det=False)[0].cpu().numpy()

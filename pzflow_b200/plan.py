@@ -20,7 +20,31 @@ from . import _native as N
 HOT_PATH_BIJECTORS = ("Chain", "ColorTransform", "InvSoftplus", "NeuralSplineCoupling", "Reverse", "Roll",
                       "RollingSplineCoupling", "Scale", "ShiftBounds", "StandardScaler")
 LATENTS = {"Uniform": N.LATENT_UNIFORM, "CentBeta13": N.LATENT_CENTBETA13, "Normal": N.LATENT_NORMAL,
-           "CentBeta": N.LATENT_CENTBETA}
+           "CentBeta": N.LATENT_CENTBETA, "Tdist": N.LATENT_TDIST, "Joint": N.LATENT_JOINT}
+
+
+def latent_segments(latent_info, latent_params) -> list:
+    """(kind, dim, B, flat float32 params or None) for every segment of a latent's ``info`` / ``_params``
+    (pzflow/distributions.py: a Joint's info is ("Joint", ("Joint info", [sub infos])), its params a list)."""
+    name, args = latent_info
+    if name == "Joint":
+        subs = args[1]
+        params = latent_params if latent_params is not None else [None] * len(subs)
+        out = []
+        for sub, p in zip(subs, params):
+            out += latent_segments(tuple(sub), p)
+        return out
+    if name not in LATENTS:
+        raise NotImplementedError(
+            f"latent {name!r} is outside the B200 hot path (supported: {', '.join(LATENTS)})")
+    dim = int(args[0])
+    B = float(args[1]) if len(args) > 1 and name in ("Uniform", "CentBeta13", "CentBeta") else 5.0
+    flat = None
+    if name == "CentBeta" and latent_params is not None and len(latent_params):
+        flat = np.asarray([[float(np.asarray(a)), float(np.asarray(b))] for a, b in latent_params], np.float32).ravel()
+    if name == "Tdist" and latent_params is not None and np.size(latent_params):
+        flat = np.asarray([float(np.asarray(latent_params))], np.float32)
+    return [(LATENTS[name], dim, B, None if flat is None else np.ascontiguousarray(flat))]
 
 
 def _f32(a) -> np.ndarray:
@@ -134,7 +158,8 @@ class Plan:
         if latent_name not in LATENTS:
             raise NotImplementedError(
                 f"latent {latent_name!r} is outside the B200 hot path (supported: {', '.join(LATENTS)})")
-        latent_B = float(latent_args[1]) if len(latent_args) > 1 else 5.0
+        latent_B = (float(latent_args[1]) if len(latent_args) > 1 and latent_name in ("Uniform", "CentBeta13", "CentBeta")
+                    else 5.0)
         self._latent_name = latent_name
         stages = flatten(bijector_info, bijector_params, input_dim)
         self._keep = []  # host arrays the descriptors point into (until plan_create returns)
@@ -162,12 +187,14 @@ class Plan:
                                     latent_B, self.device_index, C.byref(handle)))
         self._keep = []
         self._h = handle
-        if latent_name == "CentBeta":
-            if latent_params is None:
-                latent_params = tuple((0.0, 0.0) for _ in range(int(input_dim)))
-            flat = np.ascontiguousarray(np.asarray([[float(np.asarray(a)), float(np.asarray(b))]
-                                                    for a, b in latent_params], dtype=np.float32).ravel())
-            N.check(lib.pzb_plan_set_latent_params(handle, flat.ctypes.data_as(C.c_void_p), flat.size))
+        if latent_name in ("CentBeta", "Tdist", "Joint"):
+            segs = latent_segments(latent_info, latent_params)
+            arr = (N.LatentDesc * len(segs))()
+            for d, (kind, dim, B, flat) in zip(arr, segs):
+                d.kind, d.dim, d.B = kind, dim, B
+                d.params = flat.ctypes.data_as(N.c_float_p) if flat is not None else None
+                d.n_params = 0 if flat is None else flat.size
+            N.check(lib.pzb_plan_set_latent(handle, arr, len(segs)))
         self.input_dim = int(input_dim)
         self.n_conditions = lib.pzb_plan_n_conditions(handle)
         self.n_spline_dims = lib.pzb_plan_n_spline_dims(handle)

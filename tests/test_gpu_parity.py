@@ -700,6 +700,29 @@ def test_normal_and_centbeta_latents():
     np.testing.assert_allclose(s.mean(axis=0), 10 * (a / (a + b) - 0.5), atol=0.05)
     n = Dn.Normal(3).sample((), 50_000, seed=1)
     assert abs(n.mean()) < 0.02 and abs(n.std() - 1) < 0.02
+    # Tdist (learned degrees of freedom) and Joint (segments of different latents)
+    for params, key in ((None, "tdist_lp_default"), (float(z["tdist_lognu"]), "tdist_lp")):
+        plan = Plan(ident, [()], 3, ("Tdist", (3,)), latent_params=params)
+        np.testing.assert_allclose(_np(plan.log_prob(torch.from_numpy(u).cuda())), z[key], rtol=1e-5, atol=1e-5)
+        td = Dn.Tdist(3)
+        np.testing.assert_allclose(td.log_prob(td._params if params is None else params, u), z[key], rtol=1e-5, atol=1e-5)
+    t = Dn.Tdist(3).sample(float(z["tdist_lognu"]), 100_000, seed=2)
+    from scipy import stats
+    assert t.shape == (100_000, 3) and abs(np.median(t)) < 0.02
+    assert abs(np.percentile(np.abs(t), 84) - stats.t.ppf(0.92, 4.5)) < 0.03   # |t| 84th pct == t 92nd pct
+    jinfo = F.unpack_tree("joint_info", z)
+    jparams = [(), (cbp[0],), ()]
+    plan = Plan(ident, [()], 3, jinfo, latent_params=jparams)
+    got, want = _np(plan.log_prob(torch.from_numpy(u).cuda())), z["joint_lp"]
+    zero = ~np.isfinite(want)
+    assert (zero_class(got) == zero).all()
+    np.testing.assert_allclose(got[~zero], want[~zero], rtol=1e-5, atol=1e-5)
+    joint = Dn.Joint(*jinfo[1])
+    assert joint.info == jinfo and joint.input_dim == 3
+    got2 = joint.log_prob(jparams, u)
+    np.testing.assert_allclose(got2[~zero], want[~zero], rtol=1e-5, atol=1e-5)
+    js = joint.sample(jparams, 20_000, seed=4)
+    assert js.shape == (20_000, 3) and np.abs(js[:, :2]).max() <= 5.0
 
 
 @pytest.mark.parametrize("engine", ENGINES)

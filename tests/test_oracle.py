@@ -241,3 +241,11 @@ def test_extra_bijectors_and_latents_golden():
         assert np.array_equal(np.isneginf(got), np.isneginf(want))
         fin = np.isfinite(want)
         np.testing.assert_allclose(got[fin], want[fin], rtol=3e-6, atol=3e-6)
+    np.testing.assert_allclose(O.tdist_log_prob(np.log(np.float32(30.0)), u), z["tdist_lp_default"], rtol=3e-6, atol=3e-6)
+    np.testing.assert_allclose(O.tdist_log_prob(z["tdist_lognu"], u), z["tdist_lp"], rtol=3e-6, atol=3e-6)
+    jinfo = F.unpack_tree("joint_info", z)
+    got = O.joint_log_prob(jinfo, [(), (cbp[0],), ()], u)
+    want = z["joint_lp"]
+    assert np.array_equal(np.isneginf(got), np.isneginf(want))
+    fin = np.isfinite(want)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=3e-6, atol=3e-6)
