@@ -286,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
 
     peaks = measured_peaks()
     flops_row = plan.flops_per_row
@@ -348,9 +348,9 @@ def run_ours(args, rank, world, local_rank):
             "sample": {"value": n * world / (samp_ms * 1e-3), "unit": "rows/s", "ms": samp_ms},
         },
     }
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -374,7 +374,19 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), __file__] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    run_ours(args, rank, world, local_rank)
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." to fd 1
+    # on the first collective), so fd 1 points at stderr while the benchmark runs and is restored for the result.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_ours(args, rank, world, local_rank)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
