@@ -1,37 +1,45 @@
-// tcgen05 engine: fused chain kernel with the conditioner's two big GEMMs on the 5th-gen
-// tensor cores (sm_100a), for the default conditioner family (hidden_layers = 2, hidden_dim = 128,
-// K = 16, at most 8 conditioner inputs and 4 transformed columns: BASELINE configs 1-4).
+// tcgen05 engine: fused chain kernel with ALL THREE conditioner GEMMs on the 5th-gen tensor cores
+// (sm_100a), for the default conditioner family (hidden_layers = 2, hidden_dim = 128, K = 16, at most
+// 8 conditioner inputs and 4 transformed columns: BASELINE configs 1-4).
 //
 // fp32 fidelity: every fp32 operand x is split x = hi + lo with hi = fp16(x), lo = fp16(x - hi)
 // (22 significant bits), and a GEMM is three kind::f16 MMAs, lo*hi + hi*lo + hi*hi, accumulated
-// in fp32 in TMEM.  Weights are pre-scaled by a power of two so their lo parts stay normal.
+// in fp32 in TMEM.  W2 / W3 are pre-scaled by a power of two so their lo parts stay normal.
 // Measured against the float64 twin this is indistinguishable from an fp32 GEMM.
 //
 // Structure (one persistent CTA per SM, 608 threads):
 //   * 16 epilogue warps in two groups of 8.  A group owns one 128-row tile at a time; TMEM lane =
 //     row, and TWO threads share a row (warp w and w+4 of the group address the same TMEM lane
 //     quarter): "half" h does hidden columns [64h, 64h+64) in E1/E2 and the spline dimensions
-//     h, h+2 in E3.  The two groups ping-pong, and inside a tile the tensor pipe and the CUDA
-//     cores overlap as well:
-//       - the hidden GEMM is issued as two N = 64 halves with a commit each, so half 0 starts its
-//         E2 while the tensor pipe still computes half 1;
-//       - the output layer is one N = 48 pass per spline dimension into two 48-column
-//         accumulator buffers, so pass p+1 runs while pass p's spline is evaluated.
-//   * warps 16/17, one elected lane each: MMA issuer of group 0/1 (blocking mbarrier waits, every
-//     tcgen05.mma / tcgen05.commit of its group).
-//   * warp 18, one lane: streams the weights of the NEXT coupling stage with TMA bulk copies as
-//     soon as the tensor pipe has released a buffer (W2 64 KB, W3 48/96 KB, the fp32 parameter
-//     block with W1, biases, scales and the stage's column map, double buffered).
+//     h, h+2 in E3.  Per tile and coupling stage:
+//       E0  the <= 8 conditioner inputs + a constant 1 -> K = 16 A operand in Y[0,24)   (1 thread/row)
+//       G1  keys x W1 tile (bias row included) -> X                                      3 MMAs
+//       E1  X: LeakyReLU, fp16 hi/lo split, rewritten in place
+//       G2  X x W2 -> Y in four N = 32 quarters, one commit each, alternating between the halves,
+//           so E2 of a quarter runs while the tensor pipe computes the next ones
+//       E2  Y: * 2^-e2 + b2, LeakyReLU, split, in place
+//       G3  Y x W3 -> X[0,48) / X[64,112), one N = 48 pass per spline dimension into two accumulator
+//           buffers; passes 0/1 start on half 0's 64 K-elements and take half 1's when it arrives,
+//           passes 2/3 go into a buffer as soon as its half has drained it
+//       E3  48 logits of a (row, dim) in registers -> knots, bin search, RQS, log-det
+//     The half that finishes E3 first writes the NEXT tile's E0, so G1 runs under the last spline.
+//   * warps 16/17: MMA issuer of group 0/1.  The whole warp waits on the mbarriers, one elect.sync
+//     lane issues, which keeps the tcgen05.mma operands on the uniform datapath.
+//   * warp 18: streams the weights of the NEXT coupling stage with TMA bulk copies as soon as
+//     tcgen05.commit has released a buffer (W2 64 KB, W3 48/96 KB, W1 tile 8 KB; the fp32 parameter
+//     block with b2, b3, scales and the stage's column map is double buffered).
 //   * A operands (activations) never touch shared memory: epilogue threads write fp16 hi/lo pairs
 //     straight into TMEM (tcgen05.st) and the MMA reads A from TMEM (.ts form); B (weights) sits in
-//     shared memory, K-major SWIZZLE_128B.
-//   * TMEM (512 columns), per group g two 128-column regions X = 256g, Y = 256g + 128:
-//       E1 writes h1 into X; hidden GEMM X -> Y (fp32 accumulators); E2 rewrites Y IN PLACE with
-//       h2 (32 accumulator columns become 16 hi + 16 lo columns); output passes Y -> X[0,48) /
-//       X[64,112); E3 drains them.  A thread only ever overwrites TMEM columns it alone has read.
-//   * stage-outer order: a CTA takes a chunk of up to 1024 rows whose state (x[D], log-det
-//     levels, conditions) lives in shared memory as [column][row] for the whole chain, and walks
-//     the chunk's tiles once per coupling stage.  HBM sees the input rows and the result only.
+//     shared memory, K-major SWIZZLE_128B (W1: SWIZZLE_NONE).
+//   * TMEM (512 columns), per group g two 128-column regions X = 256g, Y = 256g + 128.  32 fp32
+//     accumulator columns become 16 hi + 16 lo columns IN PLACE, so a tile needs exactly 256 columns
+//     and two tiles are in flight.  A thread only ever overwrites TMEM columns it alone has read;
+//     every cross-thread hand-over is an mbarrier with one arrival per warp.
+//   * stage-outer order: a CTA takes a chunk of up to 1024 rows (an even number of tiles, so both
+//     groups get the same count) whose state (x[D], log-det levels, conditions) lives in shared
+//     memory as [column][row] for the whole chain, and walks the chunk's tiles once per coupling
+//     stage.  HBM sees the input rows and the result only.
+//   * -DPZB_TC_TRACE builds SM-clock phase stamps of CTA 0 into the kernel (pzb_debug_tc_trace).
 //
 // Follows the same reference lines as nsf_simt.cu.
 #include <cuda_fp16.h>
