@@ -796,3 +796,40 @@ def test_flow_train_reduces_the_loss_and_feeds_the_fused_kernels():
     out = ens.train(data[:2000], epochs=2, seed=1)
     assert sorted(out) == ["Flow 0", "Flow 1"] and all(len(v) == 3 for v in out.values())
     assert ens.log_prob(data[:100]).shape == (100,)
+
+
+def test_one_plan_many_host_threads_and_streams():
+    """include/pzflow_b200.h: a plan may be launched concurrently from several host threads / streams
+    (device-pointer calls), and host-buffer calls on one plan serialise."""
+    import threading
+    ex = F.example_flow()
+    plan = _plan(ex, "tc")
+    X = torch.from_numpy(F.galaxy_rows(200_000, seed=13)).cuda()
+    want = plan.log_prob(X)
+    Xh = X.cpu().pin_memory()
+    torch.cuda.synchronize()
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                outs = [plan.log_prob(X) for _ in range(6)]
+                if i % 2:
+                    outs.append(plan.log_prob_host(Xh).cuda())
+            st.synchronize()
+            results[i] = outs
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    assert sorted(results) == [0, 1, 2, 3]
+    for outs in results.values():
+        for o in outs:
+            assert _same_bits(o, want)
