@@ -10,7 +10,8 @@ with no data-path collective).  One step = one pass of log_prob over the rank's 
 `value` is device-resident throughput (CUDA events, max over ranks); `e2e` is the same call
 through the Flow-facing API with pinned HOST inputs and a host result: Flow._log_prob ->
 pzb_log_prob_host, the host-buffer C-ABI call, which pipelines chunked H2D copies, the kernel
-and D2H copies (all inside the timed region).  Secondary numbers (posterior galaxies/s on the config-3 geometry, sample
+and D2H copies (all inside the timed region).  The own arm touches nothing under oracle/ (inputs come from the flow's own
+inverse map on the device); only the CPU-baseline legs execute the oracle.  Secondary numbers (posterior galaxies/s on the config-3 geometry, sample
 rows/s) ride along under "extra".
 
 --impl reference times the CPU restatement of the reference algorithm (oracle/nsf_oracle.py,
@@ -174,8 +175,7 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from oracle import fixtures as F
-    from pzflow_b200 import Flow
+    from pzflow_b200.examples import get_example_flow
     from pzflow_b200.plan import launch_count
 
     if not torch.cuda.is_available():
@@ -188,23 +188,27 @@ def run_ours(args, rank, world, local_rank):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
-    ex = F.example_flow()
-    flow = Flow(_dictionary={"class": "Flow", "data_columns": F.GALAXY_COLUMNS, "conditional_columns": None,
-                             "condition_means": None, "condition_stds": None, "data_error_model": None,
-                             "condition_error_model": None, "autoscale_conditions": True, "info": "bench",
-                             "latent_info": ex["latent_info"], "bijector_info": ex["bijector_info"],
-                             "params": ex["params"]})
+    flow = get_example_flow()   # the reference's shipped 7-D galaxy flow (pzflow/examples.py:105-113)
     plan = flow._plan()
     plan.set_engine(args.engine)
     engine = plan.engine
 
-    # synthetic in-distribution rows: x = inverse(u), u ~ U(-5,5)^7, + 1 % OOB admixture,
-    # generated on the device from a small CPU-built pool so start-up stays short
+    # synthetic in-distribution rows: x = inverse(u), u ~ U(-5,5)^7 -- the flow's own sampling
+    # map, run on the device -- plus a 1 % admixture of rows from the ShiftBounds box widened by 20 %
+    # (exercises the out-of-bounds paths).  Nothing under oracle/ is touched on this arm.
     n = args.rows
-    pool = torch.from_numpy(F.galaxy_rows(65_536, seed=1000 + rank)).to(dev)
-    reps = (n + pool.shape[0] - 1) // pool.shape[0]
-    X = pool.repeat(reps, 1)[:n].contiguous()
-    X += (torch.arange(n, device=dev, dtype=torch.float32) % 997)[:, None] * 1e-6  # de-duplicate rows
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1000 + rank)
+    U = (torch.rand((n, 7), generator=gen, device=dev) * 10.0 - 5.0)
+    X = plan.inverse(U, want_log_det=False)[0]
+    del U
+    mins = torch.as_tensor(np.asarray(flow._bijector_info[1][0][1][0], np.float32), device=dev)
+    maxs = torch.as_tensor(np.asarray(flow._bijector_info[1][0][1][1], np.float32), device=dev)
+    n_oob = n // 100
+    rows = torch.randperm(n, generator=gen, device=dev)[:n_oob]
+    span = maxs - mins
+    X[rows] = (mins - 0.2 * span) + torch.rand((n_oob, 7), generator=gen, device=dev) * (1.4 * span)
+    X = torch.nan_to_num(X, nan=0.0).contiguous()
     out = torch.empty(n, dtype=torch.float32, device=dev)
     X_host = X.cpu().pin_memory()
 

@@ -833,3 +833,18 @@ def test_one_plan_many_host_threads_and_streams():
     for outs in results.values():
         for o in outs:
             assert _same_bits(o, want)
+
+
+def test_get_example_flow_is_the_shipped_flow():
+    """pzflow_b200.examples.get_example_flow (pzflow/examples.py:105-113) == the parameters the golden vectors
+    were produced with."""
+    from pzflow_b200.examples import get_example_flow
+    flow = get_example_flow()
+    z = golden("ref_shim_example_flow.npz")
+    df = pd.DataFrame(z["X"], columns=flow.data_columns)
+    lp = flow.log_prob(df)
+    want = z["log_prob"]
+    fin = ~zero_class(want) & (want > LP_UNDERFLOW)
+    assert (zero_class(lp) == zero_class(want)).mean() > 0.99
+    np.testing.assert_allclose(lp[fin], want[fin], atol=5e-3)
+    assert flow.sample(10, seed=0).shape == (10, 7)
