@@ -848,3 +848,39 @@ def test_get_example_flow_is_the_shipped_flow():
     assert (zero_class(lp) == zero_class(want)).mean() > 0.99
     np.testing.assert_allclose(lp[fin], want[fin], atol=5e-3)
     assert flow.sample(10, seed=0).shape == (10, 7)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_elementwise_steps_between_coupling_stages(engine):
+    """Non-NSC steps BETWEEN coupling stages (affine, colour transform, nested chains) take the kernels'
+    "light step" path in the middle of the chain, forward and inverse."""
+    rsc = ("RollingSplineCoupling", (2,))
+    info = ("Chain", (("ShiftBounds", (np.full(6, -1.0, np.float32), np.full(6, 2.0, np.float32), 4.0)), rsc,
+                      ("StandardScaler", (np.linspace(-0.3, 0.3, 6).astype(np.float32),
+                                          np.linspace(0.8, 1.3, 6).astype(np.float32))),
+                      ("Chain", (("Reverse", ()), rsc, ("Scale", (0.9,)))), ("ColorTransform", (1, [1, 2, 4])), rsc))
+    rng = np.random.default_rng(17)
+    sub = lambda: O.synth_bijector_params(O.expand_rolling((2,)), 6, rng, out_scale=2.0)  # noqa: E731
+    bparams = [(), sub(), (), [(), sub(), ()], (), sub()]
+    latent_info = ("CentBeta13", (6, 5))
+    from pzflow_b200.plan import Plan
+    plan = Plan(info, bparams, 6, latent_info)
+    if engine == "tc" and not plan.tc_supported:
+        pytest.skip("tensor-core engine does not support this shape")
+    plan.set_engine(engine)
+    X = rng.uniform(-0.9, 1.9, size=(5000, 6)).astype(np.float32)
+    o32 = O.flow_log_prob(info, latent_info, ((), bparams), X)
+    got = _np(plan.log_prob(torch.from_numpy(X).cuda()))
+    ok = ~zero_class(o32) & (o32 > LP_UNDERFLOW)
+    assert ok.mean() > 0.5 and (zero_class(got) == zero_class(o32)).mean() > 0.995
+    assert within_tol(got[ok], o32[ok]).mean() > 0.97
+    u, ld = plan.forward(torch.from_numpy(X).cuda())
+    u32, ld32 = O.apply_bijector(info, bparams, X, np.zeros((len(X), 1), np.float32))
+    fin = np.isfinite(u32).all(axis=1) & ok
+    assert within_tol(_np(u)[fin], u32[fin]).mean() > 0.97 and within_tol(_np(ld)[fin], ld32[fin]).mean() > 0.97
+    xr, ldi = plan.inverse(u)
+    inside = (np.abs(_np(u)) < 4.5).all(axis=1) & fin
+    err = np.abs(_np(xr)[inside] - X[inside])   # steep synthetic splines: judge the round trip by quantiles
+    assert np.median(err) < 1e-5 and np.quantile(err, 0.99) < 2e-3
+    asym = np.abs(_np(ld)[inside] + _np(ldi)[inside])
+    assert np.median(asym) < 1e-4 and np.quantile(asym, 0.99) < 5e-3
