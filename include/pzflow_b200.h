@@ -264,6 +264,14 @@ int pzb_error_eps(float *eps, int64_t n, int32_t W, int32_t stream_id, uint64_t 
  * one plan serialise. */
 int pzb_log_prob_host(const pzb_plan *plan, const float *X, const float *cond, int64_t N,
                       float *out);
+/* Flow.log_prob straight from DataFrame columns (pzflow/flow.py:440-446): data_cols [D] and cond_cols [C]
+ * are pointers to contiguous float64 HOST columns of N values (what `df[c].to_numpy()` is for a pandas
+ * column); the float64 -> float32 down-cast, the row gather and the standard scaling of the conditions
+ * ((float(c) - mean) / std, flow.py:330-336) happen on the host cores chunk by chunk into page-locked staging
+ * inside the same three-stage pipeline, so they overlap with the copies and the kernel.  out [N] HOST. */
+int pzb_log_prob_host_columns(const pzb_plan *plan, const double *const *data_cols,
+                              const double *const *cond_cols, const float *cond_means,
+                              const float *cond_stds, int64_t N, float *out);
 int pzb_forward_host(const pzb_plan *plan, const float *X, const float *cond, int64_t N,
                      float *U, float *log_det);
 int pzb_inverse_host(const pzb_plan *plan, const float *U, const float *cond, int64_t N,

@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     # the reference evaluates op by op in fp32: no implicit mul+add contraction;
     # the GEMM inner loops call fmaf() explicitly.
     "-fmad=false",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared",
     "-Xptxas", "-v",
 ]
 

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -56,6 +57,10 @@ struct HostPipe {
   void* d_out1[NBUF] = {};
   void* d_grid = nullptr;
   size_t cap_in = 0, cap_cond = 0, cap_out0 = 0, cap_out1 = 0, cap_grid = 0;
+  // page-locked host staging for the column-source form (float64 DataFrame columns -> float32 rows)
+  void* h_in[NBUF] = {};
+  void* h_cond[NBUF] = {};
+  size_t cap_hin = 0, cap_hcond = 0;
 };
 
 struct pzb_plan {
@@ -580,6 +585,10 @@ void pzb_plan_destroy(pzb_plan* plan) {
       cudaEventDestroy(hp.ev_out[b]);
     }
     cudaFree(hp.d_grid);
+    for (int b = 0; b < HostPipe::NBUF; ++b) {
+      if (hp.h_in[b]) cudaFreeHost(hp.h_in[b]);
+      if (hp.h_cond[b]) cudaFreeHost(hp.h_cond[b]);
+    }
     cudaStreamDestroy(hp.s_in);
     cudaStreamDestroy(hp.s_k);
     cudaStreamDestroy(hp.s_out);
@@ -1001,7 +1010,46 @@ struct HostJob {
   const float* grid = nullptr; // posterior: host [G]
   int G = 1, col_idx = 0, normalize = 0, nan_to_zero = 0;
   int64_t units = 0;           // rows, or galaxies for the posterior
+  // column-source form: in_w (and C) float64 column pointers instead of `in` / `cond`; conditions are standard-scaled
+  // here, (float(c) - mean) / std in float32 like Flow._get_conditions (pzflow/flow.py:330-336)
+  const double* const* in_cols = nullptr;
+  const double* const* cond_cols = nullptr;
+  const float* cond_mean = nullptr;
+  const float* cond_std = nullptr;
 };
+
+static cudaError_t host_reserve(void** p, size_t* cap, size_t want, int n) {
+  if (want <= *cap) return cudaSuccess;
+  for (int b = 0; b < n; ++b) {
+    if (p[b]) cudaFreeHost(p[b]);
+    p[b] = nullptr;
+  }
+  *cap = 0;
+  for (int b = 0; b < n; ++b) {
+    cudaError_t e = cudaHostAlloc(&p[b], want, cudaHostAllocDefault);
+    if (e != cudaSuccess) return e;
+  }
+  *cap = want;
+  return cudaSuccess;
+}
+
+// float64 columns -> float32 rows [n, w] on all host cores (explicit thread count: torchrun exports OMP_NUM_THREADS=1)
+static void gather_cast_rows(const double* const* cols, int w, int64_t r0, int64_t n, float* dst, const float* mean,
+                             const float* stdv, int threads) {
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (int64_t blk = 0; blk < (n + 4095) / 4096; ++blk) {
+    const int64_t a = blk * 4096, b = std::min<int64_t>(n, a + 4096);
+    for (int j = 0; j < w; ++j) {
+      const double* src = cols[j] + r0;
+      if (mean != nullptr) {
+        const float m = mean[j], sd = stdv[j];
+        for (int64_t r = a; r < b; ++r) dst[r * w + j] = ((float)src[r] - m) / sd;
+      } else {
+        for (int64_t r = a; r < b; ++r) dst[r * w + j] = (float)src[r];
+      }
+    }
+  }
+}
 
 static cudaError_t pipe_reserve(void** p, size_t* cap, size_t want, int n) {
   if (want <= *cap) return cudaSuccess;
@@ -1058,7 +1106,12 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     if (ce == cudaSuccess)
       ce = cudaMemcpyAsync(hp.d_grid, job.grid, (size_t)job.G * sizeof(float), cudaMemcpyHostToDevice, hp.s_k);
   }
+  if (ce == cudaSuccess && job.in_cols)
+    ce = host_reserve(hp.h_in, &hp.cap_hin, (size_t)chunk * std::max(job.in_w, 1) * sizeof(float), HostPipe::NBUF);
+  if (ce == cudaSuccess && job.cond_cols && C > 0)
+    ce = host_reserve(hp.h_cond, &hp.cap_hcond, (size_t)chunk * C * sizeof(float), HostPipe::NBUF);
   if (ce != cudaSuccess) return cuda_fail(ce, "host pipeline staging buffers");
+  const int host_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
 
   int rc = PZB_OK;
   int64_t i = 0;
@@ -1068,13 +1121,25 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
   for (int64_t u0 = 0; u0 < job.units && rc == PZB_OK; ++i) {
     const int b = (int)(i % HostPipe::NBUF);
     const int64_t nu = std::min(cur, job.units - u0);
+    const float* src_in = job.in ? job.in + u0 * job.in_w : nullptr;
+    const float* src_cond = job.cond ? job.cond + u0 * C : nullptr;
+    if (job.in_cols) {
+      // the previous copy out of this staging buffer (chunk i - NBUF) must have completed before it is refilled;
+      // the cast of chunk i then runs on the host cores while the GPU works on chunks i-1, i-2
+      if (i >= HostPipe::NBUF) cudaEventSynchronize(hp.ev_in[b]);
+      gather_cast_rows(job.in_cols, job.in_w, u0, nu, static_cast<float*>(hp.h_in[b]), nullptr, nullptr, host_threads);
+      src_in = static_cast<const float*>(hp.h_in[b]);
+      if (C > 0) {
+        gather_cast_rows(job.cond_cols, C, u0, nu, static_cast<float*>(hp.h_cond[b]), job.cond_mean, job.cond_std,
+                         host_threads);
+        src_cond = static_cast<const float*>(hp.h_cond[b]);
+      }
+    }
     if (i >= HostPipe::NBUF) cudaStreamWaitEvent(hp.s_in, hp.ev_k[b], 0);  // kernel i-NBUF has read d_in[b]
     if (job.in_w > 0)
-      ce = cudaMemcpyAsync(hp.d_in[b], job.in + u0 * job.in_w, (size_t)nu * job.in_w * sizeof(float),
-                           cudaMemcpyHostToDevice, hp.s_in);
+      ce = cudaMemcpyAsync(hp.d_in[b], src_in, (size_t)nu * job.in_w * sizeof(float), cudaMemcpyHostToDevice, hp.s_in);
     if (ce == cudaSuccess && C > 0)
-      ce = cudaMemcpyAsync(hp.d_cond[b], job.cond + u0 * C, (size_t)nu * C * sizeof(float), cudaMemcpyHostToDevice,
-                           hp.s_in);
+      ce = cudaMemcpyAsync(hp.d_cond[b], src_cond, (size_t)nu * C * sizeof(float), cudaMemcpyHostToDevice, hp.s_in);
     if (ce == cudaSuccess) ce = cudaEventRecord(hp.ev_in[b], hp.s_in);
     if (ce != cudaSuccess) { rc = cuda_fail(ce, "host pipeline H2D"); break; }
     cudaStreamWaitEvent(hp.s_k, hp.ev_in[b], 0);
@@ -1125,6 +1190,31 @@ int pzb_log_prob_host(const pzb_plan* plan, const float* X, const float* cond, i
   j.out0_w = 1;
   j.units = N;
   return run_host(plan, j, "log_prob_host");
+}
+
+int pzb_log_prob_host_columns(const pzb_plan* plan, const double* const* data_cols, const double* const* cond_cols,
+                              const float* cond_means, const float* cond_stds, int64_t N, float* out) {
+  if (!plan) return fail(PZB_ERR_INVALID, "log_prob_host_columns: plan is NULL");
+  if (N < 0) return fail(PZB_ERR_INVALID, "log_prob_host_columns: negative row count");
+  const int D = plan->host.D, C = plan->host.C;
+  if (N > 0 && (data_cols == nullptr || out == nullptr)) return fail(PZB_ERR_INVALID, "log_prob_host_columns: NULL buffer");
+  if (N > 0 && C > 0 && (cond_cols == nullptr || cond_means == nullptr || cond_stds == nullptr))
+    return fail(PZB_ERR_INVALID, "log_prob_host_columns: this plan is conditional (C = %d) but conditions are NULL", C);
+  for (int j = 0; N > 0 && j < D; ++j)
+    if (data_cols[j] == nullptr) return fail(PZB_ERR_INVALID, "log_prob_host_columns: data column %d is NULL", j);
+  for (int j = 0; N > 0 && j < C; ++j)
+    if (cond_cols[j] == nullptr) return fail(PZB_ERR_INVALID, "log_prob_host_columns: condition column %d is NULL", j);
+  HostJob j;
+  j.mode = MODE_LOGPROB;
+  j.in_cols = data_cols;
+  j.in_w = D;
+  j.cond_cols = C > 0 ? cond_cols : nullptr;
+  j.cond_mean = cond_means;
+  j.cond_std = cond_stds;
+  j.out0 = out;
+  j.out0_w = 1;
+  j.units = N;
+  return run_host(plan, j, "log_prob_host_columns");
 }
 
 int pzb_forward_host(const pzb_plan* plan, const float* X, const float* cond, int64_t N, float* U, float* log_det) {

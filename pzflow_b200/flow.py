@@ -210,7 +210,18 @@ class Flow:
         self._check_bijector()
         if err_samples is None:
             columns = list(self.data_columns)
-            X = _pinned_f32(inputs[columns].to_numpy())  # the float64 -> float32 down-cast (flow.py:442)
+            # float64 columns go to the C call as they are: the down-cast (flow.py:442), the row gather and the
+            # condition scaling (flow.py:330-336) run chunk by chunk inside the H2D | kernel | D2H pipeline
+            cols = [inputs[c].to_numpy() for c in columns]
+            if all(c.dtype == np.float64 and c.ndim == 1 for c in cols):
+                ccols = None
+                if self.conditional_columns is not None:
+                    ccols = [inputs[c].to_numpy() for c in self.conditional_columns]
+                    if not all(c.dtype == np.float64 and c.ndim == 1 for c in ccols):
+                        ccols = [np.asarray(c, dtype=np.float64) for c in ccols]
+                return self._plan().log_prob_host_columns(cols, ccols, self._condition_means,
+                                                          self._condition_stds).numpy()
+            X = _pinned_f32(inputs[columns].to_numpy())
             conditions = self._get_conditions(inputs)
             return self._log_prob(self._params, X, conditions).cpu().numpy()
         assert isinstance(err_samples, int), "err_samples must be a positive integer."

@@ -264,6 +264,35 @@ class Plan:
         N.check(N.lib().pzb_log_prob_host(self._h, _ptr(X), _ptr(cond), X.shape[0], _ptr(out)))
         return out
 
+    def log_prob_host_columns(self, data_cols, cond_cols=None, cond_means=None, cond_stds=None) -> torch.Tensor:
+        """Flow.log_prob from float64 DataFrame COLUMNS (one contiguous 1-D array per column): the down-cast to
+        float32, the row gather and the condition scaling run inside the pipelined C call
+        (pzb_log_prob_host_columns).  Returns a pinned CPU tensor [N]."""
+        cols = [np.ascontiguousarray(c, dtype=np.float64) for c in data_cols]
+        if len(cols) != self.input_dim:
+            raise ValueError(f"expected {self.input_dim} data columns, got {len(cols)}")
+        n = len(cols[0])
+        if any(c.ndim != 1 or len(c) != n for c in cols):
+            raise ValueError("data columns must be 1-D arrays of equal length")
+        ccols, means, stds = [], None, None
+        if self.n_conditions > 0:
+            if cond_cols is None:
+                raise ValueError(f"this bijector is conditional: conditions [N, {self.n_conditions}] are required")
+            ccols = [np.ascontiguousarray(c, dtype=np.float64) for c in list(cond_cols)[: self.n_conditions]]
+            if len(ccols) < self.n_conditions or any(c.ndim != 1 or len(c) != n for c in ccols):
+                raise ValueError(f"conditions must be {self.n_conditions} columns of {n} values")
+            means = np.ascontiguousarray(np.zeros(self.n_conditions) if cond_means is None else cond_means,
+                                         dtype=np.float32)[: self.n_conditions]
+            stds = np.ascontiguousarray(np.ones(self.n_conditions) if cond_stds is None else cond_stds,
+                                        dtype=np.float32)[: self.n_conditions]
+        dptr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        cptr = (C.c_void_p * max(1, len(ccols)))(*[c.ctypes.data for c in ccols]) if ccols else None
+        out = pinned_empty((n,))
+        N.check(N.lib().pzb_log_prob_host_columns(
+            self._h, dptr, cptr, means.ctypes.data if means is not None else None,
+            stds.ctypes.data if stds is not None else None, n, _ptr(out)))
+        return out
+
     def inverse_host(self, U, cond=None, want_log_det: bool = False):
         """Chain InverseFunction on HOST arrays -> (x [N, D], log_det [N] or None), pinned CPU tensors."""
         U = self._host_rows(U, self.input_dim, "inputs")

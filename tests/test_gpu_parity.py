@@ -884,3 +884,36 @@ def test_elementwise_steps_between_coupling_stages(engine):
     assert np.median(err) < 1e-5 and np.quantile(err, 0.99) < 2e-3
     asym = np.abs(_np(ld)[inside] + _np(ldi)[inside])
     assert np.median(asym) < 1e-4 and np.quantile(asym, 0.99) < 5e-3
+
+
+def test_dataframe_columns_take_the_pipelined_cast():
+    """Flow.log_prob on a float64 DataFrame (pzb_log_prob_host_columns: cast + gather + condition scaling inside
+    the pipeline) == the float32 array path, for an unconditional and a conditional flow; a float32 or mixed
+    DataFrame still works through the array path."""
+    from pzflow_b200 import Flow
+    from pzflow_b200.examples import get_example_flow
+    flow = get_example_flow()
+    n = 2_600_003                                     # several pipeline chunks
+    X = np.tile(F.galaxy_rows(20_000, seed=31), (n // 20_000 + 1, 1))[:n].astype(np.float64)
+    X += np.linspace(0, 1e-3, n)[:, None]
+    df = pd.DataFrame(X, columns=flow.data_columns)
+    lp = flow.log_prob(df)
+    want = _np(flow._plan().log_prob(torch.from_numpy(X.astype(np.float32)).cuda()))
+    np.testing.assert_array_equal(lp, want)
+    np.testing.assert_array_equal(flow.log_prob(df.astype(np.float32)), want)
+    np.testing.assert_array_equal(flow.log_prob(df.iloc[::-1])[::-1], want)   # non-contiguous column views
+    cfg = F.config_c4(1)[0]
+    cflow = Flow(_dictionary={"class": "Flow", "data_columns": F.GALAXY_COLUMNS, "conditional_columns": ("a", "b"),
+                              "condition_means": np.array([0.5, -1.0], np.float32),
+                              "condition_stds": np.array([2.0, 0.25], np.float32), "data_error_model": None,
+                              "condition_error_model": None, "autoscale_conditions": True, "info": None,
+                              "latent_info": cfg["latent_info"], "bijector_info": cfg["bijector_info"],
+                              "params": cfg["params"]})
+    rng = np.random.default_rng(5)
+    m = 300_001
+    dfc = pd.DataFrame(X[:m], columns=F.GALAXY_COLUMNS)
+    dfc["a"], dfc["b"] = rng.normal(0.5, 2.0, m), rng.normal(-1.0, 0.25, m)
+    got = cflow.log_prob(dfc)
+    cond = (dfc[["a", "b"]].to_numpy().astype(np.float32) - np.array([0.5, -1.0], np.float32)) / np.array([2.0, 0.25], np.float32)
+    wantc = _np(cflow._plan().log_prob(torch.from_numpy(X[:m].astype(np.float32)).cuda(), torch.from_numpy(cond).cuda()))
+    np.testing.assert_array_equal(got, wantc)
