@@ -3,14 +3,21 @@
 What runs where
 ---------------
 * The inference hot path (log_prob / posterior / sample) is the hand-written CUDA of ``csrc/``.  Training is
-  NOT on that path: the gradient of ``-mean(w * log_prob)`` (flow.py:961-965) is taken by torch autograd over a
-  differentiable restatement of the same chain in torch tensor ops on the GPU (cuBLAS GEMMs for the
-  conditioners), and the update is Adam(1e-3) like ``optax.adam`` (flow.py:968-981).  It is a library-level
-  baseline, stated as such in DESIGN.md; the fused kernels evaluate every reported loss (initial, end of epoch,
-  validation: flow.py:1033-1050, 1088-1102), so a trained flow is checked by the product path as it trains.
+  NOT on that path.  The gradient of ``-mean(w * log_prob)`` (flow.py:961-965) is assembled by torch autograd
+  from two kinds of node: the coupling stage's spline (softmax / softplus knots, bin search, rational-quadratic
+  spline, log-determinant) is ONE hand-written forward kernel and ONE hand-derived backward kernel
+  (``csrc/nsf_train.cu``, ``_SplineStage``); the conditioner's dense layers are plain batch x 128 x 128 GEMMs
+  and stay with cuBLAS (``torch.matmul``), as do the affine bijectors' few elementwise ops.  The update is
+  Adam(1e-3) like ``optax.adam`` (flow.py:968-981), one fused kernel over a flat parameter buffer
+  (``pzb_adam_step``), and the whole step is captured once as a CUDA graph and replayed per batch
+  (``GraphedStep``; ``PZB_TRAIN_GRAPH=0`` runs it eagerly).  ``TorchChain(native_spline=False)`` is the all-torch
+  restatement the gradient tests compare the kernels with.  The fused inference kernels evaluate every reported
+  loss (initial, end of epoch, validation: flow.py:1033-1050, 1088-1102), so a trained flow is checked by the
+  product path as it trains.
 * Data parallel: one process per GPU; each rank takes its contiguous share of every batch (batch 1024 over 8
-  ranks = 128 rows each), the flat fp32 gradient is summed with ONE ``all_reduce`` (NCCL over NVLink on GPUs)
-  per step, and every rank applies the same Adam update, so parameters stay bit-identical across ranks.
+  ranks = 128 rows each), the flat fp32 gradient buffer (every leaf's .grad is a view into it) is summed with
+  ONE ``all_reduce`` (NCCL over NVLink on GPUs, inside the captured graph) per step, and every rank applies the
+  same Adam update, so parameters stay bit-identical across ranks.
 
 Not reproducible from the reference without jax: its batch permutations and error samples come from
 ``jax.random`` (flow.py:1063-1066); here they come from NumPy / torch generators seeded from the same ``seed``.
@@ -18,6 +25,7 @@ Not reproducible from the reference without jax: its batch permutations and erro
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, List, Optional, Tuple
 
 import numpy as np
@@ -66,24 +74,105 @@ def _rqs_forward(x, W, H, D, B, periodic):
     return out, ld.sum(dim=-1)
 
 
+class _SplineStage(torch.autograd.Function):
+    """The coupling stage's spline on the hand-written kernels of csrc/nsf_train.cu: forward
+    ``pzb_spline_train_forward``, backward ``pzb_spline_train_backward`` (analytic gradient of the softmax /
+    softplus knots, bin search and rational-quadratic spline + log-determinant w.r.t. the conditioner's logits and
+    the transformed columns).  Non-periodic splines; periodic ones take the torch-op restatement above."""
+
+    @staticmethod
+    def forward(ctx, logits, x, K, B):
+        from ._native import check, lib
+        logits, x = logits.contiguous().float(), x.contiguous().float()
+        N, L = x.shape
+        y, ld = torch.empty_like(x), torch.empty_like(x)
+        s = torch.cuda.current_stream(x.device).cuda_stream
+        check(lib().pzb_spline_train_forward(logits.data_ptr(), x.data_ptr(), N, L, int(K), float(B), y.data_ptr(),
+                                             ld.data_ptr(), s))
+        ctx.save_for_backward(logits, x)
+        ctx.K, ctx.B = int(K), float(B)
+        return y, ld
+
+    @staticmethod
+    def backward(ctx, gy, gld):
+        from ._native import check, lib
+        logits, x = ctx.saved_tensors
+        N, L = x.shape
+        gy, gld = gy.contiguous().float(), gld.contiguous().float()
+        gl, gx = torch.empty_like(logits), torch.empty_like(x)
+        s = torch.cuda.current_stream(x.device).cuda_stream
+        check(lib().pzb_spline_train_backward(logits.data_ptr(), x.data_ptr(), gy.data_ptr(), gld.data_ptr(), N, L,
+                                              ctx.K, ctx.B, gl.data_ptr(), gx.data_ptr(), s))
+        return gl, gx, None, None
+
+
 class TorchChain:
     """(Bijector_Info, params) -> differentiable forward; leaves of the NSC conditioners become torch Parameters
     in the stax layout ``[(W, b), (), (W, b), (), (W, b)]`` so they can be written back into ``Flow._params``."""
 
     def __init__(self, bijector_info, bijector_params, latent_info, latent_params, input_dim: int, device,
-                 dtype=torch.float32):
+                 dtype=torch.float32, native_spline: bool = True):
+        self.native_spline = bool(native_spline) and dtype == torch.float32
         self.info, self.latent_info, self.D = bijector_info, latent_info, int(input_dim)
         self.device, self.dtype = device, dtype
+        self._consts: dict = {}
+        # every trainable leaf is a view into ONE flat buffer, and its .grad a view into one flat gradient buffer:
+        # the data-parallel exchange is a single all_reduce of ``flat_grad`` and Adam is one pass over ``flat``
+        sizes: List[int] = []
+        self._count(bijector_params, sizes)
+        if latent_info[0] == "CentBeta":
+            self._count(latent_params, sizes)
+        self.flat = torch.zeros(sum(sizes), dtype=dtype, device=device)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self._off = 0
         self.leaves: List[torch.Tensor] = []
         self.params = self._wrap(bijector_params)
         self.latent_params = self._wrap(latent_params) if latent_info[0] == "CentBeta" else latent_params
+        self.attach_grads()
+
+    def _count(self, p, sizes):
+        if isinstance(p, (list, tuple)):
+            for q in p:
+                self._count(q, sizes)
+        else:
+            sizes.append(int(np.asarray(p).size))
 
     def _wrap(self, p):
         if isinstance(p, (list, tuple)):
             return type(p)(self._wrap(q) for q in p)
-        t = torch.tensor(np.asarray(p, dtype=np.float64), dtype=self.dtype, device=self.device, requires_grad=True)
+        a = np.asarray(p, dtype=np.float64)
+        view = self.flat[self._off:self._off + a.size].view(a.shape)
+        view.copy_(torch.as_tensor(a, dtype=self.dtype))
+        self._off += a.size
+        t = view.requires_grad_(True)
         self.leaves.append(t)
         return t
+
+    def attach_grads(self) -> None:
+        """(Re)bind every leaf's .grad to its slice of ``flat_grad`` (autograd then accumulates in place)."""
+        off = 0
+        for t in self.leaves:
+            k = t.numel()
+            t.grad = self.flat_grad[off:off + k].view(t.shape)
+            off += k
+
+    def zero_grad(self) -> None:
+        self.flat_grad.zero_()
+        if any(t.grad is None or t.grad.data_ptr() != self.flat_grad.data_ptr() + o * self.flat_grad.element_size()
+               for t, o in zip(self.leaves, self._offsets())):
+            self.attach_grads()
+
+    def _offsets(self):
+        off = 0
+        for t in self.leaves:
+            yield off
+            off += t.numel()
+
+    def _const(self, key, make):
+        """Device constants of the affine bijectors, built once (no host-to-device copy inside a captured step)."""
+        if key not in self._consts:
+            self._consts[key] = make()
+        return self._consts[key]
 
     @staticmethod
     def _unwrap(p):
@@ -119,19 +208,24 @@ class TorchChain:
         if name == "Reverse":
             return torch.flip(x, dims=(-1,)), zeros
         if name == "ShiftBounds":                                # bijectors.py:754-765
-            mn, mx = self._t(np.atleast_1d(args[0])), self._t(np.atleast_1d(args[1]))
             B = float(args[2]) if len(args) > 2 else 5.0
-            mean, hr = (mx + mn) / 2, (mx - mn) / 2
-            return B * (x - mean) / hr, zeros + torch.log(torch.prod(B / hr))
+
+            def make():
+                mn, mx = self._t(np.atleast_1d(args[0])), self._t(np.atleast_1d(args[1]))
+                mean, hr = (mx + mn) / 2, (mx - mn) / 2
+                return mean, hr, torch.log(torch.prod(B / hr))
+            mean, hr, logdet = self._const((id(info), "sb"), make)
+            return B * (x - mean) / hr, zeros + logdet
         if name == "StandardScaler":                             # bijectors.py:848-851
-            means, stds = self._t(args[0]), self._t(args[1])
+            means, stds = self._const((id(info), "ss"), lambda: (self._t(args[0]), self._t(args[1])))
             return (x - means) / stds, zeros + torch.log(1 / torch.prod(stds))
         if name == "Scale":                                      # bijectors.py:689-697
             s = float(args[0])
             return s * x, zeros + math.log(s ** x.shape[-1])
         if name == "InvSoftplus":                                # bijectors.py:350-358
-            idx = torch.as_tensor(np.atleast_1d(args[0]), device=self.device)
-            k = self._t(np.atleast_1d(args[1] if len(args) > 1 else 1))
+            idx, k = self._const((id(info), "isp"), lambda: (
+                torch.as_tensor(np.atleast_1d(args[0]), device=self.device),
+                self._t(np.atleast_1d(args[1] if len(args) > 1 else 1))))
             y = torch.log(-1 + torch.exp(k * x[:, idx])) / k
             out = x.clone()
             out[:, idx] = y
@@ -158,6 +252,9 @@ class TorchChain:
                     h = torch.nn.functional.leaky_relu(h, LEAKY_SLOPE)
             cpd = 3 * K - 1 + int(bool(periodic))
             h = h.reshape(-1, L, cpd)
+            if self.native_spline and not periodic and h.is_cuda and int(K) <= 64:
+                y, ld = _SplineStage.apply(h, lower, int(K), float(B))
+                return torch.cat([upper, y], dim=1), ld.sum(dim=1)
             Wl, Hl, Dl = h[..., :K], h[..., K:2 * K], h[..., 2 * K:]
             Wk = 2 * B * torch.softmax(Wl, dim=-1)               # bijectors.py:489-491
             Hk = 2 * B * torch.softmax(Hl, dim=-1)
@@ -213,27 +310,85 @@ def shard_batch(n: int, rank: int, world: int) -> Tuple[int, int]:
     return a, a + base + (1 if rank < rem else 0)
 
 
-def dp_step(chain: TorchChain, opt: torch.optim.Optimizer, x, cond, w, global_rows: Optional[int] = None) -> None:
-    """grad of -mean_over_the_GLOBAL_batch(w * log_prob) on this rank's rows, one all_reduce(sum) of the flat
-    gradient, Adam update (flow.py:961-981).  Rows whose log_prob is -inf carry no gradient (jnp.nan_to_num)."""
-    n = int(x.shape[0]) if global_rows is None else int(global_rows)
-    opt.zero_grad(set_to_none=True)
+def _grads(chain: TorchChain, x, cond, w, n: int) -> None:
+    """flat_grad <- d/d params of -sum_local(w * log_prob) / n, non-finite entries zeroed, summed over ranks."""
+    chain.zero_grad()
     if x.shape[0] > 0:
         lp = chain.log_prob(x, cond)
         fin = torch.isfinite(lp)
         loss = -(torch.where(fin, w * lp, torch.zeros_like(lp))).sum() / n
         loss.backward()
+    torch.nan_to_num_(chain.flat_grad, nan=0.0, posinf=0.0, neginf=0.0)
     d = _dist()
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in chain.leaves])
-    flat = torch.nan_to_num(flat, nan=0.0, posinf=0.0, neginf=0.0)
     if d is not None:
-        d.all_reduce(flat, op=d.ReduceOp.SUM)
-    off = 0
-    for p in chain.leaves:
-        k = p.numel()
-        p.grad = flat[off:off + k].reshape(p.shape).clone()
-        off += k
+        d.all_reduce(chain.flat_grad, op=d.ReduceOp.SUM)
+
+
+def dp_step(chain: TorchChain, opt, x, cond, w, global_rows: Optional[int] = None) -> None:
+    """grad of -mean_over_the_GLOBAL_batch(w * log_prob) on this rank's rows, one all_reduce(sum) of the flat
+    gradient, Adam update (flow.py:961-981).  Rows whose log_prob is -inf carry no gradient (jnp.nan_to_num).
+    ``opt`` is a torch optimizer over ``chain.leaves`` or a ``NativeAdam``."""
+    _grads(chain, x, cond, w, int(x.shape[0]) if global_rows is None else int(global_rows))
     opt.step()
+
+
+class NativeAdam:
+    """optax.adam(learning_rate) (flow.py:968-981) as one fused kernel over the chain's flat parameter buffer
+    (``pzb_adam_step``); moments and the step count live on the device, so a step can sit inside a CUDA graph."""
+
+    def __init__(self, chain: TorchChain, lr: float = 1e-3, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
+        if chain.flat.dtype != torch.float32 or not chain.flat.is_cuda:
+            raise ValueError("NativeAdam needs float32 parameters on a CUDA device")
+        self.chain, self.lr, self.b1, self.b2, self.eps = chain, lr, b1, b2, eps
+        self.m, self.v = torch.zeros_like(chain.flat), torch.zeros_like(chain.flat)
+        self.count = torch.zeros(1, dtype=torch.int32, device=chain.flat.device)
+
+    def step(self) -> None:
+        from ._native import check, lib
+        c = self.chain
+        check(lib().pzb_adam_step(c.flat.data_ptr(), c.flat_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                  c.flat.numel(), self.lr, self.b1, self.b2, self.eps, self.count.data_ptr(),
+                                  torch.cuda.current_stream(c.flat.device).cuda_stream))
+
+
+class GraphedStep:
+    """One optimisation step -- zero the flat gradient, forward, loss, backward, nan_to_num, all_reduce, Adam --
+    captured ONCE as a CUDA graph for a fixed local batch shape and replayed per batch: a step of the default 7-D
+    flow is ~300 kernels of a few microseconds each, so launching them one by one from Python is what bounds an
+    eager step.  Inputs are copied into static buffers; everything else (parameters, gradients, Adam moments,
+    step count) already lives at fixed device addresses."""
+
+    WARMUP = 2   # eager steps before capture (cuBLAS workspaces, NCCL communicator, cached constants)
+
+    def __init__(self, chain: TorchChain, opt: NativeAdam, rows: int, n_cols: int, n_cond: int, global_rows: int):
+        dev = chain.device
+        self.chain, self.opt, self.rows, self.global_rows = chain, opt, int(rows), int(global_rows)
+        self.x = torch.zeros(rows, n_cols, device=dev)
+        self.c = torch.zeros(rows, n_cond, device=dev) if n_cond else None
+        self.w = torch.zeros(rows, device=dev)
+        self.graph, self.seen = None, 0
+
+    def _load(self, x, cond, w):
+        self.x.copy_(x)
+        self.w.copy_(w)
+        if self.c is not None:
+            self.c.copy_(cond)
+
+    def __call__(self, x, cond, w) -> None:
+        self._load(x, cond, w)
+        if self.graph is not None:
+            self.graph.replay()
+            return
+        if self.seen < self.WARMUP:
+            self.seen += 1
+            dp_step(self.chain, self.opt, self.x, self.c, self.w, self.global_rows)
+            return
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            dp_step(self.chain, self.opt, self.x, self.c, self.w, self.global_rows)
+        self.graph = g
+        g.replay()            # capture records without executing: this replay IS the step for this batch
 
 
 def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, epochs: int = 100,
@@ -267,7 +422,8 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
         flow._condition_stds = np.where(stds != 0, stds, 1).astype(np.float32)
 
     chain = TorchChain(flow._bijector_info, flow._params[1], flow._latent_info, flow._params[0], flow._input_dim, dev)
-    opt = torch.optim.Adam(chain.leaves, lr=1e-3) if optimizer is None else optimizer(chain.leaves)
+    opt = NativeAdam(chain, lr=1e-3) if optimizer is None else optimizer(chain.leaves)
+    graphed: dict = {}
 
     def to_dev(a):
         return None if a is None else torch.as_tensor(np.asarray(a, dtype=np.float32), device=dev)
@@ -308,6 +464,7 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
     noise = torch.Generator(device=dev)
     noise.manual_seed(int(batch_seed))
     best_loss, best_vals, stall = math.inf, chain.numpy_params(), 0
+    use_graph = isinstance(opt, NativeAdam) and os.environ.get("PZB_TRAIN_GRAPH", "1") != "0"
     loop = range(epochs)
     if progress_bar:
         from tqdm import tqdm
@@ -324,7 +481,14 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
             cb = None if Cm is None else Cm[mine]
             if cb is not None and Ce is not None:
                 cb = cb + torch.randn(cb.shape, generator=noise, device=dev) * Ce[mine]
-            dp_step(chain, opt, xb, cb, Wd[mine], global_rows=len(sel))
+            if use_graph and len(sel) == batch_size and len(mine) > 0:
+                key = len(mine)
+                if key not in graphed:
+                    graphed[key] = GraphedStep(chain, opt, key, xb.shape[1], 0 if cb is None else cb.shape[1],
+                                               len(sel))
+                graphed[key](xb, cb, Wd[mine])
+            else:                                   # ragged last batch of the epoch, or a caller's own optimizer
+                dp_step(chain, opt, xb, cb, Wd[mine], global_rows=len(sel))
         losses.append(fused_loss(X_all, C_all, Wd))                             # flow.py:1088-1098
         if val_set is not None:
             val_losses.append(fused_loss(Xv, Cv, Wv))
