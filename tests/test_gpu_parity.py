@@ -901,6 +901,25 @@ def test_graphed_training_step_equals_the_eager_step():
     assert (a.flat - b.flat).abs().max().item() < 1e-6
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_data_parallel_training_two_gpus():
+    """Flow.train under torchrun, one rank per GPU: the captured step holds the NCCL all_reduce of the flat gradient;
+    parameters and losses come out identical on every rank and the loss falls."""
+    import json
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29731", os.path.join(here, "dp_train_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("DPRESULT ")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.loads(line[0][len("DPRESULT "):])
+    assert res["world"] == 2 and res["identical_params"] and res["identical_losses"]
+    assert len(res["losses"]) == 5 and res["losses"][-1] < res["losses"][0] - 0.5
+
+
 def test_one_plan_many_host_threads_and_streams():
     """include/pzflow_b200.h: a plan may be launched concurrently from several host threads / streams
     (device-pointer calls), and host-buffer calls on one plan serialise."""
