@@ -254,15 +254,15 @@ int pzb_error_eps(float *eps, int64_t n, int32_t W, int32_t stream_id, uint64_t 
 /* ---- training support (the optional data-parallel training step) ---------
  * The spline of a coupling stage for the loss -mean(w * log_prob) (pzflow/flow.py:961-965): softmax / softplus
  * knot construction, bin search, rational-quadratic spline and log-determinant (pzflow/bijectors.py:488-506,
- * pzflow/utils.py:64-227; non-periodic, forward direction) as one kernel, and its hand-derived backward.
- * logits [N, L, 3K-1] (the conditioner's output), x [N, L] (the transformed columns); forward writes y [N, L] and
+ * pzflow/utils.py:64-227; forward direction) as one kernel, and its hand-derived backward.
+ * logits [N, L, 3K-1] (3K when periodic; the conditioner's output), x [N, L] (the transformed columns); forward writes y [N, L] and
  * log_det [N, L] (per element; the caller sums over L).  backward takes grad_y [N, L] and grad_log_det [N, L]
  * and writes grad_logits [N, L, 3K-1] and grad_x [N, L].  The dense layers around it are plain GEMMs (cuBLAS). */
 int pzb_spline_train_forward(const float *logits, const float *x, int64_t N, int32_t L, int32_t K, float B,
-                             float *y, float *log_det, void *stream);
+                             int32_t periodic, float *y, float *log_det, void *stream);
 int pzb_spline_train_backward(const float *logits, const float *x, const float *grad_y,
                               const float *grad_log_det, int64_t N, int32_t L, int32_t K, float B,
-                              float *grad_logits, float *grad_x, void *stream);
+                              int32_t periodic, float *grad_logits, float *grad_x, void *stream);
 
 /* Adam over one flat fp32 parameter buffer (optax.adam(1e-3) as pzflow/flow.py:968-981 uses it; eps_root = 0).
  * step_dev is a device int32 holding the number of steps taken so far; the call increments it on the stream

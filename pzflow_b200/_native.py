@@ -107,9 +107,9 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "pzb_error_eps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p]),
     "pzb_spline_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
-                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pzb_spline_train_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
-                                            C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                            C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pzb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "pzb_log_prob_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

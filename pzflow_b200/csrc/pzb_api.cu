@@ -23,10 +23,11 @@ size_t tc_pack_bytes(const NscDev& st);
 void tc_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weights, void* dst);
 cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms,
                       void* workspace, cudaStream_t stream);
-cudaError_t launch_spline_train_fwd(const float* logits, const float* x, long long n_elems, int K, float B, float* y,
-                                    float* ld, cudaStream_t stream);
+cudaError_t launch_spline_train_fwd(const float* logits, const float* x, long long n_elems, int K, float B, int periodic,
+                                    float* y, float* ld, cudaStream_t stream);
 cudaError_t launch_spline_train_bwd(const float* logits, const float* x, const float* gy, const float* gld,
-                                    long long n_elems, int K, float B, float* glogits, float* gx, cudaStream_t stream);
+                                    long long n_elems, int K, float B, int periodic, float* glogits, float* gx,
+                                    cudaStream_t stream);
 cudaError_t launch_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
                              float eps, int* step, cudaStream_t stream);
 }  // namespace pzb
@@ -999,23 +1000,24 @@ int pzb_posterior_err(const pzb_plan* plan, const float* rest, const float* rest
 // ---------------------------------------------------------------------------------------------
 // Training support: the coupling stage's spline, forward and backward (nsf_train.cu)
 // ---------------------------------------------------------------------------------------------
-int pzb_spline_train_forward(const float* logits, const float* x, int64_t N, int32_t L, int32_t K, float B, float* y,
-                             float* log_det, void* stream) {
+int pzb_spline_train_forward(const float* logits, const float* x, int64_t N, int32_t L, int32_t K, float B,
+                             int32_t periodic, float* y, float* log_det, void* stream) {
   if (N < 0 || L < 1 || K < 2 || K > 64) return fail(PZB_ERR_INVALID, "spline_train_forward: bad shape (K in [2, 64])");
   if (N > 0 && (!logits || !x || !y || !log_det)) return fail(PZB_ERR_INVALID, "spline_train_forward: NULL buffer");
-  cudaError_t ce = launch_spline_train_fwd(logits, x, N * (long long)L, K, B, y, log_det, (cudaStream_t)stream);
+  cudaError_t ce = launch_spline_train_fwd(logits, x, N * (long long)L, K, B, periodic, y, log_det, (cudaStream_t)stream);
   if (ce != cudaSuccess) return cuda_fail(ce, "spline_train_forward launch");
   g_launches.fetch_add(1);
   return PZB_OK;
 }
 
 int pzb_spline_train_backward(const float* logits, const float* x, const float* grad_y, const float* grad_log_det,
-                              int64_t N, int32_t L, int32_t K, float B, float* grad_logits, float* grad_x, void* stream) {
+                              int64_t N, int32_t L, int32_t K, float B, int32_t periodic, float* grad_logits,
+                              float* grad_x, void* stream) {
   if (N < 0 || L < 1 || K < 2 || K > 64) return fail(PZB_ERR_INVALID, "spline_train_backward: bad shape (K in [2, 64])");
   if (N > 0 && (!logits || !x || !grad_y || !grad_log_det || !grad_logits || !grad_x))
     return fail(PZB_ERR_INVALID, "spline_train_backward: NULL buffer");
-  cudaError_t ce = launch_spline_train_bwd(logits, x, grad_y, grad_log_det, N * (long long)L, K, B, grad_logits, grad_x,
-                                           (cudaStream_t)stream);
+  cudaError_t ce = launch_spline_train_bwd(logits, x, grad_y, grad_log_det, N * (long long)L, K, B, periodic, grad_logits,
+                                           grad_x, (cudaStream_t)stream);
   if (ce != cudaSuccess) return cuda_fail(ce, "spline_train_backward launch");
   g_launches.fetch_add(1);
   return PZB_OK;

@@ -78,19 +78,19 @@ class _SplineStage(torch.autograd.Function):
     """The coupling stage's spline on the hand-written kernels of csrc/nsf_train.cu: forward
     ``pzb_spline_train_forward``, backward ``pzb_spline_train_backward`` (analytic gradient of the softmax /
     softplus knots, bin search and rational-quadratic spline + log-determinant w.r.t. the conditioner's logits and
-    the transformed columns).  Non-periodic splines; periodic ones take the torch-op restatement above."""
+    the transformed columns), periodic or not."""
 
     @staticmethod
-    def forward(ctx, logits, x, K, B):
+    def forward(ctx, logits, x, K, B, periodic=False):
         from ._native import check, lib
         logits, x = logits.contiguous().float(), x.contiguous().float()
         N, L = x.shape
         y, ld = torch.empty_like(x), torch.empty_like(x)
         s = torch.cuda.current_stream(x.device).cuda_stream
-        check(lib().pzb_spline_train_forward(logits.data_ptr(), x.data_ptr(), N, L, int(K), float(B), y.data_ptr(),
-                                             ld.data_ptr(), s))
+        check(lib().pzb_spline_train_forward(logits.data_ptr(), x.data_ptr(), N, L, int(K), float(B), int(bool(periodic)),
+                                             y.data_ptr(), ld.data_ptr(), s))
         ctx.save_for_backward(logits, x)
-        ctx.K, ctx.B = int(K), float(B)
+        ctx.K, ctx.B, ctx.periodic = int(K), float(B), int(bool(periodic))
         return y, ld
 
     @staticmethod
@@ -102,8 +102,8 @@ class _SplineStage(torch.autograd.Function):
         gl, gx = torch.empty_like(logits), torch.empty_like(x)
         s = torch.cuda.current_stream(x.device).cuda_stream
         check(lib().pzb_spline_train_backward(logits.data_ptr(), x.data_ptr(), gy.data_ptr(), gld.data_ptr(), N, L,
-                                              ctx.K, ctx.B, gl.data_ptr(), gx.data_ptr(), s))
-        return gl, gx, None, None
+                                              ctx.K, ctx.B, ctx.periodic, gl.data_ptr(), gx.data_ptr(), s))
+        return gl, gx, None, None, None
 
 
 class TorchChain:
@@ -252,8 +252,8 @@ class TorchChain:
                     h = torch.nn.functional.leaky_relu(h, LEAKY_SLOPE)
             cpd = 3 * K - 1 + int(bool(periodic))
             h = h.reshape(-1, L, cpd)
-            if self.native_spline and not periodic and h.is_cuda and int(K) <= 64:
-                y, ld = _SplineStage.apply(h, lower, int(K), float(B))
+            if self.native_spline and h.is_cuda and int(K) <= 64:
+                y, ld = _SplineStage.apply(h, lower, int(K), float(B), bool(periodic))
                 return torch.cat([upper, y], dim=1), ld.sum(dim=1)
             Wl, Hl, Dl = h[..., :K], h[..., K:2 * K], h[..., 2 * K:]
             Wk = 2 * B * torch.softmax(Wl, dim=-1)               # bijectors.py:489-491

@@ -798,28 +798,29 @@ def test_flow_train_reduces_the_loss_and_feeds_the_fused_kernels():
     assert ens.log_prob(data[:100]).shape == (100,)
 
 
-@pytest.mark.parametrize("K,L,B", [(16, 4, 5.0), (2, 1, 3.0), (32, 16, 5.0), (64, 3, 4.0)])
-def test_spline_train_kernels_match_autograd_of_the_restatement(K, L, B):
+@pytest.mark.parametrize("K,L,B,periodic", [(16, 4, 5.0, False), (2, 1, 3.0, False), (32, 16, 5.0, False),
+                                            (64, 3, 4.0, False), (16, 4, 5.0, True), (8, 2, 3.0, True)])
+def test_spline_train_kernels_match_autograd_of_the_restatement(K, L, B, periodic):
     """csrc/nsf_train.cu: forward values and the hand-derived backward against float64 torch autograd over
     train._rqs_forward (the restatement of pzflow/utils.py:64-227), including out-of-bounds and knot-adjacent x."""
     from pzflow_b200.train import _SplineStage, _rqs_forward
     g = torch.Generator().manual_seed(K * 100 + L)
     N = 3000
-    logits = (torch.randn(N, L, 3 * K - 1, generator=g) * 1.5).cuda()
+    logits = (torch.randn(N, L, 3 * K - 1 + int(periodic), generator=g) * 1.5).cuda()
     x = ((torch.rand(N, L, generator=g) * 2 - 1) * (B * 1.1)).cuda()
     x[0, 0], x[1, 0], x[2, 0] = -B, B, 0.0
     gy = torch.randn(N, L, generator=g).cuda()
     gl = torch.randn(N, generator=g).cuda()
 
     a, b = logits.clone().requires_grad_(True), x.clone().requires_grad_(True)
-    y, ld = _SplineStage.apply(a, b, K, B)
+    y, ld = _SplineStage.apply(a, b, K, B, periodic)
     ((y * gy).sum() + (ld.sum(dim=1) * gl).sum()).backward()
 
     a64, b64 = logits.double().requires_grad_(True), x.double().requires_grad_(True)
     W = 2 * B * torch.softmax(a64[..., :K], dim=-1)
     H = 2 * B * torch.softmax(a64[..., K:2 * K], dim=-1)
     D = torch.nn.functional.softplus(a64[..., 2 * K:])
-    y64, ld64 = _rqs_forward(b64, W, H, D, B, False)
+    y64, ld64 = _rqs_forward(b64, W, H, D, B, periodic)
     ((y64 * gy.double()).sum() + (ld64 * gl.double()).sum()).backward()
 
     # rows whose x sits within float32 rounding of a knot may pick the neighbouring bin: same value (the spline is
@@ -835,8 +836,9 @@ def test_spline_train_kernels_match_autograd_of_the_restatement(K, L, B):
     assert bad.mean() < 2e-3, bad.mean()
     okx = np.abs(gb - gb64) <= 2e-3 * np.abs(gb64) + 1e-4
     assert okx.mean() > 0.995
-    assert gb[0, 0] == _np(gy)[0, 0] and gb[1, 0] == _np(gy)[1, 0]          # out of bounds: identity
-    assert not ga[0, 0].any() and not ga[1, 0].any()
+    if not periodic:
+        assert gb[0, 0] == _np(gy)[0, 0] and gb[1, 0] == _np(gy)[1, 0]      # out of bounds: identity
+        assert not ga[0, 0].any() and not ga[1, 0].any()
     assert np.isfinite(ga).all() and np.isfinite(gb).all()
 
 
