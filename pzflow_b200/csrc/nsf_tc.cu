@@ -1,6 +1,7 @@
 // tcgen05 engine: fused chain kernel with ALL THREE conditioner GEMMs on the 5th-gen tensor cores
 // (sm_100a), for the default conditioner family (hidden_layers = 2, hidden_dim = 128, K = 16, at most
-// 8 conditioner inputs and 4 transformed columns: BASELINE configs 1-4).
+// 8 conditioner inputs and 16 data columns: BASELINE configs 1-4 and every default flow up to 16-D).
+// A coupling stage with more than 4 transformed columns runs as sub-stages of 4 (tc_sub_stages below).
 //
 // fp32 fidelity: every fp32 operand x is split x = hi + lo with hi = fp16(x), lo = fp16(x - hi)
 // (22 significant bits), and a GEMM is three kind::f16 MMAs, lo*hi + hi*lo + hi*hi, accumulated
@@ -59,7 +60,8 @@ constexpr int TC_EPI_THREADS = 512;
 constexpr int TC_THREADS = 608;                   // 16 epilogue warps + 2 MMA issuers + 1 loader
 constexpr int TC_IN_MAX = 8;
 constexpr int TC_L_MAX = 4;
-constexpr int TC_D_MAX = 8;
+constexpr int TC_D_MAX = 16;
+constexpr int TC_SEQ_MAX = 255;                   // sub-stages of one chain walk (uint8 tables in shared memory)
 constexpr int TC_MAX_CHUNK_TILES = 16;
 constexpr int TC_DIM_N = 48;                      // logit columns of one spline dimension (47 or 48 used)
 constexpr int TC_PASS_N = 96;                     // rows of one packed W3 tile: two spline dimensions
@@ -105,17 +107,26 @@ static int tc_log_det_levels(const PlanDev& hp) {
 // ------------------------------------------------------------------------------------------
 // host side: shape check + packing
 // ------------------------------------------------------------------------------------------
+// A coupling stage with more than four spline dimensions runs as ceil(L / 4) SUB-STAGES: each recomputes the
+// conditioner's two hidden layers from the same (untouched) conditioner inputs and evaluates its own four columns of
+// the output layer, so to the kernel a sub-stage is an ordinary stage with its own weight blob.
+__host__ __device__ inline int tc_sub_stages(int L) { return (L + TC_L_MAX - 1) / TC_L_MAX; }
+__host__ __device__ inline int tc_sub_dims(int L, int sub) { return min(TC_L_MAX, L - TC_L_MAX * sub); }
+
 bool tc_plan_supported(const PlanDev& hp) {
   if (hp.n_nsc < 1 || hp.D > TC_D_MAX) return false;
+  int total = 0;
   for (int s = 0; s < hp.n_nsc; ++s) {
     const NscDev& st = hp.nsc[s];
     if (st.n_dense != 3 || st.H != 128 || st.K != 16) return false;
-    if (st.U + st.C > TC_IN_MAX || st.L > TC_L_MAX || st.L < 1) return false;
+    if (st.U + st.C > TC_IN_MAX || st.L > TC_L_MAX * TC_SUB_MAX || st.L < 1) return false;
+    total += tc_sub_stages(st.L);
   }
-  return true;
+  return total <= TC_SEQ_MAX;
 }
 
-size_t tc_pack_bytes(const NscDev& st) { return (size_t)TcLayout::make(st.L).total; }
+int tc_stage_subs(const NscDev& st) { return tc_sub_stages(st.L); }
+size_t tc_pack_bytes(const NscDev& st, int sub) { return (size_t)TcLayout::make(tc_sub_dims(st.L, sub)).total; }
 
 static int pow2_scale_exp(const float* w, size_t n) {
   float m = 0.0f;
@@ -145,8 +156,9 @@ static inline void split_store(__half* hi, __half* lo, size_t idx, float v) {
 
 // state columns of a chunk row: x[0, D), log-det levels [D, D + n_lev), pending log-det halves (2),
 // conditions (C)
-void tc_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weights, void* dst) {
-  const TcLayout lay = TcLayout::make(st.L);
+void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* const* weights, void* dst) {
+  const int d0 = TC_L_MAX * sub, Ls = tc_sub_dims(st.L, sub);  // this sub-stage's spline dimensions [d0, d0 + Ls)
+  const TcLayout lay = TcLayout::make(Ls);
   unsigned char* base = static_cast<unsigned char*>(dst);
   memset(base, 0, lay.total);
   const float *W1 = weights[0], *b1 = weights[1], *W2 = weights[2], *b2 = weights[3], *W3 = weights[4],
@@ -163,9 +175,9 @@ void tc_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weig
     __half* lo = reinterpret_cast<__half*>(base + lay.w3 + p * TC_W3_PASS_BYTES + TC_W3_PASS_BYTES / 2);
     for (int j = 0; j < 2; ++j) {
       const int d = 2 * p + j;
-      if (d >= st.L) continue;
+      if (d >= Ls) continue;
       for (int q = 0; q < st.cpd; ++q) {
-        const int col = d * st.cpd + q, n = TC_DIM_N * j + q;
+        const int col = (d0 + d) * st.cpd + q, n = TC_DIM_N * j + q;
         for (int k = 0; k < 128; ++k) split_store(hi, lo, sw128_index(TC_PASS_N, n, k), W3[(size_t)k * out_dim + col] * s3);
       }
     }
@@ -183,8 +195,8 @@ void tc_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weig
   }
   float* par = reinterpret_cast<float*>(base + lay.par);
   for (int k = 0; k < 128; ++k) par[TC_PF_B2 + k] = b2[k];
-  for (int d = 0; d < st.L; ++d)
-    for (int q = 0; q < st.cpd; ++q) par[TC_PF_B3 + d * TC_DIM_N + q] = b3[d * st.cpd + q];
+  for (int d = 0; d < Ls; ++d)
+    for (int q = 0; q < st.cpd; ++q) par[TC_PF_B3 + d * TC_DIM_N + q] = b3[(d0 + d) * st.cpd + q];
   par[TC_PF_SCAL + 0] = ldexpf(1.0f, -e2);
   par[TC_PF_SCAL + 1] = ldexpf(1.0f, -e3);
   par[TC_PF_SCAL + 2] = st.B;
@@ -193,12 +205,12 @@ void tc_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weig
   const int cond_col0 = hp.D + tc_log_det_levels(hp) + 2;
   for (int i = 0; i < TC_IN_MAX; ++i)
     pi[TC_PI_KEY + i] = i < st.U ? (int)st.perm[i] : (i < in_dim ? cond_col0 + (i - st.U) : 0);
-  for (int d = 0; d < TC_L_MAX; ++d) pi[TC_PI_LOW + d] = d < st.L ? (int)st.perm[st.U + d] : 0;
+  for (int d = 0; d < TC_L_MAX; ++d) pi[TC_PI_LOW + d] = d < Ls ? (int)st.perm[st.U + d0 + d] : 0;
   pi[TC_PI_U] = st.U;
-  pi[TC_PI_L] = st.L;
+  pi[TC_PI_L] = Ls;
   pi[TC_PI_IN] = in_dim;
   pi[TC_PI_PERIODIC] = st.periodic;
-  pi[TC_PI_BINS] = st.bins_off;
+  pi[TC_PI_BINS] = st.bins_off + d0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -550,7 +562,9 @@ struct TcShared {
   uint64_t w1_free, w2_free, w3_free;      // both issuers' tcgen05.commit after the stage's last GEMM on that buffer
   uint64_t par_free[2];                    // 16 warp arrivals: every epilogue warp is done with that parameter buffer
   uint32_t tmem_base;
-  uint8_t order[MAX_NSC];  // coupling stages in walk order (index into PlanDev::nsc)
+  int n_seq;                    // sub-stages of one chain walk
+  uint8_t order[TC_SEQ_MAX + 1];  // sub-stages in walk order: coupling stage (index into PlanDev::nsc) ...
+  uint8_t sub[TC_SEQ_MAX + 1];    // ... and which four of its spline dimensions
 };
 
 struct TcSmem {  // byte offsets from the 1024-aligned base
@@ -667,7 +681,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
   uint32_t tid;
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));  // volatile: read once, never rematerialised as S2R
   const int warp = (int)(tid >> 5), lane = (int)(tid & 31);
-  const int D = plan->D, C = plan->C, ns = plan->n_steps, n_nsc = plan->n_nsc, n_lev = lp.n_lev;
+  const int D = plan->D, C = plan->C, ns = plan->n_steps, n_lev = lp.n_lev;
   const int CR = lp.chunk_tiles * TC_TILE;           // rows of state per column
   const int COL_PEND = D + n_lev, COL_COND = D + n_lev + 2;
 
@@ -695,8 +709,13 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
     int seen = 0;
     for (int si = 0; si < ns; ++si) {
       const StepDev step = plan->steps[INV ? ns - 1 - si : si];
-      if (step.kind == STEP_NSC) sh->order[seen++] = (uint8_t)step.idx;
+      if (step.kind != STEP_NSC) continue;
+      for (int sub = 0; sub < plan->nsc[step.idx].n_sub; ++sub) {
+        sh->order[seen] = (uint8_t)step.idx;
+        sh->sub[seen++] = (uint8_t)sub;
+      }
     }
+    sh->n_seq = seen;
   }
   if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(TC_BAR(tmem_base)), "n"(512)
@@ -772,162 +791,167 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         if (has_light) level = level_after(plan, INV, prev_end, si, level);
         prev_end = si + 1;
 
-        // parameter block of this stage (double buffered); previous-stage state writes of the row's other half
-        TC_TRACE_S(0);
-        mbar_wait(TC_BAR(par_full[0]) + 8u * (seq & 1), (uint32_t)((seq >> 1) & 1));
-        TC_TRACE_S(1);
-        named_bar_sync(2 + grp, TC_GROUP_THREADS);
-        TC_TRACE_S(2);
-        const float* par = reinterpret_cast<const float*>(base + sl.par + (seq & 1) * TC_PAR_BYTES);
-        const int* pint = reinterpret_cast<const int*>(par + TC_PI);
-        const int L = pint[TC_PI_L];
-        // The half that evaluates the last spline dimension finishes a tile last; the OTHER half writes the next
-        // tile's key operand once it is through with its own dimensions.
-        const int kw = L & 1;
+        // a stage with more than four spline dimensions runs as sub-stages of four (same conditioner inputs, own blob)
+        const int n_sub = plan->nsc[plan->steps[INV ? ns - 1 - si : si].idx].n_sub;
+        for (int sub = 0; sub < n_sub; ++sub) {
+          const bool light_now = has_light && sub == 0;
+          // parameter block of this stage (double buffered); previous-stage state writes of the row's other half
+          TC_TRACE_S(0);
+          mbar_wait(TC_BAR(par_full[0]) + 8u * (seq & 1), (uint32_t)((seq >> 1) & 1));
+          TC_TRACE_S(1);
+          named_bar_sync(2 + grp, TC_GROUP_THREADS);
+          TC_TRACE_S(2);
+          const float* par = reinterpret_cast<const float*>(base + sl.par + (seq & 1) * TC_PAR_BYTES);
+          const int* pint = reinterpret_cast<const int*>(par + TC_PI);
+          const int L = pint[TC_PI_L];
+          // The half that evaluates the last spline dimension finishes a tile last; the OTHER half writes the next
+          // tile's key operand once it is through with its own dimensions.
+          const int kw = L & 1;
 
-        // Between two coupling stages: fold the previous stage's log-det halves into their chain level and apply the
-        // non-NSC steps (e.g. an affine inside the chain), for every tile of this group, before any key is read.
-        if (pending || has_light) {
-          for (int q = gtid; q < my_tiles * TC_TILE; q += TC_GROUP_THREADS) {
-            float* st = state + (2 * (q >> 7) + grp) * TC_TILE + (q & (TC_TILE - 1));
-            if (pending) st[(D + pend_level) * CR] += st[COL_PEND * CR] + st[(COL_PEND + 1) * CR];
-            if (has_light) {
-              int lv = level_in;
-              light_steps_cols(plan, INV, light0, si, lv, st, CR);
-            }
-          }
-          if (has_light) named_bar_sync(2 + grp, TC_GROUP_THREADS);
-        }
-
-        // E0: the <= 8 conditioner inputs of a row and a constant 1 (bias row) as a K = 16 fp16 hi/lo A operand in
-        // Y[0,8) / Y[16,24).  One thread per row (half kw) writes it; the tile's first-layer GEMM then runs on the
-        // tensor pipe.  For tile k + 1 this happens while tile k's last spline dimension is still being evaluated.
-        auto write_keys = [&](int kk) {
-          const float* krow = state + (2 * kk + grp) * TC_TILE + lrow;
-          const int in_dim = pint[TC_PI_IN];
-          float key[TC_IN_MAX];
-#pragma unroll
-          for (int i = 0; i < TC_IN_MAX; ++i) key[i] = (i < in_dim) ? krow[pint[TC_PI_KEY + i] * CR] : 0.0f;
-          uint32_t rh[8], rl[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) split2(key[2 * j], key[2 * j + 1], rh[j], rl[j]);
-          rh[4] = 0x00003C00u;  // (1.0, 0): k = 8 multiplies the bias row of the W1 tile
-          rl[4] = 0u;
-#pragma unroll
-          for (int j = 5; j < 8; ++j) rh[j] = rl[j] = 0u;
-          tmem_st8(t_key, rh);
-          tmem_st8(t_key + 16u, rl);
-          tc_wait_st();
-        };
-        TC_TRACE_S(3);
-        if (half == kw) write_keys(0);
-        tc_fence_before();
-        warp_arrive(bar_key, lane);
-        TC_TRACE_S(4);
-
-        for (int k = 0; k < my_tiles; ++k) {
-          const int r = (2 * k + grp) * TC_TILE + lrow;  // row within the chunk (state is allocated for every tile)
-          float* srow = state + r;
-
-          // ---- E1: h1 = LeakyReLU(D1) (bias already in the GEMM), rewritten in place over this half's 64 columns of X ----
-          TC_TRACE(0);
-          mbar_wait(bar_d1, ph_d1);
-          ph_d1 ^= 1u;
-          tc_fence_after();
-#pragma unroll 1
-          for (int bt = 0; bt < 2; ++bt) {
-            float dv[32];
-            tmem_ld32(t_x + bt * 32, dv);
-            tc_wait_ld();
-            uint32_t rh[16], rl[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) split2(pz_leaky(dv[2 * j]), pz_leaky(dv[2 * j + 1]), rh[j], rl[j]);
-            tmem_st16(t_x + bt * 32, rh);
-            tmem_st16(t_x + bt * 32 + 16, rl);
-          }
-          tc_wait_st();
-          tc_fence_before();
-          warp_arrive(bar_ready, lane);
-          TC_TRACE(1);
-
-          // ---- E2: h2 = LeakyReLU(D * 2^-e2 + b2), rewritten in place over this half's accumulator columns ----
-          {
-            const float s2inv = par[TC_PF_SCAL];
-#pragma unroll 1
-            for (int bt = 0; bt < 2; ++bt) {
-              mbar_wait(bar_d2 + 8u * bt, ph_d2);  // this quarter of the hidden GEMM has landed
-              tc_fence_after();
-              if (bt == 0) TC_TRACE(2);
-              float dv[32];
-              tmem_ld32(t_y + bt * 32, dv);
-              tc_wait_ld();
-              const float* b2 = par + TC_PF_B2 + half * 64 + bt * 32;
-              uint32_t rh[16], rl[16];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 bb = *reinterpret_cast<const float4*>(b2 + q * 4);
-                const float h0 = pz_leaky(fmaf(dv[4 * q + 0], s2inv, bb.x));
-                const float h1 = pz_leaky(fmaf(dv[4 * q + 1], s2inv, bb.y));
-                const float h2 = pz_leaky(fmaf(dv[4 * q + 2], s2inv, bb.z));
-                const float h3 = pz_leaky(fmaf(dv[4 * q + 3], s2inv, bb.w));
-                split2(h0, h1, rh[2 * q], rl[2 * q]);
-                split2(h2, h3, rh[2 * q + 1], rl[2 * q + 1]);
+          // Between two coupling stages: fold the previous stage's log-det halves into their chain level and apply the
+          // non-NSC steps (e.g. an affine inside the chain), for every tile of this group, before any key is read.
+          if (pending || light_now) {
+            for (int q = gtid; q < my_tiles * TC_TILE; q += TC_GROUP_THREADS) {
+              float* st = state + (2 * (q >> 7) + grp) * TC_TILE + (q & (TC_TILE - 1));
+              if (pending) st[(D + pend_level) * CR] += st[COL_PEND * CR] + st[(COL_PEND + 1) * CR];
+              if (light_now) {
+                int lv = level_in;
+                light_steps_cols(plan, INV, light0, si, lv, st, CR);
               }
-              tmem_st16(t_y + bt * 32, rh);
-              tmem_st16(t_y + bt * 32 + 16, rl);
             }
+            if (light_now) named_bar_sync(2 + grp, TC_GROUP_THREADS);
           }
-          ph_d2 ^= 1u;
-          tc_wait_st();
-          tc_fence_before();
-          warp_arrive(bar_ready, lane);
-          TC_TRACE(3);
 
-          // ---- E3: logits -> knots -> spline; this thread takes the dimensions half, half + 2 ----
-          const bool more = k + 1 < my_tiles;
-          float ldsum = 0.0f;
-#pragma unroll 1
-          for (int d = half; d < L; d += 2) {
-            mbar_wait(bar_d3, ph_d3);
-            ph_d3 ^= 1u;
+          // E0: the <= 8 conditioner inputs of a row and a constant 1 (bias row) as a K = 16 fp16 hi/lo A operand in
+          // Y[0,8) / Y[16,24).  One thread per row (half kw) writes it; the tile's first-layer GEMM then runs on the
+          // tensor pipe.  For tile k + 1 this happens while tile k's last spline dimension is still being evaluated.
+          auto write_keys = [&](int kk) {
+            const float* krow = state + (2 * kk + grp) * TC_TILE + lrow;
+            const int in_dim = pint[TC_PI_IN];
+            float key[TC_IN_MAX];
+  #pragma unroll
+            for (int i = 0; i < TC_IN_MAX; ++i) key[i] = (i < in_dim) ? krow[pint[TC_PI_KEY + i] * CR] : 0.0f;
+            uint32_t rh[8], rl[8];
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) split2(key[2 * j], key[2 * j + 1], rh[j], rl[j]);
+            rh[4] = 0x00003C00u;  // (1.0, 0): k = 8 multiplies the bias row of the W1 tile
+            rl[4] = 0u;
+  #pragma unroll
+            for (int j = 5; j < 8; ++j) rh[j] = rl[j] = 0u;
+            tmem_st8(t_key, rh);
+            tmem_st8(t_key + 16u, rl);
+            tc_wait_st();
+          };
+          TC_TRACE_S(3);
+          if (half == kw) write_keys(0);
+          tc_fence_before();
+          warp_arrive(bar_key, lane);
+          TC_TRACE_S(4);
+
+          for (int k = 0; k < my_tiles; ++k) {
+            const int r = (2 * k + grp) * TC_TILE + lrow;  // row within the chunk (state is allocated for every tile)
+            float* srow = state + r;
+
+            // ---- E1: h1 = LeakyReLU(D1) (bias already in the GEMM), rewritten in place over this half's 64 columns of X ----
+            TC_TRACE(0);
+            mbar_wait(bar_d1, ph_d1);
+            ph_d1 ^= 1u;
             tc_fence_after();
-            TC_TRACE(d < 2 ? 4 : 6);
-            float raw[48];
-            tmem_ld32(t_x, raw);
-            tmem_ld16(t_x + 32, raw + 32);
-            tc_wait_ld();
-            tc_fence_before();
-            warp_arrive(bar_free, lane);  // accumulator buffer drained: the next pass may overwrite it
-            if (d + 2 >= L && more && half != kw) warp_arrive(bar_key, lane);  // my last dimension: X is drained on my side
-            const int col = pint[TC_PI_LOW + d];
-            const float xin = srow[col * CR];
-            float y, ldd;
-            int idx;
-            spline_dim<INV>(raw, par + TC_PF_B3 + d * TC_DIM_N, par[TC_PF_SCAL + 1], xin, par[TC_PF_SCAL + 2],
-                            par[TC_PF_SCAL + 3], pint[TC_PI_PERIODIC] != 0, y, ldd, idx);
-            ldsum += ldd;
-            srow[col * CR] = y;
-            TC_TRACE(d < 2 ? 5 : 7);
-            if (args.bins != nullptr && r < nrows)
-              args.bins[(row0 + r) * plan->n_spline_dims + pint[TC_PI_BINS] + d] = idx;
-          }
-          srow[(COL_PEND + half) * CR] = INV ? -ldsum : ldsum;
-          if (half == kw) {
-            // every output pass of this tile has completed, so Y is free: write the next tile's key operand
-            mbar_wait(bar_g3, ph_g3);
-            ph_g3 ^= 1u;
-            if (more) {
-              tc_fence_after();
-              write_keys(k + 1);
-              tc_fence_before();
-              warp_arrive(bar_key, lane);
+  #pragma unroll 1
+            for (int bt = 0; bt < 2; ++bt) {
+              float dv[32];
+              tmem_ld32(t_x + bt * 32, dv);
+              tc_wait_ld();
+              uint32_t rh[16], rl[16];
+  #pragma unroll
+              for (int j = 0; j < 16; ++j) split2(pz_leaky(dv[2 * j]), pz_leaky(dv[2 * j + 1]), rh[j], rl[j]);
+              tmem_st16(t_x + bt * 32, rh);
+              tmem_st16(t_x + bt * 32 + 16, rl);
             }
+            tc_wait_st();
+            tc_fence_before();
+            warp_arrive(bar_ready, lane);
+            TC_TRACE(1);
+
+            // ---- E2: h2 = LeakyReLU(D * 2^-e2 + b2), rewritten in place over this half's accumulator columns ----
+            {
+              const float s2inv = par[TC_PF_SCAL];
+  #pragma unroll 1
+              for (int bt = 0; bt < 2; ++bt) {
+                mbar_wait(bar_d2 + 8u * bt, ph_d2);  // this quarter of the hidden GEMM has landed
+                tc_fence_after();
+                if (bt == 0) TC_TRACE(2);
+                float dv[32];
+                tmem_ld32(t_y + bt * 32, dv);
+                tc_wait_ld();
+                const float* b2 = par + TC_PF_B2 + half * 64 + bt * 32;
+                uint32_t rh[16], rl[16];
+  #pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 bb = *reinterpret_cast<const float4*>(b2 + q * 4);
+                  const float h0 = pz_leaky(fmaf(dv[4 * q + 0], s2inv, bb.x));
+                  const float h1 = pz_leaky(fmaf(dv[4 * q + 1], s2inv, bb.y));
+                  const float h2 = pz_leaky(fmaf(dv[4 * q + 2], s2inv, bb.z));
+                  const float h3 = pz_leaky(fmaf(dv[4 * q + 3], s2inv, bb.w));
+                  split2(h0, h1, rh[2 * q], rl[2 * q]);
+                  split2(h2, h3, rh[2 * q + 1], rl[2 * q + 1]);
+                }
+                tmem_st16(t_y + bt * 32, rh);
+                tmem_st16(t_y + bt * 32 + 16, rl);
+              }
+            }
+            ph_d2 ^= 1u;
+            tc_wait_st();
+            tc_fence_before();
+            warp_arrive(bar_ready, lane);
+            TC_TRACE(3);
+
+            // ---- E3: logits -> knots -> spline; this thread takes the dimensions half, half + 2 ----
+            const bool more = k + 1 < my_tiles;
+            float ldsum = 0.0f;
+  #pragma unroll 1
+            for (int d = half; d < L; d += 2) {
+              mbar_wait(bar_d3, ph_d3);
+              ph_d3 ^= 1u;
+              tc_fence_after();
+              TC_TRACE(d < 2 ? 4 : 6);
+              float raw[48];
+              tmem_ld32(t_x, raw);
+              tmem_ld16(t_x + 32, raw + 32);
+              tc_wait_ld();
+              tc_fence_before();
+              warp_arrive(bar_free, lane);  // accumulator buffer drained: the next pass may overwrite it
+              if (d + 2 >= L && more && half != kw) warp_arrive(bar_key, lane);  // my last dimension: X is drained on my side
+              const int col = pint[TC_PI_LOW + d];
+              const float xin = srow[col * CR];
+              float y, ldd;
+              int idx;
+              spline_dim<INV>(raw, par + TC_PF_B3 + d * TC_DIM_N, par[TC_PF_SCAL + 1], xin, par[TC_PF_SCAL + 2],
+                              par[TC_PF_SCAL + 3], pint[TC_PI_PERIODIC] != 0, y, ldd, idx);
+              ldsum += ldd;
+              srow[col * CR] = y;
+              TC_TRACE(d < 2 ? 5 : 7);
+              if (args.bins != nullptr && r < nrows)
+                args.bins[(row0 + r) * plan->n_spline_dims + pint[TC_PI_BINS] + d] = idx;
+            }
+            srow[(COL_PEND + half) * CR] = INV ? -ldsum : ldsum;
+            if (half == kw) {
+              // every output pass of this tile has completed, so Y is free: write the next tile's key operand
+              mbar_wait(bar_g3, ph_g3);
+              if (more) {
+                tc_fence_after();
+                write_keys(k + 1);
+                tc_fence_before();
+                warp_arrive(bar_key, lane);
+              }
+            }
+            ph_g3 ^= 1u;  // g3_done completes once per tile: BOTH halves count it (kw changes with the stage's L)
           }
+          warp_arrive(TC_BAR(par_free[0]) + 8u * (seq & 1), lane);
+          pending = true;
+          pend_level = level;
+          ++seq;
         }
-        warp_arrive(TC_BAR(par_free[0]) + 8u * (seq & 1), lane);
-        pending = true;
-        pend_level = level;
-        ++seq;
       }
       named_bar_sync(2 + grp, TC_GROUP_THREADS);
 
@@ -954,13 +978,15 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
   } else {
     // control warps run converged (all 32 lanes wait on the mbarriers); one elected lane issues
     const uint32_t sb = smem_u32(base);
-    const int total_seq = my_chunks * n_nsc;
-    // coupling stage (walk order) of sequence number s, and the tile count of its chunk
+    const int n_seq = sh->n_seq;
+    const int total_seq = my_chunks * n_seq;
+    // coupling stage (walk order) and sub-stage of sequence number s, and the tile count of its chunk
     auto stage_of = [&](int s) -> const NscDev& {
-      return plan->nsc[__shfl_sync(0xffffffffu, (int)sh->order[s % n_nsc], 0)];
+      return plan->nsc[__shfl_sync(0xffffffffu, (int)sh->order[s % n_seq], 0)];
     };
+    auto sub_of = [&](int s) -> int { return __shfl_sync(0xffffffffu, (int)sh->sub[s % n_seq], 0); };
     auto tiles_of = [&](int s) -> int {
-      const long long row0 = ((long long)blockIdx.x + (long long)(s / n_nsc) * gridDim.x) * chunk_rows;
+      const long long row0 = ((long long)blockIdx.x + (long long)(s / n_seq) * gridDim.x) * chunk_rows;
       const int nrows = (int)min(chunk_rows, args.N - row0);
       return max(2, (nrows + TC_TILE - 1) / TC_TILE);
     };
@@ -980,7 +1006,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       uint32_t ph_ready = 0u, ph_key = 0u;
       uint32_t np0 = 0u, np1 = 0u;  // passes issued so far into each accumulator buffer
       for (int s = 0; s < total_seq; ++s) {
-        const int L = __shfl_sync(0xffffffffu, stage_of(s).L, 0);
+        const int L = __shfl_sync(0xffffffffu, tc_sub_dims(stage_of(s).L, sub_of(s)), 0);
         const int my_tiles = (tiles_of(s) - g + 1) / 2;
         for (int k = 0; k < my_tiles; ++k) {
           // ---- first layer: keys (Y[0,24), K = 16) x W1 tile -> X, fp32, bias included ----
@@ -1076,8 +1102,9 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       // =============================== weight streamer ===============================
       for (int s = 0; s < total_seq; ++s) {
         const NscDev& st = stage_of(s);
-        const TcLayout lay = TcLayout::make(st.L);
-        const uint8_t* src = static_cast<const uint8_t*>(st.tc.blob);
+        const int sub = sub_of(s);
+        const TcLayout lay = TcLayout::make(tc_sub_dims(st.L, sub));
+        const uint8_t* src = static_cast<const uint8_t*>(st.tc[sub].blob);
         {  // parameter block: buffer s & 1 was last used by stage s - 2
           if (s >= 2) mbar_wait(TC_BAR(par_free[0]) + 8u * (s & 1), (uint32_t)(((s >> 1) - 1) & 1));
           const uint32_t bar = TC_BAR(par_full[0]) + 8u * (s & 1);
@@ -1128,7 +1155,7 @@ cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs
   (void)workspace;
   TcLaunch lp;
   lp.max_pass = 1;
-  for (int s = 0; s < hp.n_nsc; ++s) lp.max_pass = max(lp.max_pass, (hp.nsc[s].L + 1) / 2);
+  for (int s = 0; s < hp.n_nsc; ++s) lp.max_pass = max(lp.max_pass, (min(hp.nsc[s].L, TC_L_MAX) + 1) / 2);
   lp.n_lev = tc_log_det_levels(hp);
   lp.state_cols = hp.D + lp.n_lev + 2 + hp.C;
   // rows per chunk: as many 128-row tiles as shared memory holds, fewer when that leaves SMs idle

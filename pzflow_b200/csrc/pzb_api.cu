@@ -19,8 +19,9 @@ namespace pzb {
 cudaError_t launch_simt(const PlanDev* d_plan, const LaunchArgs& args, int D, int C, int Lmax,
                         int act_rows, bool pingpong, int num_sms, cudaStream_t stream);
 bool tc_plan_supported(const PlanDev& hp);
-size_t tc_pack_bytes(const NscDev& st);
-void tc_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weights, void* dst);
+int tc_stage_subs(const NscDev& st);
+size_t tc_pack_bytes(const NscDev& st, int sub);
+void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* const* weights, void* dst);
 cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms,
                       void* workspace, cudaStream_t stream);
 cudaError_t launch_spline_train_fwd(const float* logits, const float* x, long long n_elems, int K, float B, int periodic,
@@ -482,7 +483,8 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
   size_t tc_off = align_up(blob, 1024);
   size_t tc_total = 0;
   if (plan->tc_ok) {
-    for (int s = 0; s < hp.n_nsc; ++s) tc_total += align_up(tc_pack_bytes(hp.nsc[s]), 1024);
+    for (int s = 0; s < hp.n_nsc; ++s)
+      for (int sub = 0; sub < tc_stage_subs(hp.nsc[s]); ++sub) tc_total += align_up(tc_pack_bytes(hp.nsc[s], sub), 1024);
   }
   const size_t total = tc_off + tc_total;
 
@@ -541,11 +543,14 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
     size_t o = tc_off;
     for (const Pending& pe : pend) {
       NscDev& st = hp.nsc[pe.nsc_idx];
-      const size_t nb = tc_pack_bytes(st);
-      tc_pack_stage(hp, st, pe.weights, hblob.data() + o);
-      st.tc.blob = dbase + o;
-      st.tc.blob_bytes = (int)nb;
-      o += align_up(nb, 1024);
+      st.n_sub = tc_stage_subs(st);
+      for (int sub = 0; sub < st.n_sub; ++sub) {
+        const size_t nb = tc_pack_bytes(st, sub);
+        tc_pack_stage(hp, st, sub, pe.weights, hblob.data() + o);
+        st.tc[sub].blob = dbase + o;
+        st.tc[sub].blob_bytes = (int)nb;
+        o += align_up(nb, 1024);
+      }
     }
   }
   ce = cudaMemcpy(plan->d_weights, hblob.data(), hblob.size(), cudaMemcpyHostToDevice);

@@ -44,11 +44,14 @@ struct TcLayerDev {
   int blob_bytes;
 };
 
+constexpr int TC_SUB_MAX = 4;  // tensor-core engine: a coupling stage's spline dimensions are taken four at a time
+
 struct NscDev {
   int U, L, C, K, cpd, dpc, periodic, n_dense, H, Hpad, bins_off;
   float B;
   DenseDev dense[MAX_DENSE];
-  TcLayerDev tc;
+  int n_sub;                     // tensor-core sub-stages of this stage: ceil(L / 4)
+  TcLayerDev tc[TC_SUB_MAX];
   int16_t perm[MAX_D];  // logical column j lives in physical column perm[j]
 };
 

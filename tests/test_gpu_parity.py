@@ -342,6 +342,68 @@ def test_odd_shapes_simt(info, D, C):
     assert_noise_floor("odd inverse ld", _np(ldi), ldi32, ldi64, **kw)
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("D,C", [(9, 0), (12, 1), (16, 0)])
+def test_wide_default_flows_run_as_sub_stages(D, C, engine):
+    """Default flows (pzflow/flow.py:314-322: K = 16, hidden 128) with more than eight columns: a coupling stage then
+    has more than four spline dimensions and the tensor-core engine takes them four at a time (sub-stages); both
+    engines against the oracle, bin indices included."""
+    cfg = F.default_flow(D, -np.ones(D), np.ones(D), n_conditions=C, seed=D)
+    plan = _plan(cfg, engine)
+    assert plan.tc_supported
+    rng = np.random.default_rng(D)
+    n = 3000                                             # 24 tiles: ragged last chunk, both epilogue groups busy
+    X = rng.uniform(-1.02, 1.02, size=(n, D)).astype(np.float32)
+    cond = rng.normal(size=(n, max(C, 1))).astype(np.float32) if C else np.zeros((n, 1), np.float32)
+    ct = torch.from_numpy(cond) if C else None
+    bi, li, p64 = _o64(cfg)
+    ob = []
+    o32 = O.flow_log_prob(bi, li, cfg["params"], X, cond, bins=ob)
+    o64 = O.flow_log_prob(bi, li, p64, X.astype(np.float64), cond.astype(np.float64))
+    lp, bins = plan.log_prob(torch.from_numpy(X), ct, return_bins=True)
+    assert_noise_floor(f"wide D={D} log_prob [{engine}]", _np(lp), o32, o64, ratio=2.0, slack=1e-5, below=LP_UNDERFLOW)
+    flips, rows, total = count_bin_flips(_np(bins), np.concatenate(ob, axis=1))
+    print(f"BINS wide D={D} [{engine}] flipped {flips} of {total}")
+    assert flips <= max(3, int(2e-4 * total))
+    u32, ld32 = O.apply_bijector(bi, cfg["params"][1], X, cond)
+    u64, ld64 = O.apply_bijector(bi, p64[1], X.astype(np.float64), cond.astype(np.float64))
+    u, ld = plan.forward(torch.from_numpy(X), ct)
+    assert_noise_floor(f"wide D={D} forward u", _np(u), u32, u64, ratio=2.0, slack=2e-6)
+    assert_noise_floor(f"wide D={D} forward ld", _np(ld), ld32, ld64, ratio=2.0, slack=1e-5)
+    x32, _ = O.apply_bijector(bi, cfg["params"][1], u32, cond, inverse=True)
+    x64, _ = O.apply_bijector(bi, p64[1], u32.astype(np.float64), cond.astype(np.float64), inverse=True)
+    xi, _ = plan.inverse(torch.from_numpy(u32), ct)
+    assert_noise_floor(f"wide D={D} inverse x", _np(xi), x32, x64, ratio=2.0, slack=2e-6, max_class_mismatch=3)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_stages_with_different_spline_dim_counts(engine):
+    """Coupling stages with 1, 3 and 4 transformed dimensions in one chain: the tensor-core engine's per-stage
+    bookkeeping (which half of a row's threads writes the next key operand) changes from stage to stage."""
+    info = ("Chain", (("ShiftBounds", (-np.ones(6, np.float32), np.ones(6, np.float32), 4.0)),
+                      F.rolling_info(2, 1, 16, 5, 2, 128, 1, 0), F.rolling_info(3, 1, 16, 5, 2, 128, 4, 0),
+                      F.rolling_info(2, 2, 16, 5, 2, 128, 3, 0), F.rolling_info(2, 1, 16, 5, 2, 128, 2, 0)))
+    rng = np.random.default_rng(11)
+    params = O.synth_bijector_params(info, 6, rng)
+    cfg = dict(bijector_info=info, latent_info=("CentBeta13", (6, 5)), params=((), params), input_dim=6)
+    plan = _plan(cfg, engine)
+    n = 5000
+    X = rng.uniform(-1.02, 1.02, size=(n, 6)).astype(np.float32)
+    bi, li, p64 = _o64(cfg)
+    ob = []
+    o32 = O.flow_log_prob(bi, li, cfg["params"], X, bins=ob)
+    o64 = O.flow_log_prob(bi, li, p64, X.astype(np.float64))
+    lp, bins = plan.log_prob(torch.from_numpy(X), return_bins=True)
+    assert_noise_floor(f"mixed L log_prob [{engine}]", _np(lp), o32, o64, ratio=2.0, slack=1e-5, below=LP_UNDERFLOW)
+    flips, rows, total = count_bin_flips(_np(bins), np.concatenate(ob, axis=1))
+    assert flips <= max(3, int(2e-4 * total))
+    u32, _ = O.apply_bijector(bi, cfg["params"][1], X, np.zeros((n, 1), np.float32))
+    x32, _ = O.apply_bijector(bi, cfg["params"][1], u32, np.zeros((n, 1), np.float32), inverse=True)
+    x64, _ = O.apply_bijector(bi, p64[1], u32.astype(np.float64), np.zeros((n, 1)), inverse=True)
+    xi, _ = plan.inverse(torch.from_numpy(u32))
+    assert_noise_floor(f"mixed L inverse [{engine}]", _np(xi), x32, x64, ratio=2.0, slack=2e-6, max_class_mismatch=3)
+
+
 def test_empty_and_ragged_inputs():
     ex = F.example_flow()
     plan = _plan(ex, "simt")
