@@ -1,6 +1,6 @@
 // tcgen05 engine: fused chain kernel with ALL THREE conditioner GEMMs on the 5th-gen tensor cores
 // (sm_100a), for the default conditioner family (hidden_layers = 2, hidden_dim = 128, K = 16, at most
-// 8 conditioner inputs and 16 data columns: BASELINE configs 1-4 and every default flow up to 16-D).
+// 15 conditioner inputs and 31 data columns: BASELINE configs 1-4 and every default flow up to 30-D).
 // A coupling stage with more than 4 transformed columns runs as sub-stages of 4 (tc_sub_stages below).
 //
 // fp32 fidelity: every fp32 operand x is split x = hi + lo with hi = fp16(x), lo = fp16(x - hi)
@@ -13,7 +13,7 @@
 //     row, and TWO threads share a row (warp w and w+4 of the group address the same TMEM lane
 //     quarter): "half" h does hidden columns [64h, 64h+64) in E1/E2 and the spline dimensions
 //     h, h+2 in E3.  Per tile and coupling stage:
-//       E0  the <= 8 conditioner inputs + a constant 1 -> K = 16 A operand in Y[0,24)   (1 thread/row)
+//       E0  the <= 15 conditioner inputs + a constant 1 -> K = 16 A operand in Y[0,24)  (1 thread/row)
 //       G1  keys x W1 tile (bias row included) -> X                                      3 MMAs
 //       E1  X: LeakyReLU, fp16 hi/lo split, rewritten in place
 //       G2  X x W2 -> Y in four N = 32 quarters, one commit each, alternating between the halves,
@@ -58,9 +58,9 @@ constexpr int TC_TILE = 128;
 constexpr int TC_GROUP_THREADS = 256;
 constexpr int TC_EPI_THREADS = 512;
 constexpr int TC_THREADS = 608;                   // 16 epilogue warps + 2 MMA issuers + 1 loader
-constexpr int TC_IN_MAX = 8;
+constexpr int TC_IN_MAX = 15;                     // conditioner inputs: K = 16 minus the bias row
 constexpr int TC_L_MAX = 4;
-constexpr int TC_D_MAX = 16;
+constexpr int TC_D_MAX = 31;
 constexpr int TC_SEQ_MAX = 255;                   // sub-stages of one chain walk (uint8 tables in shared memory)
 constexpr int TC_MAX_CHUNK_TILES = 16;
 constexpr int TC_DIM_N = 48;                      // logit columns of one spline dimension (47 or 48 used)
@@ -72,11 +72,11 @@ constexpr int TC_W1_BYTES = 2 * 128 * 16 * 2;     // fp16 hi + lo [128 x 16] til
 constexpr int TC_PF_B2 = 0;
 constexpr int TC_PF_B3 = TC_PF_B2 + 128;
 constexpr int TC_PF_SCAL = TC_PF_B3 + 2 * TC_PASS_N;  // s2inv, s3inv, B, 1/(2B)
-constexpr int TC_PI = TC_PF_SCAL + 4;                 // ints: key_col[8], low_col[4], U, L, in_dim, periodic, bins_off
-constexpr int TC_PI_KEY = 0, TC_PI_LOW = 8, TC_PI_U = 12, TC_PI_L = 13, TC_PI_IN = 14, TC_PI_PERIODIC = 15,
-              TC_PI_BINS = 16;
-constexpr int TC_PAR_FLOATS = TC_PI + 24;
-constexpr int TC_PAR_BYTES = TC_PAR_FLOATS * 4;   // 1392, a multiple of 16
+constexpr int TC_PI = TC_PF_SCAL + 4;                 // ints: key_col[16], low_col[4], U, L, in_dim, periodic, bins_off
+constexpr int TC_PI_KEY = 0, TC_PI_LOW = 16, TC_PI_U = 20, TC_PI_L = 21, TC_PI_IN = 22, TC_PI_PERIODIC = 23,
+              TC_PI_BINS = 24;
+constexpr int TC_PAR_FLOATS = TC_PI + 32;
+constexpr int TC_PAR_BYTES = TC_PAR_FLOATS * 4;   // 1424, a multiple of 16
 constexpr int TC_SMEM_MAX = 232448;               // 227 KB opt-in limit per CTA
 static_assert(TC_PAR_BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 
@@ -182,14 +182,15 @@ void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* co
       }
     }
   }
-  {  // first layer as a [128 x 16] B operand, K-major without swizzle: K = (key_0 .. key_{in-1}, 0.., 1 at k = 8)
+  {  // first layer as a [128 x 16] B operand, K-major without swizzle: K = (key_0 .. key_7, 1 (bias row, k = 8), key_8 .. key_14)
      // so the bias rides in the GEMM.  Unscaled: |W1| and b1 are O(1), and the lo parts of small weights are
      // fp16 subnormals, which the tensor core takes at full precision of their 2^-24 grid.
     __half* hi = reinterpret_cast<__half*>(base + lay.w1);
     __half* lo = reinterpret_cast<__half*>(base + lay.w1 + TC_W1_BYTES / 2);
     for (int n = 0; n < 128; ++n)
-      for (int k = 0; k < 16; ++k) {
-        const float v = k < in_dim ? W1[k * 128 + n] : (k == 8 ? b1[n] : 0.0f);
+      for (int k = 0; k < 16; ++k) {  // k = 8 is the bias row; inputs 8.. sit one row further up
+        const int i = k < 8 ? k : k - 1;
+        const float v = k == 8 ? b1[n] : (i < in_dim ? W1[i * 128 + n] : 0.0f);
         split_store(hi, lo, w1_index(n, k), v);
       }
   }
@@ -822,22 +823,30 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             if (light_now) named_bar_sync(2 + grp, TC_GROUP_THREADS);
           }
 
-          // E0: the <= 8 conditioner inputs of a row and a constant 1 (bias row) as a K = 16 fp16 hi/lo A operand in
+          // E0: the <= 15 conditioner inputs of a row and a constant 1 (bias row) as a K = 16 fp16 hi/lo A operand in
           // Y[0,8) / Y[16,24).  One thread per row (half kw) writes it; the tile's first-layer GEMM then runs on the
           // tensor pipe.  For tile k + 1 this happens while tile k's last spline dimension is still being evaluated.
           auto write_keys = [&](int kk) {
             const float* krow = state + (2 * kk + grp) * TC_TILE + lrow;
             const int in_dim = pint[TC_PI_IN];
-            float key[TC_IN_MAX];
-  #pragma unroll
-            for (int i = 0; i < TC_IN_MAX; ++i) key[i] = (i < in_dim) ? krow[pint[TC_PI_KEY + i] * CR] : 0.0f;
+            float key[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) key[i] = (i < in_dim) ? krow[pint[TC_PI_KEY + i] * CR] : 0.0f;
             uint32_t rh[8], rl[8];
-  #pragma unroll
+#pragma unroll
             for (int j = 0; j < 4; ++j) split2(key[2 * j], key[2 * j + 1], rh[j], rl[j]);
-            rh[4] = 0x00003C00u;  // (1.0, 0): k = 8 multiplies the bias row of the W1 tile
-            rl[4] = 0u;
-  #pragma unroll
-            for (int j = 5; j < 8; ++j) rh[j] = rl[j] = 0u;
+            if (in_dim <= 8) {  // (uniform branch) the usual case: k = 8 is the constant 1 of the bias row, k > 8 unused
+              rh[4] = 0x00003C00u;
+              rl[4] = 0u;
+#pragma unroll
+              for (int j = 5; j < 8; ++j) rh[j] = rl[j] = 0u;
+            } else {            // inputs 8..14 ride in k = 9..15
+#pragma unroll
+              for (int i = 0; i < 7; ++i) key[i] = (8 + i < in_dim) ? krow[pint[TC_PI_KEY + 8 + i] * CR] : 0.0f;
+              split2(1.0f, key[0], rh[4], rl[4]);
+#pragma unroll
+              for (int j = 0; j < 3; ++j) split2(key[1 + 2 * j], key[2 + 2 * j], rh[5 + j], rl[5 + j]);
+            }
             tmem_st8(t_key, rh);
             tmem_st8(t_key + 16u, rl);
             tc_wait_st();

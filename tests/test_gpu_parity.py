@@ -343,11 +343,12 @@ def test_odd_shapes_simt(info, D, C):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("D,C", [(9, 0), (12, 1), (16, 0)])
+@pytest.mark.parametrize("D,C", [(9, 0), (12, 1), (16, 0), (20, 3), (1, 12), (7, 9)])
 def test_wide_default_flows_run_as_sub_stages(D, C, engine):
     """Default flows (pzflow/flow.py:314-322: K = 16, hidden 128) with more than eight columns: a coupling stage then
-    has more than four spline dimensions and the tensor-core engine takes them four at a time (sub-stages); both
-    engines against the oracle, bin indices included."""
+    has more than four spline dimensions and the tensor-core engine takes them four at a time (sub-stages); and with
+    more than eight conditioner inputs (columns + conditions), which ride above the bias row of the K = 16 key
+    operand.  Both engines against the oracle, bin indices included."""
     cfg = F.default_flow(D, -np.ones(D), np.ones(D), n_conditions=C, seed=D)
     plan = _plan(cfg, engine)
     assert plan.tc_supported
