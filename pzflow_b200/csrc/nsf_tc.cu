@@ -1,5 +1,6 @@
 // tcgen05 engine: fused chain kernel with ALL THREE conditioner GEMMs on the 5th-gen tensor cores
-// (sm_100a), for the default conditioner family (hidden_layers = 2, hidden_dim = 128, K = 16, at most
+// (sm_100a), for the default conditioner family (hidden_layers = 2, hidden_dim <= 128, K <= 16 -- narrower
+// shapes are padded into 128 / 16 by the packer, exactly -- at most
 // 15 conditioner inputs and 31 data columns: BASELINE configs 1-4 and every default flow up to 30-D).
 // A coupling stage with more than 4 transformed columns runs as sub-stages of 4 (tc_sub_stages below).
 //
@@ -118,7 +119,8 @@ bool tc_plan_supported(const PlanDev& hp) {
   int total = 0;
   for (int s = 0; s < hp.n_nsc; ++s) {
     const NscDev& st = hp.nsc[s];
-    if (st.n_dense != 3 || st.H != 128 || st.K != 16) return false;
+    if (st.n_dense != 3 || st.H < 1 || st.H > 128 || st.K < 1 || st.K > 16) return false;
+    if (st.K < 16 && st.periodic) return false;  // padding bins would sit inside the wrap-around
     if (st.U + st.C > TC_IN_MAX || st.L > TC_L_MAX * TC_SUB_MAX || st.L < 1) return false;
     total += tc_sub_stages(st.L);
   }
@@ -156,6 +158,18 @@ static inline void split_store(__half* hi, __half* lo, size_t idx, float v) {
 
 // state columns of a chunk row: x[0, D), log-det levels [D, D + n_lev), pending log-det halves (2),
 // conditions (C)
+// Where logit q of the kernel's K = 16 layout ([16 widths | 16 heights | 15 or 16 derivatives]) comes from in the
+// stage's own [K widths | K heights | K - 1 (periodic: K) derivatives] layout, or which padding it is.
+constexpr int TC_PAD_BIN = -1, TC_PAD_UNIT = -2, TC_PAD_NONE = -3;
+static int tc_logit_source(const NscDev& st, int q) {
+  const int K = st.K;
+  if (q < 16) return q < K ? q : TC_PAD_BIN;
+  if (q < 32) return q - 16 < K ? K + (q - 16) : TC_PAD_BIN;
+  const int j = q - 32, n_der = st.cpd - 2 * K;   // derivative j belongs to knot j + 1
+  if (j < n_der) return 2 * K + j;
+  return (j == n_der && K < 16) ? TC_PAD_UNIT : TC_PAD_NONE;
+}
+
 void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* const* weights, void* dst) {
   const int d0 = TC_L_MAX * sub, Ls = tc_sub_dims(st.L, sub);  // this sub-stage's spline dimensions [d0, d0 + Ls)
   const TcLayout lay = TcLayout::make(Ls);
@@ -163,22 +177,30 @@ void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* co
   memset(base, 0, lay.total);
   const float *W1 = weights[0], *b1 = weights[1], *W2 = weights[2], *b2 = weights[3], *W3 = weights[4],
               *b3 = weights[5];
-  const int in_dim = st.U + st.C, out_dim = st.cpd * st.L;
-  const int e2 = pow2_scale_exp(W2, 128 * 128), e3 = pow2_scale_exp(W3, (size_t)128 * out_dim);
+  const int in_dim = st.U + st.C, out_dim = st.cpd * st.L, H = st.H;
+  // The kernel is written for hidden_dim 128 and K = 16.  Narrower conditioners are PADDED into that shape, exactly:
+  // hidden units H..127 get zero weights and biases (LeakyReLU(0) = 0 contributes nothing downstream), and a spline
+  // with K < 16 bins gets 16 - K trailing bins of zero width and height (bin logits with zero weights and a bias of
+  // -1e30: their softmax terms are exactly 0, and a bin whose left knot is B is never selected), with the knot that
+  // closes the last real bin given derivative softplus(log(e - 1)) = 1, the boundary value (pzflow/utils.py:130-135).
+  const int e2 = pow2_scale_exp(W2, (size_t)H * H), e3 = pow2_scale_exp(W3, (size_t)H * out_dim);
   const float s2 = ldexpf(1.0f, e2), s3 = ldexpf(1.0f, e3);
   __half* w2hi = reinterpret_cast<__half*>(base);
   __half* w2lo = reinterpret_cast<__half*>(base + TC_W2_BYTES / 2);
   for (int n = 0; n < 128; ++n)
-    for (int k = 0; k < 128; ++k) split_store(w2hi, w2lo, sw128_index(128, n, k), W2[k * 128 + n] * s2);
+    for (int k = 0; k < 128; ++k)
+      split_store(w2hi, w2lo, sw128_index(128, n, k), (n < H && k < H) ? W2[k * H + n] * s2 : 0.0f);
   for (int p = 0; p < lay.n_pass; ++p) {
     __half* hi = reinterpret_cast<__half*>(base + lay.w3 + p * TC_W3_PASS_BYTES);
     __half* lo = reinterpret_cast<__half*>(base + lay.w3 + p * TC_W3_PASS_BYTES + TC_W3_PASS_BYTES / 2);
     for (int j = 0; j < 2; ++j) {
       const int d = 2 * p + j;
       if (d >= Ls) continue;
-      for (int q = 0; q < st.cpd; ++q) {
-        const int col = (d0 + d) * st.cpd + q, n = TC_DIM_N * j + q;
-        for (int k = 0; k < 128; ++k) split_store(hi, lo, sw128_index(TC_PASS_N, n, k), W3[(size_t)k * out_dim + col] * s3);
+      for (int q = 0; q < TC_DIM_N; ++q) {
+        const int src = tc_logit_source(st, q);
+        if (src < 0) continue;  // padding: zero weights
+        const int col = (d0 + d) * st.cpd + src, n = TC_DIM_N * j + q;
+        for (int k = 0; k < H; ++k) split_store(hi, lo, sw128_index(TC_PASS_N, n, k), W3[(size_t)k * out_dim + col] * s3);
       }
     }
   }
@@ -190,14 +212,18 @@ void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* co
     for (int n = 0; n < 128; ++n)
       for (int k = 0; k < 16; ++k) {  // k = 8 is the bias row; inputs 8.. sit one row further up
         const int i = k < 8 ? k : k - 1;
-        const float v = k == 8 ? b1[n] : (i < in_dim ? W1[i * 128 + n] : 0.0f);
+        const float v = n >= H ? 0.0f : (k == 8 ? b1[n] : (i < in_dim ? W1[i * H + n] : 0.0f));
         split_store(hi, lo, w1_index(n, k), v);
       }
   }
   float* par = reinterpret_cast<float*>(base + lay.par);
-  for (int k = 0; k < 128; ++k) par[TC_PF_B2 + k] = b2[k];
+  for (int k = 0; k < 128; ++k) par[TC_PF_B2 + k] = k < H ? b2[k] : 0.0f;
   for (int d = 0; d < Ls; ++d)
-    for (int q = 0; q < st.cpd; ++q) par[TC_PF_B3 + d * TC_DIM_N + q] = b3[(d0 + d) * st.cpd + q];
+    for (int q = 0; q < TC_DIM_N; ++q) {
+      const int src = tc_logit_source(st, q);
+      par[TC_PF_B3 + d * TC_DIM_N + q] = src >= 0 ? b3[(d0 + d) * st.cpd + src]
+                                         : (src == TC_PAD_BIN ? -1e30f : (src == TC_PAD_UNIT ? 0.5413248546129181f : 0.0f));
+    }
   par[TC_PF_SCAL + 0] = ldexpf(1.0f, -e2);
   par[TC_PF_SCAL + 1] = ldexpf(1.0f, -e3);
   par[TC_PF_SCAL + 2] = st.B;

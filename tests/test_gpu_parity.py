@@ -405,6 +405,41 @@ def test_stages_with_different_spline_dim_counts(engine):
     assert_noise_floor(f"mixed L inverse [{engine}]", _np(xi), x32, x64, ratio=2.0, slack=2e-6, max_class_mismatch=3)
 
 
+@pytest.mark.parametrize("K,H,D,C", [(8, 64, 5, 0), (3, 100, 4, 2), (15, 128, 7, 0), (2, 16, 2, 0), (12, 40, 10, 1)])
+def test_narrow_conditioners_are_padded_into_the_tensor_core_shape(K, H, D, C):
+    """hidden_dim < 128 and K < 16 on the tensor-core engine: the packer pads hidden units with zero weights and the
+    spline with zero-width trailing bins (csrc/nsf_tc.cu: tc_pack_stage); results against the oracle and against the
+    SIMT engine, bin indices included."""
+    info = ("Chain", (("ShiftBounds", (-np.ones(D, np.float32), np.ones(D, np.float32), 4.0)),
+                      F.rolling_info(D, 1, K, 5, 2, H, None, C)))
+    rng = np.random.default_rng(100 * K + H)
+    params = O.synth_bijector_params(info, D, rng)
+    cfg = dict(bijector_info=info, latent_info=("CentBeta13", (D, 5)), params=((), params), input_dim=D)
+    plan = _plan(cfg, "tc")
+    simt = _plan(cfg, "simt")
+    n = 4000
+    X = rng.uniform(-1.02, 1.02, size=(n, D)).astype(np.float32)
+    cond = rng.normal(size=(n, max(C, 1))).astype(np.float32) if C else np.zeros((n, 1), np.float32)
+    ct = torch.from_numpy(cond) if C else None
+    bi, li, p64 = _o64(cfg)
+    ob = []
+    o32 = O.flow_log_prob(bi, li, cfg["params"], X, cond, bins=ob)
+    o64 = O.flow_log_prob(bi, li, p64, X.astype(np.float64), cond.astype(np.float64))
+    lp, bins = plan.log_prob(torch.from_numpy(X), ct, return_bins=True)
+    assert_noise_floor(f"narrow K={K} H={H} log_prob", _np(lp), o32, o64, ratio=2.0, slack=1e-5, below=LP_UNDERFLOW)
+    flips, rows, total = count_bin_flips(_np(bins), np.concatenate(ob, axis=1))
+    assert flips <= max(3, int(2e-4 * total))
+    assert int(_np(bins).max()) <= K - 1 + 1            # K = out of range marker at most; never a padding bin
+    lp_simt = _np(simt.log_prob(torch.from_numpy(X), ct))
+    ok = ~zero_class(o32, LP_UNDERFLOW)
+    assert within_tol(_np(lp)[ok], lp_simt[ok]).mean() > 0.99
+    u32, _ = O.apply_bijector(bi, cfg["params"][1], X, cond)
+    x32, _ = O.apply_bijector(bi, cfg["params"][1], u32, cond, inverse=True)
+    x64, _ = O.apply_bijector(bi, p64[1], u32.astype(np.float64), cond.astype(np.float64), inverse=True)
+    xi, _ = plan.inverse(torch.from_numpy(u32), ct)
+    assert_noise_floor(f"narrow K={K} H={H} inverse", _np(xi), x32, x64, ratio=2.0, slack=2e-6, max_class_mismatch=3)
+
+
 def test_empty_and_ragged_inputs():
     ex = F.example_flow()
     plan = _plan(ex, "simt")
