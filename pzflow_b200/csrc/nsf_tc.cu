@@ -381,6 +381,14 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// Two LeakyReLUs, max(x, 0.01 x) each (pz_leaky): the two products are ONE packed fp32x2 multiply (sm_100 FMUL2),
+// bit-identical to two FMULs.
+__device__ __forceinline__ void leaky2(float a, float b, float& oa, float& ob) {
+  const float2 t = __fmul2_rn(make_float2(a, b), make_float2(0.01f, 0.01f));
+  oa = fmaxf(a, t.x);
+  ob = fmaxf(b, t.y);
+}
+
 // A operand layout in a 128-column TMEM region (K = 128 fp16 hi/lo): the 32 elements [32b, 32b+32)
 // occupy columns [32b, 32b+32): 16 hi columns then 16 lo columns (two elements per 32-bit column), so an
 // epilogue thread can rewrite 32 fp32 accumulator columns in place.  K-step k16 (16 elements):
@@ -892,14 +900,18 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             mbar_wait(bar_d1, ph_d1);
             ph_d1 ^= 1u;
             tc_fence_after();
-  #pragma unroll 1
+#pragma unroll 1
             for (int bt = 0; bt < 2; ++bt) {
               float dv[32];
               tmem_ld32(t_x + bt * 32, dv);
               tc_wait_ld();
               uint32_t rh[16], rl[16];
-  #pragma unroll
-              for (int j = 0; j < 16; ++j) split2(pz_leaky(dv[2 * j]), pz_leaky(dv[2 * j + 1]), rh[j], rl[j]);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float h0, h1;
+                leaky2(dv[2 * j], dv[2 * j + 1], h0, h1);
+                split2(h0, h1, rh[j], rl[j]);
+              }
               tmem_st16(t_x + bt * 32, rh);
               tmem_st16(t_x + bt * 32 + 16, rl);
             }
@@ -911,7 +923,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             // ---- E2: h2 = LeakyReLU(D * 2^-e2 + b2), rewritten in place over this half's accumulator columns ----
             {
               const float s2inv = par[TC_PF_SCAL];
-  #pragma unroll 1
+#pragma unroll 1
               for (int bt = 0; bt < 2; ++bt) {
                 mbar_wait(bar_d2 + 8u * bt, ph_d2);  // this quarter of the hidden GEMM has landed
                 tc_fence_after();
@@ -921,13 +933,15 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
                 tc_wait_ld();
                 const float* b2 = par + TC_PF_B2 + half * 64 + bt * 32;
                 uint32_t rh[16], rl[16];
-  #pragma unroll
+#pragma unroll
                 for (int q = 0; q < 8; ++q) {
                   const float4 bb = *reinterpret_cast<const float4*>(b2 + q * 4);
-                  const float h0 = pz_leaky(fmaf(dv[4 * q + 0], s2inv, bb.x));
-                  const float h1 = pz_leaky(fmaf(dv[4 * q + 1], s2inv, bb.y));
-                  const float h2 = pz_leaky(fmaf(dv[4 * q + 2], s2inv, bb.z));
-                  const float h3 = pz_leaky(fmaf(dv[4 * q + 3], s2inv, bb.w));
+                  const float2 sc = make_float2(s2inv, s2inv);  // packed fp32x2 FMA: the same roundings as two FFMAs
+                  const float2 p01 = __ffma2_rn(make_float2(dv[4 * q + 0], dv[4 * q + 1]), sc, make_float2(bb.x, bb.y));
+                  const float2 p23 = __ffma2_rn(make_float2(dv[4 * q + 2], dv[4 * q + 3]), sc, make_float2(bb.z, bb.w));
+                  float h0, h1, h2, h3;
+                  leaky2(p01.x, p01.y, h0, h1);
+                  leaky2(p23.x, p23.y, h2, h3);
                   split2(h0, h1, rh[2 * q], rl[2 * q]);
                   split2(h2, h3, rh[2 * q + 1], rl[2 * q + 1]);
                 }
@@ -944,7 +958,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             // ---- E3: logits -> knots -> spline; this thread takes the dimensions half, half + 2 ----
             const bool more = k + 1 < my_tiles;
             float ldsum = 0.0f;
-  #pragma unroll 1
+#pragma unroll 1
             for (int d = half; d < L; d += 2) {
               mbar_wait(bar_d3, ph_d3);
               ph_d3 ^= 1u;
