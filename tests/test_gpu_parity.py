@@ -440,6 +440,58 @@ def test_narrow_conditioners_are_padded_into_the_tensor_core_shape(K, H, D, C):
     assert_noise_floor(f"narrow K={K} H={H} inverse", _np(xi), x32, x64, ratio=2.0, slack=2e-6, max_class_mismatch=3)
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_random_chains_tensor_core_engine_against_oracle_and_simt(seed):
+    """Seeded random chains inside the tensor-core engine's envelope (2 hidden layers, hidden <= 128, K <= 16,
+    <= 15 conditioner inputs, <= 31 columns): random column counts, transformed_dim, conditions, periodic stages,
+    roll shifts and an affine step between coupling blocks.  log_prob and bins against the oracle, forward / inverse
+    against the SIMT engine."""
+    rng = np.random.default_rng(1000 + seed)
+    D = int(rng.integers(1, 13))
+    C = int(rng.integers(0, 4))
+    blocks = [("ShiftBounds", (-np.ones(D, np.float32), np.ones(D, np.float32), 4.0))]
+    for _ in range(int(rng.integers(1, 4))):
+        periodic = bool(rng.random() < 0.25)
+        K = 16 if periodic else int(rng.choice([2, 5, 8, 16, 16]))
+        H = int(rng.choice([16, 64, 100, 128, 128]))
+        td = None if (D == 1 or rng.random() < 0.5) else int(rng.integers(1, D))
+        if td is not None and (D - td) + C > 15:
+            td = None
+        blocks.append(F.rolling_info(int(rng.integers(1, 4)), int(rng.integers(1, 3)), K, 5, 2, H, td, C, periodic))
+        if rng.random() < 0.4:
+            blocks.append(("StandardScaler", (rng.normal(0, 0.05, D).astype(np.float32),
+                                              rng.uniform(0.9, 1.1, D).astype(np.float32))))
+    info = ("Chain", tuple(blocks))
+    params = O.synth_bijector_params(info, D, rng)
+    latent = ("Uniform", (D, 5)) if seed % 2 else ("CentBeta13", (D, 5))
+    cfg = dict(bijector_info=info, latent_info=latent, params=((), params), input_dim=D)
+    plan, simt = _plan(cfg, "tc"), _plan(cfg, "simt")
+    n = int(rng.integers(200, 3000))
+    X = rng.uniform(-1.05, 1.05, size=(n, D)).astype(np.float32)
+    cond = rng.normal(size=(n, max(C, 1))).astype(np.float32) if C else np.zeros((n, 1), np.float32)
+    ct = torch.from_numpy(cond) if C else None
+    bi, li, p64 = _o64(cfg)
+    ob = []
+    o32 = O.flow_log_prob(bi, li, cfg["params"], X, cond, bins=ob)
+    o64 = O.flow_log_prob(bi, li, p64, X.astype(np.float64), cond.astype(np.float64))
+    lp, bins = plan.log_prob(torch.from_numpy(X), ct, return_bins=True)
+    assert_noise_floor(f"random chain {seed} log_prob", _np(lp), o32, o64, ratio=2.0, slack=1e-5, below=LP_UNDERFLOW,
+                       max_class_mismatch=max(2, n // 100))
+    flips, rows, total = count_bin_flips(_np(bins), np.concatenate(ob, axis=1))
+    assert flips <= max(3, int(5e-4 * total)), (flips, total)
+    u_tc, ld_tc = plan.forward(torch.from_numpy(X), ct)
+    u_s, ld_s = simt.forward(torch.from_numpy(X), ct)
+    ok = np.isfinite(_np(u_s)).all(axis=1) & np.isfinite(_np(u_tc)).all(axis=1)
+    assert ok.mean() > 0.97
+    assert within_tol(_np(u_tc)[ok], _np(u_s)[ok]).mean() > 0.99
+    assert within_tol(_np(ld_tc)[ok], _np(ld_s)[ok]).mean() > 0.98
+    x_tc, _ = plan.inverse(u_s, ct)
+    x_s, _ = simt.inverse(u_s, ct)
+    ok = np.isfinite(_np(x_s)).all(axis=1) & np.isfinite(_np(x_tc)).all(axis=1)
+    assert ok.mean() > 0.97
+    assert within_tol(_np(x_tc)[ok], _np(x_s)[ok]).mean() > 0.99
+
+
 def test_empty_and_ragged_inputs():
     ex = F.example_flow()
     plan = _plan(ex, "simt")
