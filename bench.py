@@ -182,6 +182,11 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; pzflow_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = None
+    if world > 1 and os.environ.get("PZB_NUMA_BIND", "1") != "0":
+        # one process per GPU: keep this rank's threads and page-locked staging buffers on the GPU's NUMA node
+        from pzflow_b200.sharding import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         # the contract is ONE JSON line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -340,7 +345,8 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": "7-D galaxy flow log_prob, 10M synthetic rows per GPU (BASELINE config 2)",
                    "rows_per_gpu": n, "params": "shipped example flow (7 x MLP 3-128-128-188, K=16)",
                    "engine": engine, "cache": "inputs_larger_than_L2 (280 MB per GPU per step)",
-                   "parallelism": f"row-sharded x{world}, no collective"},
+                   "parallelism": f"row-sharded x{world}, no collective",
+                   "numa_bound": numa_node is not None},
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(n * 7 * 4),
                 "d2h_bytes_per_step": int(n * 4), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),

@@ -8,7 +8,8 @@ optional result gather and the max-over-ranks used for timing.
 """
 from __future__ import annotations
 
-from typing import Callable, Tuple
+import os
+from typing import Callable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -51,3 +52,36 @@ def max_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process (and every thread it starts later, e.g. the OpenMP cast team of the host pipeline) to the
+    CPUs of the NUMA node the GPU hangs off, so that the page-locked staging buffers it allocates afterwards are
+    node-local and the chunk copies do not cross the socket interconnect.  One process per GPU calls this once,
+    before the first host-buffer call.  Returns the node, or None when the topology cannot be read (single-node
+    hosts, containers without sysfs) -- in which case nothing is changed."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = _parse_cpulist(fh.read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None

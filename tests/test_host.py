@@ -344,3 +344,14 @@ def test_data_parallel_step_equals_single_process_gloo():
         p.join(timeout=60)
     np.testing.assert_array_equal(res[0], res[1])               # ranks stay bit-identical
     np.testing.assert_allclose(res[0], single, rtol=0, atol=1e-12)
+
+
+def test_numa_binding_helper_is_inert_without_topology():
+    """sharding.bind_to_gpu_numa_node: cpulist parsing, and no change of affinity when the topology is unreadable."""
+    import os
+    from pzflow_b200 import sharding
+    assert sharding._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sharding._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_to_gpu_numa_node(0) is None      # no CUDA device here
+    assert os.sched_getaffinity(0) == before
