@@ -352,6 +352,8 @@ def test_wide_default_flows_run_as_sub_stages(D, C, engine):
     cfg = F.default_flow(D, -np.ones(D), np.ones(D), n_conditions=C, seed=D)
     plan = _plan(cfg, engine)
     assert plan.tc_supported
+    from pzflow_b200.plan import Plan
+    assert Plan(cfg["bijector_info"], cfg["params"][1], D, cfg["latent_info"]).engine == "tc"   # what AUTO picks
     rng = np.random.default_rng(D)
     n = 3000                                             # 24 tiles: ragged last chunk, both epilogue groups busy
     X = rng.uniform(-1.02, 1.02, size=(n, D)).astype(np.float32)
