@@ -75,7 +75,7 @@ constexpr int TC_PF_B3 = TC_PF_B2 + 128;
 constexpr int TC_PF_SCAL = TC_PF_B3 + 2 * TC_PASS_N;  // s2inv, s3inv, B, 1/(2B)
 constexpr int TC_PI = TC_PF_SCAL + 4;                 // ints: key_col[16], low_col[4], U, L, in_dim, periodic, bins_off
 constexpr int TC_PI_KEY = 0, TC_PI_LOW = 16, TC_PI_U = 20, TC_PI_L = 21, TC_PI_IN = 22, TC_PI_PERIODIC = 23,
-              TC_PI_BINS = 24;
+              TC_PI_BINS = 24, TC_PI_K = 25;
 constexpr int TC_PAR_FLOATS = TC_PI + 32;
 constexpr int TC_PAR_BYTES = TC_PAR_FLOATS * 4;   // 1424, a multiple of 16
 constexpr int TC_SMEM_MAX = 232448;               // 227 KB opt-in limit per CTA
@@ -238,6 +238,7 @@ void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* co
   pi[TC_PI_IN] = in_dim;
   pi[TC_PI_PERIODIC] = st.periodic;
   pi[TC_PI_BINS] = st.bins_off + d0;
+  pi[TC_PI_K] = st.K;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -981,7 +982,8 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               srow[col * CR] = y;
               TC_TRACE(d < 2 ? 5 : 7);
               if (args.bins != nullptr && r < nrows)
-                args.bins[(row0 + r) * plan->n_spline_dims + pint[TC_PI_BINS] + d] = idx;
+                // (K = beyond the last knot; the padding bins of a K < 16 stage count as that)
+                args.bins[(row0 + r) * plan->n_spline_dims + pint[TC_PI_BINS] + d] = min(idx, pint[TC_PI_K]);
             }
             srow[(COL_PEND + half) * CR] = INV ? -ldsum : ldsum;
             if (half == kw) {

@@ -421,6 +421,8 @@ def test_narrow_conditioners_are_padded_into_the_tensor_core_shape(K, H, D, C):
     simt = _plan(cfg, "simt")
     n = 4000
     X = rng.uniform(-1.02, 1.02, size=(n, D)).astype(np.float32)
+    X[:4] = 3.0                                          # |x| > 2B after ShiftBounds: beyond the last knot, idx = K
+    X[4:8] = -3.0
     cond = rng.normal(size=(n, max(C, 1))).astype(np.float32) if C else np.zeros((n, 1), np.float32)
     ct = torch.from_numpy(cond) if C else None
     bi, li, p64 = _o64(cfg)
@@ -428,6 +430,7 @@ def test_narrow_conditioners_are_padded_into_the_tensor_core_shape(K, H, D, C):
     o32 = O.flow_log_prob(bi, li, cfg["params"], X, cond, bins=ob)
     o64 = O.flow_log_prob(bi, li, p64, X.astype(np.float64), cond.astype(np.float64))
     lp, bins = plan.log_prob(torch.from_numpy(X), ct, return_bins=True)
+    assert (np.concatenate(ob, axis=1)[:8] == K).any() and _np(bins)[:8].max() == K
     assert_noise_floor(f"narrow K={K} H={H} log_prob", _np(lp), o32, o64, ratio=2.0, slack=1e-5, below=LP_UNDERFLOW)
     flips, rows, total = count_bin_flips(_np(bins), np.concatenate(ob, axis=1))
     assert flips <= max(3, int(2e-4 * total))
