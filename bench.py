@@ -282,6 +282,20 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     barrier()
     post_ms = max_ranks(e0.elapsed_time(e1)) / 2
+    # the same through the host-buffer call: photometry in pinned host memory, pdfs [Ng, G] back in pinned host memory
+    from pzflow_b200.plan import pinned_empty
+    rest_h = pinned_empty((ng, rest.shape[1]))
+    rest_h.copy_(rest)
+    pdfs_h = pinned_empty((ng, POSTERIOR_GRID))
+    grid_h = grid.cpu()
+    plan.posterior_host(rest_h, 0, grid_h, out=pdfs_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        plan.posterior_host(rest_h, 0, grid_h, out=pdfs_h)
+    barrier()
+    post_e2e_ms = max_ranks((time.perf_counter() - t0) * 1e3) / 2
+    del pdfs_h
     u = flow.latent.sample_device(n, seed=rank)
     plan.inverse(u, want_log_det=False)
     barrier()
@@ -356,6 +370,8 @@ def run_ours(args, rank, world, local_rank):
         "extra": {
             "posterior": {"value": ng * world / (post_ms * 1e-3), "unit": "galaxies/s", "grid_points": POSTERIOR_GRID,
                           "galaxies_per_gpu": ng, "ms": post_ms,
+                          "e2e_value": ng * world / (post_e2e_ms * 1e-3), "e2e_ms": post_e2e_ms,
+                          "e2e_d2h_bytes": int(ng * POSTERIOR_GRID * 4),
                           "rows_per_s_equiv": ng * POSTERIOR_GRID * world / (post_ms * 1e-3)},
             "sample": {"value": n * world / (samp_ms * 1e-3), "unit": "rows/s", "ms": samp_ms},
         },
