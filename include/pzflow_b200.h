@@ -153,7 +153,9 @@ int pzb_plan_n_conditions(const pzb_plan *plan);
 int pzb_plan_n_spline_dims(const pzb_plan *plan);
 /* conditioner MLP FLOPs per row (SURVEY.md §8d formula), for rooflines. */
 double pzb_plan_flops_per_row(const pzb_plan *plan);
-/* 1 if the tensor-core engine supports this plan's shapes. */
+/* 1 if the tensor-core engine supports this plan's shapes: every coupling stage has 2 hidden layers of at most 128
+ * units, at most 16 bins (fewer than 16 only when not periodic), at most 15 conditioner inputs (columns + conditions)
+ * and at most 16 transformed columns; at most 31 data columns.  Everything else runs on the SIMT engine. */
 int pzb_plan_tc_supported(const pzb_plan *plan);
 /* select the conditioner engine for subsequent launches (default AUTO). */
 int pzb_plan_set_engine(pzb_plan *plan, int32_t engine);
