@@ -69,6 +69,11 @@ struct HostPipe {
   void* h_in[NBUF] = {};
   void* h_cond[NBUF] = {};
   size_t cap_hin = 0, cap_hcond = 0;
+  // page-locked host staging for results whose destination is PAGEABLE memory (a fresh NumPy array): the D2H copy
+  // lands here at PCIe speed and the host cores move it on while the GPU works on the next chunks
+  void* h_out0[NBUF] = {};
+  void* h_out1[NBUF] = {};
+  size_t cap_hout0 = 0, cap_hout1 = 0;
 };
 
 struct pzb_plan {
@@ -600,6 +605,8 @@ void pzb_plan_destroy(pzb_plan* plan) {
     for (int b = 0; b < HostPipe::NBUF; ++b) {
       if (hp.h_in[b]) cudaFreeHost(hp.h_in[b]);
       if (hp.h_cond[b]) cudaFreeHost(hp.h_cond[b]);
+      if (hp.h_out0[b]) cudaFreeHost(hp.h_out0[b]);
+      if (hp.h_out1[b]) cudaFreeHost(hp.h_out1[b]);
     }
     cudaStreamDestroy(hp.s_in);
     cudaStreamDestroy(hp.s_k);
@@ -1114,6 +1121,27 @@ static cudaError_t pipe_reserve(void** p, size_t* cap, size_t want, int n) {
   return cudaSuccess;
 }
 
+// memcpy on all host cores (first-touch page faults of a fresh destination included)
+static void parallel_copy(void* dst, const void* src, size_t bytes, int threads) {
+  const size_t blk = 1u << 20;
+  const int64_t nblk = (int64_t)((bytes + blk - 1) / blk);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (int64_t i = 0; i < nblk; ++i) {
+    const size_t a = (size_t)i * blk, n = std::min(blk, bytes - a);
+    memcpy(static_cast<char*>(dst) + a, static_cast<const char*>(src) + a, n);
+  }
+}
+
+// true if the CUDA driver knows p as page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+static bool host_pointer_is_pinned(const void* p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
 static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
   if (job.units == 0) return PZB_OK;
   HostPipe& hp = plan->pipe;
@@ -1158,8 +1186,26 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     ce = host_reserve(hp.h_in, &hp.cap_hin, (size_t)chunk * std::max(job.in_w, 1) * sizeof(float), HostPipe::NBUF);
   if (ce == cudaSuccess && job.cond_cols && C > 0)
     ce = host_reserve(hp.h_cond, &hp.cap_hcond, (size_t)chunk * C * sizeof(float), HostPipe::NBUF);
+  // results bound for pageable memory go through page-locked staging (small results are not worth the detour)
+  const size_t out_total = (size_t)job.units * job.out0_w * sizeof(float);
+  const bool stage_out = out_total >= (8u << 20) && !host_pointer_is_pinned(job.out0);
+  if (ce == cudaSuccess && stage_out)
+    ce = host_reserve(hp.h_out0, &hp.cap_hout0, (size_t)chunk * job.out0_w * sizeof(float), HostPipe::NBUF);
+  if (ce == cudaSuccess && stage_out && job.out1)
+    ce = host_reserve(hp.h_out1, &hp.cap_hout1, (size_t)chunk * sizeof(float), HostPipe::NBUF);
   if (ce != cudaSuccess) return cuda_fail(ce, "host pipeline staging buffers");
   const int host_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  int64_t pend_u0[HostPipe::NBUF] = {}, pend_nu[HostPipe::NBUF] = {};
+  // chunk j's staged results -> the caller's arrays, once its D2H copy has completed
+  auto drain = [&](int64_t j) {
+    const int bj = (int)(j % HostPipe::NBUF);
+    cudaError_t e = cudaEventSynchronize(hp.ev_out[bj]);
+    if (e != cudaSuccess) return e;
+    parallel_copy(job.out0 + pend_u0[bj] * job.out0_w, hp.h_out0[bj], (size_t)pend_nu[bj] * job.out0_w * sizeof(float),
+                  host_threads);
+    if (job.out1) memcpy(job.out1 + pend_u0[bj], hp.h_out1[bj], (size_t)pend_nu[bj] * sizeof(float));
+    return cudaSuccess;
+  };
 
   int rc = PZB_OK;
   int64_t i = 0;
@@ -1208,14 +1254,26 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     if (rc != PZB_OK) break;
     cudaEventRecord(hp.ev_k[b], hp.s_k);
     cudaStreamWaitEvent(hp.s_out, hp.ev_k[b], 0);
-    ce = cudaMemcpyAsync(job.out0 + u0 * job.out0_w, hp.d_out0[b], (size_t)nu * job.out0_w * sizeof(float),
-                         cudaMemcpyDeviceToHost, hp.s_out);
+    float* dst0 = stage_out ? static_cast<float*>(hp.h_out0[b]) : job.out0 + u0 * job.out0_w;
+    float* dst1 = stage_out ? static_cast<float*>(hp.h_out1[b]) : (job.out1 ? job.out1 + u0 : nullptr);
+    ce = cudaMemcpyAsync(dst0, hp.d_out0[b], (size_t)nu * job.out0_w * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out);
     if (ce == cudaSuccess && job.out1)
-      ce = cudaMemcpyAsync(job.out1 + u0, hp.d_out1[b], (size_t)nu * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out);
+      ce = cudaMemcpyAsync(dst1, hp.d_out1[b], (size_t)nu * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out);
     if (ce == cudaSuccess) ce = cudaEventRecord(hp.ev_out[b], hp.s_out);
     if (ce != cudaSuccess) { rc = cuda_fail(ce, "host pipeline D2H"); break; }
+    pend_u0[b] = u0;
+    pend_nu[b] = nu;
+    // with chunk i queued behind it, move chunk i-1's staged results on (the GPU keeps working on chunk i meanwhile)
+    if (stage_out && i >= 1) {
+      ce = drain(i - 1);
+      if (ce != cudaSuccess) { rc = cuda_fail(ce, "host pipeline staged results"); break; }
+    }
     u0 += nu;
     cur = std::min(chunk, cur * 2);
+  }
+  if (stage_out && rc == PZB_OK && i >= 1) {
+    ce = drain(i - 1);
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "host pipeline staged results");
   }
   // drain everything, also on the error path: the ring must be idle when the next call starts
   cudaError_t e1 = cudaStreamSynchronize(hp.s_in), e2 = cudaStreamSynchronize(hp.s_k),

@@ -313,14 +313,17 @@ class Plan:
 
     def posterior_host(self, rest, col_idx: int, grid, cond=None, normalize: bool = True,
                        nan_to_zero: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Flow.posterior main loop on HOST arrays: rest [Ng, D-1], grid [G] -> pinned pdfs [Ng, G];
-        neither the [Ng*G, D] expansion nor the whole pdfs array ever sits in HBM."""
+        """Flow.posterior main loop on HOST arrays: rest [Ng, D-1], grid [G] -> pdfs [Ng, G] in host memory;
+        neither the [Ng*G, D] expansion nor the whole pdfs array ever sits in HBM.  ``out`` may be page-locked
+        (copied into directly) or ordinary pageable memory (the library stages chunks through its own page-locked
+        ring and moves them on with all host cores while the GPU computes the next ones); the default is a fresh
+        pageable array -- page-locking gigabytes for one call costs more than the evaluation itself."""
         rest = self._host_rows(rest, self.input_dim - 1, "inputs")
         cond = self._host_cond(cond, rest.shape[0])
         grid = torch.as_tensor(grid).to(dtype=torch.float32).contiguous().reshape(-1).cpu()
         Ng, G = rest.shape[0], grid.numel()
         if out is None:
-            out = pinned_empty((Ng, G))
+            out = torch.empty((Ng, G), dtype=torch.float32)
         N.check(N.lib().pzb_posterior_host(self._h, _ptr(rest) if rest.numel() else None, _ptr(cond), Ng,
                                            int(col_idx), _ptr(grid), G, int(bool(normalize)),
                                            int(bool(nan_to_zero)), _ptr(out)))

@@ -642,6 +642,29 @@ def test_host_pipeline_equals_device_path(pinned):
     assert plan.log_prob_host(X[:0]).shape == (0,)
 
 
+def test_host_pipeline_pageable_results_are_staged_and_identical():
+    """Results bound for ordinary (pageable) host memory go through the library's page-locked staging ring
+    (csrc/pzb_api.cu: run_host, stage_out): same bits as the page-locked destination and as the device path."""
+    from pzflow_b200 import _native as N
+    from pzflow_b200.plan import _ptr, pinned_empty
+    ex = F.example_flow()
+    plan = _plan(ex, "tc")
+    X = F.galaxy_rows(6000, seed=3)
+    grid = np.linspace(0.0, 2.3, 1000).astype(np.float32)                  # 6000 x 1000 floats = 24 MB > 8 MB
+    rest = np.ascontiguousarray(X[:, 1:])
+    pageable = plan.posterior_host(rest, 0, grid)
+    assert not pageable.is_pinned()
+    pinned = plan.posterior_host(rest, 0, grid, out=pinned_empty((6000, 1000)))
+    dev = plan.posterior(torch.from_numpy(rest), 0, torch.from_numpy(grid))
+    assert _same_bits(pageable, pinned) and _same_bits(pageable, dev)
+    n = 700_000                                                           # forward: [n, 7] = 19.6 MB, plus log_det
+    Xh = torch.from_numpy(np.tile(X, (n // 6000 + 1, 1))[:n].copy())
+    u, ld = torch.empty((n, 7)), torch.empty(n)
+    N.check(N.lib().pzb_forward_host(plan._h, _ptr(Xh), None, n, _ptr(u), _ptr(ld)))
+    u_dev, ld_dev = plan.forward(Xh)
+    assert _same_bits(u, u_dev) and _same_bits(ld, ld_dev)
+
+
 def test_host_pipeline_posterior_and_conditions():
     ex = F.example_flow()
     plan = _plan(ex, "tc")
