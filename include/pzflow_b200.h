@@ -281,8 +281,10 @@ int pzb_adam_step(float *params, const float *grads, float *m, float *v, int64_t
  * and D2H copy of consecutive chunks overlap and HBM holds three chunks at
  * most (the 4 GB posterior of config 3 never sits on the device as a whole).
  * Blocking: the results are in the output arrays on return.  Page-locked host
- * arrays move at PCIe speed; pageable arrays work but do not overlap.  Calls on
- * one plan serialise. */
+ * arrays are copied from / into directly; pageable arrays (plain NumPy arrays)
+ * of 8 MB or more go through plan-owned page-locked staging filled / emptied
+ * by all host cores inside the same pipeline, at the same speed.  Calls on one
+ * plan serialise. */
 int pzb_log_prob_host(const pzb_plan *plan, const float *X, const float *cond, int64_t N,
                       float *out);
 /* Flow.log_prob straight from DataFrame columns (pzflow/flow.py:440-446): data_cols [D] and cond_cols [C]

@@ -1051,8 +1051,9 @@ int pzb_adam_step(float* params, const float* grads, float* m, float* v, int64_t
 // that flow through a three-deep ring of device staging buffers on three streams, so the H2D
 // copy of chunk i, the chain kernel of chunk i-1 and the D2H copy of chunk i-2 overlap; HBM
 // never holds more than three chunks.  Blocking: results are in the host buffers on return.
-// Pinned (page-locked) host arrays copy at PCIe speed; pageable ones still work (the driver
-// stages them) but do not overlap.
+// Pinned (page-locked) host arrays are copied from / into directly; pageable ones (plain NumPy arrays) of 8 MB or
+// more go through plan-owned page-locked staging buffers, filled / emptied by all host cores chunk by chunk inside
+// the same pipeline, so they overlap too.
 // ---------------------------------------------------------------------------------------------
 struct HostJob {
   int mode = MODE_LOGPROB;
@@ -1162,6 +1163,7 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     hp.ready = true;
   }
   const int C = plan->host.C;
+  const int host_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   const int rows_per_unit = (job.mode == MODE_POSTERIOR) ? job.G : 1;
   // chunk: ~1.2 M chain rows (8 waves of 148 CTAs x 1024 rows), staging buffers <= 64 MB each
   int64_t chunk = (int64_t)plan->num_sms * 1024 * 8 / rows_per_unit;
@@ -1182,9 +1184,13 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     if (ce == cudaSuccess)
       ce = cudaMemcpyAsync(hp.d_grid, job.grid, (size_t)job.G * sizeof(float), cudaMemcpyHostToDevice, hp.s_k);
   }
-  if (ce == cudaSuccess && job.in_cols)
+  // float32 rows in pageable memory (a plain NumPy array) are staged like the float64 columns are: copied into
+  // page-locked buffers by all host cores, chunk by chunk, so that the H2D copies run at PCIe speed and overlap
+  const bool stage_in = job.in != nullptr && job.in_w > 0 &&
+                        (size_t)job.units * job.in_w * sizeof(float) >= (8u << 20) && !host_pointer_is_pinned(job.in);
+  if (ce == cudaSuccess && (job.in_cols || stage_in))
     ce = host_reserve(hp.h_in, &hp.cap_hin, (size_t)chunk * std::max(job.in_w, 1) * sizeof(float), HostPipe::NBUF);
-  if (ce == cudaSuccess && job.cond_cols && C > 0)
+  if (ce == cudaSuccess && C > 0 && (job.cond_cols || (stage_in && job.cond)))
     ce = host_reserve(hp.h_cond, &hp.cap_hcond, (size_t)chunk * C * sizeof(float), HostPipe::NBUF);
   // results bound for pageable memory go through page-locked staging (small results are not worth the detour)
   const size_t out_total = (size_t)job.units * job.out0_w * sizeof(float);
@@ -1194,7 +1200,6 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
   if (ce == cudaSuccess && stage_out && job.out1)
     ce = host_reserve(hp.h_out1, &hp.cap_hout1, (size_t)chunk * sizeof(float), HostPipe::NBUF);
   if (ce != cudaSuccess) return cuda_fail(ce, "host pipeline staging buffers");
-  const int host_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   int64_t pend_u0[HostPipe::NBUF] = {}, pend_nu[HostPipe::NBUF] = {};
   // chunk j's staged results -> the caller's arrays, once its D2H copy has completed
   auto drain = [&](int64_t j) {
@@ -1226,6 +1231,14 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
       if (C > 0) {
         gather_cast_rows(job.cond_cols, C, u0, nu, static_cast<float*>(hp.h_cond[b]), job.cond_mean, job.cond_std,
                          host_threads);
+        src_cond = static_cast<const float*>(hp.h_cond[b]);
+      }
+    } else if (stage_in) {
+      if (i >= HostPipe::NBUF) cudaEventSynchronize(hp.ev_in[b]);
+      parallel_copy(hp.h_in[b], src_in, (size_t)nu * job.in_w * sizeof(float), host_threads);
+      src_in = static_cast<const float*>(hp.h_in[b]);
+      if (C > 0 && src_cond != nullptr) {
+        parallel_copy(hp.h_cond[b], src_cond, (size_t)nu * C * sizeof(float), host_threads);
         src_cond = static_cast<const float*>(hp.h_cond[b]);
       }
     }
