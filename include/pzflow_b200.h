@@ -295,6 +295,10 @@ int pzb_log_prob_host(const pzb_plan *plan, const float *X, const float *cond, i
 int pzb_log_prob_host_columns(const pzb_plan *plan, const double *const *data_cols,
                               const double *const *cond_cols, const float *cond_means,
                               const float *cond_stds, int64_t N, float *out);
+/* The same for float32 columns (a DataFrame read from float32 data). */
+int pzb_log_prob_host_columns_f32(const pzb_plan *plan, const float *const *data_cols,
+                                  const float *const *cond_cols, const float *cond_means,
+                                  const float *cond_stds, int64_t N, float *out);
 int pzb_forward_host(const pzb_plan *plan, const float *X, const float *cond, int64_t N,
                      float *U, float *log_det);
 int pzb_inverse_host(const pzb_plan *plan, const float *U, const float *cond, int64_t N,

@@ -162,6 +162,25 @@ struct DeviceGuard {
   }
 };
 
+// float64 / float32 columns -> float32 rows [n, w] on all host cores (explicit thread count: torchrun exports OMP_NUM_THREADS=1)
+template <typename T>
+static void gather_cast_rows(const void* const* cols, int w, int64_t r0, int64_t n, float* dst, const float* mean,
+                             const float* stdv, int threads) {
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (int64_t blk = 0; blk < (n + 4095) / 4096; ++blk) {
+    const int64_t a = blk * 4096, b = std::min<int64_t>(n, a + 4096);
+    for (int j = 0; j < w; ++j) {
+      const T* src = static_cast<const T*>(cols[j]) + r0;
+      if (mean != nullptr) {
+        const float m = mean[j], sd = stdv[j];
+        for (int64_t r = a; r < b; ++r) dst[r * w + j] = ((float)src[r] - m) / sd;
+      } else {
+        for (int64_t r = a; r < b; ++r) dst[r * w + j] = (float)src[r];
+      }
+    }
+  }
+}
+
 extern "C" {
 
 int pzb_abi_version(void) { return PZB_ABI_VERSION; }
@@ -1068,8 +1087,9 @@ struct HostJob {
   int64_t units = 0;           // rows, or galaxies for the posterior
   // column-source form: in_w (and C) float64 column pointers instead of `in` / `cond`; conditions are standard-scaled
   // here, (float(c) - mean) / std in float32 like Flow._get_conditions (pzflow/flow.py:330-336)
-  const double* const* in_cols = nullptr;
-  const double* const* cond_cols = nullptr;
+  const void* const* in_cols = nullptr;
+  const void* const* cond_cols = nullptr;
+  bool cols_f32 = false;       // the columns are float32 (else float64)
   const float* cond_mean = nullptr;
   const float* cond_std = nullptr;
 };
@@ -1089,23 +1109,6 @@ static cudaError_t host_reserve(void** p, size_t* cap, size_t want, int n) {
   return cudaSuccess;
 }
 
-// float64 columns -> float32 rows [n, w] on all host cores (explicit thread count: torchrun exports OMP_NUM_THREADS=1)
-static void gather_cast_rows(const double* const* cols, int w, int64_t r0, int64_t n, float* dst, const float* mean,
-                             const float* stdv, int threads) {
-#pragma omp parallel for num_threads(threads) schedule(static)
-  for (int64_t blk = 0; blk < (n + 4095) / 4096; ++blk) {
-    const int64_t a = blk * 4096, b = std::min<int64_t>(n, a + 4096);
-    for (int j = 0; j < w; ++j) {
-      const double* src = cols[j] + r0;
-      if (mean != nullptr) {
-        const float m = mean[j], sd = stdv[j];
-        for (int64_t r = a; r < b; ++r) dst[r * w + j] = ((float)src[r] - m) / sd;
-      } else {
-        for (int64_t r = a; r < b; ++r) dst[r * w + j] = (float)src[r];
-      }
-    }
-  }
-}
 
 static cudaError_t pipe_reserve(void** p, size_t* cap, size_t want, int n) {
   if (want <= *cap) return cudaSuccess;
@@ -1226,11 +1229,11 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
       // the previous copy out of this staging buffer (chunk i - NBUF) must have completed before it is refilled;
       // the cast of chunk i then runs on the host cores while the GPU works on chunks i-1, i-2
       if (i >= HostPipe::NBUF) cudaEventSynchronize(hp.ev_in[b]);
-      gather_cast_rows(job.in_cols, job.in_w, u0, nu, static_cast<float*>(hp.h_in[b]), nullptr, nullptr, host_threads);
+      auto gather = job.cols_f32 ? gather_cast_rows<float> : gather_cast_rows<double>;
+      gather(job.in_cols, job.in_w, u0, nu, static_cast<float*>(hp.h_in[b]), nullptr, nullptr, host_threads);
       src_in = static_cast<const float*>(hp.h_in[b]);
       if (C > 0) {
-        gather_cast_rows(job.cond_cols, C, u0, nu, static_cast<float*>(hp.h_cond[b]), job.cond_mean, job.cond_std,
-                         host_threads);
+        gather(job.cond_cols, C, u0, nu, static_cast<float*>(hp.h_cond[b]), job.cond_mean, job.cond_std, host_threads);
         src_cond = static_cast<const float*>(hp.h_cond[b]);
       }
     } else if (stage_in) {
@@ -1311,8 +1314,8 @@ int pzb_log_prob_host(const pzb_plan* plan, const float* X, const float* cond, i
   return run_host(plan, j, "log_prob_host");
 }
 
-int pzb_log_prob_host_columns(const pzb_plan* plan, const double* const* data_cols, const double* const* cond_cols,
-                              const float* cond_means, const float* cond_stds, int64_t N, float* out) {
+static int log_prob_columns(const pzb_plan* plan, const void* const* data_cols, const void* const* cond_cols,
+                            bool f32, const float* cond_means, const float* cond_stds, int64_t N, float* out) {
   if (!plan) return fail(PZB_ERR_INVALID, "log_prob_host_columns: plan is NULL");
   if (N < 0) return fail(PZB_ERR_INVALID, "log_prob_host_columns: negative row count");
   const int D = plan->host.D, C = plan->host.C;
@@ -1326,6 +1329,7 @@ int pzb_log_prob_host_columns(const pzb_plan* plan, const double* const* data_co
   HostJob j;
   j.mode = MODE_LOGPROB;
   j.in_cols = data_cols;
+  j.cols_f32 = f32;
   j.in_w = D;
   j.cond_cols = C > 0 ? cond_cols : nullptr;
   j.cond_mean = cond_means;
@@ -1334,6 +1338,18 @@ int pzb_log_prob_host_columns(const pzb_plan* plan, const double* const* data_co
   j.out0_w = 1;
   j.units = N;
   return run_host(plan, j, "log_prob_host_columns");
+}
+
+int pzb_log_prob_host_columns(const pzb_plan* plan, const double* const* data_cols, const double* const* cond_cols,
+                              const float* cond_means, const float* cond_stds, int64_t N, float* out) {
+  return log_prob_columns(plan, reinterpret_cast<const void* const*>(data_cols),
+                          reinterpret_cast<const void* const*>(cond_cols), false, cond_means, cond_stds, N, out);
+}
+
+int pzb_log_prob_host_columns_f32(const pzb_plan* plan, const float* const* data_cols, const float* const* cond_cols,
+                                  const float* cond_means, const float* cond_stds, int64_t N, float* out) {
+  return log_prob_columns(plan, reinterpret_cast<const void* const*>(data_cols),
+                          reinterpret_cast<const void* const*>(cond_cols), true, cond_means, cond_stds, N, out);
 }
 
 int pzb_forward_host(const pzb_plan* plan, const float* X, const float* cond, int64_t N, float* U, float* log_det) {

@@ -48,12 +48,10 @@ def _load_pickle(file: str) -> dict:
 
 
 def _pinned_f32(a: np.ndarray) -> torch.Tensor:
-    """Cast/copy a host array into a page-locked float32 tensor in one pass, so the H2D copies of
-    the host-buffer entry points run at PCIe speed and overlap with the kernel."""
-    a = np.asarray(a)
-    t = torch.empty(a.shape, dtype=torch.float32, pin_memory=torch.cuda.is_available())
-    np.copyto(t.numpy(), a, casting="unsafe")
-    return t
+    """A C-contiguous float32 CPU tensor of a host array (one cast/copy pass, none if it already is one).  Ordinary
+    pageable memory: the host-buffer entry points stage it through the plan's page-locked ring chunk by chunk,
+    which is as fast as handing them page-locked arrays and saves page-locking a fresh array per call."""
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
 
 
 def _to_numpy_tree(p):
@@ -210,17 +208,18 @@ class Flow:
         self._check_bijector()
         if err_samples is None:
             columns = list(self.data_columns)
-            # float64 columns go to the C call as they are: the down-cast (flow.py:442), the row gather and the
+            # float64 (or float32) columns go to the C call as they are: the down-cast (flow.py:442), the row gather and the
             # condition scaling (flow.py:330-336) run chunk by chunk inside the H2D | kernel | D2H pipeline
             cols = [inputs[c].to_numpy() for c in columns]
-            if all(c.dtype == np.float64 and c.ndim == 1 for c in cols):
-                ccols = None
-                if self.conditional_columns is not None:
-                    ccols = [inputs[c].to_numpy() for c in self.conditional_columns]
-                    if not all(c.dtype == np.float64 and c.ndim == 1 for c in ccols):
-                        ccols = [np.asarray(c, dtype=np.float64) for c in ccols]
-                return self._plan().log_prob_host_columns(cols, ccols, self._condition_means,
-                                                          self._condition_stds).numpy()
+            for ctype in (np.float64, np.float32):
+                if all(c.dtype == ctype and c.ndim == 1 for c in cols):
+                    ccols = None
+                    if self.conditional_columns is not None:
+                        ccols = [inputs[c].to_numpy() for c in self.conditional_columns]
+                        if not all(c.dtype == ctype and c.ndim == 1 for c in ccols):
+                            ccols = [np.asarray(c, dtype=ctype) for c in ccols]
+                    return self._plan().log_prob_host_columns(cols, ccols, self._condition_means,
+                                                              self._condition_stds).numpy()
             X = _pinned_f32(inputs[columns].to_numpy())
             conditions = self._get_conditions(inputs)
             return self._log_prob(self._params, X, conditions).cpu().numpy()

@@ -256,19 +256,24 @@ class Plan:
         return t[:, : self.n_conditions].to(dtype=torch.float32).contiguous()
 
     def log_prob_host(self, X, cond=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Flow._log_prob on HOST arrays -> pinned CPU tensor [N] (pzb_log_prob_host)."""
+        """Flow._log_prob on HOST arrays -> CPU tensor [N] (pzb_log_prob_host).  Fresh results are ordinary pageable
+        tensors: the library stages them (and pageable inputs) through its own page-locked ring, which is as fast as
+        page-locked arrays and saves page-locking a new array per call."""
         X = self._host_rows(X, self.input_dim, "inputs")
         cond = self._host_cond(cond, X.shape[0])
         if out is None:
-            out = pinned_empty((X.shape[0],))
+            out = torch.empty((X.shape[0],), dtype=torch.float32)
         N.check(N.lib().pzb_log_prob_host(self._h, _ptr(X), _ptr(cond), X.shape[0], _ptr(out)))
         return out
 
     def log_prob_host_columns(self, data_cols, cond_cols=None, cond_means=None, cond_stds=None) -> torch.Tensor:
-        """Flow.log_prob from float64 DataFrame COLUMNS (one contiguous 1-D array per column): the down-cast to
-        float32, the row gather and the condition scaling run inside the pipelined C call
-        (pzb_log_prob_host_columns).  Returns a pinned CPU tensor [N]."""
-        cols = [np.ascontiguousarray(c, dtype=np.float64) for c in data_cols]
+        """Flow.log_prob from float64 (or float32) DataFrame COLUMNS (one contiguous 1-D array per column): the
+        down-cast to float32, the row gather and the condition scaling run inside the pipelined C call
+        (pzb_log_prob_host_columns / _f32).  Returns a CPU tensor [N]."""
+        # float32 columns stay float32 (pzb_log_prob_host_columns_f32); anything else is taken as float64
+        f32 = all(getattr(c, "dtype", None) == np.float32 for c in data_cols)
+        ctype = np.float32 if f32 else np.float64
+        cols = [np.ascontiguousarray(c, dtype=ctype) for c in data_cols]
         if len(cols) != self.input_dim:
             raise ValueError(f"expected {self.input_dim} data columns, got {len(cols)}")
         n = len(cols[0])
@@ -278,7 +283,7 @@ class Plan:
         if self.n_conditions > 0:
             if cond_cols is None:
                 raise ValueError(f"this bijector is conditional: conditions [N, {self.n_conditions}] are required")
-            ccols = [np.ascontiguousarray(c, dtype=np.float64) for c in list(cond_cols)[: self.n_conditions]]
+            ccols = [np.ascontiguousarray(c, dtype=ctype) for c in list(cond_cols)[: self.n_conditions]]
             if len(ccols) < self.n_conditions or any(c.ndim != 1 or len(c) != n for c in ccols):
                 raise ValueError(f"conditions must be {self.n_conditions} columns of {n} values")
             means = np.ascontiguousarray(np.zeros(self.n_conditions) if cond_means is None else cond_means,
@@ -287,27 +292,28 @@ class Plan:
                                         dtype=np.float32)[: self.n_conditions]
         dptr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
         cptr = (C.c_void_p * max(1, len(ccols)))(*[c.ctypes.data for c in ccols]) if ccols else None
-        out = pinned_empty((n,))
-        N.check(N.lib().pzb_log_prob_host_columns(
+        out = torch.empty((n,), dtype=torch.float32)
+        call = N.lib().pzb_log_prob_host_columns_f32 if f32 else N.lib().pzb_log_prob_host_columns
+        N.check(call(
             self._h, dptr, cptr, means.ctypes.data if means is not None else None,
             stds.ctypes.data if stds is not None else None, n, _ptr(out)))
         return out
 
     def inverse_host(self, U, cond=None, want_log_det: bool = False):
-        """Chain InverseFunction on HOST arrays -> (x [N, D], log_det [N] or None), pinned CPU tensors."""
+        """Chain InverseFunction on HOST arrays -> (x [N, D], log_det [N] or None), CPU tensors."""
         U = self._host_rows(U, self.input_dim, "inputs")
         cond = self._host_cond(cond, U.shape[0])
-        X = pinned_empty(tuple(U.shape))
-        ld = pinned_empty((U.shape[0],)) if want_log_det else None
+        X = torch.empty(tuple(U.shape), dtype=torch.float32)
+        ld = torch.empty((U.shape[0],), dtype=torch.float32) if want_log_det else None
         N.check(N.lib().pzb_inverse_host(self._h, _ptr(U), _ptr(cond), U.shape[0], _ptr(X), _ptr(ld)))
         return X, ld
 
     def forward_host(self, X, cond=None):
-        """Chain ForwardFunction on HOST arrays -> (u [N, D], log_det [N]), pinned CPU tensors."""
+        """Chain ForwardFunction on HOST arrays -> (u [N, D], log_det [N]), CPU tensors."""
         X = self._host_rows(X, self.input_dim, "inputs")
         cond = self._host_cond(cond, X.shape[0])
-        U = pinned_empty(tuple(X.shape))
-        ld = pinned_empty((X.shape[0],))
+        U = torch.empty(tuple(X.shape), dtype=torch.float32)
+        ld = torch.empty((X.shape[0],), dtype=torch.float32)
         N.check(N.lib().pzb_forward_host(self._h, _ptr(X), _ptr(cond), X.shape[0], _ptr(U), _ptr(ld)))
         return U, ld
 

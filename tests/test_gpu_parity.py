@@ -1210,8 +1210,8 @@ def test_elementwise_steps_between_coupling_stages(engine):
 
 def test_dataframe_columns_take_the_pipelined_cast():
     """Flow.log_prob on a float64 DataFrame (pzb_log_prob_host_columns: cast + gather + condition scaling inside
-    the pipeline) == the float32 array path, for an unconditional and a conditional flow; a float32 or mixed
-    DataFrame still works through the array path."""
+    the pipeline) == the float32 array path, for an unconditional and a conditional flow; a float32 DataFrame
+    takes the same route (pzb_log_prob_host_columns_f32), a mixed one the array path."""
     from pzflow_b200 import Flow
     from pzflow_b200.examples import get_example_flow
     flow = get_example_flow()
@@ -1224,6 +1224,8 @@ def test_dataframe_columns_take_the_pipelined_cast():
     np.testing.assert_array_equal(lp, want)
     np.testing.assert_array_equal(flow.log_prob(df.astype(np.float32)), want)
     np.testing.assert_array_equal(flow.log_prob(df.iloc[::-1])[::-1], want)   # non-contiguous column views
+    mixed = df.astype({"redshift": np.float32})
+    np.testing.assert_array_equal(flow.log_prob(mixed), want)
     cfg = F.config_c4(1)[0]
     cflow = Flow(_dictionary={"class": "Flow", "data_columns": F.GALAXY_COLUMNS, "conditional_columns": ("a", "b"),
                               "condition_means": np.array([0.5, -1.0], np.float32),
@@ -1239,3 +1241,7 @@ def test_dataframe_columns_take_the_pipelined_cast():
     cond = (dfc[["a", "b"]].to_numpy().astype(np.float32) - np.array([0.5, -1.0], np.float32)) / np.array([2.0, 0.25], np.float32)
     wantc = _np(cflow._plan().log_prob(torch.from_numpy(X[:m].astype(np.float32)).cuda(), torch.from_numpy(cond).cuda()))
     np.testing.assert_array_equal(got, wantc)
+    np.testing.assert_array_equal(cflow.log_prob(dfc.astype(np.float32)), _np(cflow._plan().log_prob(
+        torch.from_numpy(X[:m].astype(np.float32)).cuda(),
+        torch.from_numpy((dfc[["a", "b"]].to_numpy(dtype=np.float32) - np.array([0.5, -1.0], np.float32))
+                         / np.array([2.0, 0.25], np.float32)).cuda())))
