@@ -303,6 +303,17 @@ int pzb_forward_host(const pzb_plan *plan, const float *X, const float *cond, in
                      float *U, float *log_det);
 int pzb_inverse_host(const pzb_plan *plan, const float *U, const float *cond, int64_t N,
                      float *X, float *log_det);
+/* Flow.sample (pzflow/flow.py:783-795) for latent draws that were made ON THE DEVICE (pzb_sample_uniform, or any
+ * device array U_dev [N, D]; cond_dev [N, C] device or NULL): x = inverse(u) chunk by chunk, results in the HOST
+ * arrays X [N, D] and log_det [N] (or NULL) through the same pipeline (kernel | D2H | host copy overlap, pageable
+ * destinations staged).  after_stream: the stream the draws were produced on; it is synchronised first. */
+int pzb_inverse_to_host(const pzb_plan *plan, const float *U_dev, const float *cond_dev, int64_t N, float *X,
+                        float *log_det, void *after_stream);
+/* The same with the samples delivered as D separate HOST column arrays X_cols[j][N] -- the layout a pandas
+ * DataFrame keeps its values in, so that Flow.sample's `pd.DataFrame(x, columns=...)` (flow.py:797-817) wraps the
+ * result without the transposing copy a row-major [N, D] array costs it (160 ms for 10 M rows of 7 columns). */
+int pzb_inverse_to_host_columns(const pzb_plan *plan, const float *U_dev, const float *cond_dev, int64_t N,
+                                float *const *X_cols, void *after_stream);
 int pzb_posterior_host(const pzb_plan *plan, const float *rest, const float *cond, int64_t Ng,
                        int32_t col_idx, const float *grid, int32_t G, int32_t normalize,
                        int32_t nan_to_zero, float *pdfs);

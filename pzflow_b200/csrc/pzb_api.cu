@@ -162,6 +162,18 @@ struct DeviceGuard {
   }
 };
 
+// float32 rows [n, w] -> w column arrays (rows r0.. of each), on all host cores
+static void scatter_rows_to_cols(const float* src, int w, int64_t r0, int64_t n, float* const* cols, int threads) {
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (int64_t blk = 0; blk < (n + 4095) / 4096; ++blk) {
+    const int64_t a = blk * 4096, b = std::min<int64_t>(n, a + 4096);
+    for (int j = 0; j < w; ++j) {
+      float* dst = cols[j] + r0;
+      for (int64_t r = a; r < b; ++r) dst[r] = src[r * w + j];
+    }
+  }
+}
+
 // float64 / float32 columns -> float32 rows [n, w] on all host cores (explicit thread count: torchrun exports OMP_NUM_THREADS=1)
 template <typename T>
 static void gather_cast_rows(const void* const* cols, int w, int64_t r0, int64_t n, float* dst, const float* mean,
@@ -1077,9 +1089,11 @@ int pzb_adam_step(float* params, const float* grads, float* m, float* v, int64_t
 struct HostJob {
   int mode = MODE_LOGPROB;
   const float* in = nullptr;   // [units, in_w]
+  bool in_on_device = false;   // `in` / `cond` are DEVICE arrays (latent draws made on the device): no H2D stage
   int in_w = 0;
   const float* cond = nullptr; // [units, C] or NULL
   float* out0 = nullptr;       // [units, out0_w]
+  float* const* out_cols = nullptr;  // instead of out0: out0_w HOST column arrays of `units` values each (DataFrame layout)
   int out0_w = 1;
   float* out1 = nullptr;       // [units] or NULL
   const float* grid = nullptr; // posterior: host [G]
@@ -1175,8 +1189,9 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
   if (chunk < 1) chunk = 1;
   if (chunk > job.units) chunk = job.units;
   // every ring buffer may still be in flight from this call only (the previous call drained)
-  ce = pipe_reserve(hp.d_in, &hp.cap_in, (size_t)chunk * std::max(job.in_w, 1) * sizeof(float), HostPipe::NBUF);
-  if (ce == cudaSuccess && C > 0)
+  if (!job.in_on_device)
+    ce = pipe_reserve(hp.d_in, &hp.cap_in, (size_t)chunk * std::max(job.in_w, 1) * sizeof(float), HostPipe::NBUF);
+  if (ce == cudaSuccess && C > 0 && !job.in_on_device)
     ce = pipe_reserve(hp.d_cond, &hp.cap_cond, (size_t)chunk * C * sizeof(float), HostPipe::NBUF);
   if (ce == cudaSuccess)
     ce = pipe_reserve(hp.d_out0, &hp.cap_out0, (size_t)chunk * job.out0_w * sizeof(float), HostPipe::NBUF);
@@ -1189,7 +1204,7 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
   }
   // float32 rows in pageable memory (a plain NumPy array) are staged like the float64 columns are: copied into
   // page-locked buffers by all host cores, chunk by chunk, so that the H2D copies run at PCIe speed and overlap
-  const bool stage_in = job.in != nullptr && job.in_w > 0 &&
+  const bool stage_in = job.in != nullptr && job.in_w > 0 && !job.in_on_device &&
                         (size_t)job.units * job.in_w * sizeof(float) >= (8u << 20) && !host_pointer_is_pinned(job.in);
   if (ce == cudaSuccess && (job.in_cols || stage_in))
     ce = host_reserve(hp.h_in, &hp.cap_hin, (size_t)chunk * std::max(job.in_w, 1) * sizeof(float), HostPipe::NBUF);
@@ -1197,7 +1212,7 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     ce = host_reserve(hp.h_cond, &hp.cap_hcond, (size_t)chunk * C * sizeof(float), HostPipe::NBUF);
   // results bound for pageable memory go through page-locked staging (small results are not worth the detour)
   const size_t out_total = (size_t)job.units * job.out0_w * sizeof(float);
-  const bool stage_out = out_total >= (8u << 20) && !host_pointer_is_pinned(job.out0);
+  const bool stage_out = job.out_cols != nullptr || (out_total >= (8u << 20) && !host_pointer_is_pinned(job.out0));
   if (ce == cudaSuccess && stage_out)
     ce = host_reserve(hp.h_out0, &hp.cap_hout0, (size_t)chunk * job.out0_w * sizeof(float), HostPipe::NBUF);
   if (ce == cudaSuccess && stage_out && job.out1)
@@ -1209,8 +1224,12 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     const int bj = (int)(j % HostPipe::NBUF);
     cudaError_t e = cudaEventSynchronize(hp.ev_out[bj]);
     if (e != cudaSuccess) return e;
-    parallel_copy(job.out0 + pend_u0[bj] * job.out0_w, hp.h_out0[bj], (size_t)pend_nu[bj] * job.out0_w * sizeof(float),
-                  host_threads);
+    if (job.out_cols)
+      scatter_rows_to_cols(static_cast<const float*>(hp.h_out0[bj]), job.out0_w, pend_u0[bj], pend_nu[bj], job.out_cols,
+                           host_threads);
+    else
+      parallel_copy(job.out0 + pend_u0[bj] * job.out0_w, hp.h_out0[bj], (size_t)pend_nu[bj] * job.out0_w * sizeof(float),
+                    host_threads);
     if (job.out1) memcpy(job.out1 + pend_u0[bj], hp.h_out1[bj], (size_t)pend_nu[bj] * sizeof(float));
     return cudaSuccess;
   };
@@ -1246,9 +1265,9 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
       }
     }
     if (i >= HostPipe::NBUF) cudaStreamWaitEvent(hp.s_in, hp.ev_k[b], 0);  // kernel i-NBUF has read d_in[b]
-    if (job.in_w > 0)
+    if (job.in_w > 0 && !job.in_on_device)
       ce = cudaMemcpyAsync(hp.d_in[b], src_in, (size_t)nu * job.in_w * sizeof(float), cudaMemcpyHostToDevice, hp.s_in);
-    if (ce == cudaSuccess && C > 0)
+    if (ce == cudaSuccess && C > 0 && !job.in_on_device)
       ce = cudaMemcpyAsync(hp.d_cond[b], src_cond, (size_t)nu * C * sizeof(float), cudaMemcpyHostToDevice, hp.s_in);
     if (ce == cudaSuccess) ce = cudaEventRecord(hp.ev_in[b], hp.s_in);
     if (ce != cudaSuccess) { rc = cuda_fail(ce, "host pipeline H2D"); break; }
@@ -1256,8 +1275,8 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     if (i >= HostPipe::NBUF) cudaStreamWaitEvent(hp.s_k, hp.ev_out[b], 0);  // D2H i-NBUF has read d_out[b]
     LaunchArgs a{};
     a.mode = job.mode;
-    a.X = static_cast<const float*>(hp.d_in[b]);
-    a.cond = C > 0 ? static_cast<const float*>(hp.d_cond[b]) : nullptr;
+    a.X = job.in_on_device ? src_in : static_cast<const float*>(hp.d_in[b]);
+    a.cond = C > 0 ? (job.in_on_device ? src_cond : static_cast<const float*>(hp.d_cond[b])) : nullptr;
     a.grid = static_cast<const float*>(hp.d_grid);
     a.G = job.G;
     a.col_idx = job.col_idx;
@@ -1270,7 +1289,7 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     if (rc != PZB_OK) break;
     cudaEventRecord(hp.ev_k[b], hp.s_k);
     cudaStreamWaitEvent(hp.s_out, hp.ev_k[b], 0);
-    float* dst0 = stage_out ? static_cast<float*>(hp.h_out0[b]) : job.out0 + u0 * job.out0_w;
+    float* dst0 = stage_out ? static_cast<float*>(hp.h_out0[b]) : job.out0 + u0 * job.out0_w;  // (out_cols => staged)
     float* dst1 = stage_out ? static_cast<float*>(hp.h_out1[b]) : (job.out1 ? job.out1 + u0 : nullptr);
     ce = cudaMemcpyAsync(dst0, hp.d_out0[b], (size_t)nu * job.out0_w * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out);
     if (ce == cudaSuccess && job.out1)
@@ -1380,6 +1399,52 @@ int pzb_inverse_host(const pzb_plan* plan, const float* U, const float* cond, in
   j.out1 = log_det;
   j.units = N;
   return run_host(plan, j, "inverse_host");
+}
+
+int pzb_inverse_to_host(const pzb_plan* plan, const float* U_dev, const float* cond_dev, int64_t N, float* X,
+                        float* log_det, void* after_stream) {
+  int rc = check_common(plan, U_dev, cond_dev, N, X, "inverse_to_host");
+  if (rc) return rc;
+  // the draws were produced on `after_stream`: they must be complete before the pipeline's own streams read them
+  if (N > 0) {
+    DeviceGuard guard(plan->device);
+    cudaError_t ce = cudaStreamSynchronize((cudaStream_t)after_stream);
+    if (ce != cudaSuccess) return cuda_fail(ce, "inverse_to_host: producer stream");
+  }
+  HostJob j;
+  j.mode = MODE_INVERSE;
+  j.in = U_dev;
+  j.in_on_device = true;
+  j.in_w = plan->host.D;
+  j.cond = cond_dev;
+  j.out0 = X;
+  j.out0_w = plan->host.D;
+  j.out1 = log_det;
+  j.units = N;
+  return run_host(plan, j, "inverse_to_host");
+}
+
+int pzb_inverse_to_host_columns(const pzb_plan* plan, const float* U_dev, const float* cond_dev, int64_t N,
+                                float* const* X_cols, void* after_stream) {
+  int rc = check_common(plan, U_dev, cond_dev, N, X_cols, "inverse_to_host_columns");
+  if (rc) return rc;
+  for (int j = 0; N > 0 && j < plan->host.D; ++j)
+    if (X_cols[j] == nullptr) return fail(PZB_ERR_INVALID, "inverse_to_host_columns: column %d is NULL", j);
+  if (N > 0) {
+    DeviceGuard guard(plan->device);
+    cudaError_t ce = cudaStreamSynchronize((cudaStream_t)after_stream);
+    if (ce != cudaSuccess) return cuda_fail(ce, "inverse_to_host_columns: producer stream");
+  }
+  HostJob j;
+  j.mode = MODE_INVERSE;
+  j.in = U_dev;
+  j.in_on_device = true;
+  j.in_w = plan->host.D;
+  j.cond = cond_dev;
+  j.out_cols = X_cols;
+  j.out0_w = plan->host.D;
+  j.units = N;
+  return run_host(plan, j, "inverse_to_host_columns");
 }
 
 int pzb_posterior_host(const pzb_plan* plan, const float* rest, const float* cond, int64_t Ng, int32_t col_idx,

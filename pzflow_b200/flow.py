@@ -378,38 +378,21 @@ class Flow:
         else:
             u = self.latent.sample_device(n, seed)  # draws stay on the device
         x = self._inverse_to_host(plan, u, cond)
+        # x is a fresh array in the frame's own (column-major) layout: copy=False lets pandas wrap it as it is
         if self.conditional_columns is None:
-            return pd.DataFrame(x, columns=self.data_columns)
+            return pd.DataFrame(x, columns=self.data_columns, copy=False)
         if save_conditions:
             cond = cond * np.asarray(self._condition_stds, np.float32) + np.asarray(self._condition_means, np.float32)
             return pd.DataFrame(np.hstack((x, cond)),
                                 columns=self.data_columns + self.conditional_columns).set_index(conditions_idx)
-        return pd.DataFrame(x, columns=self.data_columns).set_index(conditions_idx)
+        return pd.DataFrame(x, columns=self.data_columns, copy=False).set_index(conditions_idx)
 
     @staticmethod
     def _inverse_to_host(plan: Plan, u: torch.Tensor, cond) -> np.ndarray:
-        """x = inverse(u) for device-resident latent draws, returned as a NumPy array: the draws are cut into
-        chunks whose results are copied into page-locked memory on a side stream while the next chunk's kernel
-        runs (the D2H copy of 10 M samples otherwise costs more than the kernel)."""
-        n = u.shape[0]
-        out = torch.empty((n, plan.input_dim), dtype=torch.float32, pin_memory=True)
-        cond_t = None if cond is None else torch.as_tensor(cond).to(plan.device, torch.float32)
-        step = 1 << 20
-        main = torch.cuda.current_stream(plan.device)
-        side = torch.cuda.Stream(plan.device)
-        keep = []
-        for r0 in range(0, n, step):
-            r1 = min(n, r0 + step)
-            xc = plan.inverse(u[r0:r1], None if cond_t is None else cond_t[r0:r1], want_log_det=False)[0]
-            done = torch.cuda.Event()
-            done.record(main)
-            side.wait_event(done)
-            with torch.cuda.stream(side):
-                out[r0:r1].copy_(xc, non_blocking=True)
-            xc.record_stream(side)
-            keep.append(xc)
-        side.synchronize()
-        return out.numpy()
+        """x = inverse(u) for device-resident latent draws, returned as a NumPy array [N, D] in column-major memory
+        (pzb_inverse_to_host_columns), which `pd.DataFrame` wraps without its transposing copy: the kernel of one
+        chunk, the D2H copy of the previous one and the host-side scatter into the columns overlap."""
+        return plan.inverse_to_host_columns(u, cond)
 
     # ------------------------------------------------------------------ #
     def _save_dict(self) -> dict:

@@ -308,6 +308,32 @@ class Plan:
         N.check(N.lib().pzb_inverse_host(self._h, _ptr(U), _ptr(cond), U.shape[0], _ptr(X), _ptr(ld)))
         return X, ld
 
+    def inverse_to_host(self, U, cond=None, want_log_det: bool = False):
+        """Chain InverseFunction for DEVICE-resident latent draws U [N, D] -> (x [N, D], log_det [N] or None) as CPU
+        tensors, through the pipelined C call (pzb_inverse_to_host)."""
+        U = self._rows(U, self.input_dim, "inputs")
+        cond = self._cond(cond, U.shape[0])
+        X = torch.empty(tuple(U.shape), dtype=torch.float32)
+        ld = torch.empty((U.shape[0],), dtype=torch.float32) if want_log_det else None
+        with torch.cuda.device(self.device):
+            N.check(N.lib().pzb_inverse_to_host(self._h, _ptr(U), _ptr(cond), U.shape[0], _ptr(X), _ptr(ld),
+                                                torch.cuda.current_stream(self.device).cuda_stream))
+        return X, ld
+
+    def inverse_to_host_columns(self, U, cond=None) -> np.ndarray:
+        """Like inverse_to_host, but returns the samples as a NumPy array of shape [N, D] whose memory is
+        COLUMN-major (the transpose of a C-contiguous [D, N] buffer): `pd.DataFrame(x, columns=...)` wraps that
+        without copying (pzb_inverse_to_host_columns)."""
+        U = self._rows(U, self.input_dim, "inputs")
+        cond = self._cond(cond, U.shape[0])
+        n = U.shape[0]
+        buf = np.empty((self.input_dim, n), dtype=np.float32)
+        cols = (C.c_void_p * self.input_dim)(*[buf[j].ctypes.data for j in range(self.input_dim)])
+        with torch.cuda.device(self.device):
+            N.check(N.lib().pzb_inverse_to_host_columns(self._h, _ptr(U), _ptr(cond), n, cols,
+                                                        torch.cuda.current_stream(self.device).cuda_stream))
+        return buf.T
+
     def forward_host(self, X, cond=None):
         """Chain ForwardFunction on HOST arrays -> (u [N, D], log_det [N]), CPU tensors."""
         X = self._host_rows(X, self.input_dim, "inputs")

@@ -663,6 +663,16 @@ def test_host_pipeline_pageable_results_are_staged_and_identical():
     N.check(N.lib().pzb_forward_host(plan._h, _ptr(Xh), None, n, _ptr(u), _ptr(ld)))
     u_dev, ld_dev = plan.forward(Xh)
     assert _same_bits(u, u_dev) and _same_bits(ld, ld_dev)
+    # Flow.sample's route: latent draws on the device, samples in host memory (pzb_inverse_to_host)
+    x_host, ldi_host = plan.inverse_to_host(u_dev, want_log_det=True)
+    x_dev, ldi_dev = plan.inverse(u_dev)
+    assert not x_host.is_cuda and _same_bits(x_host, x_dev) and _same_bits(ldi_host, ldi_dev)
+    assert plan.inverse_to_host(u_dev[:0])[0].shape == (0, 7)
+    x_cols = plan.inverse_to_host_columns(u_dev)          # [N, D] view of a C-contiguous [D, N] buffer
+    assert x_cols.shape == (n, 7) and x_cols.T.flags.c_contiguous
+    assert _same_bits(torch.from_numpy(np.ascontiguousarray(x_cols)), x_dev)
+    frame = pd.DataFrame(x_cols, columns=list("abcdefg"), copy=False)
+    assert np.shares_memory(frame["c"].to_numpy(), x_cols)             # pandas wraps it without copying
 
 
 def test_host_pipeline_posterior_and_conditions():
