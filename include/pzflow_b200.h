@@ -303,6 +303,16 @@ int pzb_forward_host(const pzb_plan *plan, const float *X, const float *cond, in
                      float *U, float *log_det);
 int pzb_inverse_host(const pzb_plan *plan, const float *U, const float *cond, int64_t N,
                      float *X, float *log_det);
+/* FlowEnsemble.log_prob (pzflow/flowEnsemble.py:189-243, returnEnsemble=False) from DataFrame columns: every chunk
+ * of rows is staged ONCE, evaluated by all n_flows plans (same device, input_dim and n_conditions) and reduced with
+ * log(mean(exp(lp), axis=flows)) on the device, inside the pipeline of flows[0].  Columns are float64, or float32
+ * when cols_are_f32 != 0; the conditions are standard-scaled with ONE mean / std pair (the flows of an ensemble are
+ * trained on the same data; a caller whose flows disagree evaluates them one by one).  out [N] HOST. */
+int pzb_ensemble_log_prob_host_columns(const pzb_plan *const *flows, int32_t n_flows,
+                                       const void *const *data_cols, int32_t cols_are_f32,
+                                       const void *const *cond_cols, const float *cond_means,
+                                       const float *cond_stds, int64_t N, float *out);
+
 /* Flow.sample (pzflow/flow.py:783-795) for latent draws that were made ON THE DEVICE (pzb_sample_uniform, or any
  * device array U_dev [N, D]; cond_dev [N, C] device or NULL): x = inverse(u) chunk by chunk, results in the HOST
  * arrays X [N, D] and log_det [N] (or NULL) through the same pipeline (kernel | D2H | host copy overlap, pageable

@@ -64,7 +64,8 @@ struct HostPipe {
   void* d_out0[NBUF] = {};
   void* d_out1[NBUF] = {};
   void* d_grid = nullptr;
-  size_t cap_in = 0, cap_cond = 0, cap_out0 = 0, cap_out1 = 0, cap_grid = 0;
+  void* d_ens[NBUF] = {};  // ensemble form: [n_flows, chunk] per-flow log-probabilities of a chunk
+  size_t cap_in = 0, cap_cond = 0, cap_out0 = 0, cap_out1 = 0, cap_grid = 0, cap_ens = 0;
   // page-locked host staging for the column-source form (float64 DataFrame columns -> float32 rows)
   void* h_in[NBUF] = {};
   void* h_cond[NBUF] = {};
@@ -628,6 +629,7 @@ void pzb_plan_destroy(pzb_plan* plan) {
       cudaFree(hp.d_cond[b]);
       cudaFree(hp.d_out0[b]);
       cudaFree(hp.d_out1[b]);
+      cudaFree(hp.d_ens[b]);
       cudaEventDestroy(hp.ev_in[b]);
       cudaEventDestroy(hp.ev_k[b]);
       cudaEventDestroy(hp.ev_out[b]);
@@ -1104,6 +1106,10 @@ struct HostJob {
   const void* const* in_cols = nullptr;
   const void* const* cond_cols = nullptr;
   bool cols_f32 = false;       // the columns are float32 (else float64)
+  // ensemble form (log_prob only): every chunk is evaluated by all n_flows plans (plan == flows[0]) and reduced with
+  // log(mean(exp)) (pzflow/flowEnsemble.py:243) before it leaves the device
+  const pzb_plan* const* flows = nullptr;
+  int n_flows = 0;
   const float* cond_mean = nullptr;
   const float* cond_std = nullptr;
 };
@@ -1197,6 +1203,8 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     ce = pipe_reserve(hp.d_out0, &hp.cap_out0, (size_t)chunk * job.out0_w * sizeof(float), HostPipe::NBUF);
   if (ce == cudaSuccess && job.out1)
     ce = pipe_reserve(hp.d_out1, &hp.cap_out1, (size_t)chunk * sizeof(float), HostPipe::NBUF);
+  if (ce == cudaSuccess && job.n_flows > 0)
+    ce = pipe_reserve(hp.d_ens, &hp.cap_ens, (size_t)chunk * job.n_flows * sizeof(float), HostPipe::NBUF);
   if (ce == cudaSuccess && job.grid) {
     ce = pipe_reserve(&hp.d_grid, &hp.cap_grid, (size_t)job.G * sizeof(float), 1);
     if (ce == cudaSuccess)
@@ -1283,7 +1291,17 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     a.N = nu * rows_per_unit;
     a.out0 = static_cast<float*>(hp.d_out0[b]);
     a.out1 = job.out1 ? static_cast<float*>(hp.d_out1[b]) : nullptr;
-    rc = launch_chain(plan, a, hp.s_k);
+    if (job.n_flows > 0) {
+      float* ens = static_cast<float*>(hp.d_ens[b]);
+      for (int f = 0; f < job.n_flows && rc == PZB_OK; ++f) {
+        LaunchArgs af = a;
+        af.out0 = ens + (size_t)f * nu;
+        rc = launch_chain(job.flows[f], af, hp.s_k);
+      }
+      if (rc == PZB_OK) rc = pzb_ensemble_logmeanexp(ens, job.n_flows, nu, a.out0, hp.s_k);
+    } else {
+      rc = launch_chain(plan, a, hp.s_k);
+    }
     if (rc == PZB_OK && job.mode == MODE_POSTERIOR && (job.normalize || job.nan_to_zero))
       rc = pzb_normalize_pdfs(a.out0, nu, job.G, a.grid, job.normalize, job.nan_to_zero, hp.s_k);
     if (rc != PZB_OK) break;
@@ -1369,6 +1387,44 @@ int pzb_log_prob_host_columns_f32(const pzb_plan* plan, const float* const* data
                                   const float* cond_means, const float* cond_stds, int64_t N, float* out) {
   return log_prob_columns(plan, reinterpret_cast<const void* const*>(data_cols),
                           reinterpret_cast<const void* const*>(cond_cols), true, cond_means, cond_stds, N, out);
+}
+
+int pzb_ensemble_log_prob_host_columns(const pzb_plan* const* flows, int32_t n_flows, const void* const* data_cols,
+                                       int32_t cols_are_f32, const void* const* cond_cols, const float* cond_means,
+                                       const float* cond_stds, int64_t N, float* out) {
+  if (!flows || n_flows < 1) return fail(PZB_ERR_INVALID, "ensemble_log_prob_host_columns: no flows");
+  for (int f = 0; f < n_flows; ++f) {
+    if (!flows[f]) return fail(PZB_ERR_INVALID, "ensemble_log_prob_host_columns: flow %d is NULL", f);
+    if (flows[f]->device != flows[0]->device || flows[f]->host.D != flows[0]->host.D || flows[f]->host.C != flows[0]->host.C)
+      return fail(PZB_ERR_INVALID, "ensemble_log_prob_host_columns: flow %d differs from flow 0 in device or shape", f);
+    if (!flows[f]->latent_ready)
+      return fail(PZB_ERR_INVALID, "ensemble_log_prob_host_columns: flow %d needs pzb_plan_set_latent first", f);
+  }
+  const pzb_plan* plan = flows[0];
+  if (N < 0) return fail(PZB_ERR_INVALID, "ensemble_log_prob_host_columns: negative row count");
+  const int D = plan->host.D, C = plan->host.C;
+  if (N > 0 && (data_cols == nullptr || out == nullptr))
+    return fail(PZB_ERR_INVALID, "ensemble_log_prob_host_columns: NULL buffer");
+  if (N > 0 && C > 0 && (cond_cols == nullptr || cond_means == nullptr || cond_stds == nullptr))
+    return fail(PZB_ERR_INVALID, "ensemble_log_prob_host_columns: the flows are conditional (C = %d) but conditions are NULL", C);
+  for (int j = 0; N > 0 && j < D; ++j)
+    if (data_cols[j] == nullptr) return fail(PZB_ERR_INVALID, "ensemble_log_prob_host_columns: data column %d is NULL", j);
+  for (int j = 0; N > 0 && j < C; ++j)
+    if (cond_cols[j] == nullptr) return fail(PZB_ERR_INVALID, "ensemble_log_prob_host_columns: condition column %d is NULL", j);
+  HostJob j;
+  j.mode = MODE_LOGPROB;
+  j.in_cols = data_cols;
+  j.cols_f32 = cols_are_f32 != 0;
+  j.in_w = D;
+  j.cond_cols = C > 0 ? cond_cols : nullptr;
+  j.cond_mean = cond_means;
+  j.cond_std = cond_stds;
+  j.out0 = out;
+  j.out0_w = 1;
+  j.units = N;
+  j.flows = flows;
+  j.n_flows = n_flows;
+  return run_host(plan, j, "ensemble_log_prob_host_columns");
 }
 
 int pzb_forward_host(const pzb_plan* plan, const float* X, const float* cond, int64_t N, float* U, float* log_det) {

@@ -17,7 +17,20 @@ import torch
 from . import distributions
 from .bijectors import Bijector_Info, InitFunction
 from .flow import Flow, _load_pickle
-from .plan import ensemble_logmeanexp, ensemble_posterior_mean, normalize_pdfs_
+from .plan import (ensemble_log_prob_host_columns, ensemble_logmeanexp, ensemble_posterior_mean,
+                   normalize_pdfs_)
+
+
+def _frame_rows_to_device(inputs: pd.DataFrame, columns, device) -> torch.Tensor:
+    """float32 rows [N, D] on the device from DataFrame columns: every column goes up as it is (a contiguous 1-D
+    array) and the down-cast (pzflow/flow.py:442) and the row gather happen on the GPU -- the NumPy route
+    (`to_numpy().astype(float32)`) is a strided 2-D copy that costs more than evaluating the flows."""
+    import warnings
+    with warnings.catch_warnings():
+        # pandas hands out read-only column views; they are only read here (copied to the device)
+        warnings.filterwarnings("ignore", message="The given NumPy array is not writable")
+        cols = [torch.from_numpy(np.ascontiguousarray(inputs[c].to_numpy())).to(device) for c in columns]
+    return torch.stack([c.to(torch.float32) for c in cols], dim=1).contiguous()
 
 
 class FlowEnsemble:
@@ -88,18 +101,47 @@ class FlowEnsemble:
             with np.errstate(divide="ignore"):
                 return np.log(np.exp(lps).mean(axis=1, dtype=np.float32))
         columns = list(flows[0].data_columns)
+        if not returnEnsemble:
+            fused = self._log_prob_fused(flows, inputs, columns)
+            if fused is not None:
+                return fused
         X = None
         lps = []
         for flow in flows:
             flow._check_bijector()
             plan = flow._plan()
             if X is None:  # one host->device copy of the rows, shared by every flow
-                X = torch.from_numpy(inputs[columns].to_numpy().astype(np.float32, copy=False)).to(plan.device)
+                X = _frame_rows_to_device(inputs, columns, plan.device)
             lps.append(flow._log_prob(flow._params, X, flow._get_conditions(inputs)))
         ensemble = torch.stack(lps, dim=0)  # [n_flows, N]
         if returnEnsemble:
             return ensemble.t().contiguous().cpu().numpy()
         return ensemble_logmeanexp(ensemble).cpu().numpy()
+
+    @staticmethod
+    def _log_prob_fused(flows, inputs, columns):
+        """The ensemble rule inside the host pipeline (one staging of the rows for all flows), when the frame's
+        columns are all float64 or all float32 and the flows scale their conditions alike; else None."""
+        cols = [inputs[c].to_numpy() for c in columns]
+        ctype = cols[0].dtype
+        if ctype not in (np.float64, np.float32) or any(c.dtype != ctype or c.ndim != 1 for c in cols):
+            return None
+        ccols = means = stds = None
+        cond_names = flows[0].conditional_columns
+        if cond_names is not None:
+            means, stds = flows[0]._condition_means, flows[0]._condition_stds
+            for flow in flows[1:]:
+                if flow.conditional_columns != cond_names or \
+                        not np.array_equal(np.asarray(flow._condition_means), np.asarray(means)) or \
+                        not np.array_equal(np.asarray(flow._condition_stds), np.asarray(stds)):
+                    return None
+            ccols = [np.asarray(inputs[c].to_numpy(), dtype=ctype) for c in cond_names]
+        for flow in flows:
+            flow._check_bijector()
+        plans = [flow._plan() for flow in flows]
+        if len({(p.device, p.input_dim, p.n_conditions) for p in plans}) != 1:
+            return None
+        return ensemble_log_prob_host_columns(plans, cols, ccols, means, stds).numpy()
 
     def posterior(self, inputs: pd.DataFrame, column: str, grid, marg_rules: dict = None,
                   normalize: bool = True, err_samples: int = None, seed: int = None,

@@ -480,6 +480,40 @@ class Plan:
 
 
 # ---- reductions that are not tied to one plan ---------------------------------
+def ensemble_log_prob_host_columns(plans, data_cols, cond_cols=None, cond_means=None, cond_stds=None) -> torch.Tensor:
+    """FlowEnsemble.log_prob from DataFrame COLUMNS (float64, or all float32): each chunk of rows is staged once,
+    evaluated by every plan and reduced with log(mean(exp)) on the device (pzb_ensemble_log_prob_host_columns).
+    Returns a CPU tensor [N]."""
+    p0 = plans[0]
+    f32 = all(getattr(c, "dtype", None) == np.float32 for c in data_cols)
+    ctype = np.float32 if f32 else np.float64
+    cols = [np.ascontiguousarray(c, dtype=ctype) for c in data_cols]
+    if len(cols) != p0.input_dim:
+        raise ValueError(f"expected {p0.input_dim} data columns, got {len(cols)}")
+    n = len(cols[0])
+    if any(c.ndim != 1 or len(c) != n for c in cols):
+        raise ValueError("data columns must be 1-D arrays of equal length")
+    ccols, means, stds = [], None, None
+    if p0.n_conditions > 0:
+        if cond_cols is None:
+            raise ValueError(f"this bijector is conditional: conditions [N, {p0.n_conditions}] are required")
+        ccols = [np.ascontiguousarray(c, dtype=ctype) for c in list(cond_cols)[: p0.n_conditions]]
+        if len(ccols) < p0.n_conditions or any(c.ndim != 1 or len(c) != n for c in ccols):
+            raise ValueError(f"conditions must be {p0.n_conditions} columns of {n} values")
+        means = np.ascontiguousarray(np.zeros(p0.n_conditions) if cond_means is None else cond_means,
+                                     dtype=np.float32)[: p0.n_conditions]
+        stds = np.ascontiguousarray(np.ones(p0.n_conditions) if cond_stds is None else cond_stds,
+                                    dtype=np.float32)[: p0.n_conditions]
+    handles = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    dptr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    cptr = (C.c_void_p * max(1, len(ccols)))(*[c.ctypes.data for c in ccols]) if ccols else None
+    out = torch.empty((n,), dtype=torch.float32)
+    N.check(N.lib().pzb_ensemble_log_prob_host_columns(
+        handles, len(plans), dptr, int(f32), cptr, means.ctypes.data if means is not None else None,
+        stds.ctypes.data if stds is not None else None, n, _ptr(out)))
+    return out
+
+
 def ensemble_logmeanexp(lp: torch.Tensor) -> torch.Tensor:
     """log(mean(exp(lp), axis=flows)) for lp [n_flows, N] (pzflow/flowEnsemble.py:243)."""
     lp = lp.contiguous()

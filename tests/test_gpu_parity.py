@@ -600,6 +600,46 @@ def test_ensemble_reductions_match_oracle():
     np.testing.assert_allclose(got, want, rtol=5e-6)
 
 
+def test_ensemble_log_prob_fused_in_the_host_pipeline():
+    """FlowEnsemble.log_prob(DataFrame) takes pzb_ensemble_log_prob_host_columns (rows staged once, all flows and
+    the log-mean-exp on the device per chunk): same values as the flows evaluated one by one + the ensemble rule,
+    unconditional and conditional, float64 and float32 frames; returnEnsemble keeps the per-flow route."""
+    from pzflow_b200 import Flow, FlowEnsemble
+    cfgs = F.config_c4(3)
+    dicts = {f"Flow {i}": {"class": "Flow", "data_columns": F.GALAXY_COLUMNS, "conditional_columns": ("a", "b"),
+                           "condition_means": np.array([0.5, -1.0], np.float32),
+                           "condition_stds": np.array([2.0, 0.25], np.float32), "data_error_model": None,
+                           "condition_error_model": None, "autoscale_conditions": True, "info": None,
+                           "latent_info": c["latent_info"], "bijector_info": c["bijector_info"], "params": c["params"]}
+             for i, c in enumerate(cfgs)}
+    ens = FlowEnsemble.__new__(FlowEnsemble)
+    ens._ensemble = {k: Flow(_dictionary=dict(v)) for k, v in dicts.items()}
+    ens.data_columns, ens.conditional_columns = F.GALAXY_COLUMNS, ("a", "b")
+    rng = np.random.default_rng(8)
+    n = 700_001                                            # several pipeline chunks
+    ex = F.example_flow()
+    mins, maxs = ex["bijector_info"][1][0][1][0], ex["bijector_info"][1][0][1][1]
+    df = pd.DataFrame(rng.uniform(mins, maxs, size=(n, 7)), columns=F.GALAXY_COLUMNS)
+    df["a"], df["b"] = rng.normal(0.5, 2.0, n), rng.normal(-1.0, 0.25, n)
+    per_flow = ens.log_prob(df, returnEnsemble=True)       # [N, 3], the per-flow route
+    assert per_flow.shape == (n, 3)
+    with np.errstate(divide="ignore", over="ignore"):
+        want = np.log(np.exp(per_flow.astype(np.float64)).mean(axis=1))
+    got = ens.log_prob(df)
+    # (the ensemble rule is the reference's literal float32 log(mean(exp(lp))): below lp ~ -87 exp() is subnormal,
+    # so the comparison with the float64 evaluation stops at -80)
+    fin = np.isfinite(want) & (want > -80.0)
+    assert fin.mean() > 0.9
+    np.testing.assert_allclose(got[fin], want[fin], rtol=2e-6, atol=2e-6)
+    assert np.isfinite(got[fin]).all()
+    got32 = ens.log_prob(df.astype(np.float32))
+    np.testing.assert_allclose(got32[fin], want[fin], rtol=1e-4, atol=1e-4)   # inputs rounded to float32 first
+    # flows that scale their conditions differently are evaluated one by one (and still agree with the rule)
+    ens._ensemble["Flow 1"]._condition_means = np.array([0.4, -1.0], np.float32)
+    assert FlowEnsemble._log_prob_fused(list(ens._ensemble.values()), df, list(F.GALAXY_COLUMNS)) is None
+    assert ens.log_prob(df[:1000]).shape == (1000,)
+
+
 def test_uniform_sampler():
     from pzflow_b200.plan import sample_uniform
     u = sample_uniform(200_000, 7, 5.0, seed=3)
