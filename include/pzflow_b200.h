@@ -313,6 +313,15 @@ int pzb_ensemble_log_prob_host_columns(const pzb_plan *const *flows, int32_t n_f
                                        const void *const *cond_cols, const float *cond_means,
                                        const float *cond_stds, int64_t N, float *out);
 
+/* FlowEnsemble.posterior (pzflow/flowEnsemble.py:245-351, returnEnsemble=False) on HOST arrays: every chunk of
+ * galaxies is staged once, each flow writes its un-normalised pdfs (NaN -> 0 per flow if nan_to_zero), the mean over
+ * flows is taken and trapezoid-normalised (if normalize) on the device, and only the [Ng, G] result travels back.
+ * Arguments as pzb_posterior_host; the flows share device, input_dim and n_conditions, and `cond` is the (one)
+ * standard-scaled conditions array. */
+int pzb_ensemble_posterior_host(const pzb_plan *const *flows, int32_t n_flows, const float *rest,
+                                const float *cond, int64_t Ng, int32_t col_idx, const float *grid, int32_t G,
+                                int32_t normalize, int32_t nan_to_zero, float *pdfs);
+
 /* Flow.sample (pzflow/flow.py:783-795) for latent draws that were made ON THE DEVICE (pzb_sample_uniform, or any
  * device array U_dev [N, D]; cond_dev [N, C] device or NULL): x = inverse(u) chunk by chunk, results in the HOST
  * arrays X [N, D] and log_det [N] (or NULL) through the same pipeline (kernel | D2H | host copy overlap, pageable

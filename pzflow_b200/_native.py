@@ -120,6 +120,8 @@ SIGNATURES = {
     "pzb_inverse_to_host_columns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pzb_ensemble_log_prob_host_columns": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pzb_ensemble_posterior_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                              C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "pzb_log_prob_host_columns_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                             C.c_void_p]),
     "pzb_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

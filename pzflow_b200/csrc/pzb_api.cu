@@ -1204,7 +1204,7 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
   if (ce == cudaSuccess && job.out1)
     ce = pipe_reserve(hp.d_out1, &hp.cap_out1, (size_t)chunk * sizeof(float), HostPipe::NBUF);
   if (ce == cudaSuccess && job.n_flows > 0)
-    ce = pipe_reserve(hp.d_ens, &hp.cap_ens, (size_t)chunk * job.n_flows * sizeof(float), HostPipe::NBUF);
+    ce = pipe_reserve(hp.d_ens, &hp.cap_ens, (size_t)chunk * job.out0_w * job.n_flows * sizeof(float), HostPipe::NBUF);
   if (ce == cudaSuccess && job.grid) {
     ce = pipe_reserve(&hp.d_grid, &hp.cap_grid, (size_t)job.G * sizeof(float), 1);
     if (ce == cudaSuccess)
@@ -1293,16 +1293,23 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     a.out1 = job.out1 ? static_cast<float*>(hp.d_out1[b]) : nullptr;
     if (job.n_flows > 0) {
       float* ens = static_cast<float*>(hp.d_ens[b]);
+      const size_t per_flow = (size_t)nu * job.out0_w;
       for (int f = 0; f < job.n_flows && rc == PZB_OK; ++f) {
         LaunchArgs af = a;
-        af.out0 = ens + (size_t)f * nu;
+        af.out0 = ens + f * per_flow;
         rc = launch_chain(job.flows[f], af, hp.s_k);
+        // posterior: every flow's NaNs become 0 before the mean, as in the reference (flowEnsemble.py:317-333 -> flow.py:735-737)
+        if (rc == PZB_OK && job.mode == MODE_POSTERIOR && job.nan_to_zero)
+          rc = pzb_normalize_pdfs(af.out0, nu, job.G, a.grid, 0, 1, hp.s_k);
       }
-      if (rc == PZB_OK) rc = pzb_ensemble_logmeanexp(ens, job.n_flows, nu, a.out0, hp.s_k);
+      if (rc == PZB_OK)
+        rc = job.mode == MODE_POSTERIOR
+                 ? pzb_ensemble_posterior_mean(ens, job.n_flows, nu, job.G, a.grid, job.normalize, a.out0, hp.s_k)
+                 : pzb_ensemble_logmeanexp(ens, job.n_flows, nu, a.out0, hp.s_k);
     } else {
       rc = launch_chain(plan, a, hp.s_k);
     }
-    if (rc == PZB_OK && job.mode == MODE_POSTERIOR && (job.normalize || job.nan_to_zero))
+    if (rc == PZB_OK && job.n_flows == 0 && job.mode == MODE_POSTERIOR && (job.normalize || job.nan_to_zero))
       rc = pzb_normalize_pdfs(a.out0, nu, job.G, a.grid, job.normalize, job.nan_to_zero, hp.s_k);
     if (rc != PZB_OK) break;
     cudaEventRecord(hp.ev_k[b], hp.s_k);
@@ -1425,6 +1432,42 @@ int pzb_ensemble_log_prob_host_columns(const pzb_plan* const* flows, int32_t n_f
   j.flows = flows;
   j.n_flows = n_flows;
   return run_host(plan, j, "ensemble_log_prob_host_columns");
+}
+
+int pzb_ensemble_posterior_host(const pzb_plan* const* flows, int32_t n_flows, const float* rest, const float* cond,
+                                int64_t Ng, int32_t col_idx, const float* grid, int32_t G, int32_t normalize,
+                                int32_t nan_to_zero, float* pdfs) {
+  if (!flows || n_flows < 1) return fail(PZB_ERR_INVALID, "ensemble_posterior_host: no flows");
+  for (int f = 0; f < n_flows; ++f) {
+    if (!flows[f]) return fail(PZB_ERR_INVALID, "ensemble_posterior_host: flow %d is NULL", f);
+    if (flows[f]->device != flows[0]->device || flows[f]->host.D != flows[0]->host.D || flows[f]->host.C != flows[0]->host.C)
+      return fail(PZB_ERR_INVALID, "ensemble_posterior_host: flow %d differs from flow 0 in device or shape", f);
+    if (!flows[f]->latent_ready)
+      return fail(PZB_ERR_INVALID, "ensemble_posterior_host: flow %d needs pzb_plan_set_latent first", f);
+  }
+  const pzb_plan* plan = flows[0];
+  int rc = check_common(plan, plan->host.D > 1 ? (const void*)rest : (const void*)grid, cond, Ng, pdfs,
+                        "ensemble_posterior_host");
+  if (rc) return rc;
+  if (G < 1 || grid == nullptr) return fail(PZB_ERR_INVALID, "ensemble_posterior_host: empty grid");
+  if (col_idx < 0 || col_idx >= plan->host.D)
+    return fail(PZB_ERR_INVALID, "ensemble_posterior_host: column index %d out of range", col_idx);
+  HostJob j;
+  j.mode = MODE_POSTERIOR;
+  j.in = rest;
+  j.in_w = plan->host.D - 1;
+  j.cond = cond;
+  j.out0 = pdfs;
+  j.out0_w = G;
+  j.grid = grid;
+  j.G = G;
+  j.col_idx = col_idx;
+  j.normalize = normalize;
+  j.nan_to_zero = nan_to_zero;
+  j.units = Ng;
+  j.flows = flows;
+  j.n_flows = n_flows;
+  return run_host(plan, j, "ensemble_posterior_host");
 }
 
 int pzb_forward_host(const pzb_plan* plan, const float* X, const float* cond, int64_t N, float* U, float* log_det) {

@@ -17,8 +17,8 @@ import torch
 from . import distributions
 from .bijectors import Bijector_Info, InitFunction
 from .flow import Flow, _load_pickle
-from .plan import (ensemble_log_prob_host_columns, ensemble_logmeanexp, ensemble_posterior_mean,
-                   normalize_pdfs_)
+from .plan import (ensemble_log_prob_host_columns, ensemble_logmeanexp, ensemble_posterior_host,
+                   ensemble_posterior_mean, normalize_pdfs_)
 
 
 def _frame_rows_to_device(inputs: pd.DataFrame, columns, device) -> torch.Tensor:
@@ -149,6 +149,11 @@ class FlowEnsemble:
                   nan_to_zero: bool = True) -> np.ndarray:
         """posterior pdfs, [N, G] or [N, n_flows, G] (pzflow/flowEnsemble.py:245-351)."""
         grid = np.asarray(grid, dtype=np.float32).reshape(-1)
+        flows = list(self._ensemble.values())
+        if marg_rules is None and err_samples is None and not returnEnsemble:
+            fused = self._posterior_fused(flows, inputs, column, grid, normalize, nan_to_zero)
+            if fused is not None:
+                return fused
         per_flow = [flow.posterior(inputs=inputs, column=column, grid=grid, marg_rules=marg_rules,
                                    err_samples=err_samples, seed=seed, batch_size=batch_size,
                                    normalize=False, nan_to_zero=nan_to_zero)
@@ -164,6 +169,33 @@ class FlowEnsemble:
                 ensemble = flat.reshape(nf, n, g)
             return ensemble.permute(1, 0, 2).contiguous().cpu().numpy()
         return ensemble_posterior_mean(ensemble, grid_t, normalize).cpu().numpy()
+
+    @staticmethod
+    def _posterior_fused(flows, inputs, column, grid, normalize, nan_to_zero):
+        """Mean of the flows' pdfs and its normalisation inside the host pipeline (galaxies staged once, only the
+        [N, G] result comes back), when the flows scale their conditions alike; else None."""
+        f0 = flows[0]
+        for flow in flows:
+            flow._check_bijector()
+        if column not in f0.data_columns:
+            return None                      # Flow.posterior raises the reference's error on the per-flow route
+        for flow in flows[1:]:
+            if flow.data_columns != f0.data_columns or flow.conditional_columns != f0.conditional_columns:
+                return None
+            if f0.conditional_columns is not None and (
+                    not np.array_equal(np.asarray(flow._condition_means), np.asarray(f0._condition_means)) or
+                    not np.array_equal(np.asarray(flow._condition_stds), np.asarray(f0._condition_stds))):
+                return None
+        plans = [flow._plan() for flow in flows]
+        if len({(p.device, p.input_dim, p.n_conditions) for p in plans}) != 1:
+            return None
+        columns = list(f0.data_columns)
+        idx = columns.index(column)
+        columns.remove(column)
+        nrows = inputs.shape[0]
+        rest = np.ascontiguousarray(inputs[columns].to_numpy().reshape(nrows, -1), dtype=np.float32)
+        return ensemble_posterior_host(plans, rest, idx, grid, f0._get_conditions(inputs), normalize=normalize,
+                                       nan_to_zero=nan_to_zero).numpy()
 
     def sample(self, nsamples: int = 1, conditions: pd.DataFrame = None, save_conditions: bool = True,
                seed: int = None, returnEnsemble: bool = False) -> pd.DataFrame:

@@ -514,6 +514,23 @@ def ensemble_log_prob_host_columns(plans, data_cols, cond_cols=None, cond_means=
     return out
 
 
+def ensemble_posterior_host(plans, rest, col_idx: int, grid, cond=None, normalize: bool = True,
+                            nan_to_zero: bool = True) -> torch.Tensor:
+    """FlowEnsemble.posterior on HOST arrays (pzb_ensemble_posterior_host): rest [Ng, D-1], grid [G] -> pdfs [Ng, G],
+    the mean over the plans' un-normalised pdfs, normalised on the device chunk by chunk."""
+    p0 = plans[0]
+    rest = p0._host_rows(rest, p0.input_dim - 1, "inputs")
+    cond = p0._host_cond(cond, rest.shape[0])
+    grid = torch.as_tensor(grid).to(dtype=torch.float32).contiguous().reshape(-1).cpu()
+    Ng, G = rest.shape[0], grid.numel()
+    out = torch.empty((Ng, G), dtype=torch.float32)
+    handles = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    N.check(N.lib().pzb_ensemble_posterior_host(handles, len(plans), _ptr(rest) if rest.numel() else None, _ptr(cond),
+                                                Ng, int(col_idx), _ptr(grid), G, int(bool(normalize)),
+                                                int(bool(nan_to_zero)), _ptr(out)))
+    return out
+
+
 def ensemble_logmeanexp(lp: torch.Tensor) -> torch.Tensor:
     """log(mean(exp(lp), axis=flows)) for lp [n_flows, N] (pzflow/flowEnsemble.py:243)."""
     lp = lp.contiguous()

@@ -634,6 +634,20 @@ def test_ensemble_log_prob_fused_in_the_host_pipeline():
     assert np.isfinite(got[fin]).all()
     got32 = ens.log_prob(df.astype(np.float32))
     np.testing.assert_allclose(got32[fin], want[fin], rtol=1e-4, atol=1e-4)   # inputs rounded to float32 first
+    # posterior: mean of the flows' un-normalised pdfs, then the trapezoid normalisation (flowEnsemble.py:346-351)
+    m, grid = 30_000, np.linspace(0.0, 2.3, 700).astype(np.float32)          # 84 MB of pdfs: several chunks
+    sub = df.iloc[:m]
+    raw = np.stack([flow.posterior(sub, column="redshift", grid=grid, normalize=False)
+                    for flow in ens._ensemble.values()], axis=0).astype(np.float64)
+    mean = raw.mean(axis=0)
+    area = np.trapezoid(mean, grid.astype(np.float64), axis=1)[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want_pdf = np.nan_to_num(mean / area, nan=0.0)
+    got_pdf = ens.posterior(sub, column="redshift", grid=grid)
+    assert got_pdf.shape == (m, 700)
+    np.testing.assert_allclose(got_pdf, want_pdf, rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(ens.posterior(sub, column="redshift", grid=grid, normalize=False), mean, rtol=1e-5,
+                               atol=1e-30)
     # flows that scale their conditions differently are evaluated one by one (and still agree with the rule)
     ens._ensemble["Flow 1"]._condition_means = np.array([0.4, -1.0], np.float32)
     assert FlowEnsemble._log_prob_fused(list(ens._ensemble.values()), df, list(F.GALAXY_COLUMNS)) is None
