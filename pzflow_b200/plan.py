@@ -256,13 +256,13 @@ class Plan:
         return t[:, : self.n_conditions].to(dtype=torch.float32).contiguous()
 
     def log_prob_host(self, X, cond=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Flow._log_prob on HOST arrays -> CPU tensor [N] (pzb_log_prob_host).  Fresh results are ordinary pageable
-        tensors: the library stages them (and pageable inputs) through its own page-locked ring, which is as fast as
-        page-locked arrays and saves page-locking a new array per call."""
+        """Flow._log_prob on HOST arrays -> CPU tensor [N] (pzb_log_prob_host).  Fresh results come from ``host_result``
+        (page-locked up to 256 MB, pageable beyond); pageable inputs and results are staged through the library's own
+        page-locked ring."""
         X = self._host_rows(X, self.input_dim, "inputs")
         cond = self._host_cond(cond, X.shape[0])
         if out is None:
-            out = torch.empty((X.shape[0],), dtype=torch.float32)
+            out = host_result((X.shape[0],))
         N.check(N.lib().pzb_log_prob_host(self._h, _ptr(X), _ptr(cond), X.shape[0], _ptr(out)))
         return out
 
@@ -292,7 +292,7 @@ class Plan:
                                         dtype=np.float32)[: self.n_conditions]
         dptr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
         cptr = (C.c_void_p * max(1, len(ccols)))(*[c.ctypes.data for c in ccols]) if ccols else None
-        out = torch.empty((n,), dtype=torch.float32)
+        out = host_result((n,))
         call = N.lib().pzb_log_prob_host_columns_f32 if f32 else N.lib().pzb_log_prob_host_columns
         N.check(call(
             self._h, dptr, cptr, means.ctypes.data if means is not None else None,
@@ -303,8 +303,8 @@ class Plan:
         """Chain InverseFunction on HOST arrays -> (x [N, D], log_det [N] or None), CPU tensors."""
         U = self._host_rows(U, self.input_dim, "inputs")
         cond = self._host_cond(cond, U.shape[0])
-        X = torch.empty(tuple(U.shape), dtype=torch.float32)
-        ld = torch.empty((U.shape[0],), dtype=torch.float32) if want_log_det else None
+        X = host_result(tuple(U.shape))
+        ld = host_result((U.shape[0],)) if want_log_det else None
         N.check(N.lib().pzb_inverse_host(self._h, _ptr(U), _ptr(cond), U.shape[0], _ptr(X), _ptr(ld)))
         return X, ld
 
@@ -313,8 +313,8 @@ class Plan:
         tensors, through the pipelined C call (pzb_inverse_to_host)."""
         U = self._rows(U, self.input_dim, "inputs")
         cond = self._cond(cond, U.shape[0])
-        X = torch.empty(tuple(U.shape), dtype=torch.float32)
-        ld = torch.empty((U.shape[0],), dtype=torch.float32) if want_log_det else None
+        X = host_result(tuple(U.shape))
+        ld = host_result((U.shape[0],)) if want_log_det else None
         with torch.cuda.device(self.device):
             N.check(N.lib().pzb_inverse_to_host(self._h, _ptr(U), _ptr(cond), U.shape[0], _ptr(X), _ptr(ld),
                                                 torch.cuda.current_stream(self.device).cuda_stream))
@@ -338,8 +338,8 @@ class Plan:
         """Chain ForwardFunction on HOST arrays -> (u [N, D], log_det [N]), CPU tensors."""
         X = self._host_rows(X, self.input_dim, "inputs")
         cond = self._host_cond(cond, X.shape[0])
-        U = torch.empty(tuple(X.shape), dtype=torch.float32)
-        ld = torch.empty((X.shape[0],), dtype=torch.float32)
+        U = host_result(tuple(X.shape))
+        ld = host_result((X.shape[0],))
         N.check(N.lib().pzb_forward_host(self._h, _ptr(X), _ptr(cond), X.shape[0], _ptr(U), _ptr(ld)))
         return U, ld
 
@@ -348,14 +348,15 @@ class Plan:
         """Flow.posterior main loop on HOST arrays: rest [Ng, D-1], grid [G] -> pdfs [Ng, G] in host memory;
         neither the [Ng*G, D] expansion nor the whole pdfs array ever sits in HBM.  ``out`` may be page-locked
         (copied into directly) or ordinary pageable memory (the library stages chunks through its own page-locked
-        ring and moves them on with all host cores while the GPU computes the next ones); the default is a fresh
-        pageable array -- page-locking gigabytes for one call costs more than the evaluation itself."""
+        ring and moves them on with all host cores while the GPU computes the next ones); the default is
+        ``host_result``: page-locked up to 256 MB, pageable beyond -- page-locking gigabytes for one call costs more
+        than the evaluation itself."""
         rest = self._host_rows(rest, self.input_dim - 1, "inputs")
         cond = self._host_cond(cond, rest.shape[0])
         grid = torch.as_tensor(grid).to(dtype=torch.float32).contiguous().reshape(-1).cpu()
         Ng, G = rest.shape[0], grid.numel()
         if out is None:
-            out = torch.empty((Ng, G), dtype=torch.float32)
+            out = host_result((Ng, G))
         N.check(N.lib().pzb_posterior_host(self._h, _ptr(rest) if rest.numel() else None, _ptr(cond), Ng,
                                            int(col_idx), _ptr(grid), G, int(bool(normalize)),
                                            int(bool(nan_to_zero)), _ptr(out)))
@@ -507,7 +508,7 @@ def ensemble_log_prob_host_columns(plans, data_cols, cond_cols=None, cond_means=
     handles = (C.c_void_p * len(plans))(*[p._h for p in plans])
     dptr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
     cptr = (C.c_void_p * max(1, len(ccols)))(*[c.ctypes.data for c in ccols]) if ccols else None
-    out = torch.empty((n,), dtype=torch.float32)
+    out = host_result((n,))
     N.check(N.lib().pzb_ensemble_log_prob_host_columns(
         handles, len(plans), dptr, int(f32), cptr, means.ctypes.data if means is not None else None,
         stds.ctypes.data if stds is not None else None, n, _ptr(out)))
@@ -523,7 +524,7 @@ def ensemble_posterior_host(plans, rest, col_idx: int, grid, cond=None, normaliz
     cond = p0._host_cond(cond, rest.shape[0])
     grid = torch.as_tensor(grid).to(dtype=torch.float32).contiguous().reshape(-1).cpu()
     Ng, G = rest.shape[0], grid.numel()
-    out = torch.empty((Ng, G), dtype=torch.float32)
+    out = host_result((Ng, G))
     handles = (C.c_void_p * len(plans))(*[p._h for p in plans])
     N.check(N.lib().pzb_ensemble_posterior_host(handles, len(plans), _ptr(rest) if rest.numel() else None, _ptr(cond),
                                                 Ng, int(col_idx), _ptr(grid), G, int(bool(normalize)),
@@ -572,6 +573,22 @@ def sample_uniform(n: int, dim: int, B: float, seed: int, device=None) -> torch.
         N.check(N.lib().pzb_sample_uniform(_ptr(out), n, dim, float(B), int(seed) & (2 ** 64 - 1),
                                            _stream(device)))
     return out
+
+
+PINNED_RESULT_LIMIT = 256 << 20
+
+
+def host_result(shape) -> torch.Tensor:
+    """A fresh float32 CPU tensor for the results of a host-buffer call.  Up to 256 MB it is page-locked: torch's
+    caching host allocator hands the same block back on the next call of the same size, and the D2H copies land in
+    it directly.  Larger results are ordinary pageable memory -- page-locking gigabytes for one call costs more than
+    the evaluation, and the library stages pageable destinations through its own page-locked ring at the same speed."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if 4 * n <= PINNED_RESULT_LIMIT and torch.cuda.is_available():
+        return torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
+    return torch.empty(tuple(shape), dtype=torch.float32)
 
 
 def pinned_empty(shape, dtype=torch.float32) -> torch.Tensor:

@@ -706,8 +706,10 @@ def test_host_pipeline_pageable_results_are_staged_and_identical():
     X = F.galaxy_rows(6000, seed=3)
     grid = np.linspace(0.0, 2.3, 1000).astype(np.float32)                  # 6000 x 1000 floats = 24 MB > 8 MB
     rest = np.ascontiguousarray(X[:, 1:])
-    pageable = plan.posterior_host(rest, 0, grid)
+    pageable = plan.posterior_host(rest, 0, grid, out=torch.empty((6000, 1000)))
     assert not pageable.is_pinned()
+    from pzflow_b200.plan import host_result
+    assert host_result((6000, 1000)).is_pinned() and not host_result((70_000, 1000)).is_pinned()   # 24 MB / 280 MB
     pinned = plan.posterior_host(rest, 0, grid, out=pinned_empty((6000, 1000)))
     dev = plan.posterior(torch.from_numpy(rest), 0, torch.from_numpy(grid))
     assert _same_bits(pageable, pinned) and _same_bits(pageable, dev)
