@@ -541,12 +541,10 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
   plan->num_sms = prop.multiProcessorCount;
 
   std::vector<unsigned char> hblob(total > 0 ? total : 256, 0);
-  if (total > 0 || true) {
-    ce = cudaMalloc(&plan->d_weights, hblob.size());
-    if (ce != cudaSuccess) {
-      delete plan;
-      return cuda_fail(ce, "cudaMalloc(weights)");
-    }
+  ce = cudaMalloc(&plan->d_weights, hblob.size());  // (never empty: a chain without weights still gets 256 bytes)
+  if (ce != cudaSuccess) {
+    delete plan;
+    return cuda_fail(ce, "cudaMalloc(weights)");
   }
   plan->weight_bytes = hblob.size();
   size_t off = 0;
