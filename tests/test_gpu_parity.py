@@ -252,6 +252,13 @@ def test_example_flow_through_flow_api(tmp_path):
     pm = flow.posterior(flagged, column="redshift", grid=grid, marg_rules=rules)
     assert pm.shape == (6, 5) and np.isfinite(pm).all()
     np.testing.assert_allclose(pm[[0, 2, 3, 5]], pdfs[[0, 2, 3, 5]], rtol=1e-5, atol=1e-7)
+    # a flagged row: un-normalised pdfs summed over its marginalisation grid, then normalised (flow.py:617-664, 732-737)
+    for r in (1, 4):
+        expanded = pd.DataFrame(np.repeat(flagged.iloc[[r]].to_numpy(), 9, axis=0), columns=flagged.columns)
+        expanded["u"] = np.linspace(26, 31, 9)
+        summed = flow.posterior(expanded, column="redshift", grid=grid, normalize=False).astype(np.float64).sum(axis=0)
+        want_row = summed / np.trapezoid(summed, np.asarray(grid, np.float64))
+        np.testing.assert_allclose(pm[r], want_row, rtol=1e-4, atol=1e-7)
 
 
 # --------------------------------------------------------------------------- #
