@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -11,6 +12,7 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <sched.h>
 
 #include "../../include/pzflow_b200.h"
 #include "pzb_common.cuh"
@@ -1143,6 +1145,19 @@ static cudaError_t pipe_reserve(void** p, size_t* cap, size_t want, int n) {
   return cudaSuccess;
 }
 
+// Host threads for the casts / copies of one pipeline: the CPUs this process may run on (its affinity mask, which
+// sharding.bind_to_gpu_numa_node narrows), shared fairly when torchrun runs several ranks on the box, at most 16.
+static int host_thread_count() {
+  int n = (int)std::thread::hardware_concurrency();
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+  if (const char* lws = getenv("LOCAL_WORLD_SIZE")) {
+    const int w = atoi(lws);
+    if (w > 1) n /= w;
+  }
+  return std::max(1, std::min(16, n));
+}
+
 // memcpy on all host cores (first-touch page faults of a fresh destination included)
 static void parallel_copy(void* dst, const void* src, size_t bytes, int threads) {
   const size_t blk = 1u << 20;
@@ -1184,7 +1199,7 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
     hp.ready = true;
   }
   const int C = plan->host.C;
-  const int host_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const int host_threads = host_thread_count();
   const int rows_per_unit = (job.mode == MODE_POSTERIOR) ? job.G : 1;
   // chunk: ~1.2 M chain rows (8 waves of 148 CTAs x 1024 rows), staging buffers <= 64 MB each
   int64_t chunk = (int64_t)plan->num_sms * 1024 * 8 / rows_per_unit;
