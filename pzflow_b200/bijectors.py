@@ -15,14 +15,13 @@ UniformDequantizer (training-time noise).
 """
 from __future__ import annotations
 
-from collections import OrderedDict
 from functools import update_wrapper
 from typing import Callable, Sequence, Tuple, Union
 
 import numpy as np
 import torch
 
-from .plan import Plan, params_fingerprint
+from .plan import Plan, PlanCache
 
 Pytree = Union[tuple, list]
 Bijector_Info = Tuple[str, tuple]
@@ -96,20 +95,11 @@ class _FusedFunctions:
     def __init__(self, info: Bijector_Info, input_dim: int) -> None:
         self.info = info
         self.input_dim = input_dim
-        self._plans: "OrderedDict[tuple, Plan]" = OrderedDict()
+        self._plans = PlanCache(self._MAX_PLANS)
 
     def plan(self, params: Pytree) -> Plan:
-        key = (params_fingerprint(params), torch.cuda.current_device() if torch.cuda.is_available() else -1)
-        p = self._plans.get(key)
-        if p is None:
-            p = Plan(self.info, params, self.input_dim)
-            self._plans[key] = p
-            self._keep = params  # keep the leaves alive so ids stay unique
-            while len(self._plans) > self._MAX_PLANS:
-                self._plans.popitem(last=False)
-        else:
-            self._plans.move_to_end(key)
-        return p
+        device = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        return self._plans.get(params, device, lambda: Plan(self.info, params, self.input_dim))
 
     @staticmethod
     def _out(t: torch.Tensor, like):

@@ -426,13 +426,9 @@ cudaError_t launch_simt(const PlanDev* d_plan, const LaunchArgs& args, int D, in
                         int act_rows, bool pingpong, int num_sms, cudaStream_t stream) {
   const SmemLayout lay = make_layout(D, C, Lmax, act_rows, pingpong);
   const size_t smem = (size_t)lay.total * sizeof(float);
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(nsf_chain_simt_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  // function attributes are per DEVICE (one host thread may drive plans on several): set on every launch, like launch_tc
+  cudaError_t e = cudaFuncSetAttribute(nsf_chain_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nsf_chain_simt_kernel, NTHREADS, smem);
   if (occ < 1) occ = 1;

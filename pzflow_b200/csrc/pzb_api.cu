@@ -744,6 +744,19 @@ int pzb_inverse(const pzb_plan* plan, const float* U, const float* cond, int64_t
 
 // ---- small memory-bound helper kernels ----
 
+// SM count of the CURRENT device (the helper kernels below are not tied to a plan), cached per device
+static int current_num_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -766,9 +779,9 @@ __device__ __forceinline__ float nan_to_num0(float v) {
 // pdfs / trapezoid(pdfs, grid) per row, then nan_to_num(nan=0)  (pzflow/flow.py:732-737).
 // Optionally averages n_flows stacked inputs first (pzflow/flowEnsemble.py:346-351).
 __global__ void __launch_bounds__(256)
-normalize_pdfs_kernel(const float* __restrict__ in, int n_flows, long long Ng, int G,
+normalize_pdfs_kernel(const float* in, int n_flows, long long Ng, int G,
                       const float* __restrict__ grid, int normalize, int nan_to_zero,
-                      float* __restrict__ out) {
+                      float* out) {  // in == out for the in-place form: neither may be __restrict__
   __shared__ float red[8];
   for (long long g = blockIdx.x; g < Ng; g += gridDim.x) {
     float part = 0.0f;
@@ -849,7 +862,8 @@ int pzb_normalize_pdfs(float* pdfs, int64_t Ng, int32_t G, const float* grid, in
   if (Ng == 0) return PZB_OK;
   if (!pdfs || !grid) return fail(PZB_ERR_INVALID, "normalize_pdfs: NULL buffer");
   if (!normalize && !nan_to_zero) return PZB_OK;
-  const unsigned blocks = (unsigned)(Ng < 148 * 64 ? Ng : 148 * 64);
+  const long long cap = (long long)current_num_sms() * 64;
+  const unsigned blocks = (unsigned)(Ng < cap ? Ng : cap);
   normalize_pdfs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pdfs, 1, Ng, G, grid, normalize,
                                                                   nan_to_zero, pdfs);
   cudaError_t ce = cudaGetLastError();
@@ -885,7 +899,7 @@ int pzb_ensemble_logmeanexp(const float* lp, int32_t n_flows, int64_t N, float* 
   if (N == 0) return PZB_OK;
   if (!lp || !out) return fail(PZB_ERR_INVALID, "ensemble_logmeanexp: NULL buffer");
   long long blocks = (N + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks > (long long)current_num_sms() * 32) blocks = (long long)current_num_sms() * 32;
   logmeanexp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(lp, n_flows, N, out);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return cuda_fail(ce, "logmeanexp launch");
@@ -898,7 +912,8 @@ int pzb_ensemble_posterior_mean(const float* pdfs, int32_t n_flows, int64_t Ng, 
   if (n_flows < 1 || Ng < 0 || G < 1) return fail(PZB_ERR_INVALID, "ensemble_posterior_mean: bad shape");
   if (Ng == 0) return PZB_OK;
   if (!pdfs || !out || !grid) return fail(PZB_ERR_INVALID, "ensemble_posterior_mean: NULL buffer");
-  const unsigned blocks = (unsigned)(Ng < 148 * 64 ? Ng : 148 * 64);
+  const long long cap = (long long)current_num_sms() * 64;
+  const unsigned blocks = (unsigned)(Ng < cap ? Ng : cap);
   // n_flows == 1 degenerates to a copy (+ normalisation)
   normalize_pdfs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pdfs, n_flows, Ng, G, grid, normalize, 0, out);
   cudaError_t ce = cudaGetLastError();
@@ -913,7 +928,7 @@ int pzb_sample_uniform(float* U, int64_t N, int32_t D, float B, uint64_t seed, v
   if (!U) return fail(PZB_ERR_INVALID, "sample_uniform: NULL buffer");
   const long long n = N * (long long)D;
   long long blocks = ((n + 3) / 4 + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks > (long long)current_num_sms() * 32) blocks = (long long)current_num_sms() * 32;
   sample_uniform_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(U, n, B, seed);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return cuda_fail(ce, "sample_uniform launch");
@@ -960,7 +975,7 @@ error_eps_kernel(float* __restrict__ eps, long long n, int W, uint32_t stream_id
 
 static unsigned grid_for(long long n) {
   long long b = (n + 255) / 256;
-  if (b > 148 * 32) b = 148 * 32;
+  if (b > (long long)current_num_sms() * 32) b = (long long)current_num_sms() * 32;
   if (b < 1) b = 1;
   return (unsigned)b;
 }

@@ -13,8 +13,6 @@ drawn inside the kernel from a counter-based stream.  ``train`` (SURVEY.md §8f-
 """
 from __future__ import annotations
 
-import sys
-import types
 from typing import Any, Callable, Sequence, Tuple
 
 import dill as pickle
@@ -24,27 +22,45 @@ import torch
 
 from . import distributions
 from .bijectors import Bijector_Info, Chain, InitFunction, Pytree, RollingSplineCoupling, ShiftBounds
-from .plan import Plan, params_fingerprint
+from .plan import Plan, PlanCache
 from .utils import build_bijector_from_info, gaussian_error_model
 
 
+def _numpy_from_jax_pickle(fun, args, arr_state, aval_state=None):
+    """What jax._src.array._reconstruct_array does before its device_put: rebuild the NumPy array that a
+    jax Array's __reduce__ wrapped (jax >= 0.4 pickles an Array as (_reconstruct_array, (np_reduce...)))."""
+    value = fun(*args)
+    value.__setstate__(arr_state)
+    return value
+
+
+class _JaxFreeUnpickler(pickle.Unpickler):
+    """dill Unpickler for reference ``.pzflow.pkl`` files in a jax-less environment: jax Arrays come back as NumPy
+    arrays and pzflow.utils globals (the save dict stores gaussian_error_model by reference, pzflow/flow.py:238)
+    resolve to this package's equivalents."""
+
+    def find_class(self, module, name):
+        if module.split(".")[0] == "jax" and name == "_reconstruct_array":
+            return _numpy_from_jax_pickle
+        if module in ("pzflow.utils", "pzflow"):
+            from . import utils as _utils
+            if hasattr(_utils, name):
+                return getattr(_utils, name)
+        return super().find_class(module, name)
+
+
 def _load_pickle(file: str) -> dict:
-    """dill-load a reference ``.pzflow.pkl`` without jax: the only by-reference global
-    in the save dict is pzflow.utils.gaussian_error_model (pzflow/flow.py:238)."""
-    injected = []
-    if "pzflow" not in sys.modules:
-        pkg = types.ModuleType("pzflow")
-        sub = types.ModuleType("pzflow.utils")
-        sub.gaussian_error_model = gaussian_error_model
-        pkg.utils = sub
-        sys.modules["pzflow"], sys.modules["pzflow.utils"] = pkg, sub
-        injected = ["pzflow", "pzflow.utils"]
-    try:
-        with open(file, "rb") as handle:
-            return pickle.load(handle)
-    finally:
-        for k in injected:
-            sys.modules.pop(k, None)
+    """dill-load a reference ``.pzflow.pkl`` without jax or pzflow installed."""
+    with open(file, "rb") as handle:
+        return _JaxFreeUnpickler(handle).load()
+
+
+def _is_gaussian_error_model(model) -> bool:
+    """The default error model, whichever package it was imported from (a real pzflow install unpickles its own
+    pzflow.utils.gaussian_error_model, which is not this module's object)."""
+    return model is gaussian_error_model or (
+        getattr(model, "__name__", None) == "gaussian_error_model"
+        and str(getattr(model, "__module__", "")).split(".")[-1] == "utils")
 
 
 def _pinned_f32(a: np.ndarray) -> torch.Tensor:
@@ -92,7 +108,7 @@ class Flow:
         if file is not None and _dictionary is not None:
             raise ValueError("Only provide file or _dictionary, not both.")
 
-        self._plan_cache = {}
+        self._plan_cache = PlanCache(1)
         if file is not None or _dictionary is not None:
             save_dict = self._save_dict()
             save_dict.update(_load_pickle(file) if file is not None else _dictionary)
@@ -161,7 +177,7 @@ class Flow:
         bijector_params, self._forward, self._inverse = init_fun(seed, self._input_dim)
         bijector_params = params if params is not None else bijector_params
         self._params = (self.latent._params, bijector_params)
-        self._plan_cache = {}
+        self._plan_cache = PlanCache(1)
 
     def _set_default_bijector(self, inputs: pd.DataFrame, seed: int = 0) -> None:
         """ShiftBounds -> RollingSplineCoupling (pzflow/flow.py:296-322)."""
@@ -177,15 +193,10 @@ class Flow:
     def _plan(self, params: Pytree = None) -> Plan:
         """The fused device plan of (bijector, latent) for ``params`` on the current device."""
         params = self._params if params is None else params
-        key = (params_fingerprint(params[1]), params_fingerprint(params[0]),
-               torch.cuda.current_device() if torch.cuda.is_available() else -1)
-        plan = self._plan_cache.get(key)
-        if plan is None:
-            self._plan_cache.clear()
-            plan = Plan(self._bijector_info, params[1], self._input_dim, self._latent_info,
-                        latent_params=params[0])
-            self._plan_cache[key] = plan
-        return plan
+        device = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        return self._plan_cache.get(
+            (params[0], params[1]), device,
+            lambda: Plan(self._bijector_info, params[1], self._input_dim, self._latent_info, latent_params=params[0]))
 
     def _get_conditions(self, inputs: pd.DataFrame):
         """Standard-scaled conditions, or None for an unconditional flow -- the reference's
@@ -246,7 +257,7 @@ class Flow:
             model = self.condition_error_model
         else:
             raise ValueError("type must be `data` or `conditions`.")
-        if model is not None and model is not gaussian_error_model:
+        if model is not None and not _is_gaussian_error_model(model):
             raise NotImplementedError("only the default gaussian_error_model is fused into the B200 kernels; "
                                       "custom error models need the reference's JAX path")
         X = inputs[columns].to_numpy().astype(np.float32).reshape(len(inputs), len(columns))

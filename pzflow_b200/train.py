@@ -287,10 +287,42 @@ class TorchChain:
             return lp.sum(dim=1)
         raise NotImplementedError(f"training: latent {name!r} is outside the B200 path")
 
+    def _latent_any(self, info, params, u):
+        """Tdist (distributions.py:330-358, cov = I) and Joint (528-541: the sum over its sub-distributions, each on
+        its own consecutive columns) on top of the closed forms of ``_latent``."""
+        name, args = info
+        if name == "Joint":
+            subs = args[1]
+            plist = params if params is not None else [None] * len(subs)
+            total, start = None, 0
+            for sub, p in zip(subs, plist):
+                sub = tuple(sub)
+                n = int(sub[1][0])
+                lp = self._latent_any(sub, p, u[:, start:start + n])
+                total = lp if total is None else total + lp
+                start += n
+            return total
+        if name == "Tdist":
+            n = u.shape[1]
+            log_nu = params if params is not None else math.log(30.0)
+            nu = torch.exp(torch.as_tensor(np.asarray(log_nu, dtype=np.float64), dtype=self.dtype, device=self.device)
+                           if not isinstance(log_nu, torch.Tensor) else log_nu).reshape(())
+            t = 0.5 * (nu + n)
+            return (torch.lgamma(t) - torch.lgamma(0.5 * nu) - 0.5 * n * torch.log(nu * math.pi)
+                    - t * torch.log1p((u * u).sum(dim=1) / nu))
+        saved = self.latent_info, self.latent_params
+        try:
+            self.latent_info, self.latent_params = info, params
+            return self._latent(u)
+        finally:
+            self.latent_info, self.latent_params = saved
+
     def log_prob(self, x, cond=None):
         """Flow._log_prob (flow.py:397-407) with gradients."""
         u, ld = self._apply(self.info, self.params, x, cond)
-        return torch.nan_to_num(self._latent(u) + ld, nan=-math.inf, posinf=math.inf, neginf=-math.inf)
+        lat = (self._latent_any(self.latent_info, self.latent_params, u) if self.latent_info[0] in ("Tdist", "Joint")
+               else self._latent(u))
+        return torch.nan_to_num(lat + ld, nan=-math.inf, posinf=math.inf, neginf=-math.inf)
 
 
 # --------------------------------------------------------------------------- #
@@ -436,10 +468,11 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
     def fused_loss(X, C, W):
         """-mean(w * log_prob) through the fused CUDA kernels with the CURRENT parameters."""
         flow._params = chain.numpy_params()
-        flow._plan_cache = {}
+        flow._plan_cache.clear()
         lp = flow._plan().log_prob(torch.as_tensor(X, device=dev), C if C is None else torch.as_tensor(C, device=dev))
         lp = torch.where(lp < -1e30, torch.full_like(lp, -math.inf), lp)   # finfo.min is the zero-probability class
-        return float(-(W * lp).mean().item())
+        # a zero-weight row with zero probability contributes 0, not 0 * -inf = NaN
+        return float(-torch.where(W == 0, torch.zeros_like(lp), W * lp).mean().item())
 
     n = len(inputs)
     W = np.ones(n, np.float32) if train_weight is None else np.asarray(train_weight, np.float32)
@@ -462,7 +495,7 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
     Xm, Xe, Cm, Ce = to_dev(Xm), to_dev(Xe), to_dev(Cm), to_dev(Ce)
     perm_rng = np.random.default_rng(int(batch_seed))
     noise = torch.Generator(device=dev)
-    noise.manual_seed(int(batch_seed))
+    noise.manual_seed(int(batch_seed) + rank)   # every rank draws its own eps for its own share of the batch
     best_loss, best_vals, stall = math.inf, chain.numpy_params(), 0
     use_graph = isinstance(opt, NativeAdam) and os.environ.get("PZB_TRAIN_GRAPH", "1") != "0"
     loop = range(epochs)
@@ -506,5 +539,5 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
             print(f"Training stopping after epoch {epoch + 1}", "because training loss diverged.")
             break
     flow._params = best_vals if best_params else chain.numpy_params()            # flow.py:1151-1154
-    flow._plan_cache = {}
+    flow._plan_cache.clear()
     return losses if val_set is None else [losses, val_losses]

@@ -173,6 +173,78 @@ def test_loads_reference_style_pickle(tmp_path):
     assert len(flow._params[1][1]) == 14
 
 
+def test_loads_pickle_written_by_current_jax(tmp_path):
+    """jax >= 0.4 pickles an Array as (jax._src.array._reconstruct_array, (np reconstructor, args, state, aval
+    state)): the loader must hand back NumPy arrays without importing jax, and must recognise a pzflow-owned
+    gaussian_error_model as the default error model."""
+    import dill
+    import types
+    from pzflow_b200 import flow as flow_mod
+    ex = F.example_flow()
+    jax_pkg, jax_src, jax_arr = types.ModuleType("jax"), types.ModuleType("jax._src"), types.ModuleType("jax._src.array")
+
+    def _reconstruct_array(fun, args, arr_state, aval_state):
+        raise AssertionError("the jax reconstructor must not be called")
+    _reconstruct_array.__module__, _reconstruct_array.__qualname__ = "jax._src.array", "_reconstruct_array"
+    jax_arr._reconstruct_array = _reconstruct_array
+    jax_pkg._src, jax_src.array = jax_src, jax_arr
+
+    class FakeJaxArray:
+        def __init__(self, a):
+            self.a = np.asarray(a)
+
+        def __reduce__(self):
+            fun, args, state = self.a.__reduce__()
+            return _reconstruct_array, (fun, args, state, {"weak_type": False})
+
+    def wrap(t):
+        if isinstance(t, (list, tuple)):
+            return type(t)(wrap(q) for q in t)
+        return FakeJaxArray(t) if isinstance(t, np.ndarray) else t
+
+    pz_pkg, pz_utils = types.ModuleType("pzflow"), types.ModuleType("pzflow.utils")
+
+    def gaussian_error_model(key, X, Xerr, nsamples):
+        return None
+    gaussian_error_model.__module__, gaussian_error_model.__qualname__ = "pzflow.utils", "gaussian_error_model"
+    pz_utils.gaussian_error_model = gaussian_error_model
+    pz_pkg.utils = pz_utils
+    mods = {"jax": jax_pkg, "jax._src": jax_src, "jax._src.array": jax_arr, "pzflow": pz_pkg, "pzflow.utils": pz_utils}
+    sys.modules.update(mods)
+    try:
+        d = {"class": "Flow", "data_columns": F.GALAXY_COLUMNS, "conditional_columns": ("c0",),
+             "condition_means": FakeJaxArray(np.float32([1.5])), "condition_stds": FakeJaxArray(np.float32([2.0])),
+             "data_error_model": gaussian_error_model, "condition_error_model": gaussian_error_model,
+             "autoscale_conditions": True, "info": None, "latent_info": ex["latent_info"],
+             "bijector_info": ex["bijector_info"], "params": wrap(ex["params"])}
+        path = str(tmp_path / "jax.pkl")
+        with open(path, "wb") as fh:
+            dill.dump(d, fh)
+    finally:
+        for k in mods:
+            sys.modules.pop(k)
+    assert b"jax._src.array" in open(path, "rb").read()
+    flow = Flow(file=path)
+    W = flow._params[1][1][0][0][0]
+    assert type(W) is np.ndarray and np.array_equal(W, ex["params"][1][1][0][0][0])
+    assert type(flow._condition_means) is np.ndarray and float(flow._condition_stds[0]) == 2.0
+    # the unpickled model is this package's gaussian_error_model; a foreign pzflow.utils one is accepted by name
+    assert flow_mod._is_gaussian_error_model(flow.data_error_model)
+    assert flow_mod._is_gaussian_error_model(gaussian_error_model)
+    assert not flow_mod._is_gaussian_error_model(lambda *a: None)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/pzflow/example_files/example-flow.pzflow.pkl"),
+                    reason="the reference tree only exists in the build container")
+def test_loads_the_shipped_reference_checkpoint():
+    """pzflow/examples.py:105-113 loads this file with Flow(file=...): the same call here, no jax."""
+    flow = Flow(file="/root/reference/pzflow/example_files/example-flow.pzflow.pkl")
+    ex = F.example_flow()
+    assert tuple(flow.data_columns) == tuple(F.GALAXY_COLUMNS) and flow._latent_info[0] == "Uniform"
+    got, want = P._param_leaves(flow._params[1], []), P._param_leaves(ex["params"][1], [])
+    assert len(got) == len(want) and all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(got, want))
+
+
 def test_shard_rows_partition():
     for n in (0, 1, 7, 1000, 10_000_019):
         for world in (1, 2, 3, 8):
@@ -355,3 +427,50 @@ def test_numa_binding_helper_is_inert_without_topology():
     before = os.sched_getaffinity(0)
     assert sharding.bind_to_gpu_numa_node(0) is None      # no CUDA device here
     assert os.sched_getaffinity(0) == before
+
+
+def test_plan_cache_holds_its_params_and_sees_in_place_edits():
+    """ids of freed arrays get reused and in-place edits keep the id -- neither may return a stale plan."""
+    built = []
+
+    def builder(tag):
+        def build():
+            built.append(tag)
+            return tag
+        return build
+
+    cache = P.PlanCache(max_plans=2)
+    for i in range(20):  # fresh trees in a loop: CPython reuses the freed arrays' ids
+        params = [(), [(np.full((4, 4), i, np.float32), np.zeros(4, np.float32)), ()]]
+        assert cache.get(params, 0, builder(i)) == i
+    assert built == list(range(20)) and len(cache) == 2
+    W = np.ones((8, 8), np.float32)
+    params = [(W, np.zeros(8, np.float32))]
+    assert cache.get(params, 0, builder("a")) == "a"
+    assert cache.get(params, 0, builder("never")) == "a"          # same leaves, same bytes: hit
+    assert cache.get([(W, params[0][1])], 0, builder("never")) == "a"  # a new container around the same leaves: hit
+    assert cache.get(params, 1, builder("dev1")) == "dev1"        # another device: its own plan
+    W *= 2.0
+    assert cache.get(params, 0, builder("b")) == "b"              # edited in place: rebuilt
+    W[3, 5] = 7.0
+    assert cache.get(params, 0, builder("c")) == "c"
+    assert cache.get(params, 0, builder("never")) == "c"
+    assert "never" not in built
+
+
+def test_training_latents_cover_tdist_and_joint():
+    """Flow.train must be able to fit the latents Flow.log_prob evaluates (Tdist, Joint)."""
+    import torch
+    from pzflow_b200.train import TorchChain
+    rng = np.random.default_rng(5)
+    u = rng.uniform(-3, 3, size=(64, 5))
+    info = ("Joint", ("Joint info", [("Uniform", (2, 5.0)), ("Tdist", (2,)), ("Normal", (1,))]))
+    lat_params = [(), np.float64(np.log(12.0)), ()]
+    chain = TorchChain(("Reverse", ()), (), info, lat_params, 5, torch.device("cpu"), dtype=torch.float64,
+                       native_spline=False)
+    got = chain._latent_any(info, lat_params, torch.as_tensor(u)).numpy()
+    want = O.any_latent_log_prob(info, lat_params, u)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+    t_info = ("Tdist", (5,))
+    got = chain._latent_any(t_info, None, torch.as_tensor(u)).numpy()      # default nu = 30
+    assert np.allclose(got, O.any_latent_log_prob(t_info, np.float64(np.log(30.0)), u), rtol=1e-12, atol=1e-12)
