@@ -172,6 +172,202 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------
+# The other named shapes of BASELINE.json (configs 1, 3, 4, 5; synthetic inputs as SURVEY.md section 8d states them).
+# Each returns {"value", "unit", "e2e": {...}, "roofline": {...}, sizes}; C3 and C4 are STRONG-scaled by default
+# (BASELINE's totals -- 1e6 galaxies, 1e8 rows -- split over the ranks), `--scaling weak` gives every rank the
+# single-GPU size instead.
+# ---------------------------------------------------------------------------------------------
+C3_GALAXIES, C3_GRID = 1_000_000, 1000
+C4_ROWS, C4_ROWS_WEAK, C4_FLOWS = 100_000_000, 10_000_000, 4
+C5_ROWS, C1_ROWS = 1_000_000, 100_000
+GALAXY_COLUMNS = ("redshift", "u", "g", "r", "i", "z", "y")
+
+
+def timed_device(fn, reps, barrier, max_ranks, warm=1):
+    """ms per call, CUDA events on torch's current stream (the stream every Plan call launches on), max over ranks."""
+    import torch
+    for _ in range(warm):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    barrier()
+    return max_ranks(e0.elapsed_time(e1)) / reps
+
+
+def timed_host(fn, reps, barrier, max_ranks, warm=1):
+    """ms per blocking host-buffer call (host arrays in, host result out), wall clock, max over ranks."""
+    for _ in range(warm):
+        fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    barrier()
+    return max_ranks((time.perf_counter() - t0) * 1e3) / reps
+
+
+def pipe_roofline(engine, flops, ms, peaks):
+    """Algorithmic conditioner FLOPs of ONE GPU's share over its time, against the pipe the engine runs on."""
+    achieved = flops / (ms * 1e-3) / 1e12
+    if engine in ("tc", "wide"):
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "executed_frac": 3.0 * achieved / peak, "engine": engine,
+                "note": "algorithmic fp32 FLOPs over the measured sustained cuBLAS bf16 rate; the fp16x2 split "
+                        "executes 3 MMAs per fp32 MAC (executed_frac)"}
+    peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    return {"bound": "fp32_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "engine": engine, "note": "nominal 148 SM x 128 FFMA/clk x 2 x clocks.max.sm"}
+
+
+def share(total, rank, world):
+    base, rem = divmod(total, world)
+    return base + (1 if rank < rem else 0)
+
+
+def bench_c3(flow, plan, X, ctx):
+    """Config 3: Flow.posterior over a 1000-point redshift grid for 1e6 galaxies (pzflow/flow.py:666-738)."""
+    import torch
+    dev, rank, world = ctx["dev"], ctx["rank"], ctx["world"]
+    ng = share(C3_GALAXIES, rank, world) if ctx["strong"] else C3_GALAXIES
+    total = C3_GALAXIES if ctx["strong"] else C3_GALAXIES * world
+    rest = X[:ng, 1:].contiguous()
+    grid = torch.linspace(0.0, 2.3, C3_GRID, device=dev)
+    pdfs = torch.empty((ng, C3_GRID), dtype=torch.float32, device=dev)
+    ms = timed_device(lambda: plan.posterior(rest, 0, grid, out=pdfs), 2, ctx["barrier"], ctx["max_ranks"])
+    del pdfs
+    torch.cuda.empty_cache()
+    # end to end: photometry in host memory, pdfs [Ng, 1000] (4 GB at Ng = 1e6) into an ordinary PAGEABLE array
+    rest_h = rest.cpu()
+    grid_h = grid.cpu()
+    out_h = torch.empty((ng, C3_GRID), dtype=torch.float32)
+    e2e_ms = timed_host(lambda: plan.posterior_host(rest_h, 0, grid_h, out=out_h), 2, ctx["barrier"], ctx["max_ranks"])
+    ok = bool(torch.isfinite(out_h[:: max(1, ng // 1000)]).all())
+    del out_h
+    return {"workload": "Flow.posterior, 7-D galaxy flow, redshift grid of 1000 points (BASELINE config 3)",
+            "value": total / (ms * 1e-3), "unit": "galaxies/s", "ms": ms, "galaxies_total": total,
+            "galaxies_this_rank": ng, "grid_points": C3_GRID, "scaling": "strong" if ctx["strong"] else "weak",
+            "rows_per_s_equiv": total * C3_GRID / (ms * 1e-3),
+            "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "galaxies/s", "ms": e2e_ms,
+                    "h2d_bytes": int(ng * 6 * 4), "d2h_bytes": int(ng * C3_GRID * 4),
+                    "result": "pageable host array through pzb_posterior_host", "finite": ok},
+            "roofline": pipe_roofline(plan.engine, plan.flops_per_row * ng * C3_GRID, ms, ctx["peaks"]),
+            "algorithmic_bytes_per_galaxy": 4 * 6 + 4 * C3_GRID}
+
+
+def bench_c4(flow, ctx):
+    """Config 4: FlowEnsemble of 4 conditional 7-D flows (conditional_columns ra, dec), log_prob on 1e8 rows
+    (pzflow/flowEnsemble.py:189-243)."""
+    import pandas as pd
+    import torch
+    from pzflow_b200 import FlowEnsemble
+    from pzflow_b200.bijectors import Chain, RollingSplineCoupling, ShiftBounds
+    from pzflow_b200.plan import ensemble_logmeanexp
+    dev, rank, world = ctx["dev"], ctx["rank"], ctx["world"]
+    n = share(C4_ROWS, rank, world) if ctx["strong"] else C4_ROWS_WEAK
+    total = C4_ROWS if ctx["strong"] else C4_ROWS_WEAK * world
+    mins = np.asarray(flow._bijector_info[1][0][1][0], np.float32)
+    maxs = np.asarray(flow._bijector_info[1][0][1][1], np.float32)
+    ens = FlowEnsemble(data_columns=GALAXY_COLUMNS, conditional_columns=("ra", "dec"), N=C4_FLOWS,
+                       bijector=Chain(ShiftBounds(mins, maxs, 4.0), RollingSplineCoupling(7, n_conditions=2)))
+    flows = list(ens._ensemble.values())
+    plans = [f._plan() for f in flows]
+    gen = ctx["gen"]
+    Xc = torch.rand((n, 7), generator=gen, device=dev)
+    Xc.mul_(torch.as_tensor(maxs - mins, device=dev)).add_(torch.as_tensor(mins, device=dev))
+    Cc = torch.randn((n, 2), generator=gen, device=dev)
+    lps = torch.empty((C4_FLOWS, n), dtype=torch.float32, device=dev)
+
+    def step():
+        for f, p in enumerate(plans):
+            p.log_prob(Xc, Cc, out=lps[f])
+        return ensemble_logmeanexp(lps)
+    ms = timed_device(step, 2, ctx["barrier"], ctx["max_ranks"])
+    del lps
+    # end to end through the public API: FlowEnsemble.log_prob(DataFrame of float32 columns) -> NumPy array
+    frame = pd.DataFrame({c: Xc[:, j].cpu().numpy() for j, c in enumerate(GALAXY_COLUMNS)}, copy=False)
+    frame["ra"], frame["dec"] = Cc[:, 0].cpu().numpy(), Cc[:, 1].cpu().numpy()
+    del Xc, Cc
+    torch.cuda.empty_cache()
+    e2e_ms = timed_host(lambda: ens.log_prob(frame), 2, ctx["barrier"], ctx["max_ranks"])
+    flops = sum(p.flops_per_row for p in plans) * n
+    return {"workload": "FlowEnsemble(4) of conditional 7-D flows, log_prob (BASELINE config 4)",
+            "value": total / (ms * 1e-3), "unit": "rows/s", "ms": ms, "rows_total": total, "rows_this_rank": n,
+            "flows": C4_FLOWS, "flow_rows_per_s": C4_FLOWS * total / (ms * 1e-3),
+            "scaling": "strong" if ctx["strong"] else "weak",
+            "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "rows/s", "ms": e2e_ms, "h2d_bytes": int(n * 9 * 4),
+                    "d2h_bytes": int(n * 4), "call": "FlowEnsemble.log_prob(DataFrame[float32 x 9])"},
+            "roofline": pipe_roofline(plans[0].engine, flops, ms, ctx["peaks"]),
+            "params": "synthetic (package initialiser, seeds 0-3)"}
+
+
+def bench_c5(ctx, engine_arg):
+    """Config 5: 32-D RollingSplineCoupling, K = 32, hidden 256, log_prob + inverse on 1e6 rows."""
+    import torch
+    from pzflow_b200 import Flow
+    from pzflow_b200.bijectors import Chain, RollingSplineCoupling, ShiftBounds
+    dev, rank, world = ctx["dev"], ctx["rank"], ctx["world"]
+    n = C5_ROWS
+    cols = tuple(f"x{j}" for j in range(32))
+    f5 = Flow(data_columns=cols, bijector=Chain(ShiftBounds(-1.0, 1.0, 4.0),
+                                                RollingSplineCoupling(nlayers=32, K=32, hidden_dim=256)))
+    plan = f5._plan()
+    if engine_arg == "simt":
+        plan.set_engine("simt")
+    X5 = torch.rand((n, 32), generator=ctx["gen"], device=dev) * 2.0 - 1.0
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    ms = timed_device(lambda: plan.log_prob(X5, out=out), 2, ctx["barrier"], ctx["max_ranks"])
+    u5 = plan.forward(X5)[0]
+    inv_ms = timed_device(lambda: plan.inverse(u5, want_log_det=False), 2, ctx["barrier"], ctx["max_ranks"])
+    back = plan.inverse(u5, want_log_det=False)[0]
+    round_trip = float((back - X5).abs().median().item())
+    X5_h = X5.cpu().pin_memory()
+    del X5, u5, back
+    e2e_ms = timed_host(lambda: plan.log_prob_host(X5_h), 2, ctx["barrier"], ctx["max_ranks"])
+    return {"workload": "32-D RollingSplineCoupling(32 layers, K=32, hidden 256) log_prob + inverse, 1e6 rows per GPU "
+                        "(BASELINE config 5)",
+            "value": n * world / (ms * 1e-3), "unit": "rows/s", "ms": ms, "rows_per_gpu": n, "scaling": "weak",
+            "inverse": {"value": n * world / (inv_ms * 1e-3), "unit": "rows/s", "ms": inv_ms,
+                        "round_trip_median_abs_err": round_trip},
+            "e2e": {"value": n * world / (e2e_ms * 1e-3), "unit": "rows/s", "ms": e2e_ms, "h2d_bytes": int(n * 32 * 4),
+                    "d2h_bytes": int(n * 4)},
+            "roofline": pipe_roofline(plan.engine, plan.flops_per_row * n, ms, ctx["peaks"]),
+            "inverse_roofline": pipe_roofline(plan.engine, plan.flops_per_row * n, inv_ms, ctx["peaks"]),
+            "flops_per_row": plan.flops_per_row, "params": "synthetic (package initialiser, seed 0)"}
+
+
+def bench_c1(ctx):
+    """Config 1: the default 2-D flow (two-moons shape: ShiftBounds + RollingSplineCoupling(2), CentBeta13 latent),
+    log_prob of 100k rows."""
+    import pandas as pd
+    import torch
+    from pzflow_b200 import Flow
+    from pzflow_b200.bijectors import Chain, RollingSplineCoupling, ShiftBounds
+    dev, world = ctx["dev"], ctx["world"]
+    n = C1_ROWS
+    mins, maxs = np.float32([-1.5, -1.0]), np.float32([2.5, 1.5])
+    f1 = Flow(data_columns=("x", "y"), bijector=Chain(ShiftBounds(mins, maxs, 4.0), RollingSplineCoupling(2)))
+    plan = f1._plan()
+    X1 = torch.rand((n, 2), generator=ctx["gen"], device=dev)
+    X1.mul_(torch.as_tensor(maxs - mins, device=dev)).add_(torch.as_tensor(mins, device=dev))
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    ms = timed_device(lambda: plan.log_prob(X1, out=out), 50, ctx["barrier"], ctx["max_ranks"], warm=3)
+    frame = pd.DataFrame({"x": X1[:, 0].double().cpu().numpy(), "y": X1[:, 1].double().cpu().numpy()})
+    e2e_ms = timed_host(lambda: f1.log_prob(frame), 20, ctx["barrier"], ctx["max_ranks"], warm=3)
+    return {"workload": "default 2-D flow (two-moons shape, K=16, CentBeta13 latent) log_prob, 100k rows per GPU "
+                        "(BASELINE config 1)",
+            "value": n * world / (ms * 1e-3), "unit": "rows/s", "ms": ms, "rows_per_gpu": n, "scaling": "weak",
+            "e2e": {"value": n * world / (e2e_ms * 1e-3), "unit": "rows/s", "ms": e2e_ms,
+                    "call": "Flow.log_prob(DataFrame[float64 x 2])", "h2d_bytes": int(n * 2 * 4), "d2h_bytes": int(n * 4)},
+            "roofline": pipe_roofline(plan.engine, plan.flops_per_row * n, ms, ctx["peaks"]),
+            "note": "one launch of 100k rows is 782 row tiles over 148 SMs: launch- and tail-bound, not pipe-bound"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -201,7 +397,8 @@ def run_ours(args, rank, world, local_rank):
     # synthetic in-distribution rows: x = inverse(u), u ~ U(-5,5)^7 -- the flow's own sampling
     # map, run on the device -- plus a 1 % admixture of rows from the ShiftBounds box widened by 20 %
     # (exercises the out-of-bounds paths).  Nothing under oracle/ is touched on this arm.
-    n = args.rows
+    n = share(args.rows, rank, world) if args.scaling == "strong" else args.rows
+    total_rows = args.rows if args.scaling == "strong" else args.rows * world
     gen = torch.Generator(device=dev)
     gen.manual_seed(1000 + rank)
     U = (torch.rand((n, 7), generator=gen, device=dev) * 10.0 - 5.0)
@@ -250,7 +447,7 @@ def run_ours(args, rank, world, local_rank):
     total_ms = max_ranks(ev[0].elapsed_time(ev[-1]))
     kernel_ms = statistics.mean(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
     ms_per_step = total_ms / args.steps
-    value = n * world / (ms_per_step * 1e-3)
+    value = total_rows / (ms_per_step * 1e-3)
 
     # ---- end to end through the Flow-facing API with pinned host buffers ----
     def e2e_step():
@@ -265,53 +462,34 @@ def run_ours(args, rank, world, local_rank):
         e2e_step()
     barrier()
     e2e_ms = max_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    e2e_value = n * world / (e2e_ms * 1e-3)
+    e2e_value = total_rows / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and e2e)
 
-    # ---- secondary: posterior (config-3 geometry) and sample (inverse) ----
-    ng = min(POSTERIOR_GALAXIES, n)
-    rest = X[:ng, 1:].contiguous()
-    grid = torch.linspace(0.0, 2.3, POSTERIOR_GRID, device=dev)
-    pdfs = torch.empty((ng, POSTERIOR_GRID), dtype=torch.float32, device=dev)
-    plan.posterior(rest, 0, grid, out=pdfs)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(2):
-        plan.posterior(rest, 0, grid, out=pdfs)
-    e1.record()
-    barrier()
-    post_ms = max_ranks(e0.elapsed_time(e1)) / 2
-    # the same through the host-buffer call: photometry in pinned host memory, pdfs [Ng, G] back in pinned host memory
-    from pzflow_b200.plan import pinned_empty
-    rest_h = pinned_empty((ng, rest.shape[1]))
-    rest_h.copy_(rest)
-    pdfs_h = pinned_empty((ng, POSTERIOR_GRID))
-    grid_h = grid.cpu()
-    plan.posterior_host(rest_h, 0, grid_h, out=pdfs_h)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(2):
-        plan.posterior_host(rest_h, 0, grid_h, out=pdfs_h)
-    barrier()
-    post_e2e_ms = max_ranks((time.perf_counter() - t0) * 1e3) / 2
-    del pdfs_h
+    # ---- sample (inverse map) on the headline rows ----
     u = flow.latent.sample_device(n, seed=rank)
-    plan.inverse(u, want_log_det=False)
-    barrier()
-    e0.record()
-    for _ in range(2):
-        plan.inverse(u, want_log_det=False)
-    e1.record()
-    barrier()
-    samp_ms = max_ranks(e0.elapsed_time(e1)) / 2
+    samp_ms = timed_device(lambda: plan.inverse(u, want_log_det=False), 2, barrier, max_ranks)
+    del u
+
+    # ---- the other named shapes of BASELINE.json (configs 3, 4, 5, 1), each device-resident and end to end ----
+    peaks = measured_peaks()
+    ctx = dict(dev=dev, rank=rank, world=world, barrier=barrier, max_ranks=max_ranks, peaks=peaks,
+               strong=args.scaling != "weak", gen=gen)
+    named = {}
+    if not args.no_named_shapes:
+        named["c3_posterior"] = bench_c3(flow, plan, X, ctx)
+        del X, out, X_host
+        torch.cuda.empty_cache()
+        named["c4_ensemble"] = bench_c4(flow, ctx)
+        torch.cuda.empty_cache()
+        named["c5_high_dim"] = bench_c5(ctx, args.engine)
+        torch.cuda.empty_cache()
+        named["c1_two_moons"] = bench_c1(ctx)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return None
 
-    peaks = measured_peaks()
     flops_row = plan.flops_per_row
     achieved = flops_row * n / (kernel_ms * 1e-3) / 1e12  # algorithmic conditioner TFLOP/s of one GPU
     if engine == "tc":
@@ -353,7 +531,8 @@ def run_ours(args, rank, world, local_rank):
 
     line = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if args.scaling == "strong" else "weak",
         "vs_baseline": None, "dtype": "f32" if engine == "simt" else "f32 (fp16x2-split tensor-core conditioner)",
         "data": "synthetic",
         "config": {"workload": "7-D galaxy flow log_prob, 10M synthetic rows per GPU (BASELINE config 2)",
@@ -367,14 +546,9 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roof,
         "cpu_baseline": cpu,
         "clocks": clocks,
-        "extra": {
-            "posterior": {"value": ng * world / (post_ms * 1e-3), "unit": "galaxies/s", "grid_points": POSTERIOR_GRID,
-                          "galaxies_per_gpu": ng, "ms": post_ms,
-                          "e2e_value": ng * world / (post_e2e_ms * 1e-3), "e2e_ms": post_e2e_ms,
-                          "e2e_d2h_bytes": int(ng * POSTERIOR_GRID * 4),
-                          "rows_per_s_equiv": ng * POSTERIOR_GRID * world / (post_ms * 1e-3)},
-            "sample": {"value": n * world / (samp_ms * 1e-3), "unit": "rows/s", "ms": samp_ms},
-        },
+        "extra": dict({"sample": {"value": total_rows / (samp_ms * 1e-3), "unit": "rows/s", "ms": samp_ms,
+                                  "workload": "Flow.sample map (inverse chain) on the headline rows, device-resident"}},
+                      **named),
     }
     if world > 1:
         dist.destroy_process_group()
@@ -390,6 +564,10 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-named-shapes", action="store_true", help="skip the config 1/3/4/5 lines under `extra`")
+    ap.add_argument("--scaling", default="default", choices=["default", "weak", "strong"],
+                    help="default: headline weak (10M rows per GPU), configs 3/4 strong (BASELINE totals split over the "
+                         "ranks); weak: every rank gets the single-GPU size; strong: the headline's 10M rows are split too")
     args = ap.parse_args()
     rank, world, local_rank = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

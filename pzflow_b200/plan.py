@@ -475,15 +475,18 @@ class Plan:
         return out
 
     # ---- entry points (all asynchronous on torch's current stream) -------
-    def log_prob(self, X, cond=None, return_bins: bool = False):
+    def log_prob(self, X, cond=None, return_bins: bool = False, out: Optional[torch.Tensor] = None):
         """Flow._log_prob (pzflow/flow.py:397-407).  Device tensors are evaluated in place on torch's
         current stream; HOST arrays (NumPy / CPU tensors) take the pipelined host-buffer path and
-        come back as a CPU tensor."""
+        come back as a CPU tensor.  ``out``: a contiguous float32 device tensor [N] to write into."""
         if not return_bins and not (isinstance(X, torch.Tensor) and X.is_cuda):
-            return self.log_prob_host(X, cond)
+            return self.log_prob_host(X, cond, out=out)
         X = self._rows(X, self.input_dim, "inputs")
         cond = self._cond(cond, X.shape[0])
-        out = torch.empty(X.shape[0], dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty(X.shape[0], dtype=torch.float32, device=self.device)
+        elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == X.shape[0]):
+            raise ValueError("out must be a contiguous float32 device tensor with one element per row")
         bins = (torch.empty((X.shape[0], self.n_spline_dims), dtype=torch.int32, device=self.device)
                 if return_bins else None)
         with torch.cuda.device(self.device):
