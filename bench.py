@@ -492,7 +492,7 @@ def run_ours(args, rank, world, local_rank):
 
     flops_row = plan.flops_per_row
     achieved = flops_row * n / (kernel_ms * 1e-3) / 1e12  # algorithmic conditioner TFLOP/s of one GPU
-    if engine == "tc":
+    if engine in ("tc", "wide"):
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": f"{peaks['_source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json)",
@@ -506,7 +506,7 @@ def run_ours(args, rank, world, local_rank):
         roof = {"bound": "fp32_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": "nominal 148 SM x 128 FFMA/clk x 2 x clocks.max.sm "
                                                 "(the FP32 pipe has no entry in MEASURED_PEAKS.json)"}
-    roof["kernel"] = "nsf_chain_tc_kernel" if engine == "tc" else "nsf_chain_simt_kernel"
+    roof["kernel"] = {"tc": "nsf_chain_tc_kernel", "wide": "nsf_chain_wide_kernel"}.get(engine, "nsf_chain_simt_kernel")
     # DRAM traffic of one launch from the committed ncu --set full capture, scaled by rows (the kernel reads each
     # input row and writes each result once, so traffic is linear in rows); algorithmic bytes: 4 * (D + 1) per row
     try:
@@ -561,7 +561,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc", "wide"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-named-shapes", action="store_true", help="skip the config 1/3/4/5 lines under `extra`")

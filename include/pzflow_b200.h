@@ -86,7 +86,9 @@ typedef struct {
 typedef enum {
   PZB_ENGINE_AUTO = 0,  /* tensor-core engine when the plan's shapes allow it, else SIMT */
   PZB_ENGINE_SIMT = 1,  /* fp32 FFMA conditioner (any shape)                              */
-  PZB_ENGINE_TC = 2     /* tcgen05 conditioner, fp16x2 split-accumulate in fp32 TMEM      */
+  PZB_ENGINE_TC = 2,    /* tcgen05 conditioner, fp16x2 split-accumulate in fp32 TMEM      */
+  PZB_ENGINE_WIDE = 3   /* tcgen05 conditioner for wide / deep shapes (hidden <= 256, K <= 32, any number of hidden
+                           layers >= 1, <= 63 conditioner inputs): weights streamed L2 -> shared memory in slabs */
 } pzb_engine;
 
 typedef struct {
@@ -157,9 +159,19 @@ double pzb_plan_flops_per_row(const pzb_plan *plan);
  * units, at most 16 bins (fewer than 16 only when not periodic), at most 15 conditioner inputs (columns + conditions)
  * and at most 16 transformed columns; at most 31 data columns.  Everything else runs on the SIMT engine. */
 int pzb_plan_tc_supported(const pzb_plan *plan);
+/* 1 if the wide tensor-core engine (PZB_ENGINE_WIDE) supports this plan's shapes: every coupling stage has at least one
+ * hidden layer of at most 256 units, at most 32 bins (periodic: exactly 16 or 32) and at most 63 conditioner inputs.
+ * Replaces the same reference lines as the other engines (pzflow/bijectors.py:462-520, pzflow/utils.py:22-49, 64-227). */
+int pzb_plan_wide_supported(const pzb_plan *plan);
+/* Rows (cumulative over this plan's launches on a tensor-core engine) whose spline logits came out non-finite: the
+ * conditioner's activations ride fp16 hi parts, so a pre-activation beyond +-65504 overflows where the reference's
+ * fp32 (pzflow/utils.py:45-48) stays finite; such rows land in the zero-probability class.  Synchronises the device;
+ * `reset` != 0 clears the counter.  The host-buffer entry points of an AUTO-engine plan re-evaluate a call on the
+ * SIMT engine when it raised this counter. */
+int pzb_plan_overflow_rows(const pzb_plan *plan, int32_t reset, int64_t *count);
 /* select the conditioner engine for subsequent launches (default AUTO). */
 int pzb_plan_set_engine(pzb_plan *plan, int32_t engine);
-/* engine a launch of this plan uses right now (PZB_ENGINE_SIMT or _TC). */
+/* engine a launch of this plan uses right now (PZB_ENGINE_SIMT, _TC or _WIDE; AUTO prefers TC, then WIDE). */
 int pzb_plan_engine(const pzb_plan *plan);
 /* how many kernels of this library were launched by this process so far. */
 int64_t pzb_launch_count(void);
@@ -245,6 +257,22 @@ int pzb_posterior_err(const pzb_plan *plan, const float *rest, const float *rest
                       const float *grid, int32_t G, int32_t err_samples, uint64_t seed,
                       int64_t row_offset, int32_t normalize, int32_t nan_to_zero, float *pdfs,
                       float *scratch, void *stream);
+
+/* Flow.posterior(..., marg_rules=...) for galaxies that miss the SAME n_mcols (1..4) data columns
+ * (pzflow/flow.py:560-664): every galaxy is evaluated in V variants -- its row with the missing columns replaced by
+ * mvals[galaxy, v, q] (q-th listed column; mcols[q] = index of that column among the flow's data columns, not
+ * col_idx) -- as a second expansion axis generated inside the chain kernel (the reference re-enters posterior() on a
+ * host-side repeat of the rows, flow.py:610-643).  With err_samples = S > 0 every variant is additionally
+ * averaged over S Gaussian samples of the NON-marginalised columns / conditions (the reference drops the marginalised
+ * column's error column, flow.py:625-628); pass 0 for none.  pdf_sums [Ng, G] receives
+ *   sum_v nan_to_num?( mean_s exp(log_prob(variant v, sample s, grid point)) )
+ * un-normalised, as the reference's inner calls return it (normalize=False, flow.py:640); the caller normalises the
+ * assembled array with pzb_normalize_pdfs.  scratch: caller-owned device buffer of Ng * V * max(S, 1) * G floats. */
+int pzb_posterior_marg(const pzb_plan *plan, const float *rest, const float *rest_err, const float *cond,
+                       const float *cond_err, int64_t Ng, int32_t col_idx, const float *grid, int32_t G,
+                       int32_t n_mcols, const int32_t *mcols, const float *mvals, int32_t V, int32_t err_samples,
+                       uint64_t seed, int64_t row_offset, int32_t nan_to_zero, float *pdf_sums, float *scratch,
+                       void *stream);
 
 /* The standard normals the two calls above use: eps [n, W] for sample index
  * es in [0, n) (log_prob: es = row * S + s; posterior: es = galaxy * S + s) and

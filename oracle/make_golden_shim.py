@@ -243,8 +243,71 @@ def case_default_flows(pzflow):
     _save("default_flows", store)
 
 
+def case_marg_rules(pzflow):
+    """Flow.posterior(marg_rules=...) of the shipped flow (pzflow/flow.py:560-664; docs/tutorials/marginalization.ipynb
+    cells 12-14): a numeric flag and a NaN flag, rules whose grids depend on the row, a row with TWO flagged columns
+    (nested marginalisation) and a row whose flagged column has no rule (stays all-zero)."""
+    from pzflow import examples
+    import jax.numpy as jnp
+    flow = examples.get_example_flow()
+    X = F.galaxy_rows(40, seed=21, oob_frac=0.0).astype(np.float64)
+    grid = np.linspace(0.0, 2.3, 46).astype(np.float32)
+    store = dict(X=X, grid=grid)
+
+    def rule_u(row):
+        return np.linspace(25.0, 31.0, 12)
+
+    def rule_y(row):
+        return np.linspace(row["z"] - 1.0, row["z"] + 1.0, 9)
+
+    for tag, flag in (("f99", 99.0), ("nan", np.nan)):
+        df = pd.DataFrame(X.copy(), columns=flow.data_columns)
+        df.loc[[1, 5, 9, 13], "u"] = flag
+        df.loc[[2, 5, 20], "y"] = flag      # row 5: u AND y are missing
+        df.loc[[30], "g"] = flag            # no rule for g: the row is never evaluated
+        rules = {"flag": flag, "u": rule_u, "y": rule_y}
+        store[f"{tag}_inputs"] = df.to_numpy()
+        store[f"{tag}_posterior"] = _np(flow.posterior(df, column="redshift", grid=jnp.array(grid), marg_rules=rules))
+        store[f"{tag}_posterior_unnorm"] = _np(flow.posterior(df, column="redshift", grid=jnp.array(grid), marg_rules=rules,
+                                                              normalize=False, nan_to_zero=False))
+    store["u_grid"] = rule_u(None)
+    store["y_halfwidth"], store["y_points"] = np.float64(1.0), np.int64(9)
+    _save("marg_rules", store)
+
+
+def case_ensemble_sample(pzflow):
+    """FlowEnsemble.sample, unconditional (pzflow/flowEnsemble.py:397-408): ceil(n / n_flows) samples from every flow
+    with the same seed, concatenated, then DataFrame.sample(n, random_state=seed).reset_index(drop=True).  The per-flow
+    draws come from the jax PRNG (here: the stand-in's generator) and are stored, so the composition -- which rows of
+    which flow end up where -- is pinned given those draws."""
+    from pzflow import FlowEnsemble
+    rng = np.random.default_rng(9)
+    n = 200
+    df = pd.DataFrame({"a": rng.normal(0, 1, n), "b": rng.uniform(-2, 3, n), "c": rng.normal(1, 2, n)})
+    ens = FlowEnsemble(data_columns=("a", "b", "c"), N=3)
+    for i, fl in enumerate(ens._ensemble.values()):
+        fl._set_default_bijector(df, seed=i)
+    store = {}
+    nsamples, seed = 10, 4
+    per_flow = [fl.sample(int(np.ceil(nsamples / 3)), None, True, seed) for fl in ens._ensemble.values()]
+    store["per_flow"] = np.stack([p.to_numpy() for p in per_flow]).astype(np.float32)
+    out = ens.sample(nsamples, seed=seed)
+    store["nsamples"], store["seed"] = np.int64(nsamples), np.int64(seed)
+    store["sample"] = out.to_numpy().astype(np.float32)
+    store["sample_index"] = out.index.to_numpy()
+    both = ens.sample(4, seed=seed, returnEnsemble=True)
+    store["return_ensemble_shape"] = np.asarray(both.shape)
+    store["return_ensemble_keys"] = np.array([k for k, _ in both.index])
+    _save("ensemble_sample", store)
+
+
 def main():
     pzflow = jax_shim.install()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        case_marg_rules(pzflow)
+        case_ensemble_sample(pzflow)
+        return
     case_example_flow(pzflow)
     case_bijectors(pzflow)
     case_extra_bijectors(pzflow)

@@ -102,8 +102,17 @@ def dense_relu_network(params: Sequence, x: np.ndarray) -> np.ndarray:
     return h
 
 
+class BinTrace(list):
+    """A ``bins`` list that also collects, per coupling stage, the searched knots [N, L, K+1] and the (masked) value
+    they were compared with [N, L] (utils.py:145-152) -- what a test needs to tell a knot tie from a wrong bin."""
+
+    def __init__(self):
+        super().__init__()
+        self.knots, self.values = [], []
+
+
 def rational_quadratic_spline(inputs, W, H, D, B, periodic=False, inverse=False,
-                              return_idx=False):
+                              return_idx=False, trace=None):
     """utils.py:64-227, line for line.
 
     inputs [N, L]; W, H [N, L, K]; D [N, L, K-1] (K if periodic).
@@ -130,6 +139,9 @@ def rational_quadratic_spline(inputs, W, H, D, B, periodic=False, inverse=False,
     # utils.py:149-152 -- bin = (#knots <= x) - 1
     knots = yk if inverse else xk
     idx = np.sum(knots <= masked[..., None], axis=-1).astype(np.int32) - 1
+    if trace is not None:
+        trace.knots.append(knots)
+        trace.values.append(masked)
 
     # utils.py:155-161
     in_xk = _take_fill(xk, idx)
@@ -207,7 +219,8 @@ def neural_spline_coupling(params, inputs, conditions, args, inverse, bins=None)
     upper_dim, lower_dim = _nsc_dims(inputs.shape[1], transformed_dim)
     upper, lower = inputs[:, :upper_dim], inputs[:, upper_dim:]
     W, H, D = nsc_spline_params(params, upper, conditions, K, B, lower_dim, n_conditions, periodic)
-    lower, log_det, idx = rational_quadratic_spline(lower, W, H, D, B, periodic, inverse, return_idx=True)
+    lower, log_det, idx = rational_quadratic_spline(lower, W, H, D, B, periodic, inverse, return_idx=True,
+                                                    trace=bins if isinstance(bins, BinTrace) else None)
     if bins is not None:
         bins.append(idx)
     return np.hstack((upper, lower)), log_det

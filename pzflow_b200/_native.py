@@ -38,6 +38,7 @@ LATENT_JOINT = 6
 ENGINE_AUTO = 0
 ENGINE_SIMT = 1
 ENGINE_TC = 2
+ENGINE_WIDE = 3
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -83,6 +84,8 @@ SIGNATURES = {
     "pzb_plan_n_spline_dims": (C.c_int, [C.c_void_p]),
     "pzb_plan_flops_per_row": (C.c_double, [C.c_void_p]),
     "pzb_plan_tc_supported": (C.c_int, [C.c_void_p]),
+    "pzb_plan_wide_supported": (C.c_int, [C.c_void_p]),
+    "pzb_plan_overflow_rows": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "pzb_plan_set_engine": (C.c_int, [C.c_void_p, C.c_int32]),
     "pzb_plan_engine": (C.c_int, [C.c_void_p]),
     "pzb_launch_count": (C.c_int64, []),
@@ -105,6 +108,9 @@ SIGNATURES = {
     "pzb_posterior_err": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                     C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pzb_posterior_marg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                     C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_uint64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pzb_error_eps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p]),
     "pzb_spline_train_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -26,6 +26,11 @@ size_t tc_pack_bytes(const NscDev& st, int sub);
 void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* const* weights, void* dst);
 cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms,
                       void* workspace, cudaStream_t stream);
+bool wide_plan_supported(const PlanDev& hp);
+size_t wide_pack_bytes(const NscDev& st);
+void wide_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weights, void* dst);
+cudaError_t launch_wide(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms,
+                        unsigned long long* overflow_rows, cudaStream_t stream);
 cudaError_t launch_spline_train_fwd(const float* logits, const float* x, long long n_elems, int K, float B, int periodic,
                                     float* y, float* ld, cudaStream_t stream);
 cudaError_t launch_spline_train_bwd(const float* logits, const float* x, const float* gy, const float* gld,
@@ -90,6 +95,8 @@ struct pzb_plan {
   bool pingpong = false;
   double flops_per_row = 0.0;
   bool tc_ok = false;
+  bool wide_ok = false;
+  unsigned long long* d_overflow = nullptr;  // rows whose logits came out non-finite on a tensor-core engine (fp16 range)
   int engine = PZB_ENGINE_AUTO;
   bool latent_ready = true;
   mutable HostPipe pipe;
@@ -525,7 +532,12 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
     for (int s = 0; s < hp.n_nsc; ++s)
       for (int sub = 0; sub < tc_stage_subs(hp.nsc[s]); ++sub) tc_total += align_up(tc_pack_bytes(hp.nsc[s], sub), 1024);
   }
-  const size_t total = tc_off + tc_total;
+  plan->wide_ok = wide_plan_supported(hp);
+  const size_t wide_off = align_up(tc_off + tc_total, 1024);
+  size_t wide_total = 0;
+  if (plan->wide_ok)
+    for (int s = 0; s < hp.n_nsc; ++s) wide_total += align_up(wide_pack_bytes(hp.nsc[s]), 1024);
+  const size_t total = wide_off + wide_total;
 
   // ---- pass 2: pack on the host, upload once ----
   plan->device = device;
@@ -590,7 +602,20 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
       }
     }
   }
+  if (plan->wide_ok) {
+    size_t o = wide_off;
+    for (const Pending& pe : pend) {
+      NscDev& st = hp.nsc[pe.nsc_idx];
+      const size_t nb = wide_pack_bytes(st);
+      wide_pack_stage(hp, st, pe.weights, hblob.data() + o);
+      st.wide_blob = dbase + o;
+      st.wide_bytes = (int)nb;
+      o += align_up(nb, 1024);
+    }
+  }
   ce = cudaMemcpy(plan->d_weights, hblob.data(), hblob.size(), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&plan->d_overflow), sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMemset(plan->d_overflow, 0, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMalloc(&plan->d_plan, sizeof(PlanDev));
   if (ce == cudaSuccess) ce = cudaMemcpy(plan->d_plan, &hp, sizeof(PlanDev), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) {
@@ -619,6 +644,7 @@ void pzb_plan_destroy(pzb_plan* plan) {
   DeviceGuard guard(plan->device);
   if (plan->d_plan) cudaFree(plan->d_plan);
   if (plan->d_weights) cudaFree(plan->d_weights);
+  if (plan->d_overflow) cudaFree(plan->d_overflow);
   HostPipe& hp = plan->pipe;
   if (hp.ready) {
     cudaStreamSynchronize(hp.s_in);
@@ -653,20 +679,36 @@ int pzb_plan_n_conditions(const pzb_plan* plan) { return plan ? plan->host.C : -
 int pzb_plan_n_spline_dims(const pzb_plan* plan) { return plan ? plan->host.n_spline_dims : -1; }
 double pzb_plan_flops_per_row(const pzb_plan* plan) { return plan ? plan->flops_per_row : 0.0; }
 int pzb_plan_tc_supported(const pzb_plan* plan) { return plan && plan->tc_ok ? 1 : 0; }
+int pzb_plan_wide_supported(const pzb_plan* plan) { return plan && plan->wide_ok ? 1 : 0; }
+
+int pzb_plan_overflow_rows(const pzb_plan* plan, int32_t reset, int64_t* count) {
+  if (!plan || !count) return fail(PZB_ERR_INVALID, "overflow_rows: NULL argument");
+  DeviceGuard guard(plan->device);
+  if (!guard.ok) return fail(PZB_ERR_CUDA, "cannot select device %d", plan->device);
+  unsigned long long v = 0;
+  cudaError_t ce = cudaMemcpy(&v, plan->d_overflow, sizeof(v), cudaMemcpyDeviceToHost);  // (synchronises the device)
+  if (ce == cudaSuccess && reset) ce = cudaMemset(plan->d_overflow, 0, sizeof(v));
+  if (ce != cudaSuccess) return cuda_fail(ce, "overflow_rows");
+  *count = (int64_t)v;
+  return PZB_OK;
+}
 
 int pzb_plan_set_engine(pzb_plan* plan, int32_t engine) {
   if (!plan) return fail(PZB_ERR_INVALID, "set_engine: plan is NULL");
-  if (engine != PZB_ENGINE_AUTO && engine != PZB_ENGINE_SIMT && engine != PZB_ENGINE_TC)
+  if (engine != PZB_ENGINE_AUTO && engine != PZB_ENGINE_SIMT && engine != PZB_ENGINE_TC && engine != PZB_ENGINE_WIDE)
     return fail(PZB_ERR_INVALID, "set_engine: unknown engine %d", engine);
   if (engine == PZB_ENGINE_TC && !plan->tc_ok)
     return fail(PZB_ERR_UNSUPPORTED, "set_engine: the tensor-core engine does not support this plan's shapes");
+  if (engine == PZB_ENGINE_WIDE && !plan->wide_ok)
+    return fail(PZB_ERR_UNSUPPORTED, "set_engine: the wide tensor-core engine does not support this plan's shapes");
   plan->engine = engine;
   return PZB_OK;
 }
 
 int pzb_plan_engine(const pzb_plan* plan) {
   if (!plan) return -1;
-  if (plan->engine == PZB_ENGINE_AUTO) return plan->tc_ok ? PZB_ENGINE_TC : PZB_ENGINE_SIMT;
+  if (plan->engine == PZB_ENGINE_AUTO)
+    return plan->tc_ok ? PZB_ENGINE_TC : (plan->wide_ok ? PZB_ENGINE_WIDE : PZB_ENGINE_SIMT);
   return plan->engine;
 }
 
@@ -677,8 +719,11 @@ static int launch_chain(const pzb_plan* plan, const LaunchArgs& args, void* stre
   DeviceGuard guard(plan->device);
   if (!guard.ok) return fail(PZB_ERR_CUDA, "cannot select device %d", plan->device);
   cudaError_t ce;
-  if (pzb_plan_engine(plan) == PZB_ENGINE_TC) {
+  const int engine = pzb_plan_engine(plan);
+  if (engine == PZB_ENGINE_TC) {
     ce = launch_tc(plan->d_plan, plan->host, args, plan->num_sms, nullptr, (cudaStream_t)stream);
+  } else if (engine == PZB_ENGINE_WIDE) {
+    ce = launch_wide(plan->d_plan, plan->host, args, plan->num_sms, plan->d_overflow, (cudaStream_t)stream);
   } else {
     ce = launch_simt(plan->d_plan, args, plan->host.D, plan->host.C, plan->Lmax, plan->act_rows,
                      plan->pingpong, plan->num_sms, (cudaStream_t)stream);
@@ -1055,6 +1100,84 @@ int pzb_posterior_err(const pzb_plan* plan, const float* rest, const float* rest
   if (ce != cudaSuccess) return cuda_fail(ce, "mean_samples launch");
   g_launches.fetch_add(1);
   return pzb_normalize_pdfs(pdfs, Ng, G, grid, normalize, nan_to_zero, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Posterior marginalised over missing columns (pzflow/flow.py:560-664): the variants of a galaxy (its row with the
+// missing columns replaced by every point of their marginal grids) are a second expansion axis generated inside the
+// chain kernel; this kernel takes the mean over the error samples of a variant (flow.py:722-724), maps NaN to 0 per
+// variant (flow.py:735-737 of the inner call) and sums the variants (flow.py:651-654).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+marg_reduce_kernel(const float* __restrict__ p, long long Ng, int V, int S, int G, int nan_to_zero, float* __restrict__ out) {
+  const long long n = Ng * (long long)G;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long g = e / G;
+    const int i = (int)(e - g * G);
+    float total = 0.0f;
+    for (int v = 0; v < V; ++v) {
+      const float* pv = p + ((size_t)(g * V + v) * S) * G + i;
+      float y = pv[0];
+      if (S > 1) {
+        float s = 0.0f;
+        for (int k = 0; k < S; ++k) s += pv[(size_t)k * G];
+        y = s / (float)S;
+      }
+      if (nan_to_zero) y = nan_to_num0(y);
+      total = v == 0 ? y : total + y;
+    }
+    out[e] = total;
+  }
+}
+
+int pzb_posterior_marg(const pzb_plan* plan, const float* rest, const float* rest_err, const float* cond,
+                       const float* cond_err, int64_t Ng, int32_t col_idx, const float* grid, int32_t G,
+                       int32_t n_mcols, const int32_t* mcols, const float* mvals, int32_t V, int32_t err_samples,
+                       uint64_t seed, int64_t row_offset, int32_t nan_to_zero, float* pdf_sums, float* scratch,
+                       void* stream) {
+  int rc = check_common(plan, plan && plan->host.D > 1 ? (const void*)rest : (const void*)grid, cond, Ng, pdf_sums,
+                        "posterior_marg");
+  if (rc) return rc;
+  if (G < 1 || grid == nullptr) return fail(PZB_ERR_INVALID, "posterior_marg: empty grid");
+  if (col_idx < 0 || col_idx >= plan->host.D) return fail(PZB_ERR_INVALID, "posterior_marg: column index %d out of range", col_idx);
+  if (n_mcols < 1 || n_mcols > 4 || mcols == nullptr || mvals == nullptr || V < 1)
+    return fail(PZB_ERR_INVALID, "posterior_marg: between 1 and 4 marginalised columns with V >= 1 variants each are supported");
+  if (err_samples < 0) return fail(PZB_ERR_INVALID, "posterior_marg: negative err_samples");
+  for (int q = 0; q < n_mcols; ++q) {
+    if (mcols[q] < 0 || mcols[q] >= plan->host.D || mcols[q] == col_idx)
+      return fail(PZB_ERR_INVALID, "posterior_marg: marginalised column %d is not one of the other data columns", mcols[q]);
+    for (int r = 0; r < q; ++r)
+      if (mcols[r] == mcols[q]) return fail(PZB_ERR_INVALID, "posterior_marg: column %d listed twice", mcols[q]);
+  }
+  if (Ng > 0 && scratch == nullptr) return fail(PZB_ERR_INVALID, "posterior_marg: scratch [Ng * V * max(S, 1) * G] is NULL");
+  if (Ng == 0) return PZB_OK;
+  const int S = err_samples > 0 ? err_samples : 1;
+  LaunchArgs a{};
+  a.mode = MODE_POSTERIOR;
+  a.X = rest;
+  a.Xerr = (err_samples > 0 && plan->host.D > 1) ? rest_err : nullptr;
+  a.cond = cond;
+  a.cond_err = (err_samples > 0 && plan->host.C > 0) ? cond_err : nullptr;
+  a.grid = grid;
+  a.G = G;
+  a.col_idx = col_idx;
+  a.S = err_samples > 0 ? err_samples : 0;
+  a.seed = seed;
+  a.unit0 = row_offset;
+  a.mvals = mvals;
+  a.V = V;
+  a.n_mcols = n_mcols;
+  for (int q = 0; q < 4; ++q) a.mcol[q] = q < n_mcols ? mcols[q] : -1;
+  a.N = Ng * (int64_t)V * (int64_t)S * (int64_t)G;
+  a.out0 = scratch;
+  rc = launch_chain(plan, a, stream);
+  if (rc) return rc;
+  DeviceGuard guard(plan->device);
+  marg_reduce_kernel<<<grid_for(Ng * (long long)G), 256, 0, (cudaStream_t)stream>>>(scratch, Ng, V, S, G, nan_to_zero, pdf_sums);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "marg_reduce launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -52,6 +52,8 @@ struct NscDev {
   DenseDev dense[MAX_DENSE];
   int n_sub;                     // tensor-core sub-stages of this stage: ceil(L / 4)
   TcLayerDev tc[TC_SUB_MAX];
+  const void* wide_blob;         // wide tensor-core engine: [parameter block | W1 slabs | hidden slabs | output slabs] (nsf_wide.cu)
+  int wide_bytes;
   int16_t perm[MAX_D];  // logical column j lives in physical column perm[j]
 };
 
@@ -120,6 +122,12 @@ struct LaunchArgs {
   int S;
   unsigned long long seed;
   long long unit0;        // index of X's first row in the caller's whole array: chunked calls draw the same eps
+  // Marginalisation axis (pzflow/flow.py:560-664), V > 0: every unit (galaxy) is evaluated in V variants that differ in
+  // n_mcols data columns (mcol[q] = logical column index, -1 unused) whose values come from mvals[unit, v, q].  N then
+  // counts units * V * max(S, 1) * G rows: unit-major, then variant, then error sample, then grid point.
+  const float* mvals;
+  int V, n_mcols;
+  int mcol[4];
 };
 
 // ---- counter-based normals for the error samples: Philox-4x32-10 keyed by the seed, counter =
@@ -167,26 +175,33 @@ __device__ __forceinline__ float pz_err_normal(unsigned long long seed, uint32_t
 // expansion (pzflow/flow.py:697-714) and the Gaussian error samples are generated here.
 __device__ __forceinline__ float pz_input_value(const LaunchArgs& a, long long row, int j, int D) {
   const long long es = (a.mode == MODE_POSTERIOR) ? row / a.G : row;  // sample index
-  const long long unit = a.S > 0 ? es / a.S : es;                       // row of X
+  const long long vs = a.S > 0 ? es / a.S : es;                         // variant index (== unit without a marginal axis)
+  const long long unit = a.V > 0 ? vs / a.V : vs;                       // row of X
   int jj = j, W = D;
   if (a.mode == MODE_POSTERIOR) {
     if (j == a.col_idx) return a.grid[(int)(row - es * a.G)];
     jj = j < a.col_idx ? j : j - 1;
     W = D - 1;
   }
+  if (a.V > 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < a.n_mcols && a.mcol[q] == j) return a.mvals[vs * a.n_mcols + q];  // a marginalised column: no error model
+  }
   float v = a.X[unit * W + jj];
   if (a.S > 0 && a.Xerr != nullptr)
-    v = v + pz_err_normal(a.seed, 0u, (unsigned long long)(es + a.unit0 * a.S), jj) * a.Xerr[unit * W + jj];
+    v = v + pz_err_normal(a.seed, 0u, (unsigned long long)(es + a.unit0 * a.S * (a.V > 0 ? a.V : 1)), jj) * a.Xerr[unit * W + jj];
   return v;
 }
 
 __device__ __forceinline__ float pz_cond_value(const LaunchArgs& a, long long row, int j, int C) {
   if (a.cond == nullptr) return 0.0f;
   const long long es = (a.mode == MODE_POSTERIOR) ? row / a.G : row;
-  const long long unit = a.S > 0 ? es / a.S : es;
+  const long long vs = a.S > 0 ? es / a.S : es;
+  const long long unit = a.V > 0 ? vs / a.V : vs;
   float v = a.cond[unit * C + j];
   if (a.S > 0 && a.cond_err != nullptr)
-    v = v + pz_err_normal(a.seed, 1u, (unsigned long long)(es + a.unit0 * a.S), j) * a.cond_err[unit * C + j];
+    v = v + pz_err_normal(a.seed, 1u, (unsigned long long)(es + a.unit0 * a.S * (a.V > 0 ? a.V : 1)), j) * a.cond_err[unit * C + j];
   return v;
 }
 

@@ -292,8 +292,8 @@ class Flow:
         grid = np.asarray(grid, dtype=np.float32).reshape(-1)
 
         if marg_rules is not None:
-            return self._posterior_marginalized(inputs, column, columns, grid, marg_rules, normalize,
-                                                batch_size, nan_to_zero, err_samples, seed)
+            return self._posterior_marginalized(inputs, column, columns, idx, grid, marg_rules, normalize,
+                                                nan_to_zero, err_samples, seed)
 
         if err_samples is not None:
             # flow.py:675-693, 722-724: samples of the other columns / conditions, each expanded over the grid,
@@ -320,49 +320,70 @@ class Flow:
         pdfs = plan.posterior_host(rest, idx, grid, conditions, normalize=normalize, nan_to_zero=nan_to_zero)
         return pdfs.numpy()
 
-    def _posterior_marginalized(self, inputs, column, columns, grid, marg_rules, normalize, batch_size,
-                                nan_to_zero, err_samples=None, seed=None):
-        """Host orchestration of pzflow/flow.py:560-664 over the fused posterior."""
-        nrows = inputs.shape[0]
-        pdfs = np.zeros((nrows, len(grid)), dtype=np.float32)
-        if np.isnan(marg_rules["flag"]):
-            def check_flags(data):
-                return np.isnan(data)
-        else:
-            def check_flags(data):
-                return np.isclose(data, marg_rules["flag"])
-        unflagged_idx = inputs[~check_flags(inputs[columns]).any(axis=1)].index.tolist()
-        if len(unflagged_idx):
-            pdfs[unflagged_idx, :] = self.posterior(inputs=inputs.iloc[unflagged_idx], column=column, grid=grid,
-                                                    err_samples=err_samples, seed=seed,
-                                                    batch_size=batch_size, normalize=False,
-                                                    nan_to_zero=nan_to_zero)
-        already_done = list(unflagged_idx)
-        for name, rule in marg_rules.items():
-            if name == "flag":
+    def _posterior_marginalized(self, inputs, column, columns, idx, grid, marg_rules, normalize, nan_to_zero,
+                                err_samples=None, seed=None):
+        """Posteriors with missing values marginalised (pzflow/flow.py:560-664) as ONE extra expansion axis of the
+        fused kernel instead of the reference's recursion through ``posterior`` on repeated rows.
+
+        Rows are grouped by WHICH of the other data columns they miss.  A group's galaxies all get V variants -- the
+        missing columns replaced by every combination of their marginal grids, the first rule's grid outermost, later
+        rules evaluated on the row with the earlier columns already filled in, as the reference's nesting does
+        (flow.py:610-643) -- and one call (``Plan.posterior_marg``) evaluates galaxy x variant x error sample x grid
+        point on the device and sums the variants.  Rows that miss a column without a rule are never evaluated and
+        keep the reference's zeros (flow.py:557).  Only the rule callables themselves run on the host."""
+        from .plan import normalize_pdfs_
+        plan = self._plan()
+        nrows, G = inputs.shape[0], len(grid)
+        flag = marg_rules["flag"]
+        values = inputs[columns].to_numpy(dtype=np.float64).reshape(nrows, len(columns))
+        missing = np.isnan(values) if np.isnan(flag) else np.isclose(values, flag)            # flow.py:563-574
+        position = {c: j for j, c in enumerate(columns)}
+        ruled = [name for name in marg_rules if name != "flag" and name in position]        # marginalisation order
+        has_rule = np.zeros(len(columns), dtype=bool)
+        has_rule[[position[c] for c in ruled]] = True
+        evaluable = ~(missing & ~has_rule).any(axis=1)
+        codes = (missing.astype(np.int64) << np.arange(len(columns), dtype=np.int64)).sum(axis=1)
+        pdfs = torch.zeros((nrows, G), dtype=torch.float32, device=plan.device)
+        all_columns = list(self.data_columns)
+        for code in np.unique(codes[evaluable]) if nrows else []:
+            rows = np.nonzero(evaluable & (codes == code))[0]
+            frame = inputs.iloc[rows]
+            names = [c for c in ruled if (int(code) >> position[c]) & 1]
+            cond, cond_err = (self._get_err_arrays(frame, "conditions") if err_samples is not None
+                              else (self._get_conditions(frame), None))
+            if err_samples is not None and len(self.data_columns) > 1:
+                rest, rest_err = self._get_err_arrays(frame, "data", skip=column)
+            else:
+                rest, rest_err = values[rows].astype(np.float32), None
+            if not names:                                                                     # nothing missing
+                if err_samples is None:
+                    out = plan.posterior(torch.from_numpy(rest), idx, grid, cond, normalize=False, nan_to_zero=nan_to_zero)
+                else:
+                    out = plan.posterior_err(rest, rest_err, idx, grid, cond, cond_err, err_samples, seed,
+                                             normalize=False, nan_to_zero=nan_to_zero)
+                pdfs[torch.as_tensor(rows, device=plan.device)] = out
                 continue
-            flagged_idx = inputs[check_flags(inputs[name])].index.tolist()
-            flagged_idx = list(set(flagged_idx).difference(already_done))
-            if len(flagged_idx) == 0:
-                continue
-            marg_grids = inputs.iloc[flagged_idx].apply(rule, axis=1, result_type="expand").to_numpy()
-            marg_inputs = pd.DataFrame(np.repeat(inputs.iloc[flagged_idx].to_numpy(), marg_grids.shape[1], axis=0),
-                                       columns=inputs.columns)
-            marg_inputs[name] = marg_grids.reshape(marg_inputs.shape[0], 1)
-            marg_inputs.drop(f"{name}_err", axis=1, inplace=True, errors="ignore")
-            marg_pdfs = self.posterior(inputs=marg_inputs, column=column, grid=grid, marg_rules=marg_rules,
-                                       err_samples=err_samples, seed=seed,
-                                       batch_size=batch_size, normalize=False, nan_to_zero=nan_to_zero)
-            marg_pdfs = marg_pdfs.reshape(len(flagged_idx), marg_grids.shape[1], grid.size).sum(axis=1)
-            pdfs[flagged_idx, :] = marg_pdfs
-            already_done += flagged_idx
-        if normalize or nan_to_zero:
-            from .plan import normalize_pdfs_
-            dev = self._plan().device
-            t = normalize_pdfs_(torch.from_numpy(pdfs).to(dev), torch.from_numpy(grid).to(dev), normalize,
-                                nan_to_zero)
-            pdfs = t.cpu().numpy()
-        return pdfs
+            if len(names) > 4:
+                raise NotImplementedError("at most 4 columns of a row can be marginalised at once on the B200 path")
+            # the variants: grids[q] holds, for every (row, combination of the earlier grids), the q-th rule's grid
+            cur, levels = frame, []
+            for q, name in enumerate(names):
+                grids = np.asarray(cur.apply(marg_rules[name], axis=1, result_type="expand").to_numpy(), dtype=np.float64)
+                M = grids.shape[1]
+                levels = [np.repeat(v, M) for v in levels] + [grids.reshape(-1)]
+                if q + 1 < len(names):      # later rules see the row with this column filled in (flow.py:617-623)
+                    cur = pd.DataFrame(np.repeat(cur.to_numpy(), M, axis=0), columns=cur.columns)
+                    cur[name] = grids.reshape(-1)
+            V = levels[0].size // len(rows)
+            mvals = np.stack(levels, axis=1).reshape(len(rows), V, len(names)).astype(np.float32)
+            rest = np.where(missing[rows], np.float32(0), rest).astype(np.float32)          # never read by the kernel
+            out = plan.posterior_marg(rest, idx, grid, [all_columns.index(c) for c in names], mvals, rest_err=rest_err,
+                                      cond=cond, cond_err=cond_err, err_samples=err_samples or 0, seed=seed or 0,
+                                      nan_to_zero=nan_to_zero)
+            pdfs[torch.as_tensor(rows, device=plan.device)] = out
+        if (normalize or nan_to_zero) and nrows:
+            normalize_pdfs_(pdfs, torch.from_numpy(grid).to(plan.device), normalize, nan_to_zero)   # flow.py:732-737
+        return pdfs.cpu().numpy()
 
     def sample(self, nsamples: int = 1, conditions: pd.DataFrame = None, save_conditions: bool = True,
                seed: int = None) -> pd.DataFrame:

@@ -254,6 +254,7 @@ class Plan:
         self.n_spline_dims = lib.pzb_plan_n_spline_dims(handle)
         self.flops_per_row = lib.pzb_plan_flops_per_row(handle)
         self.tc_supported = bool(lib.pzb_plan_tc_supported(handle))
+        self.wide_supported = bool(lib.pzb_plan_wide_supported(handle))
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -266,12 +267,19 @@ class Plan:
 
     # ---- engine selection -------------------------------------------------
     def set_engine(self, engine: str) -> None:
-        code = {"auto": N.ENGINE_AUTO, "simt": N.ENGINE_SIMT, "tc": N.ENGINE_TC}[engine]
+        code = {"auto": N.ENGINE_AUTO, "simt": N.ENGINE_SIMT, "tc": N.ENGINE_TC, "wide": N.ENGINE_WIDE}[engine]
         N.check(N.lib().pzb_plan_set_engine(self._h, code))
 
     @property
     def engine(self) -> str:
-        return {N.ENGINE_SIMT: "simt", N.ENGINE_TC: "tc"}[N.lib().pzb_plan_engine(self._h)]
+        return {N.ENGINE_SIMT: "simt", N.ENGINE_TC: "tc", N.ENGINE_WIDE: "wide"}[N.lib().pzb_plan_engine(self._h)]
+
+    def overflow_rows(self, reset: bool = False) -> int:
+        """Rows (cumulative) whose spline logits came out non-finite on a tensor-core engine: an fp16 overflow of a
+        conditioner pre-activation beyond +-65504, where the reference's fp32 stays finite (pzb_plan_overflow_rows)."""
+        n = C.c_int64(0)
+        N.check(N.lib().pzb_plan_overflow_rows(self._h, int(bool(reset)), C.byref(n)))
+        return int(n.value)
 
     # ---- tensor plumbing --------------------------------------------------
     def _rows(self, X, width: int, what: str) -> torch.Tensor:
@@ -471,6 +479,41 @@ class Plan:
                     _ptr(cond[r0:r0 + m]) if cond is not None else None,
                     _ptr(cond_err[r0:r0 + m]) if cond_err is not None else None, m, int(col_idx), _ptr(grid), G, S,
                     int(seed) & (2 ** 64 - 1), r0, int(bool(normalize)), int(bool(nan_to_zero)),
+                    _ptr(out[r0:r0 + m]), _ptr(scratch), _stream(self.device)))
+        return out
+
+    def posterior_marg(self, rest, col_idx: int, grid, mcols, mvals, rest_err=None, cond=None, cond_err=None,
+                       err_samples: int = 0, seed: int = 0, nan_to_zero: bool = True) -> torch.Tensor:
+        """Un-normalised posterior sums of galaxies that miss the same data columns (pzflow/flow.py:560-664):
+        rest [Ng, D-1] (any value in the missing columns), mcols = indices of the missing columns among the data
+        columns, mvals [Ng, V, len(mcols)] the values every variant puts there -> [Ng, G] on the device,
+        sum over the variants of nan_to_num(mean over error samples of exp(log_prob)) (pzb_posterior_marg)."""
+        rest = self._rows(rest, self.input_dim - 1, "inputs")
+        Ng = rest.shape[0]
+        mcols = [int(c) for c in mcols]
+        mv = torch.as_tensor(mvals).to(device=self.device, dtype=torch.float32).contiguous()
+        if mv.dim() != 3 or mv.shape[0] != Ng or mv.shape[2] != len(mcols):
+            raise ValueError(f"mvals must have shape [{Ng}, V, {len(mcols)}], got {tuple(mv.shape)}")
+        V, S = mv.shape[1], int(err_samples or 0)
+        rest_err = self._dev_opt(rest_err, rest.shape, "input errors") if S else None
+        cond = self._cond(cond, Ng)
+        cond_err = self._dev_opt(cond_err, (Ng, self.n_conditions), "condition errors") if (S and cond is not None) else None
+        grid = torch.as_tensor(grid).to(device=self.device, dtype=torch.float32).contiguous().reshape(-1)
+        G = grid.numel()
+        out = torch.empty((Ng, G), dtype=torch.float32, device=self.device)
+        per = V * max(S, 1) * G
+        step = max(1, self.ERR_SCRATCH_FLOATS // per)
+        scratch = torch.empty(min(Ng, step) * per, dtype=torch.float32, device=self.device)
+        cols = (C.c_int32 * len(mcols))(*mcols)
+        with torch.cuda.device(self.device):
+            for r0 in range(0, Ng, step):
+                m = min(step, Ng - r0)
+                N.check(N.lib().pzb_posterior_marg(
+                    self._h, _ptr(rest[r0:r0 + m]) if rest.numel() else None,
+                    _ptr(rest_err[r0:r0 + m]) if rest_err is not None and rest_err.numel() else None,
+                    _ptr(cond[r0:r0 + m]) if cond is not None else None,
+                    _ptr(cond_err[r0:r0 + m]) if cond_err is not None else None, m, int(col_idx), _ptr(grid), G,
+                    len(mcols), cols, _ptr(mv[r0:r0 + m]), V, S, int(seed) & (2 ** 64 - 1), r0, int(bool(nan_to_zero)),
                     _ptr(out[r0:r0 + m]), _ptr(scratch), _stream(self.device)))
         return out
 

@@ -74,3 +74,63 @@ def count_bin_flips(bins_cuda, bins_oracle):
     b1, b2 = np.asarray(bins_cuda), np.asarray(bins_oracle)
     flips = b1 != b2
     return int(flips.sum()), int(flips.any(axis=1).sum()), int(b1.size)
+
+
+# ---- knot ties ---------------------------------------------------------------------------------
+def flip_tie_report(bins_cuda, trace, trace64=None, B=5.0):
+    """For every bin index that differs from the oracle's: how far the searched value sits from the knot that
+    separates the two bins, in float32 ulps of the spline range B (ulp(5.0) = 4.77e-7).  north_star allows flips
+    "at knot ties" only: a flip must be between ADJACENT bins, and the value must sit on the separating knot to
+    within the float32 uncertainty of that comparison.  That uncertainty is not 1 ulp: a stage's inputs and knots
+    carry the rounding of every stage before it (the float32 oracle and its float64 twin disagree on them by up to
+    hundreds of ulps by the last stage of the trained 7-D flow), so with `trace64` (the float64 twin's BinTrace of the
+    same rows) each distance is also given relative to the stage's own noise floor
+        noise_s = 4 ulp + q99 |value32 - value64| + q99 |knot32 - knot64|
+    and `max_ratio` = max distance / noise_s.  `trace` / `trace64` are oracle BinTraces (stages in walk order)."""
+    b1 = np.asarray(bins_cuda)
+    b2 = np.concatenate(list(trace), axis=1)
+    ulp = float(np.spacing(np.float32(B)))
+    out = dict(total=int(b1.size), flips=0, rows=0, non_adjacent=0, ulps=[], ratios=[])
+    flips = b1 != b2
+    out["flips"], out["rows"] = int(flips.sum()), int(flips.any(axis=1).sum())
+    col0 = 0
+    for s, (knots, vals, idx) in enumerate(zip(trace.knots, trace.values, trace)):
+        L = idx.shape[1]
+        rr, dd = np.nonzero(flips[:, col0:col0 + L])
+        noise = None
+        if trace64 is not None and len(rr):
+            fin = np.isfinite(vals) & np.isfinite(trace64.values[s])
+            dv = np.abs(vals.astype(np.float64) - trace64.values[s])[fin]
+            dk = np.abs(knots.astype(np.float64) - trace64.knots[s])
+            dk = dk[np.isfinite(dk)]
+            noise = 4 * ulp + (np.quantile(dv, 0.99) if dv.size else 0.0) + (np.quantile(dk, 0.99) if dk.size else 0.0)
+        for r, d in zip(rr, dd):
+            a, b = int(b1[r, col0 + d]), int(b2[r, d + col0])
+            if abs(a - b) != 1 or not 0 <= max(a, b) < knots.shape[2]:
+                out["non_adjacent"] += 1
+                continue
+            dist = abs(float(vals[r, d]) - float(knots[r, d, max(a, b)]))
+            out["ulps"].append(dist / ulp)
+            if noise is not None:
+                out["ratios"].append(dist / noise)
+        col0 += L
+    u = np.asarray(out["ulps"], np.float64)
+    out["max_ulps"] = float(u.max()) if u.size else 0.0
+    out["median_ulps"] = float(np.median(u)) if u.size else 0.0
+    out["within_4_ulps"] = int((u <= 4).sum())
+    out["max_ratio"] = float(max(out["ratios"])) if out["ratios"] else 0.0
+    del out["ratios"]
+    out["ulps"] = [round(float(x), 1) for x in sorted(u)[-8:]]   # the largest few, for the report
+    return out
+
+
+_REPORT = {}
+
+
+def record(config, **fields):
+    """Collect per-config parity figures; tests/test_gpu_parity.py writes them to profiles/parity_r02.json."""
+    _REPORT.setdefault(config, {}).update(fields)
+
+
+def report():
+    return _REPORT

@@ -474,3 +474,26 @@ def test_training_latents_cover_tdist_and_joint():
     t_info = ("Tdist", (5,))
     got = chain._latent_any(t_info, None, torch.as_tensor(u)).numpy()      # default nu = 30
     assert np.allclose(got, O.any_latent_log_prob(t_info, np.float64(np.log(30.0)), u), rtol=1e-12, atol=1e-12)
+
+
+def test_ensemble_sample_composition_matches_reference_golden(monkeypatch):
+    """FlowEnsemble.sample, unconditional (pzflow/flowEnsemble.py:397-408): given the per-flow draws, which rows of
+    which flow end up where is pinned by the reference's own code (tests/golden/ref_shim_ensemble_sample.npz)."""
+    from conftest import golden
+    z = golden("ref_shim_ensemble_sample.npz")
+    per_flow = z["per_flow"]                                   # [3 flows, ceil(10 / 3), 3 columns]
+    cols = ("a", "b", "c")
+    ens = FlowEnsemble(data_columns=cols, N=3)
+    calls = []
+    for i, flow in enumerate(ens._ensemble.values()):
+        def fake(nsamples, conditions=None, save_conditions=True, seed=None, _i=i):
+            calls.append((_i, nsamples, seed))
+            return pd.DataFrame(per_flow[_i][:nsamples], columns=cols)
+        monkeypatch.setattr(flow, "sample", fake)
+    out = ens.sample(int(z["nsamples"]), seed=int(z["seed"]))
+    assert calls == [(0, 4, 4), (1, 4, 4), (2, 4, 4)]          # ceil(10 / 3) from every flow, the same seed
+    assert np.array_equal(out.to_numpy().astype(np.float32), z["sample"])
+    assert np.array_equal(out.index.to_numpy(), z["sample_index"])
+    both = ens.sample(4, seed=int(z["seed"]), returnEnsemble=True)
+    assert tuple(both.shape) == tuple(z["return_ensemble_shape"])
+    assert [k for k, _ in both.index] == list(z["return_ensemble_keys"])
