@@ -227,8 +227,22 @@ int pzb_normalize_pdfs(float *pdfs, int64_t Ng, int32_t G, const float *grid,
 
 /* Latent draws for Flow.sample speed runs (pzflow/distributions.py:443-470):
  * U [N, D] ~ Uniform(-B, B) from a counter-based Philox stream.  This is NOT
- * jax.random's threefry stream; sample parity is defined on the map u -> x. */
-int pzb_sample_uniform(float *U, int64_t N, int32_t D, float B, uint64_t seed, void *stream);
+ * jax.random's threefry stream; sample parity is defined on the map u -> x.
+ * row_offset (here and in the three samplers below): index of U's first row in the caller's whole array, so that a
+ * call sharded over rows (several GPUs, several chunks) draws exactly what one big call would; row_offset * D must be
+ * a multiple of 4 for the uniform and the normal sampler (their draws come in blocks of four). */
+int pzb_sample_uniform(float *U, int64_t N, int32_t D, float B, uint64_t seed, int64_t row_offset, void *stream);
+
+/* The other latents' draws (pzflow/distributions.py:101-135 CentBeta, 196-229 CentBeta13, 277-303 Normal, 360-392
+ * Tdist), each from its own counter-based Philox stream keyed by (seed, element index):
+ *   centbeta: U[N, D] = 2B (Beta(a[j], b[j]) - 0.5), Beta as a ratio of two Marsaglia-Tsang gammas; a, b are HOST
+ *             arrays of D positive shapes (CentBeta13: all 13);
+ *   normal:   U[N, D] standard normal (Box-Muller);
+ *   tdist:    U[N, D] = z / sqrt(chi2(nu) / nu), one chi2 per row (unit scale matrix). */
+int pzb_sample_centbeta(float *U, int64_t N, int32_t D, const float *a, const float *b, float B, uint64_t seed,
+                        int64_t row_offset, void *stream);
+int pzb_sample_normal(float *U, int64_t N, int32_t D, uint64_t seed, int64_t row_offset, void *stream);
+int pzb_sample_tdist(float *U, int64_t N, int32_t D, float nu, uint64_t seed, int64_t row_offset, void *stream);
 
 /* ---- Gaussian error convolution (err_samples) ---------------------------
  * Flow.log_prob(inputs, err_samples=S) (pzflow/flow.py:448-464) with the default
@@ -299,6 +313,11 @@ int pzb_spline_train_backward(const float *logits, const float *x, const float *
  * before the update, so the whole call can be captured in a CUDA graph. */
 int pzb_adam_step(float *params, const float *grads, float *m, float *v, int64_t n, float lr, float b1,
                   float b2, float eps, int32_t *step_dev, void *stream);
+
+/* Host threads (casts, gathers, staging copies) the host-buffer entry points below may use when called from THIS
+ * host thread; 0 restores the default (the process's CPU affinity, shared between torchrun's local ranks, at most 16).
+ * A caller that drives several devices from several host threads gives each its share. */
+int pzb_set_host_threads(int32_t n);
 
 /* ---- host-buffer forms --------------------------------------------------
  * The same evaluations for callers whose arrays live in HOST memory, which is

@@ -102,7 +102,12 @@ SIGNATURES = {
                                               C.c_int32, C.c_void_p, C.c_void_p]),
     "pzb_normalize_pdfs": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_void_p]),
-    "pzb_sample_uniform": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_void_p]),
+    "pzb_sample_uniform": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_int64, C.c_void_p]),
+    "pzb_set_host_threads": (C.c_int, [C.c_int32]),
+    "pzb_sample_centbeta": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64,
+                                      C.c_int64, C.c_void_p]),
+    "pzb_sample_normal": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_int64, C.c_void_p]),
+    "pzb_sample_tdist": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_int64, C.c_void_p]),
     "pzb_log_prob_err": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                    C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pzb_posterior_err": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,

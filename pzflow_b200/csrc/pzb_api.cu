@@ -878,11 +878,13 @@ logmeanexp_kernel(const float* __restrict__ lp, int n_flows, long long N, float*
 }
 
 __global__ void __launch_bounds__(256)
-sample_uniform_kernel(float* __restrict__ U, long long n, float B, uint64_t seed) {
+sample_uniform_kernel(float* __restrict__ U, long long n, float B, uint64_t seed, long long q0) {
+  // q0: index of U's first element in the caller's whole array, over 4 (a sharded call draws what one big call would)
   const long long nq = (n + 3) / 4;
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq;
        q += (long long)gridDim.x * blockDim.x) {
-    uint32_t c[4] = {(uint32_t)q, (uint32_t)((unsigned long long)q >> 32), 0u, 0u};
+    const unsigned long long qq = (unsigned long long)(q + q0);
+    uint32_t c[4] = {(uint32_t)qq, (uint32_t)(qq >> 32), 0u, 0u};
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -967,16 +969,162 @@ int pzb_ensemble_posterior_mean(const float* pdfs, int32_t n_flows, int64_t Ng, 
   return PZB_OK;
 }
 
-int pzb_sample_uniform(float* U, int64_t N, int32_t D, float B, uint64_t seed, void* stream) {
-  if (N < 0 || D < 1) return fail(PZB_ERR_INVALID, "sample_uniform: bad shape");
+int pzb_sample_uniform(float* U, int64_t N, int32_t D, float B, uint64_t seed, int64_t row_offset, void* stream) {
+  if (N < 0 || D < 1 || row_offset < 0) return fail(PZB_ERR_INVALID, "sample_uniform: bad shape");
+  if ((row_offset * (int64_t)D) % 4 != 0)
+    return fail(PZB_ERR_INVALID, "sample_uniform: row_offset * D must be a multiple of 4 (draws come in blocks of four)");
   if (N == 0) return PZB_OK;
   if (!U) return fail(PZB_ERR_INVALID, "sample_uniform: NULL buffer");
   const long long n = N * (long long)D;
   long long blocks = ((n + 3) / 4 + 255) / 256;
   if (blocks > (long long)current_num_sms() * 32) blocks = (long long)current_num_sms() * 32;
-  sample_uniform_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(U, n, B, seed);
+  sample_uniform_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(U, n, B, seed, row_offset * (long long)D / 4);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return cuda_fail(ce, "sample_uniform launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Latent draws other than Uniform (pzflow/distributions.py:101-135 CentBeta, 196-229 CentBeta13, 277-303 Normal,
+// 360-392 Tdist): counter-based Philox streams, one per element, so a draw depends on (seed, element index) only.
+// Not jax's threefry: like the uniform sampler, sample parity is defined on the map u -> x.
+// ---------------------------------------------------------------------------------------------
+static unsigned grid_for(long long n) {
+  long long b = (n + 255) / 256;
+  if (b > (long long)current_num_sms() * 32) b = (long long)current_num_sms() * 32;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+struct BetaShapes {
+  float a[MAX_D], b[MAX_D];
+};
+
+// uniform in (0, 1) from 24 random bits
+__device__ __forceinline__ float pz_u01(uint32_t w) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+
+// Gamma(shape, 1), Marsaglia-Tsang squeeze (shape >= 1; smaller shapes through Gamma(shape + 1) * U^(1/shape)).
+// Attempt t of element `elem` on stream `sid` takes the Philox block (elem, t, sid): two words -> one normal (Box-Muller),
+// one word -> the acceptance uniform, one word -> the boost uniform of shape < 1.
+__device__ float pz_gamma_draw(float shape, unsigned long long seed, unsigned long long elem, uint32_t sid) {
+  const bool small = shape < 1.0f;
+  const float a = small ? shape + 1.0f : shape;
+  const float d = a - 0.33333334f, c = rsqrtf(9.0f * d);
+  float boost = 1.0f, out = d;
+  for (uint32_t t = 0; t < 64u; ++t) {
+    uint32_t w[4];
+    pz_philox4(seed, elem, t, sid, w);
+    if (t == 0u && small) boost = powf(pz_u01(w[3]), 1.0f / shape);
+    const float r = sqrtf(-2.0f * logf(pz_u01(w[0])));
+    float sn, cs;
+    sincospif(2.0f * pz_u01(w[1]), &sn, &cs);
+    const float x = r * cs;
+    float v = 1.0f + c * x;
+    if (v <= 0.0f) continue;
+    v = v * v * v;
+    const float u = pz_u01(w[2]);
+    const float x2 = x * x;
+    if (u < 1.0f - 0.0331f * x2 * x2 || logf(u) < 0.5f * x2 + d * (1.0f - v + logf(v))) {
+      out = d * v;
+      break;
+    }
+  }
+  return out * boost;
+}
+
+__global__ void __launch_bounds__(256)
+sample_centbeta_kernel(float* __restrict__ U, long long n, int D, BetaShapes sh, float B, unsigned long long seed,
+                       long long e0) {
+  // 2B (Beta(a_j, b_j) - 0.5) with Beta = Ga / (Ga + Gb)  (distributions.py:120-135, 217-229)
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % D);
+    const float ga = pz_gamma_draw(sh.a[j], seed, (unsigned long long)(e + e0), 2u);
+    const float gb = pz_gamma_draw(sh.b[j], seed, (unsigned long long)(e + e0), 3u);
+    U[e] = (2.0f * B) * (ga / (ga + gb) - 0.5f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sample_normal_kernel(float* __restrict__ U, long long n, unsigned long long seed, long long q0) {
+  const long long nq = (n + 3) / 4;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    uint32_t w[4];
+    pz_philox4(seed, (unsigned long long)(q + q0), 0u, 4u, w);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float r = sqrtf(-2.0f * logf(pz_u01(w[2 * h])));
+      float sn, cs;
+      sincospif(2.0f * pz_u01(w[2 * h + 1]), &sn, &cs);
+      const long long i = q * 4 + 2 * h;
+      if (i < n) U[i] = r * cs;
+      if (i + 1 < n) U[i + 1] = r * sn;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sample_tdist_kernel(float* __restrict__ U, long long N, int D, float nu, unsigned long long seed, long long r0) {
+  // z / sqrt(chi2(nu) / nu) with one chi2 = 2 Gamma(nu / 2) per row (distributions.py:377-392, unit scale matrix)
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < N; r += (long long)gridDim.x * blockDim.x) {
+    const float chi2 = 2.0f * pz_gamma_draw(0.5f * nu, seed, (unsigned long long)(r + r0), 5u);
+    const float scale = rsqrtf(chi2 / nu);
+    for (int j0 = 0; j0 < D; j0 += 4) {
+      uint32_t w[4];
+      pz_philox4(seed, (unsigned long long)(r + r0), (uint32_t)(j0 >> 2), 6u, w);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float rr = sqrtf(-2.0f * logf(pz_u01(w[2 * h])));
+        float sn, cs;
+        sincospif(2.0f * pz_u01(w[2 * h + 1]), &sn, &cs);
+        const int j = j0 + 2 * h;
+        if (j < D) U[r * D + j] = rr * cs * scale;
+        if (j + 1 < D) U[r * D + j + 1] = rr * sn * scale;
+      }
+    }
+  }
+}
+
+int pzb_sample_centbeta(float* U, int64_t N, int32_t D, const float* a, const float* b, float B, uint64_t seed,
+                        int64_t row_offset, void* stream) {
+  if (N < 0 || D < 1 || D > MAX_D || row_offset < 0) return fail(PZB_ERR_INVALID, "sample_centbeta: bad shape (1 <= D <= %d)", MAX_D);
+  if (N == 0) return PZB_OK;
+  if (!U || !a || !b) return fail(PZB_ERR_INVALID, "sample_centbeta: NULL buffer");
+  BetaShapes sh;
+  for (int j = 0; j < D; ++j) {
+    if (!(a[j] > 0.0f) || !(b[j] > 0.0f)) return fail(PZB_ERR_INVALID, "sample_centbeta: shapes must be positive");
+    sh.a[j] = a[j];
+    sh.b[j] = b[j];
+  }
+  sample_centbeta_kernel<<<grid_for(N * (long long)D), 256, 0, (cudaStream_t)stream>>>(U, N * (long long)D, D, sh, B, seed,
+                                                                                   row_offset * (long long)D);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "sample_centbeta launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+int pzb_sample_normal(float* U, int64_t N, int32_t D, uint64_t seed, int64_t row_offset, void* stream) {
+  if (N < 0 || D < 1 || row_offset < 0) return fail(PZB_ERR_INVALID, "sample_normal: bad shape");
+  if ((row_offset * (int64_t)D) % 4 != 0)
+    return fail(PZB_ERR_INVALID, "sample_normal: row_offset * D must be a multiple of 4 (draws come in blocks of four)");
+  if (N == 0) return PZB_OK;
+  if (!U) return fail(PZB_ERR_INVALID, "sample_normal: NULL buffer");
+  const long long n = N * (long long)D;
+  sample_normal_kernel<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(U, n, seed, row_offset * (long long)D / 4);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "sample_normal launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+int pzb_sample_tdist(float* U, int64_t N, int32_t D, float nu, uint64_t seed, int64_t row_offset, void* stream) {
+  if (N < 0 || D < 1 || !(nu > 0.0f) || row_offset < 0) return fail(PZB_ERR_INVALID, "sample_tdist: bad shape or degrees of freedom");
+  if (N == 0) return PZB_OK;
+  if (!U) return fail(PZB_ERR_INVALID, "sample_tdist: NULL buffer");
+  sample_tdist_kernel<<<grid_for(N), 256, 0, (cudaStream_t)stream>>>(U, N, D, nu, seed, row_offset);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "sample_tdist launch");
   g_launches.fetch_add(1);
   return PZB_OK;
 }
@@ -1018,12 +1166,6 @@ error_eps_kernel(float* __restrict__ eps, long long n, int W, uint32_t stream_id
   }
 }
 
-static unsigned grid_for(long long n) {
-  long long b = (n + 255) / 256;
-  if (b > (long long)current_num_sms() * 32) b = (long long)current_num_sms() * 32;
-  if (b < 1) b = 1;
-  return (unsigned)b;
-}
 
 int pzb_error_eps(float* eps, int64_t n, int32_t W, int32_t stream_id, uint64_t seed, void* stream) {
   if (n < 0 || W < 1 || (stream_id != 0 && stream_id != 1)) return fail(PZB_ERR_INVALID, "error_eps: bad arguments");
@@ -1285,7 +1427,9 @@ static cudaError_t pipe_reserve(void** p, size_t* cap, size_t want, int n) {
 
 // Host threads for the casts / copies of one pipeline: the CPUs this process may run on (its affinity mask, which
 // sharding.bind_to_gpu_numa_node narrows), shared fairly when torchrun runs several ranks on the box, at most 16.
+static thread_local int g_host_threads = 0;  // pzb_set_host_threads: this host thread's budget for its pipelines
 static int host_thread_count() {
+  if (g_host_threads > 0) return g_host_threads;
   int n = (int)std::thread::hardware_concurrency();
   cpu_set_t set;
   if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
@@ -1492,6 +1636,12 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
   if (rc != PZB_OK) return rc;
   ce = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
   if (ce != cudaSuccess) return cuda_fail(ce, who);
+  return PZB_OK;
+}
+
+int pzb_set_host_threads(int32_t n) {
+  if (n < 0) return fail(PZB_ERR_INVALID, "set_host_threads: negative thread count");
+  g_host_threads = n > 64 ? 64 : n;
   return PZB_OK;
 }
 

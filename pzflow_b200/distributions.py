@@ -20,10 +20,10 @@ from . import plan as _plan
 Pytree = tuple
 
 
-def _device() -> torch.device:
+def _device(device=None) -> torch.device:
     if not torch.cuda.is_available():
         raise _plan.N.NativeError("pzflow_b200 needs a CUDA device: there is no CPU fallback")
-    return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
 
 def _seed(seed) -> int:
@@ -66,13 +66,11 @@ class CentBeta13(LatentDist):
         out = lp.sum(dim=1)
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
-    def sample_device(self, nsamples: int, seed: int = None) -> torch.Tensor:
-        gen = torch.Generator(device=_device())
-        gen.manual_seed(_seed(seed) % (2 ** 63))
-        conc = torch.full((nsamples, self.input_dim, 2), 13.0, device=_device())
-        g = torch._standard_gamma(conc, generator=gen)
-        s = g[..., 0] / (g[..., 0] + g[..., 1])
-        return (2.0 * float(self.B) * (s - 0.5)).contiguous()
+    def sample_device(self, nsamples: int, seed: int = None, *, device=None, row_offset: int = 0) -> torch.Tensor:
+        """Draws on ``device`` (default: the current one); ``row_offset`` = index of the first row in the caller's whole
+        sample, so that row shards drawn on several devices equal one big draw."""
+        shapes = np.full(self.input_dim, 13.0, np.float32)
+        return _plan.sample_centbeta(nsamples, shapes, shapes, float(self.B), _seed(seed), _device(device), row_offset)
 
     def sample(self, params: Pytree, nsamples: int, seed: int = None):
         """[nsamples, input_dim] draws, 2B(Beta(13,13) - 0.5) (distributions.py:196-229)."""
@@ -97,8 +95,8 @@ class Uniform(LatentDist):
                           torch.full(mask.shape, -math.inf, device=u.device))
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
-    def sample_device(self, nsamples: int, seed: int = None) -> torch.Tensor:
-        return _plan.sample_uniform(nsamples, self.input_dim, float(self.B), _seed(seed), _device())
+    def sample_device(self, nsamples: int, seed: int = None, *, device=None, row_offset: int = 0) -> torch.Tensor:
+        return _plan.sample_uniform(nsamples, self.input_dim, float(self.B), _seed(seed), _device(device), row_offset)
 
     def sample(self, params: Pytree, nsamples: int, seed: int = None):
         """[nsamples, input_dim] draws from U(-B, B) (distributions.py:443-470)."""
@@ -119,10 +117,8 @@ class Normal(LatentDist):
         out = -0.5 * (self.input_dim * math.log(2.0 * math.pi) + (u * u).sum(dim=1))
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
-    def sample_device(self, nsamples: int, seed: int = None) -> torch.Tensor:
-        gen = torch.Generator(device=_device())
-        gen.manual_seed(_seed(seed) % (2 ** 63))
-        return torch.randn((nsamples, self.input_dim), generator=gen, device=_device())
+    def sample_device(self, nsamples: int, seed: int = None, *, device=None, row_offset: int = 0) -> torch.Tensor:
+        return _plan.sample_normal(nsamples, self.input_dim, _seed(seed), _device(device), row_offset)
 
     def sample(self, params: Pytree, nsamples: int, seed: int = None):
         """[nsamples, input_dim] standard normal draws (distributions.py:277-303)."""
@@ -156,14 +152,12 @@ class CentBeta(LatentDist):
         out = lp.sum(dim=1)
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
-    def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None) -> torch.Tensor:
-        gen = torch.Generator(device=_device())
-        gen.manual_seed(_seed(seed) % (2 ** 63))
-        a, b = self._ab(self._params if params is None else params, _device())
-        conc = torch.stack([a.expand(nsamples, -1), b.expand(nsamples, -1)], dim=-1).contiguous()
-        g = torch._standard_gamma(conc, generator=gen)
-        s = g[..., 0] / (g[..., 0] + g[..., 1])
-        return (2.0 * float(self.B) * (s - 0.5)).contiguous()
+    def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None, *, device=None,
+                      row_offset: int = 0) -> torch.Tensor:
+        params = self._params if params is None else params
+        a = np.exp(np.asarray([float(np.asarray(p[0])) for p in params], np.float64)).astype(np.float32)
+        b = np.exp(np.asarray([float(np.asarray(p[1])) for p in params], np.float64)).astype(np.float32)
+        return _plan.sample_centbeta(nsamples, a, b, float(self.B), _seed(seed), _device(device), row_offset)
 
     def sample(self, params: Pytree, nsamples: int, seed: int = None):
         """[nsamples, input_dim] draws, 2B(Beta(a_i, b_i) - 0.5) (distributions.py:101-135)."""
@@ -187,14 +181,11 @@ class Tdist(LatentDist):
                - t * torch.log(1 + (1.0 / nu) * (u * u).sum(dim=1)))
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
-    def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None) -> torch.Tensor:
+    def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None, *, device=None,
+                      row_offset: int = 0) -> torch.Tensor:
         """mean + z / sqrt(chi2(nu) / nu) (distributions.py:360-392)."""
         nu = math.exp(float(np.asarray(self._params if params is None else params)))
-        gen = torch.Generator(device=_device())
-        gen.manual_seed(_seed(seed) % (2 ** 63))
-        z = torch.randn((nsamples, self.input_dim), generator=gen, device=_device())
-        chi2 = 2.0 * torch._standard_gamma(torch.full((nsamples,), nu / 2.0, device=_device()), generator=gen)
-        return z / torch.sqrt(chi2 / nu)[:, None]
+        return _plan.sample_tdist(nsamples, self.input_dim, nu, _seed(seed), _device(device), row_offset)
 
     def sample(self, params: Pytree, nsamples: int, seed: int = None):
         return self.sample_device(nsamples, seed, params).cpu().numpy()
@@ -219,15 +210,17 @@ class Joint(LatentDist):
         out = torch.stack([self.dists[i].log_prob(params[i], parts[i]) for i in range(len(self.dists))], dim=1).sum(dim=1)
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
-    def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None) -> torch.Tensor:
+    def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None, *, device=None,
+                      row_offset: int = 0) -> torch.Tensor:
         params = self._params if params is None else params
         seeds = np.random.default_rng(_seed(seed)).integers(0, int(1e9), size=len(self.dists))
         cols = []
+        kw = dict(device=device, row_offset=row_offset)
         for dist, p, sd in zip(self.dists, params, seeds):
             if isinstance(dist, (CentBeta, Tdist, Joint)):
-                cols.append(dist.sample_device(nsamples, int(sd), p).reshape(nsamples, -1))
+                cols.append(dist.sample_device(nsamples, int(sd), p, **kw).reshape(nsamples, -1))
             else:
-                cols.append(dist.sample_device(nsamples, int(sd)).reshape(nsamples, -1))
+                cols.append(dist.sample_device(nsamples, int(sd), **kw).reshape(nsamples, -1))
         return torch.cat(cols, dim=1).contiguous()
 
     def sample(self, params: Pytree, nsamples: int, seed: int = None):

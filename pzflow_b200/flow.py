@@ -22,7 +22,8 @@ import torch
 
 from . import distributions
 from .bijectors import Bijector_Info, Chain, InitFunction, Pytree, RollingSplineCoupling, ShiftBounds
-from .plan import Plan, PlanCache
+from . import sharding
+from .plan import Plan, PlanCache, host_result
 from .utils import build_bijector_from_info, gaussian_error_model
 
 
@@ -190,13 +191,31 @@ class Flow:
                           seed=seed)
 
     # ------------------------------------------------------------------ #
-    def _plan(self, params: Pytree = None) -> Plan:
-        """The fused device plan of (bijector, latent) for ``params`` on the current device."""
+    def _plan(self, params: Pytree = None, device: int = None) -> Plan:
+        """The fused device plan of (bijector, latent) for ``params`` on ``device`` (default: the current device)."""
         params = self._params if params is None else params
-        device = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        self._plan_cache.max_plans = max(self._plan_cache.max_plans, torch.cuda.device_count() if device >= 0 else 1)
         return self._plan_cache.get(
             (params[0], params[1]), device,
-            lambda: Plan(self._bijector_info, params[1], self._input_dim, self._latent_info, latent_params=params[0]))
+            lambda: Plan(self._bijector_info, params[1], self._input_dim, self._latent_info, latent_params=params[0],
+                         device=None if device < 0 else device))
+
+    def _device_plans(self, n_rows: int) -> dict:
+        """{device index: plan} a host-array call of ``n_rows`` rows (posterior: grid points) is sharded over inside
+        this process (pzflow_b200.sharding.process_devices); small calls stay on the current device (one entry).
+        The plans are resolved here, on the calling thread: the row blocks' worker threads only use them."""
+        devs = sharding.process_devices()
+        if len(devs) <= 1 or n_rows < sharding.MULTI_DEVICE_MIN_ROWS:
+            return {}
+        engine = self._plan().engine   # an explicit engine choice on the current device's plan carries over
+        plans = {}
+        for d in devs:
+            plans[d] = self._plan(device=d)
+            if plans[d].engine != engine:
+                plans[d].set_engine(engine)
+        return plans
 
     def _get_conditions(self, inputs: pd.DataFrame):
         """Standard-scaled conditions, or None for an unconditional flow -- the reference's
@@ -229,8 +248,18 @@ class Flow:
                         ccols = [inputs[c].to_numpy() for c in self.conditional_columns]
                         if not all(c.dtype == ctype and c.ndim == 1 for c in ccols):
                             ccols = [np.asarray(c, dtype=ctype) for c in ccols]
-                    return self._plan().log_prob_host_columns(cols, ccols, self._condition_means,
-                                                              self._condition_stds).numpy()
+                    plans = self._device_plans(len(inputs))
+                    if len(plans) <= 1:
+                        return self._plan().log_prob_host_columns(cols, ccols, self._condition_means,
+                                                                  self._condition_stds).numpy()
+                    out = host_result((len(inputs),))
+
+                    def block(dev, a, b):
+                        plans[dev].log_prob_host_columns(
+                            [c[a:b] for c in cols], None if ccols is None else [c[a:b] for c in ccols],
+                            self._condition_means, self._condition_stds, out=out[a:b])
+                    sharding.run_sharded(len(inputs), list(plans), block)
+                    return out.numpy()
             X = _pinned_f32(inputs[columns].to_numpy())
             conditions = self._get_conditions(inputs)
             return self._log_prob(self._params, X, conditions).cpu().numpy()
@@ -317,7 +346,16 @@ class Flow:
         plan = self._plan()
         conditions = self._get_conditions(inputs)
         rest = _pinned_f32(inputs[columns].to_numpy().reshape(nrows, -1))
-        pdfs = plan.posterior_host(rest, idx, grid, conditions, normalize=normalize, nan_to_zero=nan_to_zero)
+        plans = self._device_plans(nrows * len(grid))
+        if len(plans) <= 1:
+            pdfs = plan.posterior_host(rest, idx, grid, conditions, normalize=normalize, nan_to_zero=nan_to_zero)
+            return pdfs.numpy()
+        pdfs = host_result((nrows, len(grid)))   # galaxies are independent (per-galaxy normalisation, flow.py:734)
+
+        def block(dev, a, b):
+            plans[dev].posterior_host(rest[a:b], idx, grid, None if conditions is None else conditions[a:b],
+                                      normalize=normalize, nan_to_zero=nan_to_zero, out=pdfs[a:b])
+        sharding.run_sharded(nrows, list(plans), block)
         return pdfs.numpy()
 
     def _posterior_marginalized(self, inputs, column, columns, idx, grid, marg_rules, normalize, nan_to_zero,
@@ -404,12 +442,27 @@ class Flow:
             cond = np.repeat(cond, nsamples, axis=0)
             n = cond.shape[0]
 
-        plan = self._plan()
-        if isinstance(self.latent, (distributions.CentBeta, distributions.Tdist, distributions.Joint)):
-            u = self.latent.sample_device(n, seed, self._params[0])  # latents with parameters
+        seed = int(np.random.randint(1e18)) if seed is None else int(seed)   # one seed for every row block
+        with_params = isinstance(self.latent, (distributions.CentBeta, distributions.Tdist, distributions.Joint))
+
+        def draw(dev, a, b):
+            kw = dict(device=torch.device("cuda", dev), row_offset=a)
+            if with_params:
+                return self.latent.sample_device(b - a, seed, self._params[0], **kw)  # latents with parameters
+            return self.latent.sample_device(b - a, seed, **kw)  # draws stay on the device
+        plans = self._device_plans(n)
+        if len(plans) <= 1:
+            plan = self._plan()
+            x = self._inverse_to_host(plan, draw(plan.device_index, 0, n), cond)
         else:
-            u = self.latent.sample_device(n, seed)  # draws stay on the device
-        x = self._inverse_to_host(plan, u, cond)
+            buf = np.empty((self._input_dim, n), dtype=np.float32)   # the frame's own column-major layout
+
+            def block(dev, a, b):
+                with torch.cuda.device(dev):
+                    plans[dev].inverse_to_host_columns(draw(dev, a, b), None if cond is None else cond[a:b],
+                                                       out=buf[:, a:b])
+            sharding.run_sharded(n, list(plans), block)
+            x = buf.T
         # x is a fresh array in the frame's own (column-major) layout: copy=False lets pandas wrap it as it is
         if self.conditional_columns is None:
             return pd.DataFrame(x, columns=self.data_columns, copy=False)

@@ -328,7 +328,8 @@ class Plan:
         N.check(N.lib().pzb_log_prob_host(self._h, _ptr(X), _ptr(cond), X.shape[0], _ptr(out)))
         return out
 
-    def log_prob_host_columns(self, data_cols, cond_cols=None, cond_means=None, cond_stds=None) -> torch.Tensor:
+    def log_prob_host_columns(self, data_cols, cond_cols=None, cond_means=None, cond_stds=None,
+                              out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Flow.log_prob from float64 (or float32) DataFrame COLUMNS (one contiguous 1-D array per column): the
         down-cast to float32, the row gather and the condition scaling run inside the pipelined C call
         (pzb_log_prob_host_columns / _f32).  Returns a CPU tensor [N]."""
@@ -354,7 +355,8 @@ class Plan:
                                         dtype=np.float32)[: self.n_conditions]
         dptr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
         cptr = (C.c_void_p * max(1, len(ccols)))(*[c.ctypes.data for c in ccols]) if ccols else None
-        out = host_result((n,))
+        if out is None:
+            out = host_result((n,))
         call = N.lib().pzb_log_prob_host_columns_f32 if f32 else N.lib().pzb_log_prob_host_columns
         N.check(call(
             self._h, dptr, cptr, means.ctypes.data if means is not None else None,
@@ -382,14 +384,17 @@ class Plan:
                                                 torch.cuda.current_stream(self.device).cuda_stream))
         return X, ld
 
-    def inverse_to_host_columns(self, U, cond=None) -> np.ndarray:
+    def inverse_to_host_columns(self, U, cond=None, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Like inverse_to_host, but returns the samples as a NumPy array of shape [N, D] whose memory is
         COLUMN-major (the transpose of a C-contiguous [D, N] buffer): `pd.DataFrame(x, columns=...)` wraps that
-        without copying (pzb_inverse_to_host_columns)."""
+        without copying (pzb_inverse_to_host_columns).  ``out``: a float32 [D, N] array whose rows are contiguous
+        (e.g. a column slice of a bigger [D, N_total] buffer) to write into."""
         U = self._rows(U, self.input_dim, "inputs")
         cond = self._cond(cond, U.shape[0])
         n = U.shape[0]
-        buf = np.empty((self.input_dim, n), dtype=np.float32)
+        buf = np.empty((self.input_dim, n), dtype=np.float32) if out is None else out
+        if buf.dtype != np.float32 or buf.shape != (self.input_dim, n) or (n > 1 and buf.strides[1] != 4):
+            raise ValueError(f"out must be a float32 array of shape ({self.input_dim}, {n}) with contiguous rows")
         cols = (C.c_void_p * self.input_dim)(*[buf[j].ctypes.data for j in range(self.input_dim)])
         with torch.cuda.device(self.device):
             N.check(N.lib().pzb_inverse_to_host_columns(self._h, _ptr(U), _ptr(cond), n, cols,
@@ -665,13 +670,45 @@ def normalize_pdfs_(pdfs: torch.Tensor, grid: torch.Tensor, normalize: bool, nan
     return pdfs
 
 
-def sample_uniform(n: int, dim: int, B: float, seed: int, device=None) -> torch.Tensor:
-    """U(-B, B)^dim latent draws from the library's Philox stream (not jax's threefry)."""
+def sample_uniform(n: int, dim: int, B: float, seed: int, device=None, row_offset: int = 0) -> torch.Tensor:
+    """U(-B, B)^dim latent draws from the library's Philox stream (not jax's threefry).  ``row_offset``: index of the
+    first row in the caller's whole array (a sharded call draws what one big call would)."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     out = torch.empty((n, dim), dtype=torch.float32, device=device)
     with torch.cuda.device(device):
-        N.check(N.lib().pzb_sample_uniform(_ptr(out), n, dim, float(B), int(seed) & (2 ** 64 - 1),
+        N.check(N.lib().pzb_sample_uniform(_ptr(out), n, dim, float(B), int(seed) & (2 ** 64 - 1), int(row_offset),
                                            _stream(device)))
+    return out
+
+
+def sample_centbeta(n: int, a, b, B: float, seed: int, device=None, row_offset: int = 0) -> torch.Tensor:
+    """2B (Beta(a_j, b_j) - 0.5) latent draws [n, len(a)] from the library's Philox streams (pzb_sample_centbeta)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    a = np.ascontiguousarray(a, dtype=np.float32).ravel()
+    b = np.ascontiguousarray(b, dtype=np.float32).ravel()
+    out = torch.empty((n, len(a)), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        N.check(N.lib().pzb_sample_centbeta(_ptr(out), n, len(a), a.ctypes.data, b.ctypes.data, float(B),
+                                            int(seed) & (2 ** 64 - 1), int(row_offset), _stream(device)))
+    return out
+
+
+def sample_normal(n: int, dim: int, seed: int, device=None, row_offset: int = 0) -> torch.Tensor:
+    """Standard normal latent draws [n, dim] (pzb_sample_normal)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((n, dim), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        N.check(N.lib().pzb_sample_normal(_ptr(out), n, dim, int(seed) & (2 ** 64 - 1), int(row_offset), _stream(device)))
+    return out
+
+
+def sample_tdist(n: int, dim: int, nu: float, seed: int, device=None, row_offset: int = 0) -> torch.Tensor:
+    """Multivariate-t latent draws [n, dim], unit scale matrix, nu degrees of freedom (pzb_sample_tdist)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((n, dim), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        N.check(N.lib().pzb_sample_tdist(_ptr(out), n, dim, float(nu), int(seed) & (2 ** 64 - 1), int(row_offset),
+                                         _stream(device)))
     return out
 
 

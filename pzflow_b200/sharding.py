@@ -85,3 +85,86 @@ def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
         return node
     except (OSError, ValueError, AttributeError, RuntimeError):
         return None
+
+
+# ---------------------------------------------------------------------------------------------
+# One process, several GPUs: what a pzflow user gets without torchrun.  Flow.log_prob / posterior / sample cut their
+# host arrays into contiguous row blocks (shard_rows), one per device, and run the blocks' host pipelines
+# concurrently from one host thread each (the C calls release the GIL).  No collective: every block lands in its own
+# slice of the caller's result.  Rows are independent, so the result equals the one-GPU result bit for bit.
+# ---------------------------------------------------------------------------------------------
+MULTI_DEVICE_MIN_ROWS = 1 << 21   # below this one GPU is faster than waking the others (plans, streams, staging)
+
+_devices_override = None
+
+
+def set_devices(devices) -> None:
+    """Devices the in-process sharding may use: ``"all"``, a list of CUDA device indices, or None for the default
+    (environment variable PZFLOW_B200_DEVICES = "all" | "0,1,..." | "current"; unset: every visible device unless this
+    process is one rank of a multi-process launch, which owns exactly its current device)."""
+    global _devices_override
+    _devices_override = devices
+
+
+def process_devices() -> list:
+    """CUDA device indices this process shards host-array calls over (always at least the current device)."""
+    if not torch.cuda.is_available():
+        return []
+    cur = torch.cuda.current_device()
+    spec = _devices_override if _devices_override is not None else os.environ.get("PZFLOW_B200_DEVICES")
+    n = torch.cuda.device_count()
+    if spec is None:
+        launched = int(os.environ.get("WORLD_SIZE", "1") or 1) > 1 or (dist.is_available() and dist.is_initialized())
+        return [cur] if launched else list(range(n))
+    if isinstance(spec, str):
+        spec = spec.strip().lower()
+        if spec == "all":
+            return list(range(n))
+        if spec in ("current", ""):
+            return [cur]
+        spec = [int(x) for x in spec.split(",") if x.strip()]
+    out = [int(d) for d in spec if 0 <= int(d) < n]
+    return out or [cur]
+
+
+def shard_bounds(n: int, parts: int, multiple: int = 4) -> list:
+    """[(start, stop)] of ``parts`` contiguous blocks whose starts are multiples of ``multiple`` rows (the latent
+    samplers draw in blocks of four values); empty blocks are dropped."""
+    out = []
+    for r in range(parts):
+        a, b = shard_rows(n, r, parts)
+        a = min(n, (a + multiple - 1) // multiple * multiple) if r else 0
+        b = min(n, (b + multiple - 1) // multiple * multiple) if r + 1 < parts else n
+        if b > a:
+            out.append((a, b))
+    return out
+
+
+def run_sharded(n_rows: int, devices: list, fn) -> None:
+    """fn(device_index, start, stop) for every device's row block, concurrently, one host thread per device; each
+    thread gets its share of the host cores for the pipeline's casts and staging copies (pzb_set_host_threads)."""
+    from . import _native as N
+    blocks = shard_bounds(n_rows, len(devices))
+    if len(blocks) <= 1:
+        for (a, b) in blocks:
+            fn(devices[0], a, b)
+        return
+    import threading
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    share = max(1, min(16, cores // len(blocks)))
+    errors = []
+
+    def work(dev, a, b):
+        try:
+            N.check(N.lib().pzb_set_host_threads(share))
+            fn(dev, a, b)
+        except BaseException as exc:   # re-raised in the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(devices[i], a, b), daemon=True) for i, (a, b) in enumerate(blocks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]

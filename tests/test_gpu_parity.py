@@ -788,6 +788,38 @@ def test_uniform_sampler():
     assert not torch.equal(u, sample_uniform(200_000, 7, 5.0, seed=4))
 
 
+def test_native_latent_draws_follow_their_distributions():
+    """CentBeta13 / CentBeta / Normal / Tdist draws come from the library's own Philox kernels:
+    Kolmogorov-Smirnov distance to the distribution the reference draws from (pzflow/distributions.py:101-135, 196-229,
+    277-303, 360-392), reproducible per seed, different per seed and per column."""
+    from scipy import stats
+    from pzflow_b200 import distributions as Dz
+    from pzflow_b200.plan import launch_count
+    n = 200_000
+    l0 = launch_count()
+    u = Dz.CentBeta13(3, 5).sample((), n, seed=7)
+    assert u.shape == (n, 3) and np.abs(u).max() < 5.0
+    for j in range(3):
+        assert stats.kstest((u[:, j] + 5.0) / 10.0, stats.beta(13, 13).cdf).statistic < 0.005
+    assert abs(np.corrcoef(u[:, 0], u[:, 1])[0, 1]) < 0.01
+    assert np.array_equal(u, Dz.CentBeta13(3, 5).sample((), n, seed=7))
+    assert not np.array_equal(u, Dz.CentBeta13(3, 5).sample((), n, seed=8))
+    cb = Dz.CentBeta(2, 4)
+    cb_params = ((np.log(0.6), np.log(2.5)), (np.log(7.0), np.log(0.8)))     # shapes below one take the boost path
+    v = cb.sample(cb_params, n, seed=1)
+    assert stats.kstest((v[:, 0] + 4.0) / 8.0, stats.beta(0.6, 2.5).cdf).statistic < 0.005
+    assert stats.kstest((v[:, 1] + 4.0) / 8.0, stats.beta(7.0, 0.8).cdf).statistic < 0.005
+    z = Dz.Normal(5).sample((), n, seed=2)
+    assert stats.kstest(z.ravel(), stats.norm.cdf).statistic < 0.003 and abs(np.corrcoef(z[:, 0], z[:, 1])[0, 1]) < 0.01
+    t = Dz.Tdist(3).sample(np.log(4.5), n, seed=3)
+    assert stats.kstest(t[:, 1], stats.t(4.5).cdf).statistic < 0.005
+    # one chi2 per ROW: |t|^2 / 3 is F(3, nu) distributed, which independent columns would not give
+    assert stats.kstest((t * t).sum(axis=1) / 3.0, stats.f(3, 4.5).cdf).statistic < 0.005
+    assert launch_count() - l0 == 8          # every draw above was one kernel of this library
+    j = Dz.Joint(Dz.Uniform(1, 5), Dz.CentBeta13(2, 5), Dz.Normal(1)).sample([(), ((0.0, 0.0),) * 2, ()], 1000, seed=5)
+    assert j.shape == (1000, 4)
+
+
 # --------------------------------------------------------------------------- #
 # host-buffer entry points (pzb_*_host): chunked H2D | kernel | D2H pipeline    #
 # --------------------------------------------------------------------------- #
@@ -1615,3 +1647,43 @@ def test_marg_rules_with_error_samples_and_conditions():
     noisy = flow.posterior(zero, column="a", grid=grid, marg_rules=rules, err_samples=16, seed=1)
     np.testing.assert_allclose(np.trapezoid(noisy, grid, axis=1), 1.0, rtol=1e-5)
     assert np.abs(noisy - base).max() > 1e-3
+
+
+# --------------------------------------------------------------------------- #
+# one process, several GPUs                                #
+# --------------------------------------------------------------------------- #
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_shards_host_arrays_over_all_gpus(monkeypatch):
+    """Flow.log_prob / posterior / sample of a plain process use every visible GPU (contiguous row blocks, one host
+    pipeline per device, no collective) and return, bit for bit, what one GPU returns."""
+    from pzflow_b200 import sharding
+    from pzflow_b200.examples import get_example_flow
+    from pzflow_b200 import Flow
+    from pzflow_b200.bijectors import Chain, RollingSplineCoupling, ShiftBounds
+    monkeypatch.setattr(sharding, "MULTI_DEVICE_MIN_ROWS", 10_000)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    flow = get_example_flow()
+    X = F.galaxy_rows(60_011, seed=5)
+    df = pd.DataFrame(X.astype(np.float64), columns=flow.data_columns)
+    grid = np.linspace(0, 2.3, 50).astype(np.float32)
+    sharding.set_devices([0])
+    lp1, pdf1, s1 = flow.log_prob(df), flow.posterior(df.iloc[:2000], "redshift", grid), flow.sample(40_003, seed=9)
+    sharding.set_devices("all")
+    assert len(flow._device_plans(60_011)) == torch.cuda.device_count()
+    lpn, pdfn, sn = flow.log_prob(df), flow.posterior(df.iloc[:2000], "redshift", grid), flow.sample(40_003, seed=9)
+    assert np.array_equal(lp1.view(np.int32), lpn.view(np.int32))
+    assert np.array_equal(pdf1.view(np.int32), pdfn.view(np.int32))
+    assert np.array_equal(s1.to_numpy().view(np.int32), sn.to_numpy().view(np.int32))
+    # conditional flow with the default (CentBeta13) latent: conditions travel with their row block
+    rng = np.random.default_rng(1)
+    cf = Flow(data_columns=("a", "b", "c"), conditional_columns=("p", "q"),
+              bijector=Chain(ShiftBounds(-np.ones(3), np.ones(3), 4.0), RollingSplineCoupling(3, n_conditions=2)))
+    cdf = pd.DataFrame({"a": rng.uniform(-1, 1, 30_000), "b": rng.uniform(-1, 1, 30_000), "c": rng.uniform(-1, 1, 30_000),
+                        "p": rng.normal(size=30_000), "q": rng.normal(size=30_000)})
+    sharding.set_devices([0])
+    c1, cs1 = cf.log_prob(cdf), cf.sample(2, conditions=cdf.iloc[:12_000], seed=3)
+    sharding.set_devices("all")
+    cn, csn = cf.log_prob(cdf), cf.sample(2, conditions=cdf.iloc[:12_000], seed=3)
+    sharding.set_devices(None)
+    assert np.array_equal(c1.view(np.int32), cn.view(np.int32))
+    assert np.array_equal(cs1.to_numpy().view(np.int64), csn.to_numpy().view(np.int64))

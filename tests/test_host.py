@@ -497,3 +497,40 @@ def test_ensemble_sample_composition_matches_reference_golden(monkeypatch):
     both = ens.sample(4, seed=int(z["seed"]), returnEnsemble=True)
     assert tuple(both.shape) == tuple(z["return_ensemble_shape"])
     assert [k for k, _ in both.index] == list(z["return_ensemble_keys"])
+
+
+def test_shard_bounds_cover_the_rows_in_blocks_of_four():
+    for n in (0, 1, 3, 4, 5, 1000, 10_000_019):
+        for parts in (1, 2, 3, 8):
+            blocks = sharding.shard_bounds(n, parts)
+            assert [a for a, _ in blocks] == sorted(a for a, _ in blocks)
+            covered = 0
+            for a, b in blocks:
+                assert a == covered and b > a and a % 4 == 0
+                covered = b
+            assert covered == n
+            if n >= 4 * parts:
+                sizes = [b - a for a, b in blocks]
+                assert len(blocks) == parts and max(sizes) - min(sizes) <= 8
+
+
+def test_process_devices_policy(monkeypatch):
+    import torch
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "device_count", lambda: 4)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 2)
+    monkeypatch.delenv("PZFLOW_B200_DEVICES", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    sharding.set_devices(None)
+    assert sharding.process_devices() == [0, 1, 2, 3]           # a plain process: every visible device
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    assert sharding.process_devices() == [2]                    # one rank of torchrun owns its current device
+    monkeypatch.setenv("PZFLOW_B200_DEVICES", "0,3")
+    assert sharding.process_devices() == [0, 3]
+    monkeypatch.setenv("PZFLOW_B200_DEVICES", "current")
+    assert sharding.process_devices() == [2]
+    sharding.set_devices("all")
+    assert sharding.process_devices() == [0, 1, 2, 3]
+    sharding.set_devices([1, 9])
+    assert sharding.process_devices() == [1]
+    sharding.set_devices(None)
