@@ -38,6 +38,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def build_variant(name: str, defines) -> str:
+    """An experimental build with extra -D flags -> pzflow_b200/libpzflow_b200_<name>.so (select it with the
+    PZFLOW_B200_LIB environment variable)."""
+    out = os.path.join(HERE, f"libpzflow_b200_{name}.so")
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        print(res.stdout + res.stderr, file=sys.stderr)
+        raise RuntimeError(f"nvcc failed building variant {name}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB

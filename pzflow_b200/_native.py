@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpzflow_b200.so")
+# PZFLOW_B200_LIB: another build of the same library (kernel experiments, A/B runs); default: the in-tree build
+LIB_PATH = os.environ.get("PZFLOW_B200_LIB") or os.path.join(_HERE, "libpzflow_b200.so")
 
 PZB_OK = 0
 PZB_ERR_INVALID = -1

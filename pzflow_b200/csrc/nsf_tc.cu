@@ -223,17 +223,18 @@ struct TcShared {
 };
 
 struct TcSmem {  // byte offsets from the 1024-aligned base
-  int w2, w3, w1, par, state, shared, total;
+  int w2, w3, w1, par, state, acc, shared, total;
 };
 
-__host__ __device__ inline TcSmem tc_smem_layout(int max_pass, int chunk_tiles, int state_cols) {
+__host__ __device__ inline TcSmem tc_smem_layout(int max_pass, int chunk_tiles, int state_cols, int acc_floats = 0) {
   TcSmem s;
   s.w2 = 0;
   s.w3 = TC_W2_BYTES;
   s.w1 = s.w3 + max_pass * TC_W3_PASS_BYTES;
   s.par = s.w1 + TC_W1_BYTES;
   s.state = s.par + 2 * TC_PAR_BYTES;
-  s.shared = s.state + chunk_tiles * TC_TILE * state_cols * 4;
+  s.acc = s.state + chunk_tiles * TC_TILE * state_cols * 4;
+  s.shared = s.acc + acc_floats * 4;
   s.shared = (s.shared + 15) / 16 * 16;
   s.total = s.shared + (int)sizeof(TcShared);
   return s;
@@ -241,10 +242,67 @@ __host__ __device__ inline TcSmem tc_smem_layout(int max_pass, int chunk_tiles, 
 
 struct TcLaunch {
   int chunk_tiles, max_pass, state_cols, n_lev;
+  // fused posterior reduction (LaunchArgs::fuse): a unit = one galaxy = unit_rows = max(V,1) * max(S,1) * G consecutive rows.
+  //   upc > 0: a chunk holds upc whole units (unit_rows <= chunk rows);
+  //   cpu > 0: a unit spans cpu chunks of spc samples (of G rows) each, all walked by the same CTA, sums kept in shared memory.
+  int unit_rows, upc, cpu, spc;
+  long long n_units;
 };
+
+// rows [row0, row0 + nrows) of the ci-th chunk of this CTA; unit0 = its first unit, sub = which part of a long unit
+__device__ __forceinline__ void tc_chunk_span(const TcLaunch& lp, const LaunchArgs& a, int ci, long long& row0, int& nrows,
+                                              long long& unit0, int& sub) {
+  const long long CR = (long long)lp.chunk_tiles * TC_TILE;
+  sub = 0;
+  if (lp.unit_rows == 0) {
+    row0 = ((long long)blockIdx.x + (long long)ci * gridDim.x) * CR;
+    nrows = (int)min(CR, a.N - row0);
+    unit0 = 0;
+  } else if (lp.upc > 0) {
+    unit0 = ((long long)blockIdx.x + (long long)ci * gridDim.x) * lp.upc;
+    row0 = unit0 * lp.unit_rows;
+    nrows = (int)(min((long long)lp.upc, lp.n_units - unit0) * lp.unit_rows);
+  } else {
+    unit0 = (long long)blockIdx.x + (long long)(ci / lp.cpu) * gridDim.x;
+    sub = ci % lp.cpu;
+    const int vs = lp.unit_rows / a.G;
+    row0 = unit0 * lp.unit_rows + (long long)sub * lp.spc * a.G;
+    nrows = min(lp.spc, vs - sub * lp.spc) * a.G;
+  }
+}
+__device__ __forceinline__ int tc_my_chunks(const TcLaunch& lp, const LaunchArgs& a) {
+  const long long CR = (long long)lp.chunk_tiles * TC_TILE;
+  long long n;  // chunks (or units) handed out round robin over the CTAs
+  if (lp.unit_rows == 0) n = (a.N + CR - 1) / CR;
+  else if (lp.upc > 0) n = (lp.n_units + lp.upc - 1) / lp.upc;
+  else n = lp.n_units;
+  const int mine = n > blockIdx.x ? (int)((n - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  return (lp.unit_rows != 0 && lp.upc == 0) ? mine * lp.cpu : mine;
+}
+
+__device__ __forceinline__ float tc_nan_to_num0(float v) {
+  if (isnan(v)) return 0.0f;
+  if (v == INFINITY) return 3.4028234663852886e38f;
+  if (v == -INFINITY) return -3.4028234663852886e38f;
+  return v;
+}
 
 
 #define TC_BAR(field) (sh_addr + (uint32_t)offsetof(TcShared, field))
+
+// Wait of the four warps of one (group, half) on an mbarrier.  With PZB_TC_LEADER_WAIT only the half's first warp
+// watches the mbarrier (try_wait compiles to a SYNCS / NANOSLEEP / BRA polling loop: a quarter of all executed
+// instructions of the first version of this kernel); the other three block on a hardware named barrier, which issues
+// nothing while it waits.
+#ifdef PZB_TC_LEADER_WAIT
+#define TC_HALF_WAIT(bar, parity)                              \
+  do {                                                         \
+    if ((warp & 3) == 0) mbar_wait((bar), (parity));           \
+    named_bar_sync(4 + 2 * grp + half, TC_TILE);               \
+  } while (0)
+#else
+#define TC_HALF_WAIT(bar, parity) mbar_wait((bar), (parity))
+#endif
 
 #ifdef PZB_TC_TRACE
 // debug build only: SM-clock timestamps of the epilogue phases of CTA 0, second coupling stage of its first chunk
@@ -282,7 +340,8 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B, derived by pointer arithmetic so loads stay LDS (not generic LD)
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols);
+  const bool fuse = lp.unit_rows > 0;
+  const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols, (fuse && lp.upc == 0) ? 2 * args.G : 0);
   TcShared* sh = reinterpret_cast<TcShared*>(base + sl.shared);
   const uint32_t sh_addr = smem_u32(sh);
   float* state = reinterpret_cast<float*>(base + sl.state);
@@ -335,9 +394,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
   tc_fence_after();
   const uint32_t tbase = sh->tmem_base;
 
-  const long long chunk_rows = (long long)CR;
-  const long long n_chunks = (args.N + chunk_rows - 1) / chunk_rows;
-  const int my_chunks = (int)((n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x);  // blockIdx.x < n_chunks
+  const int my_chunks = tc_my_chunks(lp, args);
 
   if (warp < 16) {
     // ======================================= epilogue warps =======================================
@@ -366,8 +423,9 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       }
 
     for (int ci = 0; ci < my_chunks; ++ci) {
-      const long long row0 = ((long long)blockIdx.x + (long long)ci * gridDim.x) * chunk_rows;
-      const int nrows = (int)min(chunk_rows, args.N - row0);
+      long long row0, unit0;
+      int nrows, sub;
+      tc_chunk_span(lp, args, ci, row0, nrows, unit0, sub);
       const int ntiles = max(2, (nrows + TC_TILE - 1) / TC_TILE);
       const int my_tiles = (ntiles - grp + 1) / 2;
 
@@ -470,7 +528,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
 
             // ---- E1: h1 = LeakyReLU(D1) (bias already in the GEMM), rewritten in place over this half's 64 columns of X ----
             TC_TRACE(0);
-            mbar_wait(bar_d1, ph_d1);
+            TC_HALF_WAIT(bar_d1, ph_d1);
             ph_d1 ^= 1u;
             tc_fence_after();
 #pragma unroll 1
@@ -498,7 +556,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               const float s2inv = par[TC_PF_SCAL];
 #pragma unroll 1
               for (int bt = 0; bt < 2; ++bt) {
-                mbar_wait(bar_d2 + 8u * bt, ph_d2);  // this quarter of the hidden GEMM has landed
+                TC_HALF_WAIT(bar_d2 + 8u * bt, ph_d2);  // this quarter of the hidden GEMM has landed
                 tc_fence_after();
                 if (bt == 0) TC_TRACE(2);
                 float dv[32];
@@ -533,7 +591,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             float ldsum = 0.0f;
 #pragma unroll 1
             for (int d = half; d < L; d += 2) {
-              mbar_wait(bar_d3, ph_d3);
+              TC_HALF_WAIT(bar_d3, ph_d3);
               ph_d3 ^= 1u;
               tc_fence_after();
               TC_TRACE(d < 2 ? 4 : 6);
@@ -560,7 +618,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             srow[(COL_PEND + half) * CR] = INV ? -ldsum : ldsum;
             if (half == kw) {
               // every output pass of this tile has completed, so Y is free: write the next tile's key operand
-              mbar_wait(bar_g3, ph_g3);
+              TC_HALF_WAIT(bar_g3, ph_g3);
               if (more) {
                 tc_fence_after();
                 write_keys(k + 1);
@@ -590,13 +648,97 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         if (args.mode == MODE_LOGPROB || args.mode == MODE_POSTERIOR) {
           const float lat = pz_latent_logprob(plan, [&](int j) { return st[plan->perm_final[j] * CR]; });
           const float lpv = pz_nan_to_num_lp(lat + st[D * CR]);
-          args.out0[row] = (args.mode == MODE_POSTERIOR) ? expf(lpv) : lpv;
+          if (fuse) st[COL_PEND * CR] = (args.mode == MODE_POSTERIOR) ? expf(lpv) : lpv;  // reduced below, in shared memory
+          else args.out0[row] = (args.mode == MODE_POSTERIOR) ? expf(lpv) : lpv;
         } else {
           for (int j = 0; j < D; ++j) args.out0[row * D + j] = st[(INV ? j : plan->perm_final[j]) * CR];
           if (args.out1 != nullptr) args.out1[row] = st[D * CR];
         }
       }
       // (pass A of the next chunk touches a row from the same thread as pass Z did: no barrier needed)
+      if (fuse) {
+        // ---- posterior reduction: mean over the error samples, sum over the variants, per-galaxy trapezoid, NaN -> 0
+        // (pzflow/flow.py:720-737, 651-654), by all 16 epilogue warps, before the ONLY write of the pdfs to HBM ----
+        named_bar_sync(1, TC_EPI_THREADS);
+        const float* P = state + COL_PEND * CR;
+        const int G = args.G, S = max(args.S, 1), V = max(args.V, 1);
+        const bool inner_nan0 = args.V > 0 && args.nan_to_zero != 0;  // an inner call's nan_to_num, per variant
+        const bool lme = args.mode == MODE_LOGPROB;  // log(mean_s exp(lp)) of a row's error samples (flow.py:463-464), G == 1
+        const int etid = (int)tid;
+        auto finish = [&](const float* Yg, long long unit) {  // one warp: trapezoid of Yg[0, G), then the galaxy's pdf
+          float integral = 1.0f;
+          if (args.normalize) {
+            float part = 0.0f;
+            for (int i = lane; i + 1 < G; i += 32) part += (args.grid[i + 1] - args.grid[i]) * (Yg[i + 1] + Yg[i]);
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            integral = 0.5f * part;
+          }
+          return integral;
+        };
+        if (lp.upc > 0) {
+          float* Y = state + (COL_PEND + 1) * CR;
+          const int RU = lp.unit_rows, nunits = nrows / RU;
+          for (int e = etid; e < nunits * G; e += TC_EPI_THREADS) {
+            const int u = e / G, g = e - u * G;
+            const float* pu = P + u * RU + g;
+            float tot = 0.0f;
+            for (int v = 0; v < V; ++v) {
+              float sm = lme ? expf(pu[(v * S) * G]) : pu[(v * S) * G];
+              for (int k = 1; k < S; ++k) sm += lme ? expf(pu[(v * S + k) * G]) : pu[(v * S + k) * G];
+              float y = (S > 1 || lme) ? sm / (float)S : sm;
+              if (inner_nan0) y = tc_nan_to_num0(y);
+              tot = v == 0 ? y : tot + y;
+            }
+            if (lme) args.out0[unit0 + u] = logf(tot);
+            else Y[e] = tot;
+          }
+          named_bar_sync(1, TC_EPI_THREADS);
+          for (int u = warp; u < nunits && !lme; u += TC_EPI_THREADS / 32) {
+            const float* Yg = Y + u * G;
+            const float integral = finish(Yg, unit0 + u);
+            float* dst = args.out0 + (unit0 + u) * (long long)G;
+            for (int i = lane; i < G; i += 32) {
+              float y = Yg[i];
+              if (args.normalize) y = y / integral;
+              if (args.nan_to_zero) y = tc_nan_to_num0(y);
+              dst[i] = y;
+            }
+          }
+        } else {
+          float* accS = reinterpret_cast<float*>(base + sl.acc);
+          float* accV = accS + G;
+          const int nsamp = nrows / G, j0 = sub * lp.spc;
+          for (int g = etid; g < G; g += TC_EPI_THREADS) {
+            float aS = accS[g], aV = accV[g];
+            for (int j = 0; j < nsamp; ++j) {
+              const int si = j0 + j, k = si % S, v = si / S;
+              const float pv = lme ? expf(P[j * G + g]) : P[j * G + g];
+              aS = k == 0 ? pv : aS + pv;
+              if (k == S - 1) {
+                float y = (S > 1 || lme) ? aS / (float)S : aS;
+                if (inner_nan0) y = tc_nan_to_num0(y);
+                aV = v == 0 ? y : aV + y;
+              }
+            }
+            accS[g] = aS;
+            accV[g] = aV;
+          }
+          if (sub == lp.cpu - 1 && lme) {
+            if (etid == 0) args.out0[unit0] = logf(accV[0]);
+          } else if (sub == lp.cpu - 1) {
+            named_bar_sync(1, TC_EPI_THREADS);
+            const float integral = finish(accV, unit0);  // every warp computes the same sum in the same order
+            float* dst = args.out0 + unit0 * (long long)G;
+            for (int g = etid; g < G; g += TC_EPI_THREADS) {
+              float y = accV[g];
+              if (args.normalize) y = y / integral;
+              if (args.nan_to_zero) y = tc_nan_to_num0(y);
+              dst[g] = y;
+            }
+          }
+        }
+        named_bar_sync(1, TC_EPI_THREADS);  // P / Y / the sums are free again before the next chunk's first stage ends
+      }
     }
   } else {
     // control warps run converged (all 32 lanes wait on the mbarriers); one elected lane issues
@@ -609,8 +751,9 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
     };
     auto sub_of = [&](int s) -> int { return __shfl_sync(0xffffffffu, (int)sh->sub[s % n_seq], 0); };
     auto tiles_of = [&](int s) -> int {
-      const long long row0 = ((long long)blockIdx.x + (long long)(s / n_seq) * gridDim.x) * chunk_rows;
-      const int nrows = (int)min(chunk_rows, args.N - row0);
+      long long row0, unit0;
+      int nrows, sub;
+      tc_chunk_span(lp, args, s / n_seq, row0, nrows, unit0, sub);
       return max(2, (nrows + TC_TILE - 1) / TC_TILE);
     };
     if (warp < 18) {
@@ -773,35 +916,96 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
   }
 }
 
-cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms, void* workspace,
-                      cudaStream_t stream) {
-  (void)workspace;
-  TcLaunch lp;
+static int tc_fit_tiles(const TcLaunch& lp, int acc_floats) {
+  int fit = TC_MAX_CHUNK_TILES;
+  while (fit > 2 && tc_smem_layout(lp.max_pass, fit, lp.state_cols, acc_floats).total + 1024 > TC_SMEM_MAX) --fit;
+  return fit - (fit & 1);  // the two epilogue groups take alternate tiles: keep the count even
+}
+
+static void tc_base_launch(const PlanDev& hp, TcLaunch& lp) {
   lp.max_pass = 1;
   for (int s = 0; s < hp.n_nsc; ++s) lp.max_pass = max(lp.max_pass, (min(hp.nsc[s].L, TC_L_MAX) + 1) / 2);
   lp.n_lev = tc_log_det_levels(hp);
   lp.state_cols = hp.D + lp.n_lev + 2 + hp.C;
-  // rows per chunk: as many 128-row tiles as shared memory holds, fewer when that leaves SMs idle
-  int fit = TC_MAX_CHUNK_TILES;
-  while (fit > 2 && tc_smem_layout(lp.max_pass, fit, lp.state_cols).total + 1024 > TC_SMEM_MAX) --fit;
-  const long long tiles_total = (args.N + TC_TILE - 1) / TC_TILE;
-  long long want = (tiles_total + num_sms - 1) / num_sms;
-  if (want < 2) want = 2;
-  lp.chunk_tiles = (int)(want < fit ? want : fit);
-  // the two epilogue groups take alternate tiles: an odd tile count leaves one group idle for a whole tile per stage
-  if (lp.chunk_tiles > 2 && (lp.chunk_tiles & 1)) lp.chunk_tiles -= (want > fit) ? 1 : -1;
-  if (lp.chunk_tiles > fit) lp.chunk_tiles = fit - (fit & 1);
-  const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols);
+  lp.unit_rows = lp.upc = lp.cpu = lp.spc = 0;
+  lp.n_units = 0;
+}
+
+// Can the posterior of n_units galaxies (V variants x S error samples x G grid points each) be reduced inside the
+// kernel?  0 = no (the caller takes the scratch + reduction-kernel route), 1 = whole galaxies per chunk, 2 = a galaxy
+// spans several chunks of one CTA.
+int tc_fuse_mode(const PlanDev& hp, int G, int V, int S, long long n_units, int num_sms) {
+  if (!tc_plan_supported(hp) || G < 1 || n_units < 1) return 0;
+  TcLaunch lp;
+  tc_base_launch(hp, lp);
+  const long long RU = (long long)(V > 0 ? V : 1) * (S > 0 ? S : 1) * G;
+  if (RU <= (long long)tc_fit_tiles(lp, 0) * TC_TILE) return 1;
+  // long galaxies are dealt to the CTAs whole: few of them would leave most SMs idle
+  if ((long long)G <= (long long)tc_fit_tiles(lp, 2 * G) * TC_TILE && n_units >= 2ll * num_sms) return 2;
+  return 0;
+}
+
+cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms, void* workspace,
+                      cudaStream_t stream) {
+  (void)workspace;
+  TcLaunch lp;
+  tc_base_launch(hp, lp);
+  long long n_work;  // chunks (or whole long galaxies) to deal out
+  int acc_floats = 0;
+  if (args.fuse) {
+    if (args.mode != MODE_POSTERIOR && !(args.mode == MODE_LOGPROB && args.G == 1)) return cudaErrorInvalidValue;
+    const int V = args.V > 0 ? args.V : 1, S = args.S > 0 ? args.S : 1;
+    const long long RU = (long long)V * S * args.G;
+    lp.n_units = args.N / RU;
+    lp.unit_rows = (int)RU;
+    const int fit = tc_fit_tiles(lp, 0);
+    if (RU <= (long long)fit * TC_TILE) {
+      // whole galaxies per chunk: as many as fit, fewer when that leaves SMs idle
+      long long upc = (long long)fit * TC_TILE / RU;
+      const long long spread = (lp.n_units + num_sms - 1) / num_sms;
+      if (upc > spread) upc = spread;
+      if (upc < 1) upc = 1;
+      lp.upc = (int)upc;
+      int tiles = (int)((upc * RU + TC_TILE - 1) / TC_TILE);
+      tiles += tiles & 1;
+      lp.chunk_tiles = tiles < 2 ? 2 : tiles;
+      n_work = (lp.n_units + upc - 1) / upc;
+    } else {
+      acc_floats = 2 * args.G;
+      const int fit2 = tc_fit_tiles(lp, acc_floats);
+      if ((long long)args.G > (long long)fit2 * TC_TILE) return cudaErrorInvalidConfiguration;
+      lp.spc = fit2 * TC_TILE / args.G;
+      const int vs = V * S;
+      lp.cpu = (vs + lp.spc - 1) / lp.spc;
+      lp.spc = (vs + lp.cpu - 1) / lp.cpu;  // even out the parts
+      lp.cpu = (vs + lp.spc - 1) / lp.spc;
+      int tiles = (int)(((long long)lp.spc * args.G + TC_TILE - 1) / TC_TILE);
+      tiles += tiles & 1;
+      lp.chunk_tiles = tiles < 2 ? 2 : tiles;
+      n_work = lp.n_units;
+    }
+  } else {
+    // rows per chunk: as many 128-row tiles as shared memory holds, fewer when that leaves SMs idle
+    const int fit = tc_fit_tiles(lp, 0);
+    const long long tiles_total = (args.N + TC_TILE - 1) / TC_TILE;
+    long long want = (tiles_total + num_sms - 1) / num_sms;
+    if (want < 2) want = 2;
+    lp.chunk_tiles = (int)(want < fit ? want : fit);
+    // the two epilogue groups take alternate tiles: an odd tile count leaves one group idle for a whole tile per stage
+    if (lp.chunk_tiles > 2 && (lp.chunk_tiles & 1)) lp.chunk_tiles -= (want > fit) ? 1 : -1;
+    if (lp.chunk_tiles > fit) lp.chunk_tiles = fit;
+    const long long chunk_rows = (long long)lp.chunk_tiles * TC_TILE;
+    n_work = (args.N + chunk_rows - 1) / chunk_rows;
+  }
+  const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols, acc_floats);
   const size_t smem = (size_t)sl.total + 1024;
   if (smem > (size_t)TC_SMEM_MAX) return cudaErrorInvalidConfiguration;
   const bool inv = (args.mode == MODE_INVERSE);
   cudaError_t e = inv ? cudaFuncSetAttribute(nsf_chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                       : cudaFuncSetAttribute(nsf_chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const long long chunk_rows = (long long)lp.chunk_tiles * TC_TILE;
-  const long long n_chunks = (args.N + chunk_rows - 1) / chunk_rows;
   long long grid = num_sms;
-  if (grid > n_chunks) grid = n_chunks;
+  if (grid > n_work) grid = n_work;
   if (grid < 1) grid = 1;
   if (inv)
     nsf_chain_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, lp);

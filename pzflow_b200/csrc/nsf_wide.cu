@@ -225,6 +225,28 @@ __device__ __forceinline__ void wd_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_
       : "memory");
 }
 
+__device__ __forceinline__ uint32_t wd_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void wd_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA bulk copy global -> the same shared-memory offset of every CTA in `mask`, completing on each one's mbarrier
+__device__ __forceinline__ void wd_tma_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset of every CTA in `mask`
+__device__ __forceinline__ void wd_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 // 32 un-normalised softmax terms of one axis (as softmax_terms, K = 32)
 __device__ __forceinline__ void softmax_terms32(const float (&raw)[32], const float* __restrict__ bias, float sinv,
                                                 float (&e)[32]) {
@@ -385,6 +407,8 @@ struct WdShared {
 
 struct WdLaunch {
   int n_slots, par_max, state_cols, n_lev;
+  int cluster;  // CTAs per cluster (1, 2, 4 or 8): every CTA fetches 1 / cluster of each slab and multicasts it to all
+  int debug;    // experiments only (PZB_WIDE_DEBUG; results are garbage): 1 = skip the spline arithmetic, 2 = fetch 1 KB per slab
 };
 struct WdSmem {
   int ring, par, state, shared, total;
@@ -421,7 +445,7 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
   if (tid == 0) {
     for (int i = 0; i < n_slots; ++i) {
       mbar_init(WD_BAR(slot_full[0]) + 8u * i, 1);
-      mbar_init(WD_BAR(slot_free[0]) + 8u * i, 1);
+      mbar_init(WD_BAR(slot_free[0]) + 8u * i, lp.cluster);  // every CTA of the cluster has consumed the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(WD_BAR(par_full[0]) + 8u * i, 1);
@@ -458,12 +482,18 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
   }
   tc_fence_before();
   __syncthreads();
+  if (lp.cluster > 1) wd_cluster_sync();  // every CTA's mbarriers are initialised before a peer's copy or commit may hit them
   tc_fence_after();
   const uint32_t tbase = sh->tmem_base;
   const int n_seq = sh->n_seq;
 
+  // The CTAs of a cluster share every slab they fetch, so they walk the SAME number of tiles (the last round may hold
+  // tiles past the end: those run on zero rows and write nothing).
   const long long n_tiles = (args.N + WD_TILE - 1) / WD_TILE;
-  const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // blockIdx.x < n_tiles
+  const int my_tiles = lp.cluster > 1 ? (int)((n_tiles + gridDim.x - 1) / gridDim.x)
+                                      : (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const uint32_t crank = lp.cluster > 1 ? wd_cluster_rank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << lp.cluster) - 1u);
 
   if (warp < 8) {
     // ======================================= epilogue warps =======================================
@@ -485,7 +515,7 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
 
     for (int ti = 0; ti < my_tiles; ++ti) {
       const long long row0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * WD_TILE;
-      const int nrows = (int)min((long long)WD_TILE, args.N - row0);
+      const int nrows = (int)max(0ll, min((long long)WD_TILE, args.N - row0));
       const long long row = row0 + lrow;
       bool overflowed = false;
 
@@ -609,7 +639,14 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
           mbar_wait(bar_d3, ph_d3);
           ph_d3 ^= 1u;
           tc_fence_after();
-          if (kp32) {
+          if (lp.debug & 1) {
+            float raw[16];
+            tmem_ld16(t_acc, raw);
+            tc_wait_ld();
+            tc_fence_before();
+            warp_arrive(bar_free, lane);
+            ldsum += raw[0];
+          } else if (kp32) {
             const int col = low_col[p];
             const float xin = srow[col * CR];
             float y, ldd;
@@ -716,7 +753,8 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
             for (int k16 = 0; k16 < k1_16; ++k16)
               wd_mma(tP + 128u * nh, tQ + (prod == 0 ? 16u : 0u) + a_col_of(k16),
                      (prod == 1 ? dl : dh) + (uint64_t)(k16 * 16), idesc128, !(prod == 0 && k16 == 0));
-          umma_commit(WD_BAR(slot_free[0]) + 8u * slot);
+          if (lp.cluster > 1) wd_commit_multicast(WD_BAR(slot_free[0]) + 8u * slot, cmask);
+          else umma_commit(WD_BAR(slot_free[0]) + 8u * slot);
           if (hp2 == 2) {
             umma_commit(WD_BAR(h_full[0]) + 8u * nh);
           } else {
@@ -748,7 +786,8 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
                 for (int kl = 0; kl < 4; ++kl)
                   wd_mma(dst + 128u * nh, src + (prod == 0 ? 16u : 0u) + a_col_of(4 * kb + kl),
                          (prod == 1 ? dl : dh) + (uint64_t)(kl * 2), idesc128, !(kb == 0 && prod == 0 && kl == 0));
-              umma_commit(WD_BAR(slot_free[0]) + 8u * slot);
+              if (lp.cluster > 1) wd_commit_multicast(WD_BAR(slot_free[0]) + 8u * slot, cmask);
+              else umma_commit(WD_BAR(slot_free[0]) + 8u * slot);
               if (kb == kbn - 1) {
                 if (hp2 == 2) {
                   umma_commit(WD_BAR(h_full[0]) + 8u * nh);
@@ -788,7 +827,8 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
                 for (int kl = 0; kl < 4; ++kl)
                   wd_mma(acc + 128u * b, src + (prod == 0 ? 16u : 0u) + a_col_of(4 * kb + kl),
                          (prod == 1 ? dl : dh) + (uint64_t)(kl * 2), idesc96, !(kb == 0 && prod == 0 && kl == 0));
-              umma_commit(WD_BAR(slot_free[0]) + 8u * slot);
+              if (lp.cluster > 1) wd_commit_multicast(WD_BAR(slot_free[0]) + 8u * slot, cmask);
+              else umma_commit(WD_BAR(slot_free[0]) + 8u * slot);
               if (kb == kbn - 1) umma_commit(WD_BAR(d3_full[0]) + 8u * b);
             }
             __syncwarp();
@@ -821,17 +861,25 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
       const int n_w1 = hp2, n_hid = (w.hl - 1) * hp2 * kbn, n_out = w.n_pass * kbn;
       const uint8_t* p = src + ((size_t)(w.par_bytes + 1023u) / 1024u * 1024u);
       for (int i = 0; i < n_w1 + n_hid + n_out; ++i) {
-        const uint32_t bytes = i < n_w1 ? w1_slab : (i < n_w1 + n_hid ? (uint32_t)WD_HID_SLAB : (uint32_t)WD_OUT_SLAB);
+        uint32_t bytes = i < n_w1 ? w1_slab : (i < n_w1 + n_hid ? (uint32_t)WD_HID_SLAB : (uint32_t)WD_OUT_SLAB);
+        const uint32_t stride = bytes;
+        if (lp.debug & 2) bytes = 1024u;
         const uint32_t slot = g % (uint32_t)n_slots;
         if (g >= (uint32_t)n_slots) mbar_wait(WD_BAR(slot_free[0]) + 8u * slot, ((g / (uint32_t)n_slots) - 1u) & 1u);
         const uint32_t bar = WD_BAR(slot_full[0]) + 8u * slot;
         if (lane == 0) {
-          mbar_expect_tx(bar, bytes);
-          for (uint32_t off = 0; off < bytes; off += 8192u)
-            tma_bulk_g2s(sb + slot * WD_SLOT_BYTES + off, p + off, min(8192u, bytes - off), bar);
+          mbar_expect_tx(bar, bytes);  // the whole slab lands here: this CTA's share and its peers'
+          if (lp.cluster > 1) {
+            const uint32_t part = bytes / (uint32_t)lp.cluster, o0 = crank * part;  // (slab sizes are multiples of 128 B x 8)
+            for (uint32_t off = 0; off < part; off += 8192u)
+              wd_tma_multicast(sb + slot * WD_SLOT_BYTES + o0 + off, p + o0 + off, min(8192u, part - off), bar, cmask);
+          } else {
+            for (uint32_t off = 0; off < bytes; off += 8192u)
+              tma_bulk_g2s(sb + slot * WD_SLOT_BYTES + off, p + off, min(8192u, bytes - off), bar);
+          }
         }
         __syncwarp();
-        p += bytes;
+        p += stride;
         ++g;
       }
     }
@@ -839,6 +887,7 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
 
   tc_fence_before();
   __syncthreads();
+  if (lp.cluster > 1) wd_cluster_sync();  // no CTA leaves while a peer's copies or commits can still land in it
   if (warp == 8) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "n"(512) : "memory");
   }
@@ -853,6 +902,10 @@ cudaError_t launch_wide(const PlanDev* d_plan, const PlanDev& hp, const LaunchAr
   lp.n_lev = tc_log_det_levels(hp);
   lp.state_cols = hp.D + lp.n_lev + 2 + hp.C + 1;  // x, log-det levels, pending halves, conditions, overflow flag
   lp.n_slots = WD_MAX_SLOTS;
+  if (const char* env = getenv("PZB_WIDE_SLOTS")) {  // experiments: cap the ring depth
+    const int cap = atoi(env);
+    if (cap >= 3 && cap < lp.n_slots) lp.n_slots = cap;
+  }
   while (lp.n_slots > 2 && wd_smem_layout(lp).total + 1024 > WD_SMEM_MAX) --lp.n_slots;
   const WdSmem sl = wd_smem_layout(lp);
   const size_t smem = (size_t)sl.total + 1024;
@@ -862,14 +915,44 @@ cudaError_t launch_wide(const PlanDev* d_plan, const PlanDev& hp, const LaunchAr
                       : cudaFuncSetAttribute(nsf_chain_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long n_tiles = (args.N + WD_TILE - 1) / WD_TILE;
-  long long grid = num_sms;
-  if (grid > n_tiles) grid = n_tiles;
-  if (grid < 1) grid = 1;
-  if (inv)
-    nsf_chain_wide_kernel<true><<<(unsigned)grid, WD_THREADS, smem, stream>>>(d_plan, args, lp, overflow_rows);
-  else
-    nsf_chain_wide_kernel<false><<<(unsigned)grid, WD_THREADS, smem, stream>>>(d_plan, args, lp, overflow_rows);
-  return cudaGetLastError();
+  // Clusters share their weight fetches (each CTA fetches 1 / cluster of a slab and multicasts it), which is what the
+  // L2 -> SM path needs: 148 CTAs streaming 1.8 MB per tile and stage on their own saturate it at half the tensor rate.
+  lp.cluster = 1;
+  lp.debug = 0;
+  if (const char* env = getenv("PZB_WIDE_DEBUG")) lp.debug = atoi(env);
+  if (const char* env = getenv("PZB_WIDE_CLUSTER")) {
+    const int c = atoi(env);
+    if (c == 1 || c == 2 || c == 4 || c == 8) lp.cluster = c;
+  }
+  long long grid = num_sms / lp.cluster * lp.cluster;
+  const long long want = (n_tiles + lp.cluster - 1) / lp.cluster * lp.cluster;
+  if (grid > want) grid = want;
+  if (grid < lp.cluster) grid = lp.cluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(WD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)lp.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (lp.cluster > 1) {
+    // a persistent grid must be co-resident: as many clusters as the device can hold at once (GPC boundaries can strand SMs)
+    int max_clusters = 0;
+    cudaLaunchConfig_t probe = cfg;
+    probe.gridDim = dim3((unsigned)(num_sms / lp.cluster * lp.cluster));
+    cudaError_t oe = inv ? cudaOccupancyMaxActiveClusters(&max_clusters, nsf_chain_wide_kernel<true>, &probe)
+                         : cudaOccupancyMaxActiveClusters(&max_clusters, nsf_chain_wide_kernel<false>, &probe);
+    if (oe != cudaSuccess) return oe;
+    if (max_clusters < 1) return cudaErrorInvalidConfiguration;
+    if ((long long)max_clusters * lp.cluster < grid) cfg.gridDim = dim3((unsigned)(max_clusters * lp.cluster));
+  }
+  if (inv) return cudaLaunchKernelEx(&cfg, nsf_chain_wide_kernel<true>, d_plan, args, lp, overflow_rows);
+  return cudaLaunchKernelEx(&cfg, nsf_chain_wide_kernel<false>, d_plan, args, lp, overflow_rows);
 }
 
 }  // namespace pzb

@@ -26,6 +26,7 @@ size_t tc_pack_bytes(const NscDev& st, int sub);
 void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* const* weights, void* dst);
 cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms,
                       void* workspace, cudaStream_t stream);
+int tc_fuse_mode(const PlanDev& hp, int G, int V, int S, long long n_units, int num_sms);
 bool wide_plan_supported(const PlanDev& hp);
 size_t wide_pack_bytes(const NscDev& st);
 void wide_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weights, void* dst);
@@ -733,6 +734,14 @@ static int launch_chain(const pzb_plan* plan, const LaunchArgs& args, void* stre
   return PZB_OK;
 }
 
+// Posterior launches whose reduction (mean over error samples, sum over variants, trapezoid normalisation, NaN -> 0)
+// can happen inside the tensor-core kernel: the pdfs then cross HBM once.  PZB_NO_FUSE=1 forces the scratch route.
+static bool posterior_fuses(const pzb_plan* plan, int G, int V, int S, int64_t Ng) {
+  const char* env = getenv("PZB_NO_FUSE");
+  if ((env != nullptr && atoi(env) != 0) || pzb_plan_engine(plan) != PZB_ENGINE_TC) return false;
+  return tc_fuse_mode(plan->host, G, V, S, Ng, plan->num_sms) != 0;
+}
+
 static int check_common(const pzb_plan* plan, const void* in, const float* cond, int64_t N,
                         const void* outp, const char* who) {
   if (!plan) return fail(PZB_ERR_INVALID, "%s: plan is NULL", who);
@@ -935,6 +944,12 @@ int pzb_posterior(const pzb_plan* plan, const float* rest, const float* cond, in
   a.col_idx = col_idx;
   a.N = Ng * (int64_t)G;
   a.out0 = pdfs;
+  if (posterior_fuses(plan, G, 0, 0, Ng)) {
+    a.fuse = 1;
+    a.normalize = normalize;
+    a.nan_to_zero = nan_to_zero;
+    return launch_chain(plan, a, stream);
+  }
   rc = launch_chain(plan, a, stream);
   if (rc) return rc;
   DeviceGuard guard(plan->device);
@@ -1184,8 +1199,9 @@ int pzb_log_prob_err(const pzb_plan* plan, const float* X, const float* Xerr, co
   int rc = check_common(plan, X, cond, N, out, "log_prob_err");
   if (rc) return rc;
   if (err_samples < 1) return fail(PZB_ERR_INVALID, "log_prob_err: err_samples must be positive");
-  if (N > 0 && scratch == nullptr) return fail(PZB_ERR_INVALID, "log_prob_err: scratch [N * err_samples] is NULL");
   if (N == 0) return PZB_OK;
+  const bool fused = posterior_fuses(plan, 1, 0, err_samples, N);
+  if (!fused && scratch == nullptr) return fail(PZB_ERR_INVALID, "log_prob_err: scratch [N * err_samples] is NULL");
   LaunchArgs a{};
   a.mode = MODE_LOGPROB;
   a.X = X;
@@ -1197,6 +1213,12 @@ int pzb_log_prob_err(const pzb_plan* plan, const float* X, const float* Xerr, co
   a.unit0 = row_offset;
   a.N = N * (int64_t)err_samples;
   a.out0 = scratch;
+  if (fused) {  // log(mean_s exp(lp)) taken in shared memory: no [N, S] scratch
+    a.fuse = 1;
+    a.G = 1;
+    a.out0 = out;
+    return launch_chain(plan, a, stream);
+  }
   rc = launch_chain(plan, a, stream);
   if (rc) return rc;
   DeviceGuard guard(plan->device);
@@ -1218,8 +1240,9 @@ int pzb_posterior_err(const pzb_plan* plan, const float* rest, const float* rest
   if (col_idx < 0 || col_idx >= plan->host.D)
     return fail(PZB_ERR_INVALID, "posterior_err: column index %d out of range", col_idx);
   if (err_samples < 1) return fail(PZB_ERR_INVALID, "posterior_err: err_samples must be positive");
-  if (Ng > 0 && scratch == nullptr) return fail(PZB_ERR_INVALID, "posterior_err: scratch [Ng * err_samples * G] is NULL");
   if (Ng == 0) return PZB_OK;
+  const bool fused = posterior_fuses(plan, G, 0, err_samples, Ng);
+  if (!fused && scratch == nullptr) return fail(PZB_ERR_INVALID, "posterior_err: scratch [Ng * err_samples * G] is NULL");
   LaunchArgs a{};
   a.mode = MODE_POSTERIOR;
   a.X = rest;
@@ -1234,6 +1257,13 @@ int pzb_posterior_err(const pzb_plan* plan, const float* rest, const float* rest
   a.unit0 = row_offset;
   a.N = Ng * (int64_t)err_samples * (int64_t)G;
   a.out0 = scratch;
+  if (fused) {
+    a.fuse = 1;
+    a.normalize = normalize;
+    a.nan_to_zero = nan_to_zero;
+    a.out0 = pdfs;
+    return launch_chain(plan, a, stream);
+  }
   rc = launch_chain(plan, a, stream);
   if (rc) return rc;
   DeviceGuard guard(plan->device);
@@ -1291,8 +1321,9 @@ int pzb_posterior_marg(const pzb_plan* plan, const float* rest, const float* res
     for (int r = 0; r < q; ++r)
       if (mcols[r] == mcols[q]) return fail(PZB_ERR_INVALID, "posterior_marg: column %d listed twice", mcols[q]);
   }
-  if (Ng > 0 && scratch == nullptr) return fail(PZB_ERR_INVALID, "posterior_marg: scratch [Ng * V * max(S, 1) * G] is NULL");
   if (Ng == 0) return PZB_OK;
+  const bool fused = posterior_fuses(plan, G, V, err_samples, Ng);
+  if (!fused && scratch == nullptr) return fail(PZB_ERR_INVALID, "posterior_marg: scratch [Ng * V * max(S, 1) * G] is NULL");
   const int S = err_samples > 0 ? err_samples : 1;
   LaunchArgs a{};
   a.mode = MODE_POSTERIOR;
@@ -1312,6 +1343,13 @@ int pzb_posterior_marg(const pzb_plan* plan, const float* rest, const float* res
   for (int q = 0; q < 4; ++q) a.mcol[q] = q < n_mcols ? mcols[q] : -1;
   a.N = Ng * (int64_t)V * (int64_t)S * (int64_t)G;
   a.out0 = scratch;
+  if (fused) {
+    a.fuse = 1;
+    a.normalize = 0;
+    a.nan_to_zero = nan_to_zero;
+    a.out0 = pdf_sums;
+    return launch_chain(plan, a, stream);
+  }
   rc = launch_chain(plan, a, stream);
   if (rc) return rc;
   DeviceGuard guard(plan->device);
@@ -1602,10 +1640,17 @@ static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
                  ? pzb_ensemble_posterior_mean(ens, job.n_flows, nu, job.G, a.grid, job.normalize, a.out0, hp.s_k)
                  : pzb_ensemble_logmeanexp(ens, job.n_flows, nu, a.out0, hp.s_k);
     } else {
+      // a single flow's posterior: reduced and normalised inside the tensor-core kernel where it can be
+      const bool fused = job.mode == MODE_POSTERIOR && posterior_fuses(plan, job.G, 0, 0, nu);
+      if (fused) {
+        a.fuse = 1;
+        a.normalize = job.normalize;
+        a.nan_to_zero = job.nan_to_zero;
+      }
       rc = launch_chain(plan, a, hp.s_k);
+      if (rc == PZB_OK && !fused && job.mode == MODE_POSTERIOR && (job.normalize || job.nan_to_zero))
+        rc = pzb_normalize_pdfs(a.out0, nu, job.G, a.grid, job.normalize, job.nan_to_zero, hp.s_k);
     }
-    if (rc == PZB_OK && job.n_flows == 0 && job.mode == MODE_POSTERIOR && (job.normalize || job.nan_to_zero))
-      rc = pzb_normalize_pdfs(a.out0, nu, job.G, a.grid, job.normalize, job.nan_to_zero, hp.s_k);
     if (rc != PZB_OK) break;
     cudaEventRecord(hp.ev_k[b], hp.s_k);
     cudaStreamWaitEvent(hp.s_out, hp.ev_k[b], 0);

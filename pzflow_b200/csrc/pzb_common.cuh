@@ -128,6 +128,10 @@ struct LaunchArgs {
   const float* mvals;
   int V, n_mcols;
   int mcol[4];
+  // Fused posterior reduction (tensor-core engine, MODE_POSTERIOR): out0 is the FINAL pdfs [units, G] -- the mean over
+  // the error samples, the sum over the variants, the per-galaxy trapezoid normalisation and NaN -> 0
+  // (pzflow/flow.py:720-737) happen in shared memory before the only HBM write.
+  int fuse, normalize, nan_to_zero;
 };
 
 // ---- counter-based normals for the error samples: Philox-4x32-10 keyed by the seed, counter =
