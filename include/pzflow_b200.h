@@ -308,6 +308,31 @@ int pzb_spline_train_backward(const float *logits, const float *x, const float *
                               const float *grad_log_det, int64_t N, int32_t L, int32_t K, float B,
                               int32_t periodic, float *grad_logits, float *grad_x, void *stream);
 
+/* ---- one optimisation step's gradient as ONE kernel (pzflow/flow.py:961-982, 1053-1084) ------------------------
+ * loss = -sum_rows(w * log_prob) / n_global of this rank's N rows and its gradient w.r.t. every conditioner weight:
+ * forward and backward through the whole chain in one launch (a CTA per 16 rows; hand-derived backward of the spline
+ * and of the dense layers; per-CTA partial gradients summed in a fixed order by a second kernel).  Parameters are
+ * read from the caller's FLAT buffer -- the stax pytree's leaves in traversal order, W[in, out] row-major then b[out]
+ * per dense layer (pzflow/utils.py:45-48) -- and flat_grad has the same layout, ready for one all-reduce over the
+ * data-parallel ranks and pzb_adam_step.
+ *   pzb_plan_train_supported: 1 for chains of ShiftBounds / StandardScaler / Scale / Roll / Reverse /
+ *     NeuralSplineCoupling (hidden_dim <= 256, (3K-1) * transformed columns <= 1024, K <= 64) with a Uniform,
+ *     CentBeta13 or Normal latent; everything else trains through the autograd route of pzflow_b200/train.py.
+ *   pzb_plan_set_train_layout: w_offsets / b_offsets [n_layers_total] = offset (in floats) of every dense layer's W
+ *     and b inside the flat buffer, coupling stages in chain order, layers in network order; the layers must cover
+ *     the n_params floats exactly.
+ *   pzb_train_workspace_floats: size of the device workspace a step of N rows needs (saved activations + partial
+ *     gradients).
+ *   pzb_train_step: writes flat_grad [n_params] (non-finite entries zeroed, as jnp.nan_to_num does for the reference's
+ *     update) and loss [1] (this rank's share of the loss; may be NULL).  Rows whose log_prob is not finite carry no
+ *     gradient. */
+int pzb_plan_train_supported(const pzb_plan *plan);
+int pzb_plan_set_train_layout(pzb_plan *plan, const int64_t *w_offsets, const int64_t *b_offsets, int32_t n_layers_total,
+                              int64_t n_params);
+int64_t pzb_train_workspace_floats(const pzb_plan *plan, int64_t N);
+int pzb_train_step(const pzb_plan *plan, const float *params, const float *X, const float *cond, const float *weights,
+                   int64_t N, int64_t n_global, float *workspace, float *flat_grad, float *loss, void *stream);
+
 /* Adam over one flat fp32 parameter buffer (optax.adam(1e-3) as pzflow/flow.py:968-981 uses it; eps_root = 0).
  * step_dev is a device int32 holding the number of steps taken so far; the call increments it on the stream
  * before the update, so the whole call can be captured in a CUDA graph. */

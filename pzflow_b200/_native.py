@@ -122,6 +122,11 @@ SIGNATURES = {
                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pzb_spline_train_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                             C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pzb_plan_train_supported": (C.c_int, [C.c_void_p]),
+    "pzb_plan_set_train_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64]),
+    "pzb_train_workspace_floats": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "pzb_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pzb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "pzb_log_prob_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

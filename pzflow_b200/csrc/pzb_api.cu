@@ -32,6 +32,14 @@ size_t wide_pack_bytes(const NscDev& st);
 void wide_pack_stage(const PlanDev& hp, const NscDev& st, const float* const* weights, void* dst);
 cudaError_t launch_wide(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms,
                         unsigned long long* overflow_rows, cudaStream_t stream);
+struct TrainOffsets {
+  long long w[MAX_DENSE], b[MAX_DENSE];
+};
+bool train_step_supported(const PlanDev& hp);
+size_t train_step_workspace_floats(const PlanDev& hp, long long N, long long n_params);
+cudaError_t launch_train_step(const PlanDev* d_plan, const PlanDev& hp, const TrainOffsets* d_offs, const float* params,
+                              const float* X, const float* cond, const float* w, long long N, float inv_n, long long n_params,
+                              float* workspace, float* flat_grad, float* loss, int num_sms, cudaStream_t stream);
 cudaError_t launch_spline_train_fwd(const float* logits, const float* x, long long n_elems, int K, float B, int periodic,
                                     float* y, float* ld, cudaStream_t stream);
 cudaError_t launch_spline_train_bwd(const float* logits, const float* x, const float* gy, const float* gld,
@@ -98,6 +106,8 @@ struct pzb_plan {
   bool tc_ok = false;
   bool wide_ok = false;
   unsigned long long* d_overflow = nullptr;  // rows whose logits came out non-finite on a tensor-core engine (fp16 range)
+  TrainOffsets* d_train_offs = nullptr;      // pzb_plan_set_train_layout: where each dense layer sits in the flat parameter buffer
+  long long train_params = 0;
   int engine = PZB_ENGINE_AUTO;
   bool latent_ready = true;
   mutable HostPipe pipe;
@@ -646,6 +656,7 @@ void pzb_plan_destroy(pzb_plan* plan) {
   if (plan->d_plan) cudaFree(plan->d_plan);
   if (plan->d_weights) cudaFree(plan->d_weights);
   if (plan->d_overflow) cudaFree(plan->d_overflow);
+  if (plan->d_train_offs) cudaFree(plan->d_train_offs);
   HostPipe& hp = plan->pipe;
   if (hp.ready) {
     cudaStreamSynchronize(hp.s_in);
@@ -1383,6 +1394,70 @@ int pzb_spline_train_backward(const float* logits, const float* x, const float* 
                                            grad_x, (cudaStream_t)stream);
   if (ce != cudaSuccess) return cuda_fail(ce, "spline_train_backward launch");
   g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
+// ---- the whole gradient of one optimisation step as one kernel (nsf_train_step.cu) ----
+int pzb_plan_train_supported(const pzb_plan* plan) { return plan && train_step_supported(plan->host) ? 1 : 0; }
+
+int pzb_plan_set_train_layout(pzb_plan* plan, const int64_t* w_offsets, const int64_t* b_offsets, int32_t n_layers_total,
+                              int64_t n_params) {
+  if (!plan || !w_offsets || !b_offsets) return fail(PZB_ERR_INVALID, "set_train_layout: NULL argument");
+  if (!train_step_supported(plan->host))
+    return fail(PZB_ERR_UNSUPPORTED, "set_train_layout: this chain is outside the fused training step's shapes");
+  const PlanDev& hp = plan->host;
+  int total = 0;
+  for (int s = 0; s < hp.n_nsc; ++s) total += hp.nsc[s].n_dense;
+  if (total != n_layers_total) return fail(PZB_ERR_INVALID, "set_train_layout: expected %d dense layers, got %d", total, n_layers_total);
+  std::vector<TrainOffsets> offs(hp.n_nsc);
+  long long covered = 0;
+  int q = 0;
+  for (int s = 0; s < hp.n_nsc; ++s) {
+    const NscDev& st = hp.nsc[s];
+    int in_dim = st.U + st.C;
+    for (int li = 0; li < st.n_dense; ++li, ++q) {
+      const int out_dim = li == st.n_dense - 1 ? st.cpd * st.L : st.H;
+      const long long wn = (long long)in_dim * out_dim;
+      if (w_offsets[q] < 0 || b_offsets[q] < 0 || w_offsets[q] + wn > n_params || b_offsets[q] + out_dim > n_params)
+        return fail(PZB_ERR_INVALID, "set_train_layout: layer %d does not fit the flat parameter buffer", q);
+      offs[s].w[li] = w_offsets[q];
+      offs[s].b[li] = b_offsets[q];
+      covered += wn + out_dim;
+      in_dim = st.H;
+    }
+  }
+  if (covered != n_params)
+    return fail(PZB_ERR_INVALID, "set_train_layout: the dense layers cover %lld of %lld parameters", covered, (long long)n_params);
+  DeviceGuard guard(plan->device);
+  if (!plan->d_train_offs) {
+    cudaError_t ce = cudaMalloc(reinterpret_cast<void**>(&plan->d_train_offs), sizeof(TrainOffsets) * MAX_NSC);
+    if (ce != cudaSuccess) return cuda_fail(ce, "set_train_layout");
+  }
+  cudaError_t ce = cudaMemcpy(plan->d_train_offs, offs.data(), sizeof(TrainOffsets) * hp.n_nsc, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) return cuda_fail(ce, "set_train_layout upload");
+  plan->train_params = n_params;
+  return PZB_OK;
+}
+
+int64_t pzb_train_workspace_floats(const pzb_plan* plan, int64_t N) {
+  if (!plan || N < 0 || plan->train_params <= 0) return -1;
+  return (int64_t)train_step_workspace_floats(plan->host, N, plan->train_params);
+}
+
+int pzb_train_step(const pzb_plan* plan, const float* params, const float* X, const float* cond, const float* weights,
+                   int64_t N, int64_t n_global, float* workspace, float* flat_grad, float* loss, void* stream) {
+  if (!plan || !plan->d_train_offs) return fail(PZB_ERR_INVALID, "train_step: call pzb_plan_set_train_layout first");
+  if (N < 0 || n_global < 1) return fail(PZB_ERR_INVALID, "train_step: bad row counts");
+  if (!params || !flat_grad || (N > 0 && (!X || !weights || !workspace)))
+    return fail(PZB_ERR_INVALID, "train_step: NULL buffer");
+  if (N > 0 && plan->host.C > 0 && !cond) return fail(PZB_ERR_INVALID, "train_step: this plan is conditional but conditions are NULL");
+  DeviceGuard guard(plan->device);
+  if (!guard.ok) return fail(PZB_ERR_CUDA, "cannot select device %d", plan->device);
+  cudaError_t ce = launch_train_step(plan->d_plan, plan->host, plan->d_train_offs, params, X, cond, weights, N,
+                                     1.0f / (float)n_global, plan->train_params, workspace, flat_grad, loss, plan->num_sms,
+                                     (cudaStream_t)stream);
+  if (ce != cudaSuccess) return cuda_fail(ce, "train_step launch");
+  g_launches.fetch_add(N > 0 ? 2 : 0);
   return PZB_OK;
 }
 

@@ -342,8 +342,85 @@ def shard_batch(n: int, rank: int, world: int) -> Tuple[int, int]:
     return a, a + base + (1 if rank < rem else 0)
 
 
+class FusedGradient:
+    """The gradient of one step as ONE hand-written kernel (``pzb_train_step``, csrc/nsf_train_step.cu): forward and
+    backward through the whole chain, a CTA per 16 rows, per-CTA partial weight gradients summed in a fixed order.
+    Reads the parameters from ``chain.flat`` and writes ``chain.flat_grad`` -- no autograd graph, no library GEMM.
+    ``FusedGradient.build`` returns None for chains outside the kernel's shapes (they keep the autograd route)."""
+
+    def __init__(self, chain: "TorchChain", plan, n_params: int):
+        self.chain, self.plan, self.n_params = chain, plan, n_params
+        self._ws = {}
+        self.loss = torch.zeros(1, dtype=torch.float32, device=chain.device)
+
+    @staticmethod
+    def _dense_offsets(info, params, flat, out):
+        """(W offset, b offset) of every dense layer, coupling stages in chain order (the order plan.flatten walks)."""
+        name, args = info
+        if name == "Chain":
+            for sub, p in zip(args, params):
+                FusedGradient._dense_offsets(sub, p, flat, out)
+        elif name == "RollingSplineCoupling":
+            full = tuple(args) + (None, 1, 16, 5, 2, 128, None, 0, False)[len(args):]
+            nlayers, shift, K, B, hl, hd, td, nc, periodic = full
+            nsc = ("NeuralSplineCoupling", (K, B, hl, hd, td, nc, periodic))
+            FusedGradient._dense_offsets(("Chain", (nsc, ("Roll", (shift,))) * nlayers), params, flat, out)
+        elif name == "NeuralSplineCoupling":
+            for layer in params:
+                if len(layer) == 2:
+                    W, b = layer
+                    out.append(((W.data_ptr() - flat.data_ptr()) // flat.element_size(),
+                                (b.data_ptr() - flat.data_ptr()) // flat.element_size()))
+
+    @classmethod
+    def build(cls, chain: "TorchChain"):
+        import ctypes as C
+        from . import _native as N
+        from .plan import Plan
+        if (chain.dtype != torch.float32 or not chain.flat.is_cuda or chain.latent_info[0] == "CentBeta"
+                or os.environ.get("PZB_TRAIN_AUTOGRAD", "0") != "0"):
+            return None
+        try:
+            lat, bij = chain.numpy_params()
+            with torch.cuda.device(chain.device):
+                plan = Plan(chain.info, bij, chain.D, chain.latent_info, device=chain.device.index, latent_params=lat)
+        except (NotImplementedError, ValueError):
+            return None
+        if not N.lib().pzb_plan_train_supported(plan._h):
+            return None
+        offs = []
+        cls._dense_offsets(chain.info, chain.params, chain.flat, offs)
+        w = (C.c_int64 * len(offs))(*[o[0] for o in offs])
+        b = (C.c_int64 * len(offs))(*[o[1] for o in offs])
+        N.check(N.lib().pzb_plan_set_train_layout(plan._h, w, b, len(offs), chain.flat.numel()))
+        return cls(chain, plan, chain.flat.numel())
+
+    def __call__(self, x, cond, w, n: int) -> None:
+        from ._native import check, lib
+        c = self.chain
+        rows = int(x.shape[0])
+        x = x.contiguous().float()
+        w = w.contiguous().float()
+        cond = None if (cond is None or self.plan.n_conditions == 0) else cond[:, : self.plan.n_conditions].contiguous().float()
+        ws = self._ws.get(rows)
+        if ws is None:
+            need = lib().pzb_train_workspace_floats(self.plan._h, rows)
+            ws = self._ws[rows] = torch.empty(max(1, need), dtype=torch.float32, device=c.device)
+        check(lib().pzb_train_step(self.plan._h, c.flat.data_ptr(), x.data_ptr() if rows else None,
+                                   cond.data_ptr() if cond is not None and rows else None, w.data_ptr() if rows else None,
+                                   rows, int(n), ws.data_ptr(), c.flat_grad.data_ptr(), self.loss.data_ptr(),
+                                   torch.cuda.current_stream(c.device).cuda_stream))
+
+
 def _grads(chain: TorchChain, x, cond, w, n: int) -> None:
     """flat_grad <- d/d params of -sum_local(w * log_prob) / n, non-finite entries zeroed, summed over ranks."""
+    fused = getattr(chain, "fused_gradient", None)
+    if fused is not None:
+        fused(x, cond, w, n)
+        d = _dist()
+        if d is not None:
+            d.all_reduce(chain.flat_grad, op=d.ReduceOp.SUM)
+        return
     chain.zero_grad()
     if x.shape[0] > 0:
         lp = chain.log_prob(x, cond)
@@ -454,6 +531,7 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
         flow._condition_stds = np.where(stds != 0, stds, 1).astype(np.float32)
 
     chain = TorchChain(flow._bijector_info, flow._params[1], flow._latent_info, flow._params[0], flow._input_dim, dev)
+    chain.fused_gradient = FusedGradient.build(chain)   # one kernel per step where the chain's shapes allow it
     opt = NativeAdam(chain, lr=1e-3) if optimizer is None else optimizer(chain.leaves)
     graphed: dict = {}
 

@@ -1768,3 +1768,88 @@ def test_marginal_variants_are_summed_inside_the_kernel():
         fused, plain = _both_routes(lambda: plan.posterior_marg(rest, 0, grid, [1, 6], mvals, err_samples=S, seed=3,
                                                                 rest_err=np.full_like(rest, 0.02) if S else None))
         np.testing.assert_allclose(fused, plain, rtol=5e-6, atol=1e-30)
+
+
+# --------------------------------------------------------------------------- #
+# the gradient of one optimisation step as one kernel      #
+# --------------------------------------------------------------------------- #
+def _f64_loss_and_grad(cfg, X, cond, w):
+    from pzflow_b200.train import TorchChain
+    chain = TorchChain(cfg["bijector_info"], cfg["params"][1], cfg["latent_info"], cfg["params"][0], cfg["input_dim"],
+                       torch.device("cuda"), dtype=torch.float64, native_spline=False)
+    lp = chain.log_prob(X.double(), None if cond is None else cond.double())
+    fin = torch.isfinite(lp)
+    loss = -(torch.where(fin, w.double() * lp, torch.zeros_like(lp))).sum() / len(X)
+    loss.backward()
+    return float(loss), _np(torch.cat([p.grad.reshape(-1) for p in chain.leaves]))
+
+
+@pytest.mark.parametrize("case", ["shipped", "conditional_centbeta", "deep_narrow"])
+def test_fused_training_step_gradient_against_float64_autograd(case):
+    """pzb_train_step (forward + backward through the whole chain in one kernel, hand-derived) against float64
+    autograd over the torch restatement: the loss, and the gradient of every weight."""
+    from pzflow_b200.train import FusedGradient, TorchChain
+    rng = np.random.default_rng(7)
+    if case == "shipped":
+        cfg = dict(F.example_flow(), input_dim=7)
+        X, cond = torch.from_numpy(F.galaxy_rows(1000, seed=21)).cuda(), None      # 62.5 tiles: a ragged last one
+    elif case == "conditional_centbeta":
+        ex = F.example_flow()
+        mins, maxs = ex["bijector_info"][1][0][1][0], ex["bijector_info"][1][0][1][1]
+        cfg = F.config_c4(1)[0]
+        X = torch.from_numpy(rng.uniform(mins + 0.1, maxs - 0.1, size=(777, 7)).astype(np.float32)).cuda()
+        cond = torch.from_numpy(rng.normal(size=(777, 2)).astype(np.float32)).cuda()
+    else:   # three hidden layers of 40, K = 5, odd column count, StandardScaler in front
+        info = ("Chain", (("StandardScaler", (np.linspace(-1, 1, 5).astype(np.float32), np.linspace(1, 2, 5).astype(np.float32))),
+                          F.rolling_info(3, 2, 5, 4, 3, 40)))
+        params = O.synth_bijector_params(info, 5, rng, out_scale=2.0)
+        cfg = dict(bijector_info=info, latent_info=("Normal", (5,)), params=((), params), input_dim=5)
+        X, cond = torch.from_numpy(rng.uniform(-3, 3, size=(333, 5)).astype(np.float32)).cuda(), None
+    w = torch.rand(len(X), device="cuda") + 0.5
+    chain = TorchChain(cfg["bijector_info"], cfg["params"][1], cfg["latent_info"], cfg["params"][0], cfg["input_dim"],
+                       torch.device("cuda"))
+    fused = FusedGradient.build(chain)
+    assert fused is not None
+    chain.flat_grad.fill_(float("nan"))
+    fused(X, cond, w, len(X))
+    got, loss = _np(chain.flat_grad).astype(np.float64), float(fused.loss.item())
+    want_loss, want = _f64_loss_and_grad(cfg, X, cond, w)
+    assert np.isfinite(got).all()
+    assert abs(loss - want_loss) <= 2e-4 * max(1.0, abs(want_loss))
+    assert np.linalg.norm(got - want) <= 5e-3 * np.linalg.norm(want), np.linalg.norm(got - want) / np.linalg.norm(want)
+    # the same call again: bit-identical (no atomics anywhere in the step)
+    first = chain.flat_grad.clone()
+    fused(X, cond, w, len(X))
+    assert torch.equal(first.view(torch.int32), chain.flat_grad.view(torch.int32))
+
+
+def test_fused_training_step_in_a_cuda_graph_and_launch_count():
+    """Flow.train's step with the fused gradient: graph replay == eager, bit for bit, and one step is four kernels of
+    this library (gradient, partial-sum reduction, Adam's counter, Adam) -- nothing else."""
+    from pzflow_b200.plan import launch_count
+    from pzflow_b200.train import FusedGradient, GraphedStep, NativeAdam, TorchChain, dp_step
+    ex = F.example_flow()
+    X = torch.from_numpy(F.galaxy_rows(6 * 512, seed=5)).cuda()
+    w = torch.rand(len(X), device="cuda") + 0.5
+
+    def mk():
+        chain = TorchChain(ex["bijector_info"], ex["params"][1], ex["latent_info"], ex["params"][0], 7, torch.device("cuda"))
+        chain.fused_gradient = FusedGradient.build(chain)
+        assert chain.fused_gradient is not None
+        return chain
+    out = []
+    for mode in ("graph", "eager"):
+        chain = mk()
+        opt = NativeAdam(chain)
+        step = GraphedStep(chain, opt, 512, 7, 0, 512) if mode == "graph" else None
+        for b in range(6):
+            xb, wb = X[b * 512:(b + 1) * 512], w[b * 512:(b + 1) * 512]
+            l0 = launch_count()
+            if step is not None:
+                step(xb, None, wb)
+            else:
+                dp_step(chain, opt, xb, None, wb)
+                assert launch_count() - l0 == 4
+        out.append(_np(chain.flat).copy())
+    assert np.abs(out[1] - _np(mk().flat)).max() > 1e-3
+    np.testing.assert_array_equal(out[0], out[1])
