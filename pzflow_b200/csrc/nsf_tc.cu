@@ -336,7 +336,8 @@ __device__ unsigned int g_tc_trace2[16 * 8];
 
 template <bool INV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch lp) {
+nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch lp,
+                    unsigned long long* __restrict__ overflow_rows) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B, derived by pointer arithmetic so loads stay LDS (not generic LD)
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -431,14 +432,25 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
 
       // ---- pass A: rows of this group's tiles -> state, steps in front of the first coupling stage ----
       // (the two groups never wait for each other: they only meet through the weight buffers)
-      for (int q = gtid; q < my_tiles * TC_TILE; q += TC_GROUP_THREADS) {
+      uint32_t in_ok = 0u;  // bit i: the i-th row this thread loads (and finishes in pass Z) has finite inputs
+      for (int q = gtid, it = 0; q < my_tiles * TC_TILE; q += TC_GROUP_THREADS, ++it) {
         const int r = (2 * (q >> 7) + grp) * TC_TILE + (q & (TC_TILE - 1));
         if (r >= nrows) continue;
         const long long row = row0 + r;
         float* st = state + r;
-        for (int j = 0; j < D; ++j) st[(INV ? plan->perm_final[j] : j) * CR] = pz_input_value(args, row, j, D);
+        float chk = 0.0f;
+        for (int j = 0; j < D; ++j) {
+          const float v = pz_input_value(args, row, j, D);
+          st[(INV ? plan->perm_final[j] : j) * CR] = v;
+          chk += v * 0.0f;   // NaN iff some input is NaN or infinite
+        }
         for (int l = 0; l < n_lev; ++l) st[(D + l) * CR] = 0.0f;
-        for (int j = 0; j < C; ++j) st[(COL_COND + j) * CR] = pz_cond_value(args, row, j, C);
+        for (int j = 0; j < C; ++j) {
+          const float v = pz_cond_value(args, row, j, C);
+          st[(COL_COND + j) * CR] = v;
+          chk += v * 0.0f;
+        }
+        in_ok |= (chk == 0.0f ? 1u : 0u) << it;
         int level = 0;
         light_steps_cols(plan, INV, 0, first_nsc, level, st, CR);
       }
@@ -637,7 +649,8 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       named_bar_sync(2 + grp, TC_GROUP_THREADS);
 
       // ---- pass Z: trailing steps, latent log-density, outputs of this group's tiles ----
-      for (int q = gtid; q < my_tiles * TC_TILE; q += TC_GROUP_THREADS) {
+      uint32_t n_bad = 0u;  // rows of finite inputs whose result is NaN: an fp16 overflow in a conditioner (see pzb_plan_overflow_rows)
+      for (int q = gtid, it = 0; q < my_tiles * TC_TILE; q += TC_GROUP_THREADS, ++it) {
         const int r = (2 * (q >> 7) + grp) * TC_TILE + (q & (TC_TILE - 1));
         if (r >= nrows) continue;
         const long long row = row0 + r;
@@ -645,6 +658,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         if (pending) st[(D + pend_level) * CR] += st[COL_PEND * CR] + st[(COL_PEND + 1) * CR];
         int lv = level;
         light_steps_cols(plan, INV, prev_end, ns, lv, st, CR);
+        n_bad += (st[D * CR] != st[D * CR] && ((in_ok >> it) & 1u)) ? 1u : 0u;
         if (args.mode == MODE_LOGPROB || args.mode == MODE_POSTERIOR) {
           const float lat = pz_latent_logprob(plan, [&](int j) { return st[plan->perm_final[j] * CR]; });
           const float lpv = pz_nan_to_num_lp(lat + st[D * CR]);
@@ -654,6 +668,10 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           for (int j = 0; j < D; ++j) args.out0[row * D + j] = st[(INV ? j : plan->perm_final[j]) * CR];
           if (args.out1 != nullptr) args.out1[row] = st[D * CR];
         }
+      }
+      if (overflow_rows != nullptr && __any_sync(0xffffffffu, n_bad != 0u)) {
+        for (int o = 16; o > 0; o >>= 1) n_bad += __shfl_xor_sync(0xffffffffu, n_bad, o);
+        if (lane == 0) atomicAdd(overflow_rows, (unsigned long long)n_bad);
       }
       // (pass A of the next chunk touches a row from the same thread as pass Z did: no barrier needed)
       if (fuse) {
@@ -947,7 +965,7 @@ int tc_fuse_mode(const PlanDev& hp, int G, int V, int S, long long n_units, int 
 
 cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs& args, int num_sms, void* workspace,
                       cudaStream_t stream) {
-  (void)workspace;
+  unsigned long long* overflow_rows = static_cast<unsigned long long*>(workspace);  // the plan's counter (may be null)
   TcLaunch lp;
   tc_base_launch(hp, lp);
   long long n_work;  // chunks (or whole long galaxies) to deal out
@@ -1008,9 +1026,9 @@ cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs
   if (grid > n_work) grid = n_work;
   if (grid < 1) grid = 1;
   if (inv)
-    nsf_chain_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, lp);
+    nsf_chain_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, lp, overflow_rows);
   else
-    nsf_chain_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, lp);
+    nsf_chain_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, lp, overflow_rows);
   return cudaGetLastError();
 }
 

@@ -439,7 +439,7 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
   const int warp = (int)(tid >> 5), lane = (int)(tid & 31);
   const int D = plan->D, C = plan->C, ns = plan->n_steps, n_lev = lp.n_lev;
   constexpr int CR = WD_TILE;
-  const int COL_PEND = D + n_lev, COL_COND = D + n_lev + 2, COL_FLAG = D + n_lev + 2 + C;
+  const int COL_PEND = D + n_lev, COL_COND = D + n_lev + 2;
   const int n_slots = lp.n_slots;
 
   if (tid == 0) {
@@ -517,13 +517,23 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
       const long long row0 = ((long long)blockIdx.x + (long long)ti * gridDim.x) * WD_TILE;
       const int nrows = (int)max(0ll, min((long long)WD_TILE, args.N - row0));
       const long long row = row0 + lrow;
-      bool overflowed = false;
+      bool in_ok = false;   // (half 0) this row's inputs are all finite
 
       // ---- pass A: the tile's rows -> state, steps in front of the first coupling stage (one thread per row) ----
       if (half == 0) {
         if (lrow < nrows) {
-          for (int j = 0; j < D; ++j) srow[(INV ? plan->perm_final[j] : j) * CR] = pz_input_value(args, row, j, D);
-          for (int j = 0; j < C; ++j) srow[(COL_COND + j) * CR] = pz_cond_value(args, row, j, C);
+          float chk = 0.0f;
+          for (int j = 0; j < D; ++j) {
+            const float v = pz_input_value(args, row, j, D);
+            srow[(INV ? plan->perm_final[j] : j) * CR] = v;
+            chk += v * 0.0f;   // NaN iff some input is NaN or infinite
+          }
+          for (int j = 0; j < C; ++j) {
+            const float v = pz_cond_value(args, row, j, C);
+            srow[(COL_COND + j) * CR] = v;
+            chk += v * 0.0f;
+          }
+          in_ok = chk == 0.0f;
         } else {
           for (int j = 0; j < D; ++j) srow[j * CR] = 0.0f;
           for (int j = 0; j < C; ++j) srow[(COL_COND + j) * CR] = 0.0f;
@@ -658,7 +668,7 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
                                  warp_arrive(bar_free, lane);
                                },
                                y, ldd, idx, fin);
-            overflowed = overflowed || !fin;
+            (void)fin;
             ldsum += ldd;
             srow[col * CR] = y;
             if (args.bins != nullptr && lrow < nrows)
@@ -681,7 +691,6 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
               float y, ldd;
               int idx;
               spline_dim<INV>(raw, b3 + d * 48, s3inv, xin, Bs, inv2B, periodic, y, ldd, idx);
-              overflowed = overflowed || !(ldd == ldd || idx < 0 || idx >= 16);
               ldsum += ldd;
               srow[col * CR] = y;
               if (args.bins != nullptr && lrow < nrows)
@@ -690,7 +699,6 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
           }
         }
         srow[(COL_PEND + half) * CR] = INV ? -ldsum : ldsum;
-        if (half == 1) srow[COL_FLAG * CR] = overflowed ? 1.0f : 0.0f;
         warp_arrive(WD_BAR(par_free[0]) + 8u * (seq & 1), lane);
         pending = true;
         pend_level = level;
@@ -699,17 +707,12 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
       named_bar_sync(1, WD_EPI_THREADS);
 
       // ---- pass Z: trailing steps, latent log-density, outputs (one thread per row) ----
-      if (half == 0 && overflow_rows != nullptr) {
-        // rows whose logits came out non-finite in some stage (an fp16 overflow of a pre-activation, or non-finite
-        // inputs): either half of the row may have seen it
-        const bool bad = (overflowed || srow[COL_FLAG * CR] != 0.0f) && lrow < nrows;
-        const unsigned m = __ballot_sync(0xffffffffu, bad);
-        if (lane == 0 && m != 0u) atomicAdd(overflow_rows, (unsigned long long)__popc(m));
-      }
+      bool bad_row = false;
       if (half == 0 && lrow < nrows) {
         if (pending) srow[(D + pend_level) * CR] += srow[COL_PEND * CR] + srow[(COL_PEND + 1) * CR];
         int lv = level;
         light_steps_cols(plan, INV, prev_end, ns, lv, srow, CR);
+        bad_row = in_ok && srow[D * CR] != srow[D * CR];   // finite inputs, NaN log-determinant: see pzb_plan_overflow_rows
         if (args.mode == MODE_LOGPROB || args.mode == MODE_POSTERIOR) {
           const float lat = pz_latent_logprob(plan, [&](int j) { return srow[plan->perm_final[j] * CR]; });
           const float lpv = pz_nan_to_num_lp(lat + srow[D * CR]);
@@ -718,6 +721,10 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
           for (int j = 0; j < D; ++j) args.out0[row * D + j] = srow[(INV ? j : plan->perm_final[j]) * CR];
           if (args.out1 != nullptr) args.out1[row] = srow[D * CR];
         }
+      }
+      if (half == 0 && overflow_rows != nullptr) {
+        const unsigned m = __ballot_sync(0xffffffffu, bad_row);
+        if (lane == 0 && m != 0u) atomicAdd(overflow_rows, (unsigned long long)__popc(m));
       }
       // (pass A of the next tile touches a row from the same thread as pass Z did: no barrier needed)
     }
@@ -900,7 +907,7 @@ cudaError_t launch_wide(const PlanDev* d_plan, const PlanDev& hp, const LaunchAr
   for (int s = 0; s < hp.n_nsc; ++s) lp.par_max = max(lp.par_max, wd_geom(hp.nsc[s]).par_bytes);
   lp.par_max = (lp.par_max + 127) / 128 * 128;
   lp.n_lev = tc_log_det_levels(hp);
-  lp.state_cols = hp.D + lp.n_lev + 2 + hp.C + 1;  // x, log-det levels, pending halves, conditions, overflow flag
+  lp.state_cols = hp.D + lp.n_lev + 2 + hp.C;  // x, log-det levels, pending halves, conditions
   lp.n_slots = WD_MAX_SLOTS;
   if (const char* env = getenv("PZB_WIDE_SLOTS")) {  // experiments: cap the ring depth
     const int cap = atoi(env);

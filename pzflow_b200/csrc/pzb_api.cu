@@ -52,6 +52,7 @@ cudaError_t launch_adam_step(float* p, const float* g, float* m, float* v, long 
 using namespace pzb;
 
 static thread_local std::string g_err = "";
+static thread_local bool g_force_simt = false;  // run_host's fp16 guard: re-evaluate this thread's job on the SIMT engine
 static std::atomic<long long> g_launches{0};
 
 static int fail(int code, const char* fmt, ...) {
@@ -106,6 +107,7 @@ struct pzb_plan {
   bool tc_ok = false;
   bool wide_ok = false;
   unsigned long long* d_overflow = nullptr;  // rows whose logits came out non-finite on a tensor-core engine (fp16 range)
+  mutable std::atomic<unsigned long long> overflow_seen{0};  // value of *d_overflow the host-buffer guard has already acted on
   TrainOffsets* d_train_offs = nullptr;      // pzb_plan_set_train_layout: where each dense layer sits in the flat parameter buffer
   long long train_params = 0;
   int engine = PZB_ENGINE_AUTO;
@@ -699,7 +701,10 @@ int pzb_plan_overflow_rows(const pzb_plan* plan, int32_t reset, int64_t* count) 
   if (!guard.ok) return fail(PZB_ERR_CUDA, "cannot select device %d", plan->device);
   unsigned long long v = 0;
   cudaError_t ce = cudaMemcpy(&v, plan->d_overflow, sizeof(v), cudaMemcpyDeviceToHost);  // (synchronises the device)
-  if (ce == cudaSuccess && reset) ce = cudaMemset(plan->d_overflow, 0, sizeof(v));
+  if (ce == cudaSuccess && reset) {
+    ce = cudaMemset(plan->d_overflow, 0, sizeof(v));
+    plan->overflow_seen.store(0);
+  }
   if (ce != cudaSuccess) return cuda_fail(ce, "overflow_rows");
   *count = (int64_t)v;
   return PZB_OK;
@@ -719,6 +724,7 @@ int pzb_plan_set_engine(pzb_plan* plan, int32_t engine) {
 
 int pzb_plan_engine(const pzb_plan* plan) {
   if (!plan) return -1;
+  if (g_force_simt) return PZB_ENGINE_SIMT;
   if (plan->engine == PZB_ENGINE_AUTO)
     return plan->tc_ok ? PZB_ENGINE_TC : (plan->wide_ok ? PZB_ENGINE_WIDE : PZB_ENGINE_SIMT);
   return plan->engine;
@@ -733,7 +739,7 @@ static int launch_chain(const pzb_plan* plan, const LaunchArgs& args, void* stre
   cudaError_t ce;
   const int engine = pzb_plan_engine(plan);
   if (engine == PZB_ENGINE_TC) {
-    ce = launch_tc(plan->d_plan, plan->host, args, plan->num_sms, nullptr, (cudaStream_t)stream);
+    ce = launch_tc(plan->d_plan, plan->host, args, plan->num_sms, plan->d_overflow, (cudaStream_t)stream);
   } else if (engine == PZB_ENGINE_WIDE) {
     ce = launch_wide(plan->d_plan, plan->host, args, plan->num_sms, plan->d_overflow, (cudaStream_t)stream);
   } else {
@@ -750,6 +756,14 @@ static int launch_chain(const pzb_plan* plan, const LaunchArgs& args, void* stre
 static bool posterior_fuses(const pzb_plan* plan, int G, int V, int S, int64_t Ng) {
   const char* env = getenv("PZB_NO_FUSE");
   if ((env != nullptr && atoi(env) != 0) || pzb_plan_engine(plan) != PZB_ENGINE_TC) return false;
+  if (V <= 0 && S <= 1) {
+    // A plain posterior has nothing to reduce but the trapezoid: fused, a galaxy of G = 1000 points fills 7.8 row
+    // tiles (24 idle rows) and both epilogue groups meet once per galaxy -- measured 6 % slower than the chain kernel
+    // followed by normalize_pdfs_kernel, whose two extra passes over the pdfs cost 0.1 % at 6.5 TB/s.  So the
+    // single-pass form is opt-in (PZB_FUSE_POSTERIOR=1) and bench.py reports it beside the default.
+    const char* on = getenv("PZB_FUSE_POSTERIOR");
+    if (on == nullptr || atoi(on) == 0) return false;
+  }
   return tc_fuse_mode(plan->host, G, V, S, Ng, plan->num_sms) != 0;
 }
 
@@ -1574,8 +1588,32 @@ static bool host_pointer_is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
+static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* who);
+
+// The fp16 guard of an AUTO-engine plan: the tensor-core engines carry activations as fp16 hi/lo pairs, so a
+// conditioner pre-activation beyond +-65504 turns a row into NaN where the reference's fp32 stays finite.  Such rows
+// (finite inputs, NaN log-determinant) are counted on the device; a host-buffer call that raised the counter is
+// evaluated again on the SIMT engine (fp32 throughout), so the caller gets the reference's answer either way.
 static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
   if (job.units == 0) return PZB_OK;
+  const bool guarded = plan->engine == PZB_ENGINE_AUTO && !g_force_simt && pzb_plan_engine(plan) != PZB_ENGINE_SIMT &&
+                       job.n_flows == 0;
+  int rc = run_host_once(plan, job, who);
+  if (rc != PZB_OK || !guarded) return rc;
+  unsigned long long now = 0;
+  {
+    DeviceGuard guard(plan->device);
+    if (cudaMemcpy(&now, plan->d_overflow, sizeof(now), cudaMemcpyDeviceToHost) != cudaSuccess) return PZB_OK;
+  }
+  const unsigned long long before = plan->overflow_seen.exchange(now);
+  if (now <= before) return PZB_OK;
+  g_force_simt = true;
+  rc = run_host_once(plan, job, who);
+  g_force_simt = false;
+  return rc;
+}
+
+static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* who) {
   HostPipe& hp = plan->pipe;
   std::lock_guard<std::mutex> lock(hp.mu);
   DeviceGuard guard(plan->device);

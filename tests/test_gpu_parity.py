@@ -428,11 +428,21 @@ def test_fp16_overflow_rows_are_counted():
     assert plan.overflow_rows(reset=True) == 0
     X[5, :2] = 3.0e6     # conditioner inputs ~1e6 x outside the box: |W1 x| > 65504
     X[200, 0] = -2.0e7
-    lp = _np(plan.log_prob(torch.from_numpy(X)))
+    X[100, 1] = np.nan   # a NaN input is NOT an overflow: the reference returns NaN for it too
+    lp = _np(plan.log_prob(torch.from_numpy(X).cuda()))
     assert plan.overflow_rows() == 2
-    assert zero_class(lp)[[5, 200]].all() and not zero_class(lp, LP_UNDERFLOW)[[4, 6, 199, 201]].any()
+    assert zero_class(lp)[[5, 100, 200]].all() and not zero_class(lp, LP_UNDERFLOW)[[4, 6, 199, 201]].any()
     plan.set_engine("simt")   # fp32 throughout: finite logits, the rows are merely out of bounds
-    plan.log_prob(torch.from_numpy(X))
+    lp_simt = _np(plan.log_prob(torch.from_numpy(X).cuda()))
+    # an AUTO plan's host-buffer calls notice the counter and re-evaluate on the SIMT engine: the reference's answer
+    plan.set_engine("auto")
+    assert plan.engine == "wide"
+    plan.overflow_rows(reset=True)
+    lp_host = plan.log_prob_host(X).numpy()
+    assert np.array_equal(lp_host.view(np.int32), lp_simt.view(np.int32))
+    Xok = np.delete(X, [5, 200], axis=0)
+    assert np.array_equal(plan.log_prob_host(Xok).numpy().view(np.int32),
+                          _np(plan.log_prob(torch.from_numpy(Xok).cuda())).view(np.int32))   # no overflow: no second pass
 
 
 @pytest.mark.parametrize("info,D,C", [
@@ -1705,12 +1715,14 @@ def _both_routes(fn):
     """fn() through the in-kernel reduction and through the scratch + reduction-kernel route (PZB_NO_FUSE=1)."""
     import os
     os.environ.pop("PZB_NO_FUSE", None)
-    fused = _np(fn())
-    os.environ["PZB_NO_FUSE"] = "1"
+    os.environ["PZB_FUSE_POSTERIOR"] = "1"     # the plain posterior's single-pass form is opt-in
     try:
+        fused = _np(fn())
+        os.environ["PZB_NO_FUSE"] = "1"
         plain = _np(fn())
     finally:
         os.environ.pop("PZB_NO_FUSE", None)
+        os.environ.pop("PZB_FUSE_POSTERIOR", None)
     return fused, plain
 
 
@@ -1729,7 +1741,12 @@ def test_posterior_is_normalised_inside_the_kernel(G, Ng):
         assert fused.shape == (Ng, G)
         np.testing.assert_allclose(fused, plain, rtol=2e-6, atol=1e-30, equal_nan=True)
     assert (fused[0] != fused[0]).all() or (fused[0] == 0).all()
-    host = plan.posterior_host(rest.cpu(), 0, grid.cpu())   # the host pipeline takes the same route, chunk by chunk
+    import os
+    os.environ["PZB_FUSE_POSTERIOR"] = "1"
+    try:
+        host = plan.posterior_host(rest.cpu(), 0, grid.cpu())   # the host pipeline takes the same route, chunk by chunk
+    finally:
+        os.environ.pop("PZB_FUSE_POSTERIOR", None)
     f2, _ = _both_routes(lambda: plan.posterior(rest, 0, grid))
     assert np.array_equal(host.numpy().view(np.int32), f2.view(np.int32))
 
