@@ -219,10 +219,24 @@ def pipe_roofline(engine, flops, ms, peaks):
         return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "executed_frac": 3.0 * achieved / peak, "engine": engine,
                 "note": "algorithmic fp32 FLOPs over the measured sustained cuBLAS bf16 rate; the fp16x2 split "
-                        "executes 3 MMAs per fp32 MAC (executed_frac)"}
+                        "executes 3 MMAs per fp32 MAC (executed_frac), so frac cannot exceed 1/3; the sustained peak is "
+                        "itself power-capped (cuBLAS: ~0.9 pipe-active x ~1.26 GHz), and these kernels sit at the same "
+                        "pipe-active x clock product (profiles/README.md)"}
     peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
     return {"bound": "fp32_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "engine": engine, "note": "nominal 148 SM x 128 FFMA/clk x 2 x clocks.max.sm"}
+
+
+def posterior_traffic(ng):
+    """DRAM bytes per galaxy of the single-pass posterior from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)["nsf_chain_tc_kernel:posterior_fused"]
+        per = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["galaxies_per_launch"]
+        return {"traffic_bytes_per_galaxy": per, "traffic_over_algorithmic": per / (4 * 6 + 4 * t["grid_points"]),
+                "traffic_source": t["source"]}
+    except (OSError, KeyError, ValueError):
+        return {"traffic_bytes_per_galaxy": None}
 
 
 def share(total, rank, world):
@@ -240,6 +254,12 @@ def bench_c3(flow, plan, X, ctx):
     grid = torch.linspace(0.0, 2.3, C3_GRID, device=dev)
     pdfs = torch.empty((ng, C3_GRID), dtype=torch.float32, device=dev)
     ms = timed_device(lambda: plan.posterior(rest, 0, grid, out=pdfs), 2, ctx["barrier"], ctx["max_ranks"])
+    # the single-pass form (exp, trapezoid, divide, NaN -> 0 in shared memory before the only write of the pdfs)
+    os.environ["PZB_FUSE_POSTERIOR"] = "1"
+    try:
+        fused_ms = timed_device(lambda: plan.posterior(rest, 0, grid, out=pdfs), 2, ctx["barrier"], ctx["max_ranks"])
+    finally:
+        os.environ.pop("PZB_FUSE_POSTERIOR", None)
     del pdfs
     torch.cuda.empty_cache()
     # end to end: photometry in host memory, pdfs [Ng, 1000] (4 GB at Ng = 1e6) into an ordinary PAGEABLE array
@@ -257,7 +277,13 @@ def bench_c3(flow, plan, X, ctx):
                     "h2d_bytes": int(ng * 6 * 4), "d2h_bytes": int(ng * C3_GRID * 4),
                     "result": "pageable host array through pzb_posterior_host", "finite": ok},
             "roofline": pipe_roofline(plan.engine, plan.flops_per_row * ng * C3_GRID, ms, ctx["peaks"]),
-            "algorithmic_bytes_per_galaxy": 4 * 6 + 4 * C3_GRID}
+            "algorithmic_bytes_per_galaxy": 4 * 6 + 4 * C3_GRID,
+            "single_pass": dict({"value": total / (fused_ms * 1e-3), "unit": "galaxies/s", "ms": fused_ms,
+                                 "note": "PZB_FUSE_POSTERIOR=1: normalised inside the chain kernel, the pdfs cross HBM once; "
+                                         "opt-in because a 1000-point galaxy fills 7.8 row tiles (24 idle rows) and both epilogue "
+                                         "groups meet once per galaxy; the default is the chain kernel + normalize_pdfs_kernel "
+                                         "(12 B per grid point instead of 4, 0.1 % of the time at 6.5 TB/s)"},
+                                **posterior_traffic(ng))}
 
 
 def bench_c4(flow, ctx):
@@ -339,6 +365,34 @@ def bench_c5(ctx, engine_arg):
             "roofline": pipe_roofline(plan.engine, plan.flops_per_row * n, ms, ctx["peaks"]),
             "inverse_roofline": pipe_roofline(plan.engine, plan.flops_per_row * n, inv_ms, ctx["peaks"]),
             "flops_per_row": plan.flops_per_row, "params": "synthetic (package initialiser, seed 0)"}
+
+
+def bench_one_process(ctx):
+    """Flow.log_prob(DataFrame) of a plain process on a multi-GPU box: the rows are sharded over every visible GPU
+    inside the call (pzflow_b200.sharding), no torchrun."""
+    import pandas as pd
+    import torch
+    from pzflow_b200 import sharding
+    from pzflow_b200.examples import get_example_flow
+    flow = get_example_flow()
+    n = ROWS_PER_GPU * torch.cuda.device_count()
+    plan = flow._plan()
+    U = torch.rand((n, 7), generator=ctx["gen"], device=ctx["dev"]) * 10.0 - 5.0
+    X = torch.nan_to_num(plan.inverse(U, want_log_det=False)[0]).cpu().numpy()
+    del U
+    frame = pd.DataFrame({c: np.ascontiguousarray(X[:, j]) for j, c in enumerate(GALAXY_COLUMNS)}, copy=False)
+    out = {}
+    for tag, devs in (("one_gpu", [0]), ("all_gpus", "all")):
+        sharding.set_devices(devs)
+        flow.log_prob(frame)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            lp = flow.log_prob(frame)
+        out[tag] = {"value": n / ((time.perf_counter() - t0) / 3), "unit": "rows/s"}
+    sharding.set_devices(None)
+    out.update({"workload": "Flow.log_prob(DataFrame[float32 x 7]) end to end in ONE process", "rows": n,
+                "gpus": torch.cuda.device_count(), "finite": bool(np.isfinite(lp).mean() > 0.9)})
+    return out
 
 
 def bench_c1(ctx):
@@ -484,6 +538,8 @@ def run_ours(args, rank, world, local_rank):
         named["c5_high_dim"] = bench_c5(ctx, args.engine)
         torch.cuda.empty_cache()
         named["c1_two_moons"] = bench_c1(ctx)
+        if world == 1 and torch.cuda.device_count() > 1:
+            named["one_process_all_gpus"] = bench_one_process(ctx)
 
     if rank != 0:
         if world > 1:

@@ -163,7 +163,7 @@ int pzb_plan_tc_supported(const pzb_plan *plan);
  * hidden layer of at most 256 units, at most 32 bins (periodic: exactly 16 or 32) and at most 63 conditioner inputs.
  * Replaces the same reference lines as the other engines (pzflow/bijectors.py:462-520, pzflow/utils.py:22-49, 64-227). */
 int pzb_plan_wide_supported(const pzb_plan *plan);
-/* Rows (cumulative over this plan's launches on a tensor-core engine) whose spline logits came out non-finite: the
+/* Rows of FINITE inputs (cumulative over this plan's launches on a tensor-core engine) whose spline logits came out non-finite: the
  * conditioner's activations ride fp16 hi parts, so a pre-activation beyond +-65504 overflows where the reference's
  * fp32 (pzflow/utils.py:45-48) stays finite; such rows land in the zero-probability class.  Synchronises the device;
  * `reset` != 0 clears the counter.  The host-buffer entry points of an AUTO-engine plan re-evaluate a call on the

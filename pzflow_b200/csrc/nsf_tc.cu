@@ -217,6 +217,7 @@ struct TcShared {
   uint64_t w1_free, w2_free, w3_free;      // both issuers' tcgen05.commit after the stage's last GEMM on that buffer
   uint64_t par_free[2];                    // 16 warp arrivals: every epilogue warp is done with that parameter buffer
   uint32_t tmem_base;
+  uint32_t ovf[TC_MAX_CHUNK_TILES * TC_TILE / 32];  // one bit per chunk row: its logits came out non-finite in some stage
   int n_seq;                    // sub-stages of one chain walk
   uint8_t order[TC_SEQ_MAX + 1];  // sub-stages in walk order: coupling stage (index into PlanDev::nsc) ...
   uint8_t sub[TC_SEQ_MAX + 1];    // ... and which four of its spline dimensions
@@ -454,6 +455,8 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         int level = 0;
         light_steps_cols(plan, INV, 0, first_nsc, level, st, CR);
       }
+      for (int q = gtid; q < my_tiles * (TC_TILE / 32); q += TC_GROUP_THREADS)   // this group's tiles' flag words
+        sh->ovf[(2 * (q >> 2) + grp) * (TC_TILE / 32) + (q & 3)] = 0u;
       int level = level_after(plan, INV, 0, first_nsc, 0);  // chain depth (row independent)
       named_bar_sync(2 + grp, TC_GROUP_THREADS);
 
@@ -618,8 +621,10 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               const float xin = srow[col * CR];
               float y, ldd;
               int idx;
+              bool fin;
               spline_dim<INV>(raw, par + TC_PF_B3 + d * TC_DIM_N, par[TC_PF_SCAL + 1], xin, par[TC_PF_SCAL + 2],
-                              par[TC_PF_SCAL + 3], pint[TC_PI_PERIODIC] != 0, y, ldd, idx);
+                              par[TC_PF_SCAL + 3], pint[TC_PI_PERIODIC] != 0, y, ldd, idx, fin);
+              if (!fin) atomicOr(&sh->ovf[r >> 5], 1u << (r & 31));   // (rare) see pzb_plan_overflow_rows
               ldsum += ldd;
               srow[col * CR] = y;
               TC_TRACE(d < 2 ? 5 : 7);
@@ -649,7 +654,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       named_bar_sync(2 + grp, TC_GROUP_THREADS);
 
       // ---- pass Z: trailing steps, latent log-density, outputs of this group's tiles ----
-      uint32_t n_bad = 0u;  // rows of finite inputs whose result is NaN: an fp16 overflow in a conditioner (see pzb_plan_overflow_rows)
+      uint32_t n_bad = 0u;  // rows of finite inputs whose logits came out non-finite: an fp16 overflow in a conditioner (pzb_plan_overflow_rows)
       for (int q = gtid, it = 0; q < my_tiles * TC_TILE; q += TC_GROUP_THREADS, ++it) {
         const int r = (2 * (q >> 7) + grp) * TC_TILE + (q & (TC_TILE - 1));
         if (r >= nrows) continue;
@@ -658,7 +663,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         if (pending) st[(D + pend_level) * CR] += st[COL_PEND * CR] + st[(COL_PEND + 1) * CR];
         int lv = level;
         light_steps_cols(plan, INV, prev_end, ns, lv, st, CR);
-        n_bad += (st[D * CR] != st[D * CR] && ((in_ok >> it) & 1u)) ? 1u : 0u;
+        n_bad += ((sh->ovf[r >> 5] >> (r & 31)) & (in_ok >> it) & 1u);
         if (args.mode == MODE_LOGPROB || args.mode == MODE_POSTERIOR) {
           const float lat = pz_latent_logprob(plan, [&](int j) { return st[plan->perm_final[j] * CR]; });
           const float lpv = pz_nan_to_num_lp(lat + st[D * CR]);

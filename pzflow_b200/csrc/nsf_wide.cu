@@ -401,6 +401,7 @@ struct WdShared {
   uint64_t d3_full[2];    // [buffer]: an output pass has landed
   uint64_t d3_free[2];    // [buffer] (4 warp arrivals): drained
   uint32_t tmem_base;
+  uint32_t ovf[WD_TILE / 32];  // one bit per tile row: its logits came out non-finite in some stage
   int n_seq;
   WdStage stage[MAX_NSC];
 };
@@ -539,6 +540,7 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
           for (int j = 0; j < C; ++j) srow[(COL_COND + j) * CR] = 0.0f;
         }
         for (int l = 0; l < n_lev; ++l) srow[(D + l) * CR] = 0.0f;
+        if (lane == 0) sh->ovf[lrow >> 5] = 0u;
         int lv = 0;
         light_steps_cols(plan, INV, 0, first_nsc, lv, srow, CR);
       }
@@ -668,7 +670,7 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
                                  warp_arrive(bar_free, lane);
                                },
                                y, ldd, idx, fin);
-            (void)fin;
+            if (!fin) atomicOr(&sh->ovf[lrow >> 5], 1u << (lrow & 31));   // (rare) see pzb_plan_overflow_rows
             ldsum += ldd;
             srow[col * CR] = y;
             if (args.bins != nullptr && lrow < nrows)
@@ -690,7 +692,9 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
               const float xin = srow[col * CR];
               float y, ldd;
               int idx;
-              spline_dim<INV>(raw, b3 + d * 48, s3inv, xin, Bs, inv2B, periodic, y, ldd, idx);
+              bool fin;
+              spline_dim<INV>(raw, b3 + d * 48, s3inv, xin, Bs, inv2B, periodic, y, ldd, idx, fin);
+              if (!fin) atomicOr(&sh->ovf[lrow >> 5], 1u << (lrow & 31));
               ldsum += ldd;
               srow[col * CR] = y;
               if (args.bins != nullptr && lrow < nrows)
@@ -712,7 +716,7 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
         if (pending) srow[(D + pend_level) * CR] += srow[COL_PEND * CR] + srow[(COL_PEND + 1) * CR];
         int lv = level;
         light_steps_cols(plan, INV, prev_end, ns, lv, srow, CR);
-        bad_row = in_ok && srow[D * CR] != srow[D * CR];   // finite inputs, NaN log-determinant: see pzb_plan_overflow_rows
+        bad_row = in_ok && ((sh->ovf[lrow >> 5] >> (lrow & 31)) & 1u);   // finite inputs, non-finite logits: pzb_plan_overflow_rows
         if (args.mode == MODE_LOGPROB || args.mode == MODE_POSTERIOR) {
           const float lat = pz_latent_logprob(plan, [&](int j) { return srow[plan->perm_final[j] * CR]; });
           const float lpv = pz_nan_to_num_lp(lat + srow[D * CR]);

@@ -380,7 +380,8 @@ __device__ __forceinline__ void pick_bin(const float (&e)[16], float G1, float G
 // is processed first, then the other axis and the two derivatives the bin needs.
 template <bool INV>
 __device__ __forceinline__ void spline_dim(const float (&raw)[48], const float* __restrict__ bias, float sinv, float x,
-                                           float B, float inv2B, bool periodic, float& out, float& ld, int& idx_out) {
+                                           float B, float inv2B, bool periodic, float& out, float& ld, int& idx_out,
+                                           bool& finite) {
   constexpr int SO = INV ? 16 : 0, OO = INV ? 0 : 16;
   const float twoB = 2.0f * B;
   const bool oob = (x <= -B) || (x >= B);
@@ -393,6 +394,7 @@ __device__ __forceinline__ void spline_dim(const float (&raw)[48], const float* 
   group_sums(e, G1, G2, G3, tot);
   group_sums(f, H1, H2, H3, tot2);
   const float target = (mx + B) * (tot * inv2B);  // (x + B) * sum(e) / 2B
+  finite = (tot + tot2) < INFINITY;  // false for NaN too: non-finite logits (an fp16 overflow upstream, or non-finite inputs)
   float cs_sel, s_sel;
   pick_bin<true>(e, G1, G2, G3, target, k, cs_sel, s_sel);
   const float rs = __fdividef(twoB, tot);
