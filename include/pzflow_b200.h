@@ -325,13 +325,17 @@ int pzb_spline_train_backward(const float *logits, const float *x, const float *
  *     gradients).
  *   pzb_train_step: writes flat_grad [n_params] (non-finite entries zeroed, as jnp.nan_to_num does for the reference's
  *     update) and loss [1] (this rank's share of the loss; may be NULL).  Rows whose log_prob is not finite carry no
- *     gradient. */
+ *     gradient.  row_idx (may be NULL): the N batch rows are X[row_idx[i]] etc. -- the epoch's permutation
+ *     (flow.py:1063-1066) applied inside the kernel, so X / cond / weights are the WHOLE training arrays.  Xerr /
+ *     cond_err (may be NULL): per-row Gaussian sigmas of convolve_errs (flow.py:1068-1079); batch row i is then
+ *     evaluated at x + eps * sigma with eps from the library's Philox stream (seed, noise_base + i). */
 int pzb_plan_train_supported(const pzb_plan *plan);
 int pzb_plan_set_train_layout(pzb_plan *plan, const int64_t *w_offsets, const int64_t *b_offsets, int32_t n_layers_total,
                               int64_t n_params);
 int64_t pzb_train_workspace_floats(const pzb_plan *plan, int64_t N);
 int pzb_train_step(const pzb_plan *plan, const float *params, const float *X, const float *cond, const float *weights,
-                   int64_t N, int64_t n_global, float *workspace, float *flat_grad, float *loss, void *stream);
+                   int64_t N, int64_t n_global, const int64_t *row_idx, const float *Xerr, const float *cond_err,
+                   uint64_t seed, uint64_t noise_base, float *workspace, float *flat_grad, float *loss, void *stream);
 
 /* Adam over one flat fp32 parameter buffer (optax.adam(1e-3) as pzflow/flow.py:968-981 uses it; eps_root = 0).
  * step_dev is a device int32 holding the number of steps taken so far; the call increments it on the stream

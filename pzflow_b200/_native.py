@@ -126,6 +126,7 @@ SIGNATURES = {
     "pzb_plan_set_train_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64]),
     "pzb_train_workspace_floats": (C.c_int64, [C.c_void_p, C.c_int64]),
     "pzb_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pzb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_void_p, C.c_void_p]),

@@ -217,7 +217,8 @@ struct TcShared {
   uint64_t w1_free, w2_free, w3_free;      // both issuers' tcgen05.commit after the stage's last GEMM on that buffer
   uint64_t par_free[2];                    // 16 warp arrivals: every epilogue warp is done with that parameter buffer
   uint32_t tmem_base;
-  uint32_t ovf[TC_MAX_CHUNK_TILES * TC_TILE / 32];  // one bit per chunk row: its logits came out non-finite in some stage
+  uint32_t ovf[TC_MAX_CHUNK_TILES * TC_TILE / 32];  // one bit per chunk row: FINITE conditioner inputs gave non-finite logits in some stage
+  uint32_t kok[TC_MAX_CHUNK_TILES * TC_TILE / 32];  // one bit per chunk row: the current stage's conditioner inputs are finite
   int n_seq;                    // sub-stages of one chain walk
   uint8_t order[TC_SEQ_MAX + 1];  // sub-stages in walk order: coupling stage (index into PlanDev::nsc) ...
   uint8_t sub[TC_SEQ_MAX + 1];    // ... and which four of its spline dimensions
@@ -512,6 +513,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             float key[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) key[i] = (i < in_dim) ? krow[pint[TC_PI_KEY + i] * CR] : 0.0f;
+            float chk = ((key[0] + key[1]) + (key[2] + key[3])) + ((key[4] + key[5]) + (key[6] + key[7]));
             uint32_t rh[8], rl[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) split2(key[2 * j], key[2 * j + 1], rh[j], rl[j]);
@@ -523,12 +525,16 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             } else {            // inputs 8..14 ride in k = 9..15
 #pragma unroll
               for (int i = 0; i < 7; ++i) key[i] = (8 + i < in_dim) ? krow[pint[TC_PI_KEY + 8 + i] * CR] : 0.0f;
+              chk += ((key[0] + key[1]) + (key[2] + key[3])) + ((key[4] + key[5]) + key[6]);
               split2(1.0f, key[0], rh[4], rl[4]);
 #pragma unroll
               for (int j = 0; j < 3; ++j) split2(key[1 + 2 * j], key[2 + 2 * j], rh[5 + j], rl[5 + j]);
             }
             tmem_st8(t_key, rh);
             tmem_st8(t_key + 16u, rl);
+            // a sum of finite inputs of this size is finite; NaN or infinite inputs make it non-finite (inf - inf -> NaN)
+            const uint32_t ok = __ballot_sync(0xffffffffu, fabsf(chk) < INFINITY);
+            if (lane == 0) sh->kok[((2 * kk + grp) * TC_TILE + lrow) >> 5] = ok;
             tc_wait_st();
           };
           TC_TRACE_S(3);
@@ -624,7 +630,8 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               bool fin;
               spline_dim<INV>(raw, par + TC_PF_B3 + d * TC_DIM_N, par[TC_PF_SCAL + 1], xin, par[TC_PF_SCAL + 2],
                               par[TC_PF_SCAL + 3], pint[TC_PI_PERIODIC] != 0, y, ldd, idx, fin);
-              if (!fin) atomicOr(&sh->ovf[r >> 5], 1u << (r & 31));   // (rare) see pzb_plan_overflow_rows
+              if (!fin && ((sh->kok[r >> 5] >> (r & 31)) & 1u))
+                atomicOr(&sh->ovf[r >> 5], 1u << (r & 31));   // (rare) finite inputs, non-finite logits: pzb_plan_overflow_rows
               ldsum += ldd;
               srow[col * CR] = y;
               TC_TRACE(d < 2 ? 5 : 7);

@@ -33,6 +33,13 @@ struct TrainOffsets {  // flat-buffer offsets (in floats) of a coupling stage's 
   long long w[MAX_DENSE], b[MAX_DENSE];
 };
 
+struct TrainBatch {  // how a step's rows are picked out of the caller's whole arrays
+  const long long* row_idx;       // [N] indices into X / cond / weights (the epoch's permutation, this rank's share), or null
+  const float* Xerr;              // [rows of X, D] Gaussian sigmas (convolve_errs), or null
+  const float* cond_err;          // [rows of X, C] sigmas in standard-scaled condition units, or null
+  unsigned long long seed, noise_base;   // eps of batch row i: Philox(seed, noise_base + i, column)
+};
+
 // [col][16 rows] with the four 16-byte row segments of a column XOR-swizzled by the column, so that float4 accesses of
 // eight consecutive columns hit eight different bank groups
 __device__ __forceinline__ int ts_swz(int col, int row) { return col * TS_ROWS + (row ^ (((col >> 1) & 3) << 2)); }
@@ -297,7 +304,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
 train_step_kernel(const PlanDev* __restrict__ plan, const TrainOffsets* __restrict__ offs, const float* __restrict__ params,
                   const float* __restrict__ X, const float* __restrict__ cond, const float* __restrict__ wrow, long long N,
                   float inv_n, long long row_scratch, float* __restrict__ scratch, long long n_params,
-                  float* __restrict__ partials, float* __restrict__ loss_part) {
+                  float* __restrict__ partials, float* __restrict__ loss_part, TrainBatch tb) {
   extern __shared__ __align__(16) float ts_smem[];
   const int D = plan->D, C = plan->C, ns = plan->n_steps;
   const TsSmem sl = ts_layout(D, C);
@@ -320,14 +327,29 @@ train_step_kernel(const PlanDev* __restrict__ plan, const TrainOffsets* __restri
   // (every parameter of the flat buffer belongs to some dense layer of the chain -- the host checks it -- so this
   // CTA's slice of the partial-gradient buffer is written completely below and needs no zeroing)
 
-  // ---- load the tile (row-major global -> [col][row] shared) ----
+  // ---- load the tile (row-major global -> [col][row] shared): the batch's rows are gathered through the epoch's
+  // permutation here, and the Gaussian error samples of convolve_errs (pzflow/flow.py:1068-1079, utils.py:52-61)
+  // are drawn here, so a step launches nothing but this kernel, the partial-sum reduction and Adam ----
   for (int e = tid; e < D * TS_ROWS; e += TS_THREADS) {
     const int r = e / D, j = e - r * D;
-    xs[ts_swz(j, r)] = row0 + r < N ? X[(row0 + r) * D + j] : 0.0f;
+    float v = 0.0f;
+    if (row0 + r < N) {
+      const long long src = tb.row_idx != nullptr ? tb.row_idx[row0 + r] : row0 + r;
+      v = X[src * D + j];
+      if (tb.Xerr != nullptr) v = v + pz_err_normal(tb.seed, 0u, tb.noise_base + (unsigned long long)(row0 + r), j) * tb.Xerr[src * D + j];
+    }
+    xs[ts_swz(j, r)] = v;
   }
   for (int e = tid; e < C * TS_ROWS; e += TS_THREADS) {
     const int r = e / C, j = e - r * C;
-    cs[ts_swz(j, r)] = row0 + r < N ? cond[(row0 + r) * C + j] : 0.0f;
+    float v = 0.0f;
+    if (row0 + r < N) {
+      const long long src = tb.row_idx != nullptr ? tb.row_idx[row0 + r] : row0 + r;
+      v = cond[src * C + j];
+      if (tb.cond_err != nullptr)
+        v = v + pz_err_normal(tb.seed, 1u, tb.noise_base + (unsigned long long)(row0 + r), j) * tb.cond_err[src * C + j];
+    }
+    cs[ts_swz(j, r)] = v;
   }
   if (tid < TS_ROWS) ldsum[tid] = 0.0f;
   __syncthreads();
@@ -423,7 +445,7 @@ train_step_kernel(const PlanDev* __restrict__ plan, const TrainOffsets* __restri
     else if (!inside) lat = -INFINITY;
     const float lp = lat + ldsum[r];
     const bool ok = row0 + r < N && isfinite(lp);                 // rows outside the support carry no gradient
-    const float wv = ok ? wrow[row0 + r] : 0.0f;
+    const float wv = ok ? wrow[tb.row_idx != nullptr ? tb.row_idx[row0 + r] : row0 + r] : 0.0f;
     my_loss = ok ? -(wv * lp) * inv_n : 0.0f;
     const float glp = -wv * inv_n;
     gld[r] = glp;
@@ -573,7 +595,8 @@ size_t train_step_workspace_floats(const PlanDev& hp, long long N, long long n_p
 
 cudaError_t launch_train_step(const PlanDev* d_plan, const PlanDev& hp, const TrainOffsets* d_offs, const float* params,
                               const float* X, const float* cond, const float* w, long long N, float inv_n, long long n_params,
-                              float* workspace, float* flat_grad, float* loss, int num_sms, cudaStream_t stream) {
+                              float* workspace, float* flat_grad, float* loss, int num_sms, const TrainBatch& tb,
+                              cudaStream_t stream) {
   const long long n_cta = (N + TS_ROWS - 1) / TS_ROWS;
   if (n_cta == 0) {
     cudaError_t e = cudaMemsetAsync(flat_grad, 0, (size_t)n_params * sizeof(float), stream);
@@ -589,7 +612,7 @@ cudaError_t launch_train_step(const PlanDev* d_plan, const PlanDev& hp, const Tr
   cudaError_t e = cudaFuncSetAttribute(train_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   train_step_kernel<<<(unsigned)n_cta, TS_THREADS, smem, stream>>>(d_plan, d_offs, params, X, cond, w, N, inv_n, rs, scratch,
-                                                                   n_params, partials, loss_part);
+                                                                   n_params, partials, loss_part, tb);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   long long blocks = (n_params + 255) / 256;

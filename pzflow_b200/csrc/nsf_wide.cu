@@ -401,7 +401,8 @@ struct WdShared {
   uint64_t d3_full[2];    // [buffer]: an output pass has landed
   uint64_t d3_free[2];    // [buffer] (4 warp arrivals): drained
   uint32_t tmem_base;
-  uint32_t ovf[WD_TILE / 32];  // one bit per tile row: its logits came out non-finite in some stage
+  uint32_t ovf[WD_TILE / 32];     // one bit per tile row: FINITE conditioner inputs gave non-finite logits in some stage
+  uint32_t kok[2][WD_TILE / 32];  // [half][..] one bit per tile row: that half's block of the stage's conditioner inputs is finite
   int n_seq;
   WdStage stage[MAX_NSC];
 };
@@ -579,6 +580,7 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
         // ---- E0: conditioner inputs + the constant 1 of the bias row -> fp16 hi/lo A operand in Q[0, K1) ----
         {
           const int* key_col = pint + pint[WD_PI_OFF_KEY];
+          float chk = 0.0f;
           for (int b = half; b * 32 < K1; b += 2) {
             uint32_t rh[16], rl[16];
 #pragma unroll
@@ -586,10 +588,15 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
               const int k0 = 32 * b + 2 * j, k1 = k0 + 1;
               const float v0 = k0 < in_dim ? srow[key_col[k0] * CR] : (k0 == in_dim ? 1.0f : 0.0f);
               const float v1 = k1 < in_dim ? srow[key_col[k1] * CR] : (k1 == in_dim ? 1.0f : 0.0f);
+              chk += v0 + v1;
               split2(v0, v1, rh[j], rl[j]);
             }
             tmem_st16(t_lane + 256u + 32u * b, rh);
             tmem_st16(t_lane + 256u + 32u * b + 16u, rl);
+          }
+          {  // finite inputs sum to something finite; NaN or infinite ones do not (inf - inf -> NaN)
+            const uint32_t ok = __ballot_sync(0xffffffffu, fabsf(chk) < INFINITY);
+            if (lane == 0) sh->kok[half][lrow >> 5] = ok;
           }
           tc_wait_st();
           tc_fence_before();
@@ -670,7 +677,8 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
                                  warp_arrive(bar_free, lane);
                                },
                                y, ldd, idx, fin);
-            if (!fin) atomicOr(&sh->ovf[lrow >> 5], 1u << (lrow & 31));   // (rare) see pzb_plan_overflow_rows
+            if (!fin && ((sh->kok[0][lrow >> 5] & sh->kok[1][lrow >> 5]) >> (lrow & 31)) & 1u)
+              atomicOr(&sh->ovf[lrow >> 5], 1u << (lrow & 31));   // (rare) finite inputs, non-finite logits: pzb_plan_overflow_rows
             ldsum += ldd;
             srow[col * CR] = y;
             if (args.bins != nullptr && lrow < nrows)
@@ -694,7 +702,8 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
               int idx;
               bool fin;
               spline_dim<INV>(raw, b3 + d * 48, s3inv, xin, Bs, inv2B, periodic, y, ldd, idx, fin);
-              if (!fin) atomicOr(&sh->ovf[lrow >> 5], 1u << (lrow & 31));
+              if (!fin && ((sh->kok[0][lrow >> 5] & sh->kok[1][lrow >> 5]) >> (lrow & 31)) & 1u)
+                atomicOr(&sh->ovf[lrow >> 5], 1u << (lrow & 31));
               ldsum += ldd;
               srow[col * CR] = y;
               if (args.bins != nullptr && lrow < nrows)

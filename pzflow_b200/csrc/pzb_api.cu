@@ -35,11 +35,18 @@ cudaError_t launch_wide(const PlanDev* d_plan, const PlanDev& hp, const LaunchAr
 struct TrainOffsets {
   long long w[MAX_DENSE], b[MAX_DENSE];
 };
+struct TrainBatch {
+  const long long* row_idx;
+  const float* Xerr;
+  const float* cond_err;
+  unsigned long long seed, noise_base;
+};
 bool train_step_supported(const PlanDev& hp);
 size_t train_step_workspace_floats(const PlanDev& hp, long long N, long long n_params);
 cudaError_t launch_train_step(const PlanDev* d_plan, const PlanDev& hp, const TrainOffsets* d_offs, const float* params,
                               const float* X, const float* cond, const float* w, long long N, float inv_n, long long n_params,
-                              float* workspace, float* flat_grad, float* loss, int num_sms, cudaStream_t stream);
+                              float* workspace, float* flat_grad, float* loss, int num_sms, const TrainBatch& tb,
+                              cudaStream_t stream);
 cudaError_t launch_spline_train_fwd(const float* logits, const float* x, long long n_elems, int K, float B, int periodic,
                                     float* y, float* ld, cudaStream_t stream);
 cudaError_t launch_spline_train_bwd(const float* logits, const float* x, const float* gy, const float* gld,
@@ -1459,7 +1466,8 @@ int64_t pzb_train_workspace_floats(const pzb_plan* plan, int64_t N) {
 }
 
 int pzb_train_step(const pzb_plan* plan, const float* params, const float* X, const float* cond, const float* weights,
-                   int64_t N, int64_t n_global, float* workspace, float* flat_grad, float* loss, void* stream) {
+                   int64_t N, int64_t n_global, const int64_t* row_idx, const float* Xerr, const float* cond_err,
+                   uint64_t seed, uint64_t noise_base, float* workspace, float* flat_grad, float* loss, void* stream) {
   if (!plan || !plan->d_train_offs) return fail(PZB_ERR_INVALID, "train_step: call pzb_plan_set_train_layout first");
   if (N < 0 || n_global < 1) return fail(PZB_ERR_INVALID, "train_step: bad row counts");
   if (!params || !flat_grad || (N > 0 && (!X || !weights || !workspace)))
@@ -1467,9 +1475,15 @@ int pzb_train_step(const pzb_plan* plan, const float* params, const float* X, co
   if (N > 0 && plan->host.C > 0 && !cond) return fail(PZB_ERR_INVALID, "train_step: this plan is conditional but conditions are NULL");
   DeviceGuard guard(plan->device);
   if (!guard.ok) return fail(PZB_ERR_CUDA, "cannot select device %d", plan->device);
+  TrainBatch tb;
+  tb.row_idx = reinterpret_cast<const long long*>(row_idx);
+  tb.Xerr = Xerr;
+  tb.cond_err = plan->host.C > 0 ? cond_err : nullptr;
+  tb.seed = seed;
+  tb.noise_base = noise_base;
   cudaError_t ce = launch_train_step(plan->d_plan, plan->host, plan->d_train_offs, params, X, cond, weights, N,
                                      1.0f / (float)n_global, plan->train_params, workspace, flat_grad, loss, plan->num_sms,
-                                     (cudaStream_t)stream);
+                                     tb, (cudaStream_t)stream);
   if (ce != cudaSuccess) return cuda_fail(ce, "train_step launch");
   g_launches.fetch_add(N > 0 ? 2 : 0);
   return PZB_OK;

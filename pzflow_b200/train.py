@@ -395,28 +395,51 @@ class FusedGradient:
         N.check(N.lib().pzb_plan_set_train_layout(plan._h, w, b, len(offs), chain.flat.numel()))
         return cls(chain, plan, chain.flat.numel())
 
-    def __call__(self, x, cond, w, n: int) -> None:
-        from ._native import check, lib
-        c = self.chain
-        rows = int(x.shape[0])
-        x = x.contiguous().float()
-        w = w.contiguous().float()
-        cond = None if (cond is None or self.plan.n_conditions == 0) else cond[:, : self.plan.n_conditions].contiguous().float()
+    def _workspace(self, rows: int) -> torch.Tensor:
+        from ._native import lib
         ws = self._ws.get(rows)
         if ws is None:
             need = lib().pzb_train_workspace_floats(self.plan._h, rows)
-            ws = self._ws[rows] = torch.empty(max(1, need), dtype=torch.float32, device=c.device)
-        check(lib().pzb_train_step(self.plan._h, c.flat.data_ptr(), x.data_ptr() if rows else None,
-                                   cond.data_ptr() if cond is not None and rows else None, w.data_ptr() if rows else None,
-                                   rows, int(n), ws.data_ptr(), c.flat_grad.data_ptr(), self.loss.data_ptr(),
-                                   torch.cuda.current_stream(c.device).cuda_stream))
+            ws = self._ws[rows] = torch.empty(max(1, need), dtype=torch.float32, device=self.chain.device)
+        return ws
+
+    def __call__(self, x, cond, w, n: int) -> None:
+        """flat_grad <- gradient of -sum(w * log_prob(x | cond)) / n for the given batch rows."""
+        self.gathered(x, cond, w, None, 0, int(x.shape[0]), n)
+
+    def gathered(self, X, cond, w, idx, start: int, rows: int, n: int, Xerr=None, cond_err=None, seed: int = 0,
+                 noise_base: int = 0) -> None:
+        """The same for the batch rows ``idx[start:start + rows]`` of the WHOLE training arrays X / cond / w (the
+        epoch's permutation is applied inside the kernel), optionally convolved with Gaussian errors drawn in the
+        kernel (flow.py:1063-1079): a step launches no gather, no random-number and no copy kernel."""
+        from ._native import check, lib
+        c = self.chain
+        nc = self.plan.n_conditions
+        for t in (X, w) + ((cond,) if nc else ()) + ((Xerr,) if Xerr is not None else ()):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("the fused training step needs contiguous float32 device tensors")
+        if nc and cond.shape[1] != nc:
+            raise ValueError(f"conditions must have {nc} columns")
+        if idx is not None and not (idx.is_cuda and idx.dtype == torch.int64 and idx.is_contiguous()):
+            raise ValueError("row indices must be a contiguous int64 device tensor")
+        ws = self._workspace(rows)
+        check(lib().pzb_train_step(
+            self.plan._h, c.flat.data_ptr(), X.data_ptr() if rows else None,
+            cond.data_ptr() if (nc and rows) else None, w.data_ptr() if rows else None, rows, int(n),
+            idx.data_ptr() + 8 * int(start) if idx is not None else None,
+            Xerr.data_ptr() if Xerr is not None else None,
+            cond_err.data_ptr() if (cond_err is not None and nc) else None, int(seed) & (2 ** 64 - 1),
+            int(noise_base) & (2 ** 64 - 1), ws.data_ptr(), c.flat_grad.data_ptr(), self.loss.data_ptr(),
+            torch.cuda.current_stream(c.device).cuda_stream))
 
 
 def _grads(chain: TorchChain, x, cond, w, n: int) -> None:
     """flat_grad <- d/d params of -sum_local(w * log_prob) / n, non-finite entries zeroed, summed over ranks."""
     fused = getattr(chain, "fused_gradient", None)
     if fused is not None:
-        fused(x, cond, w, n)
+        nc = fused.plan.n_conditions
+        fused(x.contiguous().float(), cond[:, :nc].contiguous().float() if (nc and cond is not None) else None,
+              w.contiguous().float(), n)
         d = _dist()
         if d is not None:
             d.all_reduce(chain.flat_grad, op=d.ReduceOp.SUM)
@@ -575,7 +598,15 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
     noise = torch.Generator(device=dev)
     noise.manual_seed(int(batch_seed) + rank)   # every rank draws its own eps for its own share of the batch
     best_loss, best_vals, stall = math.inf, chain.numpy_params(), 0
-    use_graph = isinstance(opt, NativeAdam) and os.environ.get("PZB_TRAIN_GRAPH", "1") != "0"
+    fused = chain.fused_gradient
+    use_graph = fused is None and isinstance(opt, NativeAdam) and os.environ.get("PZB_TRAIN_GRAPH", "1") != "0"
+    if fused is not None:   # whole arrays as the kernel wants them; the batch is picked inside the kernel
+        nc = fused.plan.n_conditions
+        Xg, Wg = Xm.contiguous().float(), Wd.contiguous().float()
+        Cg = Cm[:, :nc].contiguous().float() if (nc and Cm is not None) else None
+        Xeg = Xe.contiguous().float() if Xe is not None else None
+        Ceg = Ce[:, :nc].contiguous().float() if (nc and Ce is not None) else None
+    steps_done = 0
     loop = range(epochs)
     if progress_bar:
         from tqdm import tqdm
@@ -585,6 +616,16 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
         for b0 in range(0, n, batch_size):
             sel = idx[b0:b0 + batch_size]
             a, b = shard_batch(len(sel), rank, world)
+            if fused is not None:
+                # one kernel for the gradient (gather, error samples, forward, backward), one for the partial sums,
+                # the all-reduce of the flat gradient, Adam
+                fused.gathered(Xg, Cg, Wg, idx, b0 + a, b - a, len(sel), Xeg, Ceg, seed=int(batch_seed),
+                               noise_base=steps_done * batch_size + a)
+                if d is not None:
+                    d.all_reduce(chain.flat_grad, op=d.ReduceOp.SUM)
+                opt.step()
+                steps_done += 1
+                continue
             mine = sel[a:b]
             xb = Xm[mine]
             if Xe is not None:
