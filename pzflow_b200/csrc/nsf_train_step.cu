@@ -25,8 +25,8 @@ constexpr int TS_THREADS = 256;
 constexpr int TS_HMAX = 256;
 constexpr int TS_OUT_MAX = 1024;
 constexpr int TS_KMAX = 64;
-constexpr int TS_KC = 16;    // weight rows per streamed chunk (forward GEMM, 256 output columns at a time)
-constexpr int TS_NC = 32;    // weight columns per streamed chunk (input-gradient GEMM)
+constexpr int TS_KC = 32;    // weight rows per streamed chunk (forward GEMM, 256 output columns at a time), double buffered
+constexpr int TS_NC = 32;    // weight columns per streamed chunk (input-gradient GEMM), double buffered
 constexpr float TS_SLOPE = 0.01f;
 
 struct TrainOffsets {  // flat-buffer offsets (in floats) of a coupling stage's dense layers
@@ -80,11 +80,21 @@ __host__ __device__ inline TsSmem ts_layout(int D, int C) {
   s.g0 = o;  o += TS_HMAX * TS_ROWS;
   s.g1 = o;  o += TS_HMAX * TS_ROWS;
   s.lg = o;  o += TS_OUT_MAX * TS_ROWS;
-  s.wc = o;  o += TS_HMAX * (TS_NC + 1) > TS_KC * 256 ? TS_HMAX * (TS_NC + 1) : TS_KC * 256;
+  s.wc = o;  o += 2 * (TS_HMAX * (TS_NC + 1) > TS_KC * 256 ? TS_HMAX * (TS_NC + 1) : TS_KC * 256);   // two chunk buffers
   s.red = o; o += 32;
   s.total = o;
   return s;
 }
+
+constexpr int TS_WC_HALF = TS_HMAX * (TS_NC + 1) > TS_KC * 256 ? TS_HMAX * (TS_NC + 1) : TS_KC * 256;
+
+__device__ __forceinline__ void ts_cp4(float* smem_dst, const float* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void ts_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N_>
+__device__ __forceinline__ void ts_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_)); }
 
 // out[n][r] = act(b[n] + sum_k in[k][r] W[k][n]), n < N, k < K; W row-major [K][N] in global memory
 template <bool LEAKY>
@@ -98,25 +108,41 @@ __device__ void ts_gemm_fwd(const float* __restrict__ in, int K, const float* __
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
     const int ncols = min(256, N - n0);
-    for (int k0 = 0; k0 < K; k0 += TS_KC) {
+    // the weight chunks stream global -> shared through two buffers (cp.async): chunk i + 1 loads under chunk i's FMAs
+    auto fetch = [&](int k0, float* buf) {
       const int kr = min(TS_KC, K - k0);
-      __syncthreads();
       for (int e = tid; e < kr * 256; e += TS_THREADS) {
         const int kk = e >> 8, c = e & 255;
-        wc[e] = c < ncols ? W[(size_t)(k0 + kk) * N + n0 + c] : 0.0f;
+        if (c < ncols) ts_cp4(buf + e, W + (size_t)(k0 + kk) * N + n0 + c);
+        else buf[e] = 0.0f;
+      }
+      ts_cp_commit();
+    };
+    __syncthreads();   // the previous user of the chunk buffers is done
+    fetch(0, wc);
+    for (int k0 = 0, it = 0; k0 < K; k0 += TS_KC, ++it) {
+      const int kr = min(TS_KC, K - k0);
+      float* cur = wc + (it & 1) * TS_WC_HALF;
+      if (k0 + TS_KC < K) {
+        fetch(k0 + TS_KC, wc + ((it + 1) & 1) * TS_WC_HALF);
+        ts_cp_wait<1>();
+      } else {
+        ts_cp_wait<0>();
       }
       __syncthreads();
+#pragma unroll 4
       for (int kk = 0; kk < kr; ++kk) {
         const float4 a = *reinterpret_cast<const float4*>(in + ts_swz(k0 + kk, 4 * rg));
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float w = wc[kk * 256 + nl + 64 * j];
+          const float w = cur[kk * 256 + nl + 64 * j];
           acc[j][0] = fmaf(a.x, w, acc[j][0]);
           acc[j][1] = fmaf(a.y, w, acc[j][1]);
           acc[j][2] = fmaf(a.z, w, acc[j][2]);
           acc[j][3] = fmaf(a.w, w, acc[j][3]);
         }
       }
+      __syncthreads();   // everyone is done with `cur` before the fetch after next overwrites it
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -147,21 +173,34 @@ __device__ void ts_gemm_dgrad(const float* __restrict__ gout, int N, const float
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
-  for (int n0 = 0; n0 < N; n0 += TS_NC) {
+  auto fetch = [&](int n0, float* buf) {
     const int nc = min(TS_NC, N - n0);
-    __syncthreads();
     for (int e = tid; e < K * TS_NC; e += TS_THREADS) {
       const int k = e / TS_NC, c = e % TS_NC;
-      wc[k * (TS_NC + 1) + c] = c < nc ? W[(size_t)k * N + n0 + c] : 0.0f;
+      if (c < nc) ts_cp4(buf + k * (TS_NC + 1) + c, W + (size_t)k * N + n0 + c);
+    }
+    ts_cp_commit();
+  };
+  __syncthreads();
+  fetch(0, wc);
+  for (int n0 = 0, it = 0; n0 < N; n0 += TS_NC, ++it) {
+    const int nc = min(TS_NC, N - n0);
+    const float* cur = wc + (it & 1) * TS_WC_HALF;
+    if (n0 + TS_NC < N) {
+      fetch(n0 + TS_NC, wc + ((it + 1) & 1) * TS_WC_HALF);
+      ts_cp_wait<1>();
+    } else {
+      ts_cp_wait<0>();
     }
     __syncthreads();
+#pragma unroll 4
     for (int c = 0; c < nc; ++c) {
       const float4 g = *reinterpret_cast<const float4*>(gout + ts_swz(n0 + c, 4 * rg));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = kl + 64 * j;
         if (k < K) {
-          const float w = wc[k * (TS_NC + 1) + c];
+          const float w = cur[k * (TS_NC + 1) + c];
           acc[j][0] = fmaf(g.x, w, acc[j][0]);
           acc[j][1] = fmaf(g.y, w, acc[j][1]);
           acc[j][2] = fmaf(g.z, w, acc[j][2]);
@@ -169,6 +208,7 @@ __device__ void ts_gemm_dgrad(const float* __restrict__ gout, int N, const float
         }
       }
     }
+    __syncthreads();
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
