@@ -181,12 +181,20 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   }
 }
 
+// SM count of the current device (grid-stride kernels size their grids from it)
+static int train_num_sms() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    return 148;
+  return n;
+}
+
 cudaError_t launch_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
                              float eps, int* step, cudaStream_t stream) {
   adam_tick_kernel<<<1, 1, 0, stream>>>(step);
   if (n > 0) {
     long long blocks = (n + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > (long long)train_num_sms() * 8) blocks = (long long)train_num_sms() * 8;
     adam_step_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, step);
   }
   return cudaGetLastError();
@@ -196,7 +204,7 @@ cudaError_t launch_spline_train_fwd(const float* logits, const float* x, long lo
                                     float* y, float* ld, cudaStream_t stream) {
   if (n_elems == 0) return cudaSuccess;
   long long blocks = (n_elems + 127) / 128;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > (long long)train_num_sms() * 16) blocks = (long long)train_num_sms() * 16;
   spline_train_fwd_kernel<<<(unsigned)blocks, 128, 0, stream>>>(logits, x, n_elems, K, B, periodic, y, ld);
   return cudaGetLastError();
 }
@@ -206,7 +214,7 @@ cudaError_t launch_spline_train_bwd(const float* logits, const float* x, const f
                                     cudaStream_t stream) {
   if (n_elems == 0) return cudaSuccess;
   long long blocks = (n_elems + 127) / 128;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > (long long)train_num_sms() * 16) blocks = (long long)train_num_sms() * 16;
   spline_train_bwd_kernel<<<(unsigned)blocks, 128, 0, stream>>>(logits, x, gy, gld, n_elems, K, B, periodic, glogits, gx);
   return cudaGetLastError();
 }

@@ -1692,7 +1692,7 @@ def test_one_process_shards_host_arrays_over_all_gpus(monkeypatch):
     lpn, pdfn, sn = flow.log_prob(df), flow.posterior(df.iloc[:2000], "redshift", grid), flow.sample(40_003, seed=9)
     assert np.array_equal(lp1.view(np.int32), lpn.view(np.int32))
     assert np.array_equal(pdf1.view(np.int32), pdfn.view(np.int32))
-    assert np.array_equal(s1.to_numpy().view(np.int32), sn.to_numpy().view(np.int32))
+    assert np.array_equal(np.ascontiguousarray(s1.to_numpy()).view(np.int32), np.ascontiguousarray(sn.to_numpy()).view(np.int32))
     # conditional flow with the default (CentBeta13) latent: conditions travel with their row block
     rng = np.random.default_rng(1)
     cf = Flow(data_columns=("a", "b", "c"), conditional_columns=("p", "q"),
@@ -1705,7 +1705,8 @@ def test_one_process_shards_host_arrays_over_all_gpus(monkeypatch):
     cn, csn = cf.log_prob(cdf), cf.sample(2, conditions=cdf.iloc[:12_000], seed=3)
     sharding.set_devices(None)
     assert np.array_equal(c1.view(np.int32), cn.view(np.int32))
-    assert np.array_equal(cs1.to_numpy().view(np.int64), csn.to_numpy().view(np.int64))
+    assert np.array_equal(np.ascontiguousarray(cs1.to_numpy(), dtype=np.float64).view(np.int64),
+                          np.ascontiguousarray(csn.to_numpy(), dtype=np.float64).view(np.int64))
 
 
 # --------------------------------------------------------------------------- #
