@@ -1871,3 +1871,29 @@ def test_fused_training_step_in_a_cuda_graph_and_launch_count():
         out.append(_np(chain.flat).copy())
     assert np.abs(out[1] - _np(mk().flat)).max() > 1e-3
     np.testing.assert_array_equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("flag", [99, np.nan])
+def test_posterior_with_marginalization_like_the_reference_test(flag):
+    """tests/test_flow.py:84-112 of the reference, line for line: a flow that is only a Reverse bijector, every row
+    missing b, then b and c (nested marginalisation), numeric and NaN flags -- plus what the reference's test leaves
+    out, the values: a Reverse flow's density is the latent's, so the marginal is known in closed form."""
+    from pzflow_b200 import Flow
+    from pzflow_b200.bijectors import Reverse
+    flow = Flow(("a", "b", "c", "d"), Reverse())
+    x = pd.DataFrame(np.arange(16).reshape(-1, 4).astype(np.float64), columns=("a", "b", "c", "d"))
+    grid = np.arange(0, 2.1, 0.12)
+    marg_rules = {"flag": flag, "b": lambda row: np.linspace(0, 1, 2), "c": lambda row: np.linspace(1, 2, 3)}
+    x["b"] = flag * np.ones(x.shape[0])
+    pdfs = flow.posterior(x, column="a", grid=grid, marg_rules=marg_rules)
+    assert pdfs.shape == (x.shape[0], grid.size)
+    x["c"] = flag * np.ones(x.shape[0])
+    pdfs2 = flow.posterior(x, column="a", grid=grid, marg_rules=marg_rules)
+    assert pdfs2.shape == (x.shape[0], grid.size)
+    # row 0 has d = 3 (inside the CentBeta13 support), the others d >= 7 (outside: zero density -> all-zero pdf)
+    g = grid.astype(np.float32).astype(np.float64)
+    beta = lambda u: ((u + 5) / 10) ** 12 * (1 - (u + 5) / 10) ** 12       # un-normalised Beta(13, 13) on [-5, 5]  # noqa: E731
+    want = beta(g) / np.trapezoid(beta(g), g)                               # b, c, d only scale the density of a
+    np.testing.assert_allclose(pdfs[0], want, rtol=2e-5)
+    np.testing.assert_allclose(pdfs2[0], want, rtol=2e-5)
+    assert (pdfs[1:] == 0).all() and (pdfs2[1:] == 0).all()
