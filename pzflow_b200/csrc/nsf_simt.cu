@@ -334,14 +334,14 @@ nsf_chain_simt_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, int Lma
     for (int e = tid; e < D * TM; e += NTHREADS) {
       const int r = e / D, j = e % D;
       const long long row = row0 + r;
-      const float v = row < args.N ? pz_input_value(args, row, j, D) : 0.0f;
+      const float v = row < args.N ? pz_input_value(args, pz_row_index(args, row), j, D) : 0.0f;
       const int phys = inverse ? plan->perm_final[j] : j;
       Xs[phys * TM + r] = v;
     }
     for (int e = tid; e < C * TM; e += NTHREADS) {
       const int r = e / C, j = e % C;
       const long long row = row0 + r;
-      const float v = row < args.N ? pz_cond_value(args, row, j, C) : 0.0f;
+      const float v = row < args.N ? pz_cond_value(args, pz_row_index(args, row), j, C) : 0.0f;
       Cs[j * TM + r] = v;
     }
     for (int e = tid; e < MAX_CHAIN_DEPTH * TM; e += NTHREADS) ldacc[e] = 0.0f;

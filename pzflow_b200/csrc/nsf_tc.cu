@@ -441,14 +441,15 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         const long long row = row0 + r;
         float* st = state + r;
         float chk = 0.0f;
+        const RowIndex ri = pz_row_index(args, row);
         for (int j = 0; j < D; ++j) {
-          const float v = pz_input_value(args, row, j, D);
+          const float v = pz_input_value(args, ri, j, D);
           st[(INV ? plan->perm_final[j] : j) * CR] = v;
           chk += v * 0.0f;   // NaN iff some input is NaN or infinite
         }
         for (int l = 0; l < n_lev; ++l) st[(D + l) * CR] = 0.0f;
         for (int j = 0; j < C; ++j) {
-          const float v = pz_cond_value(args, row, j, C);
+          const float v = pz_cond_value(args, ri, j, C);
           st[(COL_COND + j) * CR] = v;
           chk += v * 0.0f;
         }

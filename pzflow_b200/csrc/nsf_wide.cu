@@ -525,13 +525,14 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
       if (half == 0) {
         if (lrow < nrows) {
           float chk = 0.0f;
+          const RowIndex ri = pz_row_index(args, row);
           for (int j = 0; j < D; ++j) {
-            const float v = pz_input_value(args, row, j, D);
+            const float v = pz_input_value(args, ri, j, D);
             srow[(INV ? plan->perm_final[j] : j) * CR] = v;
             chk += v * 0.0f;   // NaN iff some input is NaN or infinite
           }
           for (int j = 0; j < C; ++j) {
-            const float v = pz_cond_value(args, row, j, C);
+            const float v = pz_cond_value(args, ri, j, C);
             srow[(COL_COND + j) * CR] = v;
             chk += v * 0.0f;
           }

@@ -175,37 +175,61 @@ __device__ __forceinline__ float pz_err_normal(unsigned long long seed, uint32_t
   return (j & 1) ? r * sn : r * cs;
 }
 
-// Value of data column j (logical order) and of condition j for evaluation row `row`: the posterior's grid
-// expansion (pzflow/flow.py:697-714) and the Gaussian error samples are generated here.
-__device__ __forceinline__ float pz_input_value(const LaunchArgs& a, long long row, int j, int D) {
-  const long long es = (a.mode == MODE_POSTERIOR) ? row / a.G : row;  // sample index
-  const long long vs = a.S > 0 ? es / a.S : es;                         // variant index (== unit without a marginal axis)
-  const long long unit = a.V > 0 ? vs / a.V : vs;                       // row of X
+// Where evaluation row `row` sits on the expansion axes (posterior grid point, error sample, marginal variant, unit):
+// computed ONCE per row -- the divisions are 64-bit and there is one per axis.
+struct RowIndex {
+  long long es;    // error-sample index (== variant == unit without those axes): keys the eps stream
+  long long vs;    // variant index: row of mvals
+  long long unit;  // row of X / cond
+  int g;           // posterior grid point
+};
+__device__ __forceinline__ RowIndex pz_row_index(const LaunchArgs& a, long long row) {
+  RowIndex r;
+  if (a.mode == MODE_POSTERIOR) {
+    // rows of one launch stay below 2^31 in every caller of this library (chunked host pipeline, bounded scratch):
+    // take the cheap 32-bit division when they do
+    if (row < 0x7fffffffLL) {
+      const unsigned q = (unsigned)row / (unsigned)a.G;
+      r.es = q;
+      r.g = (int)((unsigned)row - q * (unsigned)a.G);
+    } else {
+      r.es = row / a.G;
+      r.g = (int)(row - r.es * a.G);
+    }
+  } else {
+    r.es = row;
+    r.g = 0;
+  }
+  r.vs = a.S > 0 ? r.es / a.S : r.es;
+  r.unit = a.V > 0 ? r.vs / a.V : r.vs;
+  return r;
+}
+
+// Value of data column j (logical order) and of condition j for an evaluation row: the posterior's grid expansion
+// (pzflow/flow.py:697-714), the marginal variants and the Gaussian error samples are generated here.
+__device__ __forceinline__ float pz_input_value(const LaunchArgs& a, const RowIndex& r, int j, int D) {
   int jj = j, W = D;
   if (a.mode == MODE_POSTERIOR) {
-    if (j == a.col_idx) return a.grid[(int)(row - es * a.G)];
+    if (j == a.col_idx) return a.grid[r.g];
     jj = j < a.col_idx ? j : j - 1;
     W = D - 1;
   }
   if (a.V > 0) {
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (q < a.n_mcols && a.mcol[q] == j) return a.mvals[vs * a.n_mcols + q];  // a marginalised column: no error model
+      if (q < a.n_mcols && a.mcol[q] == j) return a.mvals[r.vs * a.n_mcols + q];  // a marginalised column: no error model
   }
-  float v = a.X[unit * W + jj];
+  float v = a.X[r.unit * W + jj];
   if (a.S > 0 && a.Xerr != nullptr)
-    v = v + pz_err_normal(a.seed, 0u, (unsigned long long)(es + a.unit0 * a.S * (a.V > 0 ? a.V : 1)), jj) * a.Xerr[unit * W + jj];
+    v = v + pz_err_normal(a.seed, 0u, (unsigned long long)(r.es + a.unit0 * a.S * (a.V > 0 ? a.V : 1)), jj) * a.Xerr[r.unit * W + jj];
   return v;
 }
 
-__device__ __forceinline__ float pz_cond_value(const LaunchArgs& a, long long row, int j, int C) {
+__device__ __forceinline__ float pz_cond_value(const LaunchArgs& a, const RowIndex& r, int j, int C) {
   if (a.cond == nullptr) return 0.0f;
-  const long long es = (a.mode == MODE_POSTERIOR) ? row / a.G : row;
-  const long long vs = a.S > 0 ? es / a.S : es;
-  const long long unit = a.V > 0 ? vs / a.V : vs;
-  float v = a.cond[unit * C + j];
+  float v = a.cond[r.unit * C + j];
   if (a.S > 0 && a.cond_err != nullptr)
-    v = v + pz_err_normal(a.seed, 1u, (unsigned long long)(es + a.unit0 * a.S * (a.V > 0 ? a.V : 1)), j) * a.cond_err[unit * C + j];
+    v = v + pz_err_normal(a.seed, 1u, (unsigned long long)(r.es + a.unit0 * a.S * (a.V > 0 ? a.V : 1)), j) * a.cond_err[r.unit * C + j];
   return v;
 }
 
