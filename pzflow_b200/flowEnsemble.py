@@ -14,11 +14,11 @@ import numpy as np
 import pandas as pd
 import torch
 
-from . import distributions
+from . import distributions, sharding
 from .bijectors import Bijector_Info, InitFunction
 from .flow import Flow, _load_pickle
 from .plan import (ensemble_log_prob_host_columns, ensemble_logmeanexp, ensemble_posterior_host,
-                   ensemble_posterior_mean, normalize_pdfs_)
+                   ensemble_posterior_mean, normalize_pdfs_, host_result)
 
 
 def _frame_rows_to_device(inputs: pd.DataFrame, columns, device) -> torch.Tensor:
@@ -141,6 +141,16 @@ class FlowEnsemble:
         plans = [flow._plan() for flow in flows]
         if len({(p.device, p.input_dim, p.n_conditions) for p in plans}) != 1:
             return None
+        devices = flows[0]._device_plans(len(inputs))
+        if len(devices) > 1:   # one process, several GPUs: every device evaluates all flows on its block of rows
+            per_dev = {d: [flow._plan(device=d) for flow in flows] for d in devices}
+            out = host_result((len(inputs),))
+
+            def block(dev, a, b):
+                ensemble_log_prob_host_columns(per_dev[dev], [c[a:b] for c in cols],
+                                               None if ccols is None else [c[a:b] for c in ccols], means, stds, out=out[a:b])
+            sharding.run_sharded(len(inputs), list(devices), block)
+            return out.numpy()
         return ensemble_log_prob_host_columns(plans, cols, ccols, means, stds).numpy()
 
     def posterior(self, inputs: pd.DataFrame, column: str, grid, marg_rules: dict = None,
@@ -194,8 +204,18 @@ class FlowEnsemble:
         columns.remove(column)
         nrows = inputs.shape[0]
         rest = np.ascontiguousarray(inputs[columns].to_numpy().reshape(nrows, -1), dtype=np.float32)
-        return ensemble_posterior_host(plans, rest, idx, grid, f0._get_conditions(inputs), normalize=normalize,
-                                       nan_to_zero=nan_to_zero).numpy()
+        cond = f0._get_conditions(inputs)
+        devices = f0._device_plans(nrows * len(grid))
+        if len(devices) > 1:
+            per_dev = {d: [flow._plan(device=d) for flow in flows] for d in devices}
+            out = host_result((nrows, len(grid)))
+
+            def block(dev, a, b):
+                ensemble_posterior_host(per_dev[dev], rest[a:b], idx, grid, None if cond is None else cond[a:b],
+                                        normalize=normalize, nan_to_zero=nan_to_zero, out=out[a:b])
+            sharding.run_sharded(nrows, list(devices), block)
+            return out.numpy()
+        return ensemble_posterior_host(plans, rest, idx, grid, cond, normalize=normalize, nan_to_zero=nan_to_zero).numpy()
 
     def sample(self, nsamples: int = 1, conditions: pd.DataFrame = None, save_conditions: bool = True,
                seed: int = None, returnEnsemble: bool = False) -> pd.DataFrame:

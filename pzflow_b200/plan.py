@@ -586,7 +586,8 @@ class Plan:
 
 
 # ---- reductions that are not tied to one plan ---------------------------------
-def ensemble_log_prob_host_columns(plans, data_cols, cond_cols=None, cond_means=None, cond_stds=None) -> torch.Tensor:
+def ensemble_log_prob_host_columns(plans, data_cols, cond_cols=None, cond_means=None, cond_stds=None,
+                                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """FlowEnsemble.log_prob from DataFrame COLUMNS (float64, or all float32): each chunk of rows is staged once,
     evaluated by every plan and reduced with log(mean(exp)) on the device (pzb_ensemble_log_prob_host_columns).
     Returns a CPU tensor [N]."""
@@ -613,7 +614,8 @@ def ensemble_log_prob_host_columns(plans, data_cols, cond_cols=None, cond_means=
     handles = (C.c_void_p * len(plans))(*[p._h for p in plans])
     dptr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
     cptr = (C.c_void_p * max(1, len(ccols)))(*[c.ctypes.data for c in ccols]) if ccols else None
-    out = host_result((n,))
+    if out is None:
+        out = host_result((n,))
     N.check(N.lib().pzb_ensemble_log_prob_host_columns(
         handles, len(plans), dptr, int(f32), cptr, means.ctypes.data if means is not None else None,
         stds.ctypes.data if stds is not None else None, n, _ptr(out)))
@@ -621,7 +623,7 @@ def ensemble_log_prob_host_columns(plans, data_cols, cond_cols=None, cond_means=
 
 
 def ensemble_posterior_host(plans, rest, col_idx: int, grid, cond=None, normalize: bool = True,
-                            nan_to_zero: bool = True) -> torch.Tensor:
+                            nan_to_zero: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """FlowEnsemble.posterior on HOST arrays (pzb_ensemble_posterior_host): rest [Ng, D-1], grid [G] -> pdfs [Ng, G],
     the mean over the plans' un-normalised pdfs, normalised on the device chunk by chunk."""
     p0 = plans[0]
@@ -629,7 +631,8 @@ def ensemble_posterior_host(plans, rest, col_idx: int, grid, cond=None, normaliz
     cond = p0._host_cond(cond, rest.shape[0])
     grid = torch.as_tensor(grid).to(dtype=torch.float32).contiguous().reshape(-1).cpu()
     Ng, G = rest.shape[0], grid.numel()
-    out = host_result((Ng, G))
+    if out is None:
+        out = host_result((Ng, G))
     handles = (C.c_void_p * len(plans))(*[p._h for p in plans])
     N.check(N.lib().pzb_ensemble_posterior_host(handles, len(plans), _ptr(rest) if rest.numel() else None, _ptr(cond),
                                                 Ng, int(col_idx), _ptr(grid), G, int(bool(normalize)),

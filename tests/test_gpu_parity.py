@@ -1703,6 +1703,15 @@ def test_one_process_shards_host_arrays_over_all_gpus(monkeypatch):
     c1, cs1 = cf.log_prob(cdf), cf.sample(2, conditions=cdf.iloc[:12_000], seed=3)
     sharding.set_devices("all")
     cn, csn = cf.log_prob(cdf), cf.sample(2, conditions=cdf.iloc[:12_000], seed=3)
+    # an ensemble shards the same way (every device evaluates all flows on its block of rows)
+    from pzflow_b200 import FlowEnsemble
+    ens = FlowEnsemble(data_columns=("a", "b", "c"), conditional_columns=("p", "q"), N=3,
+                       bijector=Chain(ShiftBounds(-np.ones(3), np.ones(3), 4.0), RollingSplineCoupling(3, n_conditions=2)))
+    eg = np.linspace(-1, 1, 40).astype(np.float32)
+    en, epn = ens.log_prob(cdf), ens.posterior(cdf.iloc[:1500], "a", eg)
+    sharding.set_devices([0])
+    e1, ep1 = ens.log_prob(cdf), ens.posterior(cdf.iloc[:1500], "a", eg)
+    assert np.array_equal(e1.view(np.int32), en.view(np.int32)) and np.array_equal(ep1.view(np.int32), epn.view(np.int32))
     sharding.set_devices(None)
     assert np.array_equal(c1.view(np.int32), cn.view(np.int32))
     assert np.array_equal(np.ascontiguousarray(cs1.to_numpy(), dtype=np.float64).view(np.int64),
