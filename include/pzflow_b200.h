@@ -59,7 +59,12 @@ typedef enum {
   PZB_STAGE_REVERSE = 7,          /* pzflow/bijectors.py:525-556: columns reversed (folded like Roll)          */
   PZB_STAGE_SCALE = 8,            /* pzflow/bijectors.py:668-714: B = scale                                     */
   PZB_STAGE_INV_SOFTPLUS = 9,     /* pzflow/bijectors.py:314-372: vec_a = column indices, vec_b = sharpness(es) */
-  PZB_STAGE_COLOR_TRANSFORM = 10  /* pzflow/bijectors.py:177-311: shift = ref_idx, vec_a = mag_idx, n_vec       */
+  PZB_STAGE_COLOR_TRANSFORM = 10, /* pzflow/bijectors.py:177-311: shift = ref_idx, vec_a = mag_idx, n_vec       */
+  PZB_STAGE_SHUFFLE = 11,         /* pzflow/bijectors.py:780-814: out[:, j] = in[:, perm[j]], vec_a = perm (as floats),
+                                     n_vec = D; the caller derives perm from the jax key schedule (folded like Roll) */
+  PZB_STAGE_DEQUANTIZE = 12       /* pzflow/bijectors.py:865-911 (UniformDequantizer) AS THE REFERENCE EXECUTES IT: the
+                                     forward map is the identity (its .at[].set() result is discarded, line 897), the
+                                     inverse floors the columns vec_a[0, n_vec); log-det 0 both ways */
 } pzb_stage_kind;
 
 /* Latent distributions of the hot path. */
@@ -232,6 +237,17 @@ int pzb_normalize_pdfs(float *pdfs, int64_t Ng, int32_t G, const float *grid,
  * call sharded over rows (several GPUs, several chunks) draws exactly what one big call would; row_offset * D must be
  * a multiple of 4 for the uniform and the normal sampler (their draws come in blocks of four). */
 int pzb_sample_uniform(float *U, int64_t N, int32_t D, float B, uint64_t seed, int64_t row_offset, void *stream);
+
+/* Uniform.sample (pzflow/distributions.py:464-469) in jax's OWN random stream: rows [row_offset, row_offset + N) of
+ * jax.random.uniform(key, shape=(total_rows, D), minval, maxval), key = (key0, key1) -- PRNGKey(seed) with x64
+ * disabled is (0, seed mod 2^32).  Threefry-2x32/20 in the layout of jax's default PRNG implementation: the count
+ * vector iota(total_rows * D) rides through the block function as two halves (partitionable = 0; this layout
+ * reproduces the samples printed from real JAX at docs/tutorials/marginalization.ipynb:133-135), or one block per
+ * element with its two words xor-ed (partitionable = 1, jax_threefry_partitionable=True; unverified here).  total_rows
+ * is needed because the original layout pairs element g with g + ceil(total / 2).  A request of 2^32 - 1 words or more
+ * in the original layout returns PZB_ERR_UNSUPPORTED (jax cuts those into separately keyed blocks). */
+int pzb_sample_uniform_threefry(float *U, int64_t N, int32_t D, float minval, float maxval, uint32_t key0, uint32_t key1,
+                                int64_t total_rows, int64_t row_offset, int32_t partitionable, void *stream);
 
 /* The other latents' draws (pzflow/distributions.py:101-135 CentBeta, 196-229 CentBeta13, 277-303 Normal, 360-392
  * Tdist), each from its own counter-based Philox stream keyed by (seed, element index):

@@ -38,6 +38,12 @@ class ShimArray(np.ndarray):
     def __array_finalize__(self, obj):
         pass
 
+    def astype(self, dtype, *args, **kwargs):
+        # jax with x64 disabled: a request for float64 (e.g. ``.astype(float)``, pzflow/bijectors.py:896) yields float32
+        if dtype is float or np.dtype(dtype) == np.float64:
+            dtype = _F32
+        return np.ndarray.astype(self, dtype, *args, **kwargs)
+
     @property
     def at(self):
         return _At(self)
@@ -154,8 +160,28 @@ def _make_jnp() -> types.ModuleType:
 # --------------------------------------------------------------------------- #
 # jax.random (NumPy streams -- NOT threefry)                                  #
 # --------------------------------------------------------------------------- #
-def _make_random() -> types.ModuleType:
+def _make_random(prng: str = "numpy") -> types.ModuleType:
     rnd = types.ModuleType("jax.random")
+    if prng == "threefry":
+        # jax's own streams (oracle/jax_prng.py: Threefry-2x32/20 in the original layout, pinned by the samples real JAX
+        # printed in docs/tutorials/marginalization.ipynb) for keys, split, uniform and permutation; normal / beta keep
+        # NumPy generators seeded by the key words (their jax algorithms -- erf_inv, the gamma rejection loop -- are not
+        # restated), so only Uniform latents, key schedules and Shuffle are stream-exact in this mode.
+        from .. import jax_prng as J
+
+        def _g(key):
+            return np.random.default_rng([int(v) for v in np.asarray(key).ravel()])
+
+        rnd.PRNGKey = J.PRNGKey
+        rnd.split = lambda key, num=2: J.split(np.asarray(key), num)
+        rnd.uniform = lambda key, shape=(), dtype=np.float32, minval=0.0, maxval=1.0: _out(
+            J.uniform(np.asarray(key), tuple(shape), minval, maxval))
+        rnd.permutation = lambda key, x: _out(np.asarray(x)[J.permutation(np.asarray(key), len(np.asarray(x)))])
+        rnd.normal = lambda key, shape=(), dtype=np.float32: _out(_g(key).standard_normal(size=shape).astype(_F32))
+        rnd.beta = lambda key, a, b, shape=None, dtype=np.float32: _out(_g(key).beta(a, b, size=shape).astype(_F32))
+        rnd.multivariate_normal = lambda key, mean, cov, shape=None: _out(
+            _g(key).multivariate_normal(np.asarray(mean), np.asarray(cov), size=shape).astype(_F32))
+        return rnd
 
     def PRNGKey(seed):
         seed = int(seed)
@@ -308,13 +334,15 @@ def _make_stax(rnd, nn):
     return stax
 
 
-def install(reference_root: str = REFERENCE_ROOT):
-    """Register the stand-in modules and make the reference importable. Returns ``pzflow``."""
+def install(reference_root: str = REFERENCE_ROOT, prng: str = "numpy"):
+    """Register the stand-in modules and make the reference importable. Returns ``pzflow``.
+    prng: "numpy" (the streams every round-1/2 golden was cut with) or "threefry" (jax's own key schedule and uniform
+    stream, see _make_random)."""
     if "jax" in sys.modules and not getattr(sys.modules["jax"], "__pzb_shim__", False):
         raise RuntimeError("a real jax is already imported; use it instead of the shim")
     jax = types.ModuleType("jax")
     jax.__pzb_shim__ = True
-    jnp, rnd, nn = _make_jnp(), _make_random(), _make_nn()
+    jnp, rnd, nn = _make_jnp(), _make_random(prng), _make_nn()
     sp, special, stats, integrate = _make_scipy()
     ex = types.ModuleType("jax.example_libraries")
     stax = _make_stax(rnd, nn)

@@ -301,9 +301,56 @@ def case_ensemble_sample(pzflow):
     _save("ensemble_sample", store)
 
 
+def case_jax_streams(pzflow):
+    """Round 3, stand-in installed with prng="threefry" (jax's own key schedule and uniform stream, oracle/jax_prng.py):
+    the reference's Flow.sample for seeds (pzflow/flow.py:783-795 -> distributions.py:464-469), and flows whose chains
+    hold Shuffle stages (bijectors.py:780-814; permutation from the key Chain.init_fun hands down, 146-149) and a
+    UniformDequantizer (865-911), built with two seeds and re-built from a save dictionary (flow.py:186-187: PRNGKey(0))."""
+    from pzflow import Flow, examples
+    from pzflow import bijectors as B
+    from pzflow import distributions as Dn
+    import jax.numpy as jnp
+    flow = examples.get_example_flow()
+    store = {}
+    store["example_sample_2_seed0"] = flow.sample(2, seed=0).to_numpy().astype(np.float32)
+    store["example_latent_1001_seed7"] = _np(flow.latent.sample((), 1001, 7))
+    store["example_sample_1001_seed7"] = flow.sample(1001, seed=7).to_numpy().astype(np.float32)
+    rng = np.random.default_rng(5)
+    n, D = 64, 5
+    X = rng.uniform(-1.0, 1.0, size=(n, D)).astype(np.float32)
+    X[:, 2] = np.floor(X[:, 2] * 4)        # a discrete column for the dequantizer
+    mins, maxs = X.min(axis=0) - 0.5, X.max(axis=0) + 1.5
+    cols = tuple("abcde")
+    df = pd.DataFrame(X.astype(np.float64), columns=cols)
+    store["X"], store["mins"], store["maxs"] = X, mins, maxs
+
+    def bijector():
+        return B.Chain(B.UniformDequantizer([2]), B.ShiftBounds(jnp.array(mins), jnp.array(maxs), 4.0), B.Shuffle(),
+                       B.RollingSplineCoupling(3, K=8, hidden_dim=32), B.Chain(B.Reverse(), B.Shuffle()),
+                       B.RollingSplineCoupling(2, K=8, hidden_dim=32))
+    for seed in (0, 3):
+        fl = Flow(cols, bijector(), latent=Dn.Uniform(D, 5), seed=seed)
+        _boost(fl._params[1], np.random.default_rng(40 + seed))
+        tag = f"s{seed}"
+        if seed == 0:
+            F.pack_tree("shuffle_info", fl._bijector_info, store)
+        F.pack_tree(f"{tag}_params", fl._params[1], store)
+        store[f"{tag}_log_prob"] = _np(fl.log_prob(df))
+        u, ld = fl._forward(fl._params[1], jnp.array(X), conditions=jnp.zeros((n, 1)))
+        store[f"{tag}_forward_u"], store[f"{tag}_forward_ld"] = _np(u), _np(ld)
+        store[f"{tag}_sample_9_seed5"] = fl.sample(9, seed=5).to_numpy().astype(np.float32)
+        if seed == 3:
+            again = Flow(_dictionary=fl._save_dict())     # what Flow(file=...) does after unpickling
+            store["s3_reloaded_log_prob"] = _np(again.log_prob(df))
+    _save("jax_streams", store)
+
+
 def main():
-    pzflow = jax_shim.install()
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "round3":
+        case_jax_streams(jax_shim.install(prng="threefry"))
+        return
+    pzflow = jax_shim.install()
     if len(sys.argv) > 1 and sys.argv[1] == "round2":
         case_marg_rules(pzflow)
         case_ensemble_sample(pzflow)

@@ -316,6 +316,40 @@ def color_transform(inputs, ref_idx, mag_idx, inverse):
     return outputs.astype(inputs.dtype), zeros
 
 
+def shuffle(inputs, perm, inverse):
+    """bijectors.py:798-810 -- inputs[:, perm] forward, inputs[:, argsort(perm)] inverse, log_det 0."""
+    perm = np.asarray(perm, dtype=np.int64)
+    idx = np.argsort(perm) if inverse else perm
+    return inputs[:, idx].copy(), np.zeros(inputs.shape[0], dtype=inputs.dtype)
+
+
+def uniform_dequantizer(inputs, column_idx, inverse):
+    """bijectors.py:892-907 AS EXECUTED: forward returns inputs.astype(float) unchanged (line 897 drops the result of
+    .at[].set()), inverse floors the listed columns; log_det 0."""
+    out = inputs.copy()
+    if inverse:
+        idx = np.atleast_1d(column_idx)
+        out[:, idx] = np.floor(inputs[:, idx])
+    return out, np.zeros(inputs.shape[0], dtype=inputs.dtype)
+
+
+def resolve_shuffles(info, key, input_dim):
+    """Give every ("Shuffle", ()) of ``info`` the permutation the reference draws for it: Chain.init_fun splits its key
+    once per stage (bijectors.py:146-149), Shuffle.init_fun calls random.permutation(rng, arange(input_dim)) (795-797).
+    key: jax-style uint32 pair (oracle.jax_prng.PRNGKey(seed); PRNGKey(0) for a flow loaded from a file, flow.py:186-187)."""
+    from . import jax_prng as J
+    name, args = info
+    if name == "Shuffle":
+        return info if len(args) == 1 else ("Shuffle", (tuple(int(v) for v in J.permutation(key, input_dim)),))
+    if name != "Chain":
+        return info
+    out = []
+    for sub in args:
+        key, layer = J.split(key)
+        out.append(resolve_shuffles(sub, layer, input_dim))
+    return ("Chain", tuple(out))
+
+
 def apply_bijector(info, params, inputs, conditions, inverse=False, bins=None):
     """Interpret a Bijector_Info tuple the way utils.py:11-19 rebuilds it and
     bijectors.py:155-170 (Chain) runs it.  Returns (outputs, log_det)."""
@@ -348,6 +382,12 @@ def apply_bijector(info, params, inputs, conditions, inverse=False, bins=None):
         return inv_softplus(inputs, args[0], args[1] if len(args) > 1 else 1, inverse)
     if name == "ColorTransform":
         return color_transform(inputs, args[0], args[1], inverse)
+    if name == "Shuffle":
+        if len(args) != 1:
+            raise ValueError("oracle: Shuffle needs its permutation (resolve_shuffles)")
+        return shuffle(inputs, args[0], inverse)
+    if name == "UniformDequantizer":
+        return uniform_dequantizer(inputs, args[0], inverse)
     raise NotImplementedError(f"oracle: bijector {name!r} is outside the hot path (SURVEY.md §2)")
 
 

@@ -28,6 +28,8 @@ STAGE_REVERSE = 7
 STAGE_SCALE = 8
 STAGE_INV_SOFTPLUS = 9
 STAGE_COLOR_TRANSFORM = 10
+STAGE_SHUFFLE = 11
+STAGE_DEQUANTIZE = 12
 
 LATENT_UNIFORM = 1
 LATENT_CENTBETA13 = 2
@@ -104,6 +106,8 @@ SIGNATURES = {
     "pzb_normalize_pdfs": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_void_p]),
     "pzb_sample_uniform": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_int64, C.c_void_p]),
+    "pzb_sample_uniform_threefry": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_uint32, C.c_uint32,
+                                              C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "pzb_set_host_threads": (C.c_int, [C.c_int32]),
     "pzb_sample_centbeta": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64,
                                       C.c_int64, C.c_void_p]),

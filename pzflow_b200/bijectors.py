@@ -9,9 +9,12 @@ functions an ``InitFunction`` returns do not run stage by stage: each one
 compiles the WHOLE bijector it belongs to (nested Chains included) into one
 device plan and evaluates it with one fused CUDA kernel through the C-ABI.
 
-Not provided: Shuffle (its permutation is drawn from the jax PRNG at init time and is
-not stored in the Bijector_Info or the params, so it cannot be reproduced without jax) and
-UniformDequantizer (training-time noise).
+Shuffle (780-814) draws its permutation from the jax key its InitFunction receives, and stores it nowhere: the key
+schedule of the reference (PRNGKey(seed), one ``random.split`` per Chain stage, ``random.permutation``) is reproduced
+on the host (pzflow_b200.prng, plan.resolve_shuffles), so a flow built with the same ``seed`` gets the reference's
+permutation; like ``Roll`` it then costs nothing (folded into the column maps of the plan).  UniformDequantizer
+(865-911) is provided AS THE REFERENCE EXECUTES IT: its forward map is the identity (line 897 discards the result of
+``.at[].set()``), its inverse floors the listed columns.
 """
 from __future__ import annotations
 
@@ -21,6 +24,7 @@ from typing import Callable, Sequence, Tuple, Union
 import numpy as np
 import torch
 
+from . import prng
 from .plan import Plan, PlanCache
 
 Pytree = Union[tuple, list]
@@ -81,6 +85,23 @@ def _generator(rng) -> np.random.Generator:
     return np.random.default_rng(np.random.SeedSequence([int(v) for v in arr]))
 
 
+def _jax_key(rng):
+    """The jax-style key an InitFunction's ``rng`` stands for: an int seed is PRNGKey(seed), a uint32 pair is a key;
+    NumPy generators (which no jax program can hold) get a key derived from their state."""
+    if rng is None:
+        return None
+    if isinstance(rng, (int, np.integer)):
+        return prng.key_from_seed(int(rng))
+    if isinstance(rng, np.random.Generator):
+        return None  # a nested stage of a Chain: only the outermost InitFunction resolves Shuffles
+    if isinstance(rng, np.random.SeedSequence):
+        return np.asarray(rng.generate_state(2), dtype=np.uint32)
+    arr = np.asarray(rng)
+    if arr.shape == (2,):
+        return arr.astype(np.uint32)
+    return None
+
+
 def _split(rng: np.random.Generator) -> Tuple[np.random.Generator, np.random.Generator]:
     a, b = rng.bit_generator.seed_seq.spawn(2) if hasattr(rng.bit_generator, "seed_seq") else \
         np.random.SeedSequence(int(rng.integers(2 ** 63))).spawn(2)
@@ -92,14 +113,15 @@ class _FusedFunctions:
 
     _MAX_PLANS = 4
 
-    def __init__(self, info: Bijector_Info, input_dim: int) -> None:
+    def __init__(self, info: Bijector_Info, input_dim: int, key=None) -> None:
         self.info = info
         self.input_dim = input_dim
+        self.key = key  # the jax-style key the InitFunction was called with (Shuffle's permutation hangs on it)
         self._plans = PlanCache(self._MAX_PLANS)
 
     def plan(self, params: Pytree) -> Plan:
         device = torch.cuda.current_device() if torch.cuda.is_available() else -1
-        return self._plans.get(params, device, lambda: Plan(self.info, params, self.input_dim))
+        return self._plans.get(params, device, lambda: Plan(self.info, params, self.input_dim, rng_key=self.key))
 
     @staticmethod
     def _out(t: torch.Tensor, like):
@@ -114,8 +136,8 @@ class _FusedFunctions:
         return self._out(x, inputs), self._out(ld, inputs)
 
 
-def _fused(info: Bijector_Info, input_dim: int):
-    f = _FusedFunctions(info, input_dim)
+def _fused(info: Bijector_Info, input_dim: int, key=None):
+    f = _FusedFunctions(info, input_dim, key)
     return ForwardFunction(f.forward), InverseFunction(f.inverse)
 
 
@@ -146,13 +168,14 @@ def Chain(*inputs: Sequence[Tuple[InitFunction, Bijector_Info]]) -> Tuple[InitFu
 
     @InitFunction
     def init_fun(rng, input_dim, **kwargs):
+        key = _jax_key(rng)
         rng = _generator(rng)
         all_params = []
         for init_f in init_funs:
             rng, layer_rng = _split(rng)
             param, _, _ = init_f(layer_rng, input_dim)
             all_params.append(param)
-        forward_fun, inverse_fun = _fused(bijector_info, input_dim)
+        forward_fun, inverse_fun = _fused(bijector_info, input_dim, key)
         return all_params, forward_fun, inverse_fun
 
     return init_fun, bijector_info
@@ -250,7 +273,7 @@ def StandardScaler(means, stds) -> Tuple[InitFunction, Bijector_Info]:
 def _parameter_free(bijector_info: Bijector_Info) -> InitFunction:
     @InitFunction
     def init_fun(rng, input_dim, **kwargs):
-        forward_fun, inverse_fun = _fused(bijector_info, input_dim)
+        forward_fun, inverse_fun = _fused(bijector_info, input_dim, _jax_key(rng))
         return (), forward_fun, inverse_fun
 
     return init_fun
@@ -298,4 +321,22 @@ def Scale(scale: float) -> Tuple[InitFunction, Bijector_Info]:
     elif not isinstance(scale, float):
         raise ValueError("scale must be a float or array of floats.")
     bijector_info = ("Scale", (scale,))
+    return _parameter_free(bijector_info), bijector_info
+
+
+@Bijector
+def Shuffle() -> Tuple[InitFunction, Bijector_Info]:
+    """Bijector that randomly permutes inputs (pzflow/bijectors.py:780-814).  The permutation is
+    ``jax.random.permutation(rng, arange(input_dim))`` of the key the InitFunction receives -- reproduced on the host
+    (pzflow_b200.prng) -- and, like Roll, is folded into the plan's column maps."""
+    bijector_info = ("Shuffle", ())
+    return _parameter_free(bijector_info), bijector_info
+
+
+@Bijector
+def UniformDequantizer(column_idx) -> Tuple[InitFunction, Bijector_Info]:
+    """Bijector that dequantizes discrete variables with uniform noise (pzflow/bijectors.py:865-911) -- as the
+    reference executes it: forward is the identity (the noise is computed and dropped, line 897), inverse floors the
+    column(s) ``column_idx``; log-det 0 both ways."""
+    bijector_info = ("UniformDequantizer", (column_idx,))
     return _parameter_free(bijector_info), bijector_info

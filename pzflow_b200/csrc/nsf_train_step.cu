@@ -508,7 +508,8 @@ train_step_kernel(const PlanDev* __restrict__ plan, const TrainOffsets* __restri
       const AffineDev& af = plan->affine[step.idx];
       for (int e = tid; e < D * TS_ROWS; e += TS_THREADS) {
         const int j = e / TS_ROWS, r = e - j * TS_ROWS;
-        const float s = af.kind == AFF_SHIFT_BOUNDS ? af.B / af.b[j] : (af.kind == AFF_STANDARD_SCALER ? 1.0f / af.b[j] : af.B);
+        const float s = af.kind == AFF_SHIFT_BOUNDS ? af.B / af.b[j]
+                        : (af.kind == AFF_STANDARD_SCALER ? 1.0f / af.b[j] : (af.kind == AFF_DEQUANTIZE ? 1.0f : af.B));
         gx[ts_swz(j, r)] *= s;
       }
       __syncthreads();

@@ -330,6 +330,53 @@ int pzb_plan_create(const pzb_stage_desc* stages, int32_t n_stages, int32_t inpu
         memcpy(cur, nxt, sizeof(int) * D);
         break;
       }
+      case PZB_STAGE_SHUFFLE: {
+        // out[:, j] = in[:, perm[j]]  (pzflow/bijectors.py:800-804); perm comes from the caller's jax key schedule
+        if (sd.vec_a == nullptr || sd.n_vec != D) {
+          rc = fail(PZB_ERR_INVALID, "plan_create: Shuffle needs a permutation of %d columns", D);
+          break;
+        }
+        int nxt[MAX_D];
+        bool seen[MAX_D] = {false};
+        for (int j = 0; j < D && rc == PZB_OK; ++j) {
+          const int src = (int)sd.vec_a[j];
+          if (src < 0 || src >= D || seen[src]) {
+            rc = fail(PZB_ERR_INVALID, "plan_create: Shuffle's column list is not a permutation");
+            break;
+          }
+          seen[src] = true;
+          nxt[j] = cur[src];
+        }
+        if (rc != PZB_OK) break;
+        memcpy(cur, nxt, sizeof(int) * D);
+        break;
+      }
+      case PZB_STAGE_DEQUANTIZE: {
+        // UniformDequantizer as the reference executes it (pzflow/bijectors.py:892-907): forward identity, inverse floor
+        if (hp.n_affine >= MAX_AFFINE) {
+          rc = fail(PZB_ERR_UNSUPPORTED, "plan_create: more than %d elementwise stages", MAX_AFFINE);
+          break;
+        }
+        if (sd.vec_a == nullptr || sd.n_vec < 1) {
+          rc = fail(PZB_ERR_INVALID, "plan_create: UniformDequantizer needs column indices");
+          break;
+        }
+        AffineDev& af = hp.affine[hp.n_affine];
+        memset(&af, 0, sizeof(af));
+        af.kind = AFF_DEQUANTIZE;
+        for (int v = 0; v < sd.n_vec; ++v) {
+          int c = (int)sd.vec_a[v];
+          if (c < 0) c += D;  // numpy-style negative index
+          if (c < 0 || c >= D) {
+            rc = fail(PZB_ERR_INVALID, "plan_create: UniformDequantizer column %d outside [0, %d)", (int)sd.vec_a[v], D);
+            break;
+          }
+          af.b[cur[c]] = 1.0f;
+        }
+        if (rc != PZB_OK) break;
+        hp.steps[hp.n_steps++] = {STEP_AFFINE, hp.n_affine++};
+        break;
+      }
       case PZB_STAGE_SCALE:
       case PZB_STAGE_INV_SOFTPLUS: {
         if (hp.n_affine >= MAX_AFFINE) {
@@ -944,6 +991,58 @@ sample_uniform_kernel(float* __restrict__ U, long long n, float B, uint64_t seed
   }
 }
 
+// Threefry-2x32, 20 rounds (Salmon et al., SC'11): the block function of jax's default PRNG.
+__device__ __forceinline__ void pz_threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  constexpr int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  x0 += ks[0];
+  x1 += ks[1];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      x0 += x1;
+      x1 = __funnelshift_l(x1, x1, R[i & 1][r]) ^ x0;
+    }
+    x0 += ks[(i + 1) % 3];
+    x1 += ks[(i + 2) % 3] + (uint32_t)(i + 1);
+  }
+}
+
+// jax.random.uniform(key, (total_rows, D), minval, maxval) -- elements [e0, e0 + n) of its n_total, in jax's stream
+// layout (pzflow/distributions.py:464-469).  Original layout: the count vector iota(n_total) is cut into two halves
+// that ride through the block function together (element g < h pairs with g + h, a zero pads an odd count); the
+// partitionable layout gives every element its own block (hi32(g), lo32(g)) and xors the two output words.
+__global__ void __launch_bounds__(256)
+sample_uniform_threefry_kernel(float* __restrict__ U, long long n, long long e0, long long n_total, uint32_t k0, uint32_t k1,
+                               float lo, float hi, int partitionable) {
+  const long long h = (n_total + 1) / 2;
+  const float span = __fsub_rn(hi, lo);
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long g = e + e0;
+    uint32_t x0, x1, bits;
+    if (partitionable) {
+      x0 = (uint32_t)((unsigned long long)g >> 32);
+      x1 = (uint32_t)g;
+      pz_threefry2x32(k0, k1, x0, x1);
+      bits = x0 ^ x1;
+    } else if (g < h) {
+      x0 = (uint32_t)g;
+      x1 = (g + h < n_total) ? (uint32_t)(g + h) : 0u;
+      pz_threefry2x32(k0, k1, x0, x1);
+      bits = x0;
+    } else {
+      x0 = (uint32_t)(g - h);
+      x1 = (uint32_t)g;
+      pz_threefry2x32(k0, k1, x0, x1);
+      bits = x1;
+    }
+    // 23 random mantissa bits -> [1, 2) - 1 -> [0, 1); floats * (maxval - minval) + minval, clamped below (jax's order, no FMA)
+    const float u01 = __fsub_rn(__uint_as_float((bits >> 9) | 0x3f800000u), 1.0f);
+    U[e] = fmaxf(lo, __fadd_rn(__fmul_rn(u01, span), lo));
+  }
+}
+
 int pzb_normalize_pdfs(float* pdfs, int64_t Ng, int32_t G, const float* grid, int32_t normalize,
                        int32_t nan_to_zero, void* stream) {
   if (Ng < 0 || G < 1) return fail(PZB_ERR_INVALID, "normalize_pdfs: bad shape");
@@ -1042,6 +1141,26 @@ static unsigned grid_for(long long n) {
   if (b > (long long)current_num_sms() * 32) b = (long long)current_num_sms() * 32;
   if (b < 1) b = 1;
   return (unsigned)b;
+}
+
+int pzb_sample_uniform_threefry(float* U, int64_t N, int32_t D, float minval, float maxval, uint32_t key0, uint32_t key1,
+                                int64_t total_rows, int64_t row_offset, int32_t partitionable, void* stream) {
+  if (N < 0 || D < 1 || row_offset < 0 || total_rows < row_offset + N)
+    return fail(PZB_ERR_INVALID, "sample_uniform_threefry: bad shape");
+  if (N == 0) return PZB_OK;
+  if (!U) return fail(PZB_ERR_INVALID, "sample_uniform_threefry: NULL buffer");
+  const long long n_total = total_rows * (long long)D;
+  // jax cuts original-layout requests beyond 2^32 - 2 words into separately keyed blocks: not reproduced
+  if (!partitionable && n_total >= 0xFFFFFFFFLL)
+    return fail(PZB_ERR_UNSUPPORTED, "sample_uniform_threefry: %lld elements exceed one threefry call of jax's original layout",
+                n_total);
+  const long long n = N * (long long)D;
+  sample_uniform_threefry_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(U, n, row_offset * (long long)D, n_total, key0,
+                                                                               key1, minval, maxval, partitionable ? 1 : 0);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "sample_uniform_threefry launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
 }
 
 struct BetaShapes {

@@ -25,7 +25,7 @@ constexpr int MAX_CHAIN_DEPTH = 4;
 
 constexpr int MAX_COLOR = 8;
 enum StepKind : int { STEP_AFFINE = 0, STEP_NSC = 1, STEP_CHAIN_BEGIN = 2, STEP_CHAIN_END = 3, STEP_COLOR = 4 };
-enum AffKind : int { AFF_SHIFT_BOUNDS = 1, AFF_STANDARD_SCALER = 2, AFF_SCALE = 3, AFF_INV_SOFTPLUS = 4 };
+enum AffKind : int { AFF_SHIFT_BOUNDS = 1, AFF_STANDARD_SCALER = 2, AFF_SCALE = 3, AFF_INV_SOFTPLUS = 4, AFF_DEQUANTIZE = 5 };
 enum Mode : int { MODE_LOGPROB = 0, MODE_FORWARD = 1, MODE_INVERSE = 2, MODE_POSTERIOR = 3 };
 
 // One dense layer, packed chunk-major: W[n_chunks][in_dim][NC], b[n_chunks][NC]
@@ -238,6 +238,7 @@ __device__ __forceinline__ float pz_cond_value(const LaunchArgs& a, const RowInd
 //   ShiftBounds   fwd B*(x-mean)/half_range ; inv x*half_range/B + mean          (bijectors.py:760-773)
 //   StandardScaler fwd (x-means)/stds ; inv x*stds + means                        (bijectors.py:848-857)
 //   Scale         fwd scale*x ; inv (1/scale)*x                                   (bijectors.py:689-711)
+//   UniformDequantizer fwd x (as the reference runs it) ; inv floor(x) on the listed columns (bijectors.py:892-907)
 //   InvSoftplus   fwd log(-1+exp(k x))/k, ld log(1+exp(-k y)) ; inv log(1+exp(k x))/k, ld -log(1+exp(-k x))
 //                 on the listed columns (k = b[j] != 0)                             (bijectors.py:350-369)
 __device__ __forceinline__ float pz_affine_elem(const AffineDev& af, bool inverse, int j, float x, float& ld) {
@@ -249,6 +250,8 @@ __device__ __forceinline__ float pz_affine_elem(const AffineDev& af, bool invers
       return inverse ? x * af.b[j] + af.a[j] : (x - af.a[j]) / af.b[j];
     case AFF_SCALE:
       return inverse ? (1.0f / af.B) * x : af.B * x;
+    case AFF_DEQUANTIZE:  // forward identity, inverse floor of the flagged columns (bijectors.py:892-907); log-det 0
+      return (inverse && af.b[j] != 0.0f) ? floorf(x) : x;
     default: {
       const float k = af.b[j];
       if (k == 0.0f) return x;

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import plan as _plan
+from . import prng as _prng
 
 Pytree = tuple
 
@@ -66,7 +67,8 @@ class CentBeta13(LatentDist):
         out = lp.sum(dim=1)
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
-    def sample_device(self, nsamples: int, seed: int = None, *, device=None, row_offset: int = 0) -> torch.Tensor:
+    def sample_device(self, nsamples: int, seed: int = None, *, device=None, row_offset: int = 0,
+                      total_rows: int = None) -> torch.Tensor:
         """Draws on ``device`` (default: the current one); ``row_offset`` = index of the first row in the caller's whole
         sample, so that row shards drawn on several devices equal one big draw."""
         shapes = np.full(self.input_dim, 13.0, np.float32)
@@ -95,8 +97,17 @@ class Uniform(LatentDist):
                           torch.full(mask.shape, -math.inf, device=u.device))
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
-    def sample_device(self, nsamples: int, seed: int = None, *, device=None, row_offset: int = 0) -> torch.Tensor:
-        return _plan.sample_uniform(nsamples, self.input_dim, float(self.B), _seed(seed), _device(device), row_offset)
+    def sample_device(self, nsamples: int, seed: int = None, *, device=None, row_offset: int = 0,
+                      total_rows: int = None) -> torch.Tensor:
+        """Rows [row_offset, row_offset + nsamples) of the ``total_rows`` draws of ``seed``, on ``device``.  In the
+        default stream layout these are jax's own numbers -- ``random.uniform(PRNGKey(seed), (total_rows, D), -B, B)``
+        (distributions.py:464-469) -- so ``Flow.sample(n, seed=s)`` returns the reference's rows (pzflow_b200.prng)."""
+        total = nsamples + row_offset if total_rows is None else int(total_rows)
+        lay = _prng.layout()
+        if lay == "philox" or (lay == "threefry" and total * self.input_dim > _prng.MAX_THREEFRY_WORDS):
+            return _plan.sample_uniform(nsamples, self.input_dim, float(self.B), _seed(seed), _device(device), row_offset)
+        return _plan.sample_uniform_jax(nsamples, self.input_dim, float(self.B), _seed(seed), _device(device), row_offset,
+                                        total, lay)
 
     def sample(self, params: Pytree, nsamples: int, seed: int = None):
         """[nsamples, input_dim] draws from U(-B, B) (distributions.py:443-470)."""
@@ -117,7 +128,8 @@ class Normal(LatentDist):
         out = -0.5 * (self.input_dim * math.log(2.0 * math.pi) + (u * u).sum(dim=1))
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
-    def sample_device(self, nsamples: int, seed: int = None, *, device=None, row_offset: int = 0) -> torch.Tensor:
+    def sample_device(self, nsamples: int, seed: int = None, *, device=None, row_offset: int = 0,
+                      total_rows: int = None) -> torch.Tensor:
         return _plan.sample_normal(nsamples, self.input_dim, _seed(seed), _device(device), row_offset)
 
     def sample(self, params: Pytree, nsamples: int, seed: int = None):
@@ -153,7 +165,7 @@ class CentBeta(LatentDist):
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
     def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None, *, device=None,
-                      row_offset: int = 0) -> torch.Tensor:
+                      row_offset: int = 0, total_rows: int = None) -> torch.Tensor:
         params = self._params if params is None else params
         a = np.exp(np.asarray([float(np.asarray(p[0])) for p in params], np.float64)).astype(np.float32)
         b = np.exp(np.asarray([float(np.asarray(p[1])) for p in params], np.float64)).astype(np.float32)
@@ -182,7 +194,7 @@ class Tdist(LatentDist):
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
     def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None, *, device=None,
-                      row_offset: int = 0) -> torch.Tensor:
+                      row_offset: int = 0, total_rows: int = None) -> torch.Tensor:
         """mean + z / sqrt(chi2(nu) / nu) (distributions.py:360-392)."""
         nu = math.exp(float(np.asarray(self._params if params is None else params)))
         return _plan.sample_tdist(nsamples, self.input_dim, nu, _seed(seed), _device(device), row_offset)
@@ -211,11 +223,11 @@ class Joint(LatentDist):
         return out if isinstance(inputs, torch.Tensor) else out.cpu().numpy()
 
     def sample_device(self, nsamples: int, seed: int = None, params: Pytree = None, *, device=None,
-                      row_offset: int = 0) -> torch.Tensor:
+                      row_offset: int = 0, total_rows: int = None) -> torch.Tensor:
         params = self._params if params is None else params
         seeds = np.random.default_rng(_seed(seed)).integers(0, int(1e9), size=len(self.dists))
         cols = []
-        kw = dict(device=device, row_offset=row_offset)
+        kw = dict(device=device, row_offset=row_offset, total_rows=total_rows)
         for dist, p, sd in zip(self.dists, params, seeds):
             if isinstance(dist, (CentBeta, Tdist, Joint)):
                 cols.append(dist.sample_device(nsamples, int(sd), p, **kw).reshape(nsamples, -1))

@@ -127,7 +127,8 @@ class Flow:
             self._bijector_info = save_dict["bijector_info"]
             if self._bijector_info is not None:
                 init_fun, _ = build_bijector_from_info(self._bijector_info)
-                _, self._forward, self._inverse = init_fun(0, self._input_dim)
+                _, self._forward, self._inverse = init_fun(0, self._input_dim)   # PRNGKey(0), as flow.py:186-187
+            self._bijector_seed = 0
             self._params = _to_numpy_tree(save_dict["params"])
             self._condition_means = save_dict["condition_means"]
             self._condition_stds = save_dict["condition_stds"]
@@ -176,6 +177,7 @@ class Flow:
         """Set the bijector (pzflow/flow.py:263-294)."""
         init_fun, self._bijector_info = bijector
         bijector_params, self._forward, self._inverse = init_fun(seed, self._input_dim)
+        self._bijector_seed = seed   # PRNGKey(seed) is what a Shuffle stage draws its permutation from (flow.py:286-287)
         bijector_params = params if params is not None else bijector_params
         self._params = (self.latent._params, bijector_params)
         self._plan_cache = PlanCache(1)
@@ -200,7 +202,7 @@ class Flow:
         return self._plan_cache.get(
             (params[0], params[1]), device,
             lambda: Plan(self._bijector_info, params[1], self._input_dim, self._latent_info, latent_params=params[0],
-                         device=None if device < 0 else device))
+                         device=None if device < 0 else device, rng_key=getattr(self, "_bijector_seed", 0)))
 
     def _device_plans(self, n_rows: int) -> dict:
         """{device index: plan} a host-array call of ``n_rows`` rows (posterior: grid points) is sharded over inside
@@ -267,9 +269,66 @@ class Flow:
         assert err_samples > 0, "err_samples must be a positive integer."
         # Gaussian samples (pzflow/flow.py:455-464): drawn inside the kernel, reduced as log(mean(exp))
         seed = np.random.randint(1e18) if seed is None else seed
+        if self._custom_error_models():
+            # user error models (flow.py:339-395 accepts any callable): called on the host, their samples evaluated by the
+            # fused kernels in sample-major order and reduced by log(mean(exp)) over the samples (flow.py:463-464)
+            from .plan import ensemble_logmeanexp
+            plan, n = self._plan(), len(inputs)
+            out = np.empty(n, dtype=np.float32)
+            Xs = self._err_samples_host(seed, inputs, err_samples, "data")          # ONE call of the model, as the
+            Cs = self._err_samples_host(seed, inputs, err_samples, "conditions")    # reference makes it; [S, n, W]
+            step = max(1, self._HOST_SAMPLE_ROWS // err_samples)
+            for a in range(0, n, step):
+                b = min(n, a + step)
+                rows = np.ascontiguousarray(Xs[:, a:b]).reshape(err_samples * (b - a), -1)
+                cond = None if Cs is None else torch.from_numpy(np.ascontiguousarray(Cs[:, a:b]).reshape(err_samples * (b - a), -1))
+                lp = plan.log_prob(torch.from_numpy(rows), cond)
+                out[a:b] = ensemble_logmeanexp(lp.reshape(err_samples, b - a)).cpu().numpy()
+            return out
         X, Xerr = self._get_err_arrays(inputs, "data")
         C, Cerr = self._get_err_arrays(inputs, "conditions")
         return self._plan().log_prob_err(X, Xerr, C, Cerr, err_samples, seed).cpu().numpy()
+
+    _HOST_SAMPLE_ROWS = 1 << 22   # rows x samples evaluated per step of the custom-error-model route
+
+    def _custom_error_models(self) -> bool:
+        models = [self.data_error_model] + ([self.condition_error_model] if self.conditional_columns is not None else [])
+        return any(m is not None and not _is_gaussian_error_model(m) for m in models)
+
+    def _err_samples_host(self, seed, inputs: pd.DataFrame, err_samples: int, type: str = "data", skip: str = None):
+        """Error samples of each row drawn by the flow's error-model CALLABLE on the host (pzflow/flow.py:339-395), for
+        models other than the default Gaussian one: ``model(key, X[N, W], Xerr[N, W], nsamples) -> [N, nsamples, W]``
+        with NumPy arrays and ``key`` = the uint32 pair jax.random.PRNGKey(seed) would be.  Returned float32 in
+        SAMPLE-MAJOR order [nsamples, N, W] (sample s of input row i at [s, i]), skip column removed
+        (flow.py:381-384), conditions standard-scaled (386-392); None for the conditions of an unconditional flow."""
+        from . import prng
+        if type == "data":
+            columns, model = list(self.data_columns), self.data_error_model
+        elif type == "conditions":
+            if self.conditional_columns is None:
+                return None
+            columns, model = list(self.conditional_columns), self.condition_error_model
+        else:
+            raise ValueError("type must be `data` or `conditions`.")
+        n = len(inputs)
+        X = np.empty((n, len(columns)), dtype=np.float32)
+        Xerr = np.zeros((n, len(columns)), dtype=np.float32)
+        for i, col in enumerate(columns):
+            if col == skip:                      # flow.py:370-373: the skipped column rides along as NaN
+                X[:, i] = np.nan
+                Xerr[:, i] = np.nan
+                continue
+            X[:, i] = inputs[col].to_numpy()
+            if f"{col}_err" in inputs.columns:
+                Xerr[:, i] = inputs[f"{col}_err"].to_numpy()
+        model = gaussian_error_model if model is None else model
+        samples = np.asarray(model(prng.key_from_seed(seed), X, Xerr, err_samples), dtype=np.float32)
+        samples = samples.reshape(n, err_samples, len(columns))
+        if skip is not None:
+            samples = np.delete(samples, columns.index(skip), axis=2)
+        if type == "conditions":
+            samples = (samples - np.asarray(self._condition_means, np.float32)) / np.asarray(self._condition_stds, np.float32)
+        return np.ascontiguousarray(samples.transpose(1, 0, 2), dtype=np.float32)
 
     def _get_err_arrays(self, inputs: pd.DataFrame, type: str = "data", skip: str = None):
         """Means and stds of the error samples for each row (pzflow/flow.py:339-395).  The reference draws
@@ -287,8 +346,9 @@ class Flow:
         else:
             raise ValueError("type must be `data` or `conditions`.")
         if model is not None and not _is_gaussian_error_model(model):
-            raise NotImplementedError("only the default gaussian_error_model is fused into the B200 kernels; "
-                                      "custom error models need the reference's JAX path")
+            raise NotImplementedError("only the default gaussian_error_model is drawn inside the B200 kernels; custom error "
+                                      "models are supported by log_prob / posterior (host-side sampling), not together "
+                                      "with marg_rules or convolve_errs")
         X = inputs[columns].to_numpy().astype(np.float32).reshape(len(inputs), len(columns))
         Xerr = np.zeros_like(X)
         for i, col in enumerate(columns):
@@ -328,6 +388,29 @@ class Flow:
             # flow.py:675-693, 722-724: samples of the other columns / conditions, each expanded over the grid,
             # probabilities averaged over the samples -- all inside the kernel
             plan = self._plan()
+            if self._custom_error_models():
+                # user error models: samples from the callables on the host, posteriors of every sample averaged
+                # (flow.py:722-724), then normalised per galaxy (732-737)
+                from .plan import ensemble_posterior_mean, normalize_pdfs_
+                gdev = torch.from_numpy(grid).to(plan.device)
+                pdfs = np.zeros((nrows, len(grid)), dtype=np.float32)
+                if len(self.data_columns) == 1:
+                    Rs = np.zeros((err_samples, nrows, 0), dtype=np.float32)
+                else:
+                    Rs = self._err_samples_host(seed, inputs, err_samples, "data", skip=column)   # one call of the model
+                Cs = self._err_samples_host(seed, inputs, err_samples, "conditions")
+                step = max(1, self._HOST_SAMPLE_ROWS // (err_samples * len(grid)))
+                for a in range(0, nrows, step):
+                    b = min(nrows, a + step)
+                    rest = np.ascontiguousarray(Rs[:, a:b]).reshape(err_samples * (b - a), -1)
+                    cond = None if Cs is None else torch.from_numpy(
+                        np.ascontiguousarray(Cs[:, a:b]).reshape(err_samples * (b - a), -1))
+                    un = plan.posterior(torch.from_numpy(rest), idx, gdev, cond, normalize=False, nan_to_zero=False)
+                    mean = ensemble_posterior_mean(un.reshape(err_samples, b - a, len(grid)), gdev, False)
+                    if normalize or nan_to_zero:
+                        normalize_pdfs_(mean, gdev, normalize, nan_to_zero)
+                    pdfs[a:b] = mean.cpu().numpy()
+                return pdfs
             C, Cerr = self._get_err_arrays(inputs, "conditions")
             if len(self.data_columns) == 1:
                 rest = np.zeros((nrows, 0), dtype=np.float32)
@@ -446,7 +529,7 @@ class Flow:
         with_params = isinstance(self.latent, (distributions.CentBeta, distributions.Tdist, distributions.Joint))
 
         def draw(dev, a, b):
-            kw = dict(device=torch.device("cuda", dev), row_offset=a)
+            kw = dict(device=torch.device("cuda", dev), row_offset=a, total_rows=n)
             if with_params:
                 return self.latent.sample_device(b - a, seed, self._params[0], **kw)  # latents with parameters
             return self.latent.sample_device(b - a, seed, **kw)  # draws stay on the device

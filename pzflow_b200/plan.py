@@ -16,9 +16,10 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import prng
 
 HOT_PATH_BIJECTORS = ("Chain", "ColorTransform", "InvSoftplus", "NeuralSplineCoupling", "Reverse", "Roll",
-                      "RollingSplineCoupling", "Scale", "ShiftBounds", "StandardScaler")
+                      "RollingSplineCoupling", "Scale", "ShiftBounds", "Shuffle", "StandardScaler", "UniformDequantizer")
 LATENTS = {"Uniform": N.LATENT_UNIFORM, "CentBeta13": N.LATENT_CENTBETA13, "Normal": N.LATENT_NORMAL,
            "CentBeta": N.LATENT_CENTBETA, "Tdist": N.LATENT_TDIST, "Joint": N.LATENT_JOINT}
 
@@ -53,6 +54,34 @@ def _f32(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 
 
+def resolve_shuffles(info: Tuple[str, tuple], key, input_dim: int) -> Tuple[str, tuple]:
+    """``info`` with every ``("Shuffle", ())`` given the permutation the reference would draw for it.
+
+    A Shuffle's permutation is not in its Bijector_Info: the reference draws it inside ``init_fun`` from the key the
+    enclosing Chains hand down (pzflow/bijectors.py:795-797; Chain: ``rng, layer_rng = random.split(rng)`` per
+    stage, 146-149) -- ``PRNGKey(seed)`` at construction (flow.py:286-287), ``PRNGKey(0)`` when a flow is loaded from
+    a file (186-187).  This walk repeats that key schedule (pzflow_b200.prng) and returns ``("Shuffle", (perm,))``
+    nodes, the form ``flatten`` and the training chain take; everything else is returned as it is."""
+    name, args = info
+    if name == "Shuffle":
+        if len(args) == 1:
+            return info
+        if key is None:
+            raise ValueError("Shuffle draws its permutation from the key of the flow it belongs to: build it through "
+                             "Flow(..., seed=...) / set_bijector, or an InitFunction called with a seed")
+        return ("Shuffle", (tuple(int(v) for v in prng.permutation(prng.key_from_seed(key), input_dim)),))
+    if name == "RollingSplineCoupling" or name != "Chain":
+        return info  # a RollingSplineCoupling is a Chain of NeuralSplineCoupling / Roll only: nothing to resolve
+    out = []
+    rng = None if key is None else prng.key_from_seed(key)
+    for sub in args:
+        layer = None
+        if rng is not None:
+            rng, layer = prng.split(rng)
+        out.append(resolve_shuffles(sub, layer, input_dim))
+    return ("Chain", tuple(out))
+
+
 def flatten(info: Tuple[str, tuple], params: Any, input_dim: int) -> List[dict]:
     """Flatten (Bijector_Info, params) into stage dictionaries, Chains bracketed."""
     name, args = info
@@ -79,6 +108,14 @@ def flatten(info: Tuple[str, tuple], params: Any, input_dim: int) -> List[dict]:
                      vec_b=np.atleast_1d(_f32(args[1])), B=0.0)]
     if name == "Reverse":
         return [dict(kind=N.STAGE_REVERSE)]
+    if name == "Shuffle":
+        if len(args) != 1:
+            raise ValueError("Shuffle without its permutation: resolve_shuffles(info, key, input_dim) first")
+        perm = np.ascontiguousarray(np.asarray(args[0], dtype=np.float32).ravel())
+        return [dict(kind=N.STAGE_SHUFFLE, vec_a=perm, vec_b=perm)]
+    if name == "UniformDequantizer":
+        idx = np.ascontiguousarray(np.atleast_1d(np.asarray(args[0])).astype(np.float32).ravel())
+        return [dict(kind=N.STAGE_DEQUANTIZE, vec_a=idx, vec_b=idx)]
     if name == "Scale":
         (scale,) = args
         if np.ndim(scale) != 0:
@@ -202,7 +239,7 @@ class Plan:
     """One compiled chain + latent on one CUDA device."""
 
     def __init__(self, bijector_info, bijector_params, input_dim: int,
-                 latent_info=("Uniform", (None, 5)), device: Optional[int] = None, latent_params=None):
+                 latent_info=("Uniform", (None, 5)), device: Optional[int] = None, latent_params=None, rng_key=None):
         lib = N.lib()
         if lib.pzb_device_count() <= 0 or not torch.cuda.is_available():
             raise N.NativeError("pzflow_b200 needs a CUDA device: there is no CPU fallback")
@@ -215,7 +252,7 @@ class Plan:
         latent_B = (float(latent_args[1]) if len(latent_args) > 1 and latent_name in ("Uniform", "CentBeta13", "CentBeta")
                     else 5.0)
         self._latent_name = latent_name
-        stages = flatten(bijector_info, bijector_params, input_dim)
+        stages = flatten(resolve_shuffles(bijector_info, rng_key, int(input_dim)), bijector_params, input_dim)
         self._keep = []  # host arrays the descriptors point into (until plan_create returns)
         descs = (N.StageDesc * max(1, len(stages)))()
         for d, st in zip(descs, stages):
@@ -681,6 +718,22 @@ def sample_uniform(n: int, dim: int, B: float, seed: int, device=None, row_offse
     with torch.cuda.device(device):
         N.check(N.lib().pzb_sample_uniform(_ptr(out), n, dim, float(B), int(seed) & (2 ** 64 - 1), int(row_offset),
                                            _stream(device)))
+    return out
+
+
+def sample_uniform_jax(n: int, dim: int, B: float, seed, device=None, row_offset: int = 0, total_rows: int = None,
+                       layout: str = None) -> torch.Tensor:
+    """Rows [row_offset, row_offset + n) of ``jax.random.uniform(PRNGKey(seed), (total_rows, dim), -B, B)``, drawn on the
+    device in jax's own threefry stream (pzb_sample_uniform_threefry; pzflow/distributions.py:464-469)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    total_rows = n + row_offset if total_rows is None else int(total_rows)
+    key = prng.key_from_seed(seed)
+    out = torch.empty((n, dim), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        N.check(N.lib().pzb_sample_uniform_threefry(_ptr(out), n, dim, -float(B), float(B), int(key[0]), int(key[1]),
+                                                    total_rows, int(row_offset),
+                                                    int((layout or prng.layout()) == "threefry_partitionable"),
+                                                    _stream(device)))
     return out
 
 

@@ -207,6 +207,10 @@ class TorchChain:
             return torch.roll(x, int(args[0]), dims=-1), zeros
         if name == "Reverse":
             return torch.flip(x, dims=(-1,)), zeros
+        if name == "Shuffle":                                    # bijectors.py:800-804 (permutation from plan.resolve_shuffles)
+            return x[:, [int(v) for v in args[0]]], zeros
+        if name == "UniformDequantizer":                         # bijectors.py:892-899: identity as executed
+            return x, zeros
         if name == "ShiftBounds":                                # bijectors.py:754-765
             B = float(args[2]) if len(args) > 2 else 5.0
 
@@ -553,7 +557,9 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
         stds = c.std(axis=0)
         flow._condition_stds = np.where(stds != 0, stds, 1).astype(np.float32)
 
-    chain = TorchChain(flow._bijector_info, flow._params[1], flow._latent_info, flow._params[0], flow._input_dim, dev)
+    from .plan import resolve_shuffles
+    info = resolve_shuffles(flow._bijector_info, getattr(flow, "_bijector_seed", 0), flow._input_dim)
+    chain = TorchChain(info, flow._params[1], flow._latent_info, flow._params[0], flow._input_dim, dev)
     chain.fused_gradient = FusedGradient.build(chain)   # one kernel per step where the chain's shapes allow it
     opt = NativeAdam(chain, lr=1e-3) if optimizer is None else optimizer(chain.leaves)
     graphed: dict = {}

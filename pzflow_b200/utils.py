@@ -27,6 +27,8 @@ def gaussian_error_model(key, X, Xerr, nsamples):
     from .plan import error_eps
     X = np.asarray(X, dtype=np.float32)
     Xerr = np.asarray(Xerr, dtype=np.float32)
-    eps = error_eps(X.shape[0] * int(nsamples), X.shape[1], 0, int(key)).cpu().numpy()
+    k = np.asarray(key).astype(np.uint64).ravel()   # an int seed, or the uint32 pair PRNGKey(seed) would be
+    seed = int(k[0]) if k.size == 1 else (int(k[0]) << 32) | int(k[1])
+    eps = error_eps(X.shape[0] * int(nsamples), X.shape[1], 0, seed).cpu().numpy()
     eps = eps.reshape(X.shape[0], int(nsamples), X.shape[1])
     return X[:, None, :] + eps * Xerr[:, None, :]

@@ -1906,3 +1906,186 @@ def test_posterior_with_marginalization_like_the_reference_test(flag):
     np.testing.assert_allclose(pdfs[0], want, rtol=2e-5)
     np.testing.assert_allclose(pdfs2[0], want, rtol=2e-5)
     assert (pdfs[1:] == 0).all() and (pdfs2[1:] == 0).all()
+
+
+# --------------------------------------------------------------------------- #
+# round 3: jax's own random streams, Shuffle, UniformDequantizer               #
+# --------------------------------------------------------------------------- #
+def test_uniform_latent_draws_are_the_jax_stream():
+    """pzb_sample_uniform_threefry == jax.random.uniform(PRNGKey(seed), (n, D), -B, B) as oracle/jax_prng.py restates it
+    (pinned by the Random123 known answers and the notebook samples): bit for bit, odd and even totals, both layouts,
+    and row shards of a larger draw."""
+    from oracle import jax_prng as J
+    from pzflow_b200 import distributions as Dn
+    from pzflow_b200 import prng
+    from pzflow_b200.plan import sample_uniform_jax
+    assert prng.layout() == "threefry"
+    for n, D, seed in ((2, 7, 0), (1001, 7, 7), (4096, 3, 2 ** 31 + 5), (1, 1, 10 ** 17), (300_001, 5, 11)):
+        want = J.uniform(J.PRNGKey(seed), (n, D), -5.0, 5.0)
+        got = Dn.Uniform(D, 5).sample((), n, seed)
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.int32), want.view(np.int32)), (n, D, seed)
+        wantp = J.uniform(J.PRNGKey(seed), (n, D), -5.0, 5.0, partitionable=True)
+        gotp = _np(sample_uniform_jax(n, D, 5.0, seed, layout="threefry_partitionable"))
+        assert np.array_equal(gotp.view(np.int32), wantp.view(np.int32)), (n, D, seed)
+    # rows [a, b) of a 1001-row draw, as a sharded Flow.sample asks for them
+    whole = J.uniform(J.PRNGKey(3), (1001, 7), -5.0, 5.0)
+    for a, b in ((0, 400), (400, 1001), (1000, 1001)):
+        part = _np(Dn.Uniform(7, 5).sample_device(b - a, 3, row_offset=a, total_rows=1001))
+        assert np.array_equal(part.view(np.int32), whole[a:b].view(np.int32))
+    # the Philox streams of round 1 stay available
+    prng.set_layout("philox")
+    try:
+        ph = Dn.Uniform(7, 5).sample((), 1000, 0)
+        assert not np.array_equal(ph, J.uniform(J.PRNGKey(0), (1000, 7), -5.0, 5.0)) and np.abs(ph).max() <= 5
+    finally:
+        prng.set_layout("threefry")
+
+
+def test_flow_sample_reproduces_what_real_jax_printed():
+    """docs/tutorials/marginalization.ipynb:69, 133-135: ``flow.sample(2, seed=0)`` of the shipped flow under the real JAX
+    reference.  The same call here -- latents drawn on the GPU in jax's stream, the inverse chain on the tensor cores --
+    returns the printed rows to the printed precision; and 1001 samples of seed 7 equal what the reference's own
+    code returns over the stand-in (tests/golden/ref_shim_jax_streams.npz)."""
+    from pzflow_b200.examples import get_example_flow
+    flow = get_example_flow()
+    z, g = golden("ref_shim_example_flow.npz"), golden("ref_shim_jax_streams.npz")
+    s = flow.sample(2, seed=0)
+    assert list(s.columns) == ["redshift", "u", "g", "r", "i", "z", "y"]
+    np.testing.assert_allclose(s.to_numpy(), z["nb_X"], rtol=3e-6, atol=0)
+    for engine in ("simt", "tc", "wide"):
+        flow._plan().set_engine(engine)
+        np.testing.assert_allclose(flow.sample(2, seed=0).to_numpy(), z["nb_X"], rtol=3e-6, atol=0, err_msg=engine)
+        big = flow.sample(1001, seed=7).to_numpy()
+        want = g["example_sample_1001_seed7"]
+        ex = F.example_flow()
+        bi, li, p64 = _o64(ex)
+        x64, _ = O.flow_inverse(bi, p64, g["example_latent_1001_seed7"].astype(np.float64))
+        assert_noise_floor(f"sample(1001, seed=7) [{engine}]", big, want, x64, ratio=2.0, slack=2e-5)
+    flow._plan().set_engine("auto")
+
+
+@pytest.mark.parametrize("engine", ["simt", "tc", "wide"])
+def test_shuffle_and_dequantizer_flows_against_reference_golden(engine):
+    """Flows whose chains hold Shuffle stages (pzflow/bijectors.py:780-814) and a UniformDequantizer (865-911), built
+    with two seeds: log_prob, forward and Flow.sample against what the reference's own code returned (stand-in with
+    jax's key schedule, oracle/make_golden_shim.py round3); a flow re-built from its save dictionary draws its
+    permutations from PRNGKey(0) (flow.py:186-187) and so evaluates differently from the seed-3 flow it was saved from."""
+    from pzflow_b200 import Flow
+    from pzflow_b200 import bijectors as B
+    from pzflow_b200 import distributions as Dn
+    from oracle import jax_prng as J
+    g = golden("ref_shim_jax_streams.npz")
+    X, mins, maxs = g["X"], g["mins"], g["maxs"]
+    cols = tuple("abcde")
+    df = pd.DataFrame(X.astype(np.float64), columns=cols)
+    info = F.unpack_tree("shuffle_info", g)
+
+    def bijector():
+        return B.Chain(B.UniformDequantizer([2]), B.ShiftBounds(mins, maxs, 4.0), B.Shuffle(),
+                       B.RollingSplineCoupling(3, K=8, hidden_dim=32), B.Chain(B.Reverse(), B.Shuffle()),
+                       B.RollingSplineCoupling(2, K=8, hidden_dim=32))
+    for seed in (0, 3):
+        params = F.unpack_tree(f"s{seed}_params", g)
+        fl = Flow(cols, bijector(), latent=Dn.Uniform(5, 5), seed=seed)
+        assert repr(fl._bijector_info[1][2:5]) == repr(info[1][2:5])   # ("Shuffle", ()) stays free of its permutation
+        fl.set_bijector(bijector(), params=params, seed=seed)
+        plan = fl._plan()
+        if engine == "tc" and not plan.tc_supported or engine == "wide" and not plan.wide_supported:
+            pytest.skip("engine does not take this shape")
+        plan.set_engine(engine)
+        ri = O.resolve_shuffles(info, J.PRNGKey(seed), 5)
+        p64 = O.cast_params(((), params), np.float64)
+        lp = fl.log_prob(df)
+        assert_noise_floor(f"shuffle flow log_prob seed {seed} [{engine}]", lp, g[f"s{seed}_log_prob"],
+                           O.flow_log_prob(ri, ("Uniform", (5, 5)), p64, X.astype(np.float64)), ratio=2.0, slack=2e-5,
+                           below=LP_UNDERFLOW)
+        u, ld = fl._forward(fl._params[1], X)
+        u64, ld64 = O.apply_bijector(ri, p64[1], X.astype(np.float64), np.zeros((len(X), 1)))
+        assert_noise_floor(f"shuffle flow forward seed {seed} [{engine}]", u, g[f"s{seed}_forward_u"], u64, ratio=2.0, slack=2e-5)
+        smp = fl.sample(9, seed=5).to_numpy()
+        x64, _ = O.flow_inverse(ri, p64, J.uniform(J.PRNGKey(5), (9, 5), -5.0, 5.0).astype(np.float64))
+        assert_noise_floor(f"shuffle flow sample seed {seed} [{engine}]", smp, g[f"s{seed}_sample_9_seed5"], x64, ratio=2.0,
+                           slack=2e-5)
+        # inverse floors the dequantized column (bijectors.py:902-905): samples of column c are whole numbers
+        assert np.array_equal(smp[:, 2], np.floor(smp[:, 2]))
+        if seed == 3:
+            again = Flow(_dictionary=fl._save_dict())
+            again._plan().set_engine(engine)
+            r0 = O.resolve_shuffles(info, J.PRNGKey(0), 5)
+            assert_noise_floor(f"reloaded shuffle flow [{engine}]", again.log_prob(df), g["s3_reloaded_log_prob"],
+                               O.flow_log_prob(r0, ("Uniform", (5, 5)), p64, X.astype(np.float64)), ratio=2.0, slack=2e-5,
+                               below=LP_UNDERFLOW)
+            assert np.abs(again.log_prob(df) - lp).max() > 1.0
+
+
+def test_custom_error_models_run_on_the_host_and_reduce_on_the_device():
+    """pzflow/flow.py:339-395 accepts any callable as data_error_model / condition_error_model
+    (docs/tutorials/nongaussian_errors.ipynb).  Custom callables are called on the host with NumPy arrays and a
+    PRNGKey-shaped key; their samples go through the fused kernels and are reduced on the device: log(mean(exp)) for
+    log_prob (flow.py:463-464), mean then per-galaxy normalisation for posterior (722-737) -- against the oracle on the
+    same samples; zero errors == the plain calls (tests/test_flow.py:236-239, 260-264 of the reference)."""
+    from pzflow_b200 import Flow
+    from pzflow_b200 import bijectors as B
+    from pzflow_b200 import distributions as Dn
+    calls = []
+
+    def lognormal_model(key, X, Xerr, nsamples):
+        assert np.asarray(key).shape == (2,) and np.asarray(key).dtype == np.uint32
+        calls.append((X.shape, nsamples))
+        rng = np.random.default_rng([int(k) for k in key])
+        eps = rng.standard_normal((X.shape[0], nsamples, X.shape[1])).astype(np.float32)
+        return X[:, None, :] * np.exp(eps * Xerr[:, None, :])         # multiplicative (non-Gaussian) errors
+
+    ex = F.example_flow()
+    cols = ("redshift", "u", "g", "r", "i", "z", "y")
+    fl = Flow(cols, latent=Dn.Uniform(7, 5), data_error_model=lognormal_model)
+    info = ex["bijector_info"]
+    fl.set_bijector(B.Chain(B.ShiftBounds(info[1][0][1][0], info[1][0][1][1], 4.0), B.RollingSplineCoupling(7)),
+                    params=ex["params"][1])
+    rng = np.random.default_rng(8)
+    n, S, seed = 300, 6, 17
+    X = F.galaxy_rows(n, seed=31, oob_frac=0)
+    df = pd.DataFrame(X.astype(np.float64), columns=cols)
+    for c in ("u", "g", "r"):
+        df[f"{c}_err"] = rng.uniform(0.0, 0.002, n)
+    got = fl.log_prob(df, err_samples=S, seed=seed)
+    Xerr = np.zeros_like(X)
+    for j, c in enumerate(cols):
+        if f"{c}_err" in df:
+            Xerr[:, j] = df[f"{c}_err"].to_numpy()
+    from pzflow_b200 import prng
+    samples = lognormal_model(prng.key_from_seed(seed), X, Xerr, S).astype(np.float32)          # [n, S, 7]
+    bi, li, p64 = _o64(ex)
+    with np.errstate(all="ignore"):
+        lp32 = O.flow_log_prob(ex["bijector_info"], ex["latent_info"], ex["params"], samples.reshape(n * S, 7))
+        lp64 = O.flow_log_prob(bi, li, p64, samples.reshape(n * S, 7).astype(np.float64))
+        o32 = np.log(np.exp(lp32.reshape(n, S)).mean(axis=1, dtype=np.float32))
+        o64 = np.log(np.exp(lp64.reshape(n, S)).mean(axis=1))
+    assert_noise_floor("custom error model log_prob", got, o32, o64, ratio=2.0, slack=5e-6, below=LP_UNDERFLOW)
+    assert not np.array_equal(got, fl.log_prob(df, err_samples=S, seed=seed + 1))
+    # posterior: samples of the other six columns, the skipped column handed to the model as NaN (flow.py:370-373)
+    G, ng = 40, 25
+    grid = np.linspace(0.0, 2.3, G).astype(np.float32)
+    pdf = fl.posterior(df.iloc[:ng], column="redshift", grid=grid, err_samples=S, seed=seed)
+    Xn, En = X[:ng].copy(), Xerr[:ng].copy()
+    Xn[:, 0] = np.nan
+    En[:, 0] = np.nan
+    rest = np.delete(lognormal_model(prng.key_from_seed(seed), Xn, En, S).astype(np.float32), 0, axis=2).reshape(ng * S, 6)
+    un = O.flow_posterior(ex["bijector_info"], ex["latent_info"], ex["params"], rest, 0, grid, normalize=False,
+                          nan_to_zero=False).reshape(ng, S, G).mean(axis=1)
+    want = np.nan_to_num(un / O.trapezoid(un, grid)[:, None], nan=0.0)
+    np.testing.assert_allclose(pdf, want, rtol=2e-3, atol=2e-4)
+    # zero errors == plain
+    plain = pd.DataFrame(X.astype(np.float64), columns=cols)
+    lp0, lpS = fl.log_prob(plain), fl.log_prob(plain, err_samples=3, seed=1)
+    fin = lp0 > LP_UNDERFLOW
+    np.testing.assert_allclose(lpS[fin], lp0[fin], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(fl.posterior(plain.iloc[:ng], "redshift", grid, err_samples=3, seed=1),
+                               fl.posterior(plain.iloc[:ng], "redshift", grid), rtol=1e-4, atol=1e-6)
+    assert calls and all(ns in (S, 3) for _, ns in calls)
+    # the step size of the host route does not change results
+    fl._HOST_SAMPLE_ROWS = 64 * S
+    try:
+        np.testing.assert_array_equal(fl.log_prob(df, err_samples=S, seed=seed), got)
+    finally:
+        del fl._HOST_SAMPLE_ROWS

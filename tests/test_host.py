@@ -55,11 +55,14 @@ def test_flatten_rejects_bad_shapes_and_foreign_bijectors():
     params = O.synth_bijector_params(info, 7, np.random.default_rng(0))
     with pytest.raises(ValueError):
         P.flatten(info, params, 9)  # weights were built for input_dim 7
-    # Shuffle draws its permutation from the jax PRNG at init time: it cannot be rebuilt without jax
-    with pytest.raises(NotImplementedError):
+    # Shuffle draws its permutation from the key of the flow it belongs to: without one it cannot be flattened
+    with pytest.raises(ValueError):
         P.flatten(("Shuffle", ()), (), 7)
+    with pytest.raises(ValueError):
+        P.resolve_shuffles(("Chain", (("Shuffle", ()),)), None, 7)
     with pytest.raises(NotImplementedError):
-        build_bijector_from_info(("UniformDequantizer", (0,)))
+        P.flatten(("NotABijector", ()), (), 7)
+    assert build_bijector_from_info(("UniformDequantizer", (0,)))[1] == ("UniformDequantizer", (0,))
     # the parameter-free bijectors flatten to their own stage kinds
     kinds = [s["kind"] for s in P.flatten(("Chain", (("Reverse", ()), ("Scale", (0.5,)), ("InvSoftplus", ([1, 3], [2.0, 12.0])),
                                                      ("ColorTransform", (3, [1, 3, 5])))), [(), (), (), ()], 7)]
@@ -534,3 +537,52 @@ def test_process_devices_policy(monkeypatch):
     sharding.set_devices([1, 9])
     assert sharding.process_devices() == [1]
     sharding.set_devices(None)
+
+
+# --------------------------------------------------------------------------- #
+# jax-compatible key schedule (pzflow_b200.prng) and the stages that hang on it #
+# --------------------------------------------------------------------------- #
+def test_prng_matches_the_oracle_restatement_and_jax_documentation():
+    """The host-side key schedule equals the oracle's restatement of jax.random (itself pinned by the Random123
+    known answers and the notebook samples, tests/test_oracle.py); split(PRNGKey(0)) is the value jax's own
+    documentation prints."""
+    from oracle import jax_prng as J
+    from pzflow_b200 import prng
+    assert prng.layout() == "threefry"
+    np.testing.assert_array_equal(prng.split(prng.key_from_seed(0)), [[4146024105, 967050713], [2718843009, 1272950319]])
+    for seed in (0, 1, 7, 2 ** 31 + 5, 10 ** 17):
+        k = prng.key_from_seed(seed)
+        np.testing.assert_array_equal(k, J.PRNGKey(seed))
+        for part in (False, True):
+            lay = "threefry_partitionable" if part else "threefry"
+            np.testing.assert_array_equal(prng.split(k, 3, lay), J.split(k, 3, part))
+            for n in (1, 2, 7, 8, 33):
+                np.testing.assert_array_equal(prng.words(k, n, part), J.random_bits(k, n, part))
+                np.testing.assert_array_equal(prng.permutation(k, n, lay), J.permutation(k, n, part))
+                assert sorted(prng.permutation(k, n, lay)) == list(range(n))
+
+
+def test_shuffle_permutations_follow_the_chain_key_schedule():
+    """plan.resolve_shuffles repeats Chain.init_fun's splits (pzflow/bijectors.py:146-149) and Shuffle's
+    random.permutation (795-797): same result as the oracle's walk, different per position and per seed, and the
+    flattened stage carries the permutation."""
+    from oracle import jax_prng as J
+    info = ("Chain", (("Shuffle", ()), ("Chain", (("Reverse", ()), ("Shuffle", ()))), ("Shuffle", ())))
+    got = P.resolve_shuffles(info, 3, 7)
+    want = O.resolve_shuffles(info, J.PRNGKey(3), 7)
+    assert got == want
+    perms = [got[1][0][1][0], got[1][1][1][1][1][0], got[1][2][1][0]]
+    assert all(sorted(p) == list(range(7)) for p in perms) and len({tuple(p) for p in perms}) == 3
+    assert P.resolve_shuffles(info, 4, 7) != got
+    # a top-level Shuffle takes PRNGKey(seed) itself
+    assert P.resolve_shuffles(("Shuffle", ()), 0, 7) == ("Shuffle", (tuple(int(v) for v in J.permutation(J.PRNGKey(0), 7)),))
+    stages = P.flatten(got, [(), [(), ()], ()], 7)
+    sh = [s for s in stages if s["kind"] == N.STAGE_SHUFFLE]
+    assert [tuple(int(v) for v in s["vec_a"]) for s in sh] == [tuple(p) for p in perms]
+    # resolved infos pass through unchanged; the bijector factory keeps the reference's Bijector_Info
+    assert P.resolve_shuffles(got, None, 7) == got
+    from pzflow_b200 import bijectors as B
+    assert B.Shuffle()[1] == ("Shuffle", ())
+    assert B.Chain(B.Shuffle(), B.UniformDequantizer([0, 2]))[1] == ("Chain", (("Shuffle", ()), ("UniformDequantizer", ([0, 2],))))
+    kinds = [s["kind"] for s in P.flatten(("UniformDequantizer", (2,)), (), 7)]
+    assert kinds == [N.STAGE_DEQUANTIZE]

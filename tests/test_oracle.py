@@ -249,3 +249,50 @@ def test_extra_bijectors_and_latents_golden():
     assert np.array_equal(np.isneginf(got), np.isneginf(want))
     fin = np.isfinite(want)
     np.testing.assert_allclose(got[fin], want[fin], rtol=3e-6, atol=3e-6)
+
+
+# --------------------------------------------------------------------------- #
+# (4) jax's random streams (oracle/jax_prng.py)                               #
+# --------------------------------------------------------------------------- #
+def test_threefry_known_answers():
+    """Random123's threefry2x32_20 known answers (the vectors jax's own test-suite checks)."""
+    from oracle import jax_prng as J
+    for ctr, key, want in J.KAT:
+        a, b = J.threefry2x32(key, [ctr[0]], [ctr[1]])
+        assert (int(a[0]), int(b[0])) == want
+    # jax's documentation: random.split(PRNGKey(0))
+    np.testing.assert_array_equal(J.split(J.PRNGKey(0)), [[4146024105, 967050713], [2718843009, 1272950319]])
+
+
+def test_notebook_samples_from_the_seed():
+    """docs/tutorials/marginalization.ipynb:69, 133-135: ``flow.sample(2, seed=0)`` of the shipped flow, printed by the
+    real JAX reference.  Drawing the latents of seed 0 in jax's original threefry layout and pushing them through the
+    oracle's inverse reproduces the printed rows to the printed precision -- the one end-to-end anchor against real
+    JAX/XLA output in the tree: it pins the stream layout AND the whole inverse chain (14 values, 1e-6 relative)."""
+    from oracle import jax_prng as J
+    ex = F.example_flow()
+    X = golden("ref_shim_example_flow.npz")["nb_X"]
+    u = J.uniform(J.PRNGKey(0), (2, 7), -5.0, 5.0)
+    x, _ = O.flow_inverse(ex["bijector_info"], ex["params"], u)
+    np.testing.assert_allclose(x, X, rtol=1.5e-6, atol=0)
+    # the other stream layout does not produce them (it is offered unverified)
+    u2 = J.uniform(J.PRNGKey(0), (2, 7), -5.0, 5.0, partitionable=True)
+    x2, _ = O.flow_inverse(ex["bijector_info"], ex["params"], u2)
+    assert np.abs(x2 - X).max() > 0.1
+
+
+def test_shuffle_and_dequantizer_semantics():
+    """bijectors.py:798-810 (Shuffle) and 892-907 (UniformDequantizer as executed: identity forward, floor inverse)."""
+    from oracle import jax_prng as J
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(5, 7)).astype(np.float32) * 3
+    info = O.resolve_shuffles(("Chain", (("Shuffle", ()), ("UniformDequantizer", ([1, 4],)))), J.PRNGKey(2), 7)
+    perm = np.asarray(info[1][0][1][0])
+    y, ld = O.apply_bijector(info, [(), ()], X, None)
+    np.testing.assert_array_equal(y, X[:, perm])
+    assert not ld.any()
+    back, _ = O.apply_bijector(info, [(), ()], y, None, inverse=True)
+    want = X.copy()
+    cols = perm[[1, 4]]   # the dequantizer sits behind the shuffle: it floors the columns that landed at 1 and 4
+    want[:, cols] = np.floor(want[:, cols])
+    np.testing.assert_array_equal(back, want)
