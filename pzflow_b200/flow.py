@@ -281,8 +281,9 @@ class Flow:
             for a in range(0, n, step):
                 b = min(n, a + step)
                 rows = np.ascontiguousarray(Xs[:, a:b]).reshape(err_samples * (b - a), -1)
-                cond = None if Cs is None else torch.from_numpy(np.ascontiguousarray(Cs[:, a:b]).reshape(err_samples * (b - a), -1))
-                lp = plan.log_prob(torch.from_numpy(rows), cond)
+                cond = None if Cs is None else torch.from_numpy(
+                    np.ascontiguousarray(Cs[:, a:b]).reshape(err_samples * (b - a), -1)).to(plan.device)
+                lp = plan.log_prob(torch.from_numpy(rows).to(plan.device), cond)   # device tensors: results stay on the device
                 out[a:b] = ensemble_logmeanexp(lp.reshape(err_samples, b - a)).cpu().numpy()
             return out
         X, Xerr = self._get_err_arrays(inputs, "data")
@@ -404,8 +405,9 @@ class Flow:
                     b = min(nrows, a + step)
                     rest = np.ascontiguousarray(Rs[:, a:b]).reshape(err_samples * (b - a), -1)
                     cond = None if Cs is None else torch.from_numpy(
-                        np.ascontiguousarray(Cs[:, a:b]).reshape(err_samples * (b - a), -1))
-                    un = plan.posterior(torch.from_numpy(rest), idx, gdev, cond, normalize=False, nan_to_zero=False)
+                        np.ascontiguousarray(Cs[:, a:b]).reshape(err_samples * (b - a), -1)).to(plan.device)
+                    un = plan.posterior(torch.from_numpy(rest).to(plan.device), idx, gdev, cond, normalize=False,
+                                        nan_to_zero=False)
                     mean = ensemble_posterior_mean(un.reshape(err_samples, b - a, len(grid)), gdev, False)
                     if normalize or nan_to_zero:
                         normalize_pdfs_(mean, gdev, normalize, nan_to_zero)

@@ -1064,9 +1064,13 @@ def test_err_samples_through_flow_api():
     np.testing.assert_allclose(np.trapezoid(pdfs, grid, axis=1), 1.0, rtol=1e-4)
     with pytest.raises(AssertionError):
         flow.log_prob(df, err_samples=0)
-    flow2 = Flow(_dictionary=dict(d, data_error_model=lambda key, X, Xerr, n: None))
+    # a user's own error model is a host callable (test_custom_error_models_...); it cannot ride inside marg_rules
+    flow2 = Flow(_dictionary=dict(d, data_error_model=lambda key, X, Xerr, n: np.repeat(X[:, None, :], n, axis=1)))
+    fin = flow.log_prob(df[:64]) > LP_UNDERFLOW
+    np.testing.assert_allclose(flow2.log_prob(df[:64], err_samples=2)[fin], flow.log_prob(df[:64])[fin], rtol=1e-5, atol=1e-5)
     with pytest.raises(NotImplementedError):
-        flow2.log_prob(df, err_samples=2)
+        flow2.posterior(df[:4], column="redshift", grid=grid, err_samples=2,
+                        marg_rules={"flag": 99.0, "u": lambda row: np.linspace(25, 31, 4)})
 
 
 # --------------------------------------------------------------------------- #
