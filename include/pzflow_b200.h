@@ -232,7 +232,7 @@ int pzb_normalize_pdfs(float *pdfs, int64_t Ng, int32_t G, const float *grid,
 
 /* Latent draws for Flow.sample speed runs (pzflow/distributions.py:443-470):
  * U [N, D] ~ Uniform(-B, B) from a counter-based Philox stream.  This is NOT
- * jax.random's threefry stream; sample parity is defined on the map u -> x.
+ * jax.random's threefry stream (pzb_sample_uniform_threefry below is); kept for draws beyond one threefry call.
  * row_offset (here and in the three samplers below): index of U's first row in the caller's whole array, so that a
  * call sharded over rows (several GPUs, several chunks) draws exactly what one big call would; row_offset * D must be
  * a multiple of 4 for the uniform and the normal sampler (their draws come in blocks of four). */
