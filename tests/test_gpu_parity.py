@@ -2093,3 +2093,116 @@ def test_custom_error_models_run_on_the_host_and_reduce_on_the_device():
         np.testing.assert_array_equal(fl.log_prob(df, err_samples=S, seed=seed), got)
     finally:
         del fl._HOST_SAMPLE_ROWS
+
+
+# --------------------------------------------------------------------------- #
+# BASELINE's full sizes for configs 3, 4, 5: size-independent properties        #
+# --------------------------------------------------------------------------- #
+def test_full_size_properties_c3():
+    """Config 3 at BASELINE's size -- 10^6 galaxies x 1000 redshift grid points, 4 GB of pdfs: every pdf integrates to
+    one, galaxy shards (the 8-GPU partition) compute exactly what the whole call computes, a strided sample of galaxies
+    equals exp(log_prob) of its expanded rows normalised by the trapezoid rule, and the single-pass form (normalised
+    inside the chain kernel) agrees with the default one to float rounding."""
+    import os
+    from pzflow_b200.sharding import shard_rows
+    ex = F.example_flow()
+    plan = _plan(ex, "tc")
+    ng, G = 1_000_000, 1000
+    base = torch.from_numpy(np.ascontiguousarray(F.galaxy_rows(20000, seed=6, oob_frac=0.01)[:, 1:])).cuda()
+    rest = base.repeat(ng // base.shape[0], 1).contiguous()
+    rest += torch.linspace(0, 2e-3, ng, device="cuda")[:, None]        # distinct galaxies
+    grid = torch.linspace(0.0, 2.3, G, device="cuda")
+    pdf = plan.posterior(rest, 0, grid)
+    assert pdf.shape == (ng, G)
+    dx = (grid[1:] - grid[:-1]).double()
+    integ = torch.cat([0.5 * (dx * (pdf[a:a + 100_000, 1:].double() + pdf[a:a + 100_000, :-1].double())).sum(1)
+                       for a in range(0, ng, 100_000)])               # float64: only the kernel's own rounding is left
+    # galaxies whose un-normalised pdf is not itself at the bottom of float32's range (1 % of the rows sit outside the
+    # training box; dividing by a denormal integral is as meaningless here as in the reference)
+    un_max = torch.cat([plan.posterior(rest[a:a + 250_000], 0, grid, normalize=False).amax(1) for a in range(0, ng, 250_000)])
+    live = un_max > 1e-20
+    assert live.float().mean() > 0.95
+    dev = (integ[live] - 1.0).abs()
+    print(f"C3 full size: {int(live.sum())} live galaxies, |integral - 1| median {float(dev.median()):.2e} max {float(dev.max()):.2e}")
+    assert dev.median() < 1e-6 and dev.max() < 3e-5                    # 1000-term float32 trapezoid sums
+    assert not torch.isnan(pdf[::997]).any()
+    for r in (0, 3, 7):
+        a, b = shard_rows(ng, r, 8)
+        assert torch.equal(plan.posterior(rest[a:b], 0, grid), pdf[a:b])
+    pick = torch.arange(0, ng, 15625, device="cuda")                   # 64 galaxies across the whole range
+    rows = torch.cat([grid.repeat(len(pick))[:, None], rest[pick].repeat_interleave(G, 0)], dim=1)
+    un = torch.exp(plan.log_prob(rows)).reshape(len(pick), G)
+    want = torch.nan_to_num(un / (0.5 * ((grid[1:] - grid[:-1]) * (un[:, 1:] + un[:, :-1])).sum(1, keepdim=True)), nan=0.0)
+    assert torch.allclose(pdf[pick], want, rtol=3e-6, atol=1e-12)
+    os.environ["PZB_FUSE_POSTERIOR"] = "1"
+    try:
+        fused = plan.posterior(rest[:200_000], 0, grid)
+    finally:
+        os.environ.pop("PZB_FUSE_POSTERIOR", None)
+    assert torch.allclose(fused, pdf[:200_000], rtol=3e-6, atol=1e-12)
+
+
+def test_full_size_properties_c4():
+    """Config 4 at BASELINE's size -- FlowEnsemble of 4 conditional flows on 10^8 rows: the ensemble value is
+    log(mean(exp)) of the four flows' log_probs (flowEnsemble.py:243), row shards equal the whole call, repeated calls
+    are bit-identical, and the first rows equal the oracle's ensemble rule."""
+    from pzflow_b200.plan import ensemble_logmeanexp
+    from pzflow_b200.sharding import shard_rows
+    cfgs = F.config_c4(4)
+    plans = [_plan(c, "tc") for c in cfgs]
+    ex = F.example_flow()
+    mins = torch.as_tensor(ex["bijector_info"][1][0][1][0], device="cuda")
+    maxs = torch.as_tensor(ex["bijector_info"][1][0][1][1], device="cuda")
+    n = 100_000_000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4)
+    X = torch.rand((n, 7), generator=gen, device="cuda") * (maxs - mins) + mins
+    Cn = torch.randn((n, 2), generator=gen, device="cuda")
+    lps = torch.empty((4, n), dtype=torch.float32, device="cuda")
+    for f, p in enumerate(plans):
+        p.log_prob(X, Cn, out=lps[f])
+    ens = ensemble_logmeanexp(lps)
+    assert torch.isfinite(ens).float().mean() > 0.99
+    m = 2_000_000
+    ref = torch.log(torch.exp(lps[:, :m].double()).mean(0))
+    fin = torch.isfinite(ref) & (ref > -80)
+    assert torch.allclose(ens[:m][fin].double(), ref[fin], rtol=1e-5, atol=1e-5)
+    assert torch.equal(plans[2].log_prob(X, Cn), lps[2])
+    for r in (0, 5):
+        a, b = shard_rows(n, r, 8)
+        assert torch.equal(plans[1].log_prob(X[a:b], Cn[a:b]), lps[1][a:b])
+    k = 512
+    flows = [(c["bijector_info"], c["latent_info"], c["params"]) for c in cfgs]
+    want = O.ensemble_log_prob(flows, _np(X[:k]), _np(Cn[:k]))
+    assert_tolerance("C4 full-size head rows", _np(ens[:k]), want, min_frac=0.97, max_class_mismatch=1, below=LP_UNDERFLOW)
+
+
+def test_full_size_properties_c5():
+    """Config 5 at BASELINE's size -- 32-D, K = 32, hidden 256, 10^6 rows on the wide tensor-core engine: determinism,
+    shard independence, inverse(forward(x)) = x and log-det antisymmetry (tests/test_bijectors.py:71-86 of the reference),
+    log_prob = latent log-density + log-det."""
+    from pzflow_b200.sharding import shard_rows
+    cfg = F.config_c5()
+    plan = _plan(cfg, "wide")
+    n = 1_000_000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    X = torch.rand((n, 32), generator=gen, device="cuda") * 2.0 - 1.0
+    lp = plan.log_prob(X)
+    assert torch.equal(lp, plan.log_prob(X))
+    for r in (0, 6):
+        a, b = shard_rows(n, r, 8)
+        assert torch.equal(plan.log_prob(X[a:b]), lp[a:b])
+    u, ld = plan.forward(X)
+    xr, ldi = plan.inverse(u)
+    inside = (u.abs() < 4.9).all(dim=1) & torch.isfinite(lp)
+    assert inside.float().mean() > 0.9
+    err = (xr - X).abs()[inside]
+    assert err.median() < 5e-6 and torch.quantile(err.flatten()[:4_000_000], 0.999) < 1e-3
+    asym = ((ld + ldi).abs() / (1.0 + ld.abs()))[inside]             # sums of 512 float32 log terms of size |ld|
+    print(f"C5 full size: |ld| median {float(ld.abs()[inside].median()):.1f}, relative antisymmetry median {float(asym.median()):.2e}")
+    assert asym.median() < 1e-4
+    lat = torch.from_numpy(O.latent_log_prob(cfg["latent_info"], _np(u[:4096]))).cuda()
+    ok = inside[:4096] & torch.isfinite(lat)
+    assert torch.allclose(lp[:4096][ok], (lat + ld[:4096])[ok], rtol=1e-5, atol=2e-4)
+    assert plan.overflow_rows() == 0
