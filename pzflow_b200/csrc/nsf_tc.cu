@@ -46,6 +46,10 @@
 // Follows the same reference lines as nsf_simt.cu.
 #include "pzb_tc_common.cuh"
 
+#ifndef PZB_TC_STUB
+#define PZB_TC_STUB 0   // bit 0 / bit 1: measurement builds without the spline / the activation arithmetic
+#endif
+
 namespace pzb {
 
 constexpr int TC_TILE = 128;
@@ -561,9 +565,14 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               uint32_t rh[16], rl[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
+#if PZB_TC_STUB & 2   // measurement build only: the LeakyReLU + hi/lo split removed, TMEM traffic kept
+                rh[j] = 0x2c002c00u + (__float_as_uint(dv[2 * j]) & 0x00ff00ffu);
+                rl[j] = __float_as_uint(dv[2 * j + 1]) & 0x03ff03ffu;
+#else
                 float h0, h1;
                 leaky2(dv[2 * j], dv[2 * j + 1], h0, h1);
                 split2(h0, h1, rh[j], rl[j]);
+#endif
               }
               tmem_st16(t_x + bt * 32, rh);
               tmem_st16(t_x + bt * 32 + 16, rl);
@@ -592,11 +601,18 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
                   const float2 sc = make_float2(s2inv, s2inv);  // packed fp32x2 FMA: the same roundings as two FFMAs
                   const float2 p01 = __ffma2_rn(make_float2(dv[4 * q + 0], dv[4 * q + 1]), sc, make_float2(bb.x, bb.y));
                   const float2 p23 = __ffma2_rn(make_float2(dv[4 * q + 2], dv[4 * q + 3]), sc, make_float2(bb.z, bb.w));
+#if PZB_TC_STUB & 2
+                  rh[2 * q] = 0x2c002c00u + (__float_as_uint(p01.x) & 0x00ff00ffu);
+                  rl[2 * q] = __float_as_uint(p01.y) & 0x03ff03ffu;
+                  rh[2 * q + 1] = 0x2c002c00u + (__float_as_uint(p23.x) & 0x00ff00ffu);
+                  rl[2 * q + 1] = __float_as_uint(p23.y) & 0x03ff03ffu;
+#else
                   float h0, h1, h2, h3;
                   leaky2(p01.x, p01.y, h0, h1);
                   leaky2(p23.x, p23.y, h2, h3);
                   split2(h0, h1, rh[2 * q], rl[2 * q]);
                   split2(h2, h3, rh[2 * q + 1], rl[2 * q + 1]);
+#endif
                 }
                 tmem_st16(t_y + bt * 32, rh);
                 tmem_st16(t_y + bt * 32 + 16, rl);
@@ -629,8 +645,15 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               float y, ldd;
               int idx;
               bool fin;
+#if PZB_TC_STUB & 1   // measurement build only (results are garbage): the spline arithmetic removed, its TMEM reads kept
+              y = xin + (raw[0] + raw[47]) * 1e-30f;
+              ldd = raw[20] * 1e-30f;
+              idx = 0;
+              fin = true;
+#else
               spline_dim<INV>(raw, par + TC_PF_B3 + d * TC_DIM_N, par[TC_PF_SCAL + 1], xin, par[TC_PF_SCAL + 2],
                               par[TC_PF_SCAL + 3], pint[TC_PI_PERIODIC] != 0, y, ldd, idx, fin);
+#endif
               if (!fin && ((sh->kok[r >> 5] >> (r & 31)) & 1u))
                 atomicOr(&sh->ovf[r >> 5], 1u << (r & 31));   // (rare) finite inputs, non-finite logits: pzb_plan_overflow_rows
               ldsum += ldd;
