@@ -302,7 +302,7 @@ def case_ensemble_sample(pzflow):
 
 
 def case_jax_streams(pzflow):
-    """Round 3, stand-in installed with prng="threefry" (jax's own key schedule and uniform stream, oracle/jax_prng.py):
+    """Round 2 (second session), stand-in installed with prng="threefry" (jax's own key schedule and uniform stream, oracle/jax_prng.py):
     the reference's Flow.sample for seeds (pzflow/flow.py:783-795 -> distributions.py:464-469), and flows whose chains
     hold Shuffle stages (bijectors.py:780-814; permutation from the key Chain.init_fun hands down, 146-149) and a
     UniformDequantizer (865-911), built with two seeds and re-built from a save dictionary (flow.py:186-187: PRNGKey(0))."""
@@ -347,7 +347,7 @@ def case_jax_streams(pzflow):
 
 def main():
     import sys
-    if len(sys.argv) > 1 and sys.argv[1] == "round3":
+    if len(sys.argv) > 1 and sys.argv[1] == "jax_streams":
         case_jax_streams(jax_shim.install(prng="threefry"))
         return
     pzflow = jax_shim.install()

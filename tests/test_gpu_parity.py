@@ -1913,7 +1913,7 @@ def test_posterior_with_marginalization_like_the_reference_test(flag):
 
 
 # --------------------------------------------------------------------------- #
-# round 3: jax's own random streams, Shuffle, UniformDequantizer               #
+# round 2, second session: jax's own random streams, Shuffle, UniformDequantizer               #
 # --------------------------------------------------------------------------- #
 def test_uniform_latent_draws_are_the_jax_stream():
     """pzb_sample_uniform_threefry == jax.random.uniform(PRNGKey(seed), (n, D), -B, B) as oracle/jax_prng.py restates it
@@ -1972,7 +1972,7 @@ def test_flow_sample_reproduces_what_real_jax_printed():
 def test_shuffle_and_dequantizer_flows_against_reference_golden(engine):
     """Flows whose chains hold Shuffle stages (pzflow/bijectors.py:780-814) and a UniformDequantizer (865-911), built
     with two seeds: log_prob, forward and Flow.sample against what the reference's own code returned (stand-in with
-    jax's key schedule, oracle/make_golden_shim.py round3); a flow re-built from its save dictionary draws its
+    jax's key schedule, oracle/make_golden_shim.py jax_streams); a flow re-built from its save dictionary draws its
     permutations from PRNGKey(0) (flow.py:186-187) and so evaluates differently from the seed-3 flow it was saved from."""
     from pzflow_b200 import Flow
     from pzflow_b200 import bijectors as B
