@@ -260,6 +260,15 @@ int pzb_sample_centbeta(float *U, int64_t N, int32_t D, const float *a, const fl
 int pzb_sample_normal(float *U, int64_t N, int32_t D, uint64_t seed, int64_t row_offset, void *stream);
 int pzb_sample_tdist(float *U, int64_t N, int32_t D, float nu, uint64_t seed, int64_t row_offset, void *stream);
 
+/* RationalQuadraticSpline as the stand-alone function the reference exports (pzflow/utils.py:64-227; the
+ * `_RationalQuadraticSpline` of north_star): inputs [N, L], bin widths W and heights H [N, L, K] (each summing to 2B),
+ * knot derivatives D [N, L, K - 1] (K if periodic) -> outputs [N, L], log_det [N] (negated for the inverse).  Same bin
+ * rule (`sum(knots <= x) - 1`), out-of-bounds identity and NaN for a bin index of K as inside the fused chain kernels,
+ * which build W, H, D from the conditioner themselves and never call this. */
+int pzb_rational_quadratic_spline(const float *inputs, const float *W, const float *H, const float *D, int64_t N,
+                                  int32_t L, int32_t K, float B, int32_t periodic, int32_t inverse, float *outputs,
+                                  float *log_det, void *stream);
+
 /* ---- Gaussian error convolution (err_samples) ---------------------------
  * Flow.log_prob(inputs, err_samples=S) (pzflow/flow.py:448-464) with the default
  * gaussian_error_model (pzflow/utils.py:52-61): every row is expanded into S

@@ -108,6 +108,9 @@ SIGNATURES = {
     "pzb_sample_uniform": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_int64, C.c_void_p]),
     "pzb_sample_uniform_threefry": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_uint32, C.c_uint32,
                                               C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
+    "pzb_rational_quadratic_spline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                                C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                                C.c_void_p]),
     "pzb_set_host_threads": (C.c_int, [C.c_int32]),
     "pzb_sample_centbeta": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64,
                                       C.c_int64, C.c_void_p]),

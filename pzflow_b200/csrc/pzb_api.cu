@@ -1333,6 +1333,77 @@ error_eps_kernel(float* __restrict__ eps, long long n, int W, uint32_t stream_id
 }
 
 
+// RationalQuadraticSpline as the stand-alone function the reference exports (pzflow/utils.py:64-227): inputs [N, L],
+// bin widths / heights W, H [N, L, K] and derivatives D [N, L, K - 1] (K if periodic) given, not produced by a
+// conditioner.  One thread per row walks its L dimensions in order (the log-det sum keeps the reference's order);
+// knots by the sequential fp32 cumulative sum, bin = (#knots <= x) - 1, gathers out of range -> NaN, same op order as
+// the SIMT engine's spline (pz_rqs_eval).
+__global__ void __launch_bounds__(128)
+rqs_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ H, const float* __restrict__ D,
+           long long N, int L, int K, float B, int periodic, int inverse, float* __restrict__ Y, float* __restrict__ LD) {
+  const int nd = K - 1 + (periodic ? 1 : 0);
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < N; row += (long long)gridDim.x * blockDim.x) {
+    float lds = 0.0f;
+    for (int l = 0; l < L; ++l) {
+      const float* w = W + (row * L + l) * (long long)K;
+      const float* h = H + (row * L + l) * (long long)K;
+      const float* d = D + (row * L + l) * (long long)nd;
+      const float x = X[row * L + l];
+      const bool oob = (x <= -B) || (x >= B);
+      const float mx = oob ? fabsf(x) - B : x;
+      const float* srch = inverse ? h : w;
+      int idx = (-B <= mx) ? 0 : -1;
+      float c = 0.0f;
+      for (int k = 0; k < K; ++k) {
+        c = (k == 0) ? srch[0] : c + srch[k];
+        idx += ((-B + c) <= mx) ? 1 : 0;
+      }
+      const bool bad = idx < 0 || idx >= K;
+      const int ic = min(max(idx, 0), K - 1);
+      float cw = 0.0f, ch = 0.0f;
+      for (int k = 0; k < ic; ++k) {
+        cw = (k == 0) ? w[0] : cw + w[k];
+        ch = (k == 0) ? h[0] : ch + h[k];
+      }
+      const float qnan = __int_as_float(0x7fc00000);
+      SplineKnotSel s;
+      s.idx = idx;
+      s.wk = bad ? qnan : w[ic];
+      s.hk = bad ? qnan : h[ic];
+      s.xk = bad ? qnan : (ic == 0 ? -B : -B + cw);
+      s.yk = bad ? qnan : (ic == 0 ? -B : -B + ch);
+      if (periodic) {
+        s.dk = bad ? qnan : (ic == 0 ? d[K - 1] : d[ic - 1]);
+        s.dkp1 = bad ? qnan : d[ic];
+      } else {
+        s.dk = bad ? qnan : (ic == 0 ? 1.0f : d[ic - 1]);
+        s.dkp1 = bad ? qnan : (ic == K - 1 ? 1.0f : d[ic]);
+      }
+      float out, ld;
+      pz_rqs_eval<false>(s, x, mx, oob, inverse != 0, periodic != 0, out, ld);
+      Y[row * L + l] = out;
+      lds += ld;
+    }
+    LD[row] = inverse ? -lds : lds;
+  }
+}
+
+int pzb_rational_quadratic_spline(const float* inputs, const float* W, const float* H, const float* D, int64_t N, int32_t L,
+                                  int32_t K, float B, int32_t periodic, int32_t inverse, float* outputs, float* log_det,
+                                  void* stream) {
+  if (N < 0 || L < 1 || K < 1) return fail(PZB_ERR_INVALID, "rational_quadratic_spline: bad shape");
+  if (N == 0) return PZB_OK;
+  if (!inputs || !W || !H || (!D && K - 1 + (periodic ? 1 : 0) > 0) || !outputs || !log_det)
+    return fail(PZB_ERR_INVALID, "rational_quadratic_spline: NULL buffer");
+  long long blocks = (N + 127) / 128;
+  if (blocks > (long long)current_num_sms() * 32) blocks = (long long)current_num_sms() * 32;
+  rqs_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(inputs, W, H, D, N, L, K, B, periodic, inverse, outputs, log_det);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "rational_quadratic_spline launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
 int pzb_error_eps(float* eps, int64_t n, int32_t W, int32_t stream_id, uint64_t seed, void* stream) {
   if (n < 0 || W < 1 || (stream_id != 0 && stream_id != 1)) return fail(PZB_ERR_INVALID, "error_eps: bad arguments");
   if (n == 0) return PZB_OK;

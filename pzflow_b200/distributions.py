@@ -31,6 +31,17 @@ def _seed(seed) -> int:
     return int(np.random.randint(1e18)) if seed is None else int(seed)
 
 
+def _mahalanobis_and_logdet(x, cov):
+    """Mahalanobis distance of x [N, D] and log-determinant of ``cov`` exactly as pzflow/distributions.py:33-42 writes
+    them (eigen-decomposition; the only caller passes the identity, distributions.py:349-350).  Not on the hot path: the
+    Tdist log-density inside the fused kernels uses |u|^2 and 0."""
+    x = torch.as_tensor(x).to(_device(), torch.float32)
+    vals, vecs = torch.linalg.eigh(torch.as_tensor(np.asarray(cov, dtype=np.float32)).to(x.device))
+    U = vecs * torch.sqrt(1 / vals[..., None])
+    maha = torch.square(U @ x[..., None]).reshape(x.shape[0], -1).sum(dim=1)
+    return maha, torch.log(vals).sum(dim=-1)
+
+
 class LatentDist(ABC):
     """Base class for latent distributions."""
 

@@ -290,6 +290,19 @@ class Flow:
         C, Cerr = self._get_err_arrays(inputs, "conditions")
         return self._plan().log_prob_err(X, Xerr, C, Cerr, err_samples, seed).cpu().numpy()
 
+    def _get_err_samples(self, key, inputs: pd.DataFrame, err_samples: int, type: str = "data", skip: str = None) -> np.ndarray:
+        """Draw error samples for each row of inputs (pzflow/flow.py:339-395): [N * err_samples, W] float32 in the
+        reference's order (row i's samples are consecutive), skip column removed, conditions standard-scaled;
+        zeros [N * err_samples, 1] for the conditions of an unconditional flow.  ``key``: an int seed or the uint32 pair
+        jax.random.PRNGKey(seed) would be.  The fused log_prob / posterior never materialise this (the default Gaussian
+        model is drawn inside the kernels); it exists for callers of the reference's helper."""
+        if type == "conditions" and self.conditional_columns is None:
+            return np.zeros((err_samples * inputs.shape[0], 1), dtype=np.float32)
+        k = np.asarray(key).astype(np.uint64).ravel()
+        seed = int(k[0]) if k.size == 1 else (int(k[0]) << 32) | int(k[1])
+        s = self._err_samples_host(seed, inputs, err_samples, type, skip)          # [S, N, W]
+        return np.ascontiguousarray(s.transpose(1, 0, 2)).reshape(inputs.shape[0] * err_samples, -1)
+
     _HOST_SAMPLE_ROWS = 1 << 22   # rows x samples evaluated per step of the custom-error-model route
 
     def _custom_error_models(self) -> bool:

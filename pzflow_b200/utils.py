@@ -32,3 +32,85 @@ def gaussian_error_model(key, X, Xerr, nsamples):
     eps = error_eps(X.shape[0] * int(nsamples), X.shape[1], 0, seed).cpu().numpy()
     eps = eps.reshape(X.shape[0], int(nsamples), X.shape[1])
     return X[:, None, :] + eps * Xerr[:, None, :]
+
+
+def RationalQuadraticSpline(inputs, W, H, D, B: float, periodic: bool = False, inverse: bool = False):
+    """Apply rational quadratic spline to inputs and return outputs with log_det (pzflow/utils.py:64-227).
+
+    inputs [N, L]; W, H [N, L, K] bin widths / heights (each summing to 2B); D [N, L, K - 1] knot derivatives
+    (K if periodic).  Evaluated on the GPU by pzb_rational_quadratic_spline -- same bin rule, out-of-bounds identity
+    and NaN beyond the last knot as inside the fused chain kernels.  Device tensors in -> device tensors out; anything
+    else -> NumPy arrays."""
+    import numpy as np
+    import torch
+
+    from . import _native as N
+    if not torch.cuda.is_available():
+        raise N.NativeError("pzflow_b200 needs a CUDA device: there is no CPU fallback")
+    as_tensor = isinstance(inputs, torch.Tensor)
+    dev = inputs.device if as_tensor and inputs.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
+    def prep(a):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+        return t.to(device=dev, dtype=torch.float32).contiguous()
+    x, w, h, d = prep(inputs), prep(W), prep(H), prep(D)
+    if x.dim() != 2 or w.dim() != 3 or w.shape[:2] != x.shape or h.shape != w.shape:
+        raise ValueError("RationalQuadraticSpline: inputs [N, L], W and H [N, L, K] expected")
+    n, L, K = w.shape
+    if tuple(d.shape) != (n, L, K - 1 + int(bool(periodic))):
+        raise ValueError(f"RationalQuadraticSpline: D must have shape {(n, L, K - 1 + int(bool(periodic)))}")
+    out = torch.empty_like(x)
+    ld = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().pzb_rational_quadratic_spline(x.data_ptr(), w.data_ptr(), h.data_ptr(), d.data_ptr(), n, L, K,
+                                                      float(B), int(bool(periodic)), int(bool(inverse)), out.data_ptr(),
+                                                      ld.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return (out, ld) if as_tensor else (out.cpu().numpy(), ld.cpu().numpy())
+
+
+def DenseReluNetwork(out_dim: int, hidden_layers: int, hidden_dim: int):
+    """Create a dense neural network with Relu after hidden layers (pzflow/utils.py:22-49): stax-style
+    ``(init_fun, apply_fun)`` of ``serial(*(Dense(hidden_dim), LeakyRelu) * hidden_layers, Dense(out_dim))`` -- LeakyReLU
+    with slope 0.01, despite the name.  Inside a flow the conditioner is part of the fused chain kernels (tcgen05); this
+    stand-alone form exists for API parity and evaluates with library GEMMs on the device (fp32, TF32 off)."""
+    import numpy as np
+    import torch
+
+    from .bijectors import _dense_init, _generator
+
+    def init_fun(rng, input_shape):
+        params = _dense_init(_generator(rng), int(input_shape[-1]), hidden_layers, hidden_dim, out_dim)
+        return tuple(input_shape[:-1]) + (out_dim,), params
+
+    def apply_fun(params, inputs, **kwargs):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pzflow_b200 needs a CUDA device: there is no CPU fallback")
+        as_tensor = isinstance(inputs, torch.Tensor)
+        dev = inputs.device if as_tensor and inputs.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        h = torch.as_tensor(np.asarray(inputs, dtype=np.float32) if not as_tensor else inputs).to(dev, torch.float32)
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            for layer in params:
+                if len(layer) == 0:
+                    h = torch.where(h >= 0, h, 0.01 * h)
+                else:
+                    Wl, bl = (torch.as_tensor(np.asarray(a, dtype=np.float32)).to(dev) if not isinstance(a, torch.Tensor)
+                              else a.to(dev, torch.float32) for a in layer)
+                    h = h @ Wl + bl
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+        return h if as_tensor else h.cpu().numpy()
+
+    return init_fun, apply_fun
+
+
+def sub_diag_indices(inputs):
+    """Return indices for diagonal of 2D blocks in 3D array (pzflow/utils.py:230-243)."""
+    import numpy as np
+    inputs = np.asarray(inputs)
+    if inputs.ndim != 3:
+        raise ValueError("Input must be a 3D array.")
+    nblocks = inputs.shape[0]
+    ndiag = min(inputs.shape[1], inputs.shape[2])
+    return (np.repeat(np.arange(nblocks), ndiag), np.tile(np.arange(ndiag), nblocks), np.tile(np.arange(ndiag), nblocks))

@@ -2206,3 +2206,60 @@ def test_full_size_properties_c5():
     ok = inside[:4096] & torch.isfinite(lat)
     assert torch.allclose(lp[:4096][ok], (lat + ld[:4096])[ok], rtol=1e-5, atol=2e-4)
     assert plan.overflow_rows() == 0
+
+
+def test_stand_alone_spline_and_network_of_the_reference_utils():
+    """pzflow/utils.py:64-227 (RationalQuadraticSpline) and 22-49 (DenseReluNetwork) as stand-alone functions: forward,
+    inverse and periodic splines against the oracle, with rows outside the box, on knots, beyond the last knot and NaN;
+    Flow._get_err_samples in the reference's row order."""
+    from pzflow_b200 import utils as U
+    rng = np.random.default_rng(12)
+    for K, L, periodic in ((16, 4, False), (8, 3, True), (32, 2, False), (1, 2, False)):
+        n, B = 4000, 5.0
+        W = O._softmax(rng.normal(size=(n, L, K)).astype(np.float32)) * np.float32(2 * B)
+        H = O._softmax(rng.normal(size=(n, L, K)).astype(np.float32)) * np.float32(2 * B)
+        D = O._softplus(rng.normal(size=(n, L, K - 1 + int(periodic))).astype(np.float32))
+        x = rng.uniform(-B, B, size=(n, L)).astype(np.float32)
+        x[:40] = rng.uniform(-3 * B, 3 * B, size=(40, L)).astype(np.float32)      # out of bounds: identity, log-det 0
+        x[40, 0], x[41, 0], x[42, 0] = -B, B, np.nan
+        knots = np.concatenate([np.full((n, L, 1), -B, np.float32), -np.float32(B) + np.cumsum(W, -1, dtype=np.float32)], -1)
+        if K > 2:
+            x[50:60, 1] = knots[50:60, 1, 2]                                         # exactly on a knot: the bin to its right
+        for inverse in (False, True):
+            with np.errstate(all="ignore"):
+                yo, ldo, io = O.rational_quadratic_spline(x, W, H, D, B, periodic=periodic, inverse=inverse, return_idx=True)
+            y, ld = U.RationalQuadraticSpline(x, W, H, D, B, periodic=periodic, inverse=inverse)
+            assert y.shape == x.shape and ld.shape == (n,)
+            same_nan = np.isnan(y) == np.isnan(yo)
+            assert same_nan.all(), (K, periodic, inverse, int((~same_nan).sum()))
+            ok = ~np.isnan(yo)
+            np.testing.assert_allclose(y[ok], yo[ok], rtol=2e-6, atol=2e-6)
+            okr = ~np.isnan(ldo) & ~np.isnan(ld)
+            assert (np.isnan(ldo) == np.isnan(ld)).all()
+            np.testing.assert_allclose(ld[okr], ldo[okr], rtol=1e-5, atol=2e-5)
+            if not periodic:
+                oob = (x <= -B) | (x >= B)
+                assert np.array_equal(y[oob], x[oob])
+        # a device tensor in gives device tensors out
+        yt, ldt = U.RationalQuadraticSpline(torch.from_numpy(x).cuda(), W, H, D, B, periodic=periodic)
+        assert yt.is_cuda and ldt.is_cuda
+        # round trip where the forward value stayed inside the box
+        yf, ldf = U.RationalQuadraticSpline(x, W, H, D, B, periodic=periodic)
+        xb, ldb = U.RationalQuadraticSpline(yf, W, H, D, B, periodic=periodic, inverse=True)
+        inside = (np.abs(x) < B * 0.999).all(axis=1) & ~np.isnan(yf).any(axis=1)
+        assert np.median(np.abs(xb - x)[inside]) < 1e-5 and np.median(np.abs(ldf + ldb)[inside]) < 1e-4
+    init_fun, apply_fun = U.DenseReluNetwork(11, 2, 32)
+    _, params = init_fun(3, (7, 5))
+    xin = rng.normal(size=(300, 5)).astype(np.float32)
+    np.testing.assert_allclose(apply_fun(params, xin), O.dense_relu_network(params, xin), rtol=1e-5, atol=1e-5)
+    # Flow._get_err_samples (pzflow/flow.py:339-395): [N * S, W], row i's samples consecutive, zero error -> the row itself
+    from pzflow_b200.examples import get_example_flow
+    flow = get_example_flow()
+    df = pd.DataFrame(F.galaxy_rows(10, seed=2).astype(np.float64), columns=flow.data_columns)
+    df["u_err"] = 0.1
+    s = flow._get_err_samples(5, df, 4, type="data")
+    assert s.shape == (40, 7) and s.dtype == np.float32
+    np.testing.assert_array_equal(s[:, 0], np.repeat(df["redshift"].to_numpy().astype(np.float32), 4))
+    assert np.abs(s[:, 1] - np.repeat(df["u"].to_numpy(), 4)).max() > 0 and np.abs(s[:, 1] - np.repeat(df["u"].to_numpy(), 4)).max() < 1.0
+    assert flow._get_err_samples(5, df, 4, type="conditions").shape == (40, 1)
+    assert flow._get_err_samples(5, df, 4, type="data", skip="redshift").shape == (40, 6)

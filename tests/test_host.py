@@ -586,3 +586,29 @@ def test_shuffle_permutations_follow_the_chain_key_schedule():
     assert B.Chain(B.Shuffle(), B.UniformDequantizer([0, 2]))[1] == ("Chain", (("Shuffle", ()), ("UniformDequantizer", ([0, 2],))))
     kinds = [s["kind"] for s in P.flatten(("UniformDequantizer", (2,)), (), 7)]
     assert kinds == [N.STAGE_DEQUANTIZE]
+
+
+def test_small_helpers_of_the_reference_utils_and_examples(monkeypatch, tmp_path):
+    """pzflow/utils.py:230-243 (the reference's own test_sub_diag_indices_correct / _bad_input) and the example-data
+    loaders (pzflow/examples.py:13-102): the data sets are not redistributed, the loaders say where they look."""
+    import pandas as pd
+    from pzflow_b200 import examples as E
+    from pzflow_b200 import utils as U
+    x = np.array([[[0, 0], [0, 0]], [[1, 1], [1, 1]], [[2, 2], [2, 2]]])
+    y = np.array([[[1, 0], [0, 1]], [[2, 1], [1, 2]], [[3, 2], [2, 3]]])
+    idx = U.sub_diag_indices(x)
+    x[idx] = x[idx] + 1
+    assert np.array_equal(x, y)
+    for bad in (np.ones(2), np.ones((2, 2)), np.ones((2, 2, 2, 2))):
+        with pytest.raises(ValueError):
+            U.sub_diag_indices(bad)
+    monkeypatch.setenv("PZFLOW_EXAMPLE_FILES", str(tmp_path))
+    with pytest.raises(FileNotFoundError):
+        E.get_galaxy_data()
+    frame = pd.DataFrame({"x": [0.0, 1.0], "y": [2.0, 3.0]})
+    frame.to_pickle(tmp_path / "two-moons-data.pkl")
+    assert E.get_twomoons_data().equals(frame)
+    init_fun, apply_fun = U.DenseReluNetwork(5, 2, 16)
+    shape, params = init_fun(0, (10, 3))
+    assert shape == (10, 5)
+    assert [tuple(np.shape(q) for q in p) for p in params] == [((3, 16), (16,)), (), ((16, 16), (16,)), (), ((16, 5), (5,))]
