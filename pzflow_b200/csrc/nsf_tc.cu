@@ -707,7 +707,10 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
       }
       if (overflow_rows != nullptr && __any_sync(0xffffffffu, n_bad != 0u)) {
         for (int o = 16; o > 0; o >>= 1) n_bad += __shfl_xor_sync(0xffffffffu, n_bad, o);
-        if (lane == 0) atomicAdd(overflow_rows, (unsigned long long)n_bad);
+        if (lane == 0) {
+          atomicAdd(overflow_rows, (unsigned long long)n_bad);
+          if (args.ovf_flag != nullptr) *args.ovf_flag = 1u;
+        }
       }
       // (pass A of the next chunk touches a row from the same thread as pass Z did: no barrier needed)
       if (fuse) {

@@ -738,7 +738,10 @@ nsf_chain_wide_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, WdLaunc
       }
       if (half == 0 && overflow_rows != nullptr) {
         const unsigned m = __ballot_sync(0xffffffffu, bad_row);
-        if (lane == 0 && m != 0u) atomicAdd(overflow_rows, (unsigned long long)__popc(m));
+        if (lane == 0 && m != 0u) {
+          atomicAdd(overflow_rows, (unsigned long long)__popc(m));
+          if (args.ovf_flag != nullptr) *args.ovf_flag = 1u;
+        }
       }
       // (pass A of the next tile touches a row from the same thread as pass Z did: no barrier needed)
     }

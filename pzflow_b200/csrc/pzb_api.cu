@@ -99,6 +99,11 @@ struct HostPipe {
   void* h_out0[NBUF] = {};
   void* h_out1[NBUF] = {};
   size_t cap_hout0 = 0, cap_hout1 = 0;
+  // the fp16 guard: one device word per ring slot that a tensor-core launch sets when a row overflowed, copied to a
+  // page-locked per-chunk array behind the chunk's results
+  unsigned int* d_flag = nullptr;
+  unsigned int* h_flags = nullptr;
+  size_t cap_flags = 0;
 };
 
 struct pzb_plan {
@@ -729,6 +734,8 @@ void pzb_plan_destroy(pzb_plan* plan) {
       cudaEventDestroy(hp.ev_out[b]);
     }
     cudaFree(hp.d_grid);
+    if (hp.d_flag) cudaFree(hp.d_flag);
+    if (hp.h_flags) cudaFreeHost(hp.h_flags);
     for (int b = 0; b < HostPipe::NBUF; ++b) {
       if (hp.h_in[b]) cudaFreeHost(hp.h_in[b]);
       if (hp.h_cond[b]) cudaFreeHost(hp.h_cond[b]);
@@ -1723,6 +1730,7 @@ struct HostJob {
   int n_flows = 0;
   const float* cond_mean = nullptr;
   const float* cond_std = nullptr;
+  int64_t base = 0;            // unit offset into the COLUMN arrays (in_cols / cond_cols / out_cols) of a sliced job
 };
 
 static cudaError_t host_reserve(void** p, size_t* cap, size_t want, int n) {
@@ -1792,32 +1800,51 @@ static bool host_pointer_is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
-static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* who);
+struct UnitSpan {
+  int64_t u0, nu;
+};
+static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* who, std::vector<UnitSpan>* flagged);
+
+// units [u0, u0 + nu) of a job as a job of its own
+static HostJob job_slice(const HostJob& job, int C, int64_t u0, int64_t nu) {
+  HostJob s = job;
+  if (s.in) s.in += u0 * s.in_w;
+  if (s.cond) s.cond += u0 * C;
+  if (s.out0) s.out0 += u0 * s.out0_w;
+  if (s.out1) s.out1 += u0;
+  s.base = job.base + u0;
+  s.units = nu;
+  return s;
+}
 
 // The fp16 guard of an AUTO-engine plan: the tensor-core engines carry activations as fp16 hi/lo pairs, so a
-// conditioner pre-activation beyond +-65504 turns a row into NaN where the reference's fp32 stays finite.  Such rows
-// (finite inputs, NaN log-determinant) are counted on the device; a host-buffer call that raised the counter is
-// evaluated again on the SIMT engine (fp32 throughout), so the caller gets the reference's answer either way.
+// conditioner pre-activation beyond +-65504 turns a row into NaN where the reference's fp32 stays finite (catalogue
+// placeholders like -9999 are enough).  Such rows (finite inputs, non-finite logits) are counted on the device and every
+// tensor-core launch of the pipeline reports whether ITS chunk held one; the flagged chunks -- not the whole call --
+// are evaluated again on the SIMT engine (fp32 throughout), so the caller gets the reference's answer either way and
+// a few bad rows in 10 M cost a few chunks, not a tenfold slower call.
 static int run_host(const pzb_plan* plan, const HostJob& job, const char* who) {
   if (job.units == 0) return PZB_OK;
   const bool guarded = plan->engine == PZB_ENGINE_AUTO && !g_force_simt && pzb_plan_engine(plan) != PZB_ENGINE_SIMT &&
                        job.n_flows == 0;
-  int rc = run_host_once(plan, job, who);
-  if (rc != PZB_OK || !guarded) return rc;
-  unsigned long long now = 0;
-  {
-    DeviceGuard guard(plan->device);
-    if (cudaMemcpy(&now, plan->d_overflow, sizeof(now), cudaMemcpyDeviceToHost) != cudaSuccess) return PZB_OK;
-  }
-  const unsigned long long before = plan->overflow_seen.exchange(now);
-  if (now <= before) return PZB_OK;
+  if (!guarded) return run_host_once(plan, job, who, nullptr);
+  std::vector<UnitSpan> flagged;
+  int rc = run_host_once(plan, job, who, &flagged);
+  if (rc != PZB_OK || flagged.empty()) return rc;
   g_force_simt = true;
-  rc = run_host_once(plan, job, who);
+  for (size_t k = 0; k < flagged.size() && rc == PZB_OK; ++k) {
+    UnitSpan sp = flagged[k];
+    while (k + 1 < flagged.size() && flagged[k + 1].u0 == sp.u0 + sp.nu) sp.nu += flagged[++k].nu;  // adjacent chunks together
+    rc = run_host_once(plan, job_slice(job, plan->host.C, sp.u0, sp.nu), who, nullptr);
+  }
   g_force_simt = false;
+  unsigned long long now = 0;
+  DeviceGuard guard(plan->device);
+  if (cudaMemcpy(&now, plan->d_overflow, sizeof(now), cudaMemcpyDeviceToHost) == cudaSuccess) plan->overflow_seen.store(now);
   return rc;
 }
 
-static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* who) {
+static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* who, std::vector<UnitSpan>* flagged) {
   HostPipe& hp = plan->pipe;
   std::lock_guard<std::mutex> lock(hp.mu);
   DeviceGuard guard(plan->device);
@@ -1875,6 +1902,20 @@ static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* w
     ce = host_reserve(hp.h_out0, &hp.cap_hout0, (size_t)chunk * job.out0_w * sizeof(float), HostPipe::NBUF);
   if (ce == cudaSuccess && stage_out && job.out1)
     ce = host_reserve(hp.h_out1, &hp.cap_hout1, (size_t)chunk * sizeof(float), HostPipe::NBUF);
+  std::vector<UnitSpan> spans;  // the chunks of this call, in order (per-chunk guard)
+  if (ce == cudaSuccess && flagged != nullptr) {
+    // chunk count: the ramp (1/8, 1/4, 1/2) adds at most three chunks
+    const size_t n_chunks = (size_t)((job.units + chunk - 1) / chunk) + 4;
+    if (hp.d_flag == nullptr) ce = cudaMalloc(reinterpret_cast<void**>(&hp.d_flag), HostPipe::NBUF * sizeof(unsigned int));
+    if (ce == cudaSuccess && n_chunks > hp.cap_flags) {
+      if (hp.h_flags) cudaFreeHost(hp.h_flags);
+      hp.h_flags = nullptr;
+      hp.cap_flags = 0;
+      ce = cudaMallocHost(reinterpret_cast<void**>(&hp.h_flags), n_chunks * sizeof(unsigned int));
+      if (ce == cudaSuccess) hp.cap_flags = n_chunks;
+    }
+    spans.reserve(n_chunks);
+  }
   if (ce != cudaSuccess) return cuda_fail(ce, "host pipeline staging buffers");
   int64_t pend_u0[HostPipe::NBUF] = {}, pend_nu[HostPipe::NBUF] = {};
   // chunk j's staged results -> the caller's arrays, once its D2H copy has completed
@@ -1883,8 +1924,8 @@ static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* w
     cudaError_t e = cudaEventSynchronize(hp.ev_out[bj]);
     if (e != cudaSuccess) return e;
     if (job.out_cols)
-      scatter_rows_to_cols(static_cast<const float*>(hp.h_out0[bj]), job.out0_w, pend_u0[bj], pend_nu[bj], job.out_cols,
-                           host_threads);
+      scatter_rows_to_cols(static_cast<const float*>(hp.h_out0[bj]), job.out0_w, job.base + pend_u0[bj], pend_nu[bj],
+                           job.out_cols, host_threads);
     else
       parallel_copy(job.out0 + pend_u0[bj] * job.out0_w, hp.h_out0[bj], (size_t)pend_nu[bj] * job.out0_w * sizeof(float),
                     host_threads);
@@ -1907,10 +1948,11 @@ static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* w
       // the cast of chunk i then runs on the host cores while the GPU works on chunks i-1, i-2
       if (i >= HostPipe::NBUF) cudaEventSynchronize(hp.ev_in[b]);
       auto gather = job.cols_f32 ? gather_cast_rows<float> : gather_cast_rows<double>;
-      gather(job.in_cols, job.in_w, u0, nu, static_cast<float*>(hp.h_in[b]), nullptr, nullptr, host_threads);
+      gather(job.in_cols, job.in_w, job.base + u0, nu, static_cast<float*>(hp.h_in[b]), nullptr, nullptr, host_threads);
       src_in = static_cast<const float*>(hp.h_in[b]);
       if (C > 0) {
-        gather(job.cond_cols, C, u0, nu, static_cast<float*>(hp.h_cond[b]), job.cond_mean, job.cond_std, host_threads);
+        gather(job.cond_cols, C, job.base + u0, nu, static_cast<float*>(hp.h_cond[b]), job.cond_mean, job.cond_std,
+               host_threads);
         src_cond = static_cast<const float*>(hp.h_cond[b]);
       }
     } else if (stage_in) {
@@ -1941,6 +1983,10 @@ static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* w
     a.N = nu * rows_per_unit;
     a.out0 = static_cast<float*>(hp.d_out0[b]);
     a.out1 = job.out1 ? static_cast<float*>(hp.d_out1[b]) : nullptr;
+    if (flagged != nullptr) {
+      a.ovf_flag = hp.d_flag + b;
+      cudaMemsetAsync(a.ovf_flag, 0, sizeof(unsigned int), hp.s_k);
+    }
     if (job.n_flows > 0) {
       float* ens = static_cast<float*>(hp.d_ens[b]);
       const size_t per_flow = (size_t)nu * job.out0_w;
@@ -1976,6 +2022,10 @@ static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* w
     ce = cudaMemcpyAsync(dst0, hp.d_out0[b], (size_t)nu * job.out0_w * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out);
     if (ce == cudaSuccess && job.out1)
       ce = cudaMemcpyAsync(dst1, hp.d_out1[b], (size_t)nu * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out);
+    if (ce == cudaSuccess && flagged != nullptr && (size_t)i < hp.cap_flags) {
+      ce = cudaMemcpyAsync(hp.h_flags + i, hp.d_flag + b, sizeof(unsigned int), cudaMemcpyDeviceToHost, hp.s_out);
+      spans.push_back({u0, nu});
+    }
     if (ce == cudaSuccess) ce = cudaEventRecord(hp.ev_out[b], hp.s_out);
     if (ce != cudaSuccess) { rc = cuda_fail(ce, "host pipeline D2H"); break; }
     pend_u0[b] = u0;
@@ -1998,6 +2048,9 @@ static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* w
   if (rc != PZB_OK) return rc;
   ce = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
   if (ce != cudaSuccess) return cuda_fail(ce, who);
+  if (flagged != nullptr)
+    for (size_t k = 0; k < spans.size(); ++k)
+      if (hp.h_flags[k] != 0u) flagged->push_back(spans[k]);
   return PZB_OK;
 }
 

@@ -132,6 +132,9 @@ struct LaunchArgs {
   // the error samples, the sum over the variants, the per-galaxy trapezoid normalisation and NaN -> 0
   // (pzflow/flow.py:720-737) happen in shared memory before the only HBM write.
   int fuse, normalize, nan_to_zero;
+  // set to 1 by a tensor-core launch in which some row of finite inputs got non-finite logits (an fp16 overflow of a
+  // conditioner pre-activation): the host pipeline's per-chunk guard (pzb_api.cu: run_host); may be null
+  unsigned int* ovf_flag;
 };
 
 // ---- counter-based normals for the error samples: Philox-4x32-10 keyed by the seed, counter =

@@ -434,15 +434,40 @@ def test_fp16_overflow_rows_are_counted():
     assert zero_class(lp)[[5, 100, 200]].all() and not zero_class(lp, LP_UNDERFLOW)[[4, 6, 199, 201]].any()
     plan.set_engine("simt")   # fp32 throughout: finite logits, the rows are merely out of bounds
     lp_simt = _np(plan.log_prob(torch.from_numpy(X).cuda()))
-    # an AUTO plan's host-buffer calls notice the counter and re-evaluate on the SIMT engine: the reference's answer
+    # an AUTO plan's host-buffer calls notice the overflow and re-evaluate the pipeline chunks that held such rows on the
+    # SIMT engine: the reference's answer for them, the tensor-core result everywhere else
     plan.set_engine("auto")
     assert plan.engine == "wide"
     plan.overflow_rows(reset=True)
     lp_host = plan.log_prob_host(X).numpy()
-    assert np.array_equal(lp_host.view(np.int32), lp_simt.view(np.int32))
+    is_simt = lp_host.view(np.int32) == lp_simt.view(np.int32)
+    assert is_simt[[5, 200]].all() and (is_simt | (lp_host.view(np.int32) == lp.view(np.int32))).all()
     Xok = np.delete(X, [5, 200], axis=0)
     assert np.array_equal(plan.log_prob_host(Xok).numpy().view(np.int32),
                           _np(plan.log_prob(torch.from_numpy(Xok).cuda())).view(np.int32))   # no overflow: no second pass
+    # the guard works per pipeline chunk: bad rows in one chunk of a long call send THAT chunk through the SIMT engine,
+    # every other row keeps the tensor-core result bit for bit (-9999 style catalogue placeholders are enough to overflow)
+    big = rng.uniform(-4, 4, size=(3_000_000, 4)).astype(np.float32)
+    bad = [2_500_000, 2_500_017]
+    big[bad, 0] = -5.0e6
+    dev = torch.from_numpy(big).cuda()
+    tc = _np(plan.log_prob(dev))
+    plan.set_engine("simt")
+    simt = _np(plan.log_prob(dev))
+    plan.set_engine("auto")
+    plan.overflow_rows(reset=True)
+    host = plan.log_prob_host(big).numpy()
+    same_tc = host.view(np.int32) == tc.view(np.int32)
+    same_simt = host.view(np.int32) == simt.view(np.int32)
+    assert same_simt[bad].all() and zero_class(tc)[bad].all()
+    assert (same_tc | same_simt).all()
+    redone = np.nonzero(~same_tc)[0]                     # rows that differ from the tensor-core result: one chunk's worth
+    assert redone.size and redone.min() > 1_000_000 and redone.max() - redone.min() < 1_400_000
+    assert same_tc[:1_000_000].all()
+    # the same through the DataFrame column path of Flow.log_prob (sliced column jobs) -- values only
+    cols = [np.ascontiguousarray(big[:, j].astype(np.float64)) for j in range(4)]
+    hc = plan.log_prob_host_columns(cols).numpy()
+    assert np.array_equal(hc.view(np.int32), host.view(np.int32))
 
 
 @pytest.mark.parametrize("info,D,C", [
