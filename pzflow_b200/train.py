@@ -577,9 +577,11 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
         flow._params = chain.numpy_params()
         flow._plan_cache.clear()
         lp = flow._plan().log_prob(torch.as_tensor(X, device=dev), C if C is None else torch.as_tensor(C, device=dev))
-        lp = torch.where(lp < -1e30, torch.full_like(lp, -math.inf), lp)   # finfo.min is the zero-probability class
-        # a zero-weight row with zero probability contributes 0, not 0 * -inf = NaN
-        return float(-torch.where(W == 0, torch.zeros_like(lp), W * lp).mean().item())
+        # Zero-probability rows come back as finfo.min, as from the reference's nan_to_num (pzflow/flow.py:406), and enter
+        # the float32 mean as such: ONE such row makes the loss huge but finite (~1e38 / n) and training goes on -- the
+        # reference's own test_patience relies on it -- while a batch of them overflows the sum to inf and ends the run as
+        # diverged (its test_nan_train_stop).
+        return float(-(W * lp).mean().item())
 
     n = len(inputs)
     W = np.ones(n, np.float32) if train_weight is None else np.asarray(train_weight, np.float32)
@@ -619,7 +621,9 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
         loop = tqdm(loop)
     for epoch in loop:
         idx = torch.as_tensor(perm_rng.permutation(n), device=dev)            # flow.py:1063-1066
-        for b0 in range(0, n, batch_size):
+        # a chain without parameters (e.g. the reference's own Flow(columns, Reverse()) test flows) has nothing to step:
+        # its epochs only record the (constant) loss, and patience / divergence end them as in the reference
+        for b0 in (range(0, n, batch_size) if chain.leaves else ()):
             sel = idx[b0:b0 + batch_size]
             a, b = shard_batch(len(sel), rank, world)
             if fused is not None:

@@ -1,0 +1,134 @@
+"""Behaviours the reference's own test-suite asserts for Flow / FlowEnsemble (pzflow tests/test_flow.py,
+tests/test_ensemble.py), restated against the mirror package on the B200: shapes, error conventions, the training
+loop's bookkeeping (loss lists, patience, divergence, validation, weights, condition scaling) and the error-sample
+helper.  The reference exercises them on parameter-free flows -- ``Flow(columns, Reverse())`` -- and on the default
+bijector; so does this file.  Values are covered by tests/test_gpu_parity.py; this file is about the API contract."""
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+XY = ("redshift", "y")
+
+
+def _points():
+    # the third point lies outside the default CentBeta13(2, 5) support: its log-probability is finfo.min (flow.py:406)
+    return pd.DataFrame(np.array([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]]), columns=XY)
+
+
+def _reverse_flow(**kw):
+    from pzflow_b200 import Flow
+    from pzflow_b200.bijectors import Reverse
+    return Flow(XY, Reverse(), **kw)
+
+
+def test_training_bookkeeping_on_a_parameter_free_flow():
+    """tests/test_flow.py: test_patience, test_train_no_errs_same, test_nan_train_stop, test_train_bad_inputs."""
+    x = _points()
+    losses = _reverse_flow().train(x, patience=2)
+    # constant loss: epoch 1 sets the best value, epochs 2 and 3 fail to improve it -> initial + 3 entries; the
+    # zero-probability point makes the loss huge (~1e38 / 3) but FINITE, so patience, not divergence, ends the run
+    assert len(losses) == 4 and np.isfinite(losses).all() and losses[0] > 1e37 and len(set(losses)) == 1
+    flow = _reverse_flow()
+    assert np.allclose(flow.train(x, convolve_errs=True), flow.train(x, convolve_errs=False))
+    nan_rows = pd.DataFrame(np.full((4, 2), np.nan), columns=["x", "y"])
+    from pzflow_b200 import Flow
+    from pzflow_b200.bijectors import Reverse
+    stopped = Flow(nan_rows.columns, Reverse()).train(nan_rows)
+    assert len(stopped) == 2 and not np.isfinite(stopped).any()      # four finfo.min rows overflow the float32 mean
+    for epochs in (-1, 2.4, "a"):
+        with pytest.raises(ValueError):
+            _reverse_flow().train(x, epochs=epochs)
+
+
+def test_training_with_conditions_validation_weights_and_no_initial_loss():
+    """tests/test_flow.py: test_train_w_conditions, test_validation_train, test_train_weights, test_no_initial_loss."""
+    from pzflow_b200 import Flow
+    from pzflow_b200.bijectors import Reverse
+    from pzflow_b200.distributions import Normal
+    table = np.array([[1.0, 2.0, 0.1, 0.2], [3.0, 4.0, 0.3, 0.4], [5.0, 6.0, 0.5, 0.6]])
+    frame = pd.DataFrame(table, columns=XY + ("a", "b"))
+    flow = Flow(XY, Reverse(), latent=Normal(2), conditional_columns=("a", "b"))
+    assert len(flow.train(frame, epochs=11)) == 12
+    np.testing.assert_allclose(flow._condition_means, table[:, 2:].mean(axis=0), rtol=1e-6)   # flow.py:989-998
+    np.testing.assert_allclose(flow._condition_stds, table[:, 2:].std(axis=0), rtol=1e-6)
+    data = pd.DataFrame(np.random.default_rng(0).normal(size=(10, 2)), columns=("x", "y"))
+    fit, held = data[:8], data[8:]
+    for kw, n in ((dict(), 4), (dict(train_weight=np.linspace(1, 2, 8), val_weight=np.linspace(1, 2, 2)), 4),
+                  (dict(initial_loss=False), 3)):
+        both = Flow(fit.columns, Reverse()).train(fit, held, verbose=True, epochs=3, best_params=False, **kw)
+        assert [len(part) for part in both] == [n, n]
+
+
+def test_shapes_and_errors_of_the_public_calls():
+    """tests/test_flow.py: test_returns_correct_shape, test_conditional_sample, test_bijector_not_set,
+    test_latent_with_wrong_dimension, test_control_sample_randomness; tests/test_ensemble.py: shapes of every call."""
+    from pzflow_b200 import Flow, FlowEnsemble
+    from pzflow_b200.bijectors import Reverse
+    from pzflow_b200.distributions import Normal, Uniform
+    frame = pd.DataFrame(np.arange(12, dtype=float).reshape(-1, 4) / 12, columns=("x", "y", "a", "b"))
+    grid = np.arange(0, 2.1, 0.12)
+    for flow in (Flow(("x", "y"), Reverse(), latent=Normal(2)), Flow(("x", "y"), Reverse(), conditional_columns=("a", "b"))):
+        assert flow.log_prob(frame).shape == (3,) and flow.log_prob(frame, err_samples=10).shape == (3,)
+        assert flow.posterior(frame, column="x", grid=grid).shape == (3, grid.size)
+        assert flow.posterior(frame, column="x", grid=grid, err_samples=10).shape == (3, grid.size)
+        assert flow.posterior(frame.iloc[:1], column="y", grid=grid).shape == (1, grid.size)
+    cond = Flow(("x", "y"), Reverse(), conditional_columns=("a", "b"))
+    assert cond._get_conditions(frame).shape == (3, 2)
+    with pytest.raises(ValueError):
+        cond.sample(4)                                               # conditions are required (flow.py:777-780)
+    assert cond.sample(4, conditions=frame).shape == (12, 4)
+    assert cond.sample(4, conditions=frame, save_conditions=False).shape == (12, 2)
+    plain = Flow(("x", "y"), Reverse(), latent=Uniform(2, 5))
+    assert plain.sample(7, seed=3).equals(plain.sample(7, seed=3)) and not plain.sample(7, seed=3).equals(plain.sample(7, seed=4))
+    unset = Flow(["x", "y"])
+    with pytest.raises(ValueError):
+        unset.sample(1)
+    with pytest.raises(ValueError):
+        unset.posterior(frame, column="x", grid=grid)
+    with pytest.raises(ValueError):
+        Flow(data_columns=["x", "y"], latent=Uniform(3), bijector=Reverse())
+    ens = FlowEnsemble(("x", "y"), Reverse(), N=2)
+    two = pd.DataFrame(np.arange(12, dtype=float).reshape(-1, 2) / 12, columns=("x", "y"))
+    assert ens.log_prob(two).shape == (6,) and ens.log_prob(two, returnEnsemble=True).shape == (6, 2)
+    assert ens.posterior(two, "x", grid).shape == (6, grid.size)
+    assert ens.posterior(two, "x", grid, returnEnsemble=True).shape == (6, 2, grid.size)
+    assert ens.sample(3, seed=0).shape == (3, 2) and ens.sample(3, seed=0, returnEnsemble=True).shape == (6, 2)
+    assert len(ens.train(two, epochs=4)) == 2
+
+
+def test_error_sample_helper_contract():
+    """tests/test_flow.py::test_get_err_samples: [N * S, W] in row order, the skipped column removed, conditions scaled,
+    a user's error model called as given, an unknown type refused."""
+    from pzflow_b200 import Flow
+    from pzflow_b200.bijectors import Reverse
+    noisy = pd.DataFrame(np.array([[1.0, 2.0, 0.1, 0.2], [3.0, 4.0, 0.3, 0.4]]), columns=("x", "y", "x_err", "y_err"))
+    exact = pd.DataFrame(np.array([[1.0, 2.0, 0, 0]]), columns=("x", "y", "x_err", "y_err"))
+    flow = Flow(("x", "y"), Reverse())
+    assert flow._get_err_samples(0, noisy, 10).shape == (20, 2)
+    np.testing.assert_allclose(flow._get_err_samples(0, exact, 10, skip="y"), np.ones((10, 1)))
+    np.testing.assert_allclose(flow._get_err_samples(0, exact, 10, skip="x"), 2 * np.ones((10, 1)))
+    on_y = Flow(("x"), Reverse(), conditional_columns=("y"))
+    np.testing.assert_allclose(on_y._get_err_samples(0, exact, 10, type="conditions"), 2 * np.ones((10, 1)))
+    with pytest.raises(ValueError):
+        flow._get_err_samples(0, exact, 10, type="wrong")
+
+    def shifted(key, X, Xerr, nsamples):
+        return np.repeat(X + Xerr, nsamples, axis=0).reshape(X.shape[0], nsamples, X.shape[1])
+    table = noisy.to_numpy()
+    got = Flow(("x", "y"), Reverse(), data_error_model=shifted)._get_err_samples(0, noisy, 10)
+    np.testing.assert_allclose(got, shifted(None, table[:, :2], table[:, 2:], 10).reshape(20, 2), rtol=1e-6)
+    by_cond = Flow(("x"), Reverse(), conditional_columns=("y"), condition_error_model=shifted)
+    np.testing.assert_allclose(by_cond._get_err_samples(0, noisy, 10, type="conditions"),
+                               np.repeat(np.array([[2.2], [4.4]]), 10, axis=0), rtol=1e-6)
+
+
+def test_default_bijector_trains_without_nans():
+    """tests/test_flow.py::test_default_bijector: Flow(columns).train(data) builds ShiftBounds + RollingSplineCoupling."""
+    from pzflow_b200 import Flow
+    data = pd.DataFrame(np.random.default_rng(1).normal(size=(2000, 2)), columns=("x", "y"))
+    flow = Flow(["x", "y"])
+    losses = flow.train(data, epochs=3)
+    assert len(losses) == 4 and np.isfinite(losses).all() and losses[-1] < losses[0]
+    assert flow._bijector_info[0] == "Chain" and flow._bijector_info[1][0][0] == "ShiftBounds"
