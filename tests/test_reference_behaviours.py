@@ -132,3 +132,72 @@ def test_default_bijector_trains_without_nans():
     losses = flow.train(data, epochs=3)
     assert len(losses) == 4 and np.isfinite(losses).all() and losses[-1] < losses[0]
     assert flow._bijector_info[0] == "Chain" and flow._bijector_info[1][0][0] == "ShiftBounds"
+
+
+ROWS = np.array([[0.2, 0.1, -0.3, 0.5, 0.1, -0.4, -0.3],
+                 [0.6, 0.5, 0.2, 0.2, -0.4, -0.1, 0.7],
+                 [0.9, 0.2, -0.3, 0.3, 0.4, -0.4, -0.1]], np.float32)
+
+
+def _battery():
+    from pzflow_b200 import bijectors as B
+    none = np.zeros((3, 1), np.float32)
+    return [
+        ("ColorTransform", lambda: B.ColorTransform(3, [1, 3, 5]), none),
+        ("Reverse", lambda: B.Reverse(), none),
+        ("Roll", lambda: B.Roll(2), none),
+        ("Scale", lambda: B.Scale(2.0), none),
+        ("Shuffle", lambda: B.Shuffle(), none),
+        ("InvSoftplus", lambda: B.InvSoftplus(0), none),
+        ("InvSoftplus-2", lambda: B.InvSoftplus([1, 3], [2.0, 12.0]), none),
+        ("StandardScaler", lambda: B.StandardScaler(np.linspace(-1, 1, 7), np.linspace(1, 8, 7)), none),
+        ("Chain", lambda: B.Chain(B.Reverse(), B.Scale(1 / 6), B.Roll(-1)), none),
+        ("NeuralSplineCoupling", lambda: B.NeuralSplineCoupling(), none),
+        ("NeuralSplineCoupling-args", lambda: B.NeuralSplineCoupling(16, 3, 2, 128, 3), np.arange(9, dtype=np.float32).reshape(3, 3)),
+        ("RollingSplineCoupling", lambda: B.RollingSplineCoupling(2), none),
+        ("RollingSplineCoupling-periodic", lambda: B.RollingSplineCoupling(2, 1, 16, 3, 2, 128, None, 0, True), none),
+        ("ShiftBounds", lambda: B.ShiftBounds(-0.5, 0.9, 5), none),
+        ("ShiftBounds-vector", lambda: B.ShiftBounds(-1 * np.ones(7), 1.1 * np.ones(7), 3), none),
+    ]
+
+
+@pytest.mark.parametrize("case", range(15))
+def test_every_bijector_of_the_reference_battery_is_a_bijection(case):
+    """tests/test_bijectors.py::TestBijectors (shapes, inverse(forward(x)) = x and log-det antisymmetry on its 3 x 7
+    input) for every bijector the reference lists there -- Shuffle included -- through the Bijector protocol."""
+    name, make, cond = _battery()[case]
+    init_fun, info = make()
+    params, forward_fun, inverse_fun = init_fun(0, ROWS.shape[-1])
+    y, ld = forward_fun(params, ROWS, conditions=cond)
+    assert y.shape == ROWS.shape and ld.shape == (3,), name
+    xi, ldi = inverse_fun(params, ROWS, conditions=cond)
+    assert xi.shape == ROWS.shape and ldi.shape == (3,), name
+    back, ldb = inverse_fun(params, y, conditions=cond)
+    np.testing.assert_allclose(back, ROWS, atol=3e-6, err_msg=name)
+    np.testing.assert_allclose(ld, -ldb, atol=3e-6, err_msg=name)
+
+
+def test_dequantizer_shape_bad_arguments_and_latent_contract():
+    """tests/test_bijectors.py::test_uniform_dequantizer_returns_correct_shape and test_bad_inputs;
+    tests/test_distributions.py (log_prob / sample shapes, seeds control the draws) for every latent."""
+    from pzflow_b200 import bijectors as B
+    from pzflow_b200 import distributions as Dn
+    init_fun, _ = B.UniformDequantizer([1, 3, 4])
+    params, forward_fun, _ = init_fun(0, 7)
+    assert forward_fun(params, ROWS, conditions=np.zeros((3, 1), np.float32))[0].shape == ROWS.shape
+    for make in (lambda: B.ColorTransform(0, [1, 2, 3, 4]), lambda: B.ColorTransform(1.3, [1, 2, 3, 4]),
+                 lambda: B.ColorTransform(1, [2, 3, 4]), lambda: B.Roll(2.4), lambda: B.Scale(2), lambda: B.Scale(np.arange(7)),
+                 lambda: B.InvSoftplus([0, 1, 2], [1.0, 2.0]),
+                 lambda: B.RollingSplineCoupling(2, 1, 16, 3, 2, 128, None, 0, "fake"), lambda: B.ShiftBounds(4, 2, 1),
+                 lambda: B.ShiftBounds(np.array([0, 1]), 2, 1)):
+        with pytest.raises(ValueError):
+            make()
+    latents = [(Dn.CentBeta(2), ((0.0, 1.0), (2.0, 3.0))), (Dn.CentBeta13(2), ()), (Dn.Normal(2), ()),
+               (Dn.Tdist(2), np.log(30.0)), (Dn.Uniform(2), ())]
+    joint = Dn.Joint(Dn.Normal(1), Dn.Uniform(1, 3), Dn.CentBeta13(1))
+    latents.append((joint, joint._params))
+    for dist, p in latents:
+        pts = np.full((3, dist.input_dim), 0.1, np.float32) * np.arange(1, 4, dtype=np.float32)[:, None]
+        assert np.shape(dist.log_prob(p, pts)) == (3,)
+        a, b, c = dist.sample(p, 4, 0), dist.sample(p, 4, 0), dist.sample(p, 4, 1)
+        assert np.shape(a) == (4, dist.input_dim) and np.allclose(a, b) and not np.allclose(a, c)
