@@ -201,3 +201,70 @@ def test_dequantizer_shape_bad_arguments_and_latent_contract():
         assert np.shape(dist.log_prob(p, pts)) == (3,)
         a, b, c = dist.sample(p, 4, 0), dist.sample(p, 4, 0), dist.sample(p, 4, 1)
         assert np.shape(a) == (4, dist.input_dim) and np.allclose(a, b) and not np.allclose(a, c)
+
+
+def test_an_ensemble_is_its_flows_and_survives_a_file(tmp_path):
+    """tests/test_ensemble.py (test_log_prob, test_posterior, test_sample, test_conditional_sample, test_train,
+    test_load_ensemble, test_bad_inputs) and tests/test_flow.py::test_load_flow: flow i of FlowEnsemble(N) is
+    Flow(seed=i); the ensemble rules are log(mean(exp)) and mean-then-normalise; sampling takes ceil(n / N) rows per
+    flow; training flow i uses seed default_rng(0).integers(1e9, size=N)[i]; files round-trip and refuse the wrong class."""
+    import dill
+    from pzflow_b200 import Flow, FlowEnsemble
+    from pzflow_b200.bijectors import Reverse, RollingSplineCoupling
+    ens = FlowEnsemble(("x", "y"), RollingSplineCoupling(nlayers=2), N=2)
+    members = [Flow(("x", "y"), RollingSplineCoupling(nlayers=2), seed=s) for s in (0, 1)]
+    pts = pd.DataFrame(np.arange(6).reshape(3, 2) / 10, columns=("x", "y"))
+    each = np.stack([m.log_prob(pts) for m in members], axis=1)
+    np.testing.assert_allclose(ens.log_prob(pts, returnEnsemble=True), each, rtol=1e-6)
+    np.testing.assert_allclose(ens.log_prob(pts), np.log(np.exp(each).mean(axis=1)), rtol=1e-6)
+    grid = np.linspace(-1, 1, 5)
+    per = np.stack([m.posterior(pts, "x", grid) for m in members], axis=1)
+    np.testing.assert_allclose(ens.posterior(pts, "x", grid, returnEnsemble=True), per, rtol=1e-6)
+    raw = np.mean([m.posterior(pts, "x", grid, normalize=False) for m in members], axis=0)
+    np.testing.assert_allclose(ens.posterior(pts, "x", grid), raw / np.trapezoid(raw, grid, axis=1)[:, None], rtol=1e-5)
+    drawn = ens.sample(10, seed=0).values
+    stacked = np.vstack([m.sample(5, seed=0).values for m in members])
+    np.testing.assert_allclose(drawn[drawn[:, 0].argsort()], stacked[stacked[:, 0].argsort()])
+    np.testing.assert_allclose(ens.sample(10, seed=0, returnEnsemble=True).values,
+                               np.vstack([m.sample(10, seed=0).values for m in members]))
+    cond = FlowEnsemble(("x", "y"), RollingSplineCoupling(nlayers=2, n_conditions=2), conditional_columns=("a", "b"), N=2)
+    one = pd.DataFrame(np.arange(2).reshape(-1, 2), columns=("a", "b"))
+    five = pd.DataFrame(np.arange(10).reshape(-1, 2), columns=("a", "b"))
+    assert cond.sample(nsamples=1, conditions=one, save_conditions=False).shape == (1, 2)
+    assert cond.sample(nsamples=1, conditions=five, save_conditions=False).shape == (5, 2)
+    assert cond.sample(nsamples=2, conditions=five, save_conditions=False).shape == (10, 2)
+    assert cond.sample(nsamples=1, conditions=five, save_conditions=False, returnEnsemble=True).shape == (10, 2)
+    data = pd.DataFrame(np.random.default_rng(0).normal(size=(100, 2)), columns=("x", "y"))
+    path = tmp_path / "ensemble.pzflow.pkl"
+    before = ens.sample(10, seed=0)
+    ens.save(str(path))
+    np.testing.assert_allclose(FlowEnsemble(file=str(path)).sample(10, seed=0).values, before.values)
+    curves = ens.train(data, epochs=4, batch_size=50)
+    seeds = np.random.default_rng(0).integers(1e9, size=2)
+    for i, m in enumerate(members):
+        np.testing.assert_allclose(curves[f"Flow {i}"], m.train(data, epochs=4, batch_size=50, seed=seeds[i]), rtol=1e-6)
+    with open(path, "rb") as fh:
+        stored = dill.load(fh)
+    stored["class"] = "Flow"
+    with open(path, "wb") as fh:
+        dill.dump(stored, fh, recurse=True)
+    with pytest.raises(TypeError):
+        FlowEnsemble(file=str(path))
+    for kw in (dict(), dict(bijector=Reverse()), dict(data_columns=("x", "y"), file="file"), dict(bijector=Reverse(), file="file"),
+               dict(info="fake", file="file")):
+        with pytest.raises(ValueError):
+            FlowEnsemble(**kw)
+    single = tmp_path / "flow.pzflow.pkl"
+    Flow(("x", "y"), Reverse(), info=["random", 42]).save(str(single))
+    loaded = Flow(file=str(single))
+    ints = np.array([[1, 2], [3, 4]])
+    np.testing.assert_allclose(loaded._forward(loaded._params, ints)[0], ints[:, ::-1])
+    np.testing.assert_allclose(loaded._inverse(loaded._params, loaded._forward(loaded._params, ints)[0])[0], ints)
+    assert loaded.info == ["random", 42]
+    with open(single, "rb") as fh:
+        stored = dill.load(fh)
+    stored["class"] = "FlowEnsemble"
+    with open(single, "wb") as fh:
+        dill.dump(stored, fh, recurse=True)
+    with pytest.raises(TypeError):
+        Flow(file=str(single))
