@@ -99,3 +99,13 @@ def permutation(key, n: int, layout_name: str = None) -> np.ndarray:
         key, sub = split(key, 2, "threefry_partitionable" if part else "threefry")
         x = x[np.argsort(words(sub, n, part), kind="stable")]
     return x
+
+
+def epoch_orders(batch_seed: int, n: int, layout_name: str = None):
+    """The row order of every training epoch as the reference draws it (pzflow/flow.py:1015, 1062-1064):
+    ``key = PRNGKey(batch_seed)``; per epoch ``permute_key, sample_key, key = split(key, 3)`` and
+    ``idx = permutation(permute_key, n)``.  An endless generator of index arrays."""
+    key = key_from_seed(int(batch_seed))
+    while True:
+        permute_key, _, key = split(key, 3, layout_name)
+        yield permutation(permute_key, n, layout_name)

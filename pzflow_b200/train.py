@@ -603,6 +603,24 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
     (Xm, Xe), (Cm, Ce) = arrays(inputs)
     Xm, Xe, Cm, Ce = to_dev(Xm), to_dev(Xe), to_dev(Cm), to_dev(Ce)
     perm_rng = np.random.default_rng(int(batch_seed))
+    # The reference's epoch schedule (flow.py:1015, 1062-1064): key = PRNGKey(batch_seed); every epoch
+    # permute_key, sample_key, key = split(key, 3) and idx = permutation(permute_key, n) -- reproduced on the host
+    # (pzflow_b200.prng) while that stays cheap; beyond 4 M rows the epochs are shuffled by NumPy's generator instead.
+    from . import prng as _prng
+    epoch_key = _prng.key_from_seed(int(batch_seed)) if (_prng.layout() != "philox" and n <= (1 << 20)) else None
+
+    def jax_epoch_orders():
+        """The reference's permutation of every epoch (prng.epoch_orders), each computed one epoch ahead on a helper
+        thread (NumPy releases the GIL) so that the host-side threefry + sort hides behind the previous epoch's kernels."""
+        from concurrent.futures import ThreadPoolExecutor
+        orders = _prng.epoch_orders(int(batch_seed), n)
+        with ThreadPoolExecutor(1) as pool:
+            pending = pool.submit(next, orders)
+            while True:
+                order = pending.result()
+                pending = pool.submit(next, orders)
+                yield order
+    epoch_orders = jax_epoch_orders() if epoch_key is not None else None
     noise = torch.Generator(device=dev)
     noise.manual_seed(int(batch_seed) + rank)   # every rank draws its own eps for its own share of the batch
     best_loss, best_vals, stall = math.inf, chain.numpy_params(), 0
@@ -620,7 +638,10 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
         from tqdm import tqdm
         loop = tqdm(loop)
     for epoch in loop:
-        idx = torch.as_tensor(perm_rng.permutation(n), device=dev)            # flow.py:1063-1066
+        if epoch_orders is not None:
+            idx = torch.as_tensor(next(epoch_orders), device=dev)              # flow.py:1062-1064
+        else:
+            idx = torch.as_tensor(perm_rng.permutation(n), device=dev)
         # a chain without parameters (e.g. the reference's own Flow(columns, Reverse()) test flows) has nothing to step:
         # its epochs only record the (constant) loss, and patience / divergence end them as in the reference
         for b0 in (range(0, n, batch_size) if chain.leaves else ()):
@@ -667,6 +688,8 @@ def train_flow(flow, inputs, val_set=None, train_weight=None, val_weight=None, e
         if not np.isfinite(losses[-1]):
             print(f"Training stopping after epoch {epoch + 1}", "because training loss diverged.")
             break
+    if epoch_orders is not None:
+        epoch_orders.close()
     flow._params = best_vals if best_params else chain.numpy_params()            # flow.py:1151-1154
     flow._plan_cache.clear()
     return losses if val_set is None else [losses, val_losses]

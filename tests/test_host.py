@@ -612,3 +612,18 @@ def test_small_helpers_of_the_reference_utils_and_examples(monkeypatch, tmp_path
     shape, params = init_fun(0, (10, 3))
     assert shape == (10, 5)
     assert [tuple(np.shape(q) for q in p) for p in params] == [((3, 16), (16,)), (), ((16, 16), (16,)), (), ((16, 5), (5,))]
+
+
+def test_training_epochs_are_shuffled_like_the_reference():
+    """pzflow/flow.py:1015, 1062-1064: key = PRNGKey(batch_seed); per epoch permute_key, sample_key, key = split(key, 3),
+    idx = permutation(permute_key, n) -- prng.epoch_orders against the oracle's restatement of jax.random."""
+    from oracle import jax_prng as J
+    from pzflow_b200 import prng
+    for seed, n in ((0, 10), (5, 1000), (2 ** 31 + 1, 77)):
+        orders = prng.epoch_orders(seed, n)
+        key = J.PRNGKey(seed)
+        for _ in range(3):
+            permute_key, _, key = J.split(key, 3)
+            got = next(orders)
+            np.testing.assert_array_equal(got, J.permutation(permute_key, n))
+            assert sorted(got) == list(range(n))
