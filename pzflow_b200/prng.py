@@ -10,8 +10,10 @@ csrc/pzb_api.cu); this module only derives keys and the handful of words a ``Cha
 Layouts: ``"threefry"`` is jax's original layout (``jax_threefry_partitionable=False``).  It reproduces the samples
 the reference's authors printed from real JAX in docs/tutorials/marginalization.ipynb:133-135 (``flow.sample(2,
 seed=0)`` of the shipped flow) digit for digit, and ``split(PRNGKey(0))`` equals the value quoted in jax's
-documentation -- it is the default.  ``"threefry_partitionable"`` is the layout newer jax releases default to;
-nothing in the reference tree was produced with it, so it is offered UNVERIFIED.  ``"philox"`` keeps round 1's
+documentation -- it is the default.  ``"threefry_partitionable"`` is the layout jax releases from 0.5.0 on default to
+(``jax_threefry_partitionable=True``), i.e. what the reference draws under its pinned jax 0.5.3 unless that flag is
+turned off; nothing in the reference tree was produced with it and jax is not installable here, so it is offered
+UNVERIFIED (``PZFLOW_B200_PRNG=threefry_partitionable`` or ``set_layout``) and the verified layout stays the default.  ``"philox"`` keeps round 1's
 Philox-4x32-10 streams (not jax-compatible; any size).
 """
 from __future__ import annotations
