@@ -342,6 +342,32 @@ def case_jax_streams(pzflow):
         if seed == 3:
             again = Flow(_dictionary=fl._save_dict())     # what Flow(file=...) does after unpickling
             store["s3_reloaded_log_prob"] = _np(again.log_prob(df))
+    # FlowEnsemble.sample with conditions (pzflow/flowEnsemble.py:409-471): more rows than flows -> the conditions are
+    # shuffled (pandas, random_state = seed / 1e9), split into n_flows chunks, the CHUNKS permuted by
+    # jax.random.permutation(PRNGKey(seed), ...), flow i draws chunk i; fewer rows than flows -> NumPy picks a flow and a
+    # seed per row.  Uniform latents, so the draws themselves are jax's stream.
+    from pzflow import FlowEnsemble
+    # flowEnsemble.py:431 calls np.array_split on a DataFrame; pandas >= 2.1 with NumPy 2 returns bare arrays there (older
+    # releases returned positional DataFrame chunks, which is what the code expects): restore that for the call
+    _split = np.array_split
+    np.array_split = lambda a, n, axis=0: ([a.iloc[i] for i in _split(np.arange(len(a)), n)] if isinstance(a, pd.DataFrame)
+                                           else _split(a, n, axis))
+    ccols = ("p", "q")
+    ens = FlowEnsemble(("a", "b", "c"), B.Chain(B.ShiftBounds(jnp.array(mins[:3]), jnp.array(maxs[:3]), 4.0),
+                                                B.RollingSplineCoupling(3, K=8, hidden_dim=32, n_conditions=2)),
+                       latent=Dn.Uniform(3, 5), conditional_columns=ccols, N=3)
+    for i, fl in enumerate(ens._ensemble.values()):
+        _boost(fl._params[1], np.random.default_rng(60 + i))
+        F.pack_tree(f"cens{i}_params", fl._params[1], store)
+    F.pack_tree("cens_info", ens._ensemble["Flow 0"]._bijector_info, store)
+    conds = pd.DataFrame(rng.normal(size=(7, 2)), columns=ccols, index=[3, 1, 4, 15, 9, 2, 6])
+    store["cens_conditions"], store["cens_index"] = conds.to_numpy(), conds.index.to_numpy()
+    for tag, frame, ns, seed in (("many", conds, 2, 12), ("few", conds.iloc[:2], 1, 5), ("exact", conds.iloc[:3], 1, 7)):
+        out = ens.sample(ns, conditions=frame, save_conditions=True, seed=seed)
+        store[f"cens_{tag}_sample"] = out.to_numpy().astype(np.float32)
+        store[f"cens_{tag}_index"] = out.index.to_numpy()
+        store[f"cens_{tag}_args"] = np.array([ns, seed, len(frame)])
+    np.array_split = _split
     _save("jax_streams", store)
 
 

@@ -228,23 +228,29 @@ class FlowEnsemble:
             samples = pd.concat([flow.sample(N, conditions, save_conditions, seed)
                                  for flow in self._ensemble.values()])
             return samples.sample(nsamples, random_state=seed).reset_index(drop=True)
-        if nsamples > 1:
-            conditions = pd.concat([conditions] * nsamples)
+        # Conditional draws (pzflow/flowEnsemble.py:409-471): every condition row (repeated nsamples times) is handed
+        # to ONE flow.  Which flow is decided on row POSITIONS here, one Flow.sample call per flow; the draws the
+        # reference makes to decide -- pandas' shuffle with random_state = seed / 1e9, jax.random.permutation of the
+        # chunks under PRNGKey(seed), NumPy's choice / integers for fewer rows than flows -- are the same ones.
+        from . import prng
+        members = list(self._ensemble.values())
+        rows = pd.concat([conditions] * nsamples) if nsamples > 1 else conditions
         seed = np.random.randint(1e18) if seed is None else seed
-        if conditions.shape[0] > len(self._ensemble):
-            conditions_shuffled = conditions.sample(frac=1.0, random_state=int(seed / 1e9))
-            n = len(self._ensemble)
-            chunks = [conditions_shuffled.iloc[idx] for idx in
-                      np.array_split(np.arange(conditions_shuffled.shape[0]), n)]
-            order = np.random.default_rng(seed).permutation(len(chunks))
-            chunks = [chunks[i] for i in order]
-            return pd.concat([flow.sample(1, chunk, save_conditions, seed).set_index(chunk.index)
-                              for flow, chunk in zip(self._ensemble.values(), chunks)]).sort_index()
-        rng = np.random.default_rng(seed)
-        flows = rng.choice(list(self._ensemble.values()), size=conditions.shape[0], replace=True)
-        seeds = rng.integers(1e18, size=conditions.shape[0])
-        return pd.concat([flow.sample(1, conditions[i:i + 1], save_conditions, int(new_seed))
-                          for i, (flow, new_seed) in enumerate(zip(flows, seeds))]).set_index(conditions.index)
+        n_rows, n_flows = rows.shape[0], len(members)
+        if n_rows > n_flows:
+            shuffled = pd.Series(np.arange(n_rows)).sample(frac=1.0, random_state=int(seed / 1e9)).to_numpy()
+            parts = np.array_split(shuffled, n_flows)                    # positions, ~equal parts in shuffled order
+            turn = prng.permutation(prng.key_from_seed(seed), n_flows)   # flow i draws part turn[i]
+            pieces = []
+            for flow, part in zip(members, (parts[t] for t in turn)):
+                block = rows.iloc[part]
+                pieces.append(flow.sample(1, block, save_conditions, seed).set_index(block.index))
+            return pd.concat(pieces).sort_index()
+        picker = np.random.default_rng(seed)
+        chosen = picker.choice(n_flows, size=n_rows, replace=True)
+        row_seeds = picker.integers(1e18, size=n_rows)
+        return pd.concat([members[f].sample(1, rows[i:i + 1], save_conditions, int(sd))
+                          for i, (f, sd) in enumerate(zip(chosen, row_seeds))]).set_index(rows.index)
 
     # ------------------------------------------------------------------ #
     def save(self, file: str) -> None:

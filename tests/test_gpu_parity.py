@@ -2291,3 +2291,35 @@ def test_stand_alone_spline_and_network_of_the_reference_utils():
     assert np.abs(s[:, 1] - np.repeat(df["u"].to_numpy(), 4)).max() > 0 and np.abs(s[:, 1] - np.repeat(df["u"].to_numpy(), 4)).max() < 1.0
     assert flow._get_err_samples(5, df, 4, type="conditions").shape == (40, 1)
     assert flow._get_err_samples(5, df, 4, type="data", skip="redshift").shape == (40, 6)
+
+
+def test_conditional_ensemble_sampling_against_reference_golden():
+    """FlowEnsemble.sample with conditions (pzflow/flowEnsemble.py:409-471) against what the reference's own code returned
+    over the stand-in with jax's key schedule: which flow draws which condition row (pandas' shuffle, jax.random.permutation
+    of the chunks, NumPy's choice for fewer rows than flows) AND the drawn values (Uniform latents: jax's stream)."""
+    from pzflow_b200 import FlowEnsemble
+    from pzflow_b200 import bijectors as B
+    from pzflow_b200 import distributions as Dn
+    g = golden("ref_shim_jax_streams.npz")
+    mins, maxs = g["mins"][:3], g["maxs"][:3]
+    ens = FlowEnsemble(("a", "b", "c"), B.Chain(B.ShiftBounds(mins, maxs, 4.0),
+                                                B.RollingSplineCoupling(3, K=8, hidden_dim=32, n_conditions=2)),
+                       latent=Dn.Uniform(3, 5), conditional_columns=("p", "q"), N=3)
+    for i, fl in enumerate(ens._ensemble.values()):
+        fl._params = (fl._params[0], F.unpack_tree(f"cens{i}_params", g))
+        fl._plan_cache.clear()
+    conds = pd.DataFrame(g["cens_conditions"], columns=("p", "q"), index=g["cens_index"])
+    for tag in ("many", "few", "exact"):
+        ns, seed, nrow = (int(v) for v in g[f"cens_{tag}_args"])
+        out = ens.sample(ns, conditions=conds.iloc[:nrow], save_conditions=True, seed=seed)
+        assert list(out.columns) == ["a", "b", "c", "p", "q"]
+        np.testing.assert_array_equal(out.index.to_numpy(), g[f"cens_{tag}_index"])
+        want = g[f"cens_{tag}_sample"]
+        err = np.abs(out.to_numpy() - want)
+        print(f"ensemble conditional sample [{tag}]: max |err| {err.max():.2e}")
+        # rows with the same index (the nsamples copies of one condition) may come back in either order: compare as sets
+        for idx in np.unique(g[f"cens_{tag}_index"]):
+            a = out.to_numpy()[out.index.to_numpy() == idx]
+            b = want[g[f"cens_{tag}_index"] == idx]
+            a, b = a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])]
+            np.testing.assert_allclose(a, b, rtol=3e-4, atol=3e-4)
