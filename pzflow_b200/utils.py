@@ -111,6 +111,6 @@ def sub_diag_indices(inputs):
     inputs = np.asarray(inputs)
     if inputs.ndim != 3:
         raise ValueError("Input must be a 3D array.")
-    nblocks = inputs.shape[0]
-    ndiag = min(inputs.shape[1], inputs.shape[2])
-    return (np.repeat(np.arange(nblocks), ndiag), np.tile(np.arange(ndiag), nblocks), np.tile(np.arange(ndiag), nblocks))
+    per_block = min(inputs.shape[1:])
+    block, along = np.divmod(np.arange(inputs.shape[0] * per_block), per_block)   # (block, k, k) for every diagonal entry
+    return block, along, along
