@@ -1938,6 +1938,9 @@ static int run_host_once(const pzb_plan* plan, const HostJob& job, const char* w
   // ramp: the first chunks are 1/8, 1/4, 1/2 of the steady-state chunk, so the first kernel starts after a short
   // copy instead of a full-size one (the un-overlapped head of the pipeline)
   int64_t cur = std::max<int64_t>(1, chunk / 8);
+  // ... unless the whole call is a couple of waves of CTAs: a kernel launch has a floor of a few tens of microseconds
+  // (one tile walks the whole chain), so four small launches in a row cost more than the copy they would hide
+  if (job.units * rows_per_unit <= (int64_t)plan->num_sms * 1024 * 2) cur = chunk;
   for (int64_t u0 = 0; u0 < job.units && rc == PZB_OK; ++i) {
     const int b = (int)(i % HostPipe::NBUF);
     const int64_t nu = std::min(cur, job.units - u0);
