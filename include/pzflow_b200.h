@@ -373,6 +373,12 @@ int pzb_adam_step(float *params, const float *grads, float *m, float *v, int64_t
  * A caller that drives several devices from several host threads gives each its share. */
 int pzb_set_host_threads(int32_t n);
 
+/* (no reference counterpart) Content check of host arrays for the Python mirror's plan cache: sums[2i] = wrapping sum of
+ * leaf i's 8-byte words, sums[2i + 1] = sum of its tail bytes; all n leaves in one call on the host cores.  A cached
+ * plan is reused only while the parameter arrays it was built from are the same objects AND still hold the same bytes
+ * (in-place edits of a weight array must not evaluate stale weights).  No device work. */
+int pzb_host_digest(const void *const *leaves, const int64_t *nbytes, int32_t n, uint64_t *sums);
+
 /* ---- host-buffer forms --------------------------------------------------
  * The same evaluations for callers whose arrays live in HOST memory, which is
  * where the reference's callers hold them (NumPy arrays cut from a DataFrame,

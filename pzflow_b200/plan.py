@@ -189,6 +189,34 @@ def _leaf_digest(leaf) -> tuple:
     return (a.dtype.str, a.shape, s, t)
 
 
+def _digest(leaves: Sequence) -> tuple:
+    """Content digest of all leaves.  NumPy arrays go to pzb_host_digest in ONE call (the library's host cores; ~15 us for
+    the 7-D flow's 42 arrays instead of ~130 us of NumPy reductions per Flow call); anything else, or a missing library,
+    takes ``_leaf_digest``.  Same sums either way."""
+    idx, ptrs, sizes = [], [], []
+    out: list = [None] * len(leaves)
+    for i, leaf in enumerate(leaves):
+        if isinstance(leaf, np.ndarray) and leaf.flags.c_contiguous and leaf.dtype != object:
+            idx.append(i)
+            ptrs.append(leaf.__array_interface__["data"][0])
+            sizes.append(leaf.nbytes)
+        else:
+            out[i] = _leaf_digest(leaf)
+    if idx:
+        try:
+            lib = N.lib()
+            n = len(idx)
+            sums = (C.c_uint64 * (2 * n))()
+            N.check(lib.pzb_host_digest((C.c_void_p * n)(*ptrs), (C.c_int64 * n)(*sizes), n, sums))
+            for k, i in enumerate(idx):
+                a = leaves[i]
+                out[i] = (a.dtype.str, a.shape, int(sums[2 * k]), int(sums[2 * k + 1]))
+        except (N.NativeError, OSError, AttributeError):
+            for i in idx:
+                out[i] = _leaf_digest(leaves[i])
+    return tuple(out)
+
+
 class PlanCache:
     """Device plans keyed on a params pytree.  An entry holds a STRONG reference to every leaf it was built from
     and matches a query only if each leaf is the same object (``is``; ids of freed arrays get reused, so ids alone
@@ -212,14 +240,14 @@ class PlanCache:
             if dev != device or len(held) != len(leaves) or not all(a is b for a, b in zip(held, leaves)):
                 continue
             if digest is None:
-                digest = tuple(_leaf_digest(x) for x in leaves)
+                digest = _digest(leaves)
             if dg == digest:
                 self._entries.append(self._entries.pop(i))
                 return plan
             del self._entries[i]  # same arrays, edited in place: the old plan is stale
             break
         if digest is None:
-            digest = tuple(_leaf_digest(x) for x in leaves)
+            digest = _digest(leaves)
         plan = build()
         self._entries.append((device, leaves, digest, plan))
         while len(self._entries) > self.max_plans:
