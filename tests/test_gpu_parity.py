@@ -2323,3 +2323,29 @@ def test_conditional_ensemble_sampling_against_reference_golden():
             b = want[g[f"cens_{tag}_index"] == idx]
             a, b = a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])]
             np.testing.assert_allclose(a, b, rtol=3e-4, atol=3e-4)
+
+
+@pytest.mark.parametrize("engine", ["simt", "tc", "wide"])
+def test_posteriors_overlay_the_figures_real_jax_plotted(engine):
+    """docs/tutorials/marginalization.ipynb cells 9-15 through the public API: flow.posterior(samples, "redshift", grid)
+    and the same with u / y flagged 99 and marg_rules over 40 x 40 values -- the curves land on the lines of the figures
+    the reference's authors made with real JAX (tests/golden/nb_posterior_plots.npz; one pixel = 0.8 % of a panel's
+    tallest peak).  tests/test_oracle.py holds the oracle's version of the check and its negative controls."""
+    import plots as PL
+    from test_oracle import check_against_the_notebook_figures
+    from pzflow_b200.examples import get_example_flow
+    flow = get_example_flow()
+    flow._plan().set_engine(engine)
+    samples = flow.sample(2, seed=0)                                   # the notebook's own first step (cell 5)
+    nb = golden("ref_shim_example_flow.npz")["nb_X"]
+    np.testing.assert_allclose(samples.to_numpy(), nb, rtol=3e-6)
+    grid = PL.NB_GRID
+    plain = flow.posterior(samples, column="redshift", grid=grid)
+    flagged = samples.copy()
+    flagged.iloc[0, 1] = 99
+    flagged.iloc[1, 1] = 99
+    flagged.iloc[1, -1] = 99
+    rules = {"flag": 99, "u": lambda row: PL.NB_U_GRID, "y": lambda row: PL.NB_Y_GRID}
+    marg = flow.posterior(flagged, column="redshift", grid=grid, marg_rules=rules)
+    check_against_the_notebook_figures(samples.to_numpy(), plain, marg, engine)
+    flow._plan().set_engine("auto")

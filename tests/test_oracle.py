@@ -344,3 +344,66 @@ def test_latent_densities_against_scipy():
     outside[0, 1] = 5.5
     assert np.isneginf(O.latent_log_prob(("Uniform", (3, 5)), outside)[0])
     assert np.isneginf(O.latent_log_prob(("CentBeta13", (3, 5)), outside)[0])
+
+
+# --------------------------------------------------------------------------- #
+# (5) the posterior curves real JAX plotted                                     #
+# --------------------------------------------------------------------------- #
+def _notebook_curves():
+    """Plain and marginalised redshift posteriors of the notebook's two samples, by the oracle: plain as cell 9 asks;
+    marginalised by brute force over every combination of the rules' grids (cell 14), summed un-normalised with NaN -> 0,
+    then normalised (pzflow/flow.py:560-664, 732-737)."""
+    import itertools
+    import plots as PL
+    ex = F.example_flow()
+    bi, li, p = ex["bijector_info"], ex["latent_info"], ex["params"]
+    nb = golden("ref_shim_example_flow.npz")["nb_X"]
+    grid = PL.NB_GRID
+    plain = O.flow_posterior(bi, li, p, np.ascontiguousarray(nb[:, 1:]), 0, grid)
+    out = []
+    for row, missing in ((nb[0], [(1, PL.NB_U_GRID)]), (nb[1], [(1, PL.NB_U_GRID), (6, PL.NB_Y_GRID)])):
+        combos = np.array(list(itertools.product(*[g for _, g in missing])), np.float32)
+        rest = np.repeat(row[None, 1:], len(combos), axis=0).astype(np.float32)
+        for q, (col, _) in enumerate(missing):
+            rest[:, col - 1] = combos[:, q]
+        tot = O.flow_posterior(bi, li, p, rest, 0, grid, normalize=False, nan_to_zero=True).sum(axis=0)
+        out.append(tot / O.trapezoid(tot[None], grid)[0])
+    return nb, plain, np.stack(out)
+
+
+def check_against_the_notebook_figures(nb, plain, marg, tag=""):
+    """Shared by the CPU (oracle) and the GPU (CUDA) test: every pixel of the blue / orange line of the figures the
+    reference's authors made with real JAX (docs/tutorials/marginalization.ipynb cells 10 and 15) lies on the polyline
+    the computed curves predict -- 2.5-pixel-wide anti-aliased lines, so <= 2.2 px from the centre line -- and the
+    curve's vertices are all drawn.  One pixel is 0.8 % of the panel's tallest peak."""
+    import plots as PL
+    g = golden("nb_posterior_plots.npz")
+    for panel in (0, 1):
+        z = float(nb[panel, 0])
+        reports = {"cell 10 blue": PL.overlay_report(g, 10, panel, z, [plain[panel]], 0, "blue"),
+                   "cell 15 orange": PL.overlay_report(g, 15, panel, z, [plain[panel], marg[panel]], 1, "orange"),
+                   "cell 15 blue": PL.overlay_report(g, 15, panel, z, [plain[panel], marg[panel]], 0, "blue")}
+        for name, r in reports.items():
+            print(f"FIGURE {tag} panel {panel} {name}: {r}")
+            assert r["pixels"] > 20 and r["median"] < 0.8 and r["max"] < 2.2, (name, r)
+        assert reports["cell 10 blue"]["vertices_hit"] >= 0.9 and reports["cell 15 orange"]["vertices_hit"] >= 0.9
+
+
+def test_posterior_curves_overlay_the_figures_real_jax_plotted():
+    """The forward path, log-density, posterior normalisation and the marginalisation rules against real JAX output: the
+    notebook's figures.  Negative controls show what the check resolves: a 4 % lower peak, or the variants averaged
+    with the wrong normalisation order, leave the drawn line."""
+    import plots as PL
+    nb, plain, marg = _notebook_curves()
+    check_against_the_notebook_figures(nb, plain, marg, "oracle")
+    g = golden("nb_posterior_plots.npz")
+    # (a panel's y-axis follows its tallest curve, so a single curve is checked in SHAPE: relative to its peak)
+    # (the first sample's posterior is a single spike on this grid; the second has two comparable points: 1 and 0.82)
+    bent = plain[1].copy()
+    bent[np.argsort(bent)[-2]] *= 0.95                     # the second-highest grid point 5 % lower
+    assert PL.overlay_report(g, 10, 1, float(nb[1, 0]), [bent], 0, "blue")["max"] > 2.2
+    # two curves share the axis: the marginalised posterior 5 % lower than it is leaves its drawn line
+    assert PL.overlay_report(g, 15, 0, float(nb[0, 0]), [plain[0], 0.95 * marg[0]], 1, "orange")["max"] > 2.2
+    shifted = np.roll(plain[1], 1)
+    assert PL.overlay_report(g, 10, 1, float(nb[1, 0]), [shifted], 0, "blue")["max"] > 5
+    assert PL.overlay_report(g, 15, 1, float(nb[1, 0]), [plain[1], plain[1]], 1, "orange")["max"] > 5   # not the plain curve
