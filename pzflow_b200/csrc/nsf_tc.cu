@@ -975,6 +975,8 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
 
 static int tc_fit_tiles(const TcLaunch& lp, int acc_floats) {
   int fit = TC_MAX_CHUNK_TILES;
+  if (const char* cap = getenv("PZB_TC_CHUNK_TILES"))   // experiments only: fewer tiles per chunk than shared memory holds
+    fit = std::max(2, std::min(fit, atoi(cap)));
   while (fit > 2 && tc_smem_layout(lp.max_pass, fit, lp.state_cols, acc_floats).total + 1024 > TC_SMEM_MAX) --fit;
   return fit - (fit & 1);  // the two epilogue groups take alternate tiles: keep the count even
 }
