@@ -320,6 +320,21 @@ int pzb_posterior_marg(const pzb_plan *plan, const float *rest, const float *res
  * reproduce the expansion exactly. */
 int pzb_error_eps(float *eps, int64_t n, int32_t W, int32_t stream_id, uint64_t seed, void *stream);
 
+/* The error samples in jax's OWN stream.  pzb_set_error_stream(layout, total_units) tells the NEXT pzb_log_prob_err /
+ * pzb_posterior_err calls of this host thread to draw eps as the reference does (pzflow/flow.py:455-464, 552-553, 675-693
+ * with pzflow/utils.py:52-61): key = PRNGKey(seed) = (0, seed mod 2^32) for data AND conditions, eps of (unit i, sample s,
+ * column j) = element ((i * S + s) * W + j) of jax.random.normal(key, (total_units, S, W)), W = D (the posterior's evaluated
+ * column rides along, flow.py:370-373) or C.  layout 1 = jax's original threefry layout (checked against the values jax's
+ * documentation prints for random.normal), 2 = the partitionable layout (unverified here), 0 = back to the library's Philox
+ * streams.  total_units = rows / galaxies of the caller's WHOLE call (a chunked call passes row_offset as before).  The
+ * normals are sqrt(2) * erf_inv(u) with XLA's float32 erf_inv (Giles' polynomials), so they are jax's own values up to an
+ * ulp of log1pf; the values jax's documentation prints for random.normal are reproduced digit for digit.
+ * pzb_posterior_marg keeps the Philox streams.  pzb_sample_normal_threefry materialises rows [row_offset, row_offset + N) of
+ * jax.random.normal(key, (total_rows, W)): Normal.sample (pzflow/distributions.py:297-303) and gaussian_error_model's eps. */
+int pzb_set_error_stream(int32_t layout, int64_t total_units);
+int pzb_sample_normal_threefry(float *out, int64_t N, int32_t W, uint32_t key0, uint32_t key1, int64_t total_rows,
+                               int64_t row_offset, int32_t partitionable, void *stream);
+
 /* ---- training support (the optional data-parallel training step) ---------
  * The spline of a coupling stage for the loss -mean(w * log_prob) (pzflow/flow.py:961-965): softmax / softplus
  * knot construction, bin search, rational-quadratic spline and log-determinant (pzflow/bijectors.py:488-506,

@@ -13,6 +13,11 @@ of it, what ``jax/_src/prng.py`` and ``jax/_src/random.py`` build from it:
     uniform(key, shape, minval, maxval)
                            -> 23 mantissa bits | 1.0f, minus 1, scaled, clamped below at minval
     permutation(key, n)    -> ceil(3 ln n / ln(2**32 - 1)) rounds of (split, 32 random bits per element, stable sort)
+    normal(key, shape)     -> sqrt(2) * erf_inv(uniform(key, shape, nextafter(-1, 0), 1)); erf_inv is XLA's float32 one:
+                              the two degree-8 polynomials of M. Giles, "Approximating the erfinv function" (2011) in
+                              w = -log1p(-x * x).  Pinned by the values jax's documentation prints ("JAX - The Sharp
+                              Bits": normal(PRNGKey(0), (1,)) = -0.20584226, and -1.2515389 / -0.58665055 for the
+                              sub-keys of its split chain; the PRNG tutorial: normal(PRNGKey(42)) = -0.18471177).
 
 Two stream layouts exist in jax: the ORIGINAL one above (``jax_threefry_partitionable=False``) and the
 "partitionable" one (element i draws threefry(key, (hi32(i), lo32(i))) and xors the two words; split likewise).
@@ -121,3 +126,30 @@ KAT = (
     ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
     ((0x243F6A88, 0x85A308D3), (0x13198A2E, 0x03707344), (0xC4923A9C, 0x483DF7A0)),
 )
+
+
+_GILES_CENTRAL = (2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087, -0.00125372503,
+                  -0.00417768164, 0.246640727, 1.50140941)
+_GILES_TAIL = (-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773, -0.0076224613,
+               0.00943887047, 1.00167406, 2.83297682)
+
+
+def erf_inv32(x: np.ndarray) -> np.ndarray:
+    """XLA's float32 ``erf_inv``: Giles' single-precision approximation, Horner in float32 without contraction."""
+    f32 = np.float32
+    x = np.asarray(x, dtype=f32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = (-np.log1p((-x * x).astype(f32))).astype(f32)
+        central = w < f32(5.0)
+        w = np.where(central, w - f32(2.5), np.sqrt(w) - f32(3.0)).astype(f32)
+        p = np.where(central, f32(_GILES_CENTRAL[0]), f32(_GILES_TAIL[0])).astype(f32)
+        for a, b in zip(_GILES_CENTRAL[1:], _GILES_TAIL[1:]):
+            p = (np.where(central, f32(a), f32(b)) + (p * w).astype(f32)).astype(f32)
+        return (p * x).astype(f32)
+
+
+def normal(key, shape, partitionable: bool = False) -> np.ndarray:
+    """``jax.random.normal(key, shape)`` in float32 (jax/_src/random.py: _normal_real)."""
+    lo = np.nextafter(np.float32(-1.0), np.float32(0.0))
+    u = uniform(key, shape, lo, 1.0, partitionable)
+    return (np.float32(np.sqrt(2.0)) * erf_inv32(u)).astype(np.float32)

@@ -112,6 +112,9 @@ SIGNATURES = {
                                                 C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                                 C.c_void_p]),
     "pzb_set_host_threads": (C.c_int, [C.c_int32]),
+    "pzb_set_error_stream": (C.c_int, [C.c_int32, C.c_int64]),
+    "pzb_sample_normal_threefry": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_uint32, C.c_int64, C.c_int64,
+                                             C.c_int32, C.c_void_p]),
     "pzb_host_digest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pzb_sample_centbeta": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64,
                                       C.c_int64, C.c_void_p]),

@@ -60,6 +60,10 @@ using namespace pzb;
 
 static thread_local std::string g_err = "";
 static thread_local bool g_force_simt = false;  // run_host's fp16 guard: re-evaluate this thread's job on the SIMT engine
+// pzb_set_error_stream: which stream the NEXT error-sample calls of this host thread draw their eps from, and how many
+// units (rows / galaxies) the caller's WHOLE call has (jax's original layout pairs element g with g + n_total / 2)
+static thread_local int g_eps_layout = 0;
+static thread_local long long g_eps_units = 0;
 static std::atomic<long long> g_launches{0};
 
 static int fail(int code, const char* fmt, ...) {
@@ -998,24 +1002,6 @@ sample_uniform_kernel(float* __restrict__ U, long long n, float B, uint64_t seed
   }
 }
 
-// Threefry-2x32, 20 rounds (Salmon et al., SC'11): the block function of jax's default PRNG.
-__device__ __forceinline__ void pz_threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
-  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
-  constexpr int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
-  x0 += ks[0];
-  x1 += ks[1];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      x0 += x1;
-      x1 = __funnelshift_l(x1, x1, R[i & 1][r]) ^ x0;
-    }
-    x0 += ks[(i + 1) % 3];
-    x1 += ks[(i + 2) % 3] + (uint32_t)(i + 1);
-  }
-}
-
 // jax.random.uniform(key, (total_rows, D), minval, maxval) -- elements [e0, e0 + n) of its n_total, in jax's stream
 // layout (pzflow/distributions.py:464-469).  Original layout: the count vector iota(n_total) is cut into two halves
 // that ride through the block function together (element g < h pairs with g + h, a zero pads an odd count); the
@@ -1422,6 +1408,62 @@ int pzb_error_eps(float* eps, int64_t n, int32_t W, int32_t stream_id, uint64_t 
   return PZB_OK;
 }
 
+// Error samples in jax's own stream (pzb_set_error_stream): fills the launch's eps fields, or reports why it cannot.
+static int eps_stream_args(const pzb_plan* plan, LaunchArgs& a, uint64_t seed, int64_t row_offset, int64_t units,
+                           int32_t S, const char* who) {
+  if (g_eps_layout == 0) return PZB_OK;
+  if (g_eps_units < row_offset + units)
+    return fail(PZB_ERR_INVALID, "%s: pzb_set_error_stream announced %lld units, the call covers [%lld, %lld)", who,
+                g_eps_units, (long long)row_offset, (long long)(row_offset + units));
+  const long long widest = std::max(plan->host.D, plan->host.C);
+  if (g_eps_layout == 1 && g_eps_units * (long long)S * widest >= 0xFFFFFFFFLL)
+    return fail(PZB_ERR_UNSUPPORTED, "%s: %lld x %d x %lld draws exceed one threefry call of jax's original layout", who,
+                g_eps_units, S, widest);
+  a.eps_layout = g_eps_layout;
+  a.eps_k0 = 0u;                      // PRNGKey(seed) with x64 disabled: (0, seed mod 2^32)
+  a.eps_k1 = (uint32_t)seed;
+  a.eps_units = g_eps_units;
+  return PZB_OK;
+}
+
+int pzb_set_error_stream(int32_t layout, int64_t total_units) {
+  if (layout < 0 || layout > 2 || total_units < 0) return fail(PZB_ERR_INVALID, "set_error_stream: bad arguments");
+  g_eps_layout = layout;
+  g_eps_units = total_units;
+  return PZB_OK;
+}
+
+// jax.random.normal(key, (total_rows, W)) -- rows [row_offset, row_offset + N) of it -- in jax's stream layout: the
+// Normal latent's draws (pzflow/distributions.py:297-303: multivariate_normal with the identity covariance IS normal)
+// and the default error model's eps (pzflow/utils.py:59) for callers that want them materialised.
+__global__ void __launch_bounds__(256)
+sample_normal_threefry_kernel(float* __restrict__ out, long long n, long long e0, long long n_total, uint32_t k0, uint32_t k1,
+                              int partitionable) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    out[e] = pz_jax_normal(pz_jax_bits(k0, k1, e + e0, n_total, partitionable != 0));
+}
+
+int pzb_sample_normal_threefry(float* out, int64_t N, int32_t W, uint32_t key0, uint32_t key1, int64_t total_rows,
+                               int64_t row_offset, int32_t partitionable, void* stream) {
+  if (N < 0 || W < 1 || row_offset < 0 || total_rows < row_offset + N)
+    return fail(PZB_ERR_INVALID, "sample_normal_threefry: bad shape");
+  if (N == 0) return PZB_OK;
+  if (!out) return fail(PZB_ERR_INVALID, "sample_normal_threefry: NULL buffer");
+  const long long n_total = total_rows * (long long)W;
+  if (!partitionable && n_total >= 0xFFFFFFFFLL)
+    return fail(PZB_ERR_UNSUPPORTED, "sample_normal_threefry: %lld elements exceed one threefry call of jax's original layout",
+                n_total);
+  const long long n = N * (long long)W;
+  long long blocks = (n + 255) / 256;
+  if (blocks > (long long)current_num_sms() * 32) blocks = (long long)current_num_sms() * 32;
+  sample_normal_threefry_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, n, row_offset * (long long)W, n_total,
+                                                                                   key0, key1, partitionable ? 1 : 0);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return cuda_fail(ce, "sample_normal_threefry launch");
+  g_launches.fetch_add(1);
+  return PZB_OK;
+}
+
 int pzb_log_prob_err(const pzb_plan* plan, const float* X, const float* Xerr, const float* cond,
                      const float* cond_err, int64_t N, int32_t err_samples, uint64_t seed, int64_t row_offset,
                      float* out, float* scratch, void* stream) {
@@ -1442,6 +1484,8 @@ int pzb_log_prob_err(const pzb_plan* plan, const float* X, const float* Xerr, co
   a.unit0 = row_offset;
   a.N = N * (int64_t)err_samples;
   a.out0 = scratch;
+  rc = eps_stream_args(plan, a, seed, row_offset, N, err_samples, "log_prob_err");
+  if (rc) return rc;
   if (fused) {  // log(mean_s exp(lp)) taken in shared memory: no [N, S] scratch
     a.fuse = 1;
     a.G = 1;
@@ -1486,6 +1530,8 @@ int pzb_posterior_err(const pzb_plan* plan, const float* rest, const float* rest
   a.unit0 = row_offset;
   a.N = Ng * (int64_t)err_samples * (int64_t)G;
   a.out0 = scratch;
+  rc = eps_stream_args(plan, a, seed, row_offset, Ng, err_samples, "posterior_err");
+  if (rc) return rc;
   if (fused) {
     a.fuse = 1;
     a.normalize = normalize;

@@ -135,6 +135,13 @@ struct LaunchArgs {
   // set to 1 by a tensor-core launch in which some row of finite inputs got non-finite logits (an fp16 overflow of a
   // conditioner pre-activation): the host pipeline's per-chunk guard (pzb_api.cu: run_host); may be null
   unsigned int* ovf_flag;
+  // The error samples in jax's OWN stream (eps_layout 1: jax's original threefry layout, 2: the partitionable one;
+  // 0: this library's Philox streams): eps of (unit i, sample s, column j) is element ((i * S + s) * W + j) of
+  // jax.random.normal(key, (eps_units, S, W)) -- W = D for data (the posterior's evaluated column rides along as in
+  // pzflow/flow.py:370-373), C for conditions; key = (eps_k0, eps_k1); eps_units = units of the WHOLE call.
+  int eps_layout;
+  uint32_t eps_k0, eps_k1;
+  long long eps_units;
 };
 
 // ---- counter-based normals for the error samples: Philox-4x32-10 keyed by the seed, counter =
@@ -162,6 +169,83 @@ __device__ __forceinline__ void pz_philox4(unsigned long long seed, unsigned lon
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
+}
+
+// Threefry-2x32, 20 rounds (Salmon et al., SC'11): the block function of jax's default PRNG.
+__device__ __forceinline__ void pz_threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  constexpr int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  x0 += ks[0];
+  x1 += ks[1];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      x0 += x1;
+      x1 = __funnelshift_l(x1, x1, R[i & 1][r]) ^ x0;
+    }
+    x0 += ks[(i + 1) % 3];
+    x1 += ks[(i + 2) % 3] + (uint32_t)(i + 1);
+  }
+}
+
+// The 32 random bits jax's random_bits gives element g of an array of n_total elements.  Original layout: the count
+// vector iota(n_total) rides through the block function as two halves (g < h pairs with g + h, a zero pads an odd
+// count); partitionable layout: one block per element, (hi32(g), lo32(g)), its two output words xor-ed.
+__device__ __forceinline__ uint32_t pz_jax_bits(uint32_t k0, uint32_t k1, long long g, long long n_total, bool partitionable) {
+  uint32_t x0, x1;
+  if (partitionable) {
+    x0 = (uint32_t)((unsigned long long)g >> 32);
+    x1 = (uint32_t)g;
+    pz_threefry2x32(k0, k1, x0, x1);
+    return x0 ^ x1;
+  }
+  const long long h = (n_total + 1) / 2;
+  if (g < h) {
+    x0 = (uint32_t)g;
+    x1 = (g + h < n_total) ? (uint32_t)(g + h) : 0u;
+    pz_threefry2x32(k0, k1, x0, x1);
+    return x0;
+  }
+  x0 = (uint32_t)(g - h);
+  x1 = (uint32_t)g;
+  pz_threefry2x32(k0, k1, x0, x1);
+  return x1;
+}
+
+// XLA's float32 erf_inv (M. Giles, "Approximating the erfinv function", GPU Computing Gems 2011: two degree-8
+// polynomials in w = -log1p(-x * x), evaluated by Horner without contraction) -- what jax.random.normal runs through.
+__device__ __forceinline__ float pz_xla_erfinv(float x) {
+  float w = -log1pf(__fmul_rn(-x, x));
+  const bool lt = w < 5.0f;
+  w = lt ? __fsub_rn(w, 2.5f) : __fsub_rn(sqrtf(w), 3.0f);
+  float p = lt ? 2.81022636e-08f : -0.000200214257f;
+  p = __fadd_rn(lt ? 3.43273939e-07f : 0.000100950558f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? -3.5233877e-06f : 0.00134934322f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? -4.39150654e-06f : -0.00367342844f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? 0.00021858087f : 0.00573950773f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? -0.00125372503f : -0.0076224613f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? -0.00417768164f : 0.00943887047f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? 0.246640727f : 1.00167406f, __fmul_rn(p, w));
+  p = __fadd_rn(lt ? 1.50140941f : 2.83297682f, __fmul_rn(p, w));
+  return __fmul_rn(p, x);
+}
+
+// jax.random.normal from those bits: u = uniform in (-1, 1) -- 23 mantissa bits | 1.0f, minus 1, times (1 - lo) = 2,
+// plus lo = nextafter(-1, 0), clamped below at lo -- then sqrt(2) * erf_inv(u)  (jax/_src/random.py: _normal_real).
+// With the polynomial above this reproduces the values jax's documentation prints for random.normal digit for digit
+// (tests/test_oracle.py: jax_normal_known_answers); log1pf is CUDA's, within an ulp of XLA's.
+__device__ __forceinline__ float pz_jax_normal(uint32_t bits) {
+  const float lo = -0.99999994f;
+  const float f = __fsub_rn(__uint_as_float((bits >> 9) | 0x3f800000u), 1.0f);
+  const float u = fmaxf(lo, __fadd_rn(__fmul_rn(f, 2.0f), lo));
+  return __fmul_rn(1.4142135623730951f, pz_xla_erfinv(u));
+}
+
+// One error sample in jax's stream.  Not inlined: the chain kernels' input stage only pays a call for it, and only on
+// error-sample launches, so the register allocation of their hot loops stays what it was.
+static __device__ __noinline__ float pz_jax_eps(uint32_t k0, uint32_t k1, long long g, long long n_total, int layout) {
+  return pz_jax_normal(pz_jax_bits(k0, k1, g, n_total, layout == 2));
 }
 
 // eps for (sample index es, column j) of a stream: standard normal, float32
@@ -223,16 +307,26 @@ __device__ __forceinline__ float pz_input_value(const LaunchArgs& a, const RowIn
       if (q < a.n_mcols && a.mcol[q] == j) return a.mvals[r.vs * a.n_mcols + q];  // a marginalised column: no error model
   }
   float v = a.X[r.unit * W + jj];
-  if (a.S > 0 && a.Xerr != nullptr)
-    v = v + pz_err_normal(a.seed, 0u, (unsigned long long)(r.es + a.unit0 * a.S * (a.V > 0 ? a.V : 1)), jj) * a.Xerr[r.unit * W + jj];
+  if (a.S > 0 && a.Xerr != nullptr) {
+    const long long es = r.es + a.unit0 * a.S * (a.V > 0 ? a.V : 1);
+    const float eps = a.eps_layout == 0
+                          ? pz_err_normal(a.seed, 0u, (unsigned long long)es, jj)
+                          : pz_jax_eps(a.eps_k0, a.eps_k1, es * D + j, a.eps_units * a.S * D, a.eps_layout);
+    v = v + eps * a.Xerr[r.unit * W + jj];
+  }
   return v;
 }
 
 __device__ __forceinline__ float pz_cond_value(const LaunchArgs& a, const RowIndex& r, int j, int C) {
   if (a.cond == nullptr) return 0.0f;
   float v = a.cond[r.unit * C + j];
-  if (a.S > 0 && a.cond_err != nullptr)
-    v = v + pz_err_normal(a.seed, 1u, (unsigned long long)(r.es + a.unit0 * a.S * (a.V > 0 ? a.V : 1)), j) * a.cond_err[r.unit * C + j];
+  if (a.S > 0 && a.cond_err != nullptr) {
+    const long long es = r.es + a.unit0 * a.S * (a.V > 0 ? a.V : 1);
+    const float eps = a.eps_layout == 0
+                          ? pz_err_normal(a.seed, 1u, (unsigned long long)es, j)
+                          : pz_jax_eps(a.eps_k0, a.eps_k1, es * C + j, a.eps_units * a.S * C, a.eps_layout);
+    v = v + eps * a.cond_err[r.unit * C + j];
+  }
   return v;
 }
 

@@ -141,7 +141,14 @@ class Normal(LatentDist):
 
     def sample_device(self, nsamples: int, seed: int = None, *, device=None, row_offset: int = 0,
                       total_rows: int = None) -> torch.Tensor:
-        return _plan.sample_normal(nsamples, self.input_dim, _seed(seed), _device(device), row_offset)
+        """Draws on the device.  In the default stream layout these are jax's own numbers: the reference's
+        ``random.multivariate_normal(PRNGKey(seed), 0, I, (nsamples,))`` (pzflow/distributions.py:297-303) is
+        ``random.normal(key, (nsamples, D))`` pushed through the identity Cholesky factor."""
+        total = row_offset + nsamples if total_rows is None else int(total_rows)
+        lay = _prng.layout()
+        if lay == "philox" or (lay == "threefry" and total * self.input_dim > _prng.MAX_THREEFRY_WORDS):
+            return _plan.sample_normal(nsamples, self.input_dim, _seed(seed), _device(device), row_offset)
+        return _plan.sample_normal_jax(nsamples, self.input_dim, _seed(seed), _device(device), row_offset, total, lay)
 
     def sample(self, params: Pytree, nsamples: int, seed: int = None):
         """[nsamples, input_dim] standard normal draws (distributions.py:277-303)."""

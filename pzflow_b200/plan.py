@@ -517,7 +517,7 @@ class Plan:
         out = torch.empty(n, dtype=torch.float32, device=self.device)
         step = max(1, self.ERR_SCRATCH_FLOATS // S)
         scratch = torch.empty(min(n, step) * S, dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _ErrorStream(n, S, max(self.input_dim, self.n_conditions)):
             for r0 in range(0, n, step):
                 m = min(step, n - r0)
                 N.check(N.lib().pzb_log_prob_err(
@@ -540,7 +540,7 @@ class Plan:
         out = torch.empty((Ng, G), dtype=torch.float32, device=self.device)
         step = max(1, self.ERR_SCRATCH_FLOATS // (S * G))
         scratch = torch.empty(min(Ng, step) * S * G, dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _ErrorStream(Ng, S, max(self.input_dim, self.n_conditions)):
             for r0 in range(0, Ng, step):
                 m = min(step, Ng - r0)
                 N.check(N.lib().pzb_posterior_err(
@@ -738,6 +738,34 @@ def normalize_pdfs_(pdfs: torch.Tensor, grid: torch.Tensor, normalize: bool, nan
     return pdfs
 
 
+def _error_stream(total_units: int, S: int, width: int):
+    """Which stream the Gaussian error samples of a call over ``total_units`` rows / galaxies come from: jax's own
+    (``random.normal(PRNGKey(seed), (units, S, W))``, pzflow/utils.py:59) in the layout ``prng.layout()`` names, or --
+    for ``"philox"`` and for calls beyond one threefry call of jax's original layout -- the library's Philox streams.
+    Returns the layout code of pzb_set_error_stream."""
+    from . import prng
+    lay = prng.layout()
+    if lay == "philox" or (lay == "threefry" and total_units * S * max(1, width) > prng.MAX_THREEFRY_WORDS):
+        return 0
+    return 1 if lay == "threefry" else 2
+
+
+class _ErrorStream:
+    """``with _ErrorStream(units, S, W):`` -- the pzb_*_err calls of this host thread inside the block draw their
+    Gaussian error samples from the stream ``_error_stream`` picks; the library's own streams are restored on exit."""
+
+    def __init__(self, total_units: int, S: int, width: int):
+        self.layout, self.units = _error_stream(total_units, S, width), int(total_units)
+
+    def __enter__(self):
+        N.check(N.lib().pzb_set_error_stream(self.layout, self.units))
+        return self
+
+    def __exit__(self, *exc):
+        N.lib().pzb_set_error_stream(0, 0)
+        return False
+
+
 def sample_uniform(n: int, dim: int, B: float, seed: int, device=None, row_offset: int = 0) -> torch.Tensor:
     """U(-B, B)^dim latent draws from the library's Philox stream (not jax's threefry).  ``row_offset``: index of the
     first row in the caller's whole array (a sharded call draws what one big call would)."""
@@ -783,6 +811,23 @@ def sample_normal(n: int, dim: int, seed: int, device=None, row_offset: int = 0)
     out = torch.empty((n, dim), dtype=torch.float32, device=device)
     with torch.cuda.device(device):
         N.check(N.lib().pzb_sample_normal(_ptr(out), n, dim, int(seed) & (2 ** 64 - 1), int(row_offset), _stream(device)))
+    return out
+
+
+def sample_normal_jax(n: int, dim: int, seed, device=None, row_offset: int = 0, total_rows: int = None,
+                      layout: str = None) -> torch.Tensor:
+    """Rows [row_offset, row_offset + n) of ``jax.random.normal(PRNGKey(seed), (total_rows, dim))``, generated on the
+    device in jax's own threefry stream (pzb_sample_normal_threefry): the Normal latent's draws
+    (pzflow/distributions.py:297-303) and the eps of the default error model (pzflow/utils.py:59)."""
+    from . import prng
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    total_rows = row_offset + n if total_rows is None else int(total_rows)
+    key = prng.key_from_seed(seed)
+    out = torch.empty((n, dim), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        N.check(N.lib().pzb_sample_normal_threefry(_ptr(out), n, dim, int(key[0]), int(key[1]), total_rows, int(row_offset),
+                                                   int((layout or prng.layout()) == "threefry_partitionable"),
+                                                   _stream(device)))
     return out
 
 

@@ -17,20 +17,25 @@ def build_bijector_from_info(info: tuple) -> tuple:
 
 def gaussian_error_model(key, X, Xerr, nsamples):
     """Default Gaussian error model (pzflow/utils.py:52-61): X[:, None, :] + eps * Xerr[:, None, :],
-    eps ~ N(0, 1) of shape [N, nsamples, D].  ``key`` is the integer seed here (the reference passes a
-    jax PRNGKey); the draws are the library's counter-based stream (pzflow_b200.plan.error_eps), the same
-    ones the fused kernels generate on the fly -- Flow.log_prob / posterior never call this function, they
-    only check that the flow's error model IS this one and let the kernel do the expansion."""
+    eps ~ N(0, 1) of shape [N, nsamples, D].  ``key``: an int seed or the uint32 pair jax.random.PRNGKey(seed) would be.
+    In the default stream layout (pzflow_b200.prng) eps IS ``jax.random.normal(key, (N, nsamples, D))``, generated on
+    the GPU; under the "philox" layout it is the library's counter-based stream (pzflow_b200.plan.error_eps).  Either
+    way these are the draws the fused kernels generate on the fly -- Flow.log_prob / posterior never call this
+    function, they only check that the flow's error model IS this one and let the kernel do the expansion."""
     import numpy as np
-    import torch
 
-    from .plan import error_eps
+    from . import prng
+    from .plan import _error_stream, error_eps, sample_normal_jax
     X = np.asarray(X, dtype=np.float32)
     Xerr = np.asarray(Xerr, dtype=np.float32)
     k = np.asarray(key).astype(np.uint64).ravel()   # an int seed, or the uint32 pair PRNGKey(seed) would be
-    seed = int(k[0]) if k.size == 1 else (int(k[0]) << 32) | int(k[1])
-    eps = error_eps(X.shape[0] * int(nsamples), X.shape[1], 0, seed).cpu().numpy()
-    eps = eps.reshape(X.shape[0], int(nsamples), X.shape[1])
+    n, S, W = X.shape[0], int(nsamples), X.shape[1]
+    if _error_stream(n, S, W):
+        eps = sample_normal_jax(n * S, W, prng.key_from_seed(np.asarray(key, dtype=np.uint32)) if k.size == 2 else int(k[0]))
+    else:
+        seed = int(k[0]) if k.size == 1 else (int(k[0]) << 32) | int(k[1])
+        eps = error_eps(n * S, W, 0, seed)
+    eps = eps.cpu().numpy().reshape(n, S, W)
     return X[:, None, :] + eps * Xerr[:, None, :]
 
 

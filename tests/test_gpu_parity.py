@@ -989,8 +989,101 @@ def _expand(X, Xerr, eps, S):
     return (X[:, None, :] + eps.reshape(n, S, w) * Xerr[:, None, :]).reshape(n * S, w).astype(np.float32)
 
 
+def _jax_eps(n, S, W, seed, skip=None):
+    """The eps the reference's default error model draws (pzflow/utils.py:59 under flow.py:455-457):
+    jax.random.normal(PRNGKey(seed), (n, S, W)) restated by the oracle -> [n * S, W] (``skip``: the posterior's evaluated
+    column rides along in the draw and is deleted afterwards, flow.py:370-384)."""
+    from oracle import jax_prng as J
+    eps = J.normal(J.PRNGKey(seed), (n, S, W))
+    if skip is not None:
+        eps = np.delete(eps, skip, axis=2)
+    return np.ascontiguousarray(eps.reshape(n * S, -1))
+
+
+@pytest.fixture
+def philox_streams():
+    from pzflow_b200 import prng
+    was = prng.layout()
+    prng.set_layout("philox")
+    yield
+    prng.set_layout(was)
+
+
+def test_error_samples_are_jax_random_normal():
+    """The default stream of the in-kernel error samples IS jax.random.normal(PRNGKey(seed), (N, S, W)): the
+    materialised form (pzb_sample_normal_threefry == the oracle's restatement, which prints jax's documented values),
+    then Flow.log_prob(err_samples=S) == the oracle fed those eps -- on every engine, for data and conditions, cut
+    into launches or not."""
+    from oracle import jax_prng as J
+    from pzflow_b200.plan import sample_normal_jax
+    from pzflow_b200.utils import gaussian_error_model
+    assert float(sample_normal_jax(1, 1, 0)[0, 0]) == np.float32(-0.20584226)       # "JAX - The Sharp Bits"
+    assert float(sample_normal_jax(1, 1, 42)[0, 0]) == np.float32(-0.18471177)      # jax's PRNG tutorial
+    for n, w, seed in [(1, 1, 0), (1001, 7, 5), (4096, 3, 2 ** 40 + 17), (333, 2, 9)]:
+        want = J.normal(J.PRNGKey(seed), (n, w))
+        got = _np(sample_normal_jax(n, w, seed))
+        ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+        assert (ulp <= 4).all() and (ulp == 0).mean() > 0.95, (n, w, ulp.max(), (ulp == 0).mean())   # log1pf vs np.log1p
+        lo, hi = n // 3, n // 3 + max(1, n // 2)                                     # a row block of the same call
+        np.testing.assert_array_equal(_np(sample_normal_jax(hi - lo, w, seed, row_offset=lo, total_rows=n)), got[lo:hi])
+        part = _np(sample_normal_jax(n, w, seed, layout="threefry_partitionable"))
+        wantp = J.normal(J.PRNGKey(seed), (n, w), partitionable=True)
+        assert np.abs(part - wantp).max() < 1e-6
+    X = np.arange(12, dtype=np.float32).reshape(4, 3)
+    g = gaussian_error_model(np.array([0, 3], np.uint32), X, np.full_like(X, 0.5), 5)
+    np.testing.assert_allclose(g, X[:, None, :] + 0.5 * J.normal(J.PRNGKey(3), (4, 5, 3)), rtol=0, atol=1e-6)
+    ex = F.example_flow()
+    rng = np.random.default_rng(8)
+    n, S, seed = 700, 6, 31
+    X = F.galaxy_rows(n, seed=24, oob_frac=0)
+    Xerr = rng.uniform(0.0, 0.05, size=X.shape).astype(np.float32)
+    rows = _expand(X, Xerr, _jax_eps(n, S, 7, seed), S)
+    bi, li, p64 = _o64(ex)
+    with np.errstate(all="ignore"):
+        lp32 = O.flow_log_prob(ex["bijector_info"], ex["latent_info"], ex["params"], rows)
+        lp64 = O.flow_log_prob(bi, li, p64, rows.astype(np.float64))
+        o32 = np.log(np.exp(lp32.reshape(n, S)).mean(axis=1, dtype=np.float32))
+        o64 = np.log(np.exp(lp64.reshape(n, S)).mean(axis=1))
+    for engine in ENGINES + ["wide"]:
+        plan = _plan(ex, engine)
+        got = plan.log_prob_err(X, Xerr, None, None, S, seed)
+        assert_noise_floor(f"C2 log_prob, jax-stream err_samples [{engine}]", _np(got), o32, o64, ratio=2.0, slack=5e-6,
+                           below=LP_UNDERFLOW)
+        plan.ERR_SCRATCH_FLOATS = 1024
+        try:
+            assert _same_bits(plan.log_prob_err(X, Xerr, None, None, S, seed), got)
+        finally:
+            del plan.ERR_SCRATCH_FLOATS
+    # the posterior: the evaluated column rides along in the draw (W = 7), conditions use the same key with W = C
+    ng, G = 30, 40
+    rest, rest_err = np.ascontiguousarray(X[:ng, 1:]), np.ascontiguousarray(Xerr[:ng, 1:])
+    grid = np.linspace(0.0, 2.3, G).astype(np.float32)
+    samples = _expand(rest, rest_err, _jax_eps(ng, S, 7, seed, skip=0), S)
+    un = O.flow_posterior(ex["bijector_info"], ex["latent_info"], ex["params"], samples, 0, grid, normalize=False,
+                          nan_to_zero=False)
+    want = un.reshape(ng, S, G).mean(axis=1)
+    want = want / O.trapezoid(want, grid)[:, None]
+    for engine in ENGINES + ["wide"]:
+        got = _np(_plan(ex, engine).posterior_err(rest, rest_err, 0, grid, None, None, S, seed))
+        np.testing.assert_allclose(got, want, rtol=2e-3, atol=2e-4)
+    cfg = F.config_c4(1)[0]
+    mins, maxs = ex["bijector_info"][1][0][1][0], ex["bijector_info"][1][0][1][1]
+    n2 = 400
+    Xc = rng.uniform(mins, maxs, size=(n2, 7)).astype(np.float32)
+    cond, cerr = rng.normal(size=(n2, 2)).astype(np.float32), rng.uniform(0, 0.1, size=(n2, 2)).astype(np.float32)
+    xerr = rng.uniform(0, 0.02, size=(n2, 7)).astype(np.float32)
+    with np.errstate(all="ignore"):
+        lp = O.flow_log_prob(cfg["bijector_info"], cfg["latent_info"], cfg["params"],
+                             _expand(Xc, xerr, _jax_eps(n2, S, 7, seed), S), _expand(cond, cerr, _jax_eps(n2, S, 2, seed), S))
+        want = np.log(np.exp(lp.reshape(n2, S)).mean(axis=1, dtype=np.float32))
+    ok = want > LP_UNDERFLOW
+    for engine in ENGINES + ["wide"]:
+        got = _np(_plan(cfg, engine).log_prob_err(Xc, xerr, cond, cerr, S, seed))
+        assert within_tol(got[ok], want[ok]).mean() > 0.98, engine
+
+
 @pytest.mark.parametrize("engine", ENGINES)
-def test_err_samples_log_prob_matches_oracle(engine):
+def test_err_samples_log_prob_matches_oracle(engine, philox_streams):
     from pzflow_b200.plan import error_eps
     ex = F.example_flow()
     plan = _plan(ex, engine)
@@ -1023,7 +1116,7 @@ def test_err_samples_log_prob_matches_oracle(engine):
     assert not np.array_equal(got, _np(plan.log_prob_err(X, Xerr, None, None, S, seed + 1)))
 
 
-def test_err_samples_posterior_and_conditions():
+def test_err_samples_posterior_and_conditions(philox_streams):
     from pzflow_b200.plan import error_eps
     ex = F.example_flow()
     plan = _plan(ex, "tc")

@@ -264,6 +264,30 @@ def test_threefry_known_answers():
     np.testing.assert_array_equal(J.split(J.PRNGKey(0)), [[4146024105, 967050713], [2718843009, 1272950319]])
 
 
+def test_jax_normal_known_answers():
+    """``jax.random.normal`` restated (threefry bits -> uniform on (-1, 1) -> XLA's float32 erf_inv): the values jax's
+    own documentation prints -- "JAX - The Sharp Bits" (PRNGKey(0) and the sub-keys of its split chain) and the PRNG
+    tutorial (PRNGKey(42)) -- digit for digit.  This is the stream of the default error model's eps
+    (pzflow/utils.py:59) and of the Normal latent's draws (pzflow/distributions.py:297-303)."""
+    from oracle import jax_prng as J
+    k0 = J.PRNGKey(0)
+    assert J.normal(k0, (1,))[0] == np.float32(-0.20584226)
+    key, sub = J.split(k0)
+    assert J.normal(sub, (1,))[0] == np.float32(-1.2515389)
+    key, sub = J.split(key)
+    np.testing.assert_array_equal(sub, [1278412471, 2182328957])
+    assert J.normal(sub, (1,))[0] == np.float32(-0.58665055)
+    assert J.normal(J.PRNGKey(42), ())[()] == np.float32(-0.18471177)
+    # the polynomial against the exact function, over the whole open interval and in the tails
+    from scipy.special import erfinv
+    x = np.concatenate([np.linspace(-0.9999999, 0.9999999, 20001), [np.nextafter(np.float32(-1), np.float32(0))]]).astype(np.float32)
+    got, ref = J.erf_inv32(x), erfinv(x.astype(np.float64))
+    assert np.abs(got / np.where(ref == 0, 1, ref) - 1)[ref != 0].max() < 5e-6
+    big = J.normal(J.PRNGKey(7), (200000, 3))
+    assert abs(big.mean()) < 0.005 and abs(big.std() - 1) < 0.005 and abs((big ** 3).mean()) < 0.02
+    assert abs((big ** 4).mean() - 3) < 0.05
+
+
 def test_notebook_samples_from_the_seed():
     """docs/tutorials/marginalization.ipynb:69, 133-135: ``flow.sample(2, seed=0)`` of the shipped flow, printed by the
     real JAX reference.  Drawing the latents of seed 0 in jax's original threefry layout and pushing them through the
