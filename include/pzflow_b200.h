@@ -241,9 +241,10 @@ int pzb_sample_uniform(float *U, int64_t N, int32_t D, float B, uint64_t seed, i
 /* Uniform.sample (pzflow/distributions.py:464-469) in jax's OWN random stream: rows [row_offset, row_offset + N) of
  * jax.random.uniform(key, shape=(total_rows, D), minval, maxval), key = (key0, key1) -- PRNGKey(seed) with x64
  * disabled is (0, seed mod 2^32).  Threefry-2x32/20 in the layout of jax's default PRNG implementation: the count
- * vector iota(total_rows * D) rides through the block function as two halves (partitionable = 0; this layout
+ * vector iota(total_rows * D) rides through the block function as two halves (partitionable = 0: jax < 0.5's default;
  * reproduces the samples printed from real JAX at docs/tutorials/marginalization.ipynb:133-135), or one block per
- * element with its two words xor-ed (partitionable = 1, jax_threefry_partitionable=True; unverified here).  total_rows
+ * element with its two words xor-ed (partitionable = 1: jax_threefry_partitionable=True, the default of the jax >= 0.5.3
+ * the reference requires; reproduces random.uniform(key(0)) = 0.947667 of jax's documentation).  total_rows
  * is needed because the original layout pairs element g with g + ceil(total / 2).  A request of 2^32 - 1 words or more
  * in the original layout returns PZB_ERR_UNSUPPORTED (jax cuts those into separately keyed blocks). */
 int pzb_sample_uniform_threefry(float *U, int64_t N, int32_t D, float minval, float maxval, uint32_t key0, uint32_t key1,
@@ -324,9 +325,9 @@ int pzb_error_eps(float *eps, int64_t n, int32_t W, int32_t stream_id, uint64_t 
  * pzb_posterior_err calls of this host thread to draw eps as the reference does (pzflow/flow.py:455-464, 552-553, 675-693
  * with pzflow/utils.py:52-61): key = PRNGKey(seed) = (0, seed mod 2^32) for data AND conditions, eps of (unit i, sample s,
  * column j) = element ((i * S + s) * W + j) of jax.random.normal(key, (total_units, S, W)), W = D (the posterior's evaluated
- * column rides along, flow.py:370-373) or C.  layout 1 = jax's original threefry layout (checked against the values jax's
- * documentation prints for random.normal), 2 = the partitionable layout (unverified here), 0 = back to the library's Philox
- * streams.  total_units = rows / galaxies of the caller's WHOLE call (a chunked call passes row_offset as before).  The
+ * column rides along, flow.py:370-373) or C.  layout 1 = jax's original threefry layout, 2 = the partitionable layout (jax >=
+ * 0.5's default) -- each checked against the values jax's documentation prints for random.normal --, 0 = back to the
+ * library's Philox streams.  total_units = rows / galaxies of the caller's WHOLE call (a chunked call passes row_offset as before).  The
  * normals are sqrt(2) * erf_inv(u) with XLA's float32 erf_inv (Giles' polynomials), so they are jax's own values up to an
  * ulp of log1pf; the values jax's documentation prints for random.normal are reproduced digit for digit.
  * pzb_posterior_marg keeps the Philox streams.  pzb_sample_normal_threefry materialises rows [row_offset, row_offset + N) of

@@ -19,13 +19,17 @@ of it, what ``jax/_src/prng.py`` and ``jax/_src/random.py`` build from it:
                               Bits": normal(PRNGKey(0), (1,)) = -0.20584226, and -1.2515389 / -0.58665055 for the
                               sub-keys of its split chain; the PRNG tutorial: normal(PRNGKey(42)) = -0.18471177).
 
-Two stream layouts exist in jax: the ORIGINAL one above (``jax_threefry_partitionable=False``) and the
-"partitionable" one (element i draws threefry(key, (hi32(i), lo32(i))) and xors the two words; split likewise).
-**Pin:** ``uniform(PRNGKey(0), (2, 7), -5, 5)`` in the original layout, pushed through the shipped flow's inverse,
-reproduces the two samples the real JAX reference printed at docs/tutorials/marginalization.ipynb:133-135
-(``flow.sample(2, seed=0)``) to the six digits printed -- so the original layout is what produced the only
-JAX-made numbers in the reference tree, and it is the default here.  The partitionable layout is restated from
-memory of jax 0.5's source and has no anchor in the tree: it is marked UNVERIFIED wherever it is offered.
+Two stream layouts exist in jax: the ORIGINAL one above (``jax_threefry_partitionable=False``, the default before
+jax 0.5.0) and the "partitionable" one (element i draws threefry(key, (hi32(i), lo32(i))) and xors the two words; split
+keeps both words of block i) -- the default from jax 0.5.0 on, hence of the jax the reference requires
+(pyproject.toml:13, ``jax >= 0.5.3``).
+**Pins, original layout:** ``uniform(PRNGKey(0), (2, 7), -5, 5)`` pushed through the shipped flow's inverse reproduces
+the two samples the real JAX reference printed at docs/tutorials/marginalization.ipynb:133-135
+(``flow.sample(2, seed=0)``, made with an older jax) to the six digits printed; ``split(PRNGKey(0))`` and
+``normal`` of PRNGKey(0) / PRNGKey(42) and of the sub-keys of the split chains are the values older jax documentation
+prints.  **Pins, partitionable layout:** the values current jax documentation prints -- ``normal(key(42))`` =
+-0.028304616 and the draws 0.60576403 / -0.21089035 / -0.39489815 of its split loop, ``uniform(key(0))`` = 0.947667,
+``normal(key(0), (1,))`` = 1.6226422.  All of them are asserted in tests/test_oracle.py.
 
 Only tests/, oracle/make_golden_shim.py and oracle/jax_shim may import this module.
 """

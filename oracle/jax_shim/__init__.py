@@ -162,21 +162,25 @@ def _make_jnp() -> types.ModuleType:
 # --------------------------------------------------------------------------- #
 def _make_random(prng: str = "numpy") -> types.ModuleType:
     rnd = types.ModuleType("jax.random")
-    if prng == "threefry":
-        # jax's own streams (oracle/jax_prng.py: Threefry-2x32/20 in the original layout, pinned by the samples real JAX
-        # printed in docs/tutorials/marginalization.ipynb) for keys, split, uniform and permutation; normal / beta keep
-        # NumPy generators seeded by the key words (their jax algorithms -- erf_inv, the gamma rejection loop -- are not
-        # restated), so only Uniform latents, key schedules and Shuffle are stream-exact in this mode.
+    if prng in ("threefry", "threefry_partitionable"):
+        # jax's own streams (oracle/jax_prng.py: Threefry-2x32/20) for keys, split, uniform and permutation, in the
+        # ORIGINAL layout ("threefry": jax < 0.5's default, pinned by the samples real JAX printed in
+        # docs/tutorials/marginalization.ipynb) or the PARTITIONABLE one ("threefry_partitionable": the default of the
+        # jax >= 0.5 the reference requires, pyproject.toml:13; pinned by the values jax's documentation prints);
+        # normal / beta keep NumPy generators seeded by the key words here (random.normal IS restated since --
+        # oracle/jax_prng.normal -- but the goldens cut in these modes only use it for initial weights, which they
+        # store), so Uniform latents, key schedules and Shuffle are what is stream-exact in these modes.
         from .. import jax_prng as J
+        part = prng == "threefry_partitionable"
 
         def _g(key):
             return np.random.default_rng([int(v) for v in np.asarray(key).ravel()])
 
         rnd.PRNGKey = J.PRNGKey
-        rnd.split = lambda key, num=2: J.split(np.asarray(key), num)
+        rnd.split = lambda key, num=2: J.split(np.asarray(key), num, part)
         rnd.uniform = lambda key, shape=(), dtype=np.float32, minval=0.0, maxval=1.0: _out(
-            J.uniform(np.asarray(key), tuple(shape), minval, maxval))
-        rnd.permutation = lambda key, x: _out(np.asarray(x)[J.permutation(np.asarray(key), len(np.asarray(x)))])
+            J.uniform(np.asarray(key), tuple(shape), minval, maxval, part))
+        rnd.permutation = lambda key, x: _out(np.asarray(x)[J.permutation(np.asarray(key), len(np.asarray(x)), part)])
         rnd.normal = lambda key, shape=(), dtype=np.float32: _out(_g(key).standard_normal(size=shape).astype(_F32))
         rnd.beta = lambda key, a, b, shape=None, dtype=np.float32: _out(_g(key).beta(a, b, size=shape).astype(_F32))
         rnd.multivariate_normal = lambda key, mean, cov, shape=None: _out(
@@ -336,8 +340,8 @@ def _make_stax(rnd, nn):
 
 def install(reference_root: str = REFERENCE_ROOT, prng: str = "numpy"):
     """Register the stand-in modules and make the reference importable. Returns ``pzflow``.
-    prng: "numpy" (the streams every round-1/2 golden was cut with) or "threefry" (jax's own key schedule and uniform
-    stream, see _make_random)."""
+    prng: "numpy" (the streams every round-1/2 golden was cut with), or "threefry" / "threefry_partitionable" (jax's own
+    key schedule and uniform stream in the original / partitionable layout, see _make_random)."""
     if "jax" in sys.modules and not getattr(sys.modules["jax"], "__pzb_shim__", False):
         raise RuntimeError("a real jax is already imported; use it instead of the shim")
     jax = types.ModuleType("jax")

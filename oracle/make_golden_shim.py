@@ -301,8 +301,9 @@ def case_ensemble_sample(pzflow):
     _save("ensemble_sample", store)
 
 
-def case_jax_streams(pzflow):
-    """Round 2 (second session), stand-in installed with prng="threefry" (jax's own key schedule and uniform stream, oracle/jax_prng.py):
+def case_jax_streams(pzflow, name="jax_streams"):
+    """Round 2 (second session), stand-in installed with prng="threefry" (-> ref_shim_jax_streams.npz) or
+    "threefry_partitionable" (-> ref_shim_jax_streams_part.npz): jax's own key schedule and uniform stream, oracle/jax_prng.py:
     the reference's Flow.sample for seeds (pzflow/flow.py:783-795 -> distributions.py:464-469), and flows whose chains
     hold Shuffle stages (bijectors.py:780-814; permutation from the key Chain.init_fun hands down, 146-149) and a
     UniformDequantizer (865-911), built with two seeds and re-built from a save dictionary (flow.py:186-187: PRNGKey(0))."""
@@ -368,13 +369,16 @@ def case_jax_streams(pzflow):
         store[f"cens_{tag}_index"] = out.index.to_numpy()
         store[f"cens_{tag}_args"] = np.array([ns, seed, len(frame)])
     np.array_split = _split
-    _save("jax_streams", store)
+    _save(name, store)
 
 
 def main():
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "jax_streams":
         case_jax_streams(jax_shim.install(prng="threefry"))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "jax_streams_part":
+        case_jax_streams(jax_shim.install(prng="threefry_partitionable"), "jax_streams_part")
         return
     pzflow = jax_shim.install()
     if len(sys.argv) > 1 and sys.argv[1] == "round2":

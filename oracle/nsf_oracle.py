@@ -333,20 +333,21 @@ def uniform_dequantizer(inputs, column_idx, inverse):
     return out, np.zeros(inputs.shape[0], dtype=inputs.dtype)
 
 
-def resolve_shuffles(info, key, input_dim):
+def resolve_shuffles(info, key, input_dim, partitionable=False):
     """Give every ("Shuffle", ()) of ``info`` the permutation the reference draws for it: Chain.init_fun splits its key
     once per stage (bijectors.py:146-149), Shuffle.init_fun calls random.permutation(rng, arange(input_dim)) (795-797).
-    key: jax-style uint32 pair (oracle.jax_prng.PRNGKey(seed); PRNGKey(0) for a flow loaded from a file, flow.py:186-187)."""
+    key: jax-style uint32 pair (oracle.jax_prng.PRNGKey(seed); PRNGKey(0) for a flow loaded from a file, flow.py:186-187);
+    partitionable: jax's stream layout (oracle/jax_prng.py)."""
     from . import jax_prng as J
     name, args = info
     if name == "Shuffle":
-        return info if len(args) == 1 else ("Shuffle", (tuple(int(v) for v in J.permutation(key, input_dim)),))
+        return info if len(args) == 1 else ("Shuffle", (tuple(int(v) for v in J.permutation(key, input_dim, partitionable)),))
     if name != "Chain":
         return info
     out = []
     for sub in args:
-        key, layer = J.split(key)
-        out.append(resolve_shuffles(sub, layer, input_dim))
+        key, layer = J.split(key, 2, partitionable)
+        out.append(resolve_shuffles(sub, layer, input_dim, partitionable))
     return ("Chain", tuple(out))
 
 

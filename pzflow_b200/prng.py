@@ -7,14 +7,22 @@ stream layout of jax's default PRNG implementation.  The bulk draws run on the G
 csrc/pzb_api.cu); this module only derives keys and the handful of words a ``Chain`` needs when it is built
 (pzflow/bijectors.py:146-149: ``rng, layer_rng = random.split(rng)`` per stage; 795-797: Shuffle's permutation).
 
-Layouts: ``"threefry"`` is jax's original layout (``jax_threefry_partitionable=False``).  It reproduces the samples
-the reference's authors printed from real JAX in docs/tutorials/marginalization.ipynb:133-135 (``flow.sample(2,
-seed=0)`` of the shipped flow) digit for digit, and ``split(PRNGKey(0))`` equals the value quoted in jax's
-documentation -- it is the default.  ``"threefry_partitionable"`` is the layout jax releases from 0.5.0 on default to
-(``jax_threefry_partitionable=True``), i.e. what the reference draws under its pinned jax 0.5.3 unless that flag is
-turned off; nothing in the reference tree was produced with it and jax is not installable here, so it is offered
-UNVERIFIED (``PZFLOW_B200_PRNG=threefry_partitionable`` or ``set_layout``) and the verified layout stays the default.  ``"philox"`` keeps round 1's
-Philox-4x32-10 streams (not jax-compatible; any size).
+Layouts (both pinned by numbers real JAX produced, tests/test_oracle.py):
+
+``"threefry_partitionable"`` -- the DEFAULT -- is what ``jax_threefry_partitionable=True`` draws, the default of every
+jax release from 0.5.0 on, i.e. of the jax the reference requires (pyproject.toml:13: ``jax >= 0.5.3``): element i of a
+draw is threefry(key, (hi32(i), lo32(i))) with its two words xor-ed, ``split`` keeps both words.  Pinned by the values
+current jax documentation prints (``random.normal(key(42))`` = -0.028304616 and the three draws of its split loop,
+``random.uniform(key(0))`` = 0.947667, ``random.normal(key(0), (1,))`` = 1.6226422).
+
+``"threefry"`` is jax's original layout (``jax_threefry_partitionable=False``, the default before 0.5.0): the count vector
+rides through the block function as two halves.  It reproduces the samples the reference's authors printed in
+docs/tutorials/marginalization.ipynb:133-135 (``flow.sample(2, seed=0)`` of the shipped flow, made with an older jax)
+digit for digit, and the values older jax documentation prints (``split(PRNGKey(0))``, ``random.normal`` of PRNGKey(0)
+/ PRNGKey(42)).  Select it with ``PZFLOW_B200_PRNG=threefry`` or ``set_layout("threefry")`` to re-draw what a pre-0.5
+jax drew (one call of it holds at most 2**32 - 2 words; larger draws fall back to the Philox streams).
+
+``"philox"`` keeps round 1's Philox-4x32-10 streams (not jax-compatible; any size).
 """
 from __future__ import annotations
 
@@ -25,7 +33,7 @@ import numpy as np
 _U32 = np.uint32
 _ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
 LAYOUTS = ("threefry", "threefry_partitionable", "philox")
-_layout = os.environ.get("PZFLOW_B200_PRNG", "threefry")
+_layout = os.environ.get("PZFLOW_B200_PRNG", "threefry_partitionable")
 if _layout not in LAYOUTS:
     raise ValueError(f"PZFLOW_B200_PRNG must be one of {LAYOUTS}")
 # words of one original-layout call: jax cuts larger requests into separately keyed blocks, which is not reproduced

@@ -989,12 +989,12 @@ def _expand(X, Xerr, eps, S):
     return (X[:, None, :] + eps.reshape(n, S, w) * Xerr[:, None, :]).reshape(n * S, w).astype(np.float32)
 
 
-def _jax_eps(n, S, W, seed, skip=None):
+def _jax_eps(n, S, W, seed, skip=None, part=False):
     """The eps the reference's default error model draws (pzflow/utils.py:59 under flow.py:455-457):
     jax.random.normal(PRNGKey(seed), (n, S, W)) restated by the oracle -> [n * S, W] (``skip``: the posterior's evaluated
     column rides along in the draw and is deleted afterwards, flow.py:370-384)."""
     from oracle import jax_prng as J
-    eps = J.normal(J.PRNGKey(seed), (n, S, W))
+    eps = J.normal(J.PRNGKey(seed), (n, S, W), part)
     if skip is not None:
         eps = np.delete(eps, skip, axis=2)
     return np.ascontiguousarray(eps.reshape(n * S, -1))
@@ -1009,35 +1009,40 @@ def philox_streams():
     prng.set_layout(was)
 
 
-def test_error_samples_are_jax_random_normal():
+def test_error_samples_are_jax_random_normal(stream_layout):
     """The default stream of the in-kernel error samples IS jax.random.normal(PRNGKey(seed), (N, S, W)): the
     materialised form (pzb_sample_normal_threefry == the oracle's restatement, which prints jax's documented values),
     then Flow.log_prob(err_samples=S) == the oracle fed those eps -- on every engine, for data and conditions, cut
     into launches or not."""
     from oracle import jax_prng as J
+    from pzflow_b200 import distributions as Dn
     from pzflow_b200.plan import sample_normal_jax
     from pzflow_b200.utils import gaussian_error_model
-    assert float(sample_normal_jax(1, 1, 0)[0, 0]) == np.float32(-0.20584226)       # "JAX - The Sharp Bits"
-    assert float(sample_normal_jax(1, 1, 42)[0, 0]) == np.float32(-0.18471177)      # jax's PRNG tutorial
+    part = stream_layout == "threefry_partitionable"
+    # "JAX - The Sharp Bits" and the PRNG tutorial of jax's documentation, before and after jax 0.5 switched layouts
+    assert float(sample_normal_jax(1, 1, 0, layout="threefry")[0, 0]) == np.float32(-0.20584226)
+    assert float(sample_normal_jax(1, 1, 42, layout="threefry")[0, 0]) == np.float32(-0.18471177)
+    assert float(sample_normal_jax(1, 1, 0, layout="threefry_partitionable")[0, 0]) == np.float32(1.6226422)
+    assert float(sample_normal_jax(1, 1, 42, layout="threefry_partitionable")[0, 0]) == np.float32(-0.028304616)
     for n, w, seed in [(1, 1, 0), (1001, 7, 5), (4096, 3, 2 ** 40 + 17), (333, 2, 9)]:
-        want = J.normal(J.PRNGKey(seed), (n, w))
+        want = J.normal(J.PRNGKey(seed), (n, w), part)
         got = _np(sample_normal_jax(n, w, seed))
         ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
         assert (ulp <= 4).all() and (ulp == 0).mean() > 0.95, (n, w, ulp.max(), (ulp == 0).mean())   # log1pf vs np.log1p
         lo, hi = n // 3, n // 3 + max(1, n // 2)                                     # a row block of the same call
         np.testing.assert_array_equal(_np(sample_normal_jax(hi - lo, w, seed, row_offset=lo, total_rows=n)), got[lo:hi])
-        part = _np(sample_normal_jax(n, w, seed, layout="threefry_partitionable"))
-        wantp = J.normal(J.PRNGKey(seed), (n, w), partitionable=True)
-        assert np.abs(part - wantp).max() < 1e-6
+        other = _np(sample_normal_jax(n, w, seed, layout="threefry" if part else "threefry_partitionable"))
+        assert np.abs(other - J.normal(J.PRNGKey(seed), (n, w), not part)).max() < 1e-6
+        assert _np(Dn.Normal(w).sample_device(n, seed)).tobytes() == got.tobytes()   # the Normal latent draws this stream
     X = np.arange(12, dtype=np.float32).reshape(4, 3)
     g = gaussian_error_model(np.array([0, 3], np.uint32), X, np.full_like(X, 0.5), 5)
-    np.testing.assert_allclose(g, X[:, None, :] + 0.5 * J.normal(J.PRNGKey(3), (4, 5, 3)), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(g, X[:, None, :] + 0.5 * J.normal(J.PRNGKey(3), (4, 5, 3), part), rtol=0, atol=1e-6)
     ex = F.example_flow()
     rng = np.random.default_rng(8)
     n, S, seed = 700, 6, 31
     X = F.galaxy_rows(n, seed=24, oob_frac=0)
     Xerr = rng.uniform(0.0, 0.05, size=X.shape).astype(np.float32)
-    rows = _expand(X, Xerr, _jax_eps(n, S, 7, seed), S)
+    rows = _expand(X, Xerr, _jax_eps(n, S, 7, seed, part=part), S)
     bi, li, p64 = _o64(ex)
     with np.errstate(all="ignore"):
         lp32 = O.flow_log_prob(ex["bijector_info"], ex["latent_info"], ex["params"], rows)
@@ -1058,7 +1063,7 @@ def test_error_samples_are_jax_random_normal():
     ng, G = 30, 40
     rest, rest_err = np.ascontiguousarray(X[:ng, 1:]), np.ascontiguousarray(Xerr[:ng, 1:])
     grid = np.linspace(0.0, 2.3, G).astype(np.float32)
-    samples = _expand(rest, rest_err, _jax_eps(ng, S, 7, seed, skip=0), S)
+    samples = _expand(rest, rest_err, _jax_eps(ng, S, 7, seed, skip=0, part=part), S)
     un = O.flow_posterior(ex["bijector_info"], ex["latent_info"], ex["params"], samples, 0, grid, normalize=False,
                           nan_to_zero=False)
     want = un.reshape(ng, S, G).mean(axis=1)
@@ -1074,7 +1079,7 @@ def test_error_samples_are_jax_random_normal():
     xerr = rng.uniform(0, 0.02, size=(n2, 7)).astype(np.float32)
     with np.errstate(all="ignore"):
         lp = O.flow_log_prob(cfg["bijector_info"], cfg["latent_info"], cfg["params"],
-                             _expand(Xc, xerr, _jax_eps(n2, S, 7, seed), S), _expand(cond, cerr, _jax_eps(n2, S, 2, seed), S))
+                             _expand(Xc, xerr, _jax_eps(n2, S, 7, seed, part=part), S), _expand(cond, cerr, _jax_eps(n2, S, 2, seed, part=part), S))
         want = np.log(np.exp(lp.reshape(n2, S)).mean(axis=1, dtype=np.float32))
     ok = want > LP_UNDERFLOW
     for engine in ENGINES + ["wide"]:
@@ -2044,42 +2049,56 @@ def test_uniform_latent_draws_are_the_jax_stream():
     from pzflow_b200 import distributions as Dn
     from pzflow_b200 import prng
     from pzflow_b200.plan import sample_uniform_jax
-    assert prng.layout() == "threefry"
+    assert prng.layout() == "threefry_partitionable"     # the default: what the reference's required jax (>= 0.5.3) draws
+    assert float(sample_uniform_jax(1, 1, 0.5, 0)[0, 0]) + 0.5 == np.float32(0.947667)   # uniform(key(0)) of jax's docs
     for n, D, seed in ((2, 7, 0), (1001, 7, 7), (4096, 3, 2 ** 31 + 5), (1, 1, 10 ** 17), (300_001, 5, 11)):
-        want = J.uniform(J.PRNGKey(seed), (n, D), -5.0, 5.0)
-        got = Dn.Uniform(D, 5).sample((), n, seed)
-        assert got.dtype == np.float32 and np.array_equal(got.view(np.int32), want.view(np.int32)), (n, D, seed)
         wantp = J.uniform(J.PRNGKey(seed), (n, D), -5.0, 5.0, partitionable=True)
-        gotp = _np(sample_uniform_jax(n, D, 5.0, seed, layout="threefry_partitionable"))
-        assert np.array_equal(gotp.view(np.int32), wantp.view(np.int32)), (n, D, seed)
-    # rows [a, b) of a 1001-row draw, as a sharded Flow.sample asks for them
-    whole = J.uniform(J.PRNGKey(3), (1001, 7), -5.0, 5.0)
-    for a, b in ((0, 400), (400, 1001), (1000, 1001)):
-        part = _np(Dn.Uniform(7, 5).sample_device(b - a, 3, row_offset=a, total_rows=1001))
-        assert np.array_equal(part.view(np.int32), whole[a:b].view(np.int32))
+        got = Dn.Uniform(D, 5).sample((), n, seed)
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.int32), wantp.view(np.int32)), (n, D, seed)
+        want = J.uniform(J.PRNGKey(seed), (n, D), -5.0, 5.0)
+        goto = _np(sample_uniform_jax(n, D, 5.0, seed, layout="threefry"))
+        assert np.array_equal(goto.view(np.int32), want.view(np.int32)), (n, D, seed)
+    # rows [a, b) of a 1001-row draw, as a sharded Flow.sample asks for them -- in both layouts
+    for lay in ("threefry", "threefry_partitionable"):
+        prng.set_layout(lay)
+        try:
+            whole = J.uniform(J.PRNGKey(3), (1001, 7), -5.0, 5.0, partitionable=lay != "threefry")
+            for a, b in ((0, 400), (400, 1001), (1000, 1001)):
+                part = _np(Dn.Uniform(7, 5).sample_device(b - a, 3, row_offset=a, total_rows=1001))
+                assert np.array_equal(part.view(np.int32), whole[a:b].view(np.int32))
+        finally:
+            prng.set_layout("threefry_partitionable")
     # the Philox streams of round 1 stay available
     prng.set_layout("philox")
     try:
         ph = Dn.Uniform(7, 5).sample((), 1000, 0)
         assert not np.array_equal(ph, J.uniform(J.PRNGKey(0), (1000, 7), -5.0, 5.0)) and np.abs(ph).max() <= 5
     finally:
-        prng.set_layout("threefry")
+        prng.set_layout("threefry_partitionable")
 
 
-def test_flow_sample_reproduces_what_real_jax_printed():
+def test_flow_sample_reproduces_what_real_jax_printed(stream_layout):
     """docs/tutorials/marginalization.ipynb:69, 133-135: ``flow.sample(2, seed=0)`` of the shipped flow under the real JAX
-    reference.  The same call here -- latents drawn on the GPU in jax's stream, the inverse chain on the tensor cores --
-    returns the printed rows to the printed precision; and 1001 samples of seed 7 equal what the reference's own
-    code returns over the stand-in (tests/golden/ref_shim_jax_streams.npz)."""
+    reference (an older jax: the original stream layout).  The same call here -- latents drawn on the GPU in jax's stream,
+    the inverse chain on the tensor cores -- returns the printed rows to the printed precision in that layout; and in
+    either layout 2 samples of seed 0 and 1001 samples of seed 7 equal what the reference's own code returns over the
+    stand-in drawing that layout (tests/golden/ref_shim_jax_streams[_part].npz)."""
+    from conftest import STREAM_GOLDEN
     from pzflow_b200.examples import get_example_flow
     flow = get_example_flow()
-    z, g = golden("ref_shim_example_flow.npz"), golden("ref_shim_jax_streams.npz")
+    z, g = golden("ref_shim_example_flow.npz"), golden(STREAM_GOLDEN[stream_layout])
     s = flow.sample(2, seed=0)
     assert list(s.columns) == ["redshift", "u", "g", "r", "i", "z", "y"]
-    np.testing.assert_allclose(s.to_numpy(), z["nb_X"], rtol=3e-6, atol=0)
+    legacy = stream_layout == "threefry"       # the notebook was run with a jax older than 0.5: the original layout
+    if legacy:
+        np.testing.assert_allclose(s.to_numpy(), z["nb_X"], rtol=3e-6, atol=0)
+    else:
+        assert np.abs(s.to_numpy() - z["nb_X"]).max() > 0.1
     for engine in ("simt", "tc", "wide"):
         flow._plan().set_engine(engine)
-        np.testing.assert_allclose(flow.sample(2, seed=0).to_numpy(), z["nb_X"], rtol=3e-6, atol=0, err_msg=engine)
+        two = flow.sample(2, seed=0).to_numpy()
+        np.testing.assert_allclose(two, z["nb_X"] if legacy else g["example_sample_2_seed0"], rtol=3e-6 if legacy else 2e-5,
+                                   atol=0, err_msg=engine)
         big = flow.sample(1001, seed=7).to_numpy()
         want = g["example_sample_1001_seed7"]
         ex = F.example_flow()
@@ -2090,7 +2109,7 @@ def test_flow_sample_reproduces_what_real_jax_printed():
 
 
 @pytest.mark.parametrize("engine", ["simt", "tc", "wide"])
-def test_shuffle_and_dequantizer_flows_against_reference_golden(engine):
+def test_shuffle_and_dequantizer_flows_against_reference_golden(engine, stream_layout):
     """Flows whose chains hold Shuffle stages (pzflow/bijectors.py:780-814) and a UniformDequantizer (865-911), built
     with two seeds: log_prob, forward and Flow.sample against what the reference's own code returned (stand-in with
     jax's key schedule, oracle/make_golden_shim.py jax_streams); a flow re-built from its save dictionary draws its
@@ -2098,8 +2117,10 @@ def test_shuffle_and_dequantizer_flows_against_reference_golden(engine):
     from pzflow_b200 import Flow
     from pzflow_b200 import bijectors as B
     from pzflow_b200 import distributions as Dn
+    from conftest import STREAM_GOLDEN
     from oracle import jax_prng as J
-    g = golden("ref_shim_jax_streams.npz")
+    g = golden(STREAM_GOLDEN[stream_layout])
+    part = stream_layout == "threefry_partitionable"
     X, mins, maxs = g["X"], g["mins"], g["maxs"]
     cols = tuple("abcde")
     df = pd.DataFrame(X.astype(np.float64), columns=cols)
@@ -2118,7 +2139,7 @@ def test_shuffle_and_dequantizer_flows_against_reference_golden(engine):
         if engine == "tc" and not plan.tc_supported or engine == "wide" and not plan.wide_supported:
             pytest.skip("engine does not take this shape")
         plan.set_engine(engine)
-        ri = O.resolve_shuffles(info, J.PRNGKey(seed), 5)
+        ri = O.resolve_shuffles(info, J.PRNGKey(seed), 5, part)
         p64 = O.cast_params(((), params), np.float64)
         lp = fl.log_prob(df)
         assert_noise_floor(f"shuffle flow log_prob seed {seed} [{engine}]", lp, g[f"s{seed}_log_prob"],
@@ -2128,7 +2149,7 @@ def test_shuffle_and_dequantizer_flows_against_reference_golden(engine):
         u64, ld64 = O.apply_bijector(ri, p64[1], X.astype(np.float64), np.zeros((len(X), 1)))
         assert_noise_floor(f"shuffle flow forward seed {seed} [{engine}]", u, g[f"s{seed}_forward_u"], u64, ratio=2.0, slack=2e-5)
         smp = fl.sample(9, seed=5).to_numpy()
-        x64, _ = O.flow_inverse(ri, p64, J.uniform(J.PRNGKey(5), (9, 5), -5.0, 5.0).astype(np.float64))
+        x64, _ = O.flow_inverse(ri, p64, J.uniform(J.PRNGKey(5), (9, 5), -5.0, 5.0, part).astype(np.float64))
         assert_noise_floor(f"shuffle flow sample seed {seed} [{engine}]", smp, g[f"s{seed}_sample_9_seed5"], x64, ratio=2.0,
                            slack=2e-5)
         # inverse floors the dequantized column (bijectors.py:902-905): samples of column c are whole numbers
@@ -2386,14 +2407,15 @@ def test_stand_alone_spline_and_network_of_the_reference_utils():
     assert flow._get_err_samples(5, df, 4, type="data", skip="redshift").shape == (40, 6)
 
 
-def test_conditional_ensemble_sampling_against_reference_golden():
+def test_conditional_ensemble_sampling_against_reference_golden(stream_layout):
     """FlowEnsemble.sample with conditions (pzflow/flowEnsemble.py:409-471) against what the reference's own code returned
     over the stand-in with jax's key schedule: which flow draws which condition row (pandas' shuffle, jax.random.permutation
     of the chunks, NumPy's choice for fewer rows than flows) AND the drawn values (Uniform latents: jax's stream)."""
     from pzflow_b200 import FlowEnsemble
     from pzflow_b200 import bijectors as B
     from pzflow_b200 import distributions as Dn
-    g = golden("ref_shim_jax_streams.npz")
+    from conftest import STREAM_GOLDEN
+    g = golden(STREAM_GOLDEN[stream_layout])
     mins, maxs = g["mins"][:3], g["maxs"][:3]
     ens = FlowEnsemble(("a", "b", "c"), B.Chain(B.ShiftBounds(mins, maxs, 4.0),
                                                 B.RollingSplineCoupling(3, K=8, hidden_dim=32, n_conditions=2)),
@@ -2419,7 +2441,7 @@ def test_conditional_ensemble_sampling_against_reference_golden():
 
 
 @pytest.mark.parametrize("engine", ["simt", "tc", "wide"])
-def test_posteriors_overlay_the_figures_real_jax_plotted(engine):
+def test_posteriors_overlay_the_figures_real_jax_plotted(engine, notebook_era_streams):
     """docs/tutorials/marginalization.ipynb cells 9-15 through the public API: flow.posterior(samples, "redshift", grid)
     and the same with u / y flagged 99 and marg_rules over 40 x 40 values -- the curves land on the lines of the figures
     the reference's authors made with real JAX (tests/golden/nb_posterior_plots.npz; one pixel = 0.8 % of a panel's

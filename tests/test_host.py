@@ -548,8 +548,9 @@ def test_prng_matches_the_oracle_restatement_and_jax_documentation():
     documentation prints."""
     from oracle import jax_prng as J
     from pzflow_b200 import prng
-    assert prng.layout() == "threefry"
-    np.testing.assert_array_equal(prng.split(prng.key_from_seed(0)), [[4146024105, 967050713], [2718843009, 1272950319]])
+    assert prng.layout() == "threefry_partitionable"     # the default: what the reference's required jax (>= 0.5.3) draws
+    np.testing.assert_array_equal(prng.split(prng.key_from_seed(0), 2, "threefry"),
+                                  [[4146024105, 967050713], [2718843009, 1272950319]])
     for seed in (0, 1, 7, 2 ** 31 + 5, 10 ** 17):
         k = prng.key_from_seed(seed)
         np.testing.assert_array_equal(k, J.PRNGKey(seed))
@@ -562,20 +563,21 @@ def test_prng_matches_the_oracle_restatement_and_jax_documentation():
                 assert sorted(prng.permutation(k, n, lay)) == list(range(n))
 
 
-def test_shuffle_permutations_follow_the_chain_key_schedule():
+def test_shuffle_permutations_follow_the_chain_key_schedule(stream_layout):
     """plan.resolve_shuffles repeats Chain.init_fun's splits (pzflow/bijectors.py:146-149) and Shuffle's
     random.permutation (795-797): same result as the oracle's walk, different per position and per seed, and the
     flattened stage carries the permutation."""
     from oracle import jax_prng as J
+    part = stream_layout == "threefry_partitionable"
     info = ("Chain", (("Shuffle", ()), ("Chain", (("Reverse", ()), ("Shuffle", ()))), ("Shuffle", ())))
     got = P.resolve_shuffles(info, 3, 7)
-    want = O.resolve_shuffles(info, J.PRNGKey(3), 7)
+    want = O.resolve_shuffles(info, J.PRNGKey(3), 7, part)
     assert got == want
     perms = [got[1][0][1][0], got[1][1][1][1][1][0], got[1][2][1][0]]
     assert all(sorted(p) == list(range(7)) for p in perms) and len({tuple(p) for p in perms}) == 3
     assert P.resolve_shuffles(info, 4, 7) != got
     # a top-level Shuffle takes PRNGKey(seed) itself
-    assert P.resolve_shuffles(("Shuffle", ()), 0, 7) == ("Shuffle", (tuple(int(v) for v in J.permutation(J.PRNGKey(0), 7)),))
+    assert P.resolve_shuffles(("Shuffle", ()), 0, 7) == ("Shuffle", (tuple(int(v) for v in J.permutation(J.PRNGKey(0), 7, part)),))
     stages = P.flatten(got, [(), [(), ()], ()], 7)
     sh = [s for s in stages if s["kind"] == N.STAGE_SHUFFLE]
     assert [tuple(int(v) for v in s["vec_a"]) for s in sh] == [tuple(p) for p in perms]
@@ -614,16 +616,17 @@ def test_small_helpers_of_the_reference_utils_and_examples(monkeypatch, tmp_path
     assert [tuple(np.shape(q) for q in p) for p in params] == [((3, 16), (16,)), (), ((16, 16), (16,)), (), ((16, 5), (5,))]
 
 
-def test_training_epochs_are_shuffled_like_the_reference():
+def test_training_epochs_are_shuffled_like_the_reference(stream_layout):
     """pzflow/flow.py:1015, 1062-1064: key = PRNGKey(batch_seed); per epoch permute_key, sample_key, key = split(key, 3),
     idx = permutation(permute_key, n) -- prng.epoch_orders against the oracle's restatement of jax.random."""
     from oracle import jax_prng as J
     from pzflow_b200 import prng
+    part = stream_layout == "threefry_partitionable"
     for seed, n in ((0, 10), (5, 1000), (2 ** 31 + 1, 77)):
         orders = prng.epoch_orders(seed, n)
         key = J.PRNGKey(seed)
         for _ in range(3):
-            permute_key, _, key = J.split(key, 3)
+            permute_key, _, key = J.split(key, 3, part)
             got = next(orders)
-            np.testing.assert_array_equal(got, J.permutation(permute_key, n))
+            np.testing.assert_array_equal(got, J.permutation(permute_key, n, part))
             assert sorted(got) == list(range(n))

@@ -278,6 +278,21 @@ def test_jax_normal_known_answers():
     np.testing.assert_array_equal(sub, [1278412471, 2182328957])
     assert J.normal(sub, (1,))[0] == np.float32(-0.58665055)
     assert J.normal(J.PRNGKey(42), ())[()] == np.float32(-0.18471177)
+    key, draws = J.PRNGKey(42), []                                   # the split loop of the (older) PRNG tutorial
+    for _ in range(3):
+        key, sub = J.split(key)
+        draws.append(float(J.normal(sub, ())))
+    assert draws == [1.369469404220581, -0.19947023689746857, -2.298278331756592]
+    # the PARTITIONABLE layout (jax >= 0.5's default, what the reference's required jax draws): the same pages of the
+    # current documentation
+    assert J.normal(J.PRNGKey(42), (), partitionable=True)[()] == np.float32(-0.028304616)
+    key, draws = J.PRNGKey(42), []
+    for _ in range(3):
+        key, sub = J.split(key, 2, partitionable=True)
+        draws.append(float(J.normal(sub, (), partitionable=True)))
+    assert draws == [0.6057640314102173, -0.21089035272598267, -0.3948981463909149]
+    assert J.uniform(J.PRNGKey(0), (), 0.0, 1.0, partitionable=True)[()] == np.float32(0.947667)
+    assert J.normal(J.PRNGKey(0), (1,), partitionable=True)[0] == np.float32(1.6226422)
     # the polynomial against the exact function, over the whole open interval and in the tails
     from scipy.special import erfinv
     x = np.concatenate([np.linspace(-0.9999999, 0.9999999, 20001), [np.nextafter(np.float32(-1), np.float32(0))]]).astype(np.float32)
@@ -299,7 +314,7 @@ def test_notebook_samples_from_the_seed():
     u = J.uniform(J.PRNGKey(0), (2, 7), -5.0, 5.0)
     x, _ = O.flow_inverse(ex["bijector_info"], ex["params"], u)
     np.testing.assert_allclose(x, X, rtol=1.5e-6, atol=0)
-    # the other stream layout does not produce them (it is offered unverified)
+    # the other stream layout (jax >= 0.5's default) does not produce them: the notebook was run with an older jax
     u2 = J.uniform(J.PRNGKey(0), (2, 7), -5.0, 5.0, partitionable=True)
     x2, _ = O.flow_inverse(ex["bijector_info"], ex["params"], u2)
     assert np.abs(x2 - X).max() > 0.1
