@@ -432,9 +432,22 @@ class Flow:
                 rest_err = None
             else:
                 rest, rest_err = self._get_err_arrays(inputs, "data", skip=column)
-            pdfs = plan.posterior_err(rest, rest_err, idx, grid, C, Cerr, err_samples, seed,
-                                      normalize=normalize, nan_to_zero=nan_to_zero)
-            return pdfs.cpu().numpy()
+            from . import prng
+            if batch_size >= nrows or prng.layout() == "philox":
+                pdfs = plan.posterior_err(rest, rest_err, idx, grid, C, Cerr, err_samples, seed,
+                                          normalize=normalize, nan_to_zero=nan_to_zero)
+                return pdfs.cpu().numpy()
+            # the reference draws every batch's samples from the SAME key (flow.py:668-693: random.normal(key,
+            # (len(batch), S, W)) per batch), so with a batch_size the stream restarts at every batch: evaluate the
+            # batches as the separate draws they are
+            pdfs = np.empty((nrows, len(grid)), dtype=np.float32)
+            for a in range(0, nrows, batch_size):
+                b = min(nrows, a + batch_size)
+                pdfs[a:b] = plan.posterior_err(
+                    rest[a:b], None if rest_err is None else rest_err[a:b], idx, grid, None if C is None else C[a:b],
+                    None if Cerr is None else Cerr[a:b], err_samples, seed, normalize=normalize,
+                    nan_to_zero=nan_to_zero).cpu().numpy()
+            return pdfs
 
         # The reference loops over batch_size rows because it materialises [batch * G, D]
         # (pzflow/flow.py:697-730) and normalises once at the end (732-737).  Here the expansion is

@@ -1185,6 +1185,13 @@ def test_err_samples_through_flow_api():
     pdfs = flow.posterior(df[:50], column="redshift", grid=grid, err_samples=6, seed=5)
     assert pdfs.shape == (50, 40)
     np.testing.assert_allclose(np.trapezoid(pdfs, grid, axis=1), 1.0, rtol=1e-4)
+    # with a batch_size the reference draws every batch from the same key (flow.py:668-693): batch k of the call equals
+    # the call on batch k alone, and differs from the rows of the unbatched call after the first batch
+    batched = flow.posterior(df[:50], column="redshift", grid=grid, err_samples=6, seed=5, batch_size=20)
+    for a in (0, 20, 40):
+        alone = flow.posterior(df[a:min(50, a + 20)], column="redshift", grid=grid, err_samples=6, seed=5)
+        np.testing.assert_array_equal(batched[a:a + 20], alone)
+    assert np.abs(batched[20:40] - pdfs[20:40]).max() > 1e-4
     with pytest.raises(AssertionError):
         flow.log_prob(df, err_samples=0)
     # a user's own error model is a host callable (test_custom_error_models_...); it cannot ride inside marg_rules
