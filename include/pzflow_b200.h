@@ -279,8 +279,9 @@ int pzb_rational_quadratic_spline(const float *inputs, const float *W, const flo
  * (cond_err in standard-scaled units, i.e. divided by condition_stds); either
  * may be NULL = zero error (the reference fills missing *_err columns with
  * zeros, flow.py:366-369).  eps comes from a counter-based Philox stream keyed
- * by `seed` (not jax.random.normal's threefry: parity is defined given eps, see
- * pzb_error_eps).  scratch: caller-owned device buffer of N * S floats.
+ * by `seed` (see pzb_error_eps) -- or, after pzb_set_error_stream (below), from
+ * jax.random.normal(PRNGKey(seed), ...) itself, which is what the Python mirror
+ * asks for by default.  scratch: caller-owned device buffer of N * S floats.
  * row_offset: index of X's first row in the caller's whole array, so that a
  * call cut into row chunks draws exactly the eps of one big call. */
 int pzb_log_prob_err(const pzb_plan *plan, const float *X, const float *Xerr, const float *cond,
