@@ -44,11 +44,24 @@ struct TrainBatch {  // how a step's rows are picked out of the caller's whole a
 // eight consecutive columns hit eight different bank groups
 __device__ __forceinline__ int ts_swz(int col, int row) { return col * TS_ROWS + (row ^ (((col >> 1) & 3) << 2)); }
 
+// first coupling stage of the chain: the stages before it hold no parameters, so the backward walk ends there
+__host__ __device__ inline int ts_first_nsc(const PlanDev& hp) {
+  for (int si = 0; si < hp.n_steps; ++si)
+    if (hp.steps[si].kind == STEP_NSC) return si;
+  return hp.n_steps;
+}
+
 bool train_step_supported(const PlanDev& hp) {
-  if (hp.n_nsc < 1 || hp.n_color > 0) return false;
+  if (hp.n_nsc < 1) return false;
   if (hp.n_lat != 1 || (hp.lat[0].kind != 1 && hp.lat[0].kind != 2 && hp.lat[0].kind != 3)) return false;
-  for (int a = 0; a < hp.n_affine; ++a)
-    if (hp.affine[a].kind == AFF_INV_SOFTPLUS) return false;
+  // ColorTransform / InvSoftplus (the photo-z chains of the reference's tutorials put them in FRONT of the coupling
+  // stages) run forward only: behind a coupling stage they would need a backward of their own
+  const int first = ts_first_nsc(hp);
+  for (int si = first; si < hp.n_steps; ++si) {
+    const StepDev st = hp.steps[si];
+    if (st.kind == STEP_COLOR) return false;
+    if (st.kind == STEP_AFFINE && hp.affine[st.idx].kind == AFF_INV_SOFTPLUS) return false;
+  }
   for (int s = 0; s < hp.n_nsc; ++s) {
     const NscDev& st = hp.nsc[s];
     if (st.n_dense < 1 || st.H > TS_HMAX || st.K > TS_KMAX || st.cpd * st.L > TS_OUT_MAX || st.U + st.C > TS_HMAX) return false;
@@ -372,23 +385,21 @@ train_step_kernel(const PlanDev* __restrict__ plan, const TrainOffsets* __restri
   // are drawn here, so a step launches nothing but this kernel, the partial-sum reduction and Adam ----
   for (int e = tid; e < D * TS_ROWS; e += TS_THREADS) {
     const int r = e / D, j = e - r * D;
-    float v = 0.0f;
-    if (row0 + r < N) {
-      const long long src = tb.row_idx != nullptr ? tb.row_idx[row0 + r] : row0 + r;
-      v = X[src * D + j];
-      if (tb.Xerr != nullptr) v = v + pz_err_normal(tb.seed, 0u, tb.noise_base + (unsigned long long)(row0 + r), j) * tb.Xerr[src * D + j];
-    }
+    // the padding rows of a ragged last tile repeat the batch's last row (weight 0 below): zeros are not inside every
+    // chain's domain (InvSoftplus(0) = -inf), and a non-finite activation would poison the tile's weight gradient
+    const long long br = row0 + r < N ? row0 + r : N - 1;
+    const long long src = tb.row_idx != nullptr ? tb.row_idx[br] : br;
+    float v = X[src * D + j];
+    if (tb.Xerr != nullptr) v = v + pz_err_normal(tb.seed, 0u, tb.noise_base + (unsigned long long)br, j) * tb.Xerr[src * D + j];
     xs[ts_swz(j, r)] = v;
   }
   for (int e = tid; e < C * TS_ROWS; e += TS_THREADS) {
     const int r = e / C, j = e - r * C;
-    float v = 0.0f;
-    if (row0 + r < N) {
-      const long long src = tb.row_idx != nullptr ? tb.row_idx[row0 + r] : row0 + r;
-      v = cond[src * C + j];
-      if (tb.cond_err != nullptr)
-        v = v + pz_err_normal(tb.seed, 1u, tb.noise_base + (unsigned long long)(row0 + r), j) * tb.cond_err[src * C + j];
-    }
+    const long long br = row0 + r < N ? row0 + r : N - 1;
+    const long long src = tb.row_idx != nullptr ? tb.row_idx[br] : br;
+    float v = cond[src * C + j];
+    if (tb.cond_err != nullptr)
+      v = v + pz_err_normal(tb.seed, 1u, tb.noise_base + (unsigned long long)br, j) * tb.cond_err[src * C + j];
     cs[ts_swz(j, r)] = v;
   }
   if (tid < TS_ROWS) ldsum[tid] = 0.0f;
@@ -400,12 +411,39 @@ train_step_kernel(const PlanDev* __restrict__ plan, const TrainOffsets* __restri
     const StepDev step = plan->steps[si];
     if (step.kind == STEP_AFFINE) {
       const AffineDev& af = plan->affine[step.idx];
+      const bool has_ld = af.kind == AFF_INV_SOFTPLUS;   // the one elementwise stage whose log-det depends on the row
       for (int e = tid; e < D * TS_ROWS; e += TS_THREADS) {
         const int j = e / TS_ROWS, r = e - j * TS_ROWS;
         float ld;
         xs[ts_swz(j, r)] = pz_affine_elem(af, false, j, xs[ts_swz(j, r)], ld);
+        if (has_ld) gx[ts_swz(j, r)] = ld;               // (the gradient buffer is idle during the forward walk)
       }
-      if (tid < TS_ROWS) ldsum[tid] += af.logdet_fwd;
+      if (has_ld) {
+        __syncthreads();
+        if (tid < TS_ROWS) {                             // summed in column order: deterministic
+          float sld = 0.0f;
+          for (int j = 0; j < D; ++j) sld += gx[ts_swz(j, tid)];
+          ldsum[tid] += sld;
+        }
+      } else if (tid < TS_ROWS) {
+        ldsum[tid] += af.logdet_fwd;
+      }
+      __syncthreads();
+    } else if (step.kind == STEP_COLOR) {
+      // ColorTransform forward on one row per thread (bijectors.py:268-280: colours = -diff(mags), the reference
+      // magnitude last; log-det 0), same column slots as pz_color_row
+      if (tid < TS_ROWS) {
+        const ColorDev& cd = plan->color[step.idx];
+        const int r = tid, n = cd.n_mag;
+        float prev = xs[ts_swz(cd.slot[0], r)];
+        const float refv = xs[ts_swz(cd.slot[cd.ref], r)];
+        for (int i = 0; i + 1 < n; ++i) {
+          const float nxt = xs[ts_swz(cd.slot[i + 1], r)];
+          xs[ts_swz(cd.slot[i], r)] = -(nxt - prev);
+          prev = nxt;
+        }
+        xs[ts_swz(cd.slot[n - 1], r)] = refv;
+      }
       __syncthreads();
     } else if (step.kind == STEP_NSC) {
       const NscDev& st = plan->nsc[step.idx];
@@ -502,7 +540,8 @@ train_step_kernel(const PlanDev* __restrict__ plan, const TrainOffsets* __restri
   if (tid == 0) loss_part[blockIdx.x] = tile_loss;
 
   // ================================ backward ================================
-  for (int si = ns - 1; si >= 0; --si) {
+  const int first_nsc = ts_first_nsc(*plan);   // nothing in front of it has parameters: its input gradient is not needed
+  for (int si = ns - 1; si >= first_nsc; --si) {
     const StepDev step = plan->steps[si];
     if (step.kind == STEP_AFFINE) {
       const AffineDev& af = plan->affine[step.idx];

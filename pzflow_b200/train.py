@@ -235,10 +235,16 @@ class TorchChain:
             out[:, idx] = y
             return out, torch.log(1 + torch.exp(-k * y)).sum(dim=1)
         if name == "ColorTransform":                             # bijectors.py:236-276
-            ref_idx, mag_idx = int(args[0]), list(np.asarray(args[1]).ravel().astype(int))
-            front = [j for j in range(x.shape[1]) if j not in mag_idx]
-            mags = x[:, mag_idx]
-            out = torch.cat([x[:, front], x[:, ref_idx:ref_idx + 1], -(mags[:, 1:] - mags[:, :-1])], dim=1)
+            ref_idx = int(args[0])
+
+            def make():   # index tensors live on the device once: an index list would be copied per call (and
+                mag = [int(j) for j in np.asarray(args[1]).ravel()]   # cannot be inside a CUDA-graph capture)
+                front = [j for j in range(x.shape[1]) if j not in mag]
+                return (torch.as_tensor(mag, dtype=torch.long, device=self.device),
+                        torch.as_tensor(front, dtype=torch.long, device=self.device))
+            mag_idx, front = self._const((id(info), "color", x.shape[1]), make)
+            mags = x.index_select(1, mag_idx)
+            out = torch.cat([x.index_select(1, front), x[:, ref_idx:ref_idx + 1], -(mags[:, 1:] - mags[:, :-1])], dim=1)
             return out, zeros
         if name == "NeuralSplineCoupling":                       # bijectors.py:462-506
             full = tuple(args) + (16, 5, 2, 128, None, 0, False)[len(args):]

@@ -1945,7 +1945,7 @@ def _f64_loss_and_grad(cfg, X, cond, w):
     return float(loss), _np(torch.cat([p.grad.reshape(-1) for p in chain.leaves]))
 
 
-@pytest.mark.parametrize("case", ["shipped", "conditional_centbeta", "deep_narrow"])
+@pytest.mark.parametrize("case", ["shipped", "conditional_centbeta", "deep_narrow", "colour_chain"])
 def test_fused_training_step_gradient_against_float64_autograd(case):
     """pzb_train_step (forward + backward through the whole chain in one kernel, hand-derived) against float64
     autograd over the torch restatement: the loss, and the gradient of every weight."""
@@ -1960,6 +1960,15 @@ def test_fused_training_step_gradient_against_float64_autograd(case):
         cfg = F.config_c4(1)[0]
         X = torch.from_numpy(rng.uniform(mins + 0.1, maxs - 0.1, size=(777, 7)).astype(np.float32)).cuda()
         cond = torch.from_numpy(rng.normal(size=(777, 2)).astype(np.float32)).cuda()
+    elif case == "colour_chain":   # the photo-z chain of the reference's tutorials: the parameter-free stages in front
+        info = ("Chain", (("ColorTransform", (3, [1, 2, 3, 4, 5, 6])), ("InvSoftplus", (0, 4.0)),
+                          ("StandardScaler", (np.linspace(-0.5, 0.5, 7).astype(np.float32),
+                                              np.linspace(0.5, 2.0, 7).astype(np.float32))),
+                          ("Reverse", ()), ("RollingSplineCoupling", (7,)), ("Scale", (0.8,))))
+        bparams = [(), (), (), (), O.synth_bijector_params(O.expand_rolling((7,)), 7, rng, out_scale=2.0), ()]
+        cfg = dict(bijector_info=info, latent_info=("CentBeta13", (7, 5)),
+                   params=(tuple((0.0, 0.0) for _ in range(7)), bparams), input_dim=7)
+        X, cond = torch.from_numpy(rng.uniform(0.05, 1.5, size=(555, 7)).astype(np.float32)).cuda(), None
     else:   # three hidden layers of 40, K = 5, odd column count, StandardScaler in front
         info = ("Chain", (("StandardScaler", (np.linspace(-1, 1, 5).astype(np.float32), np.linspace(1, 2, 5).astype(np.float32))),
                           F.rolling_info(3, 2, 5, 4, 3, 40)))
