@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpzflow_b200.so")
 SOURCES = ["pzb_api.cu", "nsf_simt.cu", "nsf_tc.cu", "nsf_wide.cu", "nsf_train.cu", "nsf_train_step.cu"]
-HEADERS = ["pzb_common.cuh", "pzb_tc_common.cuh", os.path.join("..", "..", "include", "pzflow_b200.h")]
+HEADERS = ["pzb_common.cuh", "pzb_tc_common.cuh", "nsf_tc_pipe3.cuh", os.path.join("..", "..", "include", "pzflow_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -46,6 +46,9 @@
 // Follows the same reference lines as nsf_simt.cu.
 #include "pzb_tc_common.cuh"
 
+#ifndef PZB_TC_PIPE3_DEFAULT
+#define PZB_TC_PIPE3_DEFAULT 0   // which kernel runs when the environment does not say (PZB_TC_PIPE3)
+#endif
 #ifndef PZB_TC_STUB
 #define PZB_TC_STUB 0   // bit 0 / bit 1: measurement builds without the spline / the activation arithmetic
 #endif
@@ -208,6 +211,17 @@ void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* co
 // device side: PTX wrappers
 // ------------------------------------------------------------------------------------------
 
+// barriers of nsf_chain_tc3_kernel (nsf_tc_pipe3.cuh)
+struct TcPipe3Bars {
+  uint64_t d1_full[3];      // [region]: first-layer GEMM landed in X[region] (commit)
+  uint64_t e1_ready[3][2];  // [region][half] (4 warp arrivals): that half of h1 is written
+  uint64_t d3_full[3];      // [region]: an output pass (two spline dimensions, N = 96) landed (commit)
+  uint64_t d3_free[3];      // [region] (8 warp arrivals): both halves have their 48 logits of the pass in registers
+  uint64_t d2_full[2];      // [half]: that N = 64 half of the hidden GEMM landed in Y (commit)
+  uint64_t e2_ready[2];     // [half] (4 warp arrivals): that half of h2 is written
+  uint64_t key_ready;       // (4 warp arrivals): the key operand of the next tile is in shared memory
+  uint64_t key_free;        // the first-layer GEMM that read it has completed (commit)
+};
 struct TcShared {
   uint64_t e_ready[2][2];  // [group][half] -> the group's MMA issuer (4 warp arrivals): that half's 64 K-elements of the
                            // A operand are written (after E1 and after E2)
@@ -226,19 +240,23 @@ struct TcShared {
   int n_seq;                    // sub-stages of one chain walk
   uint8_t order[TC_SEQ_MAX + 1];  // sub-stages in walk order: coupling stage (index into PlanDev::nsc) ...
   uint8_t sub[TC_SEQ_MAX + 1];    // ... and which four of its spline dimensions
+  TcPipe3Bars p3;
 };
 
 struct TcSmem {  // byte offsets from the 1024-aligned base
-  int w2, w3, w1, par, state, acc, shared, total;
+  int w2, w3, w1, par, keys, state, acc, shared, total;
 };
 
-__host__ __device__ inline TcSmem tc_smem_layout(int max_pass, int chunk_tiles, int state_cols, int acc_floats = 0) {
+// key_bytes: the three-tile kernel keeps the first layer's key operand in shared memory (TC_W1_BYTES), the other one in TMEM (0)
+__host__ __device__ inline TcSmem tc_smem_layout(int max_pass, int chunk_tiles, int state_cols, int acc_floats = 0,
+                                                 int key_bytes = 0) {
   TcSmem s;
   s.w2 = 0;
   s.w3 = TC_W2_BYTES;
   s.w1 = s.w3 + max_pass * TC_W3_PASS_BYTES;
   s.par = s.w1 + TC_W1_BYTES;
-  s.state = s.par + 2 * TC_PAR_BYTES;
+  s.keys = s.par + 2 * TC_PAR_BYTES;
+  s.state = s.keys + key_bytes;
   s.acc = s.state + chunk_tiles * TC_TILE * state_cols * 4;
   s.shared = s.acc + acc_floats * 4;
   s.shared = (s.shared + 15) / 16 * 16;
@@ -248,6 +266,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int max_pass, int chunk_tiles, 
 
 struct TcLaunch {
   int chunk_tiles, max_pass, state_cols, n_lev;
+  int key_bytes;  // TC_W1_BYTES: nsf_chain_tc3_kernel (three tiles in flight), 0: nsf_chain_tc_kernel
   // fused posterior reduction (LaunchArgs::fuse): a unit = one galaxy = unit_rows = max(V,1) * max(S,1) * G consecutive rows.
   //   upc > 0: a chunk holds upc whole units (unit_rows <= chunk rows);
   //   cpu > 0: a unit spans cpu chunks of spc samples (of G rows) each, all walked by the same CTA, sums kept in shared memory.
@@ -293,6 +312,94 @@ __device__ __forceinline__ float tc_nan_to_num0(float v) {
   return v;
 }
 
+
+// Reductions of the fused launches, by all 16 epilogue warps, once pass Z has left exp(lp) (posterior) or lp (log_prob with
+// error samples) of the chunk's rows in the state column COL_PEND.
+__device__ __forceinline__ void tc_fused_reduction(const TcLaunch& lp, const LaunchArgs& args, const TcSmem& sl, uint8_t* base,
+                                                   float* state, int CR, int COL_PEND, int nrows, long long unit0, int sub,
+                                                   int tid, int warp, int lane) {
+  // ---- posterior reduction: mean over the error samples, sum over the variants, per-galaxy trapezoid, NaN -> 0
+  // (pzflow/flow.py:720-737, 651-654), by all 16 epilogue warps, before the ONLY write of the pdfs to HBM ----
+  named_bar_sync(1, TC_EPI_THREADS);
+  const float* P = state + COL_PEND * CR;
+  const int G = args.G, S = max(args.S, 1), V = max(args.V, 1);
+  const bool inner_nan0 = args.V > 0 && args.nan_to_zero != 0;  // an inner call's nan_to_num, per variant
+  const bool lme = args.mode == MODE_LOGPROB;  // log(mean_s exp(lp)) of a row's error samples (flow.py:463-464), G == 1
+  const int etid = (int)tid;
+  auto finish = [&](const float* Yg, long long unit) {  // one warp: trapezoid of Yg[0, G), then the galaxy's pdf
+    float integral = 1.0f;
+    if (args.normalize) {
+      float part = 0.0f;
+      for (int i = lane; i + 1 < G; i += 32) part += (args.grid[i + 1] - args.grid[i]) * (Yg[i + 1] + Yg[i]);
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      integral = 0.5f * part;
+    }
+    return integral;
+  };
+  if (lp.upc > 0) {
+    float* Y = state + (COL_PEND + 1) * CR;
+    const int RU = lp.unit_rows, nunits = nrows / RU;
+    for (int e = etid; e < nunits * G; e += TC_EPI_THREADS) {
+      const int u = e / G, g = e - u * G;
+      const float* pu = P + u * RU + g;
+      float tot = 0.0f;
+      for (int v = 0; v < V; ++v) {
+        float sm = lme ? expf(pu[(v * S) * G]) : pu[(v * S) * G];
+        for (int k = 1; k < S; ++k) sm += lme ? expf(pu[(v * S + k) * G]) : pu[(v * S + k) * G];
+        float y = (S > 1 || lme) ? sm / (float)S : sm;
+        if (inner_nan0) y = tc_nan_to_num0(y);
+        tot = v == 0 ? y : tot + y;
+      }
+      if (lme) args.out0[unit0 + u] = logf(tot);
+      else Y[e] = tot;
+    }
+    named_bar_sync(1, TC_EPI_THREADS);
+    for (int u = warp; u < nunits && !lme; u += TC_EPI_THREADS / 32) {
+      const float* Yg = Y + u * G;
+      const float integral = finish(Yg, unit0 + u);
+      float* dst = args.out0 + (unit0 + u) * (long long)G;
+      for (int i = lane; i < G; i += 32) {
+        float y = Yg[i];
+        if (args.normalize) y = y / integral;
+        if (args.nan_to_zero) y = tc_nan_to_num0(y);
+        dst[i] = y;
+      }
+    }
+  } else {
+    float* accS = reinterpret_cast<float*>(base + sl.acc);
+    float* accV = accS + G;
+    const int nsamp = nrows / G, j0 = sub * lp.spc;
+    for (int g = etid; g < G; g += TC_EPI_THREADS) {
+      float aS = accS[g], aV = accV[g];
+      for (int j = 0; j < nsamp; ++j) {
+        const int si = j0 + j, k = si % S, v = si / S;
+        const float pv = lme ? expf(P[j * G + g]) : P[j * G + g];
+        aS = k == 0 ? pv : aS + pv;
+        if (k == S - 1) {
+          float y = (S > 1 || lme) ? aS / (float)S : aS;
+          if (inner_nan0) y = tc_nan_to_num0(y);
+          aV = v == 0 ? y : aV + y;
+        }
+      }
+      accS[g] = aS;
+      accV[g] = aV;
+    }
+    if (sub == lp.cpu - 1 && lme) {
+      if (etid == 0) args.out0[unit0] = logf(accV[0]);
+    } else if (sub == lp.cpu - 1) {
+      named_bar_sync(1, TC_EPI_THREADS);
+      const float integral = finish(accV, unit0);  // every warp computes the same sum in the same order
+      float* dst = args.out0 + unit0 * (long long)G;
+      for (int g = etid; g < G; g += TC_EPI_THREADS) {
+        float y = accV[g];
+        if (args.normalize) y = y / integral;
+        if (args.nan_to_zero) y = tc_nan_to_num0(y);
+        dst[g] = y;
+      }
+    }
+  }
+  named_bar_sync(1, TC_EPI_THREADS);  // P / Y / the sums are free again before the next chunk's first stage ends
+}
 
 #define TC_BAR(field) (sh_addr + (uint32_t)offsetof(TcShared, field))
 
@@ -713,89 +820,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
         }
       }
       // (pass A of the next chunk touches a row from the same thread as pass Z did: no barrier needed)
-      if (fuse) {
-        // ---- posterior reduction: mean over the error samples, sum over the variants, per-galaxy trapezoid, NaN -> 0
-        // (pzflow/flow.py:720-737, 651-654), by all 16 epilogue warps, before the ONLY write of the pdfs to HBM ----
-        named_bar_sync(1, TC_EPI_THREADS);
-        const float* P = state + COL_PEND * CR;
-        const int G = args.G, S = max(args.S, 1), V = max(args.V, 1);
-        const bool inner_nan0 = args.V > 0 && args.nan_to_zero != 0;  // an inner call's nan_to_num, per variant
-        const bool lme = args.mode == MODE_LOGPROB;  // log(mean_s exp(lp)) of a row's error samples (flow.py:463-464), G == 1
-        const int etid = (int)tid;
-        auto finish = [&](const float* Yg, long long unit) {  // one warp: trapezoid of Yg[0, G), then the galaxy's pdf
-          float integral = 1.0f;
-          if (args.normalize) {
-            float part = 0.0f;
-            for (int i = lane; i + 1 < G; i += 32) part += (args.grid[i + 1] - args.grid[i]) * (Yg[i + 1] + Yg[i]);
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            integral = 0.5f * part;
-          }
-          return integral;
-        };
-        if (lp.upc > 0) {
-          float* Y = state + (COL_PEND + 1) * CR;
-          const int RU = lp.unit_rows, nunits = nrows / RU;
-          for (int e = etid; e < nunits * G; e += TC_EPI_THREADS) {
-            const int u = e / G, g = e - u * G;
-            const float* pu = P + u * RU + g;
-            float tot = 0.0f;
-            for (int v = 0; v < V; ++v) {
-              float sm = lme ? expf(pu[(v * S) * G]) : pu[(v * S) * G];
-              for (int k = 1; k < S; ++k) sm += lme ? expf(pu[(v * S + k) * G]) : pu[(v * S + k) * G];
-              float y = (S > 1 || lme) ? sm / (float)S : sm;
-              if (inner_nan0) y = tc_nan_to_num0(y);
-              tot = v == 0 ? y : tot + y;
-            }
-            if (lme) args.out0[unit0 + u] = logf(tot);
-            else Y[e] = tot;
-          }
-          named_bar_sync(1, TC_EPI_THREADS);
-          for (int u = warp; u < nunits && !lme; u += TC_EPI_THREADS / 32) {
-            const float* Yg = Y + u * G;
-            const float integral = finish(Yg, unit0 + u);
-            float* dst = args.out0 + (unit0 + u) * (long long)G;
-            for (int i = lane; i < G; i += 32) {
-              float y = Yg[i];
-              if (args.normalize) y = y / integral;
-              if (args.nan_to_zero) y = tc_nan_to_num0(y);
-              dst[i] = y;
-            }
-          }
-        } else {
-          float* accS = reinterpret_cast<float*>(base + sl.acc);
-          float* accV = accS + G;
-          const int nsamp = nrows / G, j0 = sub * lp.spc;
-          for (int g = etid; g < G; g += TC_EPI_THREADS) {
-            float aS = accS[g], aV = accV[g];
-            for (int j = 0; j < nsamp; ++j) {
-              const int si = j0 + j, k = si % S, v = si / S;
-              const float pv = lme ? expf(P[j * G + g]) : P[j * G + g];
-              aS = k == 0 ? pv : aS + pv;
-              if (k == S - 1) {
-                float y = (S > 1 || lme) ? aS / (float)S : aS;
-                if (inner_nan0) y = tc_nan_to_num0(y);
-                aV = v == 0 ? y : aV + y;
-              }
-            }
-            accS[g] = aS;
-            accV[g] = aV;
-          }
-          if (sub == lp.cpu - 1 && lme) {
-            if (etid == 0) args.out0[unit0] = logf(accV[0]);
-          } else if (sub == lp.cpu - 1) {
-            named_bar_sync(1, TC_EPI_THREADS);
-            const float integral = finish(accV, unit0);  // every warp computes the same sum in the same order
-            float* dst = args.out0 + unit0 * (long long)G;
-            for (int g = etid; g < G; g += TC_EPI_THREADS) {
-              float y = accV[g];
-              if (args.normalize) y = y / integral;
-              if (args.nan_to_zero) y = tc_nan_to_num0(y);
-              dst[g] = y;
-            }
-          }
-        }
-        named_bar_sync(1, TC_EPI_THREADS);  // P / Y / the sums are free again before the next chunk's first stage ends
-      }
+      if (fuse) tc_fused_reduction(lp, args, sl, base, state, CR, COL_PEND, nrows, unit0, sub, (int)tid, warp, lane);
     }
   } else {
     // control warps run converged (all 32 lanes wait on the mbarriers); one elected lane issues
@@ -973,12 +998,20 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
   }
 }
 
+#include "nsf_tc_pipe3.cuh"
+
 static int tc_fit_tiles(const TcLaunch& lp, int acc_floats) {
   int fit = TC_MAX_CHUNK_TILES;
   if (const char* cap = getenv("PZB_TC_CHUNK_TILES"))   // experiments only: fewer tiles per chunk than shared memory holds
     fit = std::max(2, std::min(fit, atoi(cap)));
-  while (fit > 2 && tc_smem_layout(lp.max_pass, fit, lp.state_cols, acc_floats).total + 1024 > TC_SMEM_MAX) --fit;
+  while (fit > 2 && tc_smem_layout(lp.max_pass, fit, lp.state_cols, acc_floats, lp.key_bytes).total + 1024 > TC_SMEM_MAX) --fit;
   return fit - (fit & 1);  // the two epilogue groups take alternate tiles: keep the count even
+}
+
+// Which of the two kernels runs: PZB_TC_PIPE3=1 selects nsf_chain_tc3_kernel (three tiles in flight), 0 the two-tile kernel.
+static bool tc_pipe3_enabled() {   // read per launch: a test switches kernels inside one process
+  const char* v = getenv("PZB_TC_PIPE3");
+  return v != nullptr ? atoi(v) != 0 : PZB_TC_PIPE3_DEFAULT != 0;
 }
 
 static void tc_base_launch(const PlanDev& hp, TcLaunch& lp) {
@@ -988,6 +1021,7 @@ static void tc_base_launch(const PlanDev& hp, TcLaunch& lp) {
   lp.state_cols = hp.D + lp.n_lev + 2 + hp.C;
   lp.unit_rows = lp.upc = lp.cpu = lp.spc = 0;
   lp.n_units = 0;
+  lp.key_bytes = tc_pipe3_enabled() ? TC_W1_BYTES : 0;
 }
 
 // Can the posterior of n_units galaxies (V variants x S error samples x G grid points each) be reduced inside the
@@ -1056,16 +1090,26 @@ cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs
     const long long chunk_rows = (long long)lp.chunk_tiles * TC_TILE;
     n_work = (args.N + chunk_rows - 1) / chunk_rows;
   }
-  const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols, acc_floats);
+  const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols, acc_floats, lp.key_bytes);
   const size_t smem = (size_t)sl.total + 1024;
   if (smem > (size_t)TC_SMEM_MAX) return cudaErrorInvalidConfiguration;
   const bool inv = (args.mode == MODE_INVERSE);
-  cudaError_t e = inv ? cudaFuncSetAttribute(nsf_chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                      : cudaFuncSetAttribute(nsf_chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   long long grid = num_sms;
   if (grid > n_work) grid = n_work;
   if (grid < 1) grid = 1;
+  if (lp.key_bytes != 0) {
+    cudaError_t e3 = inv ? cudaFuncSetAttribute(nsf_chain_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(nsf_chain_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e3 != cudaSuccess) return e3;
+    if (inv)
+      nsf_chain_tc3_kernel<true><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, lp, overflow_rows);
+    else
+      nsf_chain_tc3_kernel<false><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, lp, overflow_rows);
+    return cudaGetLastError();
+  }
+  cudaError_t e = inv ? cudaFuncSetAttribute(nsf_chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(nsf_chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   if (inv)
     nsf_chain_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, stream>>>(d_plan, args, lp, overflow_rows);
   else
@@ -1074,6 +1118,14 @@ cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs
 }
 
 }  // namespace pzb
+
+#ifdef PZB_TC3_TRACE
+extern "C" int pzb_debug_tc3_trace(unsigned int* issuer, unsigned int* epilogue) {
+  cudaError_t e = cudaMemcpyFromSymbol(issuer, pzb::g_tc3_trace, sizeof(pzb::g_tc3_trace));
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(epilogue, pzb::g_tc3_trace_e, sizeof(pzb::g_tc3_trace_e));
+  return (int)e;
+}
+#endif
 
 #ifdef PZB_TC_TRACE
 extern "C" int pzb_debug_tc_trace(unsigned int* out) {

@@ -1932,6 +1932,47 @@ def test_marginal_variants_are_summed_inside_the_kernel():
 
 
 # --------------------------------------------------------------------------- #
+# the three-tile form of the tensor-core kernel (experimental, PZB_TC_PIPE3=1)  #
+# --------------------------------------------------------------------------- #
+def test_three_tile_kernel_equals_the_two_tile_kernel_bit_for_bit(monkeypatch):
+    """nsf_chain_tc3_kernel (csrc/nsf_tc_pipe3.cuh: three tiles in flight over three X regions and one shared Y of TMEM,
+    one issuer warp, key operand in shared memory) issues the same MMAs in the same accumulation order as
+    nsf_chain_tc_kernel: every result must be the same bits -- log_prob, bins, the inverse map, posteriors; stages with
+    1, 2, 3 and 4 spline dimensions, sub-stages, conditions, ragged and tiny row counts."""
+    def both(fn):
+        out = []
+        for v in ("0", "1"):
+            monkeypatch.setenv("PZB_TC_PIPE3", v)
+            r = fn()
+            torch.cuda.synchronize()
+            out.append([x.clone() for x in (r if isinstance(r, (tuple, list)) else [r])])
+        return out
+
+    def same(a, b):
+        return all(torch.equal(x.view(torch.int32), y.view(torch.int32)) for x, y in zip(a, b))
+
+    ex = F.example_flow()
+    plan = _plan(ex, "tc")
+    for n in (1, 129, 5000, 200001):
+        X = torch.from_numpy(F.galaxy_rows(n, seed=n)).cuda()
+        assert same(*both(lambda: plan.log_prob(X, return_bins=True))), n
+    X = torch.from_numpy(F.galaxy_rows(6000, seed=2)).cuda()
+    u = plan.forward(X)[0]
+    assert same(*both(lambda: plan.inverse(u)))
+    grid = torch.linspace(0, 2.3, 300).cuda()
+    assert same(*both(lambda: plan.posterior(X[:500, 1:].contiguous(), 0, grid)))
+    for D, C in ((2, 0), (5, 0), (10, 0), (3, 2)):          # 1, 3, 4 + 1 and 2 spline dimensions per (sub-)stage
+        cfg = F.default_flow(D, -np.ones(D), np.ones(D), n_conditions=C, seed=D)
+        p = _plan(cfg, "tc")
+        rng = np.random.default_rng(D)
+        Xd = torch.from_numpy(rng.uniform(-1.02, 1.02, size=(3333, D)).astype(np.float32)).cuda()
+        Cd = torch.from_numpy(rng.normal(size=(3333, C)).astype(np.float32)).cuda() if C else None
+        assert same(*both(lambda: p.log_prob(Xd, Cd, return_bins=True))), (D, C)
+        ud = p.forward(Xd, Cd)[0]
+        assert same(*both(lambda: p.inverse(ud, Cd))), (D, C)
+
+
+# --------------------------------------------------------------------------- #
 # the gradient of one optimisation step as one kernel (VERDICT r1 item 9)      #
 # --------------------------------------------------------------------------- #
 def _f64_loss_and_grad(cfg, X, cond, w):
