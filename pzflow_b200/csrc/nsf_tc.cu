@@ -20,9 +20,10 @@
 //       G2  X x W2 -> Y in four N = 32 quarters, one commit each, alternating between the halves,
 //           so E2 of a quarter runs while the tensor pipe computes the next ones
 //       E2  Y: * 2^-e2 + b2, LeakyReLU, split, in place
-//       G3  Y x W3 -> X[0,48) / X[64,112), one N = 48 pass per spline dimension into two accumulator
-//           buffers; passes 0/1 start on half 0's 64 K-elements and take half 1's when it arrives,
-//           passes 2/3 go into a buffer as soon as its half has drained it
+//       G3  Y x W3 -> X[0,96): one N = 96 pass per PAIR of spline dimensions (dims 2p, 2p + 1 land in X[0,48) /
+//           X[48,96); a tcgen05.mma costs the issuing warp ~5 clk on top of its pipe time, so fewer, wider
+//           instructions).  The first pass starts on half 0's 64 K-elements and takes half 1's when it arrives,
+//           the second goes out once both halves have the first in registers
 //       E3  48 logits of a (row, dim) in registers -> knots, bin search, RQS, log-det
 //     The half that finishes E3 first writes the NEXT tile's E0, so G1 runs under the last spline.
 //   * warps 16/17: MMA issuer of group 0/1.  The whole warp waits on the mbarriers, one elect.sync
@@ -48,6 +49,12 @@
 
 #ifndef PZB_TC_PIPE3_DEFAULT
 #define PZB_TC_PIPE3_DEFAULT 0   // which kernel runs when the environment does not say (PZB_TC_PIPE3)
+#endif
+#ifndef PZB_TC_PAIR_PASS
+#define PZB_TC_PAIR_PASS 1   // output layer in N = 96 passes of two spline dimensions (0: one N = 48 pass per dimension, the form up to round 2; +2 %, same bits: DESIGN.md section 4.5b)
+#endif
+#ifndef PZB_TC_G2_HALVES
+#define PZB_TC_G2_HALVES 0   // experiment: hidden GEMM in two N = 64 halves instead of four N = 32 quarters
 #endif
 #ifndef PZB_TC_STUB
 #define PZB_TC_STUB 0   // bit 0 / bit 1: measurement builds without the spline / the activation arithmetic
@@ -741,8 +748,13 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               tc_fence_after();
               TC_TRACE(d < 2 ? 4 : 6);
               float raw[48];
+#if PZB_TC_PAIR_PASS
+              tmem_ld32(t_x - 16u * (uint32_t)half, raw);          // pair passes: dims 2p, 2p + 1 land in X[0,48) / X[48,96)
+              tmem_ld16(t_x - 16u * (uint32_t)half + 32, raw + 32);
+#else
               tmem_ld32(t_x, raw);
               tmem_ld16(t_x + 32, raw + 32);
+#endif
               tc_wait_ld();
               tc_fence_before();
               warp_arrive(bar_free, lane);  // accumulator buffer drained: the next pass may overwrite it
@@ -880,6 +892,17 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           tc_fence_after();
           TC_TRACE_I(1);
           if (elect_one()) {
+#if PZB_TC_G2_HALVES
+            // experiment: two N = 64 halves (half the MMA instructions; E2 of a half starts when all its 64 columns are there)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int n0 = h * 64;
+              const uint32_t id64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+              issue_gemm<0, 8, true>(t_y + (uint32_t)n0, t_x, w2 + n0 * 128, w2 + TC_W2_BYTES / 2 + n0 * 128, 128 * 128, id64);
+              umma_commit(bar_d2 + 8u * (2 * h));
+              umma_commit(bar_d2 + 8u * (2 * h + 1));
+            }
+#else
             // four N = 32 quarters, alternating between the halves so both start their E2 early
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -887,6 +910,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
               issue_gemm<0, 8, true>(t_y + (uint32_t)n0, t_x, w2 + n0 * 128, w2 + TC_W2_BYTES / 2 + n0 * 128, 128 * 128, idesc2);
               umma_commit(bar_d2 + 8u * (2 * h + bt));
             }
+#endif
             if (k == my_tiles - 1) umma_commit(TC_BAR(w2_free));  // W2 is free once this group's last hidden GEMM is done
           }
           __syncwarp();
@@ -898,6 +922,49 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
           mbar_wait(bar_ready, ph_ready);
           tc_fence_after();
           TC_TRACE_I(3);
+#if PZB_TC_PAIR_PASS
+          // the output layer as (at most) two passes of TWO spline dimensions each, N = 96 -- half the MMA
+          // instructions of one pass per dimension (48 clk each instead of 24); dims 2p / 2p + 1 land in X[0,48) / X[48,96)
+          {
+            const int ndA = L < 2 ? L : 2, ndB = L - 2;
+            const uint32_t idA = (1u << 4) | ((uint32_t)((TC_DIM_N * ndA) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            if (np0 > 0u) mbar_wait(bar_free, (np0 - 1u) & 1u);
+            if (ndA == 2 && np1 > 0u) mbar_wait(bar_free + 8u, (np1 - 1u) & 1u);
+            tc_fence_after();
+            if (elect_one()) issue_gemm<0, 4, true>(t_x, t_y, w3, w3 + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idA);
+            __syncwarp();
+            mbar_wait(bar_ready + 8u, ph_ready);
+            ph_ready ^= 1u;
+            tc_fence_after();
+            if (elect_one()) {
+              issue_gemm<4, 8, false>(t_x, t_y, w3, w3 + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idA);
+              umma_commit(bar_d3);
+              if (ndA == 2) umma_commit(bar_d3 + 8u);
+              if (L <= 2) umma_commit(TC_BAR(g3_done[0]) + 8u * g);
+              if (L <= 2 && k == my_tiles - 1) umma_commit(TC_BAR(w3_free));
+            }
+            __syncwarp();
+            np0 += 1u;
+            np1 += ndA == 2 ? 1u : 0u;
+            if (ndB > 0) {
+              const uint32_t idB = (1u << 4) | ((uint32_t)((TC_DIM_N * ndB) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+              mbar_wait(bar_free, (np0 - 1u) & 1u);
+              mbar_wait(bar_free + 8u, (np1 - 1u) & 1u);   // (dim 1's columns [48,96) are overwritten by a two-dim pass; harmless to wait for when ndB == 1)
+              tc_fence_after();
+              const uint32_t tile = w3 + TC_W3_PASS_BYTES;
+              if (elect_one()) {
+                issue_gemm<0, 8, true>(t_x, t_y, tile, tile + TC_W3_PASS_BYTES / 2, TC_PASS_N * 128, idB);
+                umma_commit(bar_d3);
+                if (ndB == 2) umma_commit(bar_d3 + 8u);
+                umma_commit(TC_BAR(g3_done[0]) + 8u * g);
+                if (k == my_tiles - 1) umma_commit(TC_BAR(w3_free));
+              }
+              __syncwarp();
+              np0 += 1u;
+              np1 += ndB == 2 ? 1u : 0u;
+            }
+          }
+#else
           const int n_early = L < 2 ? L : 2;
           for (int d = 0; d < n_early; ++d) {
             const uint32_t np = d ? np1 : np0;
@@ -944,6 +1011,7 @@ nsf_chain_tc_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch 
             np0 += b ? 0u : 1u;
             np1 += b ? 1u : 0u;
           }
+#endif
         }
       }
     } else {
