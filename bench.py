@@ -422,6 +422,30 @@ def bench_c1(ctx):
             "note": "one launch of 100k rows is 782 row tiles over 148 SMs: launch- and tail-bound, not pipe-bound"}
 
 
+def bench_train_step(flow, X, ctx):
+    """one Flow.train optimisation step (gradient of -mean(log_prob) + Adam, pzflow/flow.py:961-982) of the
+    shipped flow on a batch of 1024 rows, as the fused kernel runs it (csrc/nsf_train_step.cu); N > 1: per-rank batches of
+    1024 with the NCCL all-reduce of the flat gradient inside the step."""
+    import torch
+    from pzflow_b200.plan import launch_count
+    from pzflow_b200.train import FusedGradient, NativeAdam, TorchChain, dp_step
+    rows = 1024
+    chain = TorchChain(flow._bijector_info, flow._params[1], flow._latent_info, flow._params[0], flow._input_dim, ctx["dev"])
+    chain.fused_gradient = FusedGradient.build(chain)
+    if chain.fused_gradient is None:
+        return {"unavailable": "chain outside the fused training kernel's shapes"}
+    opt = NativeAdam(chain, lr=1e-6)
+    xb = X[:rows].contiguous()
+    w = torch.ones(rows, device=ctx["dev"])
+    n0 = launch_count()
+    ms = timed_device(lambda: dp_step(chain, opt, xb, None, w, rows * ctx["world"]), 50, ctx["barrier"], ctx["max_ranks"], warm=5)
+    per_step = (launch_count() - n0) / 55.0
+    return {"workload": "Flow.train step (gradient + Adam) of the 7-D flow, batch 1024 per GPU (SURVEY f-4)",
+            "value": ms, "unit": "ms/step", "higher_is_better": False, "batch_per_gpu": rows,
+            "rows_per_s": rows * ctx["world"] / (ms * 1e-3), "launches_per_step": per_step,
+            "collective": "NCCL all_reduce(sum) of the flat gradient" if ctx["world"] > 1 else "none (one GPU)"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -530,6 +554,7 @@ def run_ours(args, rank, world, local_rank):
                strong=args.scaling != "weak", gen=gen)
     named = {}
     if not args.no_named_shapes:
+        named["train_step"] = bench_train_step(flow, X, ctx)
         named["c3_posterior"] = bench_c3(flow, plan, X, ctx)
         del X, out, X_host
         torch.cuda.empty_cache()
