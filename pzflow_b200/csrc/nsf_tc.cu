@@ -228,6 +228,7 @@ struct TcPipe3Bars {
   uint64_t e2_ready[2];     // [half] (4 warp arrivals): that half of h2 is written
   uint64_t key_ready;       // (4 warp arrivals): the key operand of the next tile is in shared memory
   uint64_t key_free;        // the first-layer GEMM that read it has completed (commit)
+  uint32_t e2_busy;         // warps inside E2 right now: work off the tensor pipe's critical path yields to them
 };
 struct TcShared {
   uint64_t e_ready[2][2];  // [group][half] -> the group's MMA issuer (4 warp arrivals): that half's 64 K-elements of the

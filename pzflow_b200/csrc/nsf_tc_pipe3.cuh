@@ -61,6 +61,10 @@ __device__ unsigned int g_tc3_trace_e[4 * 32 * 16];
   } while (0)
 #endif
 
+#ifndef PZB_TC3_YIELD
+#define PZB_TC3_YIELD 0   // nanoseconds phase-A work sleeps per poll while a warp is inside E2 (0: no yielding)
+#endif
+
 #define TC3_BAR(field) (sh_addr + (uint32_t)offsetof(TcShared, p3) + (uint32_t)offsetof(TcPipe3Bars, field))
 
 __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc) {
@@ -112,6 +116,7 @@ nsf_chain_tc3_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch
       mbar_init(TC_BAR(par_full[h]), 1);
       mbar_init(TC_BAR(par_free[h]), TC_EPI_THREADS / 32);
     }
+    sh->p3.e2_busy = 0u;
     mbar_init(TC3_BAR(key_ready), TC_TILE / 32);
     mbar_init(TC3_BAR(key_free), 1);
     mbar_init(TC_BAR(w1_full), 1);
@@ -206,6 +211,14 @@ nsf_chain_tc3_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch
       int pv_k = 0, pv_xr = 0, pv_L = 0, pv_seq = 0;
       const float* pv_par = nullptr;
 
+      // E2 sits on the tensor pipe's critical path (G2 -> E2 -> G3 of a tile are serial on the one Y), everything a group
+      // does in phase A does not: phase-A work sleeps while some warp is inside E2, leaving it the issue slots.
+      volatile uint32_t* e2_busy = &sh->p3.e2_busy;
+      auto yield_to_e2 = [&]() {
+#if PZB_TC3_YIELD
+        while (*e2_busy != 0u) __nanosleep(PZB_TC3_YIELD);
+#endif
+      };
       // pass `second` (0: dims 0 / 1, 1: dims 2 / 3) of tile k (region xr): wait for it, pull this half's 48 logits
       // (columns [48 half, 48 half + 48) of the region) into registers, hand them back, evaluate dimension d = half + 2 * second.
       // A stage without that dimension still completes the (empty) pass: the barriers' phases stay two per tile.
@@ -226,6 +239,7 @@ nsf_chain_tc3_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch
         tc_wait_ld();
         tc_fence_before();
         warp_arrive(TC3_BAR(d3_free[0]) + 8u * xr, lane);   // (with the other half's arrivals) the pass may be overwritten
+        if (second) yield_to_e2();
         const int col = pint[TC_PI_LOW + d];
         const float xin = srow[col * CR];
         float y, ldd;
@@ -342,6 +356,7 @@ nsf_chain_tc3_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch
             tc_fence_after();
 #pragma unroll 1
             for (int bt = 0; bt < 2; ++bt) {
+              yield_to_e2();
               float dv[32];
               tmem_ld32(t_x + bt * 32, dv);
               tc_wait_ld();
@@ -365,6 +380,9 @@ nsf_chain_tc3_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch
               const float s2inv = par[TC_PF_SCAL];
               mbar_wait(TC3_BAR(d2_full[0]) + 8u * half, gpar);   // this half (N = 64) of the hidden GEMM has landed
               tc_fence_after();
+#if PZB_TC3_YIELD
+              if (lane == 0) atomicAdd(const_cast<uint32_t*>(e2_busy), 1u);
+#endif
               TC3_TE(5);
 #pragma unroll 1
               for (int bt = 0; bt < 2; ++bt) {
@@ -393,6 +411,9 @@ nsf_chain_tc3_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch
             tc_wait_st();
             tc_fence_before();
             warp_arrive(TC3_BAR(e2_ready[0]) + 8u * half, lane);
+#if PZB_TC3_YIELD
+            if (lane == 0) atomicSub(const_cast<uint32_t*>(e2_busy), 1u);
+#endif
             TC3_TE(9);
 
             // ---- E3a: this half's first dimension (pass `half`); dims half + 2 wait for the next phase A ----
@@ -472,10 +493,10 @@ nsf_chain_tc3_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch
     const uint32_t w1 = sb + sl.w1, w2 = sb + sl.w2, w3 = sb + sl.w3, keys = sb + sl.keys;
 
     // first-layer GEMM of tile Gn (stage sn; first / last tile of that stage): keys (shared memory, K = 16) x W1 -> X
-    auto issue_g1 = [&](int Gn, int sn, bool first, bool last) {
+    auto issue_g1 = [&](int Gn, int sn, bool first, bool last, bool keys_seen) {
       const int xr = (int)(Gn % 3);
       if (first) mbar_wait(TC_BAR(w1_full), (uint32_t)(sn & 1));
-      mbar_wait(TC3_BAR(key_ready), (uint32_t)(Gn & 1));
+      if (!keys_seen) mbar_wait(TC3_BAR(key_ready), (uint32_t)(Gn & 1));
       if (Gn >= 3) mbar_wait(TC3_BAR(d3_free[0]) + 8u * xr, 1u);   // the second pass of the region's previous tile is in registers
       tc_fence_after();
       if (elect_one()) {
@@ -494,10 +515,10 @@ nsf_chain_tc3_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch
 
     if (total_seq > 0) {
       int s = 0, t = 0, nt = tiles_of(0);
-      issue_g1(0, 0, true, nt == 1);
+      int L = dims_of(0);   // (a read of the plan in global memory: once per stage, not per tile)
+      issue_g1(0, 0, true, nt == 1, false);
       for (int G = 0;; ++G) {
         const int xr = (int)(G % 3);
-        const int L = dims_of(s);
         const uint32_t t_x = tb + 128u * (uint32_t)xr;
         const uint32_t gpar = (uint32_t)(G & 1);
         const bool last_tile = t == nt - 1;
@@ -530,7 +551,7 @@ nsf_chain_tc3_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch
         auto try_g1 = [&]() {
           if (g1_issued) return;
           if (__shfl_sync(0xffffffffu, (int)mbar_test(TC3_BAR(key_ready), (uint32_t)((G + 1) & 1)), 0)) {
-            issue_g1(G + 1, s2, t2 == 0, t2 == nt2 - 1);
+            issue_g1(G + 1, s2, t2 == 0, t2 == nt2 - 1, true);
             g1_issued = true;
           }
         };
@@ -573,8 +594,9 @@ nsf_chain_tc3_kernel(const PlanDev* __restrict__ plan, LaunchArgs args, TcLaunch
         TC3_TI(10);
         TC3_TI(11);
         if (!has_next) break;
-        if (!g1_issued) issue_g1(G + 1, s2, t2 == 0, t2 == nt2 - 1);   // (blocking: its keys come after this tile's splines)
+        if (!g1_issued) issue_g1(G + 1, s2, t2 == 0, t2 == nt2 - 1, false);   // (blocking: its keys come after this tile's splines)
         TC3_TI(12);
+        if (s2 != s) L = dims_of(s2);
         s = s2;
         t = t2;
         nt = nt2;
