@@ -221,14 +221,15 @@ void tc_pack_stage(const PlanDev& hp, const NscDev& st, int sub, const float* co
 // barriers of nsf_chain_tc3_kernel (nsf_tc_pipe3.cuh)
 struct TcPipe3Bars {
   uint64_t d1_full[3];      // [region]: first-layer GEMM landed in X[region] (commit)
-  uint64_t e1_ready[3][2];  // [region][half] (4 warp arrivals): that half of h1 is written
-  uint64_t d3_full[3];      // [region]: an output pass (two spline dimensions, N = 96) landed (commit)
-  uint64_t d3_free[3];      // [region] (8 warp arrivals): both halves have their 48 logits of the pass in registers
+  uint64_t e1_ready[3];     // [region] (16 warp arrivals): h1 is written
+  uint64_t d3_full[3][2];   // [region][pass]: that output pass (two spline dimensions, N = 96) landed (commit)
+  uint64_t d3_free[3][2];   // [region][pass] (8 warp arrivals): the pass's two quarters have their 48 logits in registers
   uint64_t d2_full[2];      // [half]: that N = 64 half of the hidden GEMM landed in Y (commit)
-  uint64_t e2_ready[2];     // [half] (4 warp arrivals): that half of h2 is written
+  uint64_t e2_ready[2];     // [half] (8 warp arrivals): that half of h2 (two quarters) is written
   uint64_t key_ready;       // (4 warp arrivals): the key operand of the next tile is in shared memory
   uint64_t key_free;        // the first-layer GEMM that read it has completed (commit)
-  uint32_t e2_busy;         // warps inside E2 right now: work off the tensor pipe's critical path yields to them
+  uint16_t lt0[TC_SEQ_MAX + 1], lt1[TC_SEQ_MAX + 1];   // per (sub-)stage: the steps between the previous coupling stage and it
+  int8_t lvl_in[TC_SEQ_MAX + 1], lvl[TC_SEQ_MAX + 1];  // chain depth in front of those steps / at the stage
 };
 struct TcShared {
   uint64_t e_ready[2][2];  // [group][half] -> the group's MMA issuer (4 warp arrivals): that half's 64 K-elements of the
@@ -1087,10 +1088,10 @@ static void tc_base_launch(const PlanDev& hp, TcLaunch& lp) {
   lp.max_pass = 1;
   for (int s = 0; s < hp.n_nsc; ++s) lp.max_pass = max(lp.max_pass, (min(hp.nsc[s].L, TC_L_MAX) + 1) / 2);
   lp.n_lev = tc_log_det_levels(hp);
-  lp.state_cols = hp.D + lp.n_lev + 2 + hp.C;
+  lp.key_bytes = tc_pipe3_enabled() ? TC_W1_BYTES : 0;
+  lp.state_cols = hp.D + lp.n_lev + 2 + hp.C + (lp.key_bytes != 0 ? 2 : 0);   // (three-tile kernel: a log-det column per quarter)
   lp.unit_rows = lp.upc = lp.cpu = lp.spc = 0;
   lp.n_units = 0;
-  lp.key_bytes = tc_pipe3_enabled() ? TC_W1_BYTES : 0;
 }
 
 // Can the posterior of n_units galaxies (V variants x S error samples x G grid points each) be reduced inside the
@@ -1159,6 +1160,7 @@ cudaError_t launch_tc(const PlanDev* d_plan, const PlanDev& hp, const LaunchArgs
     const long long chunk_rows = (long long)lp.chunk_tiles * TC_TILE;
     n_work = (args.N + chunk_rows - 1) / chunk_rows;
   }
+  if (lp.key_bytes != 0 && lp.chunk_tiles < 4) lp.chunk_tiles = 4;   // nsf_chain_tc3_kernel walks at least four tiles per chunk
   const TcSmem sl = tc_smem_layout(lp.max_pass, lp.chunk_tiles, lp.state_cols, acc_floats, lp.key_bytes);
   const size_t smem = (size_t)sl.total + 1024;
   if (smem > (size_t)TC_SMEM_MAX) return cudaErrorInvalidConfiguration;
