@@ -1092,6 +1092,10 @@ static void tc_base_launch(const PlanDev& hp, TcLaunch& lp) {
   lp.state_cols = hp.D + lp.n_lev + 2 + hp.C + (lp.key_bytes != 0 ? 2 : 0);   // (three-tile kernel: a log-det column per quarter)
   lp.unit_rows = lp.upc = lp.cpu = lp.spc = 0;
   lp.n_units = 0;
+  if (lp.key_bytes != 0 && tc_fit_tiles(lp, 0) < 4) {   // the three-tile kernel walks at least four tiles per chunk: a flow
+    lp.key_bytes = 0;                                    // whose state is too wide for that takes the two-tile kernel
+    lp.state_cols -= 2;
+  }
 }
 
 // Can the posterior of n_units galaxies (V variants x S error samples x G grid points each) be reduced inside the
@@ -1104,7 +1108,9 @@ int tc_fuse_mode(const PlanDev& hp, int G, int V, int S, long long n_units, int 
   const long long RU = (long long)(V > 0 ? V : 1) * (S > 0 ? S : 1) * G;
   if (RU <= (long long)tc_fit_tiles(lp, 0) * TC_TILE) return 1;
   // long galaxies are dealt to the CTAs whole: few of them would leave most SMs idle
-  if ((long long)G <= (long long)tc_fit_tiles(lp, 2 * G) * TC_TILE && n_units >= 2ll * num_sms) return 2;
+  const int fit2 = tc_fit_tiles(lp, 2 * G);
+  if (lp.key_bytes != 0 && fit2 < 4) return 0;   // (the three-tile kernel needs four tiles of state beside the sums)
+  if ((long long)G <= (long long)fit2 * TC_TILE && n_units >= 2ll * num_sms) return 2;
   return 0;
 }
 

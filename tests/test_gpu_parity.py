@@ -1970,6 +1970,25 @@ def test_three_tile_kernel_equals_the_two_tile_kernel_bit_for_bit(monkeypatch):
         assert same(*both(lambda: p.log_prob(Xd, Cd, return_bins=True))), (D, C)
         ud = p.forward(Xd, Cd)[0]
         assert same(*both(lambda: p.inverse(ud, Cd))), (D, C)
+    # more than eight conditioner inputs (they ride above the bias row of the key operand, which the three-tile kernel
+    # keeps in shared memory)
+    # (10 columns + 4 conditions = 9 inputs; four tiles of its 21 state columns still fit beside the key buffer -- a flow
+    # with a wider state takes the two-tile kernel whatever PZB_TC_PIPE3 says)
+    cfg = F.default_flow(10, -np.ones(10), np.ones(10), n_conditions=4, seed=16)
+    p = _plan(cfg, "tc")
+    rng = np.random.default_rng(16)
+    Xd = torch.from_numpy(rng.uniform(-1.02, 1.02, size=(2000, 10)).astype(np.float32)).cuda()
+    Cd = torch.from_numpy(rng.normal(size=(2000, 4)).astype(np.float32)).cuda()
+    assert same(*both(lambda: p.log_prob(Xd, Cd, return_bins=True)))
+    # the reductions inside the kernel (error samples, marginal variants): the chunk geometry differs between the two
+    # kernels (the key buffer takes shared memory), the sums' order does not
+    rest = np.ascontiguousarray(F.galaxy_rows(300, seed=4, oob_frac=0.0)[:, 1:])
+    g120 = np.linspace(0.0, 2.3, 120).astype(np.float32)
+    a, b = both(lambda: plan.posterior_err(rest, np.full_like(rest, 0.02), 0, g120, err_samples=6, seed=1))
+    torch.testing.assert_close(a[0], b[0], rtol=2e-6, atol=1e-30)
+    Xe = F.galaxy_rows(4000, seed=5)
+    a, b = both(lambda: plan.log_prob_err(Xe, np.full_like(Xe, 0.01), err_samples=5, seed=2))
+    torch.testing.assert_close(a[0], b[0], rtol=2e-6, atol=1e-6)
 
 
 # --------------------------------------------------------------------------- #
